@@ -1,0 +1,928 @@
+// env_logic.cuh -- per-environment logic of the batched BabyAI pool: level
+// generation, the 7 MiniGrid actions, the instruction verifier and the
+// egocentric 7x7 observation.  One CUDA thread runs these for one environment;
+// the kernels in pool.cu add the warp-level parts (coalesced staging of the
+// observation bytes, ballot compaction of finished episodes).
+//
+// Everything here is BB_HD (__host__ __device__) so that tests/hostemu can
+// compile the *same* source for the host and single-step it in a debugger
+// against the oracle; the product only ever runs the device build.
+//
+// Representation (B200-first, not the reference's object graph):
+//   * a grid cell is ONE byte  type | color<<3 | state<<6  (exactly the three
+//     observation channels, so encoding a visible cell is bit-slicing);
+//   * object identity -- which the reference verifier relies on through `is`
+//     (verifier.py:120,266,340,408) -- lives in a 32-entry object table
+//     (position + type/colour) and 32-bit sets: obj_set(desc) is a bitmask,
+//     the `obj_poss` snapshot is the bitmask of objects that were on the grid
+//     at the last refresh (positions of on-grid objects only change at a
+//     successful drop, which is also a refresh, so no position copy is needed);
+//   * level generation never reads the grid: occupancy is kept as one 32-bit
+//     row mask per grid row (W <= 25), reachability is a bit-parallel flood
+//     fill on those rows, descriptors are matched against the object table,
+//     and the byte grid is rendered once at the end.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BB_HD __host__ __device__ __forceinline__
+#define BB_HD_NOINLINE __host__ __device__ __noinline__
+#define BB_ALIGN16 __align__(16)
+#else
+#define BB_ALIGN16 alignas(16)
+#define BB_HD inline
+#define BB_HD_NOINLINE
+#endif
+
+namespace bb {
+
+// ---- constants (gym_minigrid OBJECT_TO_IDX / COLOR_TO_IDX / STATE_TO_IDX) ----
+enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_DOOR = 4, T_KEY = 5, T_BALL = 6, T_BOX = 7 };
+enum : int { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5 };
+enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
+enum : int { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2 };
+enum : int { I_GOTO = 0, I_PICKUP = 1, I_OPEN = 2, I_PUTNEXT = 3, I_NONE = 0xFF };
+enum : int { K_ACTION = 0, K_AND = 1, K_SEQ = 2 };
+enum : int { R_SINGLE = 0, R_BEFORE = 1, R_AFTER = 2 };
+enum : int { LOC_LEFT = 0, LOC_RIGHT = 1, LOC_FRONT = 2, LOC_BEHIND = 3, LOC_NONE = 7 };
+enum : int { ANY = 7, ANY_TYPE = 0 };   // "None" for descriptor colour / type (7 is T_BOX)
+
+constexpr int CELL_EMPTY = T_EMPTY;                       // 0x01
+constexpr int CELL_WALL = T_WALL | (C_GREY << 3);         // 0x2A
+constexpr int NO_OBJ = 0xFF;
+constexpr int MAXOBJ = 32;
+constexpr int MAXH = 25;
+constexpr int MAXROOMS = 16;
+constexpr int MAXTOK = 72;
+constexpr int OBS_BYTES = 147;
+constexpr int OBS_WORDS = 37;
+
+// vocabulary of the baby language (verifier.py surface() strings); id 0 = pad.
+enum : int {
+    W_PAD = 0, W_GO, W_TO, W_PICK, W_UP, W_OPEN, W_PUT, W_NEXT, W_THE, W_A, W_OBJECT,
+    W_RED, W_GREEN, W_BLUE, W_PURPLE, W_YELLOW, W_GREY,       // W_RED + COLOR_TO_IDX
+    W_BOX, W_BALL, W_KEY, W_DOOR,
+    W_IN, W_FRONT, W_OF, W_YOU, W_BEHIND, W_ON, W_YOUR, W_LEFT, W_RIGHT,
+    W_THEN, W_AFTER, W_AND, W_COUNT
+};
+
+// ---- level parameters (kernel argument, lives in the constant bank) ---------
+struct LevelParams {
+    int32_t kind, room_size, num_rows, num_cols, num_dists, instr, doors_open, grey_dists;
+    int32_t locations, unblocking, implicit_unlock;
+    int32_t n_action_kinds, action_kinds[4];
+    int32_t n_instr_kinds, instr_kinds[3];
+    int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
+    uint64_t locked_thr;          // rand_float(0,1) < p  <=>  u32 < ceil(p * 2^32)
+    uint32_t wall_rows[MAXH];     // bit x of row y: (x, y) is a wall of the empty RoomGrid
+};
+
+// ---- per-environment records (struct-of-arrays over envs, one array each) ---
+struct BB_ALIGN16 EnvHot {
+    uint8_t x, y;
+    uint8_t dirflags;             // bits 0-1 agent_dir, bit 2 frozen (ManyEnvs flavour)
+    uint8_t carry;                // object id or NO_OBJ
+    uint16_t step_count, max_steps;
+    uint32_t cur_mask;            // objects currently on the grid
+    uint32_t snap_mask;           // objects on the grid at the last obj_poss refresh
+};
+struct BB_ALIGN16 ObjTab {
+    uint8_t x[MAXOBJ], y[MAXOBJ]; // last on-grid position (== WorldObj.cur_pos while not carried)
+    uint8_t tc[MAXOBJ];           // type | color << 3
+};
+struct BB_ALIGN16 InstrRec {
+    uint32_t desc_mask[8];        // obj_set of descriptor d; leaf i owns descs 2i (and 2i+1: PutNext fixed)
+    uint8_t leaf_kind[4];         // leaves 0,1 = side A; 2,3 = side B
+    uint8_t leaf_pre[4];          // preCarrying (verifier.py:325,373)
+    uint8_t root_kind;            // R_SINGLE / R_BEFORE / R_AFTER
+    uint8_t side_and;             // bit 0: side A is an AndInstr, bit 1: side B
+    uint8_t flags;                // 'success' latches: 0 root.a 1 root.b 2 A.a 3 A.b 4 B.a 5 B.b
+    uint8_t pad0;
+    uint32_t pad1;
+};
+struct BB_ALIGN16 RngRec { uint64_t seed, draws; };
+
+// ---- Philox4x32-10; stream layout documented in DESIGN.md --------------------
+BB_HD uint32_t mulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+struct Rng {
+    uint32_t k0, k1;
+    uint64_t draws;
+    uint64_t blk;                 // block currently held in b0..b3 (~0 = none)
+    uint32_t b0, b1, b2, b3;
+
+    BB_HD void init(uint64_t seed, uint64_t d)
+    {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); draws = d; blk = ~0ull;
+        b0 = b1 = b2 = b3 = 0;
+    }
+    BB_HD void refill(uint64_t n)
+    {
+        uint32_t c0 = (uint32_t)n, c1 = (uint32_t)(n >> 32), c2 = 0, c3 = 0, x0 = k0, x1 = k1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ x0, n2 = hi0 ^ c3 ^ x1;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
+        }
+        b0 = c0; b1 = c1; b2 = c2; b3 = c3; blk = n;
+    }
+    BB_HD uint32_t u32()
+    {
+        uint64_t i = draws++;
+        if ((i >> 2) != blk) refill(i >> 2);
+        uint32_t w = (uint32_t)i & 3u;
+        return w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
+    }
+    // MiniGridEnv._rand_int(lo, hi); a range of one value consumes no draw
+    BB_HD int randint(int lo, int hi)
+    {
+        uint32_t n = (uint32_t)(hi - lo);
+        if (n == 1) return lo;
+        return lo + (int)mulhi32(u32(), n);
+    }
+    BB_HD bool randbool() { return randint(0, 2) == 0; }
+};
+
+BB_HD int popc32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+BB_HD int ffs32(uint32_t v)   // index of lowest set bit, v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+BB_HD int iabs(int v) { return v < 0 ? -v : v; }
+
+// DIR_TO_VEC: right, down, left, up
+BB_HD int dir_dx(int d) { return d == 0 ? 1 : d == 2 ? -1 : 0; }
+BB_HD int dir_dy(int d) { return d == 1 ? 1 : d == 3 ? -1 : 0; }
+
+// COLOR_NAMES = sorted(['red','green','blue','purple','yellow','grey'])
+BB_HD int color_by_name_rank(int k)   // blue green grey purple red yellow
+{
+    return k == 0 ? C_BLUE : k == 1 ? C_GREEN : k == 2 ? C_GREY : k == 3 ? C_PURPLE : k == 4 ? C_RED : C_YELLOW;
+}
+
+// =============================================================================
+// Level generation (RoomGridLevel._gen_grid, levelgen.py:77-102, and below)
+// =============================================================================
+struct LevelOut {           // where one generated level is written (live or spare slot)
+    uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
+};
+
+struct GenCtx {
+    Rng rng;
+    uint32_t occ[MAXH];            // walls + doors + objects, one bit per cell
+    uint32_t doorcell[MAXH];       // door cells (subset of occ)
+    uint8_t door_y_right[MAXROOMS];   // Room.door_pos[0].y of room r
+    uint8_t door_x_down[MAXROOMS];    // Room.door_pos[1].x of room r
+    uint32_t door_right, door_down;   // bit r: a door exists in room r's right / down slot
+    uint32_t room_locked;             // bit r: Room.locked
+    int nobj;
+    int ax, ay, adir; bool agent_placed;
+    int locked_door;                  // object id of the locked door or -1
+    // instruction being built
+    int leaf_kind[4]; int desc_type[8], desc_color[8], desc_loc[8];
+    uint32_t desc_mask[8];
+    int root_kind, side_and;
+    // LevelGen.locked_room (persists across episodes, levelgen.py:284)
+    int locked_room; bool locked_room_fresh;
+};
+
+enum : int { GEN_OK = 0, GEN_REJECT = 1, GEN_RECURSION = 2 };
+#define BB_TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+// RoomGrid._gen_grid (gym_minigrid.roomgrid; SURVEY App. A.6 / App. B "G0")
+BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
+{
+    const int S = lp.room_size, R = lp.num_rows, C = lp.num_cols;
+    for (int y = 0; y < lp.H; y++) { g.occ[y] = lp.wall_rows[y]; g.doorcell[y] = 0; }
+    for (int j = 0; j < R; j++)
+        for (int i = 0; i < C; i++) {
+            int r = j * C + i, tx = i * (S - 1), ty = j * (S - 1);
+            if (i < C - 1) g.door_y_right[r] = (uint8_t)g.rng.randint(ty + 1, ty + S - 1);
+            if (j < R - 1) g.door_x_down[r] = (uint8_t)g.rng.randint(tx + 1, tx + S - 1);
+        }
+    g.door_right = g.door_down = g.room_locked = 0;
+    g.nobj = 0;
+    g.ax = (C / 2) * (S - 1) + S / 2;
+    g.ay = (R / 2) * (S - 1) + S / 2;
+    g.adir = 0; g.agent_placed = true;
+    g.locked_door = -1;
+    g.locked_room_fresh = false;
+}
+
+// MiniGridEnv.place_obj over one room rectangle (walls included), App. A.3
+BB_HD int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_to, int &ox, int &oy)
+{
+    const int S = lp.room_size;
+    const int tx = (room % lp.num_cols) * (S - 1), ty = (room / lp.num_cols) * (S - 1);
+    const int hx = tx + S < lp.W ? tx + S : lp.W, hy = ty + S < lp.H ? ty + S : lp.H;
+    int tries = 0;
+    for (;;) {
+        if (tries > 1000) return GEN_RECURSION;
+        tries++;
+        int x = g.rng.randint(tx, hx);
+        int y = g.rng.randint(ty, hy);
+        if ((g.occ[y] >> x) & 1u) continue;
+        if (g.agent_placed && x == g.ax && y == g.ay) continue;
+        if (reject_next_to && iabs(g.ax - x) + iabs(g.ay - y) < 2) continue;
+        ox = x; oy = y;
+        return GEN_OK;
+    }
+}
+
+// RoomGrid.add_object -> place_in_room
+BB_HD int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id)
+{
+    int x, y;
+    id = g.nobj++;                      // the Python object exists even if placement then fails
+    BB_TRY(g_place(lp, g, room, true, x, y));
+    o.obj->x[id] = (uint8_t)x; o.obj->y[id] = (uint8_t)y; o.obj->tc[id] = (uint8_t)(type | (color << 3));
+    g.occ[y] |= 1u << x;
+    return GEN_OK;
+}
+
+BB_HD bool g_has_slot(const LevelParams &lp, int room, int k)
+{
+    int i = room % lp.num_cols, j = room / lp.num_cols;
+    return k == 0 ? i < lp.num_cols - 1 : k == 1 ? j < lp.num_rows - 1 : k == 2 ? i > 0 : j > 0;
+}
+BB_HD int g_neighbor(const LevelParams &lp, int room, int k)
+{
+    return k == 0 ? room + 1 : k == 1 ? room + lp.num_cols : k == 2 ? room - 1 : room - lp.num_cols;
+}
+BB_HD bool g_has_door(const LevelParams &lp, const GenCtx &g, int room, int k)
+{
+    if (k == 0) return (g.door_right >> room) & 1u;
+    if (k == 1) return (g.door_down >> room) & 1u;
+    if (k == 2) return (g.door_right >> (room - 1)) & 1u;
+    return (g.door_down >> (room - lp.num_cols)) & 1u;
+}
+
+// RoomGrid.add_door(i, j, door_idx, color, locked) with everything decided
+BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int k, int color, bool locked)
+{
+    const int S = lp.room_size;
+    int owner = k == 2 ? room - 1 : k == 3 ? room - lp.num_cols : room;
+    int x, y;
+    if (k == 0 || k == 2) { x = (owner % lp.num_cols) * (S - 1) + S - 1; y = g.door_y_right[owner]; g.door_right |= 1u << owner; }
+    else { x = g.door_x_down[owner]; y = (owner / lp.num_cols) * (S - 1) + S - 1; g.door_down |= 1u << owner; }
+    if (locked) g.room_locked |= 1u << room; else g.room_locked &= ~(1u << room);   // room.locked = locked
+    int id = g.nobj++;
+    o.obj->x[id] = (uint8_t)x; o.obj->y[id] = (uint8_t)y; o.obj->tc[id] = (uint8_t)(T_DOOR | (color << 3));
+    g.doorcell[y] |= 1u << x;
+    if (locked) g.locked_door = id;
+    return id;
+}
+
+// RoomGrid.place_agent(i=None, j=None, rand_dir=True)
+BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g)
+{
+    int i = g.rng.randint(0, lp.num_cols);
+    int j = g.rng.randint(0, lp.num_rows);
+    int room = j * lp.num_cols + i;
+    for (;;) {
+        int x, y;
+        g.agent_placed = false;          // MiniGridEnv.place_agent: agent_pos = None while sampling
+        BB_TRY(g_place(lp, g, room, false, x, y));
+        g.ax = x; g.ay = y; g.agent_placed = true;
+        g.adir = g.rng.randint(0, 4);
+        int fx = x + dir_dx(g.adir), fy = y + dir_dy(g.adir);
+        // front cell must be empty or a wall (a door is neither)
+        bool occupied = (g.occ[fy] >> fx) & 1u;
+        bool wall = ((lp.wall_rows[fy] >> fx) & 1u) && !((g.doorcell[fy] >> fx) & 1u);
+        if (!occupied || wall) break;
+    }
+    return GEN_OK;
+}
+
+// RoomGrid.connect_all(door_colors=COLOR_NAMES, max_itrs=5000)
+BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+{
+    const int S = lp.room_size, C = lp.num_cols, NR = lp.num_rows * lp.num_cols;
+    const int start = (g.ay / (S - 1)) * C + g.ax / (S - 1);
+    const uint32_t all = NR >= 32 ? 0xFFFFFFFFu : ((1u << NR) - 1u);
+    int itrs = 0;
+    for (;;) {
+        if (itrs > 5000) return GEN_RECURSION;
+        itrs++;
+        uint32_t reach = 1u << start;
+        for (;;) {                        // find_reach as a fixpoint over room bitmasks
+            uint32_t nr = reach;
+            for (int r = 0; r < NR; r++) {
+                if (!((reach >> r) & 1u)) continue;
+                for (int k = 0; k < 4; k++)
+                    if (g_has_slot(lp, r, k) && g_has_door(lp, g, r, k)) nr |= 1u << g_neighbor(lp, r, k);
+            }
+            if (nr == reach) break;
+            reach = nr;
+        }
+        if (reach == all) break;
+        int i = g.rng.randint(0, C);
+        int j = g.rng.randint(0, lp.num_rows);
+        int k = g.rng.randint(0, 4);
+        int room = j * C + i;
+        if (!g_has_slot(lp, room, k) || g_has_door(lp, g, room, k)) continue;
+        if (((g.room_locked >> room) & 1u) || ((g.room_locked >> g_neighbor(lp, room, k)) & 1u)) continue;
+        int color = color_by_name_rank(g.rng.randint(0, 6));
+        g_add_door(lp, g, o, room, k, color, false);
+    }
+    return GEN_OK;
+}
+
+// RoomGrid.add_distractors(i=None, j=None, num, all_unique=False)
+BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o, int num, int &first_id)
+{
+    first_id = g.nobj;
+    for (int n = 0; n < num; n++) {
+        int color = color_by_name_rank(g.rng.randint(0, 6));
+        int t = g.rng.randint(0, 3);
+        int type = t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX;
+        int ri = g.rng.randint(0, lp.num_cols);
+        int rj = g.rng.randint(0, lp.num_rows);
+        int id;
+        BB_TRY(g_add_object(lp, g, o, rj * lp.num_cols + ri, type, color, id));
+    }
+    return GEN_OK;
+}
+
+// RoomGridLevel.check_objs_reachable (levelgen.py:201-253) as a bit-parallel
+// flood fill: F grows through cells that are empty or doors; a cell counts as
+// reachable if it is in F or 4-adjacent to F; every object and door must be.
+BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
+{
+    uint32_t pass[MAXH], f[MAXH];
+    const uint32_t full = (lp.W >= 32) ? 0xFFFFFFFFu : ((1u << lp.W) - 1u);
+    for (int y = 0; y < lp.H; y++) { pass[y] = (~g.occ[y] | g.doorcell[y]) & full; f[y] = 0; }
+    f[g.ay] = 1u << g.ax;
+    for (;;) {
+        bool changed = false;
+        for (int y = 0; y < lp.H; y++) {
+            uint32_t v = f[y];
+            uint32_t n = v | (v << 1) | (v >> 1);
+            if (y > 0) n |= f[y - 1];
+            if (y + 1 < lp.H) n |= f[y + 1];
+            n &= pass[y];
+            // run the horizontal spread to its fixpoint inside the row
+            for (;;) { uint32_t m = (n | (n << 1) | (n >> 1)) & pass[y]; if (m == n) break; n = m; }
+            if (n != v) { f[y] = n; changed = true; }
+        }
+        if (!changed) break;
+    }
+    for (int y = 0; y < lp.H; y++) {
+        uint32_t v = f[y];
+        uint32_t near = v | (v << 1) | (v >> 1);
+        if (y > 0) near |= f[y - 1];
+        if (y + 1 < lp.H) near |= f[y + 1];
+        uint32_t things = (g.occ[y] & ~lp.wall_rows[y]) | g.doorcell[y];   // non-wall, non-empty cells
+        if (things & ~near) return GEN_REJECT;
+    }
+    return GEN_OK;
+}
+
+// ObjDesc.find_matching_objs(env, use_location=True) over the object table
+// (verifier.py:96-161): every object is on the grid at generation time.
+BB_HD uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &o, int type, int color, int loc)
+{
+    const int S = lp.room_size;
+    const int rtx = (g.ax / (S - 1)) * (S - 1), rty = (g.ay / (S - 1)) * (S - 1);   // agent room top
+    const int d1x = dir_dx(g.adir), d1y = dir_dy(g.adir), d2x = -d1y, d2y = d1x;
+    uint32_t m = 0;
+    for (int k = 0; k < g.nobj; k++) {
+        int tc = o.obj->tc[k];
+        if (type != ANY_TYPE && (tc & 7) != type) continue;
+        if (color != ANY && (tc >> 3) != color) continue;
+        if (loc != LOC_NONE) {
+            int x = o.obj->x[k], y = o.obj->y[k];
+            if (x < rtx || y < rty || x >= rtx + S || y >= rty + S) continue;   // Room.pos_inside
+            int vx = x - g.ax, vy = y - g.ay;
+            int dot1 = vx * d1x + vy * d1y, dot2 = vx * d2x + vy * d2y;
+            bool ok = loc == LOC_LEFT ? dot2 < 0 : loc == LOC_RIGHT ? dot2 > 0 : loc == LOC_FRONT ? dot1 > 0 : dot1 < 0;
+            if (!ok) continue;
+        }
+        m |= 1u << k;
+    }
+    return m;
+}
+
+// LevelGen.rand_obj (levelgen.py:354-395); types: 4 = OBJ_TYPES, 3 = NOT_DOOR, 1 = ['door']
+BB_HD int g_rand_obj(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ntypes, int d)
+{
+    const int S = lp.room_size;
+    int tries = 0;
+    for (;;) {
+        if (tries > 100) return GEN_RECURSION;
+        tries++;
+        int ci = g.rng.randint(0, 7);                                  // [None, *COLOR_NAMES]
+        int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
+        int ti = g.rng.randint(0, ntypes);
+        int type = ntypes == 1 ? T_DOOR : (ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR);
+        int loc = LOC_NONE;
+        if (lp.locations && g.rng.randbool()) loc = g.rng.randint(0, 4);   // LOC_NAMES order
+        uint32_t m = g_match(lp, g, o, type, color, loc);
+        if (m == 0) continue;
+        if (!lp.implicit_unlock && g.locked_room >= 0) {
+            // at least one match outside the (possibly stale) locked room's rectangle
+            int ltx = (g.locked_room % lp.num_cols) * (S - 1), lty = (g.locked_room / lp.num_cols) * (S - 1);
+            bool outside = false;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                int k = ffs32(mm);
+                int x = o.obj->x[k], y = o.obj->y[k];
+                if (x < ltx || y < lty || x >= ltx + S || y >= lty + S) outside = true;
+            }
+            if (!outside) continue;
+        }
+        g.desc_type[d] = type; g.desc_color[d] = color; g.desc_loc[d] = loc; g.desc_mask[d] = m;
+        return GEN_OK;
+    }
+}
+
+// one ActionInstr of rand_instr (levelgen.py:409-424) into leaf slot `leaf`
+BB_HD int g_rand_action(const LevelParams &lp, GenCtx &g, const LevelOut &o, int leaf)
+{
+    int action = lp.action_kinds[g.rng.randint(0, lp.n_action_kinds)];
+    g.leaf_kind[leaf] = action;
+    if (action == I_GOTO) return g_rand_obj(lp, g, o, 4, 2 * leaf);
+    if (action == I_PICKUP) return g_rand_obj(lp, g, o, 3, 2 * leaf);
+    if (action == I_OPEN) return g_rand_obj(lp, g, o, 1, 2 * leaf);
+    BB_TRY(g_rand_obj(lp, g, o, 3, 2 * leaf));
+    return g_rand_obj(lp, g, o, 4, 2 * leaf + 1);
+}
+
+// rand_instr for one side of a sequence / the whole instruction: 'action' or 'and'
+BB_HD int g_rand_side(const LevelParams &lp, GenCtx &g, const LevelOut &o, int side, int kind)
+{
+    if (kind == K_ACTION) return g_rand_action(lp, g, o, 2 * side);
+    g.side_and |= 1 << side;
+    BB_TRY(g_rand_action(lp, g, o, 2 * side));
+    return g_rand_action(lp, g, o, 2 * side + 1);
+}
+
+// LevelGen.rand_instr (levelgen.py:397-460), canonicalised: side A [, side B]
+BB_HD int g_rand_instr(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+{
+    int kind = lp.instr_kinds[g.rng.randint(0, lp.n_instr_kinds)];
+    if (kind != K_SEQ) { g.root_kind = R_SINGLE; return g_rand_side(lp, g, o, 0, kind); }
+    int ka = g.rng.randint(0, 2);            // instr_kinds=['action','and']
+    BB_TRY(g_rand_side(lp, g, o, 0, ka));
+    int kb = g.rng.randint(0, 2);
+    BB_TRY(g_rand_side(lp, g, o, 1, kb));
+    g.root_kind = g.rng.randint(0, 2) == 0 ? R_BEFORE : R_AFTER;
+    return GEN_OK;
+}
+
+// RoomGridLevel.validate_instrs (levelgen.py:104-155)
+BB_HD int g_validate(const LevelParams &lp, const GenCtx &g, const LevelOut &o)
+{
+    const bool unblocking = lp.kind == KIND_LEVELGEN && lp.unblocking;
+    const int locked_color = g.locked_door >= 0 ? (o.obj->tc[g.locked_door] >> 3) : -1;
+    for (int leaf = 0; leaf < 4; leaf++) {
+        int kind = g.leaf_kind[leaf];
+        if (kind == I_NONE) continue;
+        if (kind == I_PUTNEXT) {
+            uint32_t mv = g.desc_mask[2 * leaf], fx = g.desc_mask[2 * leaf + 1];
+            if (mv & fx) return GEN_REJECT;
+            for (uint32_t a = mv; a; a &= a - 1) {           // objs_next(), verifier.py:379-391
+                int ia = ffs32(a);
+                for (uint32_t b = fx; b; b &= b - 1) {
+                    int ib = ffs32(b);
+                    if (iabs((int)o.obj->x[ia] - (int)o.obj->x[ib]) + iabs((int)o.obj->y[ia] - (int)o.obj->y[ib]) == 1)
+                        return GEN_REJECT;
+                }
+            }
+        }
+        if (unblocking && locked_color >= 0) {
+            int nd = kind == I_PUTNEXT ? 2 : 1;
+            for (int q = 0; q < nd; q++)
+                if (g.desc_type[2 * leaf + q] == T_KEY && g.desc_color[2 * leaf + q] == locked_color) return GEN_REJECT;
+        }
+    }
+    return GEN_OK;
+}
+
+// LevelGen.add_locked_room (levelgen.py:321-352)
+BB_HD int g_add_locked_room(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+{
+    int door;
+    for (;;) {
+        int i = g.rng.randint(0, lp.num_cols);
+        int j = g.rng.randint(0, lp.num_rows);
+        int k = g.rng.randint(0, 4);
+        g.locked_room = j * lp.num_cols + i; g.locked_room_fresh = true;
+        if (!g_has_slot(lp, g.locked_room, k)) continue;
+        int color = color_by_name_rank(g.rng.randint(0, 6));     // add_door(color=None) -> _rand_color()
+        door = g_add_door(lp, g, o, g.locked_room, k, color, true);
+        break;
+    }
+    for (;;) {
+        int i = g.rng.randint(0, lp.num_cols);
+        int j = g.rng.randint(0, lp.num_rows);
+        int room = j * lp.num_cols + i;
+        if (room == g.locked_room) continue;
+        int id;
+        BB_TRY(g_add_object(lp, g, o, room, T_KEY, o.obj->tc[door] >> 3, id));
+        break;
+    }
+    return GEN_OK;
+}
+
+BB_HD void g_single_desc(GenCtx &g, const LevelParams &lp, const LevelOut &o, int kind, int obj_id)
+{
+    int tc = o.obj->tc[obj_id];
+    g.root_kind = R_SINGLE; g.side_and = 0;
+    g.leaf_kind[0] = kind;
+    g.desc_type[0] = tc & 7; g.desc_color[0] = tc >> 3; g.desc_loc[0] = LOC_NONE;
+    g.desc_mask[0] = g_match(lp, g, o, tc & 7, tc >> 3, LOC_NONE);
+}
+
+// gen_mission of the three level families
+BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+{
+    for (int k = 0; k < 4; k++) g.leaf_kind[k] = I_NONE;
+    for (int k = 0; k < 8; k++) { g.desc_mask[k] = 0; g.desc_type[k] = ANY_TYPE; g.desc_color[k] = ANY; g.desc_loc[k] = LOC_NONE; }
+    g.side_and = 0; g.root_kind = R_SINGLE;
+    if (lp.kind == KIND_REDBALL) {                 // iclr19_levels.py:26-37, 55-63
+        int ball, first;
+        BB_TRY(g_place_agent(lp, g));
+        BB_TRY(g_add_object(lp, g, o, 0, T_BALL, C_RED, ball));
+        BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first));
+        if (lp.grey_dists)
+            for (int k = first; k < g.nobj; k++) o.obj->tc[k] = (uint8_t)((o.obj->tc[k] & 7) | (C_GREY << 3));
+        BB_TRY(g_check_reachable(lp, g));
+        g_single_desc(g, lp, o, I_GOTO, ball);
+        return GEN_OK;
+    }
+    if (lp.kind == KIND_OBJ) {                     // iclr19_levels.py:88-92, 119-124, 247-257, 365-371
+        int first;
+        BB_TRY(g_place_agent(lp, g));
+        BB_TRY(g_connect_all(lp, g, o));
+        BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first));
+        BB_TRY(g_check_reachable(lp, g));
+        int pick = first + g.rng.randint(0, lp.num_dists);
+        g_single_desc(g, lp, o, lp.instr, pick);
+        return GEN_OK;
+    }
+    // LevelGen.gen_mission, levelgen.py:293-319
+    if ((uint64_t)g.rng.u32() < lp.locked_thr) BB_TRY(g_add_locked_room(lp, g, o));
+    BB_TRY(g_connect_all(lp, g, o));
+    int first;
+    BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first));
+    for (;;) {
+        BB_TRY(g_place_agent(lp, g));
+        int start = (g.ay / (lp.room_size - 1)) * lp.num_cols + g.ax / (lp.room_size - 1);
+        if (g.locked_room_fresh && start == g.locked_room) continue;   // `start_room is self.locked_room`
+        break;
+    }
+    if (!lp.unblocking) BB_TRY(g_check_reachable(lp, g));
+    return g_rand_instr(lp, g, o);
+}
+
+// ---- mission tokens (Instr.surface / ObjDesc.surface, verifier.py:64-94 ...) --
+BB_HD int tok_desc(const GenCtx &g, int d, int16_t *tok, int n)
+{
+    tok[n++] = popc32(g.desc_mask[d]) > 1 ? W_A : W_THE;
+    if (g.desc_color[d] != ANY) tok[n++] = (int16_t)(W_RED + g.desc_color[d]);
+    int t = g.desc_type[d];
+    tok[n++] = (int16_t)(t == ANY_TYPE ? W_OBJECT : t == T_BOX ? W_BOX : t == T_BALL ? W_BALL : t == T_KEY ? W_KEY : W_DOOR);
+    int loc = g.desc_loc[d];
+    if (loc == LOC_FRONT) { tok[n++] = W_IN; tok[n++] = W_FRONT; tok[n++] = W_OF; tok[n++] = W_YOU; }
+    else if (loc == LOC_BEHIND) { tok[n++] = W_BEHIND; tok[n++] = W_YOU; }
+    else if (loc == LOC_LEFT) { tok[n++] = W_ON; tok[n++] = W_YOUR; tok[n++] = W_LEFT; }
+    else if (loc == LOC_RIGHT) { tok[n++] = W_ON; tok[n++] = W_YOUR; tok[n++] = W_RIGHT; }
+    return n;
+}
+BB_HD int tok_leaf(const GenCtx &g, int leaf, int16_t *tok, int n)
+{
+    int k = g.leaf_kind[leaf];
+    if (k == I_GOTO) { tok[n++] = W_GO; tok[n++] = W_TO; }
+    else if (k == I_PICKUP) { tok[n++] = W_PICK; tok[n++] = W_UP; }
+    else if (k == I_OPEN) { tok[n++] = W_OPEN; }
+    else { tok[n++] = W_PUT; }
+    n = tok_desc(g, 2 * leaf, tok, n);
+    if (k == I_PUTNEXT) { tok[n++] = W_NEXT; tok[n++] = W_TO; n = tok_desc(g, 2 * leaf + 1, tok, n); }
+    return n;
+}
+BB_HD int tok_side(const GenCtx &g, int side, int16_t *tok, int n)
+{
+    n = tok_leaf(g, 2 * side, tok, n);
+    if ((g.side_and >> side) & 1) { tok[n++] = W_AND; n = tok_leaf(g, 2 * side + 1, tok, n); }
+    return n;
+}
+
+// One whole RoomGridLevel.reset() worth of generation (levelgen.py:35-47,77-102):
+// retries until an attempt is accepted, then renders grid + records into `o`.
+// Returns the number of attempts.
+BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist)
+{
+    GenCtx g;
+    g.rng.init(rngrec->seed, rngrec->draws);
+    g.locked_room = *locked_room_persist == 0xFF ? -1 : (int)*locked_room_persist;
+    int attempts = 0;
+    for (;;) {
+        attempts++;
+        g_roomgrid(lp, g);
+        if (g_mission(lp, g, o)) continue;
+        if (g_validate(lp, g, o)) continue;
+        break;
+    }
+    rngrec->draws = g.rng.draws;
+    *locked_room_persist = g.locked_room < 0 ? 0xFF : (uint8_t)g.locked_room;
+
+    // ---- render the byte grid: walls, then doors/objects -----------------
+    for (int y = 0; y < lp.H; y++)
+        for (int x = 0; x < lp.W; x++)
+            o.grid[y * lp.W + x] = (uint8_t)(((lp.wall_rows[y] >> x) & 1u) ? CELL_WALL : CELL_EMPTY);
+    for (int k = 0; k < g.nobj; k++) {
+        int tc = o.obj->tc[k], st = 0;
+        if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (k == g.locked_door ? 2 : 1);   // open_all_doors levelgen.py:189-199
+        o.grid[o.obj->y[k] * lp.W + o.obj->x[k]] = (uint8_t)(tc | (st << 6));
+    }
+    // ---- verifier record (reset_verifier) + max_steps (levelgen.py:42-45) --
+    int navs = 0;
+    for (int k = 0; k < 4; k++) {
+        o.ins->leaf_kind[k] = (uint8_t)g.leaf_kind[k];
+        o.ins->leaf_pre[k] = NO_OBJ;
+        if (g.leaf_kind[k] != I_NONE) navs += g.leaf_kind[k] == I_PUTNEXT ? 2 : 1;
+    }
+    for (int k = 0; k < 8; k++) o.ins->desc_mask[k] = g.desc_mask[k];
+    o.ins->root_kind = (uint8_t)g.root_kind; o.ins->side_and = (uint8_t)g.side_and; o.ins->flags = 0;
+    o.ins->pad0 = 0; o.ins->pad1 = 0;
+    EnvHot h;
+    h.x = (uint8_t)g.ax; h.y = (uint8_t)g.ay; h.dirflags = (uint8_t)g.adir; h.carry = NO_OBJ;
+    h.step_count = 0; h.max_steps = (uint16_t)(navs * lp.nav_time_maze);
+    h.cur_mask = g.nobj >= 32 ? 0xFFFFFFFFu : ((1u << g.nobj) - 1u);
+    h.snap_mask = h.cur_mask;
+    *o.hot = h;
+    // ---- mission tokens ---------------------------------------------------
+    int16_t tok[MAXTOK];
+    int n = tok_side(g, 0, tok, 0);
+    if (g.root_kind == R_BEFORE) { tok[n++] = W_THEN; n = tok_side(g, 1, tok, n); }
+    else if (g.root_kind == R_AFTER) { tok[n++] = W_AFTER; tok[n++] = W_YOU; n = tok_side(g, 1, tok, n); }
+    for (int k = 0; k < lp.max_tokens; k++) o.tok[k] = k < n ? tok[k] : (int16_t)0;
+    return attempts;
+}
+
+// =============================================================================
+// step: MiniGridEnv.step (App. A.4) + RoomGridLevel.step (levelgen.py:49-66)
+// =============================================================================
+BB_HD int find_obj_at(const ObjTab *ot, uint32_t mask, int x, int y)
+{
+    for (uint32_t m = mask; m; m &= m - 1) {
+        int k = ffs32(m);
+        if (ot->x[k] == x && ot->y[k] == y) return k;
+    }
+    return NO_OBJ;
+}
+
+struct StepCtx {            // what a leaf verifier looks at after the action was applied
+    int action, fx, fy;     // front_pos AFTER the move
+    int carry;              // env.carrying after the action
+    uint32_t cur_mask, snap_mask;
+    const uint8_t *grid; const ObjTab *ot; int W;
+};
+
+// ActionInstr.verify_action: Open :257-274, GoTo :296-303, Pickup :330-350, PutNext :393-417
+BB_HD bool verify_leaf(InstrRec *ins, int leaf, const StepCtx &s)
+{
+    const int kind = ins->leaf_kind[leaf];
+    const uint32_t set = ins->desc_mask[2 * leaf];
+    if (kind == I_GOTO) {
+        for (uint32_t m = set & s.snap_mask; m; m &= m - 1) {
+            int k = ffs32(m);
+            if (s.ot->x[k] == s.fx && s.ot->y[k] == s.fy) return true;
+        }
+        return false;
+    }
+    if (kind == I_OPEN) {
+        if (s.action != A_TOGGLE) return false;
+        int c = s.grid[s.fy * s.W + s.fx];
+        if ((c & 7) != T_DOOR || (c >> 6) != 0) return false;            // must be a door and open
+        int id = find_obj_at(s.ot, s.cur_mask, s.fx, s.fy);
+        return id != NO_OBJ && ((set >> id) & 1u);
+    }
+    const int pre = ins->leaf_pre[leaf];
+    ins->leaf_pre[leaf] = (uint8_t)s.carry;
+    if (kind == I_PICKUP) {
+        if (s.action != A_PICKUP) return false;
+        return pre == NO_OBJ && s.carry != NO_OBJ && ((set >> s.carry) & 1u);
+    }
+    // PutNext
+    if (s.action != A_DROP) return false;
+    if (pre == NO_OBJ || !((set >> pre) & 1u)) return false;
+    if (s.carry == pre) return false;                   // still in hand: cur_pos == (-1,-1)
+    int ax = s.ot->x[pre], ay = s.ot->y[pre];
+    for (uint32_t m = ins->desc_mask[2 * leaf + 1] & s.snap_mask; m; m &= m - 1) {
+        int k = ffs32(m);
+        if (iabs(ax - (int)s.ot->x[k]) + iabs(ay - (int)s.ot->y[k]) == 1) return true;
+    }
+    return false;
+}
+
+// one side: an ActionInstr, or AndInstr.verify (verifier.py:536-550)
+BB_HD bool verify_side(InstrRec *ins, int side, const StepCtx &s)
+{
+    if (!((ins->side_and >> side) & 1)) return verify_leaf(ins, 2 * side, s);
+    const int ba = 2 + 2 * side, bb_ = 3 + 2 * side;
+    if (!((ins->flags >> ba) & 1) && verify_leaf(ins, 2 * side, s)) ins->flags |= (uint8_t)(1 << ba);
+    if (!((ins->flags >> bb_) & 1) && verify_leaf(ins, 2 * side + 1, s)) ins->flags |= (uint8_t)(1 << bb_);
+    return ((ins->flags >> ba) & 1) && ((ins->flags >> bb_) & 1);
+}
+
+// BeforeInstr.verify :449-471, AfterInstr.verify :490-512 (hand-over re-verifies the same action)
+BB_HD bool verify_root(InstrRec *ins, const StepCtx &s)
+{
+    const int rk = ins->root_kind;
+    if (rk == R_SINGLE) return verify_side(ins, 0, s);
+    const int first = rk == R_BEFORE ? 0 : 1, second = 1 - first;
+    if (!((ins->flags >> first) & 1)) {
+        if (!verify_side(ins, first, s)) return false;
+        ins->flags |= (uint8_t)(1 << first);
+    }
+    return verify_side(ins, second, s);
+}
+
+struct StepResult { bool done; bool success; float reward; };
+
+// Applies one action to the live state of one env.  `h` is the env's hot record
+// held in registers by the caller (written back by the caller).
+BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTab *ot, InstrRec *ins, int action)
+{
+    int x = h.x, y = h.y, dir = h.dirflags & 3, carry = h.carry;
+    const int fx = x + dir_dx(dir), fy = y + dir_dy(dir);
+    const int fidx = fy * lp.W + fx;
+    const int fc = grid[fidx];
+    const int ftype = fc & 7;
+    if (action == A_LEFT) dir = (dir + 3) & 3;
+    else if (action == A_RIGHT) dir = (dir + 1) & 3;
+    else if (action == A_FORWARD) {
+        if (fc == CELL_EMPTY || (ftype == T_DOOR && (fc >> 6) == 0)) { x = fx; y = fy; }
+    } else if (action == A_PICKUP) {
+        if (ftype >= T_KEY && carry == NO_OBJ) {
+            int id = find_obj_at(ot, h.cur_mask, fx, fy);
+            if (id != NO_OBJ) { carry = id; h.cur_mask &= ~(1u << id); grid[fidx] = (uint8_t)CELL_EMPTY; }
+        }
+    } else if (action == A_DROP) {
+        if (fc == CELL_EMPTY && carry != NO_OBJ) {
+            grid[fidx] = ot->tc[carry];
+            ot->x[carry] = (uint8_t)fx; ot->y[carry] = (uint8_t)fy;
+            h.cur_mask |= 1u << carry;
+            carry = NO_OBJ;
+        }
+    } else if (action == A_TOGGLE) {
+        if (ftype == T_DOOR) {
+            int st = fc >> 6, ns = st;
+            if (st == 2) {           // locked: needs a carried key of the door's colour; key stays in hand
+                if (carry != NO_OBJ && (ot->tc[carry] & 7) == T_KEY && (ot->tc[carry] >> 3) == ((fc >> 3) & 7)) ns = 0;
+            } else ns = st ^ 1;
+            grid[fidx] = (uint8_t)((fc & 0x3F) | (ns << 6));
+        } else if (ftype == T_BOX) {  // Box.toggle: replaced by its contents (None)
+            int id = find_obj_at(ot, h.cur_mask, fx, fy);
+            if (id != NO_OBJ) h.cur_mask &= ~(1u << id);
+            grid[fidx] = (uint8_t)CELL_EMPTY;
+        }
+    }
+    h.step_count = (uint16_t)(h.step_count + 1);
+    StepResult r;
+    r.done = h.step_count >= h.max_steps;
+    // RoomGridLevel.step: any drop action refreshes obj_poss (levelgen.py:53-54)
+    if (action == A_DROP) h.snap_mask = h.cur_mask;
+    h.x = (uint8_t)x; h.y = (uint8_t)y; h.dirflags = (uint8_t)((h.dirflags & ~3) | dir); h.carry = (uint8_t)carry;
+    StepCtx s;
+    s.action = action; s.fx = x + dir_dx(dir); s.fy = y + dir_dy(dir); s.carry = carry;
+    s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.grid = grid; s.ot = ot; s.W = lp.W;
+    r.success = verify_root(ins, s);
+    r.reward = 0.0f;
+    if (r.success) {
+        r.done = true;
+        // _reward(): 1 - 0.9 * (step_count / max_steps) in float64, no fused multiply-add
+        double q = (double)h.step_count / (double)h.max_steps;
+#if defined(__CUDA_ARCH__)
+        r.reward = (float)__dsub_rn(1.0, __dmul_rn(0.9, q));
+#else
+        volatile double p = 0.9 * q;
+        r.reward = (float)(1.0 - p);
+#endif
+    }
+    return r;
+}
+
+// =============================================================================
+// observation: gen_obs_grid + process_vis + encode (App. A.5)
+// =============================================================================
+// Visibility of the 7x7 view as 7-bit row masks (bit i = lateral column vi).
+// see[j] = see-through cells of view row j.  Equivalent to the reference's
+// nested process_vis loops (proved exhaustively in tests/test_vis_rows.py).
+BB_HD void vis_rows(const uint32_t see[7], uint32_t vis[7])
+{
+    uint32_t v = 1u << 3;                       // agent cell (3, 6)
+#pragma unroll
+    for (int j = 6; j >= 0; j--) {
+        const uint32_t s = see[j];
+        uint32_t a = v & s;                     // visible cells that let light through
+#pragma unroll
+        for (int it = 0; it < 6; it++) a |= ((a << 1) | (a >> 1)) & s;    // flood along the row
+        const uint32_t d = (a | (a << 1) | (a >> 1)) & 0x7Fu;
+        vis[j] = v | d;
+        v = d;                                  // what the row above starts from
+    }
+}
+
+// cell byte -> 24-bit (type, color, state) observation triple
+BB_HD uint32_t expand_cell(uint32_t c) { return (c & 7u) | ((c & 0x38u) << 5) | ((c & 0xC0u) << 10); }
+
+// Writes the 147 observation bytes as 37 little-endian words (last byte 0).
+BB_HD void observe(const LevelParams &lp, const uint8_t *grid, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+{
+    const int fx = dir_dx(dir), fy = dir_dy(dir), rx = -fy, ry = fx;
+    uint8_t cell[49];                            // [vi*7 + vj]
+    uint32_t see[7], vis[7];
+#pragma unroll
+    for (int vj = 0; vj < 7; vj++) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int vi = 0; vi < 7; vi++) {
+            const int wx = ax + fx * (6 - vj) + rx * (vi - 3);
+            const int wy = ay + fy * (6 - vj) + ry * (vi - 3);
+            const bool inb = wx >= 0 && wx < lp.W && wy >= 0 && wy < lp.H;
+            const uint32_t c = inb ? grid[wy * lp.W + wx] : (uint32_t)CELL_WALL;      // slice(): OOB -> Wall()
+            cell[vi * 7 + vj] = (uint8_t)c;
+            const uint32_t t = c & 7u;
+            const bool opaque = t == T_WALL || (t == T_DOOR && (c >> 6) != 0);
+            s |= (opaque ? 0u : 1u) << vi;
+        }
+        see[vj] = s;
+    }
+    vis_rows(see, vis);
+    cell[3 * 7 + 6] = (uint8_t)carry_cell;       // the agent's own cell shows what it carries (or empty)
+    uint32_t e[49];
+#pragma unroll
+    for (int vi = 0; vi < 7; vi++)
+#pragma unroll
+        for (int vj = 0; vj < 7; vj++)
+            e[vi * 7 + vj] = ((vis[vj] >> vi) & 1u) ? expand_cell(cell[vi * 7 + vj]) : 0u;
+    // pack 24-bit triples: 4 cells -> 3 words
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+        const uint32_t e0 = e[4 * q], e1 = e[4 * q + 1], e2 = e[4 * q + 2], e3 = e[4 * q + 3];
+        w[3 * q] = e0 | (e1 << 24);
+        w[3 * q + 1] = (e1 >> 8) | (e2 << 16);
+        w[3 * q + 2] = (e2 >> 16) | (e3 << 8);
+    }
+    w[36] = e[48];
+}
+
+BB_HD int carry_cell_of(const EnvHot &h, const ObjTab *ot) { return h.carry == NO_OBJ ? CELL_EMPTY : ot->tc[h.carry]; }
+
+// ---- staging of 32 observations of a warp as aligned words ----------------------
+// Lane l owns bytes [147 l, 147 l + 147) of the 4704-byte warp tile; 147 is not a
+// multiple of 4, so each lane funnel-shifts its 37 words by its own misalignment
+// and the word that straddles two lanes is completed with the next lane's first
+// word (obtained with a shuffle in the kernel).  Every tile word is written by
+// exactly one lane, as one aligned 32-bit store.
+BB_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, int s)     // (hi:lo << s) >> 32, s in 0..31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s == 0 ? hi : (hi << s) | (lo >> (32 - s));
+#endif
+}
+BB_HD void stage_obs_words(uint32_t *tile, const uint32_t w[OBS_WORDS], int lane, uint32_t next_w0)
+{
+    const int D = OBS_BYTES * lane;
+    const int sh = D & 3, wb = D >> 2;
+    const int kl = (sh + OBS_BYTES - 1) >> 2;                 // word holding this lane's last byte
+    const int nvalid = ((sh + OBS_BYTES - 1) & 3) + 1;        // this lane's bytes in that word
+    const int s8 = 8 * sh;
+#pragma unroll
+    for (int k = 0; k <= OBS_WORDS; k++) {
+        const uint32_t lo = k > 0 ? w[k - 1] : 0u;
+        const uint32_t hi = k < OBS_WORDS ? w[k] : 0u;
+        uint32_t v = funnel_l(lo, hi, s8);
+        if (k == 0 && sh != 0) continue;                      // first word belongs to the previous lane
+        if (k > kl) continue;
+        if (k == kl && nvalid < 4) v |= next_w0 << (8 * nvalid);
+        tile[wb + k] = v;
+    }
+}
+
+}  // namespace bb

@@ -1,0 +1,552 @@
+// pool.cu -- kernels and C ABI of the batched BabyAI environment pool (sm_100a).
+//
+//   k_step : one lane per environment.  Applies the action, runs the verifier,
+//            swaps in the pre-generated next level when the episode ended
+//            (ParallelEnv auto-reset, penv.py:7-11), computes the 7x7 egocentric
+//            observation, stages the 32 x 147 observation bytes of a warp in
+//            shared memory as aligned words and streams them out as 16-byte
+//            vectors; finished episodes are compacted with a warp ballot into
+//            the refill list.
+//   k_gen  : second kernel, one lane per list entry: generates the next level
+//            of an environment (RoomGridLevel._gen_grid + gen_mission +
+//            validate_instrs) from its Philox stream into the env's spare slot.
+//            Levels depend only on the env's random stream, never on actions,
+//            so generating episode k+1 while episode k is being played is
+//            equivalent to generating it at reset time.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include <vector>
+
+#include "../../include/babyai_b200.h"
+#include "env_logic.cuh"
+
+using namespace bb;
+
+// ---------------------------------------------------------------------------------
+struct PoolPtrs {
+    // live state of every environment
+    uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
+    // spare slot: the next episode's level, pre-generated
+    uint8_t *sgrid; EnvHot *shot; ObjTab *sobj; InstrRec *sins; int16_t *stok; uint8_t *sready;
+    RngRec *rng; uint8_t *locked_room; uint32_t *attempts;
+    float *last_reward;
+    int32_t *refill_list; int32_t *refill_count; uint32_t *gen_blocks_done;
+    unsigned long long *warp_counters;   // [num_warps][4]: steps, episodes, successes, errors
+};
+
+constexpr int STEP_THREADS = 128;
+constexpr int STEP_WARPS = STEP_THREADS / 32;
+constexpr int TILE_WORDS = 32 * OBS_BYTES / 4;     // 1176 words = 4704 B per warp
+constexpr int GEN_THREADS = 32;
+
+// warp-level staging of 32 observations: see stage_obs_words() in env_logic.cuh
+__device__ __forceinline__ void stage_obs(uint32_t *tile, const uint32_t w[OBS_WORDS], int lane)
+{
+    const uint32_t next_w0 = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
+    stage_obs_words(tile, w, lane, next_w0);
+}
+
+__device__ __forceinline__ void store_tile(const uint32_t *tile, uint8_t *dst, int lane, int valid_envs)
+{
+    if (valid_envs == 32 && (((uintptr_t)dst) & 15) == 0) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(tile);
+        uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+        for (int i = 0; i < (TILE_WORDS / 4 + 31) / 32; i++) {
+            const int idx = lane + 32 * i;
+            if (idx < TILE_WORDS / 4) d[idx] = s[idx];
+        }
+    } else {                                                  // ragged tail / unaligned destination
+        const uint8_t *s = reinterpret_cast<const uint8_t *>(tile);
+        const int nbytes = valid_envs * OBS_BYTES;
+        for (int i = lane; i < nbytes; i += 32) dst[i] = s[i];
+    }
+}
+
+// spare slot -> live state (the new episode begins)
+__device__ __forceinline__ void swap_in(const LevelParams &lp, const PoolPtrs &P, int env, EnvHot &h)
+{
+    const uint4 *sg = reinterpret_cast<const uint4 *>(P.sgrid + (size_t)env * lp.cells_pad);
+    uint4 *lg = reinterpret_cast<uint4 *>(P.grid + (size_t)env * lp.cells_pad);
+    for (int i = 0; i < lp.cells_pad / 16; i++) lg[i] = sg[i];
+    const uint4 *so = reinterpret_cast<const uint4 *>(P.sobj + env);
+    uint4 *lo = reinterpret_cast<uint4 *>(P.obj + env);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(ObjTab) / 16); i++) lo[i] = so[i];
+    const uint4 *si = reinterpret_cast<const uint4 *>(P.sins + env);
+    uint4 *li = reinterpret_cast<uint4 *>(P.ins + env);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(InstrRec) / 16); i++) li[i] = si[i];
+    const int16_t *st = P.stok + (size_t)env * lp.max_tokens;
+    int16_t *lt = P.tok + (size_t)env * lp.max_tokens;
+    for (int i = 0; i < lp.max_tokens; i++) lt[i] = st[i];
+    h = P.shot[env];
+    P.sready[env] = 0;
+}
+
+template <int ACT_BYTES>
+__global__ void __launch_bounds__(STEP_THREADS)
+k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
+       float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
+       const int mode, const int force_reset)
+{
+    __shared__ __align__(16) uint32_t tiles[STEP_WARPS][TILE_WORDS];
+    const int env = blockIdx.x * STEP_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool valid = env < n;
+    uint32_t w[OBS_WORDS];
+#pragma unroll
+    for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
+    bool need_refill = false, stepped = false, ended = false, succeeded = false, error = false;
+    if (valid) {
+        EnvHot h = P.hot[env];
+        uint8_t *grid = P.grid + (size_t)env * lp.cells_pad;
+        const bool frozen = (h.dirflags & 4) != 0;
+        bool begin = force_reset != 0;
+        float rew = 0.0f; bool dn = false;
+        if (!force_reset) {
+            if (!frozen) {
+                int a;
+                if (ACT_BYTES == 1) a = reinterpret_cast<const int8_t *>(actions)[env];
+                else a = (int)reinterpret_cast<const long long *>(actions)[env];
+                StepResult r = step_env(lp, h, grid, P.obj + env, P.ins + env, a);
+                rew = r.reward; dn = r.done;
+                stepped = true; ended = dn; succeeded = r.success;
+                if (dn) {
+                    if (mode == BB_MODE_AUTORESET) begin = true;
+                    else { h.dirflags |= 4; P.last_reward[env] = rew; }
+                }
+            } else {                                   // ManyEnvs: replay the last result (evaluate.py:72-78)
+                rew = P.last_reward[env]; dn = true;
+            }
+        }
+        if (begin) {
+            if (P.sready[env]) {
+                swap_in(lp, P, env, h);
+                need_refill = mode == BB_MODE_AUTORESET;
+            } else error = true;                       // cannot happen: the host refills before every step
+        }
+        P.hot[env] = h;
+        observe(lp, grid, h.x, h.y, h.dirflags & 3, carry_cell_of(h, P.obj + env), w);
+        if (reward) reward[env] = rew;
+        if (done) done[env] = dn ? 1 : 0;
+        if (dirs) dirs[env] = (int8_t)(h.dirflags & 3);
+    }
+    // ---- compaction of finished episodes into the refill list (warp ballot) ------
+    const uint32_t m_refill = __ballot_sync(0xFFFFFFFFu, need_refill);
+    if (m_refill) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(P.refill_count, __popc(m_refill));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (need_refill) P.refill_list[base + __popc(m_refill & ((1u << lane) - 1u))] = env;
+    }
+    // ---- counters: one slot per warp, no atomics ---------------------------------
+    const uint32_t m_step = __ballot_sync(0xFFFFFFFFu, stepped), m_end = __ballot_sync(0xFFFFFFFFu, ended);
+    const uint32_t m_succ = __ballot_sync(0xFFFFFFFFu, succeeded), m_err = __ballot_sync(0xFFFFFFFFu, error);
+    if (lane == 0) {
+        unsigned long long *c = P.warp_counters + 4ull * (blockIdx.x * STEP_WARPS + warp);
+        c[0] += __popc(m_step); c[1] += __popc(m_end); c[2] += __popc(m_succ); c[3] += __popc(m_err);
+    }
+    // ---- observation bytes: stage per warp, then coalesced 16-byte stores ---------
+    uint32_t *tile = tiles[warp];
+    stage_obs(tile, w, lane);
+    __syncwarp();
+    const int env0 = blockIdx.x * STEP_THREADS + warp * 32;
+    int nv = n - env0; nv = nv > 32 ? 32 : nv;
+    if (nv > 0) store_tile(tile, obs + (size_t)env0 * OBS_BYTES, lane, nv);
+}
+
+// Level generation.  list == nullptr: every env whose spare slot is empty.
+__global__ void __launch_bounds__(GEN_THREADS)
+k_gen(const LevelParams lp, const PoolPtrs P, const int use_list, const int n)
+{
+    const int tid = blockIdx.x * GEN_THREADS + threadIdx.x;
+    int env = -1;
+    if (use_list) { if (tid < *P.refill_count) env = P.refill_list[tid]; }
+    else if (tid < n && !P.sready[tid]) env = tid;
+    if (env >= 0) {
+        LevelOut o;
+        o.grid = P.sgrid + (size_t)env * lp.cells_pad; o.hot = P.shot + env; o.obj = P.sobj + env;
+        o.ins = P.sins + env; o.tok = P.stok + (size_t)env * lp.max_tokens;
+        RngRec r = P.rng[env];
+        uint8_t lr = P.locked_room[env];
+        int att = generate_level(lp, o, &r, &lr);
+        P.rng[env] = r; P.locked_room[env] = lr; P.attempts[env] += (uint32_t)att;
+        P.sready[env] = 1;
+    }
+    if (use_list) {                                   // last block out resets the list for the next step
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned int prev = atomicAdd(P.gen_blocks_done, 1u);
+            if (prev == gridDim.x - 1) { *P.refill_count = 0; *P.gen_blocks_done = 0; __threadfence(); }
+        }
+    }
+}
+
+__global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
+{
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    RngRec r; r.seed = seeds[env]; r.draws = 0;
+    P.rng[env] = r;
+    P.locked_room[env] = 0xFF;
+    P.sready[env] = 0;
+}
+
+// ====================================== host side ======================================
+static thread_local char g_err[512] = "";
+static int fail(const char *fmt, const char *a = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, a);
+    return 1;
+}
+#define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail("CUDA error: %s", cudaGetErrorString(_e)); } while (0)
+
+struct GraphKey { const void *a, *o, *r, *d, *q; int T; int mode; };
+
+struct bb_pool {
+    LevelParams lp;
+    PoolPtrs P;
+    int n, device, mode, num_warps, step_blocks, gen_blocks;
+    std::vector<void *> allocs;
+    cudaStream_t stream;           // internal stream: host-buffer API and graph capture
+    // host-buffer API staging
+    int8_t *h_act; uint8_t *h_obs; float *h_rew; uint8_t *h_done; int8_t *h_dir;      // pinned
+    int8_t *d_act; uint8_t *d_obs; float *d_rew; uint8_t *d_done; int8_t *d_dir;
+    uint64_t *d_seeds;
+    long long launches;
+    cudaGraphExec_t graph; GraphKey gkey;
+    cudaEvent_t ev[3];
+};
+
+template <typename T>
+static int dalloc(bb_pool *p, T **out, size_t count)
+{
+    void *ptr = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    CU(cudaMalloc(&ptr, bytes));
+    CU(cudaMemset(ptr, 0, bytes));
+    p->allocs.push_back(ptr);
+    *out = reinterpret_cast<T *>(ptr);
+    return 0;
+}
+
+static int make_params(const bb_level_spec *s, LevelParams *lp)
+{
+    memset(lp, 0, sizeof *lp);
+    if (s->kind < 0 || s->kind > 2) return fail("bad level kind");
+    if (s->room_size < 4 || s->room_size > 8) return fail("room_size must be in 4..8");
+    if (s->num_rows < 1 || s->num_cols < 1 || s->num_rows * s->num_cols > MAXROOMS) return fail("too many rooms");
+    lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
+    lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
+    lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
+    lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
+    for (int i = 0; i < 4; i++) lp->action_kinds[i] = s->action_kinds[i];
+    for (int i = 0; i < 3; i++) lp->instr_kinds[i] = s->instr_kinds[i];
+    lp->W = (s->room_size - 1) * s->num_cols + 1;
+    lp->H = (s->room_size - 1) * s->num_rows + 1;
+    if (lp->W > MAXH || lp->H > MAXH) return fail("grid too large");
+    lp->cells = lp->W * lp->H;
+    lp->cells_pad = (lp->cells + 15) / 16 * 16;
+    lp->nav_time_maze = s->room_size * s->room_size * s->num_rows * s->num_cols;   // levelgen.py:42-43
+    int max_objs = s->num_dists + 1;
+    if (s->kind == BB_KIND_LEVELGEN) {
+        if (s->n_action_kinds < 1 || s->n_action_kinds > 4 || s->n_instr_kinds < 1 || s->n_instr_kinds > 3)
+            return fail("bad LevelGen kinds");
+        double t = ceil(s->locked_room_prob * 4294967296.0);
+        lp->locked_thr = t <= 0 ? 0ull : (uint64_t)t;
+    }
+    // doors: one per internal wall at most
+    max_objs += s->num_rows * (s->num_cols - 1) + s->num_cols * (s->num_rows - 1);
+    if (max_objs > MAXOBJ) return fail("too many objects for the 32-entry object table");
+    // longest mission in tokens
+    int per_desc = 3 + (s->kind == BB_KIND_LEVELGEN && s->locations ? 4 : 0);
+    int leaf = 2 + per_desc;
+    if (s->kind == BB_KIND_LEVELGEN) {
+        bool putnext = false, has_and = false, has_seq = false;
+        for (int i = 0; i < s->n_action_kinds; i++) if (s->action_kinds[i] == BB_I_PUTNEXT) putnext = true;
+        for (int i = 0; i < s->n_instr_kinds; i++) { if (s->instr_kinds[i] == BB_K_AND) has_and = true; if (s->instr_kinds[i] == BB_K_SEQ) has_seq = true; }
+        if (putnext) leaf = 1 + per_desc + 2 + per_desc;
+        int side = (has_and || has_seq) ? 2 * leaf + 1 : leaf;
+        lp->max_tokens = has_seq ? 2 * side + 2 : side;
+    } else lp->max_tokens = leaf;
+    lp->max_tokens = (lp->max_tokens + 7) / 8 * 8;          // 16-byte rows
+    if (lp->max_tokens > MAXTOK) lp->max_tokens = MAXTOK;
+    // wall template of the empty RoomGrid (Grid.wall_rect per room)
+    for (int y = 0; y < lp->H; y++) {
+        uint32_t row = 0;
+        for (int x = 0; x < lp->W; x++)
+            if (x % (s->room_size - 1) == 0 || y % (s->room_size - 1) == 0) row |= 1u << x;
+        lp->wall_rows[y] = row;
+    }
+    return 0;
+}
+
+static void launch_gen(bb_pool *p, int use_list, cudaStream_t st)
+{
+    k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, use_list, p->n);
+    p->launches++;
+}
+
+static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8_t *obs, float *rew, uint8_t *done,
+                        int8_t *dirs, int force_reset, cudaStream_t st)
+{
+    if (action_bytes == 8)
+        k_step<8><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    else
+        k_step<1><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    p->launches++;
+}
+
+extern "C" {
+
+const char *bb_last_error(void) { return g_err; }
+
+int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb_pool **out)
+{
+    if (!spec || !out || n_envs < 1) return fail("bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device available (the pool has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("bad device index");
+    CU(cudaSetDevice(device));
+    bb_pool *p = new (std::nothrow) bb_pool();
+    if (!p) return fail("out of memory");
+    if (make_params(spec, &p->lp)) { delete p; return 1; }
+    p->n = n_envs; p->device = device; p->mode = BB_MODE_AUTORESET;
+    p->step_blocks = (n_envs + STEP_THREADS - 1) / STEP_THREADS;
+    p->num_warps = p->step_blocks * STEP_WARPS;
+    p->gen_blocks = (n_envs + GEN_THREADS - 1) / GEN_THREADS;
+    p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr;
+    const LevelParams &lp = p->lp;
+    const size_t n = (size_t)n_envs;
+    PoolPtrs &P = p->P;
+    if (dalloc(p, &P.grid, n * lp.cells_pad) || dalloc(p, &P.hot, n) || dalloc(p, &P.obj, n) || dalloc(p, &P.ins, n) ||
+        dalloc(p, &P.tok, n * lp.max_tokens) || dalloc(p, &P.sgrid, n * lp.cells_pad) || dalloc(p, &P.shot, n) ||
+        dalloc(p, &P.sobj, n) || dalloc(p, &P.sins, n) || dalloc(p, &P.stok, n * lp.max_tokens) || dalloc(p, &P.sready, n) ||
+        dalloc(p, &P.rng, n) || dalloc(p, &P.locked_room, n) || dalloc(p, &P.attempts, n) || dalloc(p, &P.last_reward, n) ||
+        dalloc(p, &P.refill_list, n) || dalloc(p, &P.refill_count, 4) || dalloc(p, &P.gen_blocks_done, 4) ||
+        dalloc(p, &P.warp_counters, (size_t)p->num_warps * 4) ||
+        dalloc(p, &p->d_act, n) || dalloc(p, &p->d_obs, n * OBS_BYTES) || dalloc(p, &p->d_rew, n) || dalloc(p, &p->d_done, n) ||
+        dalloc(p, &p->d_dir, n) || dalloc(p, &p->d_seeds, n)) {
+        bb_pool_destroy(p);
+        return 1;
+    }
+    CU(cudaMemset(P.locked_room, 0xFF, n));
+    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost((void **)&p->h_act, n));
+    CU(cudaMallocHost((void **)&p->h_obs, n * OBS_BYTES));
+    CU(cudaMallocHost((void **)&p->h_rew, n * sizeof(float)));
+    CU(cudaMallocHost((void **)&p->h_done, n));
+    CU(cudaMallocHost((void **)&p->h_dir, n));
+    // default seeds 0..n-1 so that an unseeded pool is still deterministic
+    std::vector<uint64_t> seeds(n);
+    for (size_t i = 0; i < n; i++) seeds[i] = i;
+    *out = p;
+    return bb_pool_seed(p, seeds.data());
+}
+
+int bb_pool_destroy(bb_pool *p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+    for (int i = 0; i < 3; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    for (void *a : p->allocs) cudaFree(a);
+    if (p->h_act) cudaFreeHost(p->h_act);
+    if (p->h_obs) cudaFreeHost(p->h_obs);
+    if (p->h_rew) cudaFreeHost(p->h_rew);
+    if (p->h_done) cudaFreeHost(p->h_done);
+    if (p->h_dir) cudaFreeHost(p->h_dir);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return 0;
+}
+
+int bb_pool_seed(bb_pool *p, const uint64_t *seeds_host)
+{
+    if (!p || !seeds_host) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(p->d_seeds, seeds_host, (size_t)p->n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    k_seed<<<(p->n + 255) / 256, 256, 0, p->stream>>>(p->P, p->d_seeds, p->n);
+    p->launches++;
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 0, p->stream);
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int bb_pool_set_mode(bb_pool *p, int32_t mode)
+{
+    if (!p || (mode != BB_MODE_AUTORESET && mode != BB_MODE_FREEZE)) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    p->mode = mode;
+    if (mode == BB_MODE_AUTORESET) { launch_gen(p, 0, p->stream); CU(cudaStreamSynchronize(p->stream)); }
+    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+    return 0;
+}
+
+int bb_pool_reset(bb_pool *p, uint8_t *obs_dev, int8_t *dir_dev, void *stream)
+{
+    if (!p || !obs_dev) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_gen(p, 0, st);                              // make sure every spare slot holds a level
+    launch_step(p, nullptr, 1, obs_dev, nullptr, nullptr, dir_dev, 1, st);
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, st);   // refill what the reset consumed
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int bb_pool_step(bb_pool *p, const void *actions_dev, int32_t action_bytes, uint8_t *obs_dev, float *reward_dev,
+                 uint8_t *done_dev, int8_t *dir_dev, void *stream)
+{
+    if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("bad arguments");
+    if (action_bytes != 1 && action_bytes != 8) return fail("action_bytes must be 1 or 8");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_step(p, actions_dev, action_bytes, obs_dev, reward_dev, done_dev, dir_dev, 0, st);
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, st);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int bb_pool_step_timed(bb_pool *p, const void *actions_dev, int32_t action_bytes, uint8_t *obs_dev, float *reward_dev,
+                       uint8_t *done_dev, int8_t *dir_dev, float *ms_step, float *ms_gen)
+{
+    if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || !ms_step || !ms_gen) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    if (!p->ev[0]) for (int i = 0; i < 3; i++) CU(cudaEventCreate(&p->ev[i]));
+    CU(cudaEventRecord(p->ev[0], p->stream));
+    launch_step(p, actions_dev, action_bytes, obs_dev, reward_dev, done_dev, dir_dev, 0, p->stream);
+    CU(cudaEventRecord(p->ev[1], p->stream));
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, p->stream);
+    CU(cudaEventRecord(p->ev[2], p->stream));
+    CU(cudaEventSynchronize(p->ev[2]));
+    CU(cudaEventElapsedTime(ms_step, p->ev[0], p->ev[1]));
+    CU(cudaEventElapsedTime(ms_gen, p->ev[1], p->ev[2]));
+    return 0;
+}
+
+int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *obs_dev, float *reward_dev,
+                    uint8_t *done_dev, int8_t *dir_dev, void *stream)
+{
+    if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || T < 1) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    GraphKey key = { actions_dev, obs_dev, reward_dev, done_dev, dir_dev, T, p->mode };
+    if (!p->graph || memcmp(&key, &p->gkey, sizeof key) != 0) {
+        if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+        cudaGraph_t g;
+        const size_t n = (size_t)p->n;
+        long long l0 = p->launches;
+        CU(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        for (int t = 0; t < T; t++) {
+            launch_step(p, actions_dev + t * n, 1, obs_dev + t * n * OBS_BYTES, reward_dev + t * n, done_dev + t * n,
+                        dir_dev ? dir_dev + t * n : nullptr, 0, p->stream);
+            if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, p->stream);
+        }
+        CU(cudaStreamEndCapture(p->stream, &g));
+        p->launches = l0;
+        CU(cudaGraphInstantiate(&p->graph, g, 0));
+        CU(cudaGraphDestroy(g));
+        p->gkey = key;
+    }
+    CU(cudaGraphLaunch(p->graph, (cudaStream_t)stream));
+    p->launches += (long long)T * (p->mode == BB_MODE_AUTORESET ? 2 : 1);
+    return 0;
+}
+
+int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host, float *reward_host,
+                      uint8_t *done_host, int8_t *dir_host)
+{
+    if (!p || !actions_host || !obs_host || !reward_host || !done_host) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    const size_t n = (size_t)p->n;
+    memcpy(p->h_act, actions_host, n);
+    CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, p->stream));
+    launch_step(p, p->d_act, 1, p->d_obs, p->d_rew, p->d_done, p->d_dir, 0, p->stream);
+    CU(cudaMemcpyAsync(p->h_obs, p->d_obs, n * OBS_BYTES, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_rew, p->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, p->stream);   // overlaps the copies' tail on the host side
+    CU(cudaStreamSynchronize(p->stream));
+    memcpy(obs_host, p->h_obs, n * OBS_BYTES);
+    memcpy(reward_host, p->h_rew, n * sizeof(float));
+    memcpy(done_host, p->h_done, n);
+    if (dir_host) memcpy(dir_host, p->h_dir, n);
+    return 0;
+}
+
+int bb_pool_reset_host(bb_pool *p, uint8_t *obs_host, int8_t *dir_host)
+{
+    if (!p || !obs_host) return fail("bad arguments");
+    const size_t n = (size_t)p->n;
+    if (bb_pool_reset(p, p->d_obs, p->d_dir, p->stream)) return 1;
+    CU(cudaMemcpyAsync(p->h_obs, p->d_obs, n * OBS_BYTES, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    memcpy(obs_host, p->h_obs, n * OBS_BYTES);
+    if (dir_host) memcpy(dir_host, p->h_dir, n);
+    return 0;
+}
+
+int bb_pool_mission_tokens(bb_pool *p, const int16_t **tokens_dev, int32_t *max_len)
+{
+    if (!p || !tokens_dev || !max_len) return fail("bad arguments");
+    *tokens_dev = p->P.tok; *max_len = p->lp.max_tokens;
+    return 0;
+}
+
+static const char *VOCAB[W_COUNT] = {
+    "", "go", "to", "pick", "up", "open", "put", "next", "the", "a", "object",
+    "red", "green", "blue", "purple", "yellow", "grey", "box", "ball", "key", "door",
+    "in", "front", "of", "you", "behind", "on", "your", "left", "right", "then", "after", "and" };
+
+int32_t bb_vocab_size(void) { return W_COUNT - 1; }
+const char *bb_vocab_word(int32_t id) { return (id >= 0 && id < W_COUNT) ? VOCAB[id] : ""; }
+
+int bb_pool_get_state(bb_pool *p, int32_t env, uint8_t *grid_host, int32_t *info)
+{
+    if (!p || env < 0 || env >= p->n || !grid_host || !info) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    EnvHot h; ObjTab ot; RngRec r; uint32_t att;
+    CU(cudaMemcpy(grid_host, p->P.grid + (size_t)env * p->lp.cells_pad, p->lp.cells, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&h, p->P.hot + env, sizeof h, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&ot, p->P.obj + env, sizeof ot, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&r, p->P.rng + env, sizeof r, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&att, p->P.attempts + env, sizeof att, cudaMemcpyDeviceToHost));
+    info[0] = h.x; info[1] = h.y; info[2] = h.dirflags & 3;
+    info[3] = h.carry == NO_OBJ ? 0 : ot.tc[h.carry];
+    info[4] = h.step_count; info[5] = h.max_steps;
+    info[6] = (int32_t)(r.draws & 0x7FFFFFFF); info[7] = (int32_t)att;
+    return 0;
+}
+
+int32_t bb_pool_width(const bb_pool *p) { return p ? p->lp.W : 0; }
+int32_t bb_pool_height(const bb_pool *p) { return p ? p->lp.H : 0; }
+int32_t bb_pool_num_envs(const bb_pool *p) { return p ? p->n : 0; }
+int64_t bb_pool_launches(const bb_pool *p) { return p ? p->launches : 0; }
+
+int bb_pool_counters(bb_pool *p, int64_t *out4)
+{
+    if (!p || !out4) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<unsigned long long> c((size_t)p->num_warps * 4);
+    CU(cudaMemcpy(c.data(), p->P.warp_counters, c.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; k++) out4[k] = 0;
+    for (int wi = 0; wi < p->num_warps; wi++) for (int k = 0; k < 4; k++) out4[k] += (int64_t)c[(size_t)wi * 4 + k];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's environment-facing interface, on top of
+the C ABI (include/babyai_b200.h):
+
+  BabyAIVecEnv      tensor API: everything stays in PyTorch-owned CUDA tensors
+  ParallelEnv       drop-in for babyai.rl.utils.penv.ParallelEnv (penv.py:18-59):
+                    reset() -> list of obs dicts, step(actions) -> zip(obs, reward,
+                    done, info) with auto-reset on done
+  ManyEnvs          drop-in for babyai.evaluate.ManyEnvs (evaluate.py:58-81):
+                    seed(seeds), reset(), step() that freezes finished envs
+  make_envs         what `[gym.make(id) ...; env.seed(100*seed+i)]` builds in
+                    scripts/train_rl.py:53-60, as one list-like handle
+  preprocess_obss   device-resident stand-in for ObssPreprocessor (utils/format.py:100-119)
+
+PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .levels import VOCAB, detokenize, level_spec
+
+MODE_AUTORESET, MODE_FREEZE = 0, 1
+
+
+class _DevArray(object):
+    """A device pointer owned by the pool, exposed through the CUDA array interface."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 2, 'strides': None}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class BabyAIVecEnv(object):
+    """N environments of one BabyAI level living in HBM of one GPU."""
+
+    def __init__(self, level, num_envs, seeds=None, device=0, mode=MODE_AUTORESET):
+        self.L = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('babyai_b200 needs a CUDA device; there is no CPU fallback')
+        self.level = level
+        self.num_envs = int(num_envs)
+        self.device = torch.device('cuda', device)
+        self.spec = level_spec(level)
+        h = C.c_void_p()
+        torch.cuda.set_device(self.device)
+        _lib.check(self.L.bb_pool_create(C.byref(self.spec), self.num_envs, device, C.byref(h)))
+        self.h = h
+        self.width = self.L.bb_pool_width(h)
+        self.height = self.L.bb_pool_height(h)
+        n = self.num_envs
+        self.obs = torch.zeros((n, 7, 7, 3), dtype=torch.uint8, device=self.device)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self.direction = torch.zeros(n, dtype=torch.int8, device=self.device)
+        tp, ml = C.c_void_p(), C.c_int32()
+        _lib.check(self.L.bb_pool_mission_tokens(h, C.byref(tp), C.byref(ml)))
+        self.max_tokens = ml.value
+        self.mission_tokens = torch.as_tensor(_DevArray(tp.value, (n, ml.value), '<i2'), device=self.device)
+        self.mode = MODE_AUTORESET
+        if mode != MODE_AUTORESET:
+            self.set_mode(mode)
+        if seeds is not None:
+            self.seed(seeds)
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            self.L.bb_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_mode(self, mode):
+        _lib.check(self.L.bb_pool_set_mode(self.h, mode))
+        self.mode = mode
+
+    def seed(self, seeds):
+        s = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        assert s.shape == (self.num_envs,)
+        _lib.check(self.L.bb_pool_seed(self.h, s.ctypes.data_as(C.c_void_p)))
+
+    def reset(self, obs=None, direction=None):
+        obs = self.obs if obs is None else obs
+        direction = self.direction if direction is None else direction
+        _lib.check(self.L.bb_pool_reset(self.h, _ptr(obs), _ptr(direction), self._stream()))
+        return obs
+
+    def step(self, actions, obs=None, reward=None, done=None, direction=None):
+        """actions: CUDA tensor of N int8/uint8 or int64 values."""
+        assert actions.is_cuda and actions.is_contiguous() and actions.numel() == self.num_envs
+        nbytes = actions.element_size()
+        obs = self.obs if obs is None else obs
+        reward = self.reward if reward is None else reward
+        done = self.done if done is None else done
+        direction = self.direction if direction is None else direction
+        _lib.check(self.L.bb_pool_step(self.h, _ptr(actions), nbytes, _ptr(obs), _ptr(reward), _ptr(done),
+                                       _ptr(direction), self._stream()))
+        return obs, reward, done
+
+    def step_timed(self, actions):
+        """bb_pool_step with CUDA events around each kernel -> (ms k_step, ms k_gen)."""
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self.L.bb_pool_step_timed(self.h, _ptr(actions), actions.element_size(), _ptr(self.obs),
+                                             _ptr(self.reward), _ptr(self.done), _ptr(self.direction),
+                                             C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def rollout(self, actions, obs, reward, done, direction=None):
+        """actions int8 [T, N] (CUDA); outputs [T, N, ...] CUDA tensors written in place."""
+        T = actions.shape[0]
+        assert actions.dtype in (torch.int8, torch.uint8) and actions.is_contiguous()
+        _lib.check(self.L.bb_pool_rollout(self.h, _ptr(actions), T, _ptr(obs), _ptr(reward), _ptr(done),
+                                          _ptr(direction), self._stream()))
+        return obs, reward, done
+
+    # ---- host-buffer path (what the reference's callers see) -----------------
+    def step_host(self, actions, obs, reward, done, direction):
+        a = np.ascontiguousarray(actions, dtype=np.int8)
+        _lib.check(self.L.bb_pool_step_host(self.h, a.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p),
+                                            reward.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p),
+                                            direction.ctypes.data_as(C.c_void_p)))
+
+    def reset_host(self, obs, direction):
+        _lib.check(self.L.bb_pool_reset_host(self.h, obs.ctypes.data_as(C.c_void_p),
+                                             direction.ctypes.data_as(C.c_void_p)))
+
+    # ---- introspection ----------------------------------------------------------
+    def missions(self, idx=None):
+        tok = self.mission_tokens.cpu().numpy()
+        idx = range(self.num_envs) if idx is None else idx
+        return [detokenize(tok[i]) for i in idx]
+
+    def state(self, i):
+        grid = np.zeros((self.height, self.width), np.uint8)
+        info = np.zeros(8, np.int32)
+        _lib.check(self.L.bb_pool_get_state(self.h, i, grid.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p)))
+        return grid, dict(agent_x=int(info[0]), agent_y=int(info[1]), agent_dir=int(info[2]), carrying=int(info[3]),
+                          step_count=int(info[4]), max_steps=int(info[5]), draws=int(info[6]), attempts=int(info[7]))
+
+    def counters(self):
+        c = np.zeros(4, np.int64)
+        _lib.check(self.L.bb_pool_counters(self.h, c.ctypes.data_as(C.c_void_p)))
+        return dict(steps=int(c[0]), episodes=int(c[1]), successes=int(c[2]), errors=int(c[3]))
+
+    def launches(self):
+        return int(self.L.bb_pool_launches(self.h))
+
+
+# ---------------------------------------------------------------------------------
+# gym-flavoured facades
+# ---------------------------------------------------------------------------------
+class _Space(object):
+    pass
+
+
+def _spaces():
+    """observation_space / action_space with the attributes the reference reads
+    (utils/format.py:124-126: .spaces['image'].shape/.high; train_rl.py:96: action_space.n)."""
+    img = _Space()
+    img.shape = (7, 7, 3)
+    img.low = np.zeros((7, 7, 3), np.uint8)
+    img.high = np.full((7, 7, 3), 255, np.uint8)
+    img.dtype = np.dtype('uint8')
+    obs = _Space()
+    obs.spaces = {'image': img}
+    act = _Space()
+    act.n = 7
+    return obs, act
+
+
+class EnvHandle(object):
+    """Stands for env i of a pool where the reference expects a list of gym envs."""
+
+    def __init__(self, pool_spec, index):
+        self.pool_spec = pool_spec
+        self.index = index
+        self.observation_space, self.action_space = _spaces()
+
+
+class EnvList(list):
+    """What scripts/train_rl.py:53-60 builds: N seeded envs of one level."""
+
+    def __init__(self, level, seeds, device=0):
+        self.level, self.seeds, self.device = level, list(seeds), device
+        super().__init__(EnvHandle(self, i) for i in range(len(self.seeds)))
+
+
+def make_envs(level, num_envs, seed=1, device=0):
+    """`env.seed(100 * seed + i)` for env i (scripts/train_rl.py:59)."""
+    return EnvList(level, [100 * seed + i for i in range(num_envs)], device)
+
+
+class _HostVec(object):
+    def __init__(self, envs, mode):
+        assert isinstance(envs, EnvList), 'build the env list with babyai_b200.make_envs()'
+        self.envs = envs
+        self.observation_space, self.action_space = _spaces()
+        self.pool = BabyAIVecEnv(envs.level, len(envs), seeds=envs.seeds, device=envs.device, mode=mode)
+        n = len(envs)
+        self._obs = np.zeros((n, 7, 7, 3), np.uint8)
+        self._rew = np.zeros(n, np.float32)
+        self._done = np.zeros(n, np.uint8)
+        self._dir = np.zeros(n, np.int8)
+        self._missions = [''] * n
+
+    def _obs_list(self, refresh):
+        if refresh is None:
+            self._missions = self.pool.missions()
+        else:
+            idx = np.nonzero(refresh)[0]
+            if len(idx):
+                for i, m in zip(idx, self.pool.missions(idx)):
+                    self._missions[i] = m
+        img = self._obs.copy()
+        return [{'image': img[i], 'direction': int(self._dir[i]), 'mission': self._missions[i]}
+                for i in range(len(self.envs))]
+
+    def render(self):
+        raise NotImplementedError
+
+
+class ParallelEnv(_HostVec):
+    """babyai.rl.utils.penv.ParallelEnv surface (auto-reset on done)."""
+
+    def __init__(self, envs):
+        super().__init__(envs, MODE_AUTORESET)
+
+    def reset(self):
+        self.pool.reset_host(self._obs, self._dir)
+        return self._obs_list(None)
+
+    def step(self, actions):
+        if torch.is_tensor(actions):
+            actions = actions.cpu().numpy()
+        self.pool.step_host(np.asarray(actions).astype(np.int8), self._obs, self._rew, self._done, self._dir)
+        obs = self._obs_list(self._done)
+        return zip(obs, [float(r) for r in self._rew], [bool(d) for d in self._done], [{} for _ in self.envs])
+
+
+class ManyEnvs(_HostVec):
+    """babyai.evaluate.ManyEnvs surface (seed / reset / step; finished envs freeze)."""
+
+    def __init__(self, envs):
+        super().__init__(envs, MODE_FREEZE)
+
+    def seed(self, seeds):
+        self.pool.seed(list(seeds))
+
+    def reset(self):
+        self.pool.reset_host(self._obs, self._dir)
+        return self._obs_list(None)
+
+    def step(self, actions):
+        if torch.is_tensor(actions):
+            actions = actions.cpu().numpy()
+        self.pool.step_host(np.asarray(actions).astype(np.int8), self._obs, self._rew, self._done, self._dir)
+        obs = self._obs_list(np.zeros(len(self.envs), bool))
+        return zip(obs, [float(r) for r in self._rew], [bool(d) for d in self._done], [{} for _ in self.envs])
+
+
+def preprocess_obss(pool):
+    """Returns a `preprocess_obss(obss, device=None)` callable for BaseAlgo
+    (rl/algos/base.py:13-14,65,134) that ignores the host obs list and hands the
+    model the pool's device tensors: image float[B,7,7,3], instr long[B,L]."""
+    from types import SimpleNamespace
+
+    def fn(obss=None, device=None):
+        return SimpleNamespace(image=pool.obs.float(), instr=pool.mission_tokens.long())
+    fn.vocab = {w: i for i, w in enumerate(VOCAB) if i > 0}
+    return fn

@@ -1,0 +1,144 @@
+/*
+ * babyai_b200.h -- C ABI of the B200-native batched BabyAI environment pool.
+ *
+ * The reference (mila-iqia/babyai) has no FFI: its "plugin interface" for the
+ * environment path is the duck-typed Python surface that babyai/rl and
+ * babyai/imitation.py consume.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference tree).  The Python
+ * host side (babyai_b200/vecenv.py) mirrors that surface on top of this ABI;
+ * INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  `*_dev`
+ * pointers are CUDA device pointers on the pool's device (typically the
+ * data_ptr() of PyTorch-owned tensors); `*_host` pointers are host memory.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Every function returns 0 on success, non-zero on error; bb_last_error()
+ * returns a thread-local message.  A pool is used by one host thread at a
+ * time, one outstanding step at a time (penv.py has the same contract).
+ */
+#ifndef BABYAI_B200_H
+#define BABYAI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_OBS_BYTES 147          /* uint8[7][7][3], index (vi*7+vj)*3+c   */
+#define BB_MAX_OBJ 32             /* describable objects per env (doors incl.) */
+#define BB_MAX_TOKENS 72          /* longest BossLevel mission, in words    */
+
+/* level families (which gen_mission the generator kernel runs) */
+#define BB_KIND_REDBALL 0         /* iclr19_levels.py:10-72   GoToRedBall*          */
+#define BB_KIND_OBJ 1             /* iclr19_levels.py:75-301,360-371 GoToObj/GoToLocal/GoTo/Pickup */
+#define BB_KIND_LEVELGEN 2        /* levelgen.py:256-460 LevelGen (PickupLoc .. BossLevel) */
+/* instruction / action kinds (verifier.py) */
+#define BB_I_GOTO 0
+#define BB_I_PICKUP 1
+#define BB_I_OPEN 2
+#define BB_I_PUTNEXT 3
+/* rand_instr kinds (levelgen.py:407) */
+#define BB_K_ACTION 0
+#define BB_K_AND 1
+#define BB_K_SEQ 2
+
+/* Constructor arguments of the reference level classes
+ * (RoomGridLevel.__init__ levelgen.py:25-33, LevelGen.__init__ :262-291,
+ *  Level_* in iclr19_levels.py). */
+typedef struct bb_level_spec {
+    int32_t kind;
+    int32_t room_size, num_rows, num_cols, num_dists;
+    int32_t instr;              /* BB_KIND_OBJ: BB_I_GOTO or BB_I_PICKUP      */
+    int32_t doors_open;         /* Level_GoTo(doors_open=...)                 */
+    int32_t grey_dists;         /* Level_GoToRedBallGrey                      */
+    double  locked_room_prob;   /* LevelGen(...) from here on                 */
+    int32_t locations, unblocking, implicit_unlock;
+    int32_t n_action_kinds; int32_t action_kinds[4];
+    int32_t n_instr_kinds;  int32_t instr_kinds[3];
+} bb_level_spec;
+
+typedef struct bb_pool bb_pool;
+
+/* step-mode: what happens to an environment whose episode ended */
+#define BB_MODE_AUTORESET 0       /* babyai/rl/utils/penv.py:7-11,48-50 (ParallelEnv) */
+#define BB_MODE_FREEZE 1          /* babyai/evaluate.py:72-78 (ManyEnvs)              */
+
+/* Replaces: `envs = [gym.make(id) for _ in range(N)]` + `ParallelEnv(envs)` /
+ * `ManyEnvs(envs)` construction (scripts/train_rl.py:53-60, rl/algos/base.py:54,
+ * evaluate.py:86-94).  Allocates the struct-of-arrays state of n_envs
+ * environments in device memory of CUDA device `device`. */
+int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb_pool **out);
+int bb_pool_destroy(bb_pool *pool);
+
+/* Replaces: env.seed(seed) per env (scripts/train_rl.py:59; ManyEnvs.seed
+ * evaluate.py:64-65).  seeds_host[n_envs]; restarts each env's random stream. */
+int bb_pool_seed(bb_pool *pool, const uint64_t *seeds_host);
+
+int bb_pool_set_mode(bb_pool *pool, int32_t mode);
+
+/* Replaces: ParallelEnv.reset (penv.py:39-43) / ManyEnvs.reset (evaluate.py:67-70)
+ * -> RoomGridLevel.reset (levelgen.py:35-47).  Generates a new level for every
+ * env and writes the first observation.  obs_dev: uint8[n_envs][147];
+ * dir_dev: int8[n_envs] or NULL. */
+int bb_pool_reset(bb_pool *pool, uint8_t *obs_dev, int8_t *dir_dev, void *stream);
+
+/* Replaces: ParallelEnv.step (penv.py:45-52) / ManyEnvs.step (evaluate.py:72-78)
+ * -> RoomGridLevel.step (levelgen.py:49-66) -> MiniGridEnv.step/gen_obs.
+ * actions_dev: n_envs actions, action_bytes = 1 (int8/uint8) or 8 (int64, what
+ * torch's dist.sample() yields, rl/algos/base.py:142).  Outputs: obs uint8
+ * [n_envs][147]; reward float32[n_envs]; done uint8[n_envs]; dir int8[n_envs]
+ * (may be NULL).  In AUTORESET mode a finished env returns the terminal
+ * reward/done together with the first observation of its next episode. */
+int bb_pool_step(bb_pool *pool, const void *actions_dev, int32_t action_bytes,
+                 uint8_t *obs_dev, float *reward_dev, uint8_t *done_dev, int8_t *dir_dev, void *stream);
+
+/* bb_pool_step on the pool's internal stream with CUDA events around each of its
+ * two kernels (measurement hook for bench.py's roofline line; synchronises). */
+int bb_pool_step_timed(bb_pool *pool, const void *actions_dev, int32_t action_bytes,
+                       uint8_t *obs_dev, float *reward_dev, uint8_t *done_dev, int8_t *dir_dev,
+                       float *ms_step_kernel, float *ms_gen_kernel);
+
+/* T consecutive steps with pre-recorded actions (the "random action" rollout
+ * of BASELINE.json configs): actions int8 [T][n_envs]; outputs [T][n_envs]...
+ * Equivalent to T calls of bb_pool_step; launched as one CUDA graph. */
+int bb_pool_rollout(bb_pool *pool, const int8_t *actions_dev, int32_t T,
+                    uint8_t *obs_dev, float *reward_dev, uint8_t *done_dev, int8_t *dir_dev, void *stream);
+
+/* Same as bb_pool_step but with HOST buffers (what ParallelEnv.step hands
+ * back to BaseAlgo.collect_experiences, rl/algos/base.py:144): copies actions
+ * host->device, steps, copies obs/reward/done/dir device->host, synchronises. */
+int bb_pool_step_host(bb_pool *pool, const int8_t *actions_host,
+                      uint8_t *obs_host, float *reward_host, uint8_t *done_host, int8_t *dir_host);
+int bb_pool_reset_host(bb_pool *pool, uint8_t *obs_host, int8_t *dir_host);
+
+/* Replaces: obs['mission'] + InstructionsPreprocessor (utils/format.py:59-75).
+ * Device pointer to int16 [n_envs][max_len] token ids of the current missions
+ * (0 = pad, ids index bb_vocab_word); rewritten whenever an env is reset. */
+int bb_pool_mission_tokens(bb_pool *pool, const int16_t **tokens_dev, int32_t *max_len);
+int32_t bb_vocab_size(void);
+const char *bb_vocab_word(int32_t id);   /* id 1..bb_vocab_size(); 0 = pad -> "" */
+
+/* Introspection for parity tests: one env's hidden state copied to host.
+ * grid_host: uint8[height*width], cell = type | color<<3 | state<<6 (empty 0x01);
+ * info_host: int32[8] = agent_x, agent_y, agent_dir, carrying cell byte (0 none),
+ * step_count, max_steps, rng draws (low 31 bits), generation attempts. */
+int bb_pool_get_state(bb_pool *pool, int32_t env, uint8_t *grid_host, int32_t *info_host);
+int32_t bb_pool_width(const bb_pool *pool);
+int32_t bb_pool_height(const bb_pool *pool);
+int32_t bb_pool_num_envs(const bb_pool *pool);
+
+/* Counters since creation, summed on the device: [0] env-steps, [1] episodes
+ * ended, [2] episodes ended in success, [3] internal errors (must stay 0).
+ * (Multi-GPU runs all-gather these -- the only collective on this path.) */
+int bb_pool_counters(bb_pool *pool, int64_t *out4_host);
+
+/* Number of kernel launches issued by this pool since creation. */
+int64_t bb_pool_launches(const bb_pool *pool);
+
+const char *bb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

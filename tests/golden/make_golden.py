@@ -1,0 +1,93 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own BabyAI layer
+(/root/reference/babyai/levels/*, unmodified) on the gym_minigrid shim
+(oracle/shim) with the Philox back-end, under ParallelEnv's auto-reset rule
+(penv.py:7-11).  Build container only (needs /root/reference); the committed
+.npz files travel to the GPU box.
+
+Per level: K traces of T steps.  Actions are 75 % reference-bot (babyai/bot.py)
+/ 25 % uniform random so that episodes actually succeed and the pickup / drop /
+toggle / PutNext / Before / After paths of the verifier are exercised.
+
+usage: python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.normpath(os.path.join(HERE, '..', '..'))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import refenv  # noqa: E402
+
+CONFIG_LEVELS = ['GoToRedBall', 'GoToLocal', 'PickupLoc', 'GoTo', 'BossLevel']
+OTHER_LEVELS = ['GoToRedBallGrey', 'GoToObjMazeS4R2', 'GoToOpen', 'Pickup', 'GoToSeq', 'Synth', 'SynthSeq',
+                'MiniBossLevel', 'BossLevelNoUnlock']
+
+
+def trace(level, seed, T, act_seed):
+    env = refenv.make_env(level, seed, 'philox')
+    from babyai.bot import Bot
+    rng = np.random.RandomState(act_seed)
+    obs = env.reset()
+    obs0 = obs['image'].copy().reshape(-1)
+    dir0 = obs['direction']
+    missions = [obs['mission']]
+    bot, last = Bot(env), None
+    A = np.zeros(T, np.int8)
+    O = np.zeros((T, 147), np.uint8)
+    R = np.zeros(T, np.float32)
+    D = np.zeros(T, np.uint8)
+    Q = np.zeros(T, np.int8)
+    for t in range(T):
+        a = None
+        if bot is not None and rng.rand() < 0.75:
+            try:
+                a = int(bot.replan(last))
+            except Exception:
+                bot = None
+        if a is None:
+            a = int(rng.randint(0, 7))
+            if bot is not None:   # things the bot cannot recover from (scripts/eval_bot.py:131-139)
+                fc = env.grid.get(*env.front_pos)
+                if a == 5 and fc is not None and (fc.type == 'box' or (fc.type == 'door' and fc.is_open)):
+                    a = 6
+        last = a
+        obs, reward, done, _ = env.step(a)
+        if done:
+            obs = env.reset()
+            missions.append(obs['mission'])
+            bot, last = Bot(env), None
+        A[t], R[t], D[t], Q[t] = a, np.float32(reward), done, obs['direction']
+        O[t] = obs['image'].reshape(-1)
+    return dict(actions=A, obs0=obs0, dir0=dir0, obs=O, reward=R, done=D, direction=Q, missions=missions)
+
+
+def main():
+    for level in CONFIG_LEVELS + OTHER_LEVELS:
+        K, T = (4, 400) if level in CONFIG_LEVELS else (2, 300)
+        if level == 'GoTo':
+            T = 700
+        if level == 'BossLevel':
+            K, T = 6, 1500
+        if level in ('SynthSeq', 'MiniBossLevel', 'BossLevelNoUnlock'):
+            K, T = 3, 800
+        seeds = [1000 + 17 * k for k in range(K)]
+        tr = [trace(level, s, T, act_seed=k) for k, s in enumerate(seeds)]
+        out = os.path.join(HERE, level + '.npz')
+        np.savez_compressed(
+            out, seeds=np.array(seeds, np.uint64),
+            actions=np.stack([t['actions'] for t in tr]), obs0=np.stack([t['obs0'] for t in tr]),
+            dir0=np.array([t['dir0'] for t in tr], np.int8), obs=np.stack([t['obs'] for t in tr]),
+            reward=np.stack([t['reward'] for t in tr]), done=np.stack([t['done'] for t in tr]),
+            direction=np.stack([t['direction'] for t in tr]),
+            missions=np.array(json.dumps([t['missions'] for t in tr])))
+        eps = sum(int(t['done'].sum()) for t in tr)
+        succ = sum(int((t['reward'] > 0).sum()) for t in tr)
+        print('%20s  %d traces x %d steps, %d episodes (%d successes) -> %s (%d KB)'
+              % (level, K, T, eps, succ, os.path.basename(out), os.path.getsize(out) // 1024), flush=True)
+
+
+if __name__ == '__main__':
+    main()

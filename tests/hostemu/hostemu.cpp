@@ -1,0 +1,147 @@
+// hostemu.cpp -- TEST-ONLY host build of babyai_b200/csrc/env_logic.cuh.
+//
+// The product has no CPU path: babyai_b200/ never loads this.  It exists so that
+// the `not gpu` test-suite (which runs in a container without a GPU) can execute
+// the very same per-environment source the CUDA kernels inline -- generation,
+// step, verifier, observation, word staging -- and compare it with the oracle.
+// The pool semantics of pool.cu (spare slot, refill, auto-reset / freeze) are
+// mirrored sequentially.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include "../../babyai_b200/csrc/env_logic.cuh"
+#include "../../include/babyai_b200.h"
+
+using namespace bb;
+
+struct Slot { std::vector<uint8_t> grid; EnvHot hot; ObjTab obj; InstrRec ins; std::vector<int16_t> tok; };
+struct HPool {
+    LevelParams lp; int n; int mode;
+    std::vector<Slot> live, spare; std::vector<uint8_t> sready, locked_room; std::vector<RngRec> rng;
+    std::vector<uint32_t> attempts; std::vector<float> last_reward;
+};
+
+// identical to make_params() in pool.cu (kept in sync by tests/test_hostemu.py::test_params_match on GPU)
+static void make_params(const bb_level_spec *s, LevelParams *lp)
+{
+    memset(lp, 0, sizeof *lp);
+    lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
+    lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
+    lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
+    lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
+    for (int i = 0; i < 4; i++) lp->action_kinds[i] = s->action_kinds[i];
+    for (int i = 0; i < 3; i++) lp->instr_kinds[i] = s->instr_kinds[i];
+    lp->W = (s->room_size - 1) * s->num_cols + 1;
+    lp->H = (s->room_size - 1) * s->num_rows + 1;
+    lp->cells = lp->W * lp->H;
+    lp->cells_pad = (lp->cells + 15) / 16 * 16;
+    lp->nav_time_maze = s->room_size * s->room_size * s->num_rows * s->num_cols;
+    if (s->kind == BB_KIND_LEVELGEN) {
+        double t = ceil(s->locked_room_prob * 4294967296.0);
+        lp->locked_thr = t <= 0 ? 0ull : (uint64_t)t;
+    }
+    lp->max_tokens = MAXTOK;
+    for (int y = 0; y < lp->H; y++) {
+        uint32_t row = 0;
+        for (int x = 0; x < lp->W; x++)
+            if (x % (s->room_size - 1) == 0 || y % (s->room_size - 1) == 0) row |= 1u << x;
+        lp->wall_rows[y] = row;
+    }
+}
+
+static void gen_spare(HPool *p, int e)
+{
+    Slot &s = p->spare[e];
+    LevelOut o; o.grid = s.grid.data(); o.hot = &s.hot; o.obj = &s.obj; o.ins = &s.ins; o.tok = s.tok.data();
+    p->attempts[e] += (uint32_t)generate_level(p->lp, o, &p->rng[e], &p->locked_room[e]);
+    p->sready[e] = 1;
+}
+
+static void obs_of(HPool *p, int e, uint8_t *out)
+{
+    Slot &s = p->live[e];
+    uint32_t w[OBS_WORDS];
+    observe(p->lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, &s.obj), w);
+    memcpy(out, w, OBS_BYTES);
+}
+
+extern "C" {
+
+HPool *he_create(const bb_level_spec *spec, int n)
+{
+    HPool *p = new HPool();
+    make_params(spec, &p->lp); p->n = n; p->mode = BB_MODE_AUTORESET;
+    p->live.resize(n); p->spare.resize(n); p->sready.assign(n, 0); p->locked_room.assign(n, 0xFF);
+    p->rng.resize(n); p->attempts.assign(n, 0); p->last_reward.assign(n, 0.f);
+    for (int i = 0; i < n; i++) {
+        p->live[i].grid.assign(p->lp.cells_pad, 0); p->spare[i].grid.assign(p->lp.cells_pad, 0);
+        p->live[i].tok.assign(MAXTOK, 0); p->spare[i].tok.assign(MAXTOK, 0);
+        memset(&p->live[i].hot, 0, sizeof(EnvHot)); memset(&p->live[i].obj, 0, sizeof(ObjTab)); memset(&p->live[i].ins, 0, sizeof(InstrRec));
+        p->rng[i].seed = (uint64_t)i; p->rng[i].draws = 0;
+    }
+    return p;
+}
+void he_destroy(HPool *p) { delete p; }
+void he_set_mode(HPool *p, int mode) { p->mode = mode; }
+void he_seed(HPool *p, const uint64_t *seeds)
+{
+    for (int i = 0; i < p->n; i++) { p->rng[i].seed = seeds[i]; p->rng[i].draws = 0; p->locked_room[i] = 0xFF; p->sready[i] = 0; }
+}
+void he_reset(HPool *p, uint8_t *obs, int8_t *dir)
+{
+    for (int e = 0; e < p->n; e++) {
+        if (!p->sready[e]) gen_spare(p, e);
+        p->live[e] = p->spare[e]; p->sready[e] = 0;
+        if (p->mode == BB_MODE_AUTORESET) gen_spare(p, e);
+        obs_of(p, e, obs + (size_t)e * OBS_BYTES);
+        if (dir) dir[e] = (int8_t)(p->live[e].hot.dirflags & 3);
+    }
+}
+void he_step(HPool *p, const int8_t *actions, uint8_t *obs, float *reward, uint8_t *done, int8_t *dir)
+{
+    for (int e = 0; e < p->n; e++) {
+        Slot &s = p->live[e];
+        float rew = 0; bool dn = false;
+        if (!(s.hot.dirflags & 4)) {
+            StepResult r = step_env(p->lp, s.hot, s.grid.data(), &s.obj, &s.ins, actions[e]);
+            rew = r.reward; dn = r.done;
+            if (dn) {
+                if (p->mode == BB_MODE_AUTORESET) { p->live[e] = p->spare[e]; p->sready[e] = 0; gen_spare(p, e); }
+                else { s.hot.dirflags |= 4; p->last_reward[e] = rew; }
+            }
+        } else { rew = p->last_reward[e]; dn = true; }
+        obs_of(p, e, obs + (size_t)e * OBS_BYTES);
+        reward[e] = rew; done[e] = dn; if (dir) dir[e] = (int8_t)(p->live[e].hot.dirflags & 3);
+    }
+}
+void he_tokens(HPool *p, int e, int16_t *out) { memcpy(out, p->live[e].tok.data(), MAXTOK * sizeof(int16_t)); }
+void he_get_state(HPool *p, int e, uint8_t *grid, int32_t *info)
+{
+    Slot &s = p->live[e];
+    memcpy(grid, s.grid.data(), p->lp.cells);
+    info[0] = s.hot.x; info[1] = s.hot.y; info[2] = s.hot.dirflags & 3;
+    info[3] = s.hot.carry == NO_OBJ ? 0 : s.obj.tc[s.hot.carry];
+    info[4] = s.hot.step_count; info[5] = s.hot.max_steps;
+    info[6] = (int32_t)(p->rng[e].draws & 0x7FFFFFFF); info[7] = (int32_t)p->attempts[e];
+}
+int he_width(HPool *p) { return p->lp.W; }
+int he_height(HPool *p) { return p->lp.H; }
+
+// vis_rows against 7-bit see-through rows
+void he_vis_rows(const uint32_t *see, uint32_t *vis) { vis_rows(see, vis); }
+
+// staging: 32 lanes x 37 words -> 4704-byte tile, emulating the shuffle
+void he_stage(const uint32_t *w /* [32][37] */, uint8_t *tile /* 4704 + slack */)
+{
+    uint32_t t[32 * OBS_BYTES / 4 + 2];
+    memset(t, 0xEE, sizeof t);
+    for (int lane = 0; lane < 32; lane++) {
+        uint32_t next_w0 = lane < 31 ? w[(lane + 1) * OBS_WORDS] : w[lane * OBS_WORDS];   // shfl_down keeps own value at the edge
+        stage_obs_words(t, w + lane * OBS_WORDS, lane, next_w0);
+    }
+    memcpy(tile, t, 32 * OBS_BYTES);
+}
+
+}  // extern "C"
