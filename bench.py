@@ -204,7 +204,8 @@ def main():
 
     n, K, W = args.envs, args.steps, args.warmup
     # rank r owns global env indices [r*n, (r+1)*n); seeds follow the global index (train_rl.py:59, --seed 1)
-    seeds = np.array([100 + rank * n + i for i in range(n)], dtype=np.uint64)
+    from babyai_b200.sharding import gather_counters, shard_seeds
+    seeds = shard_seeds(1, world * n, rank, world)
     env = BabyAIVecEnv(args.level, n, seeds=seeds, device=local_rank)
     env.reset()
 
@@ -281,13 +282,7 @@ def main():
     e2e_s = float(te.item())
 
     # ---- the only collective on this path: all-gather of the counters --------------------
-    c = env.counters()
-    cnt = torch.tensor([c['steps'], c['episodes'], c['successes'], c['errors']], dtype=torch.int64, device=dev)
-    if world > 1:
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        cnt = torch.stack(allc).sum(0)
-    cnt = [int(x) for x in cnt.tolist()]
+    cnt = gather_counters(env.counters(), device=dev)
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -317,7 +312,7 @@ def main():
                     'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke, 'api': 'bb_pool_step_host'},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'counters': {'steps': cnt[0], 'episodes': cnt[1], 'successes': cnt[2], 'errors': cnt[3]},
+            'counters': cnt,
         }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
