@@ -112,10 +112,15 @@ BB_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 #endif
 }
 
+// Per-env random stream.  Host build (tests/hostemu): scalar.  Device build: the
+// WHOLE WARP runs generate_level() for one environment with identical control
+// flow (k_gen maps one warp to one refill-list entry), so the 32 lanes compute 32
+// consecutive Philox blocks (128 draws) at once and a draw is a shuffle from the
+// lane that holds its block.
 struct Rng {
     uint32_t k0, k1;
     uint64_t draws;
-    uint64_t blk;                 // block currently held in b0..b3 (~0 = none)
+    uint64_t blk;                 // block held in b0..b3 (device: by lane 0; lane l holds blk + l); ~0 = none
     uint32_t b0, b1, b2, b3;
 
     BB_HD void init(uint64_t seed, uint64_t d)
@@ -134,14 +139,24 @@ struct Rng {
             c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
             x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
         }
-        b0 = c0; b1 = c1; b2 = c2; b3 = c3; blk = n;
+        b0 = c0; b1 = c1; b2 = c2; b3 = c3;
     }
     BB_HD uint32_t u32()
     {
-        uint64_t i = draws++;
-        if ((i >> 2) != blk) refill(i >> 2);
-        uint32_t w = (uint32_t)i & 3u;
+        const uint64_t i = draws++;
+        const uint64_t nb = i >> 2;
+        const uint32_t w = (uint32_t)i & 3u;
+#if defined(__CUDA_ARCH__)
+        if (blk == ~0ull || nb - blk >= 32ull) {          // warp-uniform condition
+            blk = nb;
+            refill(nb + (threadIdx.x & 31));
+        }
+        const uint32_t mine = w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
+        return __shfl_sync(0xFFFFFFFFu, mine, (int)(nb - blk));
+#else
+        if (nb != blk) { blk = nb; refill(nb); }
         return w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
+#endif
     }
     // MiniGridEnv._rand_int(lo, hi); a range of one value consumes no draw
     BB_HD int randint(int lo, int hi)
@@ -648,9 +663,19 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     *locked_room_persist = g.locked_room < 0 ? 0xFF : (uint8_t)g.locked_room;
 
     // ---- render the byte grid: walls, then doors/objects -----------------
-    for (int y = 0; y < lp.H; y++)
-        for (int x = 0; x < lp.W; x++)
-            o.grid[y * lp.W + x] = (uint8_t)(((lp.wall_rows[y] >> x) & 1u) ? CELL_WALL : CELL_EMPTY);
+    // (device: the warp's lanes split the cells; every lane holds the same level)
+#if defined(__CUDA_ARCH__)
+    const int lane = threadIdx.x & 31, nlanes = 32;
+#else
+    const int lane = 0, nlanes = 1;
+#endif
+    for (int c = lane; c < lp.cells; c += nlanes) {
+        const int y = c / lp.W, x = c - y * lp.W;
+        o.grid[c] = (uint8_t)(((lp.wall_rows[y] >> x) & 1u) ? CELL_WALL : CELL_EMPTY);
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
     for (int k = 0; k < g.nobj; k++) {
         int tc = o.obj->tc[k], st = 0;
         if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (k == g.locked_door ? 2 : 1);   // open_all_doors levelgen.py:189-199
@@ -677,7 +702,7 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     int n = tok_side(g, 0, tok, 0);
     if (g.root_kind == R_BEFORE) { tok[n++] = W_THEN; n = tok_side(g, 1, tok, n); }
     else if (g.root_kind == R_AFTER) { tok[n++] = W_AFTER; tok[n++] = W_YOU; n = tok_side(g, 1, tok, n); }
-    for (int k = 0; k < lp.max_tokens; k++) o.tok[k] = k < n ? tok[k] : (int16_t)0;
+    for (int k = lane; k < lp.max_tokens; k += nlanes) o.tok[k] = k < n ? tok[k] : (int16_t)0;
     return attempts;
 }
 
