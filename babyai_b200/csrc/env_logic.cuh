@@ -73,6 +73,7 @@ struct LevelParams {
     int32_t n_action_kinds, action_kinds[4];
     int32_t n_instr_kinds, instr_kinds[3];
     int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
+    int32_t rs_g, rs_t, gt_off;   // grid bytes of one env: G = H rows x rs_g at 0, GT = W rows x rs_t at gt_off
     uint64_t locked_thr;          // rand_float(0,1) < p  <=>  u32 < ceil(p * 2^32)
     uint32_t wall_rows[MAXH];     // bit x of row y: (x, y) is a wall of the empty RoomGrid
 };
@@ -199,6 +200,14 @@ BB_HD int color_by_name_rank(int k)   // blue green grey purple red yellow
 // =============================================================================
 // Level generation (RoomGridLevel._gen_grid, levelgen.py:77-102, and below)
 // =============================================================================
+// the two orientations of one env's grid (see LevelParams::rs_g / rs_t / gt_off)
+BB_HD int get_cell(const LevelParams &lp, const uint8_t *grid, int x, int y) { return grid[y * lp.rs_g + x]; }
+BB_HD void set_cell(const LevelParams &lp, uint8_t *grid, int x, int y, int v)
+{
+    grid[y * lp.rs_g + x] = (uint8_t)v;
+    grid[lp.gt_off + x * lp.rs_t + y] = (uint8_t)v;
+}
+
 struct LevelOut {           // where one generated level is written (live or spare slot)
     uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
 };
@@ -669,9 +678,14 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
 #else
     const int lane = 0, nlanes = 1;
 #endif
-    for (int c = lane; c < lp.cells; c += nlanes) {
-        const int y = c / lp.W, x = c - y * lp.W;
-        o.grid[c] = (uint8_t)(((lp.wall_rows[y] >> x) & 1u) ? CELL_WALL : CELL_EMPTY);
+    // G (row-major) and GT (column-major); row padding up to the stride is wall
+    for (int c = lane; c < lp.H * lp.rs_g; c += nlanes) {
+        const int y = c / lp.rs_g, x = c - y * lp.rs_g;
+        o.grid[c] = (uint8_t)((x >= lp.W || ((lp.wall_rows[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
+    }
+    for (int c = lane; c < lp.W * lp.rs_t; c += nlanes) {
+        const int x = c / lp.rs_t, y = c - x * lp.rs_t;
+        o.grid[lp.gt_off + c] = (uint8_t)((y >= lp.H || ((lp.wall_rows[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
     }
 #if defined(__CUDA_ARCH__)
     __syncwarp();
@@ -679,7 +693,7 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     for (int k = 0; k < g.nobj; k++) {
         int tc = o.obj->tc[k], st = 0;
         if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (k == g.locked_door ? 2 : 1);   // open_all_doors levelgen.py:189-199
-        o.grid[o.obj->y[k] * lp.W + o.obj->x[k]] = (uint8_t)(tc | (st << 6));
+        set_cell(lp, o.grid, o.obj->x[k], o.obj->y[k], tc | (st << 6));
     }
     // ---- verifier record (reset_verifier) + max_steps (levelgen.py:42-45) --
     int navs = 0;
@@ -793,8 +807,7 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
 {
     int x = h.x, y = h.y, dir = h.dirflags & 3, carry = h.carry;
     const int fx = x + dir_dx(dir), fy = y + dir_dy(dir);
-    const int fidx = fy * lp.W + fx;
-    const int fc = grid[fidx];
+    const int fc = get_cell(lp, grid, fx, fy);
     const int ftype = fc & 7;
     if (action == A_LEFT) dir = (dir + 3) & 3;
     else if (action == A_RIGHT) dir = (dir + 1) & 3;
@@ -803,11 +816,11 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
     } else if (action == A_PICKUP) {
         if (ftype >= T_KEY && carry == NO_OBJ) {
             int id = find_obj_at(ot, h.cur_mask, fx, fy);
-            if (id != NO_OBJ) { carry = id; h.cur_mask &= ~(1u << id); grid[fidx] = (uint8_t)CELL_EMPTY; }
+            if (id != NO_OBJ) { carry = id; h.cur_mask &= ~(1u << id); set_cell(lp, grid, fx, fy, CELL_EMPTY); }
         }
     } else if (action == A_DROP) {
         if (fc == CELL_EMPTY && carry != NO_OBJ) {
-            grid[fidx] = ot->tc[carry];
+            set_cell(lp, grid, fx, fy, ot->tc[carry]);
             ot->x[carry] = (uint8_t)fx; ot->y[carry] = (uint8_t)fy;
             h.cur_mask |= 1u << carry;
             carry = NO_OBJ;
@@ -818,11 +831,11 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
             if (st == 2) {           // locked: needs a carried key of the door's colour; key stays in hand
                 if (carry != NO_OBJ && (ot->tc[carry] & 7) == T_KEY && (ot->tc[carry] >> 3) == ((fc >> 3) & 7)) ns = 0;
             } else ns = st ^ 1;
-            grid[fidx] = (uint8_t)((fc & 0x3F) | (ns << 6));
+            if (ns != st) set_cell(lp, grid, fx, fy, (fc & 0x3F) | (ns << 6));
         } else if (ftype == T_BOX) {  // Box.toggle: replaced by its contents (None)
             int id = find_obj_at(ot, h.cur_mask, fx, fy);
             if (id != NO_OBJ) h.cur_mask &= ~(1u << id);
-            grid[fidx] = (uint8_t)CELL_EMPTY;
+            set_cell(lp, grid, fx, fy, CELL_EMPTY);
         }
     }
     h.step_count = (uint16_t)(h.step_count + 1);
@@ -833,7 +846,7 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
     h.x = (uint8_t)x; h.y = (uint8_t)y; h.dirflags = (uint8_t)((h.dirflags & ~3) | dir); h.carry = (uint8_t)carry;
     StepCtx s;
     s.action = action; s.fx = x + dir_dx(dir); s.fy = y + dir_dy(dir); s.carry = carry;
-    s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.grid = grid; s.ot = ot; s.W = lp.W;
+    s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.grid = grid; s.ot = ot; s.W = lp.rs_g;
     r.success = verify_root(ins, s);
     r.reward = 0.0f;
     if (r.success) {
@@ -853,66 +866,215 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
 // =============================================================================
 // observation: gen_obs_grid + process_vis + encode (App. A.5)
 // =============================================================================
-// Visibility of the 7x7 view as 7-bit row masks (bit i = lateral column vi).
-// see[j] = see-through cells of view row j.  Equivalent to the reference's
-// nested process_vis loops (proved exhaustively in tests/test_vis_rows.py).
+// The 7x7 view is handled as seven "view columns" (fixed lateral index vi, the
+// seven depths vj as bytes), because that is the order of the output bytes
+// (image[vi][vj][c]).  A view column is a 7-byte window of ONE stored grid row:
+// of G (row-major) when the agent faces left/right, of GT (column-major) when it
+// faces up/down -- three aligned 32-bit loads + a funnel shift, byte-reversed for
+// two of the four headings.  Everything after that is SWAR on packed bytes:
+// see-through flags, 8x8 bit transposes between column and row domain, the
+// row-wise visibility propagation with a carry trick, byte masks, and the
+// (type, color, state) expansion with byte permutes.
+BB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s)     // low 32 bits of (hi:lo) >> s, s in 0..31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s == 0 ? lo : (lo >> s) | (hi << (32 - s));
+#endif
+}
+BB_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel)   // PRMT, selector nibbles 0..7 only
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+#endif
+}
+BB_HD uint32_t rev7(uint32_t x)                                  // reverse the low 7 bits
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(x & 0x7Fu) >> 25;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 7; i++) r |= ((x >> i) & 1u) << (6 - i);
+    return r;
+#endif
+}
+BB_HD uint32_t load_u32(const uint8_t *p)                        // p is 4-byte aligned
+{
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const uint32_t *>(p);
+#else
+    uint32_t v;
+    __builtin_memcpy(&v, p, 4);
+    return v;
+#endif
+}
+
+// 0x80 in every byte of x (all bytes <= 0x7F) that is non-zero
+BB_HD uint32_t nz80(uint32_t x) { return (x + 0x7F7F7F7Fu) & 0x80808080u; }
+// see-through flags (0x80 per byte) of four packed cells: opaque = wall, or door that is not open
+BB_HD uint32_t see80(uint32_t c)
+{
+    const uint32_t t = c & 0x07070707u;
+    const uint32_t notwall = nz80(t ^ 0x02020202u);
+    const uint32_t notdoor = nz80(t ^ 0x04040404u);
+    const uint32_t closed = nz80((c >> 6) & 0x03030303u);
+    return notwall & (notdoor | ~closed);
+}
+// the four 0x80 flags of a word -> bits 0..3 (partial products land on distinct bits: no carries)
+BB_HD uint32_t gather4(uint32_t f80) { return (((f80 >> 7) * 0x01020408u) >> 24) & 0xFu; }
+// bits 0..3 -> 0xFF in bytes 0..3
+BB_HD uint32_t expand4(uint32_t bits) { return (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
+// 8x8 bit-matrix transpose, bit (i, j) at position 8 i + j of (hi:lo)
+BB_HD void transpose8(uint32_t &lo, uint32_t &hi)
+{
+    uint64_t x = ((uint64_t)hi << 32) | lo, t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull; x = x ^ t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
+    lo = (uint32_t)x; hi = (uint32_t)(x >> 32);
+}
+
+// Visibility of the 7x7 view as 7-bit row masks (bit i = lateral column vi);
+// see[j] = see-through cells of view row j, row 6 is the agent's.  Equivalent to the
+// reference's nested process_vis loops (exhaustive test in tests/test_hostemu.py).
+// Row rule: the visible see-through cells flood sideways through see-through cells,
+// and the cell just beyond each end of a flooded run is visible too; that same set
+// (run + its two neighbours) is what the next row starts from.  The flood towards
+// higher bits is one addition: carries ripple through the run of ones in `s` and stop
+// on (and set) the first blocked cell; the other direction is the same on reversed bits.
 BB_HD void vis_rows(const uint32_t see[7], uint32_t vis[7])
 {
     uint32_t v = 1u << 3;                       // agent cell (3, 6)
 #pragma unroll
     for (int j = 6; j >= 0; j--) {
-        const uint32_t s = see[j];
-        uint32_t a = v & s;                     // visible cells that let light through
-#pragma unroll
-        for (int it = 0; it < 6; it++) a |= ((a << 1) | (a >> 1)) & s;    // flood along the row
-        const uint32_t d = (a | (a << 1) | (a >> 1)) & 0x7Fu;
+        const uint32_t s = see[j] & 0x7Fu;
+        const uint32_t a = v & s;               // visible cells that let light through
+        const uint32_t up = ((s + a) ^ s) | a;
+        const uint32_t rs = rev7(s), ra = rev7(a);
+        const uint32_t dn = rev7(((rs + ra) ^ rs) | ra);
+        const uint32_t d = (up | dn) & 0x7Fu;
         vis[j] = v | d;
         v = d;                                  // what the row above starts from
     }
 }
 
-// cell byte -> 24-bit (type, color, state) observation triple
-BB_HD uint32_t expand_cell(uint32_t c) { return (c & 7u) | ((c & 0x38u) << 5) | ((c & 0xC0u) << 10); }
-
 // Writes the 147 observation bytes as 37 little-endian words (last byte 0).
 BB_HD void observe(const LevelParams &lp, const uint8_t *grid, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
 {
-    const int fx = dir_dx(dir), fy = dir_dy(dir), rx = -fy, ry = fx;
-    uint8_t cell[49];                            // [vi*7 + vj]
+    const uint32_t WALLW = 0x2A2A2A2Au;
+    // which stored row holds view column vi, and where its 7-cell window starts
+    //   dir 3 (up):    GT row ax-3+vi, window y = ay-6 .. ay     (byte vj <-> y = ay-6+vj)
+    //   dir 1 (down):  GT row ax+3-vi, window y = ay .. ay+6     reversed (vj <-> y = ay+6-vj)
+    //   dir 0 (right): G  row ay-3+vi, window x = ax .. ax+6     reversed (vj <-> x = ax+6-vj)
+    //   dir 2 (left):  G  row ay+3-vi, window x = ax-6 .. ax     (vj <-> x = ax-6+vj)
+    const bool vert = (dir & 1) != 0;
+    const uint8_t *base = grid + (vert ? lp.gt_off : 0);
+    const int rs = vert ? lp.rs_t : lp.rs_g;
+    const int nrows = vert ? lp.W : lp.H;
+    const int c_row = vert ? ax : ay, c_win = vert ? ay : ax;
+    const int rstep = (dir == 3 || dir == 0) ? 1 : -1;
+    const bool rev = (dir == 1 || dir == 0);
+    const int s0 = rev ? c_win : c_win - 6;
+    const int k0 = s0 >> 2;                      // arithmetic shift: floor for negative starts
+    const int sh = (s0 & 3) * 8;
+    const int nwords = rs >> 2;
+    const bool ok0 = k0 >= 0 && k0 < nwords, ok1 = k0 + 1 >= 0 && k0 + 1 < nwords, ok2 = k0 + 2 >= 0 && k0 + 2 < nwords;
+    const uint32_t sel_lo = rev ? 0x3456u : 0x3210u, sel_hi = rev ? 0x7012u : 0x7654u;
+
+    uint32_t R[14];                              // R[2 vi] = cells vj 0..3, R[2 vi + 1] = cells vj 4..6 (+1 unused byte)
+#pragma unroll
+    for (int vi = 0; vi < 7; vi++) {
+        const int row = c_row + rstep * (vi - 3);
+        const bool rok = row >= 0 && row < nrows;
+        const uint8_t *rp = base + row * rs + 4 * k0;
+        const uint32_t w0 = (rok && ok0) ? load_u32(rp) : WALLW;          // slice(): out of bounds -> Wall()
+        const uint32_t w1 = (rok && ok1) ? load_u32(rp + 4) : WALLW;
+        const uint32_t w2 = (rok && ok2) ? load_u32(rp + 8) : WALLW;
+        const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);
+        R[2 * vi] = byte_perm(lo, hi, sel_lo);
+        R[2 * vi + 1] = byte_perm(lo, hi, sel_hi);
+    }
+    // see-through bits: per column (bit vj), then transposed to per row (bit vi)
+    uint32_t blo = 0, bhi = 0;
+#pragma unroll
+    for (int vi = 0; vi < 7; vi++) {
+        const uint32_t cm = (gather4(see80(R[2 * vi])) | (gather4(see80(R[2 * vi + 1])) << 4)) & 0x7Fu;
+        if (vi < 4) blo |= cm << (8 * vi); else bhi |= cm << (8 * (vi - 4));
+    }
+    transpose8(blo, bhi);
     uint32_t see[7], vis[7];
 #pragma unroll
+    for (int vj = 0; vj < 7; vj++) see[vj] = ((vj < 4 ? blo >> (8 * vj) : bhi >> (8 * (vj - 4)))) & 0x7Fu;
+    vis_rows(see, vis);
+    uint32_t vlo = 0, vhi = 0;
+#pragma unroll
+    for (int vj = 0; vj < 7; vj++) { if (vj < 4) vlo |= vis[vj] << (8 * vj); else vhi |= vis[vj] << (8 * (vj - 4)); }
+    transpose8(vlo, vhi);                        // byte vi = visibility of column vi, bit vj
+    // the agent's own cell (3, 6) shows what it carries (or empty); it is always visible
+    R[7] = (R[7] & 0xFF00FFFFu) | ((uint32_t)carry_cell << 16);
+#pragma unroll
+    for (int vi = 0; vi < 7; vi++) {
+        const uint32_t cv = (vi < 4 ? vlo >> (8 * vi) : vhi >> (8 * (vi - 4))) & 0x7Fu;
+        R[2 * vi] &= expand4(cv);
+        R[2 * vi + 1] &= expand4(cv >> 4);       // also clears the unused fourth byte
+    }
+    // cell stream (49 bytes, index 7 vi + vj) four cells at a time -> 3 output words each
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+        // stream bytes 4k .. 4k+3 live in at most two consecutive registers of R (7-byte records: 4 + 3)
+        uint32_t sel = 0; int ra = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = 4 * k + i;
+            const int vi = q / 7, vj = q % 7;
+            const int r = 2 * vi + (vj >= 4 ? 1 : 0), byte = vj >= 4 ? vj - 4 : vj;
+            if (q >= 49) { sel |= 3u << (4 * i); continue; }          // byte 3 of R[13] is zero
+            if (ra < 0) ra = r;
+            sel |= (uint32_t)(r == ra ? byte : 4 + byte) << (4 * i);
+        }
+        const uint32_t c = byte_perm(R[ra], ra + 1 < 14 ? R[ra + 1] : 0u, sel);
+        const uint32_t T = c & 0x07070707u, K = (c >> 3) & 0x07070707u, S = (c >> 6) & 0x03030303u;
+        const uint32_t o0 = byte_perm(byte_perm(T, K, 0x1040u), S, 0x3410u);      // t0 k0 s0 t1
+        const uint32_t o1 = byte_perm(byte_perm(T, K, 0x6205u), S, 0x3250u);      // k1 s1 t2 k2
+        const uint32_t o2 = byte_perm(byte_perm(T, K, 0x0730u), S, 0x7216u);      // s2 t3 k3 s3
+        w[3 * k] = o0;
+        if (k < 12) { w[3 * k + 1] = o1; w[3 * k + 2] = o2; }
+    }
+}
+
+// The same observation computed cell by cell (straightforward form; test cross-check only)
+BB_HD void observe_simple(const LevelParams &lp, const uint8_t *grid, int ax, int ay, int dir, int carry_cell, uint8_t out[OBS_BYTES])
+{
+    const int fx = dir_dx(dir), fy = dir_dy(dir), rx = -fy, ry = fx;
+    uint8_t cell[49];
+    uint32_t see[7], vis[7];
     for (int vj = 0; vj < 7; vj++) {
         uint32_t s = 0;
-#pragma unroll
         for (int vi = 0; vi < 7; vi++) {
-            const int wx = ax + fx * (6 - vj) + rx * (vi - 3);
-            const int wy = ay + fy * (6 - vj) + ry * (vi - 3);
+            const int wx = ax + fx * (6 - vj) + rx * (vi - 3), wy = ay + fy * (6 - vj) + ry * (vi - 3);
             const bool inb = wx >= 0 && wx < lp.W && wy >= 0 && wy < lp.H;
-            const uint32_t c = inb ? grid[wy * lp.W + wx] : (uint32_t)CELL_WALL;      // slice(): OOB -> Wall()
+            const uint32_t c = inb ? (uint32_t)get_cell(lp, grid, wx, wy) : (uint32_t)CELL_WALL;
             cell[vi * 7 + vj] = (uint8_t)c;
             const uint32_t t = c & 7u;
-            const bool opaque = t == T_WALL || (t == T_DOOR && (c >> 6) != 0);
-            s |= (opaque ? 0u : 1u) << vi;
+            s |= ((t == T_WALL || (t == T_DOOR && (c >> 6) != 0)) ? 0u : 1u) << vi;
         }
         see[vj] = s;
     }
     vis_rows(see, vis);
-    cell[3 * 7 + 6] = (uint8_t)carry_cell;       // the agent's own cell shows what it carries (or empty)
-    uint32_t e[49];
-#pragma unroll
+    cell[3 * 7 + 6] = (uint8_t)carry_cell;
     for (int vi = 0; vi < 7; vi++)
-#pragma unroll
-        for (int vj = 0; vj < 7; vj++)
-            e[vi * 7 + vj] = ((vis[vj] >> vi) & 1u) ? expand_cell(cell[vi * 7 + vj]) : 0u;
-    // pack 24-bit triples: 4 cells -> 3 words
-#pragma unroll
-    for (int q = 0; q < 12; q++) {
-        const uint32_t e0 = e[4 * q], e1 = e[4 * q + 1], e2 = e[4 * q + 2], e3 = e[4 * q + 3];
-        w[3 * q] = e0 | (e1 << 24);
-        w[3 * q + 1] = (e1 >> 8) | (e2 << 16);
-        w[3 * q + 2] = (e2 >> 16) | (e3 << 8);
-    }
-    w[36] = e[48];
+        for (int vj = 0; vj < 7; vj++) {
+            const uint32_t c = ((vis[vj] >> vi) & 1u) ? cell[vi * 7 + vj] : 0u;
+            uint8_t *px = out + (vi * 7 + vj) * 3;
+            px[0] = (uint8_t)(c & 7u); px[1] = (uint8_t)((c >> 3) & 7u); px[2] = (uint8_t)(c >> 6);
+        }
 }
 
 BB_HD int carry_cell_of(const EnvHot &h, const ObjTab *ot) { return h.carry == NO_OBJ ? CELL_EMPTY : ot->tc[h.carry]; }

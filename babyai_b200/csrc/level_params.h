@@ -1,0 +1,69 @@
+// level_params.h -- host-side derivation of the kernels' LevelParams from the
+// reference-style constructor arguments (bb_level_spec).  Shared by pool.cu and
+// the test-only host build (tests/hostemu) so both see the same layout.
+#pragma once
+#include <math.h>
+#include <string.h>
+#include "../../include/babyai_b200.h"
+#include "env_logic.cuh"
+
+namespace bb {
+
+// returns nullptr on success, else a static error message
+static inline const char *make_level_params(const bb_level_spec *s, LevelParams *lp)
+{
+    memset(lp, 0, sizeof *lp);
+    if (s->kind < 0 || s->kind > 2) return "bad level kind";
+    if (s->room_size < 4 || s->room_size > 8) return "room_size must be in 4..8";
+    if (s->num_rows < 1 || s->num_cols < 1 || s->num_rows * s->num_cols > MAXROOMS) return "too many rooms";
+    lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
+    lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
+    lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
+    lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
+    for (int i = 0; i < 4; i++) lp->action_kinds[i] = s->action_kinds[i];
+    for (int i = 0; i < 3; i++) lp->instr_kinds[i] = s->instr_kinds[i];
+    lp->W = (s->room_size - 1) * s->num_cols + 1;
+    lp->H = (s->room_size - 1) * s->num_rows + 1;
+    if (lp->W > MAXH || lp->H > MAXH) return "grid too large";
+    lp->cells = lp->W * lp->H;
+    // the grid is stored twice: row-major G (H rows, stride rs_g) and column-major GT (W rows, stride rs_t);
+    // strides are multiples of 4 so that a 7-cell window is three aligned 32-bit loads; padding bytes are walls
+    lp->rs_g = (lp->W + 3) / 4 * 4;
+    lp->rs_t = (lp->H + 3) / 4 * 4;
+    lp->gt_off = (lp->H * lp->rs_g + 15) / 16 * 16;
+    lp->cells_pad = lp->gt_off + (lp->W * lp->rs_t + 15) / 16 * 16;
+    lp->nav_time_maze = s->room_size * s->room_size * s->num_rows * s->num_cols;   // levelgen.py:42-43
+    int max_objs = s->num_dists + 1;
+    if (s->kind == BB_KIND_LEVELGEN) {
+        if (s->n_action_kinds < 1 || s->n_action_kinds > 4 || s->n_instr_kinds < 1 || s->n_instr_kinds > 3)
+            return "bad LevelGen kinds";
+        double t = ceil(s->locked_room_prob * 4294967296.0);
+        lp->locked_thr = t <= 0 ? 0ull : (uint64_t)t;
+    }
+    // doors: one per internal wall at most
+    max_objs += s->num_rows * (s->num_cols - 1) + s->num_cols * (s->num_rows - 1);
+    if (max_objs > MAXOBJ) return "too many objects for the 32-entry object table";
+    // longest mission in tokens
+    int per_desc = 3 + (s->kind == BB_KIND_LEVELGEN && s->locations ? 4 : 0);
+    int leaf = 2 + per_desc;
+    if (s->kind == BB_KIND_LEVELGEN) {
+        bool putnext = false, has_and = false, has_seq = false;
+        for (int i = 0; i < s->n_action_kinds; i++) if (s->action_kinds[i] == BB_I_PUTNEXT) putnext = true;
+        for (int i = 0; i < s->n_instr_kinds; i++) { if (s->instr_kinds[i] == BB_K_AND) has_and = true; if (s->instr_kinds[i] == BB_K_SEQ) has_seq = true; }
+        if (putnext) leaf = 1 + per_desc + 2 + per_desc;
+        int side = (has_and || has_seq) ? 2 * leaf + 1 : leaf;
+        lp->max_tokens = has_seq ? 2 * side + 2 : side;
+    } else lp->max_tokens = leaf;
+    lp->max_tokens = (lp->max_tokens + 7) / 8 * 8;          // 16-byte rows
+    if (lp->max_tokens > MAXTOK) lp->max_tokens = MAXTOK;
+    // wall template of the empty RoomGrid (Grid.wall_rect per room)
+    for (int y = 0; y < lp->H; y++) {
+        uint32_t row = 0;
+        for (int x = 0; x < lp->W; x++)
+            if (x % (s->room_size - 1) == 0 || y % (s->room_size - 1) == 0) row |= 1u << x;
+        lp->wall_rows[y] = row;
+    }
+    return nullptr;
+}
+
+}  // namespace bb

@@ -23,6 +23,7 @@
 
 #include "../../include/babyai_b200.h"
 #include "env_logic.cuh"
+#include "level_params.h"
 
 using namespace bb;
 
@@ -90,7 +91,7 @@ __device__ __forceinline__ void swap_in(const LevelParams &lp, const PoolPtrs &P
 }
 
 template <int ACT_BYTES>
-__global__ void __launch_bounds__(STEP_THREADS)
+__global__ void __launch_bounds__(STEP_THREADS, 4)
 k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
        float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
        const int mode, const int force_reset)
@@ -254,53 +255,8 @@ static int dalloc(bb_pool *p, T **out, size_t count)
 
 static int make_params(const bb_level_spec *s, LevelParams *lp)
 {
-    memset(lp, 0, sizeof *lp);
-    if (s->kind < 0 || s->kind > 2) return fail("bad level kind");
-    if (s->room_size < 4 || s->room_size > 8) return fail("room_size must be in 4..8");
-    if (s->num_rows < 1 || s->num_cols < 1 || s->num_rows * s->num_cols > MAXROOMS) return fail("too many rooms");
-    lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
-    lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
-    lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
-    lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
-    for (int i = 0; i < 4; i++) lp->action_kinds[i] = s->action_kinds[i];
-    for (int i = 0; i < 3; i++) lp->instr_kinds[i] = s->instr_kinds[i];
-    lp->W = (s->room_size - 1) * s->num_cols + 1;
-    lp->H = (s->room_size - 1) * s->num_rows + 1;
-    if (lp->W > MAXH || lp->H > MAXH) return fail("grid too large");
-    lp->cells = lp->W * lp->H;
-    lp->cells_pad = (lp->cells + 15) / 16 * 16;
-    lp->nav_time_maze = s->room_size * s->room_size * s->num_rows * s->num_cols;   // levelgen.py:42-43
-    int max_objs = s->num_dists + 1;
-    if (s->kind == BB_KIND_LEVELGEN) {
-        if (s->n_action_kinds < 1 || s->n_action_kinds > 4 || s->n_instr_kinds < 1 || s->n_instr_kinds > 3)
-            return fail("bad LevelGen kinds");
-        double t = ceil(s->locked_room_prob * 4294967296.0);
-        lp->locked_thr = t <= 0 ? 0ull : (uint64_t)t;
-    }
-    // doors: one per internal wall at most
-    max_objs += s->num_rows * (s->num_cols - 1) + s->num_cols * (s->num_rows - 1);
-    if (max_objs > MAXOBJ) return fail("too many objects for the 32-entry object table");
-    // longest mission in tokens
-    int per_desc = 3 + (s->kind == BB_KIND_LEVELGEN && s->locations ? 4 : 0);
-    int leaf = 2 + per_desc;
-    if (s->kind == BB_KIND_LEVELGEN) {
-        bool putnext = false, has_and = false, has_seq = false;
-        for (int i = 0; i < s->n_action_kinds; i++) if (s->action_kinds[i] == BB_I_PUTNEXT) putnext = true;
-        for (int i = 0; i < s->n_instr_kinds; i++) { if (s->instr_kinds[i] == BB_K_AND) has_and = true; if (s->instr_kinds[i] == BB_K_SEQ) has_seq = true; }
-        if (putnext) leaf = 1 + per_desc + 2 + per_desc;
-        int side = (has_and || has_seq) ? 2 * leaf + 1 : leaf;
-        lp->max_tokens = has_seq ? 2 * side + 2 : side;
-    } else lp->max_tokens = leaf;
-    lp->max_tokens = (lp->max_tokens + 7) / 8 * 8;          // 16-byte rows
-    if (lp->max_tokens > MAXTOK) lp->max_tokens = MAXTOK;
-    // wall template of the empty RoomGrid (Grid.wall_rect per room)
-    for (int y = 0; y < lp->H; y++) {
-        uint32_t row = 0;
-        for (int x = 0; x < lp->W; x++)
-            if (x % (s->room_size - 1) == 0 || y % (s->room_size - 1) == 0) row |= 1u << x;
-        lp->wall_rows[y] = row;
-    }
-    return 0;
+    const char *e = make_level_params(s, lp);
+    return e ? fail("%s", e) : 0;
 }
 
 static void launch_gen(bb_pool *p, int use_list, cudaStream_t st)
@@ -395,7 +351,9 @@ int bb_pool_seed(bb_pool *p, const uint64_t *seeds_host)
     if (!p || !seeds_host) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(p->d_seeds, seeds_host, (size_t)p->n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    // stream-ordered copy: a synchronous cudaMemcpy from pageable memory may return before its last
+    // chunk has landed, and p->stream (non-blocking) is not ordered after the legacy stream
+    CU(cudaMemcpyAsync(p->d_seeds, seeds_host, (size_t)p->n * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
     k_seed<<<(p->n + 255) / 256, 256, 0, p->stream>>>(p->P, p->d_seeds, p->n);
     p->launches++;
     if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 0, p->stream);
@@ -541,7 +499,16 @@ int bb_pool_get_state(bb_pool *p, int32_t env, uint8_t *grid_host, int32_t *info
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
     EnvHot h; ObjTab ot; RngRec r; uint32_t att;
-    CU(cudaMemcpy(grid_host, p->P.grid + (size_t)env * p->lp.cells_pad, p->lp.cells, cudaMemcpyDeviceToHost));
+    {
+        const LevelParams &lp = p->lp;
+        std::vector<uint8_t> raw((size_t)lp.cells_pad);
+        CU(cudaMemcpy(raw.data(), p->P.grid + (size_t)env * lp.cells_pad, raw.size(), cudaMemcpyDeviceToHost));
+        for (int y = 0; y < lp.H; y++)
+            for (int x = 0; x < lp.W; x++) {
+                grid_host[y * lp.W + x] = raw[(size_t)y * lp.rs_g + x];
+                if (raw[(size_t)lp.gt_off + x * lp.rs_t + y] != raw[(size_t)y * lp.rs_g + x]) return fail("internal: row-major / column-major grid copies differ");
+            }
+    }
     CU(cudaMemcpy(&h, p->P.hot + env, sizeof h, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&ot, p->P.obj + env, sizeof ot, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&r, p->P.rng + env, sizeof r, cudaMemcpyDeviceToHost));

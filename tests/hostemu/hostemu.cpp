@@ -11,7 +11,9 @@
 #include <string.h>
 #include <math.h>
 #include <vector>
+#include <stdio.h>
 #include "../../babyai_b200/csrc/env_logic.cuh"
+#include "../../babyai_b200/csrc/level_params.h"
 #include "../../include/babyai_b200.h"
 
 using namespace bb;
@@ -23,32 +25,11 @@ struct HPool {
     std::vector<uint32_t> attempts; std::vector<float> last_reward;
 };
 
-// identical to make_params() in pool.cu (kept in sync by tests/test_hostemu.py::test_params_match on GPU)
 static void make_params(const bb_level_spec *s, LevelParams *lp)
 {
-    memset(lp, 0, sizeof *lp);
-    lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
-    lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
-    lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
-    lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
-    for (int i = 0; i < 4; i++) lp->action_kinds[i] = s->action_kinds[i];
-    for (int i = 0; i < 3; i++) lp->instr_kinds[i] = s->instr_kinds[i];
-    lp->W = (s->room_size - 1) * s->num_cols + 1;
-    lp->H = (s->room_size - 1) * s->num_rows + 1;
-    lp->cells = lp->W * lp->H;
-    lp->cells_pad = (lp->cells + 15) / 16 * 16;
-    lp->nav_time_maze = s->room_size * s->room_size * s->num_rows * s->num_cols;
-    if (s->kind == BB_KIND_LEVELGEN) {
-        double t = ceil(s->locked_room_prob * 4294967296.0);
-        lp->locked_thr = t <= 0 ? 0ull : (uint64_t)t;
-    }
+    const char *e = make_level_params(s, lp);
+    if (e) { fprintf(stderr, "hostemu: %s\n", e); abort(); }
     lp->max_tokens = MAXTOK;
-    for (int y = 0; y < lp->H; y++) {
-        uint32_t row = 0;
-        for (int x = 0; x < lp->W; x++)
-            if (x % (s->room_size - 1) == 0 || y % (s->room_size - 1) == 0) row |= 1u << x;
-        lp->wall_rows[y] = row;
-    }
 }
 
 static void gen_spare(HPool *p, int e)
@@ -120,7 +101,17 @@ void he_tokens(HPool *p, int e, int16_t *out) { memcpy(out, p->live[e].tok.data(
 void he_get_state(HPool *p, int e, uint8_t *grid, int32_t *info)
 {
     Slot &s = p->live[e];
-    memcpy(grid, s.grid.data(), p->lp.cells);
+    const LevelParams &lp = p->lp;
+    for (int y = 0; y < lp.H; y++) memcpy(grid + y * lp.W, s.grid.data() + y * lp.rs_g, lp.W);
+    for (int y = 0; y < lp.H; y++)          // the column-major copy must mirror the row-major one
+        for (int x = 0; x < lp.W; x++)
+            if (s.grid[lp.gt_off + x * lp.rs_t + y] != s.grid[y * lp.rs_g + x]) { fprintf(stderr, "hostemu: G/GT mismatch\n"); abort(); }
+    {   // and the SWAR observation must equal the cell-by-cell one
+        uint32_t w[OBS_WORDS]; uint8_t simple[OBS_BYTES];
+        observe(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, &s.obj), w);
+        observe_simple(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, &s.obj), simple);
+        if (memcmp(w, simple, OBS_BYTES) != 0) { fprintf(stderr, "hostemu: observe != observe_simple\n"); abort(); }
+    }
     info[0] = s.hot.x; info[1] = s.hot.y; info[2] = s.hot.dirflags & 3;
     info[3] = s.hot.carry == NO_OBJ ? 0 : s.obj.tc[s.hot.carry];
     info[4] = s.hot.step_count; info[5] = s.hot.max_steps;

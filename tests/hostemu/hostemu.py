@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, '..', '..'))
 SRC = os.path.join(HERE, 'hostemu.cpp')
 OUT = os.path.join(HERE, 'libhostemu.so')
-DEPS = [SRC, os.path.join(ROOT, 'babyai_b200', 'csrc', 'env_logic.cuh'), os.path.join(ROOT, 'include', 'babyai_b200.h')]
+DEPS = [SRC, os.path.join(ROOT, 'babyai_b200', 'csrc', 'env_logic.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'level_params.h'), os.path.join(ROOT, 'include', 'babyai_b200.h')]
 
 
 def build():
