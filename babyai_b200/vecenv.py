@@ -3,8 +3,8 @@ the C ABI (include/babyai_b200.h):
 
   BabyAIVecEnv      tensor API: everything stays in PyTorch-owned CUDA tensors
   ParallelEnv       drop-in for babyai.rl.utils.penv.ParallelEnv (penv.py:18-59):
-                    reset() -> list of obs dicts, step(actions) -> zip(obs, reward,
-                    done, info) with auto-reset on done
+                    reset() -> list of obs dicts, step(actions) -> (obs, reward, done,
+                    info) sequences (zip(*results)) with auto-reset on done
   ManyEnvs          drop-in for babyai.evaluate.ManyEnvs (evaluate.py:58-81):
                     seed(seeds), reset(), step() that freezes finished envs
   make_envs         what `[gym.make(id) ...; env.seed(100*seed+i)]` builds in
@@ -246,7 +246,9 @@ class ParallelEnv(_HostVec):
             actions = actions.cpu().numpy()
         self.pool.step_host(np.asarray(actions).astype(np.int8), self._obs, self._rew, self._done, self._dir)
         obs = self._obs_list(self._done)
-        return zip(obs, [float(r) for r in self._rew], [bool(d) for d in self._done], [{} for _ in self.envs])
+        # penv.py:51-52 returns zip(*per_env_results): four sequences (obs, reward, done, info)
+        return iter((tuple(obs), tuple(float(r) for r in self._rew), tuple(bool(d) for d in self._done),
+                     tuple({} for _ in self.envs)))
 
 
 class ManyEnvs(_HostVec):
@@ -267,7 +269,9 @@ class ManyEnvs(_HostVec):
             actions = actions.cpu().numpy()
         self.pool.step_host(np.asarray(actions).astype(np.int8), self._obs, self._rew, self._done, self._dir)
         obs = self._obs_list(np.zeros(len(self.envs), bool))
-        return zip(obs, [float(r) for r in self._rew], [bool(d) for d in self._done], [{} for _ in self.envs])
+        # evaluate.py:78 returns zip(*self.results): four sequences
+        return iter((tuple(obs), tuple(float(r) for r in self._rew), tuple(bool(d) for d in self._done),
+                     tuple({} for _ in self.envs)))
 
 
 def preprocess_obss(pool):
