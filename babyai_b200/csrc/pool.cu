@@ -20,6 +20,7 @@
 #include <math.h>
 #include <new>
 #include <vector>
+#include <stdlib.h>
 
 #include "../../include/babyai_b200.h"
 #include "env_logic.cuh"
@@ -31,19 +32,23 @@ using namespace bb;
 struct PoolPtrs {
     // live state of every environment
     uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
-    // spare slot: the next episode's level, pre-generated
-    uint8_t *sgrid; EnvHot *shot; ObjTab *sobj; InstrRec *sins; int16_t *stok; uint8_t *sready;
+    // ring of pre-generated levels: arrays [depth][n]; env e has consumed head[e] and k_gen has produced
+    // tail[e] levels since the last seed(); level number L lives in slot L % depth
+    uint8_t *rgrid; EnvHot *rhot; ObjTab *robj; InstrRec *rins; int16_t *rtok;
+    uint32_t *head, *tail;
     RngRec *rng; uint8_t *locked_room; uint32_t *attempts;
     float *last_reward;
-    int32_t *refill_list; int32_t *refill_count; uint32_t *gen_blocks_done;
+    uint32_t *gen_ticket; uint32_t *gen_blocks_done;
     unsigned long long *warp_counters;   // [num_warps][4]: steps, episodes, successes, errors
+    int32_t depth, n;
 };
 
 constexpr int STEP_THREADS = 128;
 constexpr int STEP_WARPS = STEP_THREADS / 32;
 constexpr int TILE_WORDS = 32 * OBS_BYTES / 4;     // 1176 words = 4704 B per warp
-constexpr int GEN_THREADS = 64;           // 2 warps per block, one warp per environment
+constexpr int GEN_THREADS = 64;                    // 2 warps per block; one warp generates one level at a time
 constexpr int GEN_BLOCKS_PER_SM = 8;
+constexpr int GEN_CHUNK = 8;                       // environments per work ticket
 
 // warp-level staging of 32 observations: see stage_obs_words() in env_logic.cuh
 __device__ __forceinline__ void stage_obs(uint32_t *tile, const uint32_t w[OBS_WORDS], int lane)
@@ -69,25 +74,36 @@ __device__ __forceinline__ void store_tile(const uint32_t *tile, uint8_t *dst, i
     }
 }
 
-// spare slot -> live state (the new episode begins)
-__device__ __forceinline__ void swap_in(const LevelParams &lp, const PoolPtrs &P, int env, EnvHot &h)
+__device__ __forceinline__ LevelOut ring_slot(const LevelParams &lp, const PoolPtrs &P, int env, int slot)
 {
-    const uint4 *sg = reinterpret_cast<const uint4 *>(P.sgrid + (size_t)env * lp.cells_pad);
+    const size_t idx = (size_t)slot * P.n + env;
+    LevelOut o;
+    o.grid = P.rgrid + idx * lp.cells_pad; o.hot = P.rhot + idx; o.obj = P.robj + idx; o.ins = P.rins + idx;
+    o.tok = P.rtok + idx * lp.max_tokens;
+    return o;
+}
+
+// ring slot -> live state (the new episode begins).  k_gen may be running concurrently on other slots, so
+// the slot is read through L2 (ld.global.cg), never through a possibly stale L1 line.
+__device__ __forceinline__ void swap_in(const LevelParams &lp, const PoolPtrs &P, int env, int slot, EnvHot &h)
+{
+    const LevelOut o = ring_slot(lp, P, env, slot);
+    const uint4 *sg = reinterpret_cast<const uint4 *>(o.grid);
     uint4 *lg = reinterpret_cast<uint4 *>(P.grid + (size_t)env * lp.cells_pad);
-    for (int i = 0; i < lp.cells_pad / 16; i++) lg[i] = sg[i];
-    const uint4 *so = reinterpret_cast<const uint4 *>(P.sobj + env);
+    for (int i = 0; i < lp.cells_pad / 16; i++) lg[i] = __ldcg(sg + i);
+    const uint4 *so = reinterpret_cast<const uint4 *>(o.obj);
     uint4 *lo = reinterpret_cast<uint4 *>(P.obj + env);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(ObjTab) / 16); i++) lo[i] = so[i];
-    const uint4 *si = reinterpret_cast<const uint4 *>(P.sins + env);
+    for (int i = 0; i < (int)(sizeof(ObjTab) / 16); i++) lo[i] = __ldcg(so + i);
+    const uint4 *si = reinterpret_cast<const uint4 *>(o.ins);
     uint4 *li = reinterpret_cast<uint4 *>(P.ins + env);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(InstrRec) / 16); i++) li[i] = si[i];
-    const int16_t *st = P.stok + (size_t)env * lp.max_tokens;
-    int16_t *lt = P.tok + (size_t)env * lp.max_tokens;
-    for (int i = 0; i < lp.max_tokens; i++) lt[i] = st[i];
-    h = P.shot[env];
-    P.sready[env] = 0;
+    for (int i = 0; i < (int)(sizeof(InstrRec) / 16); i++) li[i] = __ldcg(si + i);
+    const uint4 *st = reinterpret_cast<const uint4 *>(o.tok);
+    uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
+    for (int i = 0; i < lp.max_tokens / 8; i++) lt[i] = __ldcg(st + i);
+    const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(o.hot));
+    h = *reinterpret_cast<const EnvHot *>(&hv);
 }
 
 template <int ACT_BYTES>
@@ -103,7 +119,7 @@ k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions,
     uint32_t w[OBS_WORDS];
 #pragma unroll
     for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
-    bool need_refill = false, stepped = false, ended = false, succeeded = false, error = false;
+    bool stepped = false, ended = false, succeeded = false, error = false;
     if (valid) {
         EnvHot h = P.hot[env];
         uint8_t *grid = P.grid + (size_t)env * lp.cells_pad;
@@ -127,10 +143,13 @@ k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions,
             }
         }
         if (begin) {
-            if (P.sready[env]) {
-                swap_in(lp, P, env, h);
-                need_refill = mode == BB_MODE_AUTORESET;
-            } else error = true;                       // cannot happen: the host refills before every step
+            const uint32_t hd = P.head[env];
+            const uint32_t tl = __ldcg(P.tail + env);
+            if (tl - hd >= 1u && tl - hd <= (uint32_t)P.depth) {
+                swap_in(lp, P, env, (int)(hd % (uint32_t)P.depth), h);
+                __threadfence();                       // the slot is free for k_gen only after it was copied
+                P.head[env] = hd + 1u;
+            } else error = true;                       // cannot happen: the host orders k_gen before this step
         }
         P.hot[env] = h;
         observe(lp, grid, h.x, h.y, h.dirflags & 3, carry_cell_of(h, P.obj + env), w);
@@ -138,15 +157,7 @@ k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions,
         if (done) done[env] = dn ? 1 : 0;
         if (dirs) dirs[env] = (int8_t)(h.dirflags & 3);
     }
-    // ---- compaction of finished episodes into the refill list (warp ballot) ------
-    const uint32_t m_refill = __ballot_sync(0xFFFFFFFFu, need_refill);
-    if (m_refill) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(P.refill_count, __popc(m_refill));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (need_refill) P.refill_list[base + __popc(m_refill & ((1u << lane) - 1u))] = env;
-    }
-    // ---- counters: one slot per warp, no atomics ---------------------------------
+    // ---- counters: warp ballots, one slot per warp, no atomics -------------------
     const uint32_t m_step = __ballot_sync(0xFFFFFFFFu, stepped), m_end = __ballot_sync(0xFFFFFFFFu, ended);
     const uint32_t m_succ = __ballot_sync(0xFFFFFFFFu, succeeded), m_err = __ballot_sync(0xFFFFFFFFu, error);
     if (lane == 0) {
@@ -162,44 +173,57 @@ k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions,
     if (nv > 0) store_tile(tile, obs + (size_t)env0 * OBS_BYTES, lane, nv);
 }
 
-// Level generation: ONE WARP PER ENVIRONMENT.  Generation is a long, branchy,
-// data-dependent rejection-sampling program; with one lane per env the 32 lanes of
-// a warp diverge onto 32 different paths and run serially (measured round 1:
-// 3.0 active lanes per instruction, 525 us per step).  Instead every lane of the
-// warp runs the same env with identical control flow: no divergence, the Philox
-// blocks are computed 32 at a time across the lanes (Rng::u32), and lane 0 alone
-// commits the stores.  use_list: entries of the refill list; else every env whose
-// spare slot is empty.
+// Level generation, decoupled from the step: tops every environment's ring up to `target` levels.
+//
+// ONE WARP PER ENVIRONMENT.  Generation is a long, branchy, data-dependent rejection-sampling program;
+// with one lane per env the 32 lanes of a warp run 32 different paths serially (measured in round 1:
+// 3.0 active lanes per instruction).  Instead every lane of the warp runs the same env with identical
+// control flow: no divergence, the Philox blocks are computed 32 at a time across the lanes (Rng::u32),
+// the lanes split the grid rendering, and lane 0 commits the scalar records.
+// Work distribution: tickets of GEN_CHUNK consecutive envs from a global counter (the slowest
+// generations are a geometric tail of rejected attempts, so static assignment would wait for them).
 __global__ void __launch_bounds__(GEN_THREADS)
-k_gen(const LevelParams lp, const PoolPtrs P, const int use_list, const int n)
+k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
 {
     const int lane = threadIdx.x & 31;
-    const int warps_per_block = GEN_THREADS / 32;
-    const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const int nw = gridDim.x * warps_per_block;
-    const int count = use_list ? *P.refill_count : n;
-    for (int idx = gw; idx < count; idx += nw) {
-        int env = use_list ? P.refill_list[idx] : idx;
-        if (!use_list && P.sready[env]) continue;                 // warp-uniform
-        LevelOut o;
-        o.grid = P.sgrid + (size_t)env * lp.cells_pad; o.hot = P.shot + env; o.obj = P.sobj + env;
-        o.ins = P.sins + env; o.tok = P.stok + (size_t)env * lp.max_tokens;
-        RngRec r = P.rng[env];
-        uint8_t lr = P.locked_room[env];
-        int att = generate_level(lp, o, &r, &lr);
-        __syncwarp();
-        if (lane == 0) {
-            P.rng[env] = r; P.locked_room[env] = lr; P.attempts[env] += (uint32_t)att;
-            P.sready[env] = 1;
+    const uint32_t nchunks = (uint32_t)((n + GEN_CHUNK - 1) / GEN_CHUNK);
+    const uint32_t D = (uint32_t)P.depth;
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(P.gen_ticket, 1u);
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        if (c >= nchunks) break;
+        const int e_l = (int)c * GEN_CHUNK + (lane & (GEN_CHUNK - 1));
+        uint32_t tl = 0; int missing = 0;
+        if (lane < GEN_CHUNK && e_l < n) {
+            const uint32_t hd = __ldcg(P.head + e_l);          // k_step may be consuming concurrently
+            tl = P.tail[e_l];
+            missing = target - (int)(tl - hd);
+        }
+        uint32_t need = __ballot_sync(0xFFFFFFFFu, missing > 0);
+        while (need) {                                         // warp-uniform loop
+            const int b = __ffs((int)need) - 1;
+            need &= need - 1;
+            const int env = (int)c * GEN_CHUNK + b;
+            const int m = __shfl_sync(0xFFFFFFFFu, missing, b);
+            const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, tl, b);
+            RngRec r = P.rng[env];
+            uint8_t lr = P.locked_room[env];
+            int att = 0;
+            for (int i = 0; i < m; i++) {
+                const LevelOut o = ring_slot(lp, P, env, (int)((t0 + (uint32_t)i) % D));
+                att += generate_level(lp, o, &r, &lr);
+                __syncwarp();
+                if (lane == 0) { __threadfence(); P.tail[env] = t0 + (uint32_t)i + 1u; }   // publish the slot
+            }
+            if (lane == 0) { P.rng[env] = r; P.locked_room[env] = lr; P.attempts[env] += (uint32_t)att; }
         }
     }
-    if (use_list) {                                   // last block out resets the list for the next step
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            unsigned int prev = atomicAdd(P.gen_blocks_done, 1u);
-            if (prev == gridDim.x - 1) { *P.refill_count = 0; *P.gen_blocks_done = 0; __threadfence(); }
-        }
+    __syncthreads();                                           // last block out resets the ticket counter
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(P.gen_blocks_done, 1u);
+        if (prev == gridDim.x - 1) { *P.gen_ticket = 0; *P.gen_blocks_done = 0; __threadfence(); }
     }
 }
 
@@ -210,7 +234,7 @@ __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
     RngRec r; r.seed = seeds[env]; r.draws = 0;
     P.rng[env] = r;
     P.locked_room[env] = 0xFF;
-    P.sready[env] = 0;
+    P.tail[env] = P.head[env];                                 // empty ring: old levels belong to the old stream
     P.attempts[env] = 0;
 }
 
@@ -224,13 +248,24 @@ static int fail(const char *fmt, const char *a = "")
 #define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail("CUDA error: %s", cudaGetErrorString(_e)); } while (0)
 
 struct GraphKey { const void *a, *o, *r, *d, *q; int T; int mode; };
+constexpr int MAX_GEN_EVENTS = 40;
 
 struct bb_pool {
     LevelParams lp;
     PoolPtrs P;
     int n, device, mode, num_warps, step_blocks, gen_blocks;
+    // level supply schedule: ring depth D; k_gen is enqueued on gen_stream after every G-th step and
+    // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
+    // k_gen launched at >= s - D
+    int D, G, nev;
+    long long rel;
+    cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
+    cudaStream_t gen_stream;       // level generation runs here, concurrently with the steps
+    cudaEvent_t ev_fork, ev_join;
+    cudaEvent_t gen_ev[MAX_GEN_EVENTS];
+    long long gens_enqueued;       // k index of the next k_gen in the current epoch
+    bool gen_outstanding;
     std::vector<void *> allocs;
-    cudaStream_t stream;           // internal stream: host-buffer API and graph capture
     // host-buffer API staging
     int8_t *h_act; uint8_t *h_obs; float *h_rew; uint8_t *h_done; int8_t *h_dir;      // pinned
     int8_t *d_act; uint8_t *d_obs; float *d_rew; uint8_t *d_done; int8_t *d_dir;
@@ -259,9 +294,10 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
     return e ? fail("%s", e) : 0;
 }
 
-static void launch_gen(bb_pool *p, int use_list, cudaStream_t st)
+static void launch_gen(bb_pool *p, cudaStream_t st)
 {
-    k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, use_list, p->n);
+    const int target = p->mode == BB_MODE_AUTORESET ? p->D : 1;
+    k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
     p->launches++;
 }
 
@@ -273,6 +309,45 @@ static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8
     else
         k_step<1><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
     p->launches++;
+}
+
+// ---- level-supply schedule ---------------------------------------------------------------------
+// Invariant at a "sync point" (rel = 0): every k_gen enqueued so far is ordered before the next step
+// and the most recent one was enqueued at relative step >= -G, i.e. every ring held >= D - G + ... levels.
+// A k_gen that ran to completion after step t leaves every ring full with respect to the heads it saw,
+// and one env consumes at most one level per step, so step s is safe once a k_gen enqueued at t >= s - D
+// has finished.
+static int sched_before_step(bb_pool *p, long long s, cudaStream_t st)
+{
+    if (p->mode != BB_MODE_AUTORESET) return 0;
+    const long long need = s - p->D;                 // a finished k_gen enqueued at >= need is required
+    if (need <= -(long long)p->G) return 0;          // the sync-point state suffices
+    const long long k = need <= 0 ? 0 : (need + p->G - 1) / p->G;
+    CU(cudaStreamWaitEvent(st, p->gen_ev[k % p->nev], 0));
+    return 0;
+}
+static int sched_after_step(bb_pool *p, long long s, cudaStream_t st)
+{
+    if (p->mode != BB_MODE_AUTORESET) return 0;
+    if (s % p->G != 0) return 0;
+    const long long k = s / p->G;
+    CU(cudaEventRecord(p->ev_fork, st));
+    CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
+    launch_gen(p, p->gen_stream);
+    CU(cudaEventRecord(p->gen_ev[k % p->nev], p->gen_stream));
+    p->gen_outstanding = true;
+    return 0;
+}
+// make `st` wait for every k_gen enqueued so far; afterwards rel = 0 is a sync point again
+static int sched_join(bb_pool *p, cudaStream_t st)
+{
+    if (p->gen_outstanding) {
+        CU(cudaEventRecord(p->ev_join, p->gen_stream));
+        CU(cudaStreamWaitEvent(st, p->ev_join, 0));
+        p->gen_outstanding = false;
+    }
+    p->rel = 0;
+    return 0;
 }
 
 extern "C" {
@@ -295,19 +370,30 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
-        int want = (n_envs + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);
+        int want = ((n_envs + GEN_CHUNK - 1) / GEN_CHUNK + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);
         int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
     }
+    // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
+    // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
+    p->D = p->lp.cells_pad <= 256 ? 32 : 8;
+    if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 64) p->D = d; }
+    p->G = p->D >= 8 ? p->D / 8 : 1;
+    if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
+    p->nev = p->D / p->G + 3;
+    if (p->nev > MAX_GEN_EVENTS) { delete p; return fail("ring depth / generation period too large"); }
+    p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
     p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr;
     const LevelParams &lp = p->lp;
-    const size_t n = (size_t)n_envs;
+    const size_t n = (size_t)n_envs, D = (size_t)p->D;
     PoolPtrs &P = p->P;
+    P.depth = p->D; P.n = n_envs;
     if (dalloc(p, &P.grid, n * lp.cells_pad) || dalloc(p, &P.hot, n) || dalloc(p, &P.obj, n) || dalloc(p, &P.ins, n) ||
-        dalloc(p, &P.tok, n * lp.max_tokens) || dalloc(p, &P.sgrid, n * lp.cells_pad) || dalloc(p, &P.shot, n) ||
-        dalloc(p, &P.sobj, n) || dalloc(p, &P.sins, n) || dalloc(p, &P.stok, n * lp.max_tokens) || dalloc(p, &P.sready, n) ||
+        dalloc(p, &P.tok, n * lp.max_tokens) || dalloc(p, &P.rgrid, D * n * lp.cells_pad) || dalloc(p, &P.rhot, D * n) ||
+        dalloc(p, &P.robj, D * n) || dalloc(p, &P.rins, D * n) || dalloc(p, &P.rtok, D * n * lp.max_tokens) ||
+        dalloc(p, &P.head, n) || dalloc(p, &P.tail, n) ||
         dalloc(p, &P.rng, n) || dalloc(p, &P.locked_room, n) || dalloc(p, &P.attempts, n) || dalloc(p, &P.last_reward, n) ||
-        dalloc(p, &P.refill_list, n) || dalloc(p, &P.refill_count, 4) || dalloc(p, &P.gen_blocks_done, 4) ||
+        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_blocks_done, 4) ||
         dalloc(p, &P.warp_counters, (size_t)p->num_warps * 4) ||
         dalloc(p, &p->d_act, n) || dalloc(p, &p->d_obs, n * OBS_BYTES) || dalloc(p, &p->d_rew, n) || dalloc(p, &p->d_done, n) ||
         dalloc(p, &p->d_dir, n) || dalloc(p, &p->d_seeds, n)) {
@@ -316,6 +402,10 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     }
     CU(cudaMemset(P.locked_room, 0xFF, n));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&p->gen_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < p->nev; i++) CU(cudaEventCreateWithFlags(&p->gen_ev[i], cudaEventDisableTiming));
     CU(cudaMallocHost((void **)&p->h_act, n));
     CU(cudaMallocHost((void **)&p->h_obs, n * OBS_BYTES));
     CU(cudaMallocHost((void **)&p->h_rew, n * sizeof(float)));
@@ -335,6 +425,9 @@ int bb_pool_destroy(bb_pool *p)
     cudaDeviceSynchronize();
     if (p->graph) cudaGraphExecDestroy(p->graph);
     for (int i = 0; i < 3; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    for (int i = 0; i < p->nev; i++) if (p->gen_ev[i]) cudaEventDestroy(p->gen_ev[i]);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (void *a : p->allocs) cudaFree(a);
     if (p->h_act) cudaFreeHost(p->h_act);
     if (p->h_obs) cudaFreeHost(p->h_obs);
@@ -342,6 +435,7 @@ int bb_pool_destroy(bb_pool *p)
     if (p->h_done) cudaFreeHost(p->h_done);
     if (p->h_dir) cudaFreeHost(p->h_dir);
     if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->gen_stream) cudaStreamDestroy(p->gen_stream);
     delete p;
     return 0;
 }
@@ -351,12 +445,13 @@ int bb_pool_seed(bb_pool *p, const uint64_t *seeds_host)
     if (!p || !seeds_host) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
+    p->gen_outstanding = false; p->rel = 0;
     // stream-ordered copy: a synchronous cudaMemcpy from pageable memory may return before its last
     // chunk has landed, and p->stream (non-blocking) is not ordered after the legacy stream
     CU(cudaMemcpyAsync(p->d_seeds, seeds_host, (size_t)p->n * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
     k_seed<<<(p->n + 255) / 256, 256, 0, p->stream>>>(p->P, p->d_seeds, p->n);
     p->launches++;
-    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 0, p->stream);
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, p->stream);
     CU(cudaStreamSynchronize(p->stream));
     CU(cudaGetLastError());
     return 0;
@@ -367,8 +462,9 @@ int bb_pool_set_mode(bb_pool *p, int32_t mode)
     if (!p || (mode != BB_MODE_AUTORESET && mode != BB_MODE_FREEZE)) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
+    p->gen_outstanding = false; p->rel = 0;
     p->mode = mode;
-    if (mode == BB_MODE_AUTORESET) { launch_gen(p, 0, p->stream); CU(cudaStreamSynchronize(p->stream)); }
+    if (mode == BB_MODE_AUTORESET) { launch_gen(p, p->stream); CU(cudaStreamSynchronize(p->stream)); }
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
     return 0;
 }
@@ -378,9 +474,10 @@ int bb_pool_reset(bb_pool *p, uint8_t *obs_dev, int8_t *dir_dev, void *stream)
     if (!p || !obs_dev) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    launch_gen(p, 0, st);                              // make sure every spare slot holds a level
+    if (sched_join(p, st)) return 1;
+    launch_gen(p, st);                                 // make sure every ring holds a level
     launch_step(p, nullptr, 1, obs_dev, nullptr, nullptr, dir_dev, 1, st);
-    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, st);   // refill what the reset consumed
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, st);      // rings full again: a sync point
     CU(cudaGetLastError());
     return 0;
 }
@@ -392,8 +489,10 @@ int bb_pool_step(bb_pool *p, const void *actions_dev, int32_t action_bytes, uint
     if (action_bytes != 1 && action_bytes != 8) return fail("action_bytes must be 1 or 8");
     CU(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (sched_before_step(p, p->rel, st)) return 1;
     launch_step(p, actions_dev, action_bytes, obs_dev, reward_dev, done_dev, dir_dev, 0, st);
-    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, st);
+    if (sched_after_step(p, p->rel, st)) return 1;
+    p->rel++;
     CU(cudaGetLastError());
     return 0;
 }
@@ -404,10 +503,12 @@ int bb_pool_step_timed(bb_pool *p, const void *actions_dev, int32_t action_bytes
     if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || !ms_step || !ms_gen) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     if (!p->ev[0]) for (int i = 0; i < 3; i++) CU(cudaEventCreate(&p->ev[i]));
+    if (sched_join(p, p->stream)) return 1;
+    launch_gen(p, p->stream);                           // rings full before the timed pair
     CU(cudaEventRecord(p->ev[0], p->stream));
     launch_step(p, actions_dev, action_bytes, obs_dev, reward_dev, done_dev, dir_dev, 0, p->stream);
     CU(cudaEventRecord(p->ev[1], p->stream));
-    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, p->stream);
+    launch_gen(p, p->stream);                           // one step's worth of refills, timed in isolation
     CU(cudaEventRecord(p->ev[2], p->stream));
     CU(cudaEventSynchronize(p->ev[2]));
     CU(cudaEventElapsedTime(ms_step, p->ev[0], p->ev[1]));
@@ -420,26 +521,38 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
 {
     if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || T < 1) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
+    cudaStream_t user = (cudaStream_t)stream;
     GraphKey key = { actions_dev, obs_dev, reward_dev, done_dev, dir_dev, T, p->mode };
     if (!p->graph || memcmp(&key, &p->gkey, sizeof key) != 0) {
         if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
         cudaGraph_t g;
         const size_t n = (size_t)p->n;
-        long long l0 = p->launches;
+        const long long l0 = p->launches;
+        const bool saved_out = p->gen_outstanding;
+        // the generation branch forks from and joins back into the origin stream inside the capture
         CU(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        p->gen_outstanding = false;
         for (int t = 0; t < T; t++) {
+            if (sched_before_step(p, t, p->stream)) return 1;
             launch_step(p, actions_dev + t * n, 1, obs_dev + t * n * OBS_BYTES, reward_dev + t * n, done_dev + t * n,
                         dir_dev ? dir_dev + t * n : nullptr, 0, p->stream);
-            if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, p->stream);
+            if (sched_after_step(p, t, p->stream)) return 1;
+        }
+        if (p->gen_outstanding) {
+            CU(cudaEventRecord(p->ev_join, p->gen_stream));
+            CU(cudaStreamWaitEvent(p->stream, p->ev_join, 0));
         }
         CU(cudaStreamEndCapture(p->stream, &g));
+        p->gen_outstanding = saved_out;
         p->launches = l0;
         CU(cudaGraphInstantiate(&p->graph, g, 0));
         CU(cudaGraphDestroy(g));
         p->gkey = key;
     }
-    CU(cudaGraphLaunch(p->graph, (cudaStream_t)stream));
-    p->launches += (long long)T * (p->mode == BB_MODE_AUTORESET ? 2 : 1);
+    if (sched_join(p, user)) return 1;                  // per-step k_gens still in flight come first
+    CU(cudaGraphLaunch(p->graph, user));
+    p->rel = 0;                                         // the graph ends with its k_gens joined: a sync point
+    p->launches += (long long)T + (p->mode == BB_MODE_AUTORESET ? (T + p->G - 1) / p->G : 0);
     return 0;
 }
 
@@ -451,12 +564,14 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
     const size_t n = (size_t)p->n;
     memcpy(p->h_act, actions_host, n);
     CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, p->stream));
+    if (sched_before_step(p, p->rel, p->stream)) return 1;
     launch_step(p, p->d_act, 1, p->d_obs, p->d_rew, p->d_done, p->d_dir, 0, p->stream);
+    if (sched_after_step(p, p->rel, p->stream)) return 1;
+    p->rel++;
     CU(cudaMemcpyAsync(p->h_obs, p->d_obs, n * OBS_BYTES, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(p->h_rew, p->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaMemcpyAsync(p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
-    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, 1, p->stream);   // overlaps the copies' tail on the host side
     CU(cudaStreamSynchronize(p->stream));
     memcpy(obs_host, p->h_obs, n * OBS_BYTES);
     memcpy(reward_host, p->h_rew, n * sizeof(float));
