@@ -212,20 +212,30 @@ struct LevelOut {           // where one generated level is written (live or spa
     uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
 };
 
-struct GenCtx {
-    Rng rng;
+// Working arrays of one generation.  Device: ONE copy per warp in shared memory (all 32 lanes run the
+// same environment in lockstep and would otherwise each keep a private copy in local memory: 40 KB of
+// L1 per warp, which round 1 showed evicts the step kernel's working set).  Host build: on the stack.
+struct GenMem {
     uint32_t occ[MAXH];            // walls + doors + objects, one bit per cell
     uint32_t doorcell[MAXH];       // door cells (subset of occ)
+    uint32_t pass[MAXH], fill[MAXH];  // reachability flood fill
     uint8_t door_y_right[MAXROOMS];   // Room.door_pos[0].y of room r
     uint8_t door_x_down[MAXROOMS];    // Room.door_pos[1].x of room r
+    // instruction being built
+    int leaf_kind[4]; int desc_type[8], desc_color[8], desc_loc[8];
+    uint32_t desc_mask[8];
+    int16_t tok[MAXTOK];
+    ObjTab obj;                    // object table under construction (copied to the slot at the end)
+};
+
+struct GenCtx {
+    Rng rng;
+    GenMem *m;
     uint32_t door_right, door_down;   // bit r: a door exists in room r's right / down slot
     uint32_t room_locked;             // bit r: Room.locked
     int nobj;
     int ax, ay, adir; bool agent_placed;
     int locked_door;                  // object id of the locked door or -1
-    // instruction being built
-    int leaf_kind[4]; int desc_type[8], desc_color[8], desc_loc[8];
-    uint32_t desc_mask[8];
     int root_kind, side_and;
     // LevelGen.locked_room (persists across episodes, levelgen.py:284)
     int locked_room; bool locked_room_fresh;
@@ -238,12 +248,12 @@ enum : int { GEN_OK = 0, GEN_REJECT = 1, GEN_RECURSION = 2 };
 BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
 {
     const int S = lp.room_size, R = lp.num_rows, C = lp.num_cols;
-    for (int y = 0; y < lp.H; y++) { g.occ[y] = lp.wall_rows[y]; g.doorcell[y] = 0; }
+    for (int y = 0; y < lp.H; y++) { g.m->occ[y] = lp.wall_rows[y]; g.m->doorcell[y] = 0; }
     for (int j = 0; j < R; j++)
         for (int i = 0; i < C; i++) {
             int r = j * C + i, tx = i * (S - 1), ty = j * (S - 1);
-            if (i < C - 1) g.door_y_right[r] = (uint8_t)g.rng.randint(ty + 1, ty + S - 1);
-            if (j < R - 1) g.door_x_down[r] = (uint8_t)g.rng.randint(tx + 1, tx + S - 1);
+            if (i < C - 1) g.m->door_y_right[r] = (uint8_t)g.rng.randint(ty + 1, ty + S - 1);
+            if (j < R - 1) g.m->door_x_down[r] = (uint8_t)g.rng.randint(tx + 1, tx + S - 1);
         }
     g.door_right = g.door_down = g.room_locked = 0;
     g.nobj = 0;
@@ -266,7 +276,7 @@ BB_HD int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_t
         tries++;
         int x = g.rng.randint(tx, hx);
         int y = g.rng.randint(ty, hy);
-        if ((g.occ[y] >> x) & 1u) continue;
+        if ((g.m->occ[y] >> x) & 1u) continue;
         if (g.agent_placed && x == g.ax && y == g.ay) continue;
         if (reject_next_to && iabs(g.ax - x) + iabs(g.ay - y) < 2) continue;
         ox = x; oy = y;
@@ -280,8 +290,8 @@ BB_HD int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int 
     int x, y;
     id = g.nobj++;                      // the Python object exists even if placement then fails
     BB_TRY(g_place(lp, g, room, true, x, y));
-    o.obj->x[id] = (uint8_t)x; o.obj->y[id] = (uint8_t)y; o.obj->tc[id] = (uint8_t)(type | (color << 3));
-    g.occ[y] |= 1u << x;
+    g.m->obj.x[id] = (uint8_t)x; g.m->obj.y[id] = (uint8_t)y; g.m->obj.tc[id] = (uint8_t)(type | (color << 3));
+    g.m->occ[y] |= 1u << x;
     return GEN_OK;
 }
 
@@ -308,12 +318,12 @@ BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ro
     const int S = lp.room_size;
     int owner = k == 2 ? room - 1 : k == 3 ? room - lp.num_cols : room;
     int x, y;
-    if (k == 0 || k == 2) { x = (owner % lp.num_cols) * (S - 1) + S - 1; y = g.door_y_right[owner]; g.door_right |= 1u << owner; }
-    else { x = g.door_x_down[owner]; y = (owner / lp.num_cols) * (S - 1) + S - 1; g.door_down |= 1u << owner; }
+    if (k == 0 || k == 2) { x = (owner % lp.num_cols) * (S - 1) + S - 1; y = g.m->door_y_right[owner]; g.door_right |= 1u << owner; }
+    else { x = g.m->door_x_down[owner]; y = (owner / lp.num_cols) * (S - 1) + S - 1; g.door_down |= 1u << owner; }
     if (locked) g.room_locked |= 1u << room; else g.room_locked &= ~(1u << room);   // room.locked = locked
     int id = g.nobj++;
-    o.obj->x[id] = (uint8_t)x; o.obj->y[id] = (uint8_t)y; o.obj->tc[id] = (uint8_t)(T_DOOR | (color << 3));
-    g.doorcell[y] |= 1u << x;
+    g.m->obj.x[id] = (uint8_t)x; g.m->obj.y[id] = (uint8_t)y; g.m->obj.tc[id] = (uint8_t)(T_DOOR | (color << 3));
+    g.m->doorcell[y] |= 1u << x;
     if (locked) g.locked_door = id;
     return id;
 }
@@ -332,8 +342,8 @@ BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g)
         g.adir = g.rng.randint(0, 4);
         int fx = x + dir_dx(g.adir), fy = y + dir_dy(g.adir);
         // front cell must be empty or a wall (a door is neither)
-        bool occupied = (g.occ[fy] >> fx) & 1u;
-        bool wall = ((lp.wall_rows[fy] >> fx) & 1u) && !((g.doorcell[fy] >> fx) & 1u);
+        bool occupied = (g.m->occ[fy] >> fx) & 1u;
+        bool wall = ((lp.wall_rows[fy] >> fx) & 1u) && !((g.m->doorcell[fy] >> fx) & 1u);
         if (!occupied || wall) break;
     }
     return GEN_OK;
@@ -394,9 +404,9 @@ BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o,
 // reachable if it is in F or 4-adjacent to F; every object and door must be.
 BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
 {
-    uint32_t pass[MAXH], f[MAXH];
+    uint32_t *pass = g.m->pass, *f = g.m->fill;
     const uint32_t full = (lp.W >= 32) ? 0xFFFFFFFFu : ((1u << lp.W) - 1u);
-    for (int y = 0; y < lp.H; y++) { pass[y] = (~g.occ[y] | g.doorcell[y]) & full; f[y] = 0; }
+    for (int y = 0; y < lp.H; y++) { pass[y] = (~g.m->occ[y] | g.m->doorcell[y]) & full; f[y] = 0; }
     f[g.ay] = 1u << g.ax;
     for (;;) {
         bool changed = false;
@@ -417,7 +427,7 @@ BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
         uint32_t near = v | (v << 1) | (v >> 1);
         if (y > 0) near |= f[y - 1];
         if (y + 1 < lp.H) near |= f[y + 1];
-        uint32_t things = (g.occ[y] & ~lp.wall_rows[y]) | g.doorcell[y];   // non-wall, non-empty cells
+        uint32_t things = (g.m->occ[y] & ~lp.wall_rows[y]) | g.m->doorcell[y];   // non-wall, non-empty cells
         if (things & ~near) return GEN_REJECT;
     }
     return GEN_OK;
@@ -432,11 +442,11 @@ BB_HD uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &o
     const int d1x = dir_dx(g.adir), d1y = dir_dy(g.adir), d2x = -d1y, d2y = d1x;
     uint32_t m = 0;
     for (int k = 0; k < g.nobj; k++) {
-        int tc = o.obj->tc[k];
+        int tc = g.m->obj.tc[k];
         if (type != ANY_TYPE && (tc & 7) != type) continue;
         if (color != ANY && (tc >> 3) != color) continue;
         if (loc != LOC_NONE) {
-            int x = o.obj->x[k], y = o.obj->y[k];
+            int x = g.m->obj.x[k], y = g.m->obj.y[k];
             if (x < rtx || y < rty || x >= rtx + S || y >= rty + S) continue;   // Room.pos_inside
             int vx = x - g.ax, vy = y - g.ay;
             int dot1 = vx * d1x + vy * d1y, dot2 = vx * d2x + vy * d2y;
@@ -470,12 +480,12 @@ BB_HD int g_rand_obj(const LevelParams &lp, GenCtx &g, const LevelOut &o, int nt
             bool outside = false;
             for (uint32_t mm = m; mm; mm &= mm - 1) {
                 int k = ffs32(mm);
-                int x = o.obj->x[k], y = o.obj->y[k];
+                int x = g.m->obj.x[k], y = g.m->obj.y[k];
                 if (x < ltx || y < lty || x >= ltx + S || y >= lty + S) outside = true;
             }
             if (!outside) continue;
         }
-        g.desc_type[d] = type; g.desc_color[d] = color; g.desc_loc[d] = loc; g.desc_mask[d] = m;
+        g.m->desc_type[d] = type; g.m->desc_color[d] = color; g.m->desc_loc[d] = loc; g.m->desc_mask[d] = m;
         return GEN_OK;
     }
 }
@@ -484,7 +494,7 @@ BB_HD int g_rand_obj(const LevelParams &lp, GenCtx &g, const LevelOut &o, int nt
 BB_HD int g_rand_action(const LevelParams &lp, GenCtx &g, const LevelOut &o, int leaf)
 {
     int action = lp.action_kinds[g.rng.randint(0, lp.n_action_kinds)];
-    g.leaf_kind[leaf] = action;
+    g.m->leaf_kind[leaf] = action;
     if (action == I_GOTO) return g_rand_obj(lp, g, o, 4, 2 * leaf);
     if (action == I_PICKUP) return g_rand_obj(lp, g, o, 3, 2 * leaf);
     if (action == I_OPEN) return g_rand_obj(lp, g, o, 1, 2 * leaf);
@@ -518,18 +528,18 @@ BB_HD int g_rand_instr(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 BB_HD int g_validate(const LevelParams &lp, const GenCtx &g, const LevelOut &o)
 {
     const bool unblocking = lp.kind == KIND_LEVELGEN && lp.unblocking;
-    const int locked_color = g.locked_door >= 0 ? (o.obj->tc[g.locked_door] >> 3) : -1;
+    const int locked_color = g.locked_door >= 0 ? (g.m->obj.tc[g.locked_door] >> 3) : -1;
     for (int leaf = 0; leaf < 4; leaf++) {
-        int kind = g.leaf_kind[leaf];
+        int kind = g.m->leaf_kind[leaf];
         if (kind == I_NONE) continue;
         if (kind == I_PUTNEXT) {
-            uint32_t mv = g.desc_mask[2 * leaf], fx = g.desc_mask[2 * leaf + 1];
+            uint32_t mv = g.m->desc_mask[2 * leaf], fx = g.m->desc_mask[2 * leaf + 1];
             if (mv & fx) return GEN_REJECT;
             for (uint32_t a = mv; a; a &= a - 1) {           // objs_next(), verifier.py:379-391
                 int ia = ffs32(a);
                 for (uint32_t b = fx; b; b &= b - 1) {
                     int ib = ffs32(b);
-                    if (iabs((int)o.obj->x[ia] - (int)o.obj->x[ib]) + iabs((int)o.obj->y[ia] - (int)o.obj->y[ib]) == 1)
+                    if (iabs((int)g.m->obj.x[ia] - (int)g.m->obj.x[ib]) + iabs((int)g.m->obj.y[ia] - (int)g.m->obj.y[ib]) == 1)
                         return GEN_REJECT;
                 }
             }
@@ -537,7 +547,7 @@ BB_HD int g_validate(const LevelParams &lp, const GenCtx &g, const LevelOut &o)
         if (unblocking && locked_color >= 0) {
             int nd = kind == I_PUTNEXT ? 2 : 1;
             for (int q = 0; q < nd; q++)
-                if (g.desc_type[2 * leaf + q] == T_KEY && g.desc_color[2 * leaf + q] == locked_color) return GEN_REJECT;
+                if (g.m->desc_type[2 * leaf + q] == T_KEY && g.m->desc_color[2 * leaf + q] == locked_color) return GEN_REJECT;
         }
     }
     return GEN_OK;
@@ -563,7 +573,7 @@ BB_HD int g_add_locked_room(const LevelParams &lp, GenCtx &g, const LevelOut &o)
         int room = j * lp.num_cols + i;
         if (room == g.locked_room) continue;
         int id;
-        BB_TRY(g_add_object(lp, g, o, room, T_KEY, o.obj->tc[door] >> 3, id));
+        BB_TRY(g_add_object(lp, g, o, room, T_KEY, g.m->obj.tc[door] >> 3, id));
         break;
     }
     return GEN_OK;
@@ -571,18 +581,18 @@ BB_HD int g_add_locked_room(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 
 BB_HD void g_single_desc(GenCtx &g, const LevelParams &lp, const LevelOut &o, int kind, int obj_id)
 {
-    int tc = o.obj->tc[obj_id];
+    int tc = g.m->obj.tc[obj_id];
     g.root_kind = R_SINGLE; g.side_and = 0;
-    g.leaf_kind[0] = kind;
-    g.desc_type[0] = tc & 7; g.desc_color[0] = tc >> 3; g.desc_loc[0] = LOC_NONE;
-    g.desc_mask[0] = g_match(lp, g, o, tc & 7, tc >> 3, LOC_NONE);
+    g.m->leaf_kind[0] = kind;
+    g.m->desc_type[0] = tc & 7; g.m->desc_color[0] = tc >> 3; g.m->desc_loc[0] = LOC_NONE;
+    g.m->desc_mask[0] = g_match(lp, g, o, tc & 7, tc >> 3, LOC_NONE);
 }
 
 // gen_mission of the three level families
 BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 {
-    for (int k = 0; k < 4; k++) g.leaf_kind[k] = I_NONE;
-    for (int k = 0; k < 8; k++) { g.desc_mask[k] = 0; g.desc_type[k] = ANY_TYPE; g.desc_color[k] = ANY; g.desc_loc[k] = LOC_NONE; }
+    for (int k = 0; k < 4; k++) g.m->leaf_kind[k] = I_NONE;
+    for (int k = 0; k < 8; k++) { g.m->desc_mask[k] = 0; g.m->desc_type[k] = ANY_TYPE; g.m->desc_color[k] = ANY; g.m->desc_loc[k] = LOC_NONE; }
     g.side_and = 0; g.root_kind = R_SINGLE;
     if (lp.kind == KIND_REDBALL) {                 // iclr19_levels.py:26-37, 55-63
         int ball, first;
@@ -590,7 +600,7 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
         BB_TRY(g_add_object(lp, g, o, 0, T_BALL, C_RED, ball));
         BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first));
         if (lp.grey_dists)
-            for (int k = first; k < g.nobj; k++) o.obj->tc[k] = (uint8_t)((o.obj->tc[k] & 7) | (C_GREY << 3));
+            for (int k = first; k < g.nobj; k++) g.m->obj.tc[k] = (uint8_t)((g.m->obj.tc[k] & 7) | (C_GREY << 3));
         BB_TRY(g_check_reachable(lp, g));
         g_single_desc(g, lp, o, I_GOTO, ball);
         return GEN_OK;
@@ -623,11 +633,11 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 // ---- mission tokens (Instr.surface / ObjDesc.surface, verifier.py:64-94 ...) --
 BB_HD int tok_desc(const GenCtx &g, int d, int16_t *tok, int n)
 {
-    tok[n++] = popc32(g.desc_mask[d]) > 1 ? W_A : W_THE;
-    if (g.desc_color[d] != ANY) tok[n++] = (int16_t)(W_RED + g.desc_color[d]);
-    int t = g.desc_type[d];
+    tok[n++] = popc32(g.m->desc_mask[d]) > 1 ? W_A : W_THE;
+    if (g.m->desc_color[d] != ANY) tok[n++] = (int16_t)(W_RED + g.m->desc_color[d]);
+    int t = g.m->desc_type[d];
     tok[n++] = (int16_t)(t == ANY_TYPE ? W_OBJECT : t == T_BOX ? W_BOX : t == T_BALL ? W_BALL : t == T_KEY ? W_KEY : W_DOOR);
-    int loc = g.desc_loc[d];
+    int loc = g.m->desc_loc[d];
     if (loc == LOC_FRONT) { tok[n++] = W_IN; tok[n++] = W_FRONT; tok[n++] = W_OF; tok[n++] = W_YOU; }
     else if (loc == LOC_BEHIND) { tok[n++] = W_BEHIND; tok[n++] = W_YOU; }
     else if (loc == LOC_LEFT) { tok[n++] = W_ON; tok[n++] = W_YOUR; tok[n++] = W_LEFT; }
@@ -636,7 +646,7 @@ BB_HD int tok_desc(const GenCtx &g, int d, int16_t *tok, int n)
 }
 BB_HD int tok_leaf(const GenCtx &g, int leaf, int16_t *tok, int n)
 {
-    int k = g.leaf_kind[leaf];
+    int k = g.m->leaf_kind[leaf];
     if (k == I_GOTO) { tok[n++] = W_GO; tok[n++] = W_TO; }
     else if (k == I_PICKUP) { tok[n++] = W_PICK; tok[n++] = W_UP; }
     else if (k == I_OPEN) { tok[n++] = W_OPEN; }
@@ -655,9 +665,10 @@ BB_HD int tok_side(const GenCtx &g, int side, int16_t *tok, int n)
 // One whole RoomGridLevel.reset() worth of generation (levelgen.py:35-47,77-102):
 // retries until an attempt is accepted, then renders grid + records into `o`.
 // Returns the number of attempts.
-BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist)
+BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist, GenMem *mem)
 {
     GenCtx g;
+    g.m = mem;
     g.rng.init(rngrec->seed, rngrec->draws);
     g.locked_room = *locked_room_persist == 0xFF ? -1 : (int)*locked_room_persist;
     int attempts = 0;
@@ -691,18 +702,24 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     __syncwarp();
 #endif
     for (int k = 0; k < g.nobj; k++) {
-        int tc = o.obj->tc[k], st = 0;
+        int tc = g.m->obj.tc[k], st = 0;
         if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (k == g.locked_door ? 2 : 1);   // open_all_doors levelgen.py:189-199
-        set_cell(lp, o.grid, o.obj->x[k], o.obj->y[k], tc | (st << 6));
+        set_cell(lp, o.grid, g.m->obj.x[k], g.m->obj.y[k], tc | (st << 6));
+    }
+    // object table: working copy -> slot
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&g.m->obj);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(o.obj);
+        for (int k = lane; k < (int)(sizeof(ObjTab) / 4); k += nlanes) dst[k] = src[k];
     }
     // ---- verifier record (reset_verifier) + max_steps (levelgen.py:42-45) --
     int navs = 0;
     for (int k = 0; k < 4; k++) {
-        o.ins->leaf_kind[k] = (uint8_t)g.leaf_kind[k];
+        o.ins->leaf_kind[k] = (uint8_t)g.m->leaf_kind[k];
         o.ins->leaf_pre[k] = NO_OBJ;
-        if (g.leaf_kind[k] != I_NONE) navs += g.leaf_kind[k] == I_PUTNEXT ? 2 : 1;
+        if (g.m->leaf_kind[k] != I_NONE) navs += g.m->leaf_kind[k] == I_PUTNEXT ? 2 : 1;
     }
-    for (int k = 0; k < 8; k++) o.ins->desc_mask[k] = g.desc_mask[k];
+    for (int k = 0; k < 8; k++) o.ins->desc_mask[k] = g.m->desc_mask[k];
     o.ins->root_kind = (uint8_t)g.root_kind; o.ins->side_and = (uint8_t)g.side_and; o.ins->flags = 0;
     o.ins->pad0 = 0; o.ins->pad1 = 0;
     EnvHot h;
@@ -712,7 +729,7 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     h.snap_mask = h.cur_mask;
     *o.hot = h;
     // ---- mission tokens ---------------------------------------------------
-    int16_t tok[MAXTOK];
+    int16_t *tok = g.m->tok;
     int n = tok_side(g, 0, tok, 0);
     if (g.root_kind == R_BEFORE) { tok[n++] = W_THEN; n = tok_side(g, 1, tok, n); }
     else if (g.root_kind == R_AFTER) { tok[n++] = W_AFTER; tok[n++] = W_YOU; n = tok_side(g, 1, tok, n); }
@@ -943,7 +960,7 @@ BB_HD void transpose8(uint32_t &lo, uint32_t &hi)
 
 // Visibility of the 7x7 view as 7-bit row masks (bit i = lateral column vi);
 // see[j] = see-through cells of view row j, row 6 is the agent's.  Equivalent to the
-// reference's nested process_vis loops (exhaustive test in tests/test_hostemu.py).
+// reference's nested process_vis loops (exhaustive test: test_vis_rows_bit_trick_equals_literal_loops).
 // Row rule: the visible see-through cells flood sideways through see-through cells,
 // and the cell just beyond each end of a flooded run is visible too; that same set
 // (run + its two neighbours) is what the next row starts from.  The flood towards

@@ -185,6 +185,8 @@ k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions,
 __global__ void __launch_bounds__(GEN_THREADS)
 k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
 {
+    __shared__ GenMem gen_mem[GEN_THREADS / 32];
+    GenMem *mem = &gen_mem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t nchunks = (uint32_t)((n + GEN_CHUNK - 1) / GEN_CHUNK);
     const uint32_t D = (uint32_t)P.depth;
@@ -212,7 +214,7 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
             int att = 0;
             for (int i = 0; i < m; i++) {
                 const LevelOut o = ring_slot(lp, P, env, (int)((t0 + (uint32_t)i) % D));
-                att += generate_level(lp, o, &r, &lr);
+                att += generate_level(lp, o, &r, &lr, mem);
                 __syncwarp();
                 if (lane == 0) { __threadfence(); P.tail[env] = t0 + (uint32_t)i + 1u; }   // publish the slot
             }

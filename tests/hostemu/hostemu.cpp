@@ -36,7 +36,8 @@ static void gen_spare(HPool *p, int e)
 {
     Slot &s = p->spare[e];
     LevelOut o; o.grid = s.grid.data(); o.hot = &s.hot; o.obj = &s.obj; o.ins = &s.ins; o.tok = s.tok.data();
-    p->attempts[e] += (uint32_t)generate_level(p->lp, o, &p->rng[e], &p->locked_room[e]);
+    GenMem mem;
+    p->attempts[e] += (uint32_t)generate_level(p->lp, o, &p->rng[e], &p->locked_room[e], &mem);
     p->sready[e] = 1;
 }
 
