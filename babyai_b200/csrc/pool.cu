@@ -36,9 +36,12 @@ struct PoolPtrs {
     // tail[e] levels since the last seed(); level number L lives in slot L % depth
     uint8_t *rgrid; EnvHot *rhot; ObjTab *robj; InstrRec *rins; int16_t *rtok;
     uint32_t *head, *tail;
+    // no fences: k_gen works from head_snap (copied from head after the step it was forked from finished)
+    // and k_step trusts tail_pub (copied from tail only after a k_gen has completed)
+    uint32_t *head_snap, *tail_pub;
     RngRec *rng; uint8_t *locked_room; uint32_t *attempts;
     float *last_reward;
-    uint32_t *gen_ticket; uint32_t *gen_blocks_done;
+    uint32_t *gen_ticket;
     unsigned long long *warp_counters;   // [num_warps][4]: steps, episodes, successes, errors
     int32_t depth, n;
 };
@@ -144,10 +147,9 @@ k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions,
         }
         if (begin) {
             const uint32_t hd = P.head[env];
-            const uint32_t tl = __ldcg(P.tail + env);
+            const uint32_t tl = __ldcg(P.tail_pub + env);
             if (tl - hd >= 1u && tl - hd <= (uint32_t)P.depth) {
                 swap_in(lp, P, env, (int)(hd % (uint32_t)P.depth), h);
-                __threadfence();                       // the slot is free for k_gen only after it was copied
                 P.head[env] = hd + 1u;
             } else error = true;                       // cannot happen: the host orders k_gen before this step
         }
@@ -198,7 +200,7 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
         const int e_l = (int)c * GEN_CHUNK + (lane & (GEN_CHUNK - 1));
         uint32_t tl = 0; int missing = 0;
         if (lane < GEN_CHUNK && e_l < n) {
-            const uint32_t hd = __ldcg(P.head + e_l);          // k_step may be consuming concurrently
+            const uint32_t hd = P.head_snap[e_l];             // consumption as of the step this launch was forked from
             tl = P.tail[e_l];
             missing = target - (int)(tl - hd);
         }
@@ -216,16 +218,10 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
                 const LevelOut o = ring_slot(lp, P, env, (int)((t0 + (uint32_t)i) % D));
                 att += generate_level(lp, o, &r, &lr, mem);
                 __syncwarp();
-                if (lane == 0) { __threadfence(); P.tail[env] = t0 + (uint32_t)i + 1u; }   // publish the slot
+                if (lane == 0) P.tail[env] = t0 + (uint32_t)i + 1u;
             }
             if (lane == 0) { P.rng[env] = r; P.locked_room[env] = lr; P.attempts[env] += (uint32_t)att; }
         }
-    }
-    __syncthreads();                                           // last block out resets the ticket counter
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int prev = atomicAdd(P.gen_blocks_done, 1u);
-        if (prev == gridDim.x - 1) { *P.gen_ticket = 0; *P.gen_blocks_done = 0; __threadfence(); }
     }
 }
 
@@ -237,6 +233,7 @@ __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
     P.rng[env] = r;
     P.locked_room[env] = 0xFF;
     P.tail[env] = P.head[env];                                 // empty ring: old levels belong to the old stream
+    P.tail_pub[env] = P.head[env];
     P.attempts[env] = 0;
 }
 
@@ -296,10 +293,17 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
     return e ? fail("%s", e) : 0;
 }
 
+// One generation pass on stream `st`: snapshot the consumption counters, reset the work-ticket counter,
+// run k_gen, then publish the production counters.  The two small device-to-device copies replace
+// __threadfence() pairs in the kernels (a gpu-scope fence invalidates the SM's whole L1).
 static void launch_gen(bb_pool *p, cudaStream_t st)
 {
     const int target = p->mode == BB_MODE_AUTORESET ? p->D : 1;
+    const size_t nb = (size_t)p->n * sizeof(uint32_t);
+    cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, st);
+    cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), st);
     k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, st);
     p->launches++;
 }
 
@@ -393,9 +397,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (dalloc(p, &P.grid, n * lp.cells_pad) || dalloc(p, &P.hot, n) || dalloc(p, &P.obj, n) || dalloc(p, &P.ins, n) ||
         dalloc(p, &P.tok, n * lp.max_tokens) || dalloc(p, &P.rgrid, D * n * lp.cells_pad) || dalloc(p, &P.rhot, D * n) ||
         dalloc(p, &P.robj, D * n) || dalloc(p, &P.rins, D * n) || dalloc(p, &P.rtok, D * n * lp.max_tokens) ||
-        dalloc(p, &P.head, n) || dalloc(p, &P.tail, n) ||
+        dalloc(p, &P.head, n) || dalloc(p, &P.tail, n) || dalloc(p, &P.head_snap, n) || dalloc(p, &P.tail_pub, n) ||
         dalloc(p, &P.rng, n) || dalloc(p, &P.locked_room, n) || dalloc(p, &P.attempts, n) || dalloc(p, &P.last_reward, n) ||
-        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_blocks_done, 4) ||
+        dalloc(p, &P.gen_ticket, 4) ||
         dalloc(p, &P.warp_counters, (size_t)p->num_warps * 4) ||
         dalloc(p, &p->d_act, n) || dalloc(p, &p->d_obs, n * OBS_BYTES) || dalloc(p, &p->d_rew, n) || dalloc(p, &p->d_done, n) ||
         dalloc(p, &p->d_dir, n) || dalloc(p, &p->d_seeds, n)) {
