@@ -740,11 +740,47 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
 // =============================================================================
 // step: MiniGridEnv.step (App. A.4) + RoomGridLevel.step (levelgen.py:49-66)
 // =============================================================================
-BB_HD int find_obj_at(const ObjTab *ot, uint32_t mask, int x, int y)
+// The step / verifier / observation code below is written against a small "environment memory"
+// accessor M so that the same source runs on (a) plain pointers into the struct-of-arrays state
+// (GlobalMem: host build, large grids) and (b) the warp's shared-memory staging area (pool.cu).
+//   cell(x,y) set_cell(x,y,v) row_word(vert,row,k)      grid (both orientations)
+//   ox(k) oy(k) otc(k) set_oxy(k,x,y)                   object table
+//   desc_mask(d) leaf_kind(l) leaf_pre(l) set_leaf_pre(l,v) root_kind() side_and() flags() set_flags(v)
+struct GlobalMem {
+    const LevelParams &lp; uint8_t *grid; ObjTab *ot; InstrRec *ins;
+    BB_HD GlobalMem(const LevelParams &lp_, uint8_t *g, ObjTab *o, InstrRec *i) : lp(lp_), grid(g), ot(o), ins(i) {}
+    BB_HD int cell(int x, int y) const { return grid[y * lp.rs_g + x]; }
+    BB_HD void set_cell(int x, int y, int v) { bb::set_cell(lp, grid, x, y, v); }
+    // aligned word k of stored row `row` of G (vert = false) or GT (vert = true)
+    BB_HD uint32_t row_word(bool vert, int row, int k) const
+    {
+        const uint8_t *p = grid + (vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) + 4 * k;
+#if defined(__CUDA_ARCH__)
+        return *reinterpret_cast<const uint32_t *>(p);
+#else
+        uint32_t v; __builtin_memcpy(&v, p, 4); return v;
+#endif
+    }
+    BB_HD int ox(int k) const { return ot->x[k]; }
+    BB_HD int oy(int k) const { return ot->y[k]; }
+    BB_HD int otc(int k) const { return ot->tc[k]; }
+    BB_HD void set_oxy(int k, int x, int y) { ot->x[k] = (uint8_t)x; ot->y[k] = (uint8_t)y; }
+    BB_HD uint32_t desc_mask(int d) const { return ins->desc_mask[d]; }
+    BB_HD int leaf_kind(int l) const { return ins->leaf_kind[l]; }
+    BB_HD int leaf_pre(int l) const { return ins->leaf_pre[l]; }
+    BB_HD void set_leaf_pre(int l, int v) { ins->leaf_pre[l] = (uint8_t)v; }
+    BB_HD int root_kind() const { return ins->root_kind; }
+    BB_HD int side_and() const { return ins->side_and; }
+    BB_HD int flags() const { return ins->flags; }
+    BB_HD void set_flags(int v) { ins->flags = (uint8_t)v; }
+};
+
+template <class M>
+BB_HD int find_obj_at(const M &mem, uint32_t mask, int x, int y)
 {
     for (uint32_t m = mask; m; m &= m - 1) {
         int k = ffs32(m);
-        if (ot->x[k] == x && ot->y[k] == y) return k;
+        if (mem.ox(k) == x && mem.oy(k) == y) return k;
     }
     return NO_OBJ;
 }
@@ -753,30 +789,30 @@ struct StepCtx {            // what a leaf verifier looks at after the action wa
     int action, fx, fy;     // front_pos AFTER the move
     int carry;              // env.carrying after the action
     uint32_t cur_mask, snap_mask;
-    const uint8_t *grid; const ObjTab *ot; int W;
 };
 
 // ActionInstr.verify_action: Open :257-274, GoTo :296-303, Pickup :330-350, PutNext :393-417
-BB_HD bool verify_leaf(InstrRec *ins, int leaf, const StepCtx &s)
+template <class M>
+BB_HD bool verify_leaf(M &mem, int leaf, const StepCtx &s)
 {
-    const int kind = ins->leaf_kind[leaf];
-    const uint32_t set = ins->desc_mask[2 * leaf];
+    const int kind = mem.leaf_kind(leaf);
+    const uint32_t set = mem.desc_mask(2 * leaf);
     if (kind == I_GOTO) {
         for (uint32_t m = set & s.snap_mask; m; m &= m - 1) {
             int k = ffs32(m);
-            if (s.ot->x[k] == s.fx && s.ot->y[k] == s.fy) return true;
+            if (mem.ox(k) == s.fx && mem.oy(k) == s.fy) return true;
         }
         return false;
     }
     if (kind == I_OPEN) {
         if (s.action != A_TOGGLE) return false;
-        int c = s.grid[s.fy * s.W + s.fx];
+        int c = mem.cell(s.fx, s.fy);
         if ((c & 7) != T_DOOR || (c >> 6) != 0) return false;            // must be a door and open
-        int id = find_obj_at(s.ot, s.cur_mask, s.fx, s.fy);
+        int id = find_obj_at(mem, s.cur_mask, s.fx, s.fy);
         return id != NO_OBJ && ((set >> id) & 1u);
     }
-    const int pre = ins->leaf_pre[leaf];
-    ins->leaf_pre[leaf] = (uint8_t)s.carry;
+    const int pre = mem.leaf_pre(leaf);
+    mem.set_leaf_pre(leaf, s.carry);
     if (kind == I_PICKUP) {
         if (s.action != A_PICKUP) return false;
         return pre == NO_OBJ && s.carry != NO_OBJ && ((set >> s.carry) & 1u);
@@ -785,46 +821,49 @@ BB_HD bool verify_leaf(InstrRec *ins, int leaf, const StepCtx &s)
     if (s.action != A_DROP) return false;
     if (pre == NO_OBJ || !((set >> pre) & 1u)) return false;
     if (s.carry == pre) return false;                   // still in hand: cur_pos == (-1,-1)
-    int ax = s.ot->x[pre], ay = s.ot->y[pre];
-    for (uint32_t m = ins->desc_mask[2 * leaf + 1] & s.snap_mask; m; m &= m - 1) {
+    int ax = mem.ox(pre), ay = mem.oy(pre);
+    for (uint32_t m = mem.desc_mask(2 * leaf + 1) & s.snap_mask; m; m &= m - 1) {
         int k = ffs32(m);
-        if (iabs(ax - (int)s.ot->x[k]) + iabs(ay - (int)s.ot->y[k]) == 1) return true;
+        if (iabs(ax - mem.ox(k)) + iabs(ay - mem.oy(k)) == 1) return true;
     }
     return false;
 }
 
 // one side: an ActionInstr, or AndInstr.verify (verifier.py:536-550)
-BB_HD bool verify_side(InstrRec *ins, int side, const StepCtx &s)
+template <class M>
+BB_HD bool verify_side(M &mem, int side, const StepCtx &s)
 {
-    if (!((ins->side_and >> side) & 1)) return verify_leaf(ins, 2 * side, s);
+    if (!((mem.side_and() >> side) & 1)) return verify_leaf(mem, 2 * side, s);
     const int ba = 2 + 2 * side, bb_ = 3 + 2 * side;
-    if (!((ins->flags >> ba) & 1) && verify_leaf(ins, 2 * side, s)) ins->flags |= (uint8_t)(1 << ba);
-    if (!((ins->flags >> bb_) & 1) && verify_leaf(ins, 2 * side + 1, s)) ins->flags |= (uint8_t)(1 << bb_);
-    return ((ins->flags >> ba) & 1) && ((ins->flags >> bb_) & 1);
+    if (!((mem.flags() >> ba) & 1) && verify_leaf(mem, 2 * side, s)) mem.set_flags(mem.flags() | (1 << ba));
+    if (!((mem.flags() >> bb_) & 1) && verify_leaf(mem, 2 * side + 1, s)) mem.set_flags(mem.flags() | (1 << bb_));
+    return ((mem.flags() >> ba) & 1) && ((mem.flags() >> bb_) & 1);
 }
 
 // BeforeInstr.verify :449-471, AfterInstr.verify :490-512 (hand-over re-verifies the same action)
-BB_HD bool verify_root(InstrRec *ins, const StepCtx &s)
+template <class M>
+BB_HD bool verify_root(M &mem, const StepCtx &s)
 {
-    const int rk = ins->root_kind;
-    if (rk == R_SINGLE) return verify_side(ins, 0, s);
+    const int rk = mem.root_kind();
+    if (rk == R_SINGLE) return verify_side(mem, 0, s);
     const int first = rk == R_BEFORE ? 0 : 1, second = 1 - first;
-    if (!((ins->flags >> first) & 1)) {
-        if (!verify_side(ins, first, s)) return false;
-        ins->flags |= (uint8_t)(1 << first);
+    if (!((mem.flags() >> first) & 1)) {
+        if (!verify_side(mem, first, s)) return false;
+        mem.set_flags(mem.flags() | (1 << first));
     }
-    return verify_side(ins, second, s);
+    return verify_side(mem, second, s);
 }
 
 struct StepResult { bool done; bool success; float reward; };
 
 // Applies one action to the live state of one env.  `h` is the env's hot record
 // held in registers by the caller (written back by the caller).
-BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTab *ot, InstrRec *ins, int action)
+template <class M>
+BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
 {
     int x = h.x, y = h.y, dir = h.dirflags & 3, carry = h.carry;
     const int fx = x + dir_dx(dir), fy = y + dir_dy(dir);
-    const int fc = get_cell(lp, grid, fx, fy);
+    const int fc = mem.cell(fx, fy);
     const int ftype = fc & 7;
     if (action == A_LEFT) dir = (dir + 3) & 3;
     else if (action == A_RIGHT) dir = (dir + 1) & 3;
@@ -832,13 +871,13 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
         if (fc == CELL_EMPTY || (ftype == T_DOOR && (fc >> 6) == 0)) { x = fx; y = fy; }
     } else if (action == A_PICKUP) {
         if (ftype >= T_KEY && carry == NO_OBJ) {
-            int id = find_obj_at(ot, h.cur_mask, fx, fy);
-            if (id != NO_OBJ) { carry = id; h.cur_mask &= ~(1u << id); set_cell(lp, grid, fx, fy, CELL_EMPTY); }
+            int id = find_obj_at(mem, h.cur_mask, fx, fy);
+            if (id != NO_OBJ) { carry = id; h.cur_mask &= ~(1u << id); mem.set_cell(fx, fy, CELL_EMPTY); }
         }
     } else if (action == A_DROP) {
         if (fc == CELL_EMPTY && carry != NO_OBJ) {
-            set_cell(lp, grid, fx, fy, ot->tc[carry]);
-            ot->x[carry] = (uint8_t)fx; ot->y[carry] = (uint8_t)fy;
+            mem.set_cell(fx, fy, mem.otc(carry));
+            mem.set_oxy(carry, fx, fy);
             h.cur_mask |= 1u << carry;
             carry = NO_OBJ;
         }
@@ -846,13 +885,13 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
         if (ftype == T_DOOR) {
             int st = fc >> 6, ns = st;
             if (st == 2) {           // locked: needs a carried key of the door's colour; key stays in hand
-                if (carry != NO_OBJ && (ot->tc[carry] & 7) == T_KEY && (ot->tc[carry] >> 3) == ((fc >> 3) & 7)) ns = 0;
+                if (carry != NO_OBJ && (mem.otc(carry) & 7) == T_KEY && (mem.otc(carry) >> 3) == ((fc >> 3) & 7)) ns = 0;
             } else ns = st ^ 1;
-            if (ns != st) set_cell(lp, grid, fx, fy, (fc & 0x3F) | (ns << 6));
+            if (ns != st) mem.set_cell(fx, fy, (fc & 0x3F) | (ns << 6));
         } else if (ftype == T_BOX) {  // Box.toggle: replaced by its contents (None)
-            int id = find_obj_at(ot, h.cur_mask, fx, fy);
+            int id = find_obj_at(mem, h.cur_mask, fx, fy);
             if (id != NO_OBJ) h.cur_mask &= ~(1u << id);
-            set_cell(lp, grid, fx, fy, CELL_EMPTY);
+            mem.set_cell(fx, fy, CELL_EMPTY);
         }
     }
     h.step_count = (uint16_t)(h.step_count + 1);
@@ -863,8 +902,8 @@ BB_HD StepResult step_env(const LevelParams &lp, EnvHot &h, uint8_t *grid, ObjTa
     h.x = (uint8_t)x; h.y = (uint8_t)y; h.dirflags = (uint8_t)((h.dirflags & ~3) | dir); h.carry = (uint8_t)carry;
     StepCtx s;
     s.action = action; s.fx = x + dir_dx(dir); s.fy = y + dir_dy(dir); s.carry = carry;
-    s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.grid = grid; s.ot = ot; s.W = lp.rs_g;
-    r.success = verify_root(ins, s);
+    s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask;
+    r.success = verify_root(mem, s);
     r.reward = 0.0f;
     if (r.success) {
         r.done = true;
@@ -983,7 +1022,8 @@ BB_HD void vis_rows(const uint32_t see[7], uint32_t vis[7])
 }
 
 // Writes the 147 observation bytes as 37 little-endian words (last byte 0).
-BB_HD void observe(const LevelParams &lp, const uint8_t *grid, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+template <class M>
+BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
 {
     const uint32_t WALLW = 0x2A2A2A2Au;
     // which stored row holds view column vi, and where its 7-cell window starts
@@ -992,7 +1032,6 @@ BB_HD void observe(const LevelParams &lp, const uint8_t *grid, int ax, int ay, i
     //   dir 0 (right): G  row ay-3+vi, window x = ax .. ax+6     reversed (vj <-> x = ax+6-vj)
     //   dir 2 (left):  G  row ay+3-vi, window x = ax-6 .. ax     (vj <-> x = ax-6+vj)
     const bool vert = (dir & 1) != 0;
-    const uint8_t *base = grid + (vert ? lp.gt_off : 0);
     const int rs = vert ? lp.rs_t : lp.rs_g;
     const int nrows = vert ? lp.W : lp.H;
     const int c_row = vert ? ax : ay, c_win = vert ? ay : ax;
@@ -1010,10 +1049,9 @@ BB_HD void observe(const LevelParams &lp, const uint8_t *grid, int ax, int ay, i
     for (int vi = 0; vi < 7; vi++) {
         const int row = c_row + rstep * (vi - 3);
         const bool rok = row >= 0 && row < nrows;
-        const uint8_t *rp = base + row * rs + 4 * k0;
-        const uint32_t w0 = (rok && ok0) ? load_u32(rp) : WALLW;          // slice(): out of bounds -> Wall()
-        const uint32_t w1 = (rok && ok1) ? load_u32(rp + 4) : WALLW;
-        const uint32_t w2 = (rok && ok2) ? load_u32(rp + 8) : WALLW;
+        const uint32_t w0 = (rok && ok0) ? mem.row_word(vert, row, k0) : WALLW;          // slice(): out of bounds -> Wall()
+        const uint32_t w1 = (rok && ok1) ? mem.row_word(vert, row, k0 + 1) : WALLW;
+        const uint32_t w2 = (rok && ok2) ? mem.row_word(vert, row, k0 + 2) : WALLW;
         const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);
         R[2 * vi] = byte_perm(lo, hi, sel_lo);
         R[2 * vi + 1] = byte_perm(lo, hi, sel_hi);
@@ -1094,7 +1132,8 @@ BB_HD void observe_simple(const LevelParams &lp, const uint8_t *grid, int ax, in
         }
 }
 
-BB_HD int carry_cell_of(const EnvHot &h, const ObjTab *ot) { return h.carry == NO_OBJ ? CELL_EMPTY : ot->tc[h.carry]; }
+template <class M>
+BB_HD int carry_cell_of(const EnvHot &h, const M &mem) { return h.carry == NO_OBJ ? CELL_EMPTY : mem.otc(h.carry); }
 
 // ---- staging of 32 observations of a warp as aligned words ----------------------
 // Lane l owns bytes [147 l, 147 l + 147) of the 4704-byte warp tile; 147 is not a

@@ -109,6 +109,61 @@ __device__ __forceinline__ void swap_in(const LevelParams &lp, const PoolPtrs &P
     h = *reinterpret_cast<const EnvHot *>(&hv);
 }
 
+// ---- one environment step for the lane's env (shared by the two k_step variants) -----------------
+struct LaneOut { bool stepped, ended, succeeded, error; };
+
+template <int ACT_BYTES, class M, class SwapIn>
+__device__ __forceinline__ LaneOut lane_step(const LevelParams &lp, const PoolPtrs &P, int env, EnvHot &h, M &mem,
+                                             const void *actions, float *reward, uint8_t *done, int8_t *dirs,
+                                             int mode, int force_reset, uint32_t w[OBS_WORDS], SwapIn swap)
+{
+    LaneOut lo = { false, false, false, false };
+    const bool frozen = (h.dirflags & 4) != 0;
+    bool begin = force_reset != 0;
+    float rew = 0.0f; bool dn = false;
+    if (!force_reset) {
+        if (!frozen) {
+            int a;
+            if (ACT_BYTES == 1) a = reinterpret_cast<const int8_t *>(actions)[env];
+            else a = (int)reinterpret_cast<const long long *>(actions)[env];
+            StepResult r = step_env(h, mem, a);
+            rew = r.reward; dn = r.done;
+            lo.stepped = true; lo.ended = dn; lo.succeeded = r.success;
+            if (dn) {
+                if (mode == BB_MODE_AUTORESET) begin = true;
+                else { h.dirflags |= 4; P.last_reward[env] = rew; }
+            }
+        } else {                                   // ManyEnvs: replay the last result (evaluate.py:72-78)
+            rew = P.last_reward[env]; dn = true;
+        }
+    }
+    if (begin) {
+        const uint32_t hd = P.head[env];
+        const uint32_t tl = __ldcg(P.tail_pub + env);
+        if (tl - hd >= 1u && tl - hd <= (uint32_t)P.depth) {
+            swap(env, (int)(hd % (uint32_t)P.depth), h);
+            P.head[env] = hd + 1u;
+        } else lo.error = true;                    // cannot happen: the host orders k_gen before this step
+    }
+    P.hot[env] = h;
+    observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of(h, mem), w);
+    if (reward) reward[env] = rew;
+    if (done) done[env] = dn ? 1 : 0;
+    if (dirs) dirs[env] = (int8_t)(h.dirflags & 3);
+    return lo;
+}
+
+__device__ __forceinline__ void warp_counters(const PoolPtrs &P, int warp_global, int lane, const LaneOut &lo)
+{
+    const uint32_t m_step = __ballot_sync(0xFFFFFFFFu, lo.stepped), m_end = __ballot_sync(0xFFFFFFFFu, lo.ended);
+    const uint32_t m_succ = __ballot_sync(0xFFFFFFFFu, lo.succeeded), m_err = __ballot_sync(0xFFFFFFFFu, lo.error);
+    if (lane == 0) {                               // one slot per warp, no atomics
+        unsigned long long *c = P.warp_counters + 4ull * warp_global;
+        c[0] += __popc(m_step); c[1] += __popc(m_end); c[2] += __popc(m_succ); c[3] += __popc(m_err);
+    }
+}
+
+// ---- generic variant: state read straight from global memory (large grids) ----------------------
 template <int ACT_BYTES>
 __global__ void __launch_bounds__(STEP_THREADS, 4)
 k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
@@ -118,60 +173,163 @@ k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions,
     __shared__ __align__(16) uint32_t tiles[STEP_WARPS][TILE_WORDS];
     const int env = blockIdx.x * STEP_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool valid = env < n;
     uint32_t w[OBS_WORDS];
 #pragma unroll
     for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
-    bool stepped = false, ended = false, succeeded = false, error = false;
-    if (valid) {
+    LaneOut lo = { false, false, false, false };
+    if (env < n) {
         EnvHot h = P.hot[env];
-        uint8_t *grid = P.grid + (size_t)env * lp.cells_pad;
-        const bool frozen = (h.dirflags & 4) != 0;
-        bool begin = force_reset != 0;
-        float rew = 0.0f; bool dn = false;
-        if (!force_reset) {
-            if (!frozen) {
-                int a;
-                if (ACT_BYTES == 1) a = reinterpret_cast<const int8_t *>(actions)[env];
-                else a = (int)reinterpret_cast<const long long *>(actions)[env];
-                StepResult r = step_env(lp, h, grid, P.obj + env, P.ins + env, a);
-                rew = r.reward; dn = r.done;
-                stepped = true; ended = dn; succeeded = r.success;
-                if (dn) {
-                    if (mode == BB_MODE_AUTORESET) begin = true;
-                    else { h.dirflags |= 4; P.last_reward[env] = rew; }
-                }
-            } else {                                   // ManyEnvs: replay the last result (evaluate.py:72-78)
-                rew = P.last_reward[env]; dn = true;
-            }
-        }
-        if (begin) {
-            const uint32_t hd = P.head[env];
-            const uint32_t tl = __ldcg(P.tail_pub + env);
-            if (tl - hd >= 1u && tl - hd <= (uint32_t)P.depth) {
-                swap_in(lp, P, env, (int)(hd % (uint32_t)P.depth), h);
-                P.head[env] = hd + 1u;
-            } else error = true;                       // cannot happen: the host orders k_gen before this step
-        }
-        P.hot[env] = h;
-        observe(lp, grid, h.x, h.y, h.dirflags & 3, carry_cell_of(h, P.obj + env), w);
-        if (reward) reward[env] = rew;
-        if (done) done[env] = dn ? 1 : 0;
-        if (dirs) dirs[env] = (int8_t)(h.dirflags & 3);
+        GlobalMem mem(lp, P.grid + (size_t)env * lp.cells_pad, P.obj + env, P.ins + env);
+        lo = lane_step<ACT_BYTES>(lp, P, env, h, mem, actions, reward, done, dirs, mode, force_reset, w,
+                                  [&](int e, int slot, EnvHot &hh) { swap_in(lp, P, e, slot, hh); });
     }
-    // ---- counters: warp ballots, one slot per warp, no atomics -------------------
-    const uint32_t m_step = __ballot_sync(0xFFFFFFFFu, stepped), m_end = __ballot_sync(0xFFFFFFFFu, ended);
-    const uint32_t m_succ = __ballot_sync(0xFFFFFFFFu, succeeded), m_err = __ballot_sync(0xFFFFFFFFu, error);
-    if (lane == 0) {
-        unsigned long long *c = P.warp_counters + 4ull * (blockIdx.x * STEP_WARPS + warp);
-        c[0] += __popc(m_step); c[1] += __popc(m_end); c[2] += __popc(m_succ); c[3] += __popc(m_err);
-    }
+    warp_counters(P, blockIdx.x * STEP_WARPS + warp, lane, lo);
     // ---- observation bytes: stage per warp, then coalesced 16-byte stores ---------
     uint32_t *tile = tiles[warp];
     stage_obs(tile, w, lane);
     __syncwarp();
     const int env0 = blockIdx.x * STEP_THREADS + warp * 32;
     int nv = n - env0; nv = nv > 32 ? 32 : nv;
+    if (nv > 0) store_tile(tile, obs + (size_t)env0 * OBS_BYTES, lane, nv);
+}
+
+// ---- staged variant (grids up to 128 bytes per env: every single-room level) ---------------------
+// Round-1 profile of the generic kernel: 58 % of the warp stalls are long-scoreboard -- a chain of dependent
+// DRAM round trips (hot -> front cell -> verifier records -> view window).  All of an env's state addresses
+// depend only on the env index, so the warp first copies the records of its 32 envs into shared memory with
+// coalesced 16-byte loads, all in flight at once (ONE DRAM latency), and the per-lane logic then runs on
+// shared memory.  Record strides are odd numbers of words: the coalesced fill (8 lanes per env, 4 envs per
+// instruction) and the per-lane same-offset accesses are both bank-conflict free.
+constexpr int SM_OBJ_STRIDE = 25, SM_INS_STRIDE = 13, SM_GRID_STRIDE_MAX = 33;
+constexpr int SM_WORDS = 32 * (SM_GRID_STRIDE_MAX + SM_OBJ_STRIDE + SM_INS_STRIDE);     // 2272 words per warp
+
+struct SmemMem {
+    const LevelParams &lp;
+    uint32_t *g, *o, *i;                           // this lane's records in shared memory
+    uint8_t *grid; ObjTab *ot; InstrRec *ins;      // the same records in global memory (write-through)
+    bool ins_dirty;
+    __device__ __forceinline__ SmemMem(const LevelParams &lp_, uint32_t *g_, uint32_t *o_, uint32_t *i_, uint8_t *grid_,
+                                       ObjTab *ot_, InstrRec *ins_)
+        : lp(lp_), g(g_), o(o_), i(i_), grid(grid_), ot(ot_), ins(ins_), ins_dirty(false) {}
+    __device__ __forceinline__ static int byte_of(const uint32_t *base, int k) { return (base[k >> 2] >> (8 * (k & 3))) & 0xFF; }
+    __device__ __forceinline__ static void put_byte(uint32_t *base, int k, int v)
+    {
+        const int sh = 8 * (k & 3);
+        base[k >> 2] = (base[k >> 2] & ~(0xFFu << sh)) | ((uint32_t)(v & 0xFF) << sh);
+    }
+    __device__ __forceinline__ int cell(int x, int y) const { return byte_of(g, y * lp.rs_g + x); }
+    __device__ __forceinline__ void set_cell(int x, int y, int v)
+    {
+        put_byte(g, y * lp.rs_g + x, v);
+        put_byte(g, lp.gt_off + x * lp.rs_t + y, v);
+        bb::set_cell(lp, grid, x, y, v);
+    }
+    __device__ __forceinline__ uint32_t row_word(bool vert, int row, int k) const
+    {
+        return g[((vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) >> 2) + k];
+    }
+    __device__ __forceinline__ int ox(int k) const { return byte_of(o, k); }
+    __device__ __forceinline__ int oy(int k) const { return byte_of(o + 8, k); }
+    __device__ __forceinline__ int otc(int k) const { return byte_of(o + 16, k); }
+    __device__ __forceinline__ void set_oxy(int k, int x, int y)
+    {
+        put_byte(o, k, x); put_byte(o + 8, k, y);
+        ot->x[k] = (uint8_t)x; ot->y[k] = (uint8_t)y;
+    }
+    __device__ __forceinline__ uint32_t desc_mask(int d) const { return i[d]; }
+    __device__ __forceinline__ int leaf_kind(int l) const { return byte_of(i + 8, l); }
+    __device__ __forceinline__ int leaf_pre(int l) const { return byte_of(i + 9, l); }
+    __device__ __forceinline__ void set_leaf_pre(int l, int v) { put_byte(i + 9, l, v); ins_dirty = true; }
+    __device__ __forceinline__ int root_kind() const { return i[10] & 0xFF; }
+    __device__ __forceinline__ int side_and() const { return (i[10] >> 8) & 0xFF; }
+    __device__ __forceinline__ int flags() const { return (i[10] >> 16) & 0xFF; }
+    __device__ __forceinline__ void set_flags(int v) { i[10] = (i[10] & 0xFF00FFFFu) | ((uint32_t)(v & 0xFF) << 16); ins_dirty = true; }
+    __device__ __forceinline__ void write_back()
+    {
+        if (ins_dirty) {                           // leaf_pre[4] and root_kind/side_and/flags words
+            uint32_t *gi = reinterpret_cast<uint32_t *>(ins);
+            gi[9] = i[9]; gi[10] = i[10];
+        }
+    }
+};
+
+template <int ACT_BYTES>
+__global__ void __launch_bounds__(STEP_THREADS, 4)
+k_step_staged(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
+              float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
+              const int mode, const int force_reset)
+{
+    __shared__ __align__(16) uint32_t sm[STEP_WARPS][SM_WORDS];
+    const int env = blockIdx.x * STEP_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int env0 = blockIdx.x * STEP_THREADS + warp * 32;
+    int nv = n - env0; nv = nv > 32 ? 32 : (nv < 0 ? 0 : nv);
+    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;       // odd stride
+    uint32_t *sg = sm[warp], *so = sg + 32 * gs, *si = so + 32 * SM_OBJ_STRIDE;
+    // ---- coalesced fill: grid, object table, instruction record of the warp's envs ----------------
+    {
+        const int cpe = lp.cells_pad >> 4;                       // 16-byte chunks per env
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.grid + (size_t)env0 * lp.cells_pad);
+        for (int idx = lane; idx < nv * cpe; idx += 32) {
+            const uint4 v = src[idx];
+            const int e = idx / cpe, w0 = (idx - e * cpe) * 4;
+            uint32_t *d = sg + e * gs + w0;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        const uint4 *osrc = reinterpret_cast<const uint4 *>(P.obj + env0);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int idx = lane + 32 * k;
+            if (idx < nv * 6) {
+                const uint4 v = osrc[idx];
+                const int e = idx / 6, w0 = (idx - e * 6) * 4;
+                uint32_t *d = so + e * SM_OBJ_STRIDE + w0;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+        const uint4 *isrc = reinterpret_cast<const uint4 *>(P.ins + env0);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int idx = lane + 32 * k;
+            if (idx < nv * 3) {
+                const uint4 v = isrc[idx];
+                const int e = idx / 3, w0 = (idx - e * 3) * 4;
+                uint32_t *d = si + e * SM_INS_STRIDE + w0;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+    }
+    uint32_t w[OBS_WORDS];
+#pragma unroll
+    for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
+    LaneOut lo = { false, false, false, false };
+    EnvHot h;
+    if (env < n) h = P.hot[env];
+    __syncwarp();
+    if (env < n) {
+        SmemMem mem(lp, sg + lane * gs, so + lane * SM_OBJ_STRIDE, si + lane * SM_INS_STRIDE,
+                    P.grid + (size_t)env * lp.cells_pad, P.obj + env, P.ins + env);
+        lo = lane_step<ACT_BYTES>(lp, P, env, h, mem, actions, reward, done, dirs, mode, force_reset, w,
+            [&](int e, int slot, EnvHot &hh) {
+                swap_in(lp, P, e, slot, hh);                     // ring slot -> live state in global memory
+                // ... and into this lane's staged copy (same thread wrote the live state just now)
+                const uint32_t *lg = reinterpret_cast<const uint32_t *>(mem.grid);
+                for (int k = 0; k < gwords; k++) mem.g[k] = lg[k];
+                const uint32_t *lob = reinterpret_cast<const uint32_t *>(mem.ot);
+#pragma unroll
+                for (int k = 0; k < 24; k++) mem.o[k] = lob[k];
+                const uint32_t *li = reinterpret_cast<const uint32_t *>(mem.ins);
+#pragma unroll
+                for (int k = 0; k < 12; k++) mem.i[k] = li[k];
+                mem.ins_dirty = false;
+            });
+        mem.write_back();
+    }
+    warp_counters(P, blockIdx.x * STEP_WARPS + warp, lane, lo);
+    __syncwarp();                                                // every lane is done with the staged state:
+    uint32_t *tile = sm[warp];                                   // reuse the region as the observation tile
+    stage_obs(tile, w, lane);
+    __syncwarp();
     if (nv > 0) store_tile(tile, obs + (size_t)env0 * OBS_BYTES, lane, nv);
 }
 
@@ -257,6 +415,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
+    bool force_generic;            // BB_STEP_GENERIC=1: use the unstaged k_step even for small grids (A/B runs)
     long long rel;
     cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
     cudaStream_t gen_stream;       // level generation runs here, concurrently with the steps
@@ -310,10 +469,18 @@ static void launch_gen(bb_pool *p, cudaStream_t st)
 static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8_t *obs, float *rew, uint8_t *done,
                         int8_t *dirs, int force_reset, cudaStream_t st)
 {
-    if (action_bytes == 8)
-        k_step<8><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-    else
-        k_step<1><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    const bool staged = p->lp.cells_pad <= 128 && !p->force_generic;
+    if (staged) {
+        if (action_bytes == 8)
+            k_step_staged<8><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+        else
+            k_step_staged<1><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    } else {
+        if (action_bytes == 8)
+            k_step<8><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+        else
+            k_step<1><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    }
     p->launches++;
 }
 
@@ -389,6 +556,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->nev = p->D / p->G + 3;
     if (p->nev > MAX_GEN_EVENTS) { delete p; return fail("ring depth / generation period too large"); }
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
+    p->force_generic = getenv("BB_STEP_GENERIC") != nullptr;
     p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr;
     const LevelParams &lp = p->lp;
     const size_t n = (size_t)n_envs, D = (size_t)p->D;

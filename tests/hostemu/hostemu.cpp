@@ -45,7 +45,8 @@ static void obs_of(HPool *p, int e, uint8_t *out)
 {
     Slot &s = p->live[e];
     uint32_t w[OBS_WORDS];
-    observe(p->lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, &s.obj), w);
+    GlobalMem mem(p->lp, s.grid.data(), &s.obj, &s.ins);
+    observe(p->lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), w);
     memcpy(out, w, OBS_BYTES);
 }
 
@@ -87,7 +88,8 @@ void he_step(HPool *p, const int8_t *actions, uint8_t *obs, float *reward, uint8
         Slot &s = p->live[e];
         float rew = 0; bool dn = false;
         if (!(s.hot.dirflags & 4)) {
-            StepResult r = step_env(p->lp, s.hot, s.grid.data(), &s.obj, &s.ins, actions[e]);
+            GlobalMem mem(p->lp, s.grid.data(), &s.obj, &s.ins);
+            StepResult r = step_env(s.hot, mem, actions[e]);
             rew = r.reward; dn = r.done;
             if (dn) {
                 if (p->mode == BB_MODE_AUTORESET) { p->live[e] = p->spare[e]; p->sready[e] = 0; gen_spare(p, e); }
@@ -109,8 +111,9 @@ void he_get_state(HPool *p, int e, uint8_t *grid, int32_t *info)
             if (s.grid[lp.gt_off + x * lp.rs_t + y] != s.grid[y * lp.rs_g + x]) { fprintf(stderr, "hostemu: G/GT mismatch\n"); abort(); }
     {   // and the SWAR observation must equal the cell-by-cell one
         uint32_t w[OBS_WORDS]; uint8_t simple[OBS_BYTES];
-        observe(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, &s.obj), w);
-        observe_simple(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, &s.obj), simple);
+        GlobalMem mem(lp, s.grid.data(), &s.obj, &s.ins);
+        observe(lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), w);
+        observe_simple(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), simple);
         if (memcmp(w, simple, OBS_BYTES) != 0) { fprintf(stderr, "hostemu: observe != observe_simple\n"); abort(); }
     }
     info[0] = s.hot.x; info[1] = s.hot.y; info[2] = s.hot.dirflags & 3;
