@@ -1021,46 +1021,80 @@ BB_HD void vis_rows(const uint32_t see[7], uint32_t vis[7])
     }
 }
 
-// Writes the 147 observation bytes as 37 little-endian words (last byte 0).
+// ---- view columns -------------------------------------------------------------------------------
+// Geometry of the view for one agent pose: which stored row holds view column vi and where its
+// 7-cell window starts.
+//   dir 3 (up):    GT row ax-3+vi, window y = ay-6 .. ay     (byte vj <-> y = ay-6+vj)
+//   dir 1 (down):  GT row ax+3-vi, window y = ay .. ay+6     reversed (vj <-> y = ay+6-vj)
+//   dir 0 (right): G  row ay-3+vi, window x = ax .. ax+6     reversed (vj <-> x = ax+6-vj)
+//   dir 2 (left):  G  row ay+3-vi, window x = ax-6 .. ax     (vj <-> x = ax-6+vj)
+struct ViewGeom {
+    bool vert; int nrows, c_row, rstep, k0, sh; bool ok0, ok1, ok2; uint32_t sel_lo, sel_hi;
+};
+BB_HD ViewGeom view_geom(const LevelParams &lp, int ax, int ay, int dir)
+{
+    ViewGeom v;
+    v.vert = (dir & 1) != 0;
+    const int rs = v.vert ? lp.rs_t : lp.rs_g;
+    v.nrows = v.vert ? lp.W : lp.H;
+    v.c_row = v.vert ? ax : ay;
+    const int c_win = v.vert ? ay : ax;
+    v.rstep = (dir == 3 || dir == 0) ? 1 : -1;
+    const bool rev = (dir == 1 || dir == 0);
+    const int s0 = rev ? c_win : c_win - 6;
+    v.k0 = s0 >> 2;                              // arithmetic shift: floor for negative starts
+    v.sh = (s0 & 3) * 8;
+    const int nwords = rs >> 2;
+    v.ok0 = v.k0 >= 0 && v.k0 < nwords; v.ok1 = v.k0 + 1 >= 0 && v.k0 + 1 < nwords; v.ok2 = v.k0 + 2 >= 0 && v.k0 + 2 < nwords;
+    v.sel_lo = rev ? 0x3456u : 0x3210u; v.sel_hi = rev ? 0x7012u : 0x7654u;
+    return v;
+}
+// cells of view column vi: lo = depths vj 0..3, hi = vj 4..6 (+ one unused byte)
+template <class M>
+BB_HD void col_load(const M &mem, const ViewGeom &v, int vi, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t WALLW = 0x2A2A2A2Au;
+    const int row = v.c_row + v.rstep * (vi - 3);
+    const bool rok = row >= 0 && row < v.nrows;
+    const uint32_t w0 = (rok && v.ok0) ? mem.row_word(v.vert, row, v.k0) : WALLW;          // slice(): out of bounds -> Wall()
+    const uint32_t w1 = (rok && v.ok1) ? mem.row_word(v.vert, row, v.k0 + 1) : WALLW;
+    const uint32_t w2 = (rok && v.ok2) ? mem.row_word(v.vert, row, v.k0 + 2) : WALLW;
+    const uint32_t a = funnel_r(w0, w1, v.sh), b = funnel_r(w1, w2, v.sh);
+    lo = byte_perm(a, b, v.sel_lo);
+    hi = byte_perm(a, b, v.sel_hi);
+}
+// see-through cells of a column: bit vj
+BB_HD uint32_t col_see(uint32_t lo, uint32_t hi) { return (gather4(see80(lo)) | (gather4(see80(hi)) << 4)) & 0x7Fu; }
+// four cells -> 12 observation bytes (type, color, state each)
+BB_HD void encode4(uint32_t c, uint32_t &o0, uint32_t &o1, uint32_t &o2)
+{
+    const uint32_t T = c & 0x07070707u, K = (c >> 3) & 0x07070707u, S = (c >> 6) & 0x03030303u;
+    o0 = byte_perm(byte_perm(T, K, 0x1040u), S, 0x3410u);      // t0 k0 s0 t1
+    o1 = byte_perm(byte_perm(T, K, 0x6205u), S, 0x3250u);      // k1 s1 t2 k2
+    o2 = byte_perm(byte_perm(T, K, 0x0730u), S, 0x7216u);      // s2 t3 k3 s3
+}
+// one view column -> its 21 output bytes (6 words, bytes 21..23 zero); cv = visibility of the column, bit vj
+BB_HD void col_encode(uint32_t lo, uint32_t hi, uint32_t cv, uint32_t out[6])
+{
+    lo &= expand4(cv);
+    hi &= expand4(cv >> 4) & 0x00FFFFFFu;
+    encode4(lo, out[0], out[1], out[2]);
+    encode4(hi, out[3], out[4], out[5]);
+}
+
+// Writes the 147 observation bytes as 37 little-endian words (last byte 0): one lane does all columns.
 template <class M>
 BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
 {
-    const uint32_t WALLW = 0x2A2A2A2Au;
-    // which stored row holds view column vi, and where its 7-cell window starts
-    //   dir 3 (up):    GT row ax-3+vi, window y = ay-6 .. ay     (byte vj <-> y = ay-6+vj)
-    //   dir 1 (down):  GT row ax+3-vi, window y = ay .. ay+6     reversed (vj <-> y = ay+6-vj)
-    //   dir 0 (right): G  row ay-3+vi, window x = ax .. ax+6     reversed (vj <-> x = ax+6-vj)
-    //   dir 2 (left):  G  row ay+3-vi, window x = ax-6 .. ax     (vj <-> x = ax-6+vj)
-    const bool vert = (dir & 1) != 0;
-    const int rs = vert ? lp.rs_t : lp.rs_g;
-    const int nrows = vert ? lp.W : lp.H;
-    const int c_row = vert ? ax : ay, c_win = vert ? ay : ax;
-    const int rstep = (dir == 3 || dir == 0) ? 1 : -1;
-    const bool rev = (dir == 1 || dir == 0);
-    const int s0 = rev ? c_win : c_win - 6;
-    const int k0 = s0 >> 2;                      // arithmetic shift: floor for negative starts
-    const int sh = (s0 & 3) * 8;
-    const int nwords = rs >> 2;
-    const bool ok0 = k0 >= 0 && k0 < nwords, ok1 = k0 + 1 >= 0 && k0 + 1 < nwords, ok2 = k0 + 2 >= 0 && k0 + 2 < nwords;
-    const uint32_t sel_lo = rev ? 0x3456u : 0x3210u, sel_hi = rev ? 0x7012u : 0x7654u;
-
+    const ViewGeom v = view_geom(lp, ax, ay, dir);
     uint32_t R[14];                              // R[2 vi] = cells vj 0..3, R[2 vi + 1] = cells vj 4..6 (+1 unused byte)
 #pragma unroll
-    for (int vi = 0; vi < 7; vi++) {
-        const int row = c_row + rstep * (vi - 3);
-        const bool rok = row >= 0 && row < nrows;
-        const uint32_t w0 = (rok && ok0) ? mem.row_word(vert, row, k0) : WALLW;          // slice(): out of bounds -> Wall()
-        const uint32_t w1 = (rok && ok1) ? mem.row_word(vert, row, k0 + 1) : WALLW;
-        const uint32_t w2 = (rok && ok2) ? mem.row_word(vert, row, k0 + 2) : WALLW;
-        const uint32_t lo = funnel_r(w0, w1, sh), hi = funnel_r(w1, w2, sh);
-        R[2 * vi] = byte_perm(lo, hi, sel_lo);
-        R[2 * vi + 1] = byte_perm(lo, hi, sel_hi);
-    }
+    for (int vi = 0; vi < 7; vi++) col_load(mem, v, vi, R[2 * vi], R[2 * vi + 1]);
     // see-through bits: per column (bit vj), then transposed to per row (bit vi)
     uint32_t blo = 0, bhi = 0;
 #pragma unroll
     for (int vi = 0; vi < 7; vi++) {
-        const uint32_t cm = (gather4(see80(R[2 * vi])) | (gather4(see80(R[2 * vi + 1])) << 4)) & 0x7Fu;
+        const uint32_t cm = col_see(R[2 * vi], R[2 * vi + 1]);
         if (vi < 4) blo |= cm << (8 * vi); else bhi |= cm << (8 * (vi - 4));
     }
     transpose8(blo, bhi);
@@ -1095,12 +1129,31 @@ BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir,
             sel |= (uint32_t)(r == ra ? byte : 4 + byte) << (4 * i);
         }
         const uint32_t c = byte_perm(R[ra], ra + 1 < 14 ? R[ra + 1] : 0u, sel);
-        const uint32_t T = c & 0x07070707u, K = (c >> 3) & 0x07070707u, S = (c >> 6) & 0x03030303u;
-        const uint32_t o0 = byte_perm(byte_perm(T, K, 0x1040u), S, 0x3410u);      // t0 k0 s0 t1
-        const uint32_t o1 = byte_perm(byte_perm(T, K, 0x6205u), S, 0x3250u);      // k1 s1 t2 k2
-        const uint32_t o2 = byte_perm(byte_perm(T, K, 0x0730u), S, 0x7216u);      // s2 t3 k3 s3
+        uint32_t o0, o1, o2;
+        encode4(c, o0, o1, o2);
         w[3 * k] = o0;
         if (k < 12) { w[3 * k + 1] = o1; w[3 * k + 2] = o2; }
+    }
+}
+
+// The same observation assembled from per-column pieces exactly as the 8-lanes-per-env kernel does
+// (lane vi = column vi; the ballots become loops here).  Test cross-check only.
+template <class M>
+BB_HD void observe_columns(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint8_t out[OBS_BYTES])
+{
+    const ViewGeom v = view_geom(lp, ax, ay, dir);
+    uint32_t lo[7], hi[7], cm[7], see[7], vis[7];
+    for (int vi = 0; vi < 7; vi++) { col_load(mem, v, vi, lo[vi], hi[vi]); cm[vi] = col_see(lo[vi], hi[vi]); }
+    for (int vj = 0; vj < 7; vj++) { see[vj] = 0; for (int vi = 0; vi < 7; vi++) see[vj] |= ((cm[vi] >> vj) & 1u) << vi; }   // = 7 ballots
+    vis_rows(see, vis);
+    for (int vi = 0; vi < 7; vi++) {
+        uint32_t cv = 0;
+        for (int vj = 0; vj < 7; vj++) cv |= ((vis[vj] >> vi) & 1u) << vj;
+        uint32_t h = hi[vi];
+        if (vi == 3) h = (h & 0xFF00FFFFu) | ((uint32_t)carry_cell << 16);
+        uint32_t o[6];
+        col_encode(lo[vi], h, cv, o);
+        for (int b = 0; b < 21; b++) out[21 * vi + b] = (uint8_t)(o[b >> 2] >> (8 * (b & 3)));
     }
 }
 
@@ -1162,6 +1215,29 @@ BB_HD void stage_obs_words(uint32_t *tile, const uint32_t w[OBS_WORDS], int lane
         const uint32_t hi = k < OBS_WORDS ? w[k] : 0u;
         uint32_t v = funnel_l(lo, hi, s8);
         if (k == 0 && sh != 0) continue;                      // first word belongs to the previous lane
+        if (k > kl) continue;
+        if (k == kl && nvalid < 4) v |= next_w0 << (8 * nvalid);
+        tile[wb + k] = v;
+    }
+}
+
+
+// Same idea for records of LBYTES bytes held in NW words (bytes beyond LBYTES must be zero):
+// record number q of the tile starts at byte LBYTES * q; next_w0 = first word of record q + 1.
+template <int LBYTES, int NW>
+BB_HD void stage_record_words(uint32_t *tile, const uint32_t w[NW], int q, uint32_t next_w0)
+{
+    const int D = LBYTES * q;
+    const int sh = D & 3, wb = D >> 2;
+    const int kl = (sh + LBYTES - 1) >> 2;
+    const int nvalid = ((sh + LBYTES - 1) & 3) + 1;
+    const int s8 = 8 * sh;
+#pragma unroll
+    for (int k = 0; k <= NW; k++) {
+        const uint32_t lo = k > 0 ? w[k - 1] : 0u;
+        const uint32_t hi = k < NW ? w[k] : 0u;
+        uint32_t v = funnel_l(lo, hi, s8);
+        if (k == 0 && sh != 0) continue;
         if (k > kl) continue;
         if (k == kl && nvalid < 4) v |= next_w0 << (8 * nvalid);
         tile[wb + k] = v;

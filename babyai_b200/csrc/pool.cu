@@ -333,6 +333,138 @@ k_step_staged(const LevelParams lp, const PoolPtrs P, const void *__restrict__ a
     if (nv > 0) store_tile(tile, obs + (size_t)env0 * OBS_BYTES, lane, nv);
 }
 
+// ---- column-parallel variant: EIGHT LANES PER ENVIRONMENT (default) ------------------------------
+// The lane-per-env kernels above are latency-bound: 65 536 envs are only 2 048 warps, 11-14 per SM, and
+// each lane carries a ~1 500-2 000 instruction dependent program (r01d/r01h profiles: 0.9 IPC per SM, 9-12
+// cycles per issued instruction).  Here a group of 8 lanes serves one env (4 envs per warp, 16 384 warps at
+// 65 536 envs):
+//   lane 0 of the group applies the action and runs the verifier (step_env) and broadcasts the new pose;
+//   lanes 0..6 each fetch ONE view column (3 aligned words) and compute its see-through bits;
+//   seven warp ballots turn the column bits of all four envs into row masks (the 8x8 bit transposes of the
+//   scalar path for free); every lane runs the 7-row visibility propagation; lanes 0..6 encode their
+//   column's 21 output bytes and stage them as aligned words (same funnel-shift scheme, 21-byte records);
+//   the warp's 588 observation bytes leave as coalesced 32-bit stores.
+//   A finished env's next level is copied from the ring by the 8 lanes together.
+constexpr int S8_THREADS = 128;
+constexpr int S8_WARPS = S8_THREADS / 32;
+constexpr int S8_TILE_WORDS = 4 * OBS_BYTES / 4;               // 147 words: 4 envs per warp
+
+__device__ __forceinline__ void swap_in8(const LevelParams &lp, const PoolPtrs &P, int env, int slot, int r)
+{
+    const LevelOut o = ring_slot(lp, P, env, slot);
+    const uint4 *sg = reinterpret_cast<const uint4 *>(o.grid);
+    uint4 *lg = reinterpret_cast<uint4 *>(P.grid + (size_t)env * lp.cells_pad);
+    for (int i = r; i < lp.cells_pad / 16; i += 8) lg[i] = __ldcg(sg + i);
+    if (r < 6) reinterpret_cast<uint4 *>(P.obj + env)[r] = __ldcg(reinterpret_cast<const uint4 *>(o.obj) + r);
+    if (r >= 5) reinterpret_cast<uint4 *>(P.ins + env)[r - 5] = __ldcg(reinterpret_cast<const uint4 *>(o.ins) + (r - 5));
+    const uint4 *st = reinterpret_cast<const uint4 *>(o.tok);
+    uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
+    for (int i = r; i < lp.max_tokens / 8; i += 8) lt[i] = __ldcg(st + i);
+}
+
+template <int ACT_BYTES>
+__global__ void __launch_bounds__(S8_THREADS)
+k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
+        float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
+        const int mode, const int force_reset)
+{
+    __shared__ __align__(16) uint32_t tiles[S8_WARPS][S8_TILE_WORDS + 1];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = lane & 7, g = lane >> 3;
+    const int wg = blockIdx.x * S8_WARPS + warp;
+    const int env0 = wg * 4, env = env0 + g;
+    const bool valid = env < n;
+    const int leader = lane & ~7;
+    const unsigned gmask = 0xFFu << (8 * g);
+
+    EnvHot h;
+    { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
+    if (valid) h = P.hot[env];
+    GlobalMem mem(lp, P.grid + (size_t)(valid ? env : 0) * lp.cells_pad, P.obj + (valid ? env : 0), P.ins + (valid ? env : 0));
+    bool stepped = false, ended = false, succeeded = false, error = false, begin = force_reset != 0;
+    float rew = 0.0f; bool dn = false;
+    if (valid && r == 0 && !force_reset) {                        // the group's leader steps the env
+        if (!(h.dirflags & 4)) {
+            int a;
+            if (ACT_BYTES == 1) a = reinterpret_cast<const int8_t *>(actions)[env];
+            else a = (int)reinterpret_cast<const long long *>(actions)[env];
+            const StepResult sr = step_env(h, mem, a);
+            rew = sr.reward; dn = sr.done;
+            stepped = true; ended = dn; succeeded = sr.success;
+            if (dn) {
+                if (mode == BB_MODE_AUTORESET) begin = true;
+                else { h.dirflags |= 4; P.last_reward[env] = rew; }
+            }
+        } else { rew = P.last_reward[env]; dn = true; }           // ManyEnvs: replay the last result
+    }
+    __syncwarp();
+    {   // leader's pose and "episode begins" flag to the whole group
+        uint4 hv = *reinterpret_cast<uint4 *>(&h);
+        hv.x = __shfl_sync(FULL, hv.x, leader); hv.y = __shfl_sync(FULL, hv.y, leader);
+        hv.z = __shfl_sync(FULL, hv.z, leader); hv.w = __shfl_sync(FULL, hv.w, leader);
+        h = *reinterpret_cast<EnvHot *>(&hv);
+        begin = __shfl_sync(FULL, begin ? 1 : 0, leader) != 0;
+    }
+    if (begin && valid) {                                         // uniform within the group
+        const uint32_t hd = P.head[env];
+        const uint32_t tl = __ldcg(P.tail_pub + env);
+        if (tl - hd >= 1u && tl - hd <= (uint32_t)P.depth) {
+            const int slot = (int)(hd % (uint32_t)P.depth);
+            swap_in8(lp, P, env, slot, r);                        // the 8 lanes copy the level together
+            const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(ring_slot(lp, P, env, slot).hot));
+            h = *reinterpret_cast<const EnvHot *>(&hv);
+            __syncwarp(gmask);
+            if (r == 0) P.head[env] = hd + 1u;
+        } else if (r == 0) error = true;                          // cannot happen: the host orders k_gen first
+    }
+    if (valid && r == 0) {
+        P.hot[env] = h;
+        if (reward) reward[env] = rew;
+        if (done) done[env] = dn ? 1 : 0;
+        if (dirs) dirs[env] = (int8_t)(h.dirflags & 3);
+    }
+    __syncwarp();                                                 // grid writes above are visible to the column loads
+    // ---- observation: lane r < 7 holds view column vi = r --------------------------------------
+    const ViewGeom v = view_geom(lp, h.x, h.y, h.dirflags & 3);
+    uint32_t lo = 0, hi = 0, cm = 0;
+    if (valid && r < 7) { col_load(mem, v, r, lo, hi); cm = col_see(lo, hi); }
+    uint32_t see[7], vis[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) see[j] = (__ballot_sync(FULL, (cm >> j) & 1u) >> (8 * g)) & 0x7Fu;
+    vis_rows(see, vis);
+    uint32_t cv = 0;
+#pragma unroll
+    for (int j = 0; j < 7; j++) cv |= ((vis[j] >> r) & 1u) << j;
+    if (r == 3 && valid) hi = (hi & 0xFF00FFFFu) | ((uint32_t)carry_cell_of(h, mem) << 16);   // own cell: what it carries
+    uint32_t o[6];
+    col_encode(lo, hi, (valid && r < 7) ? cv : 0u, o);
+    // ---- stage 28 records of 21 bytes, then coalesced stores ------------------------------------
+    uint32_t *tile = tiles[warp];
+    const uint32_t next_w0 = __shfl_sync(FULL, o[0], r < 6 ? lane + 1 : lane + 2);
+    if (r < 7) stage_record_words<21, 6>(tile, o, 7 * g + r, next_w0);
+    __syncwarp();
+    int nv = n - env0; nv = nv > 4 ? 4 : nv;
+    if (nv > 0) {
+        uint8_t *dst = obs + (size_t)env0 * OBS_BYTES;
+        if (nv == 4 && (((uintptr_t)dst) & 3) == 0) {
+            uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+#pragma unroll
+            for (int i = 0; i < (S8_TILE_WORDS + 31) / 32; i++) { const int idx = lane + 32 * i; if (idx < S8_TILE_WORDS) d32[idx] = tile[idx]; }
+        } else {
+            const uint8_t *sb = reinterpret_cast<const uint8_t *>(tile);
+            for (int i = lane; i < nv * OBS_BYTES; i += 32) dst[i] = sb[i];
+        }
+    }
+    // ---- counters ----------------------------------------------------------------------------
+    const uint32_t m_step = __ballot_sync(FULL, stepped), m_end = __ballot_sync(FULL, ended);
+    const uint32_t m_succ = __ballot_sync(FULL, succeeded), m_err = __ballot_sync(FULL, error);
+    if (lane == 0) {
+        unsigned long long *c = P.warp_counters + 4ull * wg;
+        c[0] += __popc(m_step); c[1] += __popc(m_end); c[2] += __popc(m_succ); c[3] += __popc(m_err);
+    }
+}
+
 // Level generation, decoupled from the step: tops every environment's ring up to `target` levels.
 //
 // ONE WARP PER ENVIRONMENT.  Generation is a long, branchy, data-dependent rejection-sampling program;
@@ -415,7 +547,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
-    bool force_generic;            // BB_STEP_GENERIC=1: use the unstaged k_step even for small grids (A/B runs)
+    int step_kernel;               // 0 = k_step8 (8 lanes per env, default), 1 = k_step (lane per env), 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
     cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
     cudaStream_t gen_stream;       // level generation runs here, concurrently with the steps
@@ -469,18 +601,17 @@ static void launch_gen(bb_pool *p, cudaStream_t st)
 static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8_t *obs, float *rew, uint8_t *done,
                         int8_t *dirs, int force_reset, cudaStream_t st)
 {
-    const bool staged = p->lp.cells_pad <= 128 && !p->force_generic;
-    if (staged) {
-        if (action_bytes == 8)
-            k_step_staged<8><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-        else
-            k_step_staged<1><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-    } else {
-        if (action_bytes == 8)
-            k_step<8><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-        else
-            k_step<1><<<p->step_blocks, STEP_THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-    }
+    const int blocks8 = (p->n + 4 * S8_WARPS - 1) / (4 * S8_WARPS);
+    const int kernel = p->step_kernel == 2 && p->lp.cells_pad > 128 ? 1 : p->step_kernel;
+#define BB_LAUNCH(K, GRID, THREADS)                                                                                      \
+    do {                                                                                                                 \
+        if (action_bytes == 8) K<8><<<GRID, THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset); \
+        else K<1><<<GRID, THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);     \
+    } while (0)
+    if (kernel == 0) BB_LAUNCH(k_step8, blocks8, S8_THREADS);
+    else if (kernel == 2) BB_LAUNCH(k_step_staged, p->step_blocks, STEP_THREADS);
+    else BB_LAUNCH(k_step, p->step_blocks, STEP_THREADS);
+#undef BB_LAUNCH
     p->launches++;
 }
 
@@ -539,7 +670,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (make_params(spec, &p->lp)) { delete p; return 1; }
     p->n = n_envs; p->device = device; p->mode = BB_MODE_AUTORESET;
     p->step_blocks = (n_envs + STEP_THREADS - 1) / STEP_THREADS;
-    p->num_warps = p->step_blocks * STEP_WARPS;
+    p->num_warps = (n_envs + 3) / 4 + STEP_WARPS;          // counter slots: the 8-lanes-per-env kernel has the most warps
     {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
@@ -556,7 +687,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->nev = p->D / p->G + 3;
     if (p->nev > MAX_GEN_EVENTS) { delete p; return fail("ring depth / generation period too large"); }
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
-    p->force_generic = getenv("BB_STEP_GENERIC") != nullptr;
+    p->step_kernel = 0;
+    if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : 0;
     p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr;
     const LevelParams &lp = p->lp;
     const size_t n = (size_t)n_envs, D = (size_t)p->D;

@@ -115,6 +115,9 @@ void he_get_state(HPool *p, int e, uint8_t *grid, int32_t *info)
         observe(lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), w);
         observe_simple(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), simple);
         if (memcmp(w, simple, OBS_BYTES) != 0) { fprintf(stderr, "hostemu: observe != observe_simple\n"); abort(); }
+        uint8_t cols[OBS_BYTES];
+        observe_columns(lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), cols);
+        if (memcmp(cols, simple, OBS_BYTES) != 0) { fprintf(stderr, "hostemu: observe_columns != observe_simple\n"); abort(); }
     }
     info[0] = s.hot.x; info[1] = s.hot.y; info[2] = s.hot.dirflags & 3;
     info[3] = s.hot.carry == NO_OBJ ? 0 : s.obj.tc[s.hot.carry];
@@ -137,6 +140,18 @@ void he_stage(const uint32_t *w /* [32][37] */, uint8_t *tile /* 4704 + slack */
         stage_obs_words(t, w + lane * OBS_WORDS, lane, next_w0);
     }
     memcpy(tile, t, 32 * OBS_BYTES);
+}
+
+// staging of 28 records of 21 bytes (4 envs x 7 view columns of one warp) -> 588-byte tile
+void he_stage21(const uint32_t *w /* [28][6] */, uint8_t *tile)
+{
+    uint32_t t[147 + 2];
+    memset(t, 0xEE, sizeof t);
+    for (int q = 0; q < 28; q++) {
+        uint32_t next_w0 = q < 27 ? w[(q + 1) * 6] : 0u;
+        stage_record_words<21, 6>(t, w + q * 6, q, next_w0);
+    }
+    memcpy(tile, t, 588);
 }
 
 }  // extern "C"

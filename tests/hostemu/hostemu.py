@@ -44,6 +44,7 @@ def lib():
         L.he_height.argtypes = [C.c_void_p]
         L.he_vis_rows.argtypes = [C.c_void_p, C.c_void_p]
         L.he_stage.argtypes = [C.c_void_p, C.c_void_p]
+        L.he_stage21.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -118,3 +118,18 @@ def test_warp_staging_packs_147_byte_records():
         tile = np.zeros(4704 + 16, np.uint8)
         L.he_stage(words.ctypes.data_as(C.c_void_p), tile.ctypes.data_as(C.c_void_p))
         assert np.array_equal(tile[:4704], by.reshape(-1))
+
+
+def test_column_record_staging_packs_21_byte_records():
+    """28 view-column records of 21 bytes (4 envs x 7 columns) -> the packed 588-byte warp tile."""
+    import ctypes as C
+    L = hostemu.lib()
+    rng = np.random.RandomState(2)
+    for _ in range(50):
+        by = rng.randint(0, 256, (28, 21)).astype(np.uint8)
+        w = np.zeros((28, 24), np.uint8)
+        w[:, :21] = by
+        words = np.ascontiguousarray(w).view(np.uint32).reshape(28, 6)
+        tile = np.zeros(588 + 16, np.uint8)
+        L.he_stage21(words.ctypes.data_as(C.c_void_p), tile.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(tile[:588], by.reshape(-1))
