@@ -159,7 +159,10 @@ __device__ __forceinline__ void warp_counters(const PoolPtrs &P, int warp_global
     const uint32_t m_succ = __ballot_sync(0xFFFFFFFFu, lo.succeeded), m_err = __ballot_sync(0xFFFFFFFFu, lo.error);
     if (lane == 0) {                               // one slot per warp, no atomics
         unsigned long long *c = P.warp_counters + 4ull * warp_global;
-        c[0] += __popc(m_step); c[1] += __popc(m_end); c[2] += __popc(m_succ); c[3] += __popc(m_err);
+        if (m_step) atomicAdd(c + 0, (unsigned long long)__popc(m_step));
+        if (m_end) atomicAdd(c + 1, (unsigned long long)__popc(m_end));
+        if (m_succ) atomicAdd(c + 2, (unsigned long long)__popc(m_succ));
+        if (m_err) atomicAdd(c + 3, (unsigned long long)__popc(m_err));
     }
 }
 
@@ -348,15 +351,56 @@ k_step_staged(const LevelParams lp, const PoolPtrs P, const void *__restrict__ a
 constexpr int S8_THREADS = 128;
 constexpr int S8_WARPS = S8_THREADS / 32;
 constexpr int S8_TILE_WORDS = 4 * OBS_BYTES / 4;               // 147 words: 4 envs per warp
+constexpr int S8_REC_FIXED = (int)(sizeof(ObjTab) + sizeof(InstrRec));   // 144 bytes after the grid
 
-__device__ __forceinline__ void swap_in8(const LevelParams &lp, const PoolPtrs &P, int env, int slot, int r)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// Environment memory of the 8-lane kernel: the env's grid, object table and instruction record staged in
+// shared memory (plain byte/word accesses, ~30 cycles), every write mirrored to the state in global memory.
+struct StagedMem {
+    const LevelParams &lp; uint8_t *sg; ObjTab *so; InstrRec *si;      // shared-memory copies
+    uint8_t *grid; ObjTab *ot; InstrRec *ins;                          // global state
+    __device__ __forceinline__ StagedMem(const LevelParams &lp_, uint8_t *sg_, ObjTab *so_, InstrRec *si_, uint8_t *g, ObjTab *o, InstrRec *i)
+        : lp(lp_), sg(sg_), so(so_), si(si_), grid(g), ot(o), ins(i) {}
+    __device__ __forceinline__ int cell(int x, int y) const { return sg[y * lp.rs_g + x]; }
+    __device__ __forceinline__ void set_cell(int x, int y, int v) { bb::set_cell(lp, sg, x, y, v); bb::set_cell(lp, grid, x, y, v); }
+    __device__ __forceinline__ uint32_t row_word(bool vert, int row, int k) const
+    {
+        return *reinterpret_cast<const uint32_t *>(sg + (vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) + 4 * k);
+    }
+    __device__ __forceinline__ int ox(int k) const { return so->x[k]; }
+    __device__ __forceinline__ int oy(int k) const { return so->y[k]; }
+    __device__ __forceinline__ int otc(int k) const { return so->tc[k]; }
+    __device__ __forceinline__ void set_oxy(int k, int x, int y)
+    {
+        so->x[k] = (uint8_t)x; so->y[k] = (uint8_t)y; ot->x[k] = (uint8_t)x; ot->y[k] = (uint8_t)y;
+    }
+    __device__ __forceinline__ uint32_t desc_mask(int d) const { return si->desc_mask[d]; }
+    __device__ __forceinline__ int leaf_kind(int l) const { return si->leaf_kind[l]; }
+    __device__ __forceinline__ int leaf_pre(int l) const { return si->leaf_pre[l]; }
+    __device__ __forceinline__ void set_leaf_pre(int l, int v) { si->leaf_pre[l] = (uint8_t)v; ins->leaf_pre[l] = (uint8_t)v; }
+    __device__ __forceinline__ int root_kind() const { return si->root_kind; }
+    __device__ __forceinline__ int side_and() const { return si->side_and; }
+    __device__ __forceinline__ int flags() const { return si->flags; }
+    __device__ __forceinline__ void set_flags(int v) { si->flags = (uint8_t)v; ins->flags = (uint8_t)v; }
+};
+
+// ring slot -> live state (global) and -> the staged copy (shared), by the 8 lanes of the group together
+__device__ __forceinline__ void swap_in8(const LevelParams &lp, const PoolPtrs &P, int env, int slot, int r, uint8_t *srec)
 {
     const LevelOut o = ring_slot(lp, P, env, slot);
     const uint4 *sg = reinterpret_cast<const uint4 *>(o.grid);
     uint4 *lg = reinterpret_cast<uint4 *>(P.grid + (size_t)env * lp.cells_pad);
-    for (int i = r; i < lp.cells_pad / 16; i += 8) lg[i] = __ldcg(sg + i);
-    if (r < 6) reinterpret_cast<uint4 *>(P.obj + env)[r] = __ldcg(reinterpret_cast<const uint4 *>(o.obj) + r);
-    if (r >= 5) reinterpret_cast<uint4 *>(P.ins + env)[r - 5] = __ldcg(reinterpret_cast<const uint4 *>(o.ins) + (r - 5));
+    uint4 *mg = reinterpret_cast<uint4 *>(srec);
+    const int gch = lp.cells_pad / 16;
+    for (int i = r; i < gch; i += 8) { const uint4 v = __ldcg(sg + i); lg[i] = v; mg[i] = v; }
+    if (r < 6) { const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.obj) + r); reinterpret_cast<uint4 *>(P.obj + env)[r] = v; mg[gch + r] = v; }
+    if (r >= 5) { const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.ins) + (r - 5)); reinterpret_cast<uint4 *>(P.ins + env)[r - 5] = v; mg[gch + 6 + (r - 5)] = v; }
     const uint4 *st = reinterpret_cast<const uint4 *>(o.tok);
     uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
     for (int i = r; i < lp.max_tokens / 8; i += 8) lt[i] = __ldcg(st + i);
@@ -368,7 +412,7 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
         float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
         const int mode, const int force_reset)
 {
-    __shared__ __align__(16) uint32_t tiles[S8_WARPS][S8_TILE_WORDS + 1];
+    extern __shared__ __align__(16) uint8_t smem8[];               // [16 envs][cells_pad + 144] then the tiles
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = lane & 7, g = lane >> 3;
@@ -377,18 +421,37 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
     const bool valid = env < n;
     const int leader = lane & ~7;
     const unsigned gmask = 0xFFu << (8 * g);
+    const int rec_bytes = lp.cells_pad + S8_REC_FIXED;
+    uint8_t *srec = smem8 + (size_t)(warp * 4 + g) * rec_bytes;    // this env's staged record
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem8 + (size_t)S8_WARPS * 4 * rec_bytes) + warp * (S8_TILE_WORDS + 1);
+    const int gch = lp.cells_pad / 16;
 
+    // ---- all of the env's state in flight at once: asynchronous copies to shared memory + the hot record
+    const size_t e = (size_t)(valid ? env : 0);
+    if (valid) {
+        const uint4 *gsrc = reinterpret_cast<const uint4 *>(P.grid + e * lp.cells_pad);
+        for (int i = r; i < gch; i += 8) cp_async16(srec + 16 * i, gsrc + i);
+        if (r < 6) cp_async16(srec + 16 * (gch + r), reinterpret_cast<const uint4 *>(P.obj + e) + r);
+        if (r >= 5) cp_async16(srec + 16 * (gch + 6 + r - 5), reinterpret_cast<const uint4 *>(P.ins + e) + (r - 5));
+    }
     EnvHot h;
     { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
-    if (valid) h = P.hot[env];
-    GlobalMem mem(lp, P.grid + (size_t)(valid ? env : 0) * lp.cells_pad, P.obj + (valid ? env : 0), P.ins + (valid ? env : 0));
+    int a = 0;
+    if (valid) {
+        h = P.hot[env];
+        if (r == 0 && !force_reset) {
+            if (ACT_BYTES == 1) a = reinterpret_cast<const int8_t *>(actions)[env];
+            else a = (int)reinterpret_cast<const long long *>(actions)[env];
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    StagedMem mem(lp, srec, reinterpret_cast<ObjTab *>(srec + lp.cells_pad), reinterpret_cast<InstrRec *>(srec + lp.cells_pad + sizeof(ObjTab)),
+                  P.grid + e * lp.cells_pad, P.obj + e, P.ins + e);
     bool stepped = false, ended = false, succeeded = false, error = false, begin = force_reset != 0;
     float rew = 0.0f; bool dn = false;
     if (valid && r == 0 && !force_reset) {                        // the group's leader steps the env
         if (!(h.dirflags & 4)) {
-            int a;
-            if (ACT_BYTES == 1) a = reinterpret_cast<const int8_t *>(actions)[env];
-            else a = (int)reinterpret_cast<const long long *>(actions)[env];
             const StepResult sr = step_env(h, mem, a);
             rew = sr.reward; dn = sr.done;
             stepped = true; ended = dn; succeeded = sr.success;
@@ -411,7 +474,7 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
         const uint32_t tl = __ldcg(P.tail_pub + env);
         if (tl - hd >= 1u && tl - hd <= (uint32_t)P.depth) {
             const int slot = (int)(hd % (uint32_t)P.depth);
-            swap_in8(lp, P, env, slot, r);                        // the 8 lanes copy the level together
+            swap_in8(lp, P, env, slot, r, srec);                  // the 8 lanes copy the level together
             const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(ring_slot(lp, P, env, slot).hot));
             h = *reinterpret_cast<const EnvHot *>(&hv);
             __syncwarp(gmask);
@@ -424,7 +487,7 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
         if (done) done[env] = dn ? 1 : 0;
         if (dirs) dirs[env] = (int8_t)(h.dirflags & 3);
     }
-    __syncwarp();                                                 // grid writes above are visible to the column loads
+    __syncwarp();                                                 // staged-copy writes above are visible to the column loads
     // ---- observation: lane r < 7 holds view column vi = r --------------------------------------
     const ViewGeom v = view_geom(lp, h.x, h.y, h.dirflags & 3);
     uint32_t lo = 0, hi = 0, cm = 0;
@@ -440,7 +503,6 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
     uint32_t o[6];
     col_encode(lo, hi, (valid && r < 7) ? cv : 0u, o);
     // ---- stage 28 records of 21 bytes, then coalesced stores ------------------------------------
-    uint32_t *tile = tiles[warp];
     const uint32_t next_w0 = __shfl_sync(FULL, o[0], r < 6 ? lane + 1 : lane + 2);
     if (r < 7) stage_record_words<21, 6>(tile, o, 7 * g + r, next_w0);
     __syncwarp();
@@ -456,12 +518,15 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
             for (int i = lane; i < nv * OBS_BYTES; i += 32) dst[i] = sb[i];
         }
     }
-    // ---- counters ----------------------------------------------------------------------------
+    // ---- counters: one slot per warp, reductions without a return value (no stall at exit) ------
     const uint32_t m_step = __ballot_sync(FULL, stepped), m_end = __ballot_sync(FULL, ended);
     const uint32_t m_succ = __ballot_sync(FULL, succeeded), m_err = __ballot_sync(FULL, error);
     if (lane == 0) {
         unsigned long long *c = P.warp_counters + 4ull * wg;
-        c[0] += __popc(m_step); c[1] += __popc(m_end); c[2] += __popc(m_succ); c[3] += __popc(m_err);
+        if (m_step) atomicAdd(c + 0, (unsigned long long)__popc(m_step));
+        if (m_end) atomicAdd(c + 1, (unsigned long long)__popc(m_end));
+        if (m_succ) atomicAdd(c + 2, (unsigned long long)__popc(m_succ));
+        if (m_err) atomicAdd(c + 3, (unsigned long long)__popc(m_err));
     }
 }
 
@@ -608,7 +673,11 @@ static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8
         if (action_bytes == 8) K<8><<<GRID, THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset); \
         else K<1><<<GRID, THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);     \
     } while (0)
-    if (kernel == 0) BB_LAUNCH(k_step8, blocks8, S8_THREADS);
+    if (kernel == 0) {
+        const size_t sm8 = (size_t)S8_WARPS * 4 * (p->lp.cells_pad + S8_REC_FIXED) + (size_t)S8_WARPS * (S8_TILE_WORDS + 1) * 4;
+        if (action_bytes == 8) k_step8<8><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+        else k_step8<1><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    }
     else if (kernel == 2) BB_LAUNCH(k_step_staged, p->step_blocks, STEP_THREADS);
     else BB_LAUNCH(k_step, p->step_blocks, STEP_THREADS);
 #undef BB_LAUNCH
