@@ -530,6 +530,165 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
     }
 }
 
+// ---- persistent rollout kernel: T steps per launch, state resident in shared memory --------------
+// bb_pool_rollout's kernel.  Every per-step kernel above reloads ~290 bytes of env state per step through
+// a chain of dependent DRAM round trips and is latency-bound at 11-14 warps per SM.  Here a warp loads the
+// records of its 32 envs ONCE (coalesced), then runs T steps on them out of shared memory -- per step it
+// only reads 32 action bytes and writes the 32 observations / rewards / dones -- and stores the state
+// back at the end.  Finished envs take their next level from the ring (the host guarantees >= T levels
+// per env before the launch; k_gen refills concurrently on the side stream from a head snapshot taken
+// before the launch, so it never touches a slot this launch can consume).
+constexpr int R_THREADS = 64;
+constexpr int R_WARPS = R_THREADS / 32;
+
+struct SmemOnlyMem {            // lane-private records in shared memory (byte addressable; odd word strides)
+    const LevelParams &lp; uint8_t *g, *o, *i;
+    __device__ __forceinline__ SmemOnlyMem(const LevelParams &lp_, uint8_t *g_, uint8_t *o_, uint8_t *i_) : lp(lp_), g(g_), o(o_), i(i_) {}
+    __device__ __forceinline__ int cell(int x, int y) const { return g[y * lp.rs_g + x]; }
+    __device__ __forceinline__ void set_cell(int x, int y, int v) { bb::set_cell(lp, g, x, y, v); }
+    __device__ __forceinline__ uint32_t row_word(bool vert, int row, int k) const
+    {
+        return *reinterpret_cast<const uint32_t *>(g + (vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) + 4 * k);
+    }
+    __device__ __forceinline__ int ox(int k) const { return o[k]; }
+    __device__ __forceinline__ int oy(int k) const { return o[MAXOBJ + k]; }
+    __device__ __forceinline__ int otc(int k) const { return o[2 * MAXOBJ + k]; }
+    __device__ __forceinline__ void set_oxy(int k, int x, int y) { o[k] = (uint8_t)x; o[MAXOBJ + k] = (uint8_t)y; }
+    __device__ __forceinline__ uint32_t desc_mask(int d) const { return reinterpret_cast<const uint32_t *>(i)[d]; }
+    __device__ __forceinline__ int leaf_kind(int l) const { return i[32 + l]; }
+    __device__ __forceinline__ int leaf_pre(int l) const { return i[36 + l]; }
+    __device__ __forceinline__ void set_leaf_pre(int l, int v) { i[36 + l] = (uint8_t)v; }
+    __device__ __forceinline__ int root_kind() const { return i[40]; }
+    __device__ __forceinline__ int side_and() const { return i[41]; }
+    __device__ __forceinline__ int flags() const { return i[42]; }
+    __device__ __forceinline__ void set_flags(int v) { i[42] = (uint8_t)v; }
+};
+
+// coalesced copy of `chunks_per_env` 16-byte chunks per env between global memory (contiguous records of
+// the warp's envs) and the lane-strided shared-memory records
+template <bool TO_SMEM>
+__device__ __forceinline__ void warp_copy_records(uint32_t *sm, int stride_words, uint4 *glob, int chunks_per_env, int nv, int lane)
+{
+    for (int idx = lane; idx < nv * chunks_per_env; idx += 32) {
+        const int e = idx / chunks_per_env, w0 = (idx - e * chunks_per_env) * 4;
+        uint32_t *d = sm + e * stride_words + w0;
+        if (TO_SMEM) { const uint4 v = glob[idx]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+        else glob[idx] = make_uint4(d[0], d[1], d[2], d[3]);
+    }
+}
+
+__global__ void __launch_bounds__(R_THREADS)
+k_rollout(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
+          float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
+          const int mode)
+{
+    extern __shared__ __align__(16) uint32_t smr[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int env0 = (blockIdx.x * R_WARPS + warp) * 32, env = env0 + lane;
+    int nv = n - env0; nv = nv > 32 ? 32 : (nv < 0 ? 0 : nv);
+    const bool valid = lane < nv;
+    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;
+    const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
+    uint32_t *sg = smr + warp * warp_words, *so = sg + 32 * gs, *si = so + 32 * SM_OBJ_STRIDE;
+    uint32_t *tile = si + 32 * SM_INS_STRIDE;       // 16-byte aligned: see launch_rollout
+    // ---- load the state of the warp's envs once ---------------------------------------------------
+    warp_copy_records<true>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
+    warp_copy_records<true>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
+    warp_copy_records<true>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
+    EnvHot h;
+    { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
+    uint32_t head = 0, avail = 0;
+    float last_rew = 0.0f;
+    if (valid) {
+        h = P.hot[env];
+        head = P.head[env];
+        avail = __ldcg(P.tail_pub + env) - head;
+        if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env];
+    }
+    __syncwarp();
+    SmemOnlyMem mem(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * SM_OBJ_STRIDE),
+                    reinterpret_cast<uint8_t *>(si + lane * SM_INS_STRIDE));
+    uint32_t n_step = 0, n_end = 0, n_succ = 0, n_err = 0, consumed = 0;
+    int a_next = valid ? actions[env] : 0;
+    for (int t = 0; t < T; t++) {
+        const int a = a_next;
+        if (valid && t + 1 < T) a_next = actions[(size_t)(t + 1) * n + env];      // prefetch the next action
+        uint32_t w[OBS_WORDS];
+#pragma unroll
+        for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
+        if (valid) {
+            float rew = 0.0f; bool dn = false, begin = false;
+            if (!(h.dirflags & 4)) {
+                const StepResult sr = step_env(h, mem, a);
+                rew = sr.reward; dn = sr.done;
+                n_step++; n_end += dn; n_succ += sr.success;
+                if (dn) {
+                    if (mode == BB_MODE_AUTORESET) begin = true;
+                    else { h.dirflags |= 4; last_rew = rew; }
+                }
+            } else { rew = last_rew; dn = true; }
+            if (begin) {
+                if (consumed < avail && avail <= (uint32_t)P.depth) {
+                    const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
+                    uint32_t *mg = reinterpret_cast<uint32_t *>(mem.g);
+                    for (int k = 0; k < lp.cells_pad / 16; k++) {
+                        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.grid) + k);
+                        mg[4 * k] = v.x; mg[4 * k + 1] = v.y; mg[4 * k + 2] = v.z; mg[4 * k + 3] = v.w;
+                    }
+                    uint32_t *mo = reinterpret_cast<uint32_t *>(mem.o);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.obj) + k);
+                        mo[4 * k] = v.x; mo[4 * k + 1] = v.y; mo[4 * k + 2] = v.z; mo[4 * k + 3] = v.w;
+                    }
+                    uint32_t *mi = reinterpret_cast<uint32_t *>(mem.i);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.ins) + k);
+                        mi[4 * k] = v.x; mi[4 * k + 1] = v.y; mi[4 * k + 2] = v.z; mi[4 * k + 3] = v.w;
+                    }
+                    uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
+                    for (int k = 0; k < lp.max_tokens / 8; k++) lt[k] = __ldcg(reinterpret_cast<const uint4 *>(o.tok) + k);
+                    const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(o.hot));
+                    h = *reinterpret_cast<const EnvHot *>(&hv);
+                    consumed++;
+                } else n_err++;
+            }
+            observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of(h, mem), w);
+            const size_t oi = (size_t)t * n + env;
+            reward[oi] = rew;
+            done[oi] = dn ? 1 : 0;
+            if (dirs) dirs[oi] = (int8_t)(h.dirflags & 3);
+        }
+        stage_obs(tile, w, lane);
+        __syncwarp();
+        if (nv > 0) store_tile(tile, obs + ((size_t)t * n + env0) * OBS_BYTES, lane, nv);
+        __syncwarp();                              // the tile is rewritten in the next iteration
+    }
+    // ---- store the state back ---------------------------------------------------------------------
+    __syncwarp();
+    warp_copy_records<false>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
+    warp_copy_records<false>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
+    warp_copy_records<false>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
+    if (valid) {
+        P.hot[env] = h;
+        P.head[env] = head + consumed;
+        if (mode == BB_MODE_FREEZE) P.last_reward[env] = last_rew;
+    }
+    // counters: warp sums, one RED per counter per warp
+    for (int off = 16; off; off >>= 1) {
+        n_step += __shfl_down_sync(0xFFFFFFFFu, n_step, off); n_end += __shfl_down_sync(0xFFFFFFFFu, n_end, off);
+        n_succ += __shfl_down_sync(0xFFFFFFFFu, n_succ, off); n_err += __shfl_down_sync(0xFFFFFFFFu, n_err, off);
+    }
+    if (lane == 0) {
+        unsigned long long *c = P.warp_counters + 4ull * (blockIdx.x * R_WARPS + warp);
+        if (n_step) atomicAdd(c + 0, (unsigned long long)n_step);
+        if (n_end) atomicAdd(c + 1, (unsigned long long)n_end);
+        if (n_succ) atomicAdd(c + 2, (unsigned long long)n_succ);
+        if (n_err) atomicAdd(c + 3, (unsigned long long)n_err);
+    }
+}
+
 // Level generation, decoupled from the step: tops every environment's ring up to `target` levels.
 //
 // ONE WARP PER ENVIRONMENT.  Generation is a long, branchy, data-dependent rejection-sampling program;
@@ -612,6 +771,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
+    bool no_persistent, after_rollout;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 0 = k_step8 (8 lanes per env, default), 1 = k_step (lane per env), 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
     cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
@@ -723,6 +883,16 @@ static int sched_join(bb_pool *p, cudaStream_t st)
     return 0;
 }
 
+// leaving rollout mode: the rings only hold >= D - T levels; make this a proper sync point again
+static int sched_leave_rollout(bb_pool *p, cudaStream_t st)
+{
+    if (!p->after_rollout) return 0;
+    if (sched_join(p, st)) return 1;
+    if (p->mode == BB_MODE_AUTORESET) launch_gen(p, st);
+    p->after_rollout = false;
+    return 0;
+}
+
 extern "C" {
 
 const char *bb_last_error(void) { return g_err; }
@@ -749,14 +919,15 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
-    p->D = p->lp.cells_pad <= 256 ? 32 : 8;
-    if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 64) p->D = d; }
+    p->D = p->lp.cells_pad <= 256 ? 96 : 8;             // small grids: >= 2 x the 40-step rollout of bb_pool_rollout
+    if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 256) p->D = d; }
     p->G = p->D >= 8 ? p->D / 8 : 1;
     if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
     p->nev = p->D / p->G + 3;
     if (p->nev > MAX_GEN_EVENTS) { delete p; return fail("ring depth / generation period too large"); }
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
     p->step_kernel = 0;
+    p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
     if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : 0;
     p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr;
     const LevelParams &lp = p->lp;
@@ -778,6 +949,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CU(cudaMemset(P.locked_room, 0xFF, n));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&p->gen_stream, cudaStreamNonBlocking));
+    CU(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < p->nev; i++) CU(cudaEventCreateWithFlags(&p->gen_ev[i], cudaEventDisableTiming));
@@ -820,7 +992,7 @@ int bb_pool_seed(bb_pool *p, const uint64_t *seeds_host)
     if (!p || !seeds_host) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
-    p->gen_outstanding = false; p->rel = 0;
+    p->gen_outstanding = false; p->rel = 0; p->after_rollout = false;
     // stream-ordered copy: a synchronous cudaMemcpy from pageable memory may return before its last
     // chunk has landed, and p->stream (non-blocking) is not ordered after the legacy stream
     CU(cudaMemcpyAsync(p->d_seeds, seeds_host, (size_t)p->n * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
@@ -837,7 +1009,7 @@ int bb_pool_set_mode(bb_pool *p, int32_t mode)
     if (!p || (mode != BB_MODE_AUTORESET && mode != BB_MODE_FREEZE)) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
-    p->gen_outstanding = false; p->rel = 0;
+    p->gen_outstanding = false; p->rel = 0; p->after_rollout = false;
     p->mode = mode;
     if (mode == BB_MODE_AUTORESET) { launch_gen(p, p->stream); CU(cudaStreamSynchronize(p->stream)); }
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
@@ -850,6 +1022,7 @@ int bb_pool_reset(bb_pool *p, uint8_t *obs_dev, int8_t *dir_dev, void *stream)
     CU(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (sched_join(p, st)) return 1;
+    p->after_rollout = false;
     launch_gen(p, st);                                 // make sure every ring holds a level
     launch_step(p, nullptr, 1, obs_dev, nullptr, nullptr, dir_dev, 1, st);
     if (p->mode == BB_MODE_AUTORESET) launch_gen(p, st);      // rings full again: a sync point
@@ -864,6 +1037,7 @@ int bb_pool_step(bb_pool *p, const void *actions_dev, int32_t action_bytes, uint
     if (action_bytes != 1 && action_bytes != 8) return fail("action_bytes must be 1 or 8");
     CU(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (sched_leave_rollout(p, st)) return 1;
     if (sched_before_step(p, p->rel, st)) return 1;
     launch_step(p, actions_dev, action_bytes, obs_dev, reward_dev, done_dev, dir_dev, 0, st);
     if (sched_after_step(p, p->rel, st)) return 1;
@@ -879,6 +1053,7 @@ int bb_pool_step_timed(bb_pool *p, const void *actions_dev, int32_t action_bytes
     CU(cudaSetDevice(p->device));
     if (!p->ev[0]) for (int i = 0; i < 3; i++) CU(cudaEventCreate(&p->ev[i]));
     if (sched_join(p, p->stream)) return 1;
+    p->after_rollout = false;
     launch_gen(p, p->stream);                           // rings full before the timed pair
     CU(cudaEventRecord(p->ev[0], p->stream));
     launch_step(p, actions_dev, action_bytes, obs_dev, reward_dev, done_dev, dir_dev, 0, p->stream);
@@ -891,12 +1066,50 @@ int bb_pool_step_timed(bb_pool *p, const void *actions_dev, int32_t action_bytes
     return 0;
 }
 
+// T steps per launch.  Small grids with a ring deep enough (D >= 2T): the persistent kernel k_rollout, with
+// k_gen refilling on the side stream what the PREVIOUS launch consumed (head snapshot taken before this
+// launch starts, so generation never writes a slot this launch may read).  Otherwise: a captured CUDA graph
+// of T per-step launches with the k_gen branch forked and joined inside.
+static int rollout_graph(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *obs_dev, float *reward_dev,
+                         uint8_t *done_dev, int8_t *dir_dev, cudaStream_t user);
+
 int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *obs_dev, float *reward_dev,
                     uint8_t *done_dev, int8_t *dir_dev, void *stream)
 {
     if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || T < 1) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     cudaStream_t user = (cudaStream_t)stream;
+    const bool persistent = p->lp.cells_pad <= 128 && !p->no_persistent && (p->mode == BB_MODE_FREEZE || p->D >= 2 * T);
+    if (!persistent) return rollout_graph(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, user);
+    if (sched_join(p, user)) return 1;                 // every k_gen enqueued so far (rings topped up to D - what
+                                                       // the previous rollout consumed >= D - T >= T levels per env)
+    const int gs = (p->lp.cells_pad >> 2) | 1;
+    const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
+    const size_t smem = (size_t)R_WARPS * warp_words * 4;
+    const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
+    if (p->mode == BB_MODE_AUTORESET) {
+        // fork: generation for the levels consumed before this launch, concurrently with it
+        const size_t nb = (size_t)p->n * sizeof(uint32_t);
+        CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
+        CU(cudaEventRecord(p->ev_fork, user));
+        CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
+        cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), p->gen_stream);
+        k_gen<<<p->gen_blocks, GEN_THREADS, 0, p->gen_stream>>>(p->lp, p->P, p->n, p->D);
+        cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
+        p->gen_outstanding = true;
+        p->launches++;
+    }
+    k_rollout<<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+    p->launches++;
+    p->rel = 0;
+    p->after_rollout = true;                           // a per-step call that follows tops the rings up first
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int rollout_graph(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *obs_dev, float *reward_dev,
+                         uint8_t *done_dev, int8_t *dir_dev, cudaStream_t user)
+{
     GraphKey key = { actions_dev, obs_dev, reward_dev, done_dev, dir_dev, T, p->mode };
     if (!p->graph || memcmp(&key, &p->gkey, sizeof key) != 0) {
         if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
@@ -924,6 +1137,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaGraphDestroy(g));
         p->gkey = key;
     }
+    if (sched_leave_rollout(p, user)) return 1;
     if (sched_join(p, user)) return 1;                  // per-step k_gens still in flight come first
     CU(cudaGraphLaunch(p->graph, user));
     p->rel = 0;                                         // the graph ends with its k_gens joined: a sync point
@@ -939,6 +1153,7 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
     const size_t n = (size_t)p->n;
     memcpy(p->h_act, actions_host, n);
     CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, p->stream));
+    if (sched_leave_rollout(p, p->stream)) return 1;
     if (sched_before_step(p, p->rel, p->stream)) return 1;
     launch_step(p, p->d_act, 1, p->d_obs, p->d_rew, p->d_done, p->d_dir, 0, p->stream);
     if (sched_after_step(p, p->rel, p->stream)) return 1;
