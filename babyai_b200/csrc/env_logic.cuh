@@ -76,6 +76,11 @@ struct LevelParams {
     int32_t rs_g, rs_t, gt_off;   // grid bytes of one env: G = H rows x rs_g at 0, GT = W rows x rs_t at gt_off
     uint64_t locked_thr;          // rand_float(0,1) < p  <=>  u32 < ceil(p * 2^32)
     uint32_t wall_rows[MAXH];     // bit x of row y: (x, y) is a wall of the empty RoomGrid
+    // single-room levels up to 8x8 ("small"): bitboard (bit 8 y + x) of walls and of everything outside the grid,
+    // and the byte rows of the empty room for both stored orientations (G rows 0..7, GT rows 8..15)
+    int32_t small;
+    uint64_t wall64;
+    uint64_t row_tmpl[16];
 };
 
 // ---- per-environment records (struct-of-arrays over envs, one array each) ---
@@ -113,15 +118,11 @@ BB_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 #endif
 }
 
-// Per-env random stream.  Host build (tests/hostemu): scalar.  Device build: the
-// WHOLE WARP runs generate_level() for one environment with identical control
-// flow (k_gen maps one warp to one refill-list entry), so the 32 lanes compute 32
-// consecutive Philox blocks (128 draws) at once and a draw is a shuffle from the
-// lane that holds its block.
-struct Rng {
+// Per-env random stream, scalar form: one lane owns the stream (generate_small, host build).
+struct RngScalar {
     uint32_t k0, k1;
     uint64_t draws;
-    uint64_t blk;                 // block held in b0..b3 (device: by lane 0; lane l holds blk + l); ~0 = none
+    uint64_t blk;                 // block held in b0..b3; ~0 = none
     uint32_t b0, b1, b2, b3;
 
     BB_HD void init(uint64_t seed, uint64_t d)
@@ -147,17 +148,8 @@ struct Rng {
         const uint64_t i = draws++;
         const uint64_t nb = i >> 2;
         const uint32_t w = (uint32_t)i & 3u;
-#if defined(__CUDA_ARCH__)
-        if (blk == ~0ull || nb - blk >= 32ull) {          // warp-uniform condition
-            blk = nb;
-            refill(nb + (threadIdx.x & 31));
-        }
-        const uint32_t mine = w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
-        return __shfl_sync(0xFFFFFFFFu, mine, (int)(nb - blk));
-#else
         if (nb != blk) { blk = nb; refill(nb); }
         return w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
-#endif
     }
     // MiniGridEnv._rand_int(lo, hi); a range of one value consumes no draw
     BB_HD int randint(int lo, int hi)
@@ -167,6 +159,33 @@ struct Rng {
         return lo + (int)mulhi32(u32(), n);
     }
     BB_HD bool randbool() { return randint(0, 2) == 0; }
+};
+
+// Warp-cooperative form (generate_level on the device): the WHOLE WARP runs one environment with identical
+// control flow, the 32 lanes compute 32 consecutive Philox blocks (128 draws) at once and a draw is a shuffle
+// from the lane that holds its block.  In the host build it is the scalar generator.
+struct Rng : RngScalar {
+#if defined(__CUDA_ARCH__)
+    __device__ __forceinline__ uint32_t u32()
+    {
+        const uint64_t i = draws++;
+        const uint64_t nb = i >> 2;
+        const uint32_t w = (uint32_t)i & 3u;
+        if (blk == ~0ull || nb - blk >= 32ull) {          // warp-uniform condition
+            blk = nb;
+            refill(nb + (threadIdx.x & 31));
+        }
+        const uint32_t mine = w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
+        return __shfl_sync(0xFFFFFFFFu, mine, (int)(nb - blk));
+    }
+    __device__ __forceinline__ int randint(int lo, int hi)
+    {
+        uint32_t n = (uint32_t)(hi - lo);
+        if (n == 1) return lo;
+        return lo + (int)mulhi32(u32(), n);
+    }
+    __device__ __forceinline__ bool randbool() { return randint(0, 2) == 0; }
+#endif
 };
 
 BB_HD int popc32(uint32_t v)
@@ -256,6 +275,10 @@ BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
             if (j < R - 1) g.m->door_x_down[r] = (uint8_t)g.rng.randint(tx + 1, tx + S - 1);
         }
     g.door_right = g.door_down = g.room_locked = 0;
+    {   // unused object-table entries are zero (deterministic state bytes)
+        uint32_t *ow = reinterpret_cast<uint32_t *>(&g.m->obj);
+        for (int k = 0; k < (int)(sizeof(ObjTab) / 4); k++) ow[k] = 0;
+    }
     g.nobj = 0;
     g.ax = (C / 2) * (S - 1) + S / 2;
     g.ay = (R / 2) * (S - 1) + S / 2;
@@ -735,6 +758,201 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     else if (g.root_kind == R_AFTER) { tok[n++] = W_AFTER; tok[n++] = W_YOU; n = tok_side(g, 1, tok, n); }
     for (int k = lane; k < lp.max_tokens; k += nlanes) o.tok[k] = k < n ? tok[k] : (int16_t)0;
     return attempts;
+}
+
+// =============================================================================
+// Small-level generator: ONE LANE PER LEVEL, written as a single flat loop
+// =============================================================================
+// For single-room levels up to 8x8 (GoToRedBall*, GoToObj*, GoToLocal*, PickupLoc) the whole generator state
+// fits in registers: occupancy is a 64-bit board, the objects are two packed 64-bit words.  The reference's
+// nested rejection loops (attempts > placements > tries) are flattened into ONE loop whose body performs one
+// RNG-consuming event chosen by a phase variable.  Every lane of a warp runs that same loop on a different
+// environment: lanes differ only in predicates and trip count and reconverge at every iteration, which the
+// nested-loop form (generate_level) cannot do -- that is why it had to be run one warp per level.
+// Draw order and accept/reject rules are exactly those of generate_level; the two are cross-checked level by
+// level in the host build (tests/hostemu) and both against the oracle.
+struct SmallLevel {             // everything emit_small_level() needs
+    uint64_t poss;              // 6 bits per object: x | y << 3
+    uint64_t tcs;               // 6 bits per object: type | color << 3
+    int nobj, ax, ay, adir;
+    int leaf_kind, d_type, d_color, d_loc;
+    uint32_t d_mask;
+};
+
+enum : int { PH_START = 0, PH_AGENT, PH_OBJ, PH_CHECK, PH_PICK, PH_DESC, PH_DONE };
+
+BB_HD int sm_obj_x(uint64_t poss, int k) { return (int)((poss >> (6 * k)) & 7u); }
+BB_HD int sm_obj_y(uint64_t poss, int k) { return (int)((poss >> (6 * k + 3)) & 7u); }
+BB_HD int sm_obj_tc(uint64_t tcs, int k) { return (int)((tcs >> (6 * k)) & 63u); }
+
+// ObjDesc.find_matching_objs over the packed objects (single room: every object is in the agent's room)
+BB_HD uint32_t sm_match(const SmallLevel &L, int type, int color, int loc)
+{
+    const int d1x = dir_dx(L.adir), d1y = dir_dy(L.adir), d2x = -d1y, d2y = d1x;
+    uint32_t m = 0;
+    for (int k = 0; k < L.nobj; k++) {
+        const int tc = sm_obj_tc(L.tcs, k);
+        if (type != ANY_TYPE && (tc & 7) != type) continue;
+        if (color != ANY && (tc >> 3) != color) continue;
+        if (loc != LOC_NONE) {
+            const int vx = sm_obj_x(L.poss, k) - L.ax, vy = sm_obj_y(L.poss, k) - L.ay;
+            const int dot1 = vx * d1x + vy * d1y, dot2 = vx * d2x + vy * d2y;
+            const bool ok = loc == LOC_LEFT ? dot2 < 0 : loc == LOC_RIGHT ? dot2 > 0 : loc == LOC_FRONT ? dot1 > 0 : dot1 < 0;
+            if (!ok) continue;
+        }
+        m |= 1u << k;
+    }
+    return m;
+}
+
+// Generates one level of a small single-room environment.  Returns the number of attempts.
+BB_HD int generate_small(const LevelParams &lp, RngScalar &rng, SmallLevel &L)
+{
+    const int S = lp.room_size, n = lp.num_dists;
+    const bool levelgen = lp.kind == KIND_LEVELGEN;
+    const int nplace = n + (lp.kind == KIND_REDBALL ? 1 : 0);   // objects placed per attempt
+    uint64_t occ = 0, fill = 0;
+    int phase = PH_START, tries = 0, k = 0, attempts = 0, cur_tc = 0;
+    bool agent_placed = true;
+    L.poss = 0; L.tcs = 0; L.nobj = 0; L.ax = L.ay = L.adir = 0;
+    L.leaf_kind = lp.kind == KIND_OBJ ? lp.instr : (levelgen ? lp.action_kinds[0] : I_GOTO);
+    L.d_type = ANY_TYPE; L.d_color = ANY; L.d_loc = LOC_NONE; L.d_mask = 0;
+    while (phase != PH_DONE) {
+        if (phase == PH_START) {                     // RoomGrid._gen_grid of one room: no draws
+            attempts++;
+            occ = lp.wall64; L.poss = 0; L.tcs = 0; L.nobj = 0; k = 0; tries = 0;
+            L.ax = S / 2; L.ay = S / 2; L.adir = 0; agent_placed = true;
+            if (levelgen) { (void)rng.u32(); phase = n > 0 ? PH_OBJ : PH_AGENT; }     // `_rand_float(0,1) < 0`: one draw
+            else phase = PH_AGENT;
+        } else if (phase == PH_AGENT) {              // RoomGrid.place_agent -> MiniGridEnv.place_agent tries
+            if (tries > 1000) { phase = PH_START; continue; }
+            tries++;
+            const int x = rng.randint(0, S), y = rng.randint(0, S);
+            if ((occ >> (8 * y + x)) & 1u) continue;
+            L.ax = x; L.ay = y; agent_placed = true;
+            L.adir = rng.randint(0, 4);
+            const int fb = 8 * (y + dir_dy(L.adir)) + x + dir_dx(L.adir);
+            const bool front_ok = !((occ >> fb) & 1u) || ((lp.wall64 >> fb) & 1u);
+            tries = 0;                               // each inner place_agent call counts its own tries
+            if (!front_ok) continue;
+            if (levelgen) phase = lp.unblocking ? PH_DESC : PH_CHECK;
+            else phase = nplace > 0 ? PH_OBJ : PH_CHECK;
+            if (phase == PH_CHECK) fill = 0;
+        } else if (phase == PH_OBJ) {                // add_object / add_distractors: one placement try
+            if (tries == 0) {
+                if (lp.kind == KIND_REDBALL && k == 0) cur_tc = T_BALL | (C_RED << 3);
+                else {
+                    const int color = color_by_name_rank(rng.randint(0, 6));
+                    const int t = rng.randint(0, 3);
+                    cur_tc = (t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX) | (color << 3);
+                }
+            }
+            if (tries > 1000) { phase = PH_START; continue; }
+            tries++;
+            const int x = rng.randint(0, S), y = rng.randint(0, S);
+            if ((occ >> (8 * y + x)) & 1u) continue;
+            if (agent_placed && x == L.ax && y == L.ay) continue;
+            if (iabs(L.ax - x) + iabs(L.ay - y) < 2) continue;            // reject_next_to
+            occ |= 1ull << (8 * y + x);
+            L.poss |= (uint64_t)(x | (y << 3)) << (6 * k);
+            L.tcs |= (uint64_t)cur_tc << (6 * k);
+            k++; L.nobj = k; tries = 0;
+            if (k == nplace) {
+                if (lp.kind == KIND_REDBALL && lp.grey_dists)              // GoToRedBallGrey: distractors turn grey
+                    for (int q = 1; q < k; q++) L.tcs = (L.tcs & ~(56ull << (6 * q))) | ((uint64_t)(C_GREY << 3) << (6 * q));
+                if (levelgen) { phase = PH_AGENT; agent_placed = false; }   // MiniGridEnv.place_agent: agent_pos = None
+                else { phase = PH_CHECK; fill = 0; }
+            }
+        } else if (phase == PH_CHECK) {              // check_objs_reachable: bitboard flood fill, two sweeps per iteration
+            if (fill == 0) fill = 1ull << (8 * L.ay + L.ax);
+            const uint64_t pass = ~occ;
+            uint64_t f1 = fill | ((fill << 1 | fill >> 1 | fill << 8 | fill >> 8) & pass);
+            f1 |= (f1 << 1 | f1 >> 1 | f1 << 8 | f1 >> 8) & pass;
+            if (f1 != fill) { fill = f1; continue; }
+            const uint64_t near = fill | fill << 1 | fill >> 1 | fill << 8 | fill >> 8;
+            const uint64_t things = occ & ~lp.wall64;
+            if (things & ~near) { phase = PH_START; continue; }            // RejectSampling
+            phase = levelgen ? PH_DESC : (lp.kind == KIND_OBJ ? PH_PICK : PH_DONE);
+            tries = 0;
+            if (phase == PH_DONE) {                                        // GoToRedBall: the ball's descriptor
+                const int tc = sm_obj_tc(L.tcs, 0);
+                L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
+                L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
+            }
+        } else if (phase == PH_PICK) {               // obj = self._rand_elem(objs)
+            const int tc = sm_obj_tc(L.tcs, rng.randint(0, n));
+            L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
+            L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
+            phase = PH_DONE;
+        } else {                                     // PH_DESC: LevelGen.rand_obj, one try
+            if (tries > 100) { phase = PH_START; continue; }
+            tries++;
+            const int ci = rng.randint(0, 7);
+            const int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
+            const int ntypes = L.leaf_kind == I_GOTO ? 4 : 3;
+            const int ti = rng.randint(0, ntypes);
+            const int type = ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR;
+            int loc = LOC_NONE;
+            if (lp.locations && rng.randbool()) loc = rng.randint(0, 4);
+            const uint32_t m = sm_match(L, type, color, loc);
+            if (m == 0) continue;
+            L.d_type = type; L.d_color = color; L.d_loc = loc; L.d_mask = m;
+            phase = PH_DONE;
+        }
+    }
+    return attempts;
+}
+
+// SmallLevel -> the records of a level slot (grid in both orientations, object table, verifier, tokens, hot)
+BB_HD void emit_small_level(const LevelParams &lp, const SmallLevel &L, const LevelOut &o)
+{
+    uint64_t rows[16];
+    for (int r = 0; r < 16; r++) rows[r] = lp.row_tmpl[r];
+    ObjTab ot;
+    for (int k = 0; k < MAXOBJ; k++) { ot.x[k] = 0; ot.y[k] = 0; ot.tc[k] = 0; }
+    for (int k = 0; k < L.nobj; k++) {
+        const int x = sm_obj_x(L.poss, k), y = sm_obj_y(L.poss, k), tc = sm_obj_tc(L.tcs, k);
+        ot.x[k] = (uint8_t)x; ot.y[k] = (uint8_t)y; ot.tc[k] = (uint8_t)tc;
+        rows[y] = (rows[y] & ~(0xFFull << (8 * x))) | ((uint64_t)tc << (8 * x));
+        rows[8 + x] = (rows[8 + x] & ~(0xFFull << (8 * y))) | ((uint64_t)tc << (8 * y));
+    }
+    // rs_g = rs_t = 4 or 8 bytes per stored row
+    if (lp.rs_g == 8) {
+        uint64_t *g = reinterpret_cast<uint64_t *>(o.grid);
+        for (int r = 0; r < lp.H; r++) g[r] = rows[r];
+        uint64_t *gt = reinterpret_cast<uint64_t *>(o.grid + lp.gt_off);
+        for (int r = 0; r < lp.W; r++) gt[r] = rows[8 + r];
+    } else {
+        uint32_t *g = reinterpret_cast<uint32_t *>(o.grid);
+        for (int r = 0; r < lp.H; r++) g[r] = (uint32_t)rows[r];
+        uint32_t *gt = reinterpret_cast<uint32_t *>(o.grid + lp.gt_off);
+        for (int r = 0; r < lp.W; r++) gt[r] = (uint32_t)rows[8 + r];
+    }
+    *o.obj = ot;
+    InstrRec ins;
+    for (int k = 0; k < 8; k++) ins.desc_mask[k] = 0;
+    ins.desc_mask[0] = L.d_mask;
+    for (int k = 0; k < 4; k++) { ins.leaf_kind[k] = (uint8_t)I_NONE; ins.leaf_pre[k] = NO_OBJ; }
+    ins.leaf_kind[0] = (uint8_t)L.leaf_kind;
+    ins.root_kind = R_SINGLE; ins.side_and = 0; ins.flags = 0; ins.pad0 = 0; ins.pad1 = 0;
+    *o.ins = ins;
+    EnvHot h;
+    h.x = (uint8_t)L.ax; h.y = (uint8_t)L.ay; h.dirflags = (uint8_t)L.adir; h.carry = NO_OBJ;
+    h.step_count = 0; h.max_steps = (uint16_t)lp.nav_time_maze;          // one non-PutNext leaf: one navigation
+    h.cur_mask = (1u << L.nobj) - 1u; h.snap_mask = h.cur_mask;
+    *o.hot = h;
+    // "go to" / "pick up" + ObjDesc.surface
+    int16_t tok[16];
+    int nt = 0;
+    if (L.leaf_kind == I_GOTO) { tok[nt++] = W_GO; tok[nt++] = W_TO; } else { tok[nt++] = W_PICK; tok[nt++] = W_UP; }
+    tok[nt++] = popc32(L.d_mask) > 1 ? W_A : W_THE;
+    if (L.d_color != ANY) tok[nt++] = (int16_t)(W_RED + L.d_color);
+    tok[nt++] = (int16_t)(L.d_type == ANY_TYPE ? W_OBJECT : L.d_type == T_BOX ? W_BOX : L.d_type == T_BALL ? W_BALL : L.d_type == T_KEY ? W_KEY : W_DOOR);
+    if (L.d_loc == LOC_FRONT) { tok[nt++] = W_IN; tok[nt++] = W_FRONT; tok[nt++] = W_OF; tok[nt++] = W_YOU; }
+    else if (L.d_loc == LOC_BEHIND) { tok[nt++] = W_BEHIND; tok[nt++] = W_YOU; }
+    else if (L.d_loc == LOC_LEFT) { tok[nt++] = W_ON; tok[nt++] = W_YOUR; tok[nt++] = W_LEFT; }
+    else if (L.d_loc == LOC_RIGHT) { tok[nt++] = W_ON; tok[nt++] = W_YOUR; tok[nt++] = W_RIGHT; }
+    for (int k = 0; k < lp.max_tokens; k++) o.tok[k] = k < nt ? tok[k] : (int16_t)0;
 }
 
 // =============================================================================

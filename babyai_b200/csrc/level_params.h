@@ -63,6 +63,27 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
             if (x % (s->room_size - 1) == 0 || y % (s->room_size - 1) == 0) row |= 1u << x;
         lp->wall_rows[y] = row;
     }
+    // small single-room levels: bitboard walls + byte rows of the empty room (generate_small / emit_small_level)
+    lp->small = 0;
+    const bool lg_ok = s->kind != BB_KIND_LEVELGEN ||
+        (s->locked_room_prob <= 0 && s->n_instr_kinds == 1 && s->instr_kinds[0] == BB_K_ACTION && s->n_action_kinds == 1 &&
+         (s->action_kinds[0] == BB_I_GOTO || s->action_kinds[0] == BB_I_PICKUP));
+    if (s->num_rows == 1 && s->num_cols == 1 && lp->W <= 8 && lp->H <= 8 && s->num_dists + 1 <= 10 && lg_ok) {
+        lp->small = 1;
+        lp->wall64 = 0;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++)
+                if (x >= lp->W || y >= lp->H || ((lp->wall_rows[y] >> x) & 1u)) lp->wall64 |= 1ull << (8 * y + x);
+        for (int r = 0; r < 16; r++) {
+            uint64_t row = 0;
+            for (int c = 0; c < 8; c++) {
+                const int x = r < 8 ? c : r - 8, y = r < 8 ? r : c;      // G row r = y; GT row r - 8 = x
+                const bool wall = x >= lp->W || y >= lp->H || ((lp->wall_rows[y < lp->H ? y : 0] >> x) & 1u);
+                row |= (uint64_t)(wall ? CELL_WALL : CELL_EMPTY) << (8 * c);
+            }
+            lp->row_tmpl[r] = row;
+        }
+    }
     return nullptr;
 }
 

@@ -739,6 +739,54 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
     }
 }
 
+// Level generation for small single-room levels: ONE LANE PER ENVIRONMENT running the flat state-machine
+// generator (generate_small): lanes differ only in predicates and trip counts, so the warp stays converged;
+// emit_small_level() then runs for all lanes together.  A ticket is 32 consecutive environments.
+constexpr int GS_THREADS = 128;
+__global__ void __launch_bounds__(GS_THREADS)
+k_gen_small(const LevelParams lp, const PoolPtrs P, const int n, const int target)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nchunks = (uint32_t)((n + 31) / 32);
+    const uint32_t D = (uint32_t)P.depth;
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(P.gen_ticket, 1u);
+        c = __shfl_sync(FULL, c, 0);
+        if (c >= nchunks) break;
+        const int env = (int)c * 32 + lane;
+        uint32_t tl = 0; int missing = 0;
+        if (env < n) {
+            const uint32_t hd = P.head_snap[env];
+            tl = P.tail[env];
+            missing = target - (int)(tl - hd);
+            if (missing < 0) missing = 0;
+        }
+        int maxm = missing;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) maxm = max(maxm, __shfl_xor_sync(FULL, maxm, off));
+        if (maxm == 0) continue;
+        RngScalar rng;
+        rng.init(0, 0);
+        if (missing > 0) { const RngRec r = P.rng[env]; rng.init(r.seed, r.draws); }
+        int att = 0;
+        for (int j = 0; j < maxm; j++) {                       // warp-uniform
+            SmallLevel L;
+            const bool active = j < missing;
+            if (active) att += generate_small(lp, rng, L);
+            __syncwarp();
+            if (active) emit_small_level(lp, L, ring_slot(lp, P, env, (int)((tl + (uint32_t)j) % D)));
+        }
+        if (missing > 0) {
+            RngRec r; r.seed = ((uint64_t)rng.k1 << 32) | rng.k0; r.draws = rng.draws;
+            P.rng[env] = r;
+            P.tail[env] = tl + (uint32_t)missing;
+            P.attempts[env] += (uint32_t)att;
+        }
+    }
+}
+
 __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -771,6 +819,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
+    bool gen_generic; int gen_small_blocks;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 0 = k_step8 (8 lanes per env, default), 1 = k_step (lane per env), 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
@@ -809,6 +858,15 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
     return e ? fail("%s", e) : 0;
 }
 
+static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st)
+{
+    if (p->lp.small && !p->gen_generic) {
+        int blocks = (p->n + 32 * (GS_THREADS / 32) - 1) / (32 * (GS_THREADS / 32));
+        if (blocks > p->gen_small_blocks) blocks = p->gen_small_blocks;
+        k_gen_small<<<blocks, GS_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    } else k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+}
+
 // One generation pass on stream `st`: snapshot the consumption counters, reset the work-ticket counter,
 // run k_gen, then publish the production counters.  The two small device-to-device copies replace
 // __threadfence() pairs in the kernels (a gpu-scope fence invalidates the SM's whole L1).
@@ -818,7 +876,7 @@ static void launch_gen(bb_pool *p, cudaStream_t st)
     const size_t nb = (size_t)p->n * sizeof(uint32_t);
     cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, st);
     cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), st);
-    k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    launch_gen_kernel(p, target, st);
     cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, st);
     p->launches++;
 }
@@ -916,7 +974,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         int want = ((n_envs + GEN_CHUNK - 1) / GEN_CHUNK + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);
         int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
+        p->gen_small_blocks = prop.multiProcessorCount * 4;
     }
+    p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
     p->D = p->lp.cells_pad <= 256 ? 96 : 8;             // small grids: >= 2 x the 40-step rollout of bb_pool_rollout
@@ -1094,7 +1154,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaEventRecord(p->ev_fork, user));
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
         cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), p->gen_stream);
-        k_gen<<<p->gen_blocks, GEN_THREADS, 0, p->gen_stream>>>(p->lp, p->P, p->n, p->D);
+        launch_gen_kernel(p, p->D, p->gen_stream);
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
         p->gen_outstanding = true;
         p->launches++;

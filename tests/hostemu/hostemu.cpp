@@ -32,12 +32,42 @@ static void make_params(const bb_level_spec *s, LevelParams *lp)
     lp->max_tokens = MAXTOK;
 }
 
+// env var HOSTEMU_GEN=generic forces the nested-loop generator; default: the flat small-level generator when the
+// level qualifies, and in that case BOTH are run and every output byte compared.
+static bool records_equal(const LevelParams &lp, Slot &a, Slot &b)
+{
+    return memcmp(a.grid.data(), b.grid.data(), lp.cells_pad) == 0 && memcmp(&a.hot, &b.hot, sizeof(EnvHot)) == 0 &&
+           memcmp(&a.obj, &b.obj, sizeof(ObjTab)) == 0 && memcmp(&a.ins, &b.ins, sizeof(InstrRec)) == 0 &&
+           memcmp(a.tok.data(), b.tok.data(), lp.max_tokens * sizeof(int16_t)) == 0;
+}
 static void gen_spare(HPool *p, int e)
 {
     Slot &s = p->spare[e];
     LevelOut o; o.grid = s.grid.data(); o.hot = &s.hot; o.obj = &s.obj; o.ins = &s.ins; o.tok = s.tok.data();
-    GenMem mem;
-    p->attempts[e] += (uint32_t)generate_level(p->lp, o, &p->rng[e], &p->locked_room[e], &mem);
+    const char *force = getenv("HOSTEMU_GEN");
+    if (p->lp.small && !(force && !strcmp(force, "generic"))) {
+        RngRec r0 = p->rng[e];
+        RngScalar rng; rng.init(r0.seed, r0.draws);
+        SmallLevel L;
+        int att = generate_small(p->lp, rng, L);
+        memset(s.grid.data(), 0, s.grid.size());
+        emit_small_level(p->lp, L, o);
+        // cross-check with the nested-loop generator from the same stream position
+        Slot ref = s; ref.grid.assign(s.grid.size(), 0);
+        LevelOut oref; oref.grid = ref.grid.data(); oref.hot = &ref.hot; oref.obj = &ref.obj; oref.ins = &ref.ins; oref.tok = ref.tok.data();
+        GenMem mem; uint8_t lr = p->locked_room[e]; RngRec r1 = r0;
+        int att2 = generate_level(p->lp, oref, &r1, &lr, &mem);
+        if (att != att2 || r1.draws != rng.draws || !records_equal(p->lp, s, ref)) {
+            fprintf(stderr, "hostemu: generate_small != generate_level (env %d: attempts %d/%d draws %llu/%llu)\n", e, att, att2,
+                    (unsigned long long)rng.draws, (unsigned long long)r1.draws);
+            abort();
+        }
+        p->rng[e].draws = rng.draws;
+        p->attempts[e] += (uint32_t)att;
+    } else {
+        GenMem mem;
+        p->attempts[e] += (uint32_t)generate_level(p->lp, o, &p->rng[e], &p->locked_room[e], &mem);
+    }
     p->sready[e] = 1;
 }
 
