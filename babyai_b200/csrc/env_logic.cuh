@@ -805,102 +805,122 @@ BB_HD uint32_t sm_match(const SmallLevel &L, int type, int color, int loc)
     return m;
 }
 
-// Generates one level of a small single-room environment.  Returns the number of attempts.
-BB_HD int generate_small(const LevelParams &lp, RngScalar &rng, SmallLevel &L)
+// Generator state of one lane; small_gen_step() performs ONE iteration of the flat loop.
+struct SmallGen {
+    RngScalar rng;
+    SmallLevel L;
+    uint64_t occ, fill;
+    int phase, tries, k, attempts, cur_tc;
+    bool agent_placed;
+};
+
+BB_HD void small_gen_begin(const LevelParams &lp, SmallGen &g)
+{
+    const bool levelgen = lp.kind == KIND_LEVELGEN;
+    g.occ = 0; g.fill = 0; g.phase = PH_START; g.tries = 0; g.k = 0; g.attempts = 0; g.cur_tc = 0; g.agent_placed = true;
+    g.L.poss = 0; g.L.tcs = 0; g.L.nobj = 0; g.L.ax = g.L.ay = g.L.adir = 0;
+    g.L.leaf_kind = lp.kind == KIND_OBJ ? lp.instr : (levelgen ? lp.action_kinds[0] : I_GOTO);
+    g.L.d_type = ANY_TYPE; g.L.d_color = ANY; g.L.d_loc = LOC_NONE; g.L.d_mask = 0;
+}
+
+BB_HD void small_gen_step(const LevelParams &lp, SmallGen &g)
 {
     const int S = lp.room_size, n = lp.num_dists;
     const bool levelgen = lp.kind == KIND_LEVELGEN;
     const int nplace = n + (lp.kind == KIND_REDBALL ? 1 : 0);   // objects placed per attempt
-    uint64_t occ = 0, fill = 0;
-    int phase = PH_START, tries = 0, k = 0, attempts = 0, cur_tc = 0;
-    bool agent_placed = true;
-    L.poss = 0; L.tcs = 0; L.nobj = 0; L.ax = L.ay = L.adir = 0;
-    L.leaf_kind = lp.kind == KIND_OBJ ? lp.instr : (levelgen ? lp.action_kinds[0] : I_GOTO);
-    L.d_type = ANY_TYPE; L.d_color = ANY; L.d_loc = LOC_NONE; L.d_mask = 0;
-    while (phase != PH_DONE) {
-        if (phase == PH_START) {                     // RoomGrid._gen_grid of one room: no draws
-            attempts++;
-            occ = lp.wall64; L.poss = 0; L.tcs = 0; L.nobj = 0; k = 0; tries = 0;
-            L.ax = S / 2; L.ay = S / 2; L.adir = 0; agent_placed = true;
-            if (levelgen) { (void)rng.u32(); phase = n > 0 ? PH_OBJ : PH_AGENT; }     // `_rand_float(0,1) < 0`: one draw
-            else phase = PH_AGENT;
-        } else if (phase == PH_AGENT) {              // RoomGrid.place_agent -> MiniGridEnv.place_agent tries
-            if (tries > 1000) { phase = PH_START; continue; }
-            tries++;
-            const int x = rng.randint(0, S), y = rng.randint(0, S);
-            if ((occ >> (8 * y + x)) & 1u) continue;
-            L.ax = x; L.ay = y; agent_placed = true;
-            L.adir = rng.randint(0, 4);
-            const int fb = 8 * (y + dir_dy(L.adir)) + x + dir_dx(L.adir);
-            const bool front_ok = !((occ >> fb) & 1u) || ((lp.wall64 >> fb) & 1u);
-            tries = 0;                               // each inner place_agent call counts its own tries
-            if (!front_ok) continue;
-            if (levelgen) phase = lp.unblocking ? PH_DESC : PH_CHECK;
-            else phase = nplace > 0 ? PH_OBJ : PH_CHECK;
-            if (phase == PH_CHECK) fill = 0;
-        } else if (phase == PH_OBJ) {                // add_object / add_distractors: one placement try
-            if (tries == 0) {
-                if (lp.kind == KIND_REDBALL && k == 0) cur_tc = T_BALL | (C_RED << 3);
-                else {
-                    const int color = color_by_name_rank(rng.randint(0, 6));
-                    const int t = rng.randint(0, 3);
-                    cur_tc = (t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX) | (color << 3);
-                }
+    SmallLevel &L = g.L;
+    if (g.phase == PH_START) {                       // RoomGrid._gen_grid of one room: no draws
+        g.attempts++;
+        g.occ = lp.wall64; L.poss = 0; L.tcs = 0; L.nobj = 0; g.k = 0; g.tries = 0;
+        L.ax = S / 2; L.ay = S / 2; L.adir = 0; g.agent_placed = true;
+        if (levelgen) { (void)g.rng.u32(); g.phase = n > 0 ? PH_OBJ : PH_AGENT; }     // `_rand_float(0,1) < 0`: one draw
+        else g.phase = PH_AGENT;
+    } else if (g.phase == PH_AGENT) {                // RoomGrid.place_agent -> MiniGridEnv.place_agent tries
+        if (g.tries > 1000) { g.phase = PH_START; return; }
+        g.tries++;
+        const int x = g.rng.randint(0, S), y = g.rng.randint(0, S);
+        if ((g.occ >> (8 * y + x)) & 1u) return;
+        L.ax = x; L.ay = y; g.agent_placed = true;
+        L.adir = g.rng.randint(0, 4);
+        const int fb = 8 * (y + dir_dy(L.adir)) + x + dir_dx(L.adir);
+        const bool front_ok = !((g.occ >> fb) & 1u) || ((lp.wall64 >> fb) & 1u);
+        g.tries = 0;                                 // each inner place_agent call counts its own tries
+        if (!front_ok) return;
+        if (levelgen) g.phase = lp.unblocking ? PH_DESC : PH_CHECK;
+        else g.phase = nplace > 0 ? PH_OBJ : PH_CHECK;
+        if (g.phase == PH_CHECK) g.fill = 0;
+    } else if (g.phase == PH_OBJ) {                  // add_object / add_distractors: one placement try
+        if (g.tries == 0) {
+            if (lp.kind == KIND_REDBALL && g.k == 0) g.cur_tc = T_BALL | (C_RED << 3);
+            else {
+                const int color = color_by_name_rank(g.rng.randint(0, 6));
+                const int t = g.rng.randint(0, 3);
+                g.cur_tc = (t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX) | (color << 3);
             }
-            if (tries > 1000) { phase = PH_START; continue; }
-            tries++;
-            const int x = rng.randint(0, S), y = rng.randint(0, S);
-            if ((occ >> (8 * y + x)) & 1u) continue;
-            if (agent_placed && x == L.ax && y == L.ay) continue;
-            if (iabs(L.ax - x) + iabs(L.ay - y) < 2) continue;            // reject_next_to
-            occ |= 1ull << (8 * y + x);
-            L.poss |= (uint64_t)(x | (y << 3)) << (6 * k);
-            L.tcs |= (uint64_t)cur_tc << (6 * k);
-            k++; L.nobj = k; tries = 0;
-            if (k == nplace) {
-                if (lp.kind == KIND_REDBALL && lp.grey_dists)              // GoToRedBallGrey: distractors turn grey
-                    for (int q = 1; q < k; q++) L.tcs = (L.tcs & ~(56ull << (6 * q))) | ((uint64_t)(C_GREY << 3) << (6 * q));
-                if (levelgen) { phase = PH_AGENT; agent_placed = false; }   // MiniGridEnv.place_agent: agent_pos = None
-                else { phase = PH_CHECK; fill = 0; }
-            }
-        } else if (phase == PH_CHECK) {              // check_objs_reachable: bitboard flood fill, two sweeps per iteration
-            if (fill == 0) fill = 1ull << (8 * L.ay + L.ax);
-            const uint64_t pass = ~occ;
-            uint64_t f1 = fill | ((fill << 1 | fill >> 1 | fill << 8 | fill >> 8) & pass);
-            f1 |= (f1 << 1 | f1 >> 1 | f1 << 8 | f1 >> 8) & pass;
-            if (f1 != fill) { fill = f1; continue; }
-            const uint64_t near = fill | fill << 1 | fill >> 1 | fill << 8 | fill >> 8;
-            const uint64_t things = occ & ~lp.wall64;
-            if (things & ~near) { phase = PH_START; continue; }            // RejectSampling
-            phase = levelgen ? PH_DESC : (lp.kind == KIND_OBJ ? PH_PICK : PH_DONE);
-            tries = 0;
-            if (phase == PH_DONE) {                                        // GoToRedBall: the ball's descriptor
-                const int tc = sm_obj_tc(L.tcs, 0);
-                L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
-                L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
-            }
-        } else if (phase == PH_PICK) {               // obj = self._rand_elem(objs)
-            const int tc = sm_obj_tc(L.tcs, rng.randint(0, n));
+        }
+        if (g.tries > 1000) { g.phase = PH_START; return; }
+        g.tries++;
+        const int x = g.rng.randint(0, S), y = g.rng.randint(0, S);
+        if ((g.occ >> (8 * y + x)) & 1u) return;
+        if (g.agent_placed && x == L.ax && y == L.ay) return;
+        if (iabs(L.ax - x) + iabs(L.ay - y) < 2) return;                  // reject_next_to
+        g.occ |= 1ull << (8 * y + x);
+        L.poss |= (uint64_t)(x | (y << 3)) << (6 * g.k);
+        L.tcs |= (uint64_t)g.cur_tc << (6 * g.k);
+        g.k++; L.nobj = g.k; g.tries = 0;
+        if (g.k == nplace) {
+            if (lp.kind == KIND_REDBALL && lp.grey_dists)                  // GoToRedBallGrey: distractors turn grey
+                for (int q = 1; q < g.k; q++) L.tcs = (L.tcs & ~(56ull << (6 * q))) | ((uint64_t)(C_GREY << 3) << (6 * q));
+            if (levelgen) { g.phase = PH_AGENT; g.agent_placed = false; }   // MiniGridEnv.place_agent: agent_pos = None
+            else { g.phase = PH_CHECK; g.fill = 0; }
+        }
+    } else if (g.phase == PH_CHECK) {                // check_objs_reachable: bitboard flood fill, two sweeps per iteration
+        if (g.fill == 0) g.fill = 1ull << (8 * L.ay + L.ax);
+        const uint64_t pass = ~g.occ;
+        uint64_t f1 = g.fill | ((g.fill << 1 | g.fill >> 1 | g.fill << 8 | g.fill >> 8) & pass);
+        f1 |= (f1 << 1 | f1 >> 1 | f1 << 8 | f1 >> 8) & pass;
+        if (f1 != g.fill) { g.fill = f1; return; }
+        const uint64_t near = g.fill | g.fill << 1 | g.fill >> 1 | g.fill << 8 | g.fill >> 8;
+        const uint64_t things = g.occ & ~lp.wall64;
+        if (things & ~near) { g.phase = PH_START; return; }              // RejectSampling
+        g.phase = levelgen ? PH_DESC : (lp.kind == KIND_OBJ ? PH_PICK : PH_DONE);
+        g.tries = 0;
+        if (g.phase == PH_DONE) {                                        // GoToRedBall: the ball's descriptor
+            const int tc = sm_obj_tc(L.tcs, 0);
             L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
             L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
-            phase = PH_DONE;
-        } else {                                     // PH_DESC: LevelGen.rand_obj, one try
-            if (tries > 100) { phase = PH_START; continue; }
-            tries++;
-            const int ci = rng.randint(0, 7);
-            const int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
-            const int ntypes = L.leaf_kind == I_GOTO ? 4 : 3;
-            const int ti = rng.randint(0, ntypes);
-            const int type = ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR;
-            int loc = LOC_NONE;
-            if (lp.locations && rng.randbool()) loc = rng.randint(0, 4);
-            const uint32_t m = sm_match(L, type, color, loc);
-            if (m == 0) continue;
-            L.d_type = type; L.d_color = color; L.d_loc = loc; L.d_mask = m;
-            phase = PH_DONE;
         }
+    } else if (g.phase == PH_PICK) {                 // obj = self._rand_elem(objs)
+        const int tc = sm_obj_tc(L.tcs, g.rng.randint(0, n));
+        L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
+        L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
+        g.phase = PH_DONE;
+    } else if (g.phase == PH_DESC) {                 // LevelGen.rand_obj, one try
+        if (g.tries > 100) { g.phase = PH_START; return; }
+        g.tries++;
+        const int ci = g.rng.randint(0, 7);
+        const int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
+        const int ntypes = L.leaf_kind == I_GOTO ? 4 : 3;
+        const int ti = g.rng.randint(0, ntypes);
+        const int type = ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR;
+        int loc = LOC_NONE;
+        if (lp.locations && g.rng.randbool()) loc = g.rng.randint(0, 4);
+        const uint32_t m = sm_match(L, type, color, loc);
+        if (m == 0) return;
+        L.d_type = type; L.d_color = color; L.d_loc = loc; L.d_mask = m;
+        g.phase = PH_DONE;
     }
-    return attempts;
+}
+
+// Generates one level of a small single-room environment.  Returns the number of attempts.
+BB_HD int generate_small(const LevelParams &lp, RngScalar &rng, SmallLevel &L)
+{
+    SmallGen g;
+    g.rng = rng;
+    small_gen_begin(lp, g);
+    while (g.phase != PH_DONE) small_gen_step(lp, g);
+    rng = g.rng; L = g.L;
+    return g.attempts;
 }
 
 // SmallLevel -> the records of a level slot (grid in both orientations, object table, verifier, tokens, hot)

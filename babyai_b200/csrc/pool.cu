@@ -41,7 +41,8 @@ struct PoolPtrs {
     uint32_t *head_snap, *tail_pub;
     RngRec *rng; uint8_t *locked_room; uint32_t *attempts;
     float *last_reward;
-    uint32_t *gen_ticket;
+    uint32_t *gen_ticket;      // work-ticket counter of k_gen / k_gen_small
+    uint32_t *gen_count; int32_t *gen_list;       // k_gen_scan: envs whose ring is not full
     unsigned long long *warp_counters;   // [num_warps][4]: steps, episodes, successes, errors
     int32_t depth, n;
 };
@@ -740,51 +741,93 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
 }
 
 // Level generation for small single-room levels: ONE LANE PER ENVIRONMENT running the flat state-machine
-// generator (generate_small): lanes differ only in predicates and trip counts, so the warp stays converged;
-// emit_small_level() then runs for all lanes together.  A ticket is 32 consecutive environments.
+// generator (small_gen_step): lanes differ only in predicates, so the warp stays converged.
+//   k_gen_scan   compacts the environments whose ring is not full into a dense work list (warp ballot);
+//   k_gen_small  every lane runs its own generator; a lane that finished its env immediately takes the next
+//                list entry (warp-aggregated atomic), finished levels wait in a small per-lane shared-memory
+//                buffer and are written out (emit_small_level) for all lanes together when a buffer fills.
 constexpr int GS_THREADS = 128;
-__global__ void __launch_bounds__(GS_THREADS)
-k_gen_small(const LevelParams lp, const PoolPtrs P, const int n, const int target)
+constexpr int GS_BUF = 3;
+
+__global__ void k_gen_scan(const PoolPtrs P, const int n, const int target)
 {
-    const unsigned FULL = 0xFFFFFFFFu;
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const uint32_t nchunks = (uint32_t)((n + 31) / 32);
+    bool need = false;
+    if (env < n) need = target - (int)(P.tail[env] - P.head_snap[env]) > 0;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+    if (m) {
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(P.gen_count, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (need) P.gen_list[base + __popc(m & ((1u << lane) - 1u))] = env;
+    }
+}
+
+struct GsBuffered { SmallLevel L; int env, slot; };
+
+__global__ void __launch_bounds__(GS_THREADS)
+k_gen_small(const LevelParams lp, const PoolPtrs P, const int target)
+{
+    __shared__ GsBuffered buf[GS_BUF][GS_THREADS];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    const uint32_t count = *P.gen_count;
     const uint32_t D = (uint32_t)P.depth;
+    SmallGen g;
+    g.rng.init(0, 0);
+    small_gen_begin(lp, g);
+    int env = -1, left = 0, nbuf = 0, att = 0;
+    uint32_t tl = 0;
+    bool exhausted = false;
     for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(P.gen_ticket, 1u);
-        c = __shfl_sync(FULL, c, 0);
-        if (c >= nchunks) break;
-        const int env = (int)c * 32 + lane;
-        uint32_t tl = 0; int missing = 0;
-        if (env < n) {
-            const uint32_t hd = P.head_snap[env];
-            tl = P.tail[env];
-            missing = target - (int)(tl - hd);
-            if (missing < 0) missing = 0;
+        // ---- idle lanes take the next work item (one atomic per warp) -----------------------------
+        const bool need = left == 0 && !exhausted;
+        const uint32_t mneed = __ballot_sync(FULL, need);
+        if (mneed) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.gen_ticket, (uint32_t)__popc(mneed));
+            base = __shfl_sync(FULL, base, 0);
+            if (need) {
+                const uint32_t idx = base + (uint32_t)__popc(mneed & ((1u << lane) - 1u));
+                if (idx < count) {
+                    env = P.gen_list[idx];
+                    tl = P.tail[env];
+                    left = target - (int)(tl - P.head_snap[env]);
+                    const RngRec r = P.rng[env];
+                    g.rng.init(r.seed, r.draws);
+                    small_gen_begin(lp, g);
+                    att = 0;
+                } else exhausted = true;
+            }
         }
-        int maxm = missing;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) maxm = max(maxm, __shfl_xor_sync(FULL, maxm, off));
-        if (maxm == 0) continue;
-        RngScalar rng;
-        rng.init(0, 0);
-        if (missing > 0) { const RngRec r = P.rng[env]; rng.init(r.seed, r.draws); }
-        int att = 0;
-        for (int j = 0; j < maxm; j++) {                       // warp-uniform
-            SmallLevel L;
-            const bool active = j < missing;
-            if (active) att += generate_small(lp, rng, L);
-            __syncwarp();
-            if (active) emit_small_level(lp, L, ring_slot(lp, P, env, (int)((tl + (uint32_t)j) % D)));
+        if (!__any_sync(FULL, left > 0)) break;
+        // ---- one generator iteration per lane --------------------------------------------------------
+        if (left > 0) {
+            small_gen_step(lp, g);
+            if (g.phase == PH_DONE) {
+                GsBuffered &b = buf[nbuf][tid];
+                b.L = g.L; b.env = env; b.slot = (int)(tl % D);
+                nbuf++; tl++; left--; att += g.attempts;
+                if (left == 0) {
+                    RngRec r; r.seed = ((uint64_t)g.rng.k1 << 32) | g.rng.k0; r.draws = g.rng.draws;
+                    P.rng[env] = r;
+                    P.tail[env] = tl;
+                    P.attempts[env] += (uint32_t)att;
+                } else small_gen_begin(lp, g);
+            }
         }
-        if (missing > 0) {
-            RngRec r; r.seed = ((uint64_t)rng.k1 << 32) | rng.k0; r.draws = rng.draws;
-            P.rng[env] = r;
-            P.tail[env] = tl + (uint32_t)missing;
-            P.attempts[env] += (uint32_t)att;
+        // ---- flush: all lanes write their buffered levels together ---------------------------------
+        if (__any_sync(FULL, nbuf == GS_BUF)) {
+#pragma unroll 1
+            for (int j = 0; j < GS_BUF; j++)
+                if (j < nbuf) { const GsBuffered &b = buf[j][tid]; emit_small_level(lp, b.L, ring_slot(lp, P, b.env, b.slot)); }
+            nbuf = 0;
         }
     }
+#pragma unroll 1
+    for (int j = 0; j < GS_BUF; j++)
+        if (j < nbuf) { const GsBuffered &b = buf[j][tid]; emit_small_level(lp, b.L, ring_slot(lp, P, b.env, b.slot)); }
 }
 
 __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
@@ -861,9 +904,9 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
 static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st)
 {
     if (p->lp.small && !p->gen_generic) {
-        int blocks = (p->n + 32 * (GS_THREADS / 32) - 1) / (32 * (GS_THREADS / 32));
-        if (blocks > p->gen_small_blocks) blocks = p->gen_small_blocks;
-        k_gen_small<<<blocks, GS_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+        cudaMemsetAsync(p->P.gen_count, 0, sizeof(uint32_t), st);
+        k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target);
+        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target);
     } else k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
 
@@ -974,7 +1017,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         int want = ((n_envs + GEN_CHUNK - 1) / GEN_CHUNK + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);
         int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
-        p->gen_small_blocks = prop.multiProcessorCount * 4;
+        int per_sm = 4;
+        if (const char *e = getenv("BB_GEN_SMALL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) per_sm = v; }
+        p->gen_small_blocks = prop.multiProcessorCount * per_sm;
     }
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
@@ -999,7 +1044,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         dalloc(p, &P.robj, D * n) || dalloc(p, &P.rins, D * n) || dalloc(p, &P.rtok, D * n * lp.max_tokens) ||
         dalloc(p, &P.head, n) || dalloc(p, &P.tail, n) || dalloc(p, &P.head_snap, n) || dalloc(p, &P.tail_pub, n) ||
         dalloc(p, &P.rng, n) || dalloc(p, &P.locked_room, n) || dalloc(p, &P.attempts, n) || dalloc(p, &P.last_reward, n) ||
-        dalloc(p, &P.gen_ticket, 4) ||
+        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_count, 4) || dalloc(p, &P.gen_list, n) ||
         dalloc(p, &P.warp_counters, (size_t)p->num_warps * 4) ||
         dalloc(p, &p->d_act, n) || dalloc(p, &p->d_obs, n * OBS_BYTES) || dalloc(p, &p->d_rew, n) || dalloc(p, &p->d_done, n) ||
         dalloc(p, &p->d_dir, n) || dalloc(p, &p->d_seeds, n)) {
