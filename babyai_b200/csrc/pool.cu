@@ -29,6 +29,7 @@
 using namespace bb;
 
 // ---------------------------------------------------------------------------------
+struct GenSave;
 struct PoolPtrs {
     // live state of every environment
     uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
@@ -42,7 +43,7 @@ struct PoolPtrs {
     RngRec *rng; uint8_t *locked_room; uint32_t *attempts;
     float *last_reward;
     uint32_t *gen_ticket;      // work-ticket counter of k_gen / k_gen_small
-    uint32_t *gen_count; int32_t *gen_list;       // k_gen_scan: envs whose ring is not full
+    uint32_t *gen_count; int32_t *gen_list; GenSave *gen_save;       // k_gen_scan: envs whose ring is not full
     unsigned long long *warp_counters;   // [num_warps][4]: steps, episodes, successes, errors
     int32_t depth, n;
 };
@@ -749,6 +750,37 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
 constexpr int GS_THREADS = 128;
 constexpr int GS_BUF = 3;
 
+// A generation interrupted by the per-launch iteration budget (bb_pool_rollout refills concurrently with the
+// stepping kernel and must finish in bounded time; the slowest levels are a geometric tail of rejected
+// attempts) is parked here and resumed by the next launch.
+struct __align__(16) GenSave {
+    uint64_t draws, occ, fill, poss, tcs;
+    uint16_t tries, attempts;
+    uint8_t phase, k, cur_tc, agent_placed, nobj, ax, ay, adir;
+    uint8_t valid, pad[11];
+};
+static_assert(sizeof(GenSave) == 64, "GenSave is one 64-byte record");
+
+__device__ __forceinline__ void gen_save(GenSave *d, const SmallGen &g)
+{
+    GenSave v;
+    v.draws = g.rng.draws; v.occ = g.occ; v.fill = g.fill; v.poss = g.L.poss; v.tcs = g.L.tcs;
+    v.tries = (uint16_t)g.tries; v.attempts = (uint16_t)g.attempts;
+    v.phase = (uint8_t)g.phase; v.k = (uint8_t)g.k; v.cur_tc = (uint8_t)g.cur_tc; v.agent_placed = g.agent_placed ? 1 : 0;
+    v.nobj = (uint8_t)g.L.nobj; v.ax = (uint8_t)g.L.ax; v.ay = (uint8_t)g.L.ay; v.adir = (uint8_t)g.L.adir;
+    v.valid = 1;
+    for (int i = 0; i < 11; i++) v.pad[i] = 0;
+    *d = v;
+}
+__device__ __forceinline__ void gen_restore(const GenSave &v, SmallGen &g)
+{
+    g.rng.draws = v.draws; g.rng.blk = ~0ull;
+    g.occ = v.occ; g.fill = v.fill; g.L.poss = v.poss; g.L.tcs = v.tcs;
+    g.tries = v.tries; g.attempts = v.attempts; g.phase = v.phase; g.k = v.k; g.cur_tc = v.cur_tc;
+    g.agent_placed = v.agent_placed != 0;
+    g.L.nobj = v.nobj; g.L.ax = v.ax; g.L.ay = v.ay; g.L.adir = v.adir;
+}
+
 __global__ void k_gen_scan(const PoolPtrs P, const int n, const int target)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -767,7 +799,7 @@ __global__ void k_gen_scan(const PoolPtrs P, const int n, const int target)
 struct GsBuffered { SmallLevel L; int env, slot; };
 
 __global__ void __launch_bounds__(GS_THREADS)
-k_gen_small(const LevelParams lp, const PoolPtrs P, const int target)
+k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_iters)
 {
     __shared__ GsBuffered buf[GS_BUF][GS_THREADS];
     const unsigned FULL = 0xFFFFFFFFu;
@@ -777,11 +809,15 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target)
     SmallGen g;
     g.rng.init(0, 0);
     small_gen_begin(lp, g);
-    int env = -1, left = 0, nbuf = 0, att = 0;
+    int env = -1, left = 0, nbuf = 0, iters = 0;
     uint32_t tl = 0;
     bool exhausted = false;
     for (;;) {
         // ---- idle lanes take the next work item (one atomic per warp) -----------------------------
+        if (max_iters > 0 && iters >= max_iters && !exhausted) {   // budget spent: park the level in progress
+            if (left > 0) gen_save(P.gen_save + env, g);
+            left = 0; exhausted = true;
+        }
         const bool need = left == 0 && !exhausted;
         const uint32_t mneed = __ballot_sync(FULL, need);
         if (mneed) {
@@ -797,7 +833,8 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target)
                     const RngRec r = P.rng[env];
                     g.rng.init(r.seed, r.draws);
                     small_gen_begin(lp, g);
-                    att = 0;
+                    const GenSave sv = P.gen_save[env];
+                    if (sv.valid) { gen_restore(sv, g); P.gen_save[env].valid = 0; }
                 } else exhausted = true;
             }
         }
@@ -805,16 +842,16 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target)
         // ---- one generator iteration per lane --------------------------------------------------------
         if (left > 0) {
             small_gen_step(lp, g);
+            iters++;
             if (g.phase == PH_DONE) {
                 GsBuffered &b = buf[nbuf][tid];
                 b.L = g.L; b.env = env; b.slot = (int)(tl % D);
-                nbuf++; tl++; left--; att += g.attempts;
-                if (left == 0) {
-                    RngRec r; r.seed = ((uint64_t)g.rng.k1 << 32) | g.rng.k0; r.draws = g.rng.draws;
-                    P.rng[env] = r;
-                    P.tail[env] = tl;
-                    P.attempts[env] += (uint32_t)att;
-                } else small_gen_begin(lp, g);
+                nbuf++; tl++; left--;
+                RngRec r; r.seed = ((uint64_t)g.rng.k1 << 32) | g.rng.k0; r.draws = g.rng.draws;
+                P.rng[env] = r;                                 // the env's records are consistent after every level
+                P.tail[env] = tl;
+                P.attempts[env] += (uint32_t)g.attempts;
+                if (left > 0) small_gen_begin(lp, g);
             }
         }
         // ---- flush: all lanes write their buffered levels together ---------------------------------
@@ -839,6 +876,7 @@ __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
     P.locked_room[env] = 0xFF;
     P.tail[env] = P.head[env];                                 // empty ring: old levels belong to the old stream
     P.tail_pub[env] = P.head[env];
+    reinterpret_cast<uint4 *>(P.gen_save)[4 * (size_t)env + 3] = make_uint4(0, 0, 0, 0);      // GenSave::valid = 0
     P.attempts[env] = 0;
 }
 
@@ -862,7 +900,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
-    bool gen_generic; int gen_small_blocks;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
+    bool gen_generic; int gen_small_blocks, gen_budget;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 0 = k_step8 (8 lanes per env, default), 1 = k_step (lane per env), 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
@@ -895,18 +933,28 @@ static int dalloc(bb_pool *p, T **out, size_t count)
     return 0;
 }
 
+static int dalloc_bytes(bb_pool *p, void **out, size_t bytes)
+{
+    void *ptr = nullptr;
+    CU(cudaMalloc(&ptr, bytes ? bytes : 16));
+    CU(cudaMemset(ptr, 0, bytes ? bytes : 16));
+    p->allocs.push_back(ptr);
+    *out = ptr;
+    return 0;
+}
+
 static int make_params(const bb_level_spec *s, LevelParams *lp)
 {
     const char *e = make_level_params(s, lp);
     return e ? fail("%s", e) : 0;
 }
 
-static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st)
+static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_iters = 0)
 {
     if (p->lp.small && !p->gen_generic) {
         cudaMemsetAsync(p->P.gen_count, 0, sizeof(uint32_t), st);
         k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target);
-        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target);
+        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_iters);
     } else k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
 
@@ -1022,6 +1070,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         p->gen_small_blocks = prop.multiProcessorCount * per_sm;
     }
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
+    p->gen_budget = 192;                                   // generator iterations per lane per rollout refill
+    if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
     p->D = p->lp.cells_pad <= 256 ? 96 : 8;             // small grids: >= 2 x the 40-step rollout of bb_pool_rollout
@@ -1044,7 +1094,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         dalloc(p, &P.robj, D * n) || dalloc(p, &P.rins, D * n) || dalloc(p, &P.rtok, D * n * lp.max_tokens) ||
         dalloc(p, &P.head, n) || dalloc(p, &P.tail, n) || dalloc(p, &P.head_snap, n) || dalloc(p, &P.tail_pub, n) ||
         dalloc(p, &P.rng, n) || dalloc(p, &P.locked_room, n) || dalloc(p, &P.attempts, n) || dalloc(p, &P.last_reward, n) ||
-        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_count, 4) || dalloc(p, &P.gen_list, n) ||
+        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_count, 4) || dalloc(p, &P.gen_list, n) || dalloc_bytes(p, (void **)&P.gen_save, n * 64) ||
         dalloc(p, &P.warp_counters, (size_t)p->num_warps * 4) ||
         dalloc(p, &p->d_act, n) || dalloc(p, &p->d_obs, n * OBS_BYTES) || dalloc(p, &p->d_rew, n) || dalloc(p, &p->d_done, n) ||
         dalloc(p, &p->d_dir, n) || dalloc(p, &p->d_seeds, n)) {
@@ -1199,7 +1249,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaEventRecord(p->ev_fork, user));
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
         cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), p->gen_stream);
-        launch_gen_kernel(p, p->D, p->gen_stream);
+        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget);      // bounded: runs beside k_rollout
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
         p->gen_outstanding = true;
         p->launches++;
