@@ -1103,7 +1103,11 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     }
     CU(cudaMemset(P.locked_room, 0xFF, n));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&p->gen_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));                  // lo = lowest priority
+        CU(cudaStreamCreateWithPriority(&p->gen_stream, cudaStreamNonBlocking, lo));
+    }
     CU(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
@@ -1242,11 +1246,18 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
     const size_t smem = (size_t)R_WARPS * warp_words * 4;
     const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
-    if (p->mode == BB_MODE_AUTORESET) {
-        // fork: generation for the levels consumed before this launch, concurrently with it
-        const size_t nb = (size_t)p->n * sizeof(uint32_t);
+    const bool refill = p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL");
+    const size_t nb = (size_t)p->n * sizeof(uint32_t);
+    if (refill) {
+        // fork point: the head snapshot k_gen will work from (levels consumed before this launch)
         CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
         CU(cudaEventRecord(p->ev_fork, user));
+    }
+    // the stepping kernel is submitted FIRST so that it gets its full residency (7 CTAs per SM); generation
+    // then fills the remaining slots and runs beside it
+    k_rollout<<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+    p->launches++;
+    if (refill) {
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
         cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), p->gen_stream);
         launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget);      // bounded: runs beside k_rollout
@@ -1254,8 +1265,6 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         p->gen_outstanding = true;
         p->launches++;
     }
-    k_rollout<<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-    p->launches++;
     p->rel = 0;
     p->after_rollout = true;                           // a per-step call that follows tops the rings up first
     CU(cudaGetLastError());
