@@ -1070,7 +1070,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         p->gen_small_blocks = prop.multiProcessorCount * per_sm;
     }
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
-    p->gen_budget = 192;                                   // generator iterations per lane per rollout refill
+    p->gen_budget = 64;                                    // generator iterations per lane per rollout refill
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
@@ -1109,6 +1109,16 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         CU(cudaStreamCreateWithPriority(&p->gen_stream, cudaStreamNonBlocking, lo));
     }
     CU(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
+    // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
+    CU(cudaFuncSetAttribute(k_rollout, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_gen_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_gen_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_gen, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_step8<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_step8<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_step<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < p->nev; i++) CU(cudaEventCreateWithFlags(&p->gen_ev[i], cudaEventDisableTiming));
@@ -1247,21 +1257,49 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     const size_t smem = (size_t)R_WARPS * warp_words * 4;
     const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
     const bool refill = p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL");
+    static const bool dbg_timing = getenv("BB_DEBUG_TIMING") != nullptr;
+    static cudaEvent_t dbg_ev[4]; static int dbg_calls = 0;
+    if (dbg_timing) {
+        if (dbg_calls == 0) for (int i = 0; i < 4; i++) cudaEventCreate(&dbg_ev[i]);
+        else if (dbg_calls < 40) {
+            cudaDeviceSynchronize();
+            float r = 0, g = 0, lag = 0;
+            cudaEventElapsedTime(&r, dbg_ev[0], dbg_ev[1]); cudaEventElapsedTime(&g, dbg_ev[2], dbg_ev[3]);
+            cudaEventElapsedTime(&lag, dbg_ev[0], dbg_ev[2]);
+            fprintf(stderr, "[bb timing] rollout %.1f us, refill %.1f us (starts %.1f us after the rollout)\n", r * 1e3, g * 1e3, lag * 1e3);
+        }
+        dbg_calls++;
+    }
     const size_t nb = (size_t)p->n * sizeof(uint32_t);
-    if (refill) {
+    // Default: refill in-stream, right before the stepping kernel, with a bounded iteration budget.  Measured
+    // (r01l): running k_gen_small on the side stream BESIDE k_rollout does not pay -- alone they take 263 us and
+    // ~210 us, together 460-490 us and 580 us (both are issue/latency bound on the same SMs); BB_GEN_CONCURRENT=1
+    // selects that variant for A/B runs.
+    static const bool gen_serial = getenv("BB_GEN_CONCURRENT") == nullptr;
+    if (refill && gen_serial) {
+        if (dbg_timing) cudaEventRecord(dbg_ev[2], user);
+        CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
+        cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), user);
+        launch_gen_kernel(p, p->D, user, p->gen_budget);
+        cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, user);
+        if (dbg_timing) cudaEventRecord(dbg_ev[3], user);
+        p->launches++;
+    } else if (refill) {
         // fork point: the head snapshot k_gen will work from (levels consumed before this launch)
         CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
         CU(cudaEventRecord(p->ev_fork, user));
     }
-    // the stepping kernel is submitted FIRST so that it gets its full residency (7 CTAs per SM); generation
-    // then fills the remaining slots and runs beside it
+    if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
     k_rollout<<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+    if (dbg_timing) cudaEventRecord(dbg_ev[1], user);
     p->launches++;
-    if (refill) {
+    if (refill && !gen_serial) {
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
+        if (dbg_timing) cudaEventRecord(dbg_ev[2], p->gen_stream);
         cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), p->gen_stream);
         launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget);      // bounded: runs beside k_rollout
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
+        if (dbg_timing) cudaEventRecord(dbg_ev[3], p->gen_stream);
         p->gen_outstanding = true;
         p->launches++;
     }
