@@ -918,6 +918,7 @@ struct bb_pool {
     long long launches;
     cudaGraphExec_t graph; GraphKey gkey;
     cudaEvent_t ev[3];
+    cudaEvent_t tev[4]; bool time_rollout;       // bb_pool_rollout_timed
 };
 
 template <typename T>
@@ -955,6 +956,7 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_i
         cudaMemsetAsync(p->P.gen_count, 0, sizeof(uint32_t), st);
         k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target);
         k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_iters);
+        p->launches++;
     } else k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
 
@@ -1084,7 +1086,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->step_kernel = 0;
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
     if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : 0;
-    p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr;
+    p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr; p->tev[0] = p->tev[1] = p->tev[2] = p->tev[3] = nullptr; p->time_rollout = false;
     const LevelParams &lp = p->lp;
     const size_t n = (size_t)n_envs, D = (size_t)p->D;
     PoolPtrs &P = p->P;
@@ -1141,6 +1143,7 @@ int bb_pool_destroy(bb_pool *p)
     cudaDeviceSynchronize();
     if (p->graph) cudaGraphExecDestroy(p->graph);
     for (int i = 0; i < 3; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    for (int i = 0; i < 4; i++) if (p->tev[i]) cudaEventDestroy(p->tev[i]);
     for (int i = 0; i < p->nev; i++) if (p->gen_ev[i]) cudaEventDestroy(p->gen_ev[i]);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
@@ -1257,19 +1260,9 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     const size_t smem = (size_t)R_WARPS * warp_words * 4;
     const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
     const bool refill = p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL");
-    static const bool dbg_timing = getenv("BB_DEBUG_TIMING") != nullptr;
-    static cudaEvent_t dbg_ev[4]; static int dbg_calls = 0;
-    if (dbg_timing) {
-        if (dbg_calls == 0) for (int i = 0; i < 4; i++) cudaEventCreate(&dbg_ev[i]);
-        else if (dbg_calls < 40) {
-            cudaDeviceSynchronize();
-            float r = 0, g = 0, lag = 0;
-            cudaEventElapsedTime(&r, dbg_ev[0], dbg_ev[1]); cudaEventElapsedTime(&g, dbg_ev[2], dbg_ev[3]);
-            cudaEventElapsedTime(&lag, dbg_ev[0], dbg_ev[2]);
-            fprintf(stderr, "[bb timing] rollout %.1f us, refill %.1f us (starts %.1f us after the rollout)\n", r * 1e3, g * 1e3, lag * 1e3);
-        }
-        dbg_calls++;
-    }
+    const bool dbg_timing = p->time_rollout;
+    cudaEvent_t *dbg_ev = p->tev;
+    if (dbg_timing && !dbg_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&dbg_ev[i]));
     const size_t nb = (size_t)p->n * sizeof(uint32_t);
     // Default: refill in-stream, right before the stepping kernel, with a bounded iteration budget.  Measured
     // (r01l): running k_gen_small on the side stream BESIDE k_rollout does not pay -- alone they take 263 us and
@@ -1306,6 +1299,24 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     p->rel = 0;
     p->after_rollout = true;                           // a per-step call that follows tops the rings up first
     CU(cudaGetLastError());
+    return 0;
+}
+
+int bb_pool_rollout_timed(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *obs_dev, float *reward_dev,
+                          uint8_t *done_dev, int8_t *dir_dev, float *ms_rollout_kernel, float *ms_refill)
+{
+    if (!p || !ms_rollout_kernel || !ms_refill) return fail("bad arguments");
+    *ms_rollout_kernel = 0; *ms_refill = 0;
+    p->time_rollout = true;
+    const int rc = bb_pool_rollout(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, p->stream);
+    p->time_rollout = false;
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaDeviceSynchronize());
+    if (p->tev[0] && cudaEventQuery(p->tev[1]) == cudaSuccess) {
+        CU(cudaEventElapsedTime(ms_rollout_kernel, p->tev[0], p->tev[1]));
+        if (cudaEventQuery(p->tev[3]) == cudaSuccess) cudaEventElapsedTime(ms_refill, p->tev[2], p->tev[3]);
+    }
     return 0;
 }
 

@@ -125,6 +125,13 @@ class BabyAIVecEnv(object):
                                           _ptr(direction), self._stream()))
         return obs, reward, done
 
+    def rollout_timed(self, actions, obs, reward, done, direction=None):
+        """rollout() with CUDA events around the stepping kernel and the level refill -> (ms, ms)."""
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self.L.bb_pool_rollout_timed(self.h, _ptr(actions), actions.shape[0], _ptr(obs), _ptr(reward), _ptr(done),
+                                                _ptr(direction), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- host-buffer path (what the reference's callers see) -----------------
     def step_host(self, actions, obs, reward, done, direction):
         a = np.ascontiguousarray(actions, dtype=np.int8)

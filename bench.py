@@ -10,15 +10,18 @@ A "step" is one environment step of all 65 536 environments of a rank.
 Own arm, printed as ONE JSON line by rank 0:
   value     env-steps/sec, whole job, actions resident in HBM ([T, N] int8),
             observations written to a [T, N, 147] rollout buffer (385 MB > L2),
-            K steps launched as K/T CUDA graphs of (k_step, k_gen) pairs;
-            CUDA events, barrier + synchronize on both sides, max over ranks.
+            K steps run as K/T calls of bb_pool_rollout (T = 40): the persistent
+            stepping kernel k_rollout + the bounded level refill (k_gen_scan,
+            k_gen_small); CUDA events, barrier + synchronize on both sides,
+            max over ranks.
   e2e       the same metric through the reference-facing host-buffer call
             (bb_pool_step_host = what ParallelEnv.step returns to BaseAlgo):
             actions host->device and obs/reward/done/direction device->host
             inside the timed region, every step.
-  roofline  dominant kernel k_step: 153 algorithmic bytes per env-step
-            (147 obs + 4 reward + 1 done + 1 action) x N envs
-            / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  roofline  dominant kernel k_rollout: 153 algorithmic bytes per env-step
+            (147 obs + 4 reward + 1 done + 1 action) x N envs x T
+            steps per launch / its CUDA-event duration (bb_pool_rollout_timed),
+            against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the oracle's C port of the same path on this box's host cores.
 
 --impl reference: the CPU arm (oracle C port, all host threads, same workload);
@@ -252,14 +255,26 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
 
-    # ---- per-kernel timing (roofline) ------------------------------------------------
-    ks, kg = [], []
-    for t in range(60):
-        a, b = env.step_timed(actions[t % T])
-        if t >= 10:
-            ks.append(a); kg.append(b)
-    k_step_ms = sum(ks) / len(ks)
-    k_gen_ms = sum(kg) / len(kg)
+    # ---- per-kernel timing (roofline): the stepping kernel of one rollout launch, CUDA events on its stream ----
+    kr, kf = [], []
+    for t in range(24):
+        a, b = env.rollout_timed(actions, obs, rew, done, dirs)
+        if t >= 4 and a > 0:
+            kr.append(a); kf.append(b)
+    k_roll_ms = sum(kr) / len(kr) if kr else 0.0
+    k_refill_ms = sum(kf) / len(kf) if kf else 0.0
+    # the per-step entry point (policy in the loop): bb_pool_step on device buffers, one launch per step
+    Ks = min(K, 600)
+    for t in range(20):
+        env.step(actions[t % T], obs[t % T], rew[t % T], done[t % T], dirs[t % T])
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for t in range(Ks):
+        env.step(actions[t % T], obs[t % T], rew[t % T], done[t % T], dirs[t % T])
+    s1.record()
+    barrier()
+    per_step_ms = s0.elapsed_time(s1) / Ks
 
     # ---- end to end through the host-buffer call ----------------------------------------
     h_act = np.random.RandomState(7 + rank).randint(0, 7, (64, n)).astype(np.int8)
@@ -287,12 +302,12 @@ def main():
     if rank == 0:
         peak, peak_src = hbm_peak()
         value = world * n * K / (ms * 1e-3)
-        achieved = ALGO_BYTES_PER_STEP * n / (k_step_ms * 1e-3) / 1e9
+        achieved = ALGO_BYTES_PER_STEP * n * T / (k_roll_ms * 1e-3) / 1e9 if k_roll_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get('k_step_dram_bytes_per_launch')
+                traffic = json.load(open(tp)).get('k_rollout_dram_bytes_per_launch')
             except Exception:
                 traffic = None
         out = {
@@ -303,11 +318,15 @@ def main():
                                    'ParallelEnv auto-reset, in-kernel verifier' % (args.level, n),
                        'envs_per_gpu': n, 'rollout_chunk': T,
                        'l2_policy': 'obs written to a [%d, %d, 147] buffer (%.0f MB) larger than L2' % (T, n, T * n * 147 / 1e6),
-                       'execution': 'CUDA graph of %d x (k_step, k_gen) per launch' % T,
+                       'execution': 'bb_pool_rollout: persistent kernel k_rollout (%d steps per launch, env state resident in '
+                                    'shared memory) + bounded in-stream level refill (k_gen_scan, k_gen_small)' % T,
                        'parallelism': 'replicas x%d, counters all-gather only' % world},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'kernel': 'k_step', 'kernel_ms': k_step_ms, 'k_gen_ms': k_gen_ms,
-                         'algorithmic_bytes_per_launch': ALGO_BYTES_PER_STEP * n, 'peak_source': peak_src},
+                         'traffic': traffic, 'kernel': 'k_rollout', 'kernel_ms': k_roll_ms, 'steps_per_launch': T,
+                         'kernel_us_per_step': 1e3 * k_roll_ms / T, 'refill_ms_per_launch': k_refill_ms,
+                         'algorithmic_bytes_per_launch': ALGO_BYTES_PER_STEP * n * T, 'peak_source': peak_src},
+            'per_step_api': {'value': world * n / (per_step_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': per_step_ms,
+                             'api': 'bb_pool_step (k_step8 + k_gen on a side stream), device buffers', 'steps': Ks},
             'e2e': {'value': world * n * Ke / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n,
                     'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke, 'api': 'bb_pool_step_host'},
             'gpu_launches': int(launches),

@@ -105,6 +105,13 @@ int bb_pool_step_timed(bb_pool *pool, const void *actions_dev, int32_t action_by
 int bb_pool_rollout(bb_pool *pool, const int8_t *actions_dev, int32_t T,
                     uint8_t *obs_dev, float *reward_dev, uint8_t *done_dev, int8_t *dir_dev, void *stream);
 
+/* bb_pool_rollout on the pool's internal stream with CUDA events around the stepping kernel and around the
+ * level refill (measurement hook for bench.py's roofline line; synchronises).  Times are 0 when the call
+ * took the per-step-graph path. */
+int bb_pool_rollout_timed(bb_pool *pool, const int8_t *actions_dev, int32_t T,
+                          uint8_t *obs_dev, float *reward_dev, uint8_t *done_dev, int8_t *dir_dev,
+                          float *ms_rollout_kernel, float *ms_refill);
+
 /* Same as bb_pool_step but with HOST buffers (what ParallelEnv.step hands
  * back to BaseAlgo.collect_experiences, rl/algos/base.py:144): copies actions
  * host->device, steps, copies obs/reward/done/dir device->host, synchronises. */
