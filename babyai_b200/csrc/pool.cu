@@ -918,7 +918,8 @@ struct bb_pool {
     long long launches;
     cudaGraphExec_t graph; GraphKey gkey;
     cudaEvent_t ev[3];
-    cudaEvent_t tev[4]; bool time_rollout;       // bb_pool_rollout_timed
+    cudaEvent_t tev[4]; bool time_rollout;
+    const void *chk_obs; bool direct;            // bb_pool_step_host: caller buffers are page-locked       // bb_pool_rollout_timed
 };
 
 template <typename T>
@@ -1086,7 +1087,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->step_kernel = 0;
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
     if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : 0;
-    p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr; p->tev[0] = p->tev[1] = p->tev[2] = p->tev[3] = nullptr; p->time_rollout = false;
+    p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr; p->tev[0] = p->tev[1] = p->tev[2] = p->tev[3] = nullptr; p->time_rollout = false; p->chk_obs = nullptr; p->direct = false;
     const LevelParams &lp = p->lp;
     const size_t n = (size_t)n_envs, D = (size_t)p->D;
     PoolPtrs &P = p->P;
@@ -1358,12 +1359,23 @@ static int rollout_graph(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8
     return 0;
 }
 
+static bool is_pinned(const void *ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host, float *reward_host,
                       uint8_t *done_host, int8_t *dir_host)
 {
     if (!p || !actions_host || !obs_host || !reward_host || !done_host) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     const size_t n = (size_t)p->n;
+    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are the DMA targets
+    // themselves; pageable ones go through the pool's pinned staging buffers + a host memcpy
+    if (obs_host != p->chk_obs) { p->chk_obs = obs_host; p->direct = is_pinned(obs_host) && is_pinned(reward_host) && is_pinned(done_host) && (!dir_host || is_pinned(dir_host)); }
+    const bool direct = p->direct;
     memcpy(p->h_act, actions_host, n);
     CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, p->stream));
     if (sched_leave_rollout(p, p->stream)) return 1;
@@ -1371,15 +1383,17 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
     launch_step(p, p->d_act, 1, p->d_obs, p->d_rew, p->d_done, p->d_dir, 0, p->stream);
     if (sched_after_step(p, p->rel, p->stream)) return 1;
     p->rel++;
-    CU(cudaMemcpyAsync(p->h_obs, p->d_obs, n * OBS_BYTES, cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaMemcpyAsync(p->h_rew, p->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaMemcpyAsync(p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaMemcpyAsync(p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(direct ? obs_host : p->h_obs, p->d_obs, n * OBS_BYTES, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(direct ? (void *)reward_host : (void *)p->h_rew, p->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(direct ? done_host : p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, p->stream));
+    if (!direct || dir_host) CU(cudaMemcpyAsync(direct ? dir_host : p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
-    memcpy(obs_host, p->h_obs, n * OBS_BYTES);
-    memcpy(reward_host, p->h_rew, n * sizeof(float));
-    memcpy(done_host, p->h_done, n);
-    if (dir_host) memcpy(dir_host, p->h_dir, n);
+    if (!direct) {
+        memcpy(obs_host, p->h_obs, n * OBS_BYTES);
+        memcpy(reward_host, p->h_rew, n * sizeof(float));
+        memcpy(done_host, p->h_done, n);
+        if (dir_host) memcpy(dir_host, p->h_dir, n);
+    }
     return 0;
 }
 

@@ -216,10 +216,10 @@ class _HostVec(object):
         self.observation_space, self.action_space = _spaces()
         self.pool = BabyAIVecEnv(envs.level, len(envs), seeds=envs.seeds, device=envs.device, mode=mode)
         n = len(envs)
-        self._obs = np.zeros((n, 7, 7, 3), np.uint8)
-        self._rew = np.zeros(n, np.float32)
-        self._done = np.zeros(n, np.uint8)
-        self._dir = np.zeros(n, np.int8)
+        # page-locked host buffers: bb_pool_step_host DMAs straight into them
+        self._pin = [torch.zeros((n, 7, 7, 3), dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
+                     torch.zeros(n, dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.int8).pin_memory()]
+        self._obs, self._rew, self._done, self._dir = [t.numpy() for t in self._pin]
         self._missions = [''] * n
 
     def _obs_list(self, refresh):

@@ -278,10 +278,10 @@ def main():
 
     # ---- end to end through the host-buffer call ----------------------------------------
     h_act = np.random.RandomState(7 + rank).randint(0, 7, (64, n)).astype(np.int8)
-    h_obs = np.zeros((n, 7, 7, 3), np.uint8)
-    h_rew = np.zeros(n, np.float32)
-    h_done = np.zeros(n, np.uint8)
-    h_dir = np.zeros(n, np.int8)
+    # page-locked host buffers (what babyai_b200.ParallelEnv hands to bb_pool_step_host)
+    pins = [torch.zeros((n, 7, 7, 3), dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
+            torch.zeros(n, dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.int8).pin_memory()]
+    h_obs, h_rew, h_done, h_dir = [t.numpy() for t in pins]
     Ke = min(K, 400)
     for k in range(5):
         env.step_host(h_act[k], h_obs, h_rew, h_done, h_dir)
@@ -328,7 +328,8 @@ def main():
             'per_step_api': {'value': world * n / (per_step_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': per_step_ms,
                              'api': 'bb_pool_step (k_step8 + k_gen on a side stream), device buffers', 'steps': Ks},
             'e2e': {'value': world * n * Ke / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n,
-                    'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke, 'api': 'bb_pool_step_host'},
+                    'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke,
+                    'api': 'bb_pool_step_host, page-locked host buffers'},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'counters': cnt,
