@@ -823,58 +823,84 @@ BB_HD void small_gen_begin(const LevelParams &lp, SmallGen &g)
     g.L.d_type = ANY_TYPE; g.L.d_color = ANY; g.L.d_loc = LOC_NONE; g.L.d_mask = 0;
 }
 
-BB_HD void small_gen_step(const LevelParams &lp, SmallGen &g)
+// Draw window of a lane: the eight 32-bit words of Philox blocks blk and blk + 1, kept in memory that can be
+// indexed dynamically (shared memory on the device, stride ws words between consecutive entries).  One iteration
+// of the generator consumes at most four draws, so after win_ensure() every draw it needs is a plain indexed read.
+BB_HD void win_ensure(RngScalar &r, uint32_t *win, int ws)
+{
+    const uint64_t nb = r.draws >> 2;
+    if (nb == r.blk) return;
+    if (nb == r.blk + 1 && r.blk != ~0ull) {       // slide: block blk + 1 becomes the low half
+#pragma unroll
+        for (int j = 0; j < 4; j++) win[j * ws] = win[(4 + j) * ws];
+    } else {
+        r.refill(nb);
+        win[0] = r.b0; win[ws] = r.b1; win[2 * ws] = r.b2; win[3 * ws] = r.b3;
+    }
+    r.refill(nb + 1);
+    win[4 * ws] = r.b0; win[5 * ws] = r.b1; win[6 * ws] = r.b2; win[7 * ws] = r.b3;
+    r.blk = nb;
+}
+
+// One iteration of the flat generator loop.  Agent and object placement share one code path (they are ~95 %
+// of the iterations), draws are indexed reads from the lane's window: lanes of a warp stay converged.
+BB_HD void small_gen_step(const LevelParams &lp, SmallGen &g, uint32_t *win, int ws)
 {
     const int S = lp.room_size, n = lp.num_dists;
     const bool levelgen = lp.kind == KIND_LEVELGEN;
     const int nplace = n + (lp.kind == KIND_REDBALL ? 1 : 0);   // objects placed per attempt
     SmallLevel &L = g.L;
-    if (g.phase == PH_START) {                       // RoomGrid._gen_grid of one room: no draws
-        g.attempts++;
-        g.occ = lp.wall64; L.poss = 0; L.tcs = 0; L.nobj = 0; g.k = 0; g.tries = 0;
-        L.ax = S / 2; L.ay = S / 2; L.adir = 0; g.agent_placed = true;
-        if (levelgen) { (void)g.rng.u32(); g.phase = n > 0 ? PH_OBJ : PH_AGENT; }     // `_rand_float(0,1) < 0`: one draw
-        else g.phase = PH_AGENT;
-    } else if (g.phase == PH_AGENT) {                // RoomGrid.place_agent -> MiniGridEnv.place_agent tries
+    win_ensure(g.rng, win, ws);
+    const int off = (int)(g.rng.draws & 3u);
+#define BB_PEEK(j) win[(off + (j)) * ws]
+    const int ph = g.phase;
+    if (ph == PH_AGENT || ph == PH_OBJ) {
+        // RoomGrid.place_agent -> MiniGridEnv.place_agent tries / add_object, add_distractors: one placement try
         if (g.tries > 1000) { g.phase = PH_START; return; }
-        g.tries++;
-        const int x = g.rng.randint(0, S), y = g.rng.randint(0, S);
-        if ((g.occ >> (8 * y + x)) & 1u) return;
-        L.ax = x; L.ay = y; g.agent_placed = true;
-        L.adir = g.rng.randint(0, 4);
-        const int fb = 8 * (y + dir_dy(L.adir)) + x + dir_dx(L.adir);
-        const bool front_ok = !((g.occ >> fb) & 1u) || ((lp.wall64 >> fb) & 1u);
-        g.tries = 0;                                 // each inner place_agent call counts its own tries
-        if (!front_ok) return;
-        if (levelgen) g.phase = lp.unblocking ? PH_DESC : PH_CHECK;
-        else g.phase = nplace > 0 ? PH_OBJ : PH_CHECK;
-        if (g.phase == PH_CHECK) g.fill = 0;
-    } else if (g.phase == PH_OBJ) {                  // add_object / add_distractors: one placement try
-        if (g.tries == 0) {
-            if (lp.kind == KIND_REDBALL && g.k == 0) g.cur_tc = T_BALL | (C_RED << 3);
+        const bool isobj = ph == PH_OBJ;
+        const bool fixed = lp.kind == KIND_REDBALL && g.k == 0;            // the red ball: no colour / type draws
+        int used = 0;
+        if (isobj && g.tries == 0) {
+            if (fixed) g.cur_tc = T_BALL | (C_RED << 3);
             else {
-                const int color = color_by_name_rank(g.rng.randint(0, 6));
-                const int t = g.rng.randint(0, 3);
+                const int color = color_by_name_rank((int)mulhi32(BB_PEEK(0), 6u));
+                const int t = (int)mulhi32(BB_PEEK(1), 3u);
                 g.cur_tc = (t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX) | (color << 3);
+                used = 2;
             }
         }
-        if (g.tries > 1000) { g.phase = PH_START; return; }
         g.tries++;
-        const int x = g.rng.randint(0, S), y = g.rng.randint(0, S);
-        if ((g.occ >> (8 * y + x)) & 1u) return;
-        if (g.agent_placed && x == L.ax && y == L.ay) return;
-        if (iabs(L.ax - x) + iabs(L.ay - y) < 2) return;                  // reject_next_to
-        g.occ |= 1ull << (8 * y + x);
-        L.poss |= (uint64_t)(x | (y << 3)) << (6 * g.k);
-        L.tcs |= (uint64_t)g.cur_tc << (6 * g.k);
-        g.k++; L.nobj = g.k; g.tries = 0;
-        if (g.k == nplace) {
-            if (lp.kind == KIND_REDBALL && lp.grey_dists)                  // GoToRedBallGrey: distractors turn grey
-                for (int q = 1; q < g.k; q++) L.tcs = (L.tcs & ~(56ull << (6 * q))) | ((uint64_t)(C_GREY << 3) << (6 * q));
-            if (levelgen) { g.phase = PH_AGENT; g.agent_placed = false; }   // MiniGridEnv.place_agent: agent_pos = None
-            else { g.phase = PH_CHECK; g.fill = 0; }
+        const int x = (int)mulhi32(BB_PEEK(used), (uint32_t)S), y = (int)mulhi32(BB_PEEK(used + 1), (uint32_t)S);
+        used += 2;
+        bool ok = !((g.occ >> (8 * y + x)) & 1u);
+        if (isobj) ok = ok && !(g.agent_placed && x == L.ax && y == L.ay) && (iabs(L.ax - x) + iabs(L.ay - y) >= 2);   // reject_next_to
+        if (!ok) { g.rng.draws += (uint64_t)used; return; }
+        g.tries = 0;
+        if (isobj) {
+            g.occ |= 1ull << (8 * y + x);
+            L.poss |= (uint64_t)(x | (y << 3)) << (6 * g.k);
+            L.tcs |= (uint64_t)g.cur_tc << (6 * g.k);
+            g.k++; L.nobj = g.k;
+            if (g.k == nplace) {
+                if (lp.kind == KIND_REDBALL && lp.grey_dists)              // GoToRedBallGrey: distractors turn grey
+                    for (int q = 1; q < g.k; q++) L.tcs = (L.tcs & ~(56ull << (6 * q))) | ((uint64_t)(C_GREY << 3) << (6 * q));
+                if (levelgen) { g.phase = PH_AGENT; g.agent_placed = false; }   // MiniGridEnv.place_agent: agent_pos = None
+                else { g.phase = PH_CHECK; g.fill = 0; }
+            }
+        } else {
+            L.ax = x; L.ay = y; g.agent_placed = true;
+            L.adir = (int)mulhi32(BB_PEEK(used), 4u);
+            used++;
+            const int fb = 8 * (y + dir_dy(L.adir)) + x + dir_dx(L.adir);
+            const bool front_ok = !((g.occ >> fb) & 1u) || ((lp.wall64 >> fb) & 1u);
+            if (front_ok) {
+                if (levelgen) g.phase = lp.unblocking ? PH_DESC : PH_CHECK;
+                else g.phase = nplace > 0 ? PH_OBJ : PH_CHECK;
+                if (g.phase == PH_CHECK) g.fill = 0;
+            }
         }
-    } else if (g.phase == PH_CHECK) {                // check_objs_reachable: bitboard flood fill, two sweeps per iteration
+        g.rng.draws += (uint64_t)used;
+    } else if (ph == PH_CHECK) {                     // check_objs_reachable: bitboard flood fill, two sweeps per iteration
         if (g.fill == 0) g.fill = 1ull << (8 * L.ay + L.ax);
         const uint64_t pass = ~g.occ;
         uint64_t f1 = g.fill | ((g.fill << 1 | g.fill >> 1 | g.fill << 8 | g.fill >> 8) & pass);
@@ -890,35 +916,50 @@ BB_HD void small_gen_step(const LevelParams &lp, SmallGen &g)
             L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
             L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
         }
-    } else if (g.phase == PH_PICK) {                 // obj = self._rand_elem(objs)
-        const int tc = sm_obj_tc(L.tcs, g.rng.randint(0, n));
+    } else if (ph == PH_START) {                     // RoomGrid._gen_grid of one room: no draws
+        g.attempts++;
+        g.occ = lp.wall64; L.poss = 0; L.tcs = 0; L.nobj = 0; g.k = 0; g.tries = 0;
+        L.ax = S / 2; L.ay = S / 2; L.adir = 0; g.agent_placed = true;
+        if (levelgen) { g.rng.draws += 1; g.phase = n > 0 ? PH_OBJ : PH_AGENT; }      // `_rand_float(0,1) < 0`: one draw
+        else g.phase = PH_AGENT;
+    } else if (ph == PH_PICK) {                      // obj = self._rand_elem(objs); one object: no draw
+        int idx = 0;
+        if (n > 1) { idx = (int)mulhi32(BB_PEEK(0), (uint32_t)n); g.rng.draws += 1; }
+        const int tc = sm_obj_tc(L.tcs, idx);
         L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
         L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
         g.phase = PH_DONE;
-    } else if (g.phase == PH_DESC) {                 // LevelGen.rand_obj, one try
+    } else if (ph == PH_DESC) {                      // LevelGen.rand_obj, one try
         if (g.tries > 100) { g.phase = PH_START; return; }
         g.tries++;
-        const int ci = g.rng.randint(0, 7);
+        const int ci = (int)mulhi32(BB_PEEK(0), 7u);
         const int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
         const int ntypes = L.leaf_kind == I_GOTO ? 4 : 3;
-        const int ti = g.rng.randint(0, ntypes);
+        const int ti = (int)mulhi32(BB_PEEK(1), (uint32_t)ntypes);
         const int type = ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR;
-        int loc = LOC_NONE;
-        if (lp.locations && g.rng.randbool()) loc = g.rng.randint(0, 4);
+        int used = 2, loc = LOC_NONE;
+        if (lp.locations) {
+            const bool with_loc = mulhi32(BB_PEEK(2), 2u) == 0;          // _rand_bool()
+            used = 3;
+            if (with_loc) { loc = (int)mulhi32(BB_PEEK(3), 4u); used = 4; }
+        }
+        g.rng.draws += (uint64_t)used;
         const uint32_t m = sm_match(L, type, color, loc);
         if (m == 0) return;
         L.d_type = type; L.d_color = color; L.d_loc = loc; L.d_mask = m;
         g.phase = PH_DONE;
     }
+#undef BB_PEEK
 }
 
 // Generates one level of a small single-room environment.  Returns the number of attempts.
 BB_HD int generate_small(const LevelParams &lp, RngScalar &rng, SmallLevel &L)
 {
     SmallGen g;
-    g.rng = rng;
+    g.rng = rng; g.rng.blk = ~0ull;
     small_gen_begin(lp, g);
-    while (g.phase != PH_DONE) small_gen_step(lp, g);
+    uint32_t win[8];
+    while (g.phase != PH_DONE) small_gen_step(lp, g, win, 1);
     rng = g.rng; L = g.L;
     return g.attempts;
 }

@@ -802,6 +802,8 @@ __global__ void __launch_bounds__(GS_THREADS)
 k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_iters)
 {
     __shared__ GsBuffered buf[GS_BUF][GS_THREADS];
+    __shared__ uint32_t s_win[8][GS_THREADS];                 // per-lane draw windows (win_ensure)
+    uint32_t *win = &s_win[0][threadIdx.x];
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, tid = threadIdx.x;
     const uint32_t count = *P.gen_count;
@@ -841,7 +843,7 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int 
         if (!__any_sync(FULL, left > 0)) break;
         // ---- one generator iteration per lane --------------------------------------------------------
         if (left > 0) {
-            small_gen_step(lp, g);
+            small_gen_step(lp, g, win, GS_THREADS);
             iters++;
             if (g.phase == PH_DONE) {
                 GsBuffered &b = buf[nbuf][tid];
