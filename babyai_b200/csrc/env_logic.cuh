@@ -1022,7 +1022,7 @@ BB_HD void emit_small_level(const LevelParams &lp, const SmallLevel &L, const Le
 // The step / verifier / observation code below is written against a small "environment memory"
 // accessor M so that the same source runs on (a) plain pointers into the struct-of-arrays state
 // (GlobalMem: host build, large grids) and (b) the warp's shared-memory staging area (pool.cu).
-//   cell(x,y) set_cell(x,y,v) row_word(vert,row,k)      grid (both orientations)
+//   cell(x,y) set_cell(x,y,v) word_at(byte_offset)       grid (both orientations)
 //   ox(k) oy(k) otc(k) set_oxy(k,x,y)                   object table
 //   desc_mask(d) leaf_kind(l) leaf_pre(l) set_leaf_pre(l,v) root_kind() side_and() flags() set_flags(v)
 struct GlobalMem {
@@ -1030,10 +1030,10 @@ struct GlobalMem {
     BB_HD GlobalMem(const LevelParams &lp_, uint8_t *g, ObjTab *o, InstrRec *i) : lp(lp_), grid(g), ot(o), ins(i) {}
     BB_HD int cell(int x, int y) const { return grid[y * lp.rs_g + x]; }
     BB_HD void set_cell(int x, int y, int v) { bb::set_cell(lp, grid, x, y, v); }
-    // aligned word k of stored row `row` of G (vert = false) or GT (vert = true)
-    BB_HD uint32_t row_word(bool vert, int row, int k) const
+    // aligned 32-bit word at byte offset `off` of the env's grid bytes (G at 0, GT at gt_off)
+    BB_HD uint32_t word_at(int off) const
     {
-        const uint8_t *p = grid + (vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) + 4 * k;
+        const uint8_t *p = grid + off;
 #if defined(__CUDA_ARCH__)
         return *reinterpret_cast<const uint32_t *>(p);
 #else
@@ -1309,6 +1309,7 @@ BB_HD void vis_rows(const uint32_t see[7], uint32_t vis[7])
 //   dir 2 (left):  G  row ay+3-vi, window x = ax-6 .. ax     (vj <-> x = ax-6+vj)
 struct ViewGeom {
     bool vert; int nrows, c_row, rstep, k0, sh; bool ok0, ok1, ok2; uint32_t sel_lo, sel_hi;
+    int off0, dstep;            // byte offset (within the env's grid bytes) of window word 0 of column vi: off0 + vi * dstep
 };
 BB_HD ViewGeom view_geom(const LevelParams &lp, int ax, int ay, int dir)
 {
@@ -1326,6 +1327,8 @@ BB_HD ViewGeom view_geom(const LevelParams &lp, int ax, int ay, int dir)
     const int nwords = rs >> 2;
     v.ok0 = v.k0 >= 0 && v.k0 < nwords; v.ok1 = v.k0 + 1 >= 0 && v.k0 + 1 < nwords; v.ok2 = v.k0 + 2 >= 0 && v.k0 + 2 < nwords;
     v.sel_lo = rev ? 0x3456u : 0x3210u; v.sel_hi = rev ? 0x7012u : 0x7654u;
+    v.dstep = v.rstep * rs;
+    v.off0 = (v.vert ? lp.gt_off : 0) + (v.c_row - 3 * v.rstep) * rs + 4 * v.k0;
     return v;
 }
 // cells of view column vi: lo = depths vj 0..3, hi = vj 4..6 (+ one unused byte)
@@ -1335,9 +1338,10 @@ BB_HD void col_load(const M &mem, const ViewGeom &v, int vi, uint32_t &lo, uint3
     const uint32_t WALLW = 0x2A2A2A2Au;
     const int row = v.c_row + v.rstep * (vi - 3);
     const bool rok = row >= 0 && row < v.nrows;
-    const uint32_t w0 = (rok && v.ok0) ? mem.row_word(v.vert, row, v.k0) : WALLW;          // slice(): out of bounds -> Wall()
-    const uint32_t w1 = (rok && v.ok1) ? mem.row_word(v.vert, row, v.k0 + 1) : WALLW;
-    const uint32_t w2 = (rok && v.ok2) ? mem.row_word(v.vert, row, v.k0 + 2) : WALLW;
+    const int off = v.off0 + vi * v.dstep;
+    const uint32_t w0 = (rok && v.ok0) ? mem.word_at(off) : WALLW;          // slice(): out of bounds -> Wall()
+    const uint32_t w1 = (rok && v.ok1) ? mem.word_at(off + 4) : WALLW;
+    const uint32_t w2 = (rok && v.ok2) ? mem.word_at(off + 8) : WALLW;
     const uint32_t a = funnel_r(w0, w1, v.sh), b = funnel_r(w1, w2, v.sh);
     lo = byte_perm(a, b, v.sel_lo);
     hi = byte_perm(a, b, v.sel_hi);

@@ -229,10 +229,7 @@ struct SmemMem {
         put_byte(g, lp.gt_off + x * lp.rs_t + y, v);
         bb::set_cell(lp, grid, x, y, v);
     }
-    __device__ __forceinline__ uint32_t row_word(bool vert, int row, int k) const
-    {
-        return g[((vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) >> 2) + k];
-    }
+    __device__ __forceinline__ uint32_t word_at(int off) const { return g[off >> 2]; }
     __device__ __forceinline__ int ox(int k) const { return byte_of(o, k); }
     __device__ __forceinline__ int oy(int k) const { return byte_of(o + 8, k); }
     __device__ __forceinline__ int otc(int k) const { return byte_of(o + 16, k); }
@@ -371,10 +368,7 @@ struct StagedMem {
         : lp(lp_), sg(sg_), so(so_), si(si_), grid(g), ot(o), ins(i) {}
     __device__ __forceinline__ int cell(int x, int y) const { return sg[y * lp.rs_g + x]; }
     __device__ __forceinline__ void set_cell(int x, int y, int v) { bb::set_cell(lp, sg, x, y, v); bb::set_cell(lp, grid, x, y, v); }
-    __device__ __forceinline__ uint32_t row_word(bool vert, int row, int k) const
-    {
-        return *reinterpret_cast<const uint32_t *>(sg + (vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) + 4 * k);
-    }
+    __device__ __forceinline__ uint32_t word_at(int off) const { return *reinterpret_cast<const uint32_t *>(sg + off); }
     __device__ __forceinline__ int ox(int k) const { return so->x[k]; }
     __device__ __forceinline__ int oy(int k) const { return so->y[k]; }
     __device__ __forceinline__ int otc(int k) const { return so->tc[k]; }
@@ -548,10 +542,7 @@ struct SmemOnlyMem {            // lane-private records in shared memory (byte a
     __device__ __forceinline__ SmemOnlyMem(const LevelParams &lp_, uint8_t *g_, uint8_t *o_, uint8_t *i_) : lp(lp_), g(g_), o(o_), i(i_) {}
     __device__ __forceinline__ int cell(int x, int y) const { return g[y * lp.rs_g + x]; }
     __device__ __forceinline__ void set_cell(int x, int y, int v) { bb::set_cell(lp, g, x, y, v); }
-    __device__ __forceinline__ uint32_t row_word(bool vert, int row, int k) const
-    {
-        return *reinterpret_cast<const uint32_t *>(g + (vert ? lp.gt_off + row * lp.rs_t : row * lp.rs_g) + 4 * k);
-    }
+    __device__ __forceinline__ uint32_t word_at(int off) const { return *reinterpret_cast<const uint32_t *>(g + off); }
     __device__ __forceinline__ int ox(int k) const { return o[k]; }
     __device__ __forceinline__ int oy(int k) const { return o[MAXOBJ + k]; }
     __device__ __forceinline__ int otc(int k) const { return o[2 * MAXOBJ + k]; }
