@@ -893,7 +893,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
-    bool gen_generic; int gen_small_blocks, gen_budget;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
+    bool gen_generic; int gen_small_blocks, gen_budget, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 0 = k_step8 (8 lanes per env, default), 1 = k_step (lane per env), 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
@@ -911,7 +911,7 @@ struct bb_pool {
     long long launches;
     cudaGraphExec_t graph; GraphKey gkey;
     cudaEvent_t ev[3];
-    cudaEvent_t tev[4]; bool time_rollout;
+    cudaEvent_t tev[4]; bool time_rollout, tev_kernel, tev_refill;
     const void *chk_obs; bool direct;            // bb_pool_step_host: caller buffers are page-locked       // bb_pool_rollout_timed
 };
 
@@ -1032,6 +1032,7 @@ static int sched_join(bb_pool *p, cudaStream_t st)
 static int sched_leave_rollout(bb_pool *p, cudaStream_t st)
 {
     if (!p->after_rollout) return 0;
+    p->rollouts = 0;
     if (sched_join(p, st)) return 1;
     if (p->mode == BB_MODE_AUTORESET) launch_gen(p, st);
     p->after_rollout = false;
@@ -1066,11 +1067,13 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         p->gen_small_blocks = prop.multiProcessorCount * per_sm;
     }
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
-    p->gen_budget = 64;                                    // generator iterations per lane per rollout refill
+    p->gen_budget = 128;                                   // generator iterations per lane per refill pass
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
+    p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
+    if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) p->refill_every = v; }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
-    p->D = p->lp.cells_pad <= 256 ? 96 : 8;             // small grids: >= 2 x the 40-step rollout of bb_pool_rollout
+    p->D = p->lp.cells_pad <= 256 ? 128 : 8;            // small grids: >= 3 x the 40-step rollout of bb_pool_rollout (refill every 2nd launch)
     if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 256) p->D = d; }
     p->G = p->D >= 8 ? p->D / 8 : 1;
     if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
@@ -1188,7 +1191,7 @@ int bb_pool_reset(bb_pool *p, uint8_t *obs_dev, int8_t *dir_dev, void *stream)
     CU(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (sched_join(p, st)) return 1;
-    p->after_rollout = false;
+    p->after_rollout = false; p->rollouts = 0;
     launch_gen(p, st);                                 // make sure every ring holds a level
     launch_step(p, nullptr, 1, obs_dev, nullptr, nullptr, dir_dev, 1, st);
     if (p->mode == BB_MODE_AUTORESET) launch_gen(p, st);      // rings full again: a sync point
@@ -1245,7 +1248,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || T < 1) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     cudaStream_t user = (cudaStream_t)stream;
-    const bool persistent = p->lp.cells_pad <= 128 && !p->no_persistent && (p->mode == BB_MODE_FREEZE || p->D >= 2 * T);
+    const bool persistent = p->lp.cells_pad <= 128 && !p->no_persistent && (p->mode == BB_MODE_FREEZE || p->D >= (p->refill_every + 1) * T);
     if (!persistent) return rollout_graph(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, user);
     if (sched_join(p, user)) return 1;                 // every k_gen enqueued so far (rings topped up to D - what
                                                        // the previous rollout consumed >= D - T >= T levels per env)
@@ -1253,7 +1256,8 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
     const size_t smem = (size_t)R_WARPS * warp_words * 4;
     const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
-    const bool refill = p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL");
+    // one refill pass serves `refill_every` launches (more envs per pass = more lanes busy in k_gen_small)
+    const bool refill = p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL") && (p->rollouts++ % p->refill_every) == 0;
     const bool dbg_timing = p->time_rollout;
     cudaEvent_t *dbg_ev = p->tev;
     if (dbg_timing && !dbg_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&dbg_ev[i]));
@@ -1269,7 +1273,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), user);
         launch_gen_kernel(p, p->D, user, p->gen_budget);
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, user);
-        if (dbg_timing) cudaEventRecord(dbg_ev[3], user);
+        if (dbg_timing) { cudaEventRecord(dbg_ev[3], user); p->tev_refill = true; }
         p->launches++;
     } else if (refill) {
         // fork point: the head snapshot k_gen will work from (levels consumed before this launch)
@@ -1278,7 +1282,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     }
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
     k_rollout<<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-    if (dbg_timing) cudaEventRecord(dbg_ev[1], user);
+    if (dbg_timing) { cudaEventRecord(dbg_ev[1], user); p->tev_kernel = true; }
     p->launches++;
     if (refill && !gen_serial) {
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
@@ -1286,7 +1290,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), p->gen_stream);
         launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget);      // bounded: runs beside k_rollout
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
-        if (dbg_timing) cudaEventRecord(dbg_ev[3], p->gen_stream);
+        if (dbg_timing) { cudaEventRecord(dbg_ev[3], p->gen_stream); p->tev_refill = true; }
         p->gen_outstanding = true;
         p->launches++;
     }
@@ -1301,15 +1305,15 @@ int bb_pool_rollout_timed(bb_pool *p, const int8_t *actions_dev, int32_t T, uint
 {
     if (!p || !ms_rollout_kernel || !ms_refill) return fail("bad arguments");
     *ms_rollout_kernel = 0; *ms_refill = 0;
-    p->time_rollout = true;
+    p->time_rollout = true; p->tev_kernel = false; p->tev_refill = false;
     const int rc = bb_pool_rollout(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, p->stream);
     p->time_rollout = false;
     if (rc) return rc;
     CU(cudaStreamSynchronize(p->stream));
     CU(cudaDeviceSynchronize());
-    if (p->tev[0] && cudaEventQuery(p->tev[1]) == cudaSuccess) {
+    if (p->tev[0] && p->tev_kernel) {
         CU(cudaEventElapsedTime(ms_rollout_kernel, p->tev[0], p->tev[1]));
-        if (cudaEventQuery(p->tev[3]) == cudaSuccess) cudaEventElapsedTime(ms_refill, p->tev[2], p->tev[3]);
+        if (p->tev_refill) CU(cudaEventElapsedTime(ms_refill, p->tev[2], p->tev[3]));
     }
     return 0;
 }

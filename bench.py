@@ -260,9 +260,9 @@ def main():
     for t in range(24):
         a, b = env.rollout_timed(actions, obs, rew, done, dirs)
         if t >= 4 and a > 0:
-            kr.append(a); kf.append(b)
+            kr.append(a); kf.append(b)          # b = 0 for the launches that do not refill
     k_roll_ms = sum(kr) / len(kr) if kr else 0.0
-    k_refill_ms = sum(kf) / len(kf) if kf else 0.0
+    k_refill_ms = sum(kf) / len(kf) if kf else 0.0      # amortised per launch
     # the per-step entry point (policy in the loop): bb_pool_step on device buffers, one launch per step
     Ks = min(K, 600)
     for t in range(20):
