@@ -602,10 +602,13 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ act
     SmemOnlyMem mem(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * SM_OBJ_STRIDE),
                     reinterpret_cast<uint8_t *>(si + lane * SM_INS_STRIDE));
     uint32_t n_step = 0, n_end = 0, n_succ = 0, n_err = 0, consumed = 0;
-    int a_next = valid ? actions[env] : 0;
+    // actions are read one step ahead with a sign-extending load (no dependent conversion instruction: the
+    // compiler otherwise converts the byte right after the load and the warp waits for DRAM there)
+    int a_next = 0;
+    if (valid) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + env));
     for (int t = 0; t < T; t++) {
         const int a = a_next;
-        if (valid && t + 1 < T) a_next = actions[(size_t)(t + 1) * n + env];      // prefetch the next action
+        if (valid && t + 1 < T) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + (size_t)(t + 1) * n + env));
         uint32_t w[OBS_WORDS];
 #pragma unroll
         for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
@@ -646,6 +649,18 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ act
                     h = *reinterpret_cast<const EnvHot *>(&hv);
                     consumed++;
                 } else n_err++;
+            }
+            // an episode about to time out (73 % of the episode ends under random actions) will need its next
+            // level two steps from now: pull that ring slot into L2 ahead of the dependent loads of the swap-in
+            if (mode == BB_MODE_AUTORESET && (int)h.step_count + 2 == (int)h.max_steps && consumed < avail) {
+                const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.grid));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.obj));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.obj) + 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.ins));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.ins) + 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.hot));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.tok));
             }
             observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of(h, mem), w);
             const size_t oi = (size_t)t * n + env;
