@@ -427,8 +427,34 @@ BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o,
 // reachable if it is in F or 4-adjacent to F; every object and door must be.
 BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
 {
-    uint32_t *pass = g.m->pass, *f = g.m->fill;
     const uint32_t full = (lp.W >= 32) ? 0xFFFFFFFFu : ((1u << lp.W) - 1u);
+#if defined(__CUDA_ARCH__)
+    // device (generate_level runs with the whole warp on one level): lane y owns grid row y, the rows above and
+    // below come by shuffle, one iteration spreads the fill by one row and up to four columns in every row at once
+    const int lane = threadIdx.x & 31;
+    uint32_t pass = 0, things = 0, f = 0;
+    if (lane < lp.H) {
+        const uint32_t occ = g.m->occ[lane], door = g.m->doorcell[lane];
+        pass = (~occ | door) & full;
+        things = (occ & ~lp.wall_rows[lane]) | door;              // non-wall, non-empty cells
+        if (lane == g.ay) f = 1u << g.ax;
+    }
+    uint32_t up, dn;
+    for (;;) {
+        up = __shfl_up_sync(0xFFFFFFFFu, f, 1); if (lane == 0) up = 0;
+        dn = __shfl_down_sync(0xFFFFFFFFu, f, 1); if (lane == 31) dn = 0;
+        uint32_t n = (f | (f << 1) | (f >> 1) | up | dn) & pass;
+        n |= ((n << 1) | (n >> 1)) & pass;
+        n |= ((n << 1) | (n >> 1)) & pass;
+        n |= ((n << 1) | (n >> 1)) & pass;
+        const bool changed = n != f;
+        f = n;
+        if (!__any_sync(0xFFFFFFFFu, changed)) break;
+    }
+    const uint32_t near = f | (f << 1) | (f >> 1) | up | dn;
+    return __any_sync(0xFFFFFFFFu, (things & ~near) != 0u) ? GEN_REJECT : GEN_OK;
+#else
+    uint32_t *pass = g.m->pass, *f = g.m->fill;
     for (int y = 0; y < lp.H; y++) { pass[y] = (~g.m->occ[y] | g.m->doorcell[y]) & full; f[y] = 0; }
     f[g.ay] = 1u << g.ax;
     for (;;) {
@@ -454,6 +480,7 @@ BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
         if (things & ~near) return GEN_REJECT;
     }
     return GEN_OK;
+#endif
 }
 
 // ObjDesc.find_matching_objs(env, use_location=True) over the object table
