@@ -1088,9 +1088,11 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) p->refill_every = v; }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
-    p->D = p->lp.cells_pad <= 256 ? 128 : 8;            // small grids: >= 3 x the 40-step rollout of bb_pool_rollout (refill every 2nd launch)
+    // small grids: >= 3 x the 40-step rollout of bb_pool_rollout (refill every 2nd launch); large grids: deep enough
+    // that one generation pass per 32 steps (many levels per pass: a level is ~0.2-0.4 ms of serial work) stays ahead
+    p->D = p->lp.cells_pad <= 256 ? 128 : 64;
     if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 256) p->D = d; }
-    p->G = p->D >= 8 ? p->D / 8 : 1;
+    p->G = p->D >= 64 ? 32 : (p->D >= 8 ? p->D / 4 : 1);
     if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
     p->nev = p->D / p->G + 3;
     if (p->nev > MAX_GEN_EVENTS) { delete p; return fail("ring depth / generation period too large"); }
