@@ -570,11 +570,13 @@ __device__ __forceinline__ void warp_copy_records(uint32_t *sm, int stride_words
     }
 }
 
+template <int ACT_BYTES>
 __global__ void __launch_bounds__(R_THREADS)
-k_rollout(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
+k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions_v, uint8_t *__restrict__ obs,
           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
-          const int mode)
+          const int mode, const int force_reset)
 {
+    const int8_t *actions = reinterpret_cast<const int8_t *>(actions_v);
     extern __shared__ __align__(16) uint32_t smr[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int env0 = (blockIdx.x * R_WARPS + warp) * 32, env = env0 + lane;
@@ -605,16 +607,20 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ act
     // actions are read one step ahead with a sign-extending load (no dependent conversion instruction: the
     // compiler otherwise converts the byte right after the load and the warp waits for DRAM there)
     int a_next = 0;
-    if (valid) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + env));
+    if (valid && !force_reset) {
+        if (ACT_BYTES == 1) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + env));
+        else a_next = (int)reinterpret_cast<const long long *>(actions_v)[env];      // int64 actions: single-step calls only
+    }
     for (int t = 0; t < T; t++) {
         const int a = a_next;
-        if (valid && t + 1 < T) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + (size_t)(t + 1) * n + env));
+        if (ACT_BYTES == 1 && valid && t + 1 < T) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + (size_t)(t + 1) * n + env));
         uint32_t w[OBS_WORDS];
 #pragma unroll
         for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
         if (valid) {
-            float rew = 0.0f; bool dn = false, begin = false;
-            if (!(h.dirflags & 4)) {
+            float rew = 0.0f; bool dn = false, begin = force_reset != 0;
+            if (force_reset) {
+            } else if (!(h.dirflags & 4)) {
                 const StepResult sr = step_env(h, mem, a);
                 rew = sr.reward; dn = sr.done;
                 n_step++; n_end += dn; n_succ += sr.success;
@@ -664,8 +670,8 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ act
             }
             observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of(h, mem), w);
             const size_t oi = (size_t)t * n + env;
-            reward[oi] = rew;
-            done[oi] = dn ? 1 : 0;
+            if (reward) reward[oi] = rew;
+            if (done) done[oi] = dn ? 1 : 0;
             if (dirs) dirs[oi] = (int8_t)(h.dirflags & 3);
         }
         stage_obs(tile, w, lane);
@@ -910,7 +916,7 @@ struct bb_pool {
     int D, G, nev;
     bool gen_generic; int gen_small_blocks, gen_budget, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
-    int step_kernel;               // 0 = k_step8 (8 lanes per env, default), 1 = k_step (lane per env), 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
+    int step_kernel;               // 3 = k_rollout with T = 1 for small grids, k_step8 otherwise (default); 0 = k_step8; 1 = k_step; 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
     cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
     cudaStream_t gen_stream;       // level generation runs here, concurrently with the steps
@@ -987,7 +993,17 @@ static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8
                         int8_t *dirs, int force_reset, cudaStream_t st)
 {
     const int blocks8 = (p->n + 4 * S8_WARPS - 1) / (4 * S8_WARPS);
-    const int kernel = p->step_kernel == 2 && p->lp.cells_pad > 128 ? 1 : p->step_kernel;
+    int kernel = p->step_kernel;
+    if ((kernel == 2 || kernel == 3) && p->lp.cells_pad > 128) kernel = kernel == 3 ? 0 : 1;
+    if (kernel == 3) {                   // small grids: the persistent kernel with T = 1 (coalesced state load / store)
+        const int gs = (p->lp.cells_pad >> 2) | 1;
+        const size_t smem = (size_t)R_WARPS * (32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS) * 4;
+        const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
+        if (action_bytes == 8) k_rollout<8><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset);
+        else k_rollout<1><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset);
+        p->launches++;
+        return;
+    }
 #define BB_LAUNCH(K, GRID, THREADS)                                                                                      \
     do {                                                                                                                 \
         if (action_bytes == 8) K<8><<<GRID, THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset); \
@@ -1124,10 +1140,12 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));                  // lo = lowest priority
         CU(cudaStreamCreateWithPriority(&p->gen_stream, cudaStreamNonBlocking, lo));
     }
-    CU(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
     // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
-    CU(cudaFuncSetAttribute(k_rollout, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_gen_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_gen_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_gen, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1298,7 +1316,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaEventRecord(p->ev_fork, user));
     }
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
-    k_rollout<<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+    k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0);
     if (dbg_timing) { cudaEventRecord(dbg_ev[1], user); p->tev_kernel = true; }
     p->launches++;
     if (refill && !gen_serial) {

@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 LEVEL = 'GoToLocal'
 N_ENVS = 65536
-CHUNK = 40                      # rollout length per CUDA graph (= --frames-per-proc, arguments.py:42)
+CHUNK = int(os.environ.get("BENCH_CHUNK", "40"))   # rollout length per launch (= --frames-per-proc, arguments.py:42)
 ALGO_BYTES_PER_STEP = 153       # 147 obs + 4 reward + 1 done + 1 action
 FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
 METRIC = 'env-steps/sec at 65 536 envs (GoToLocal); obs bit-exact vs CPU ref'
