@@ -1113,9 +1113,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->nev = p->D / p->G + 3;
     if (p->nev > MAX_GEN_EVENTS) { delete p; return fail("ring depth / generation period too large"); }
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
-    p->step_kernel = 0;
+    p->step_kernel = 3;
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
-    if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : 0;
+    if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : !strcmp(e, "cols") ? 0 : 3;
     p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr; p->tev[0] = p->tev[1] = p->tev[2] = p->tev[3] = nullptr; p->time_rollout = false; p->chk_obs = nullptr; p->direct = false;
     const LevelParams &lp = p->lp;
     const size_t n = (size_t)n_envs, D = (size_t)p->D;
