@@ -70,6 +70,7 @@ enum : int {
 struct LevelParams {
     int32_t kind, room_size, num_rows, num_cols, num_dists, instr, doors_open, grey_dists;
     int32_t locations, unblocking, implicit_unlock;
+    int32_t all_unique, require_unreachable;
     int32_t n_action_kinds, action_kinds[4];
     int32_t n_instr_kinds, instr_kinds[3];
     int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
@@ -240,6 +241,8 @@ struct GenMem {
     uint32_t pass[MAXH], fill[MAXH];  // reachability flood fill
     uint8_t door_y_right[MAXROOMS];   // Room.door_pos[0].y of room r
     uint8_t door_x_down[MAXROOMS];    // Room.door_pos[1].x of room r
+    uint8_t door_id_right[MAXROOMS];  // object id of the door in room r's right / down slot
+    uint8_t door_id_down[MAXROOMS];
     // instruction being built
     int leaf_kind[4]; int desc_type[8], desc_color[8], desc_loc[8];
     uint32_t desc_mask[8];
@@ -345,6 +348,7 @@ BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ro
     else { x = g.m->door_x_down[owner]; y = (owner / lp.num_cols) * (S - 1) + S - 1; g.door_down |= 1u << owner; }
     if (locked) g.room_locked |= 1u << room; else g.room_locked &= ~(1u << room);   // room.locked = locked
     int id = g.nobj++;
+    if (k == 0 || k == 2) g.m->door_id_right[owner] = (uint8_t)id; else g.m->door_id_down[owner] = (uint8_t)id;
     g.m->obj.x[id] = (uint8_t)x; g.m->obj.y[id] = (uint8_t)y; g.m->obj.tc[id] = (uint8_t)(T_DOOR | (color << 3));
     g.m->doorcell[y] |= 1u << x;
     if (locked) g.locked_door = id;
@@ -406,18 +410,26 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o)
     return GEN_OK;
 }
 
-// RoomGrid.add_distractors(i=None, j=None, num, all_unique=False)
-BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o, int num, int &first_id)
+// RoomGrid.add_distractors(i=None, j=None, num, all_unique): with all_unique a (type, color) pair that was
+// already drawn is drawn again before any room / position draw
+BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o, int num, int &first_id, bool all_unique = false)
 {
     first_id = g.nobj;
-    for (int n = 0; n < num; n++) {
+    uint32_t seen = 0;                       // bit 6 * type_rank + color
+    for (int n = 0; n < num;) {
         int color = color_by_name_rank(g.rng.randint(0, 6));
         int t = g.rng.randint(0, 3);
         int type = t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX;
+        if (all_unique) {
+            const uint32_t bit = 1u << (6 * t + color);
+            if (seen & bit) continue;
+            seen |= bit;
+        }
         int ri = g.rng.randint(0, lp.num_cols);
         int rj = g.rng.randint(0, lp.num_rows);
         int id;
         BB_TRY(g_add_object(lp, g, o, rj * lp.num_cols + ri, type, color, id));
+        n++;
     }
     return GEN_OK;
 }
@@ -655,14 +667,42 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
         g_single_desc(g, lp, o, I_GOTO, ball);
         return GEN_OK;
     }
-    if (lp.kind == KIND_OBJ) {                     // iclr19_levels.py:88-92, 119-124, 247-257, 365-371
+    if (lp.kind == KIND_OBJ) {                     // iclr19_levels.py:88-92, 119-124, 202-211, 247-257, 365-415, 482-491
         int first;
         BB_TRY(g_place_agent(lp, g));
         BB_TRY(g_connect_all(lp, g, o));
-        BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first));
-        BB_TRY(g_check_reachable(lp, g));
-        int pick = first + g.rng.randint(0, lp.num_dists);
-        g_single_desc(g, lp, o, lp.instr, pick);
+        BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first, lp.all_unique != 0));
+        if (lp.require_unreachable) { if (g_check_reachable(lp, g) == GEN_OK) return GEN_REJECT; }   // Level_UnblockPickup
+        else BB_TRY(g_check_reachable(lp, g));
+        if (lp.instr == I_OPEN) {
+            // doors as Level_Open lists them: every door once per adjacent room; columns outer, rows inner, sides 0..3
+            int nd = 0;
+            for (int i = 0; i < lp.num_cols; i++)
+                for (int j = 0; j < lp.num_rows; j++)
+                    for (int k = 0; k < 4; k++) { const int r = j * lp.num_cols + i; if (g_has_slot(lp, r, k) && g_has_door(lp, g, r, k)) nd++; }
+            int pick = g.rng.randint(0, nd), door = 0;
+            for (int i = 0; i < lp.num_cols; i++)
+                for (int j = 0; j < lp.num_rows; j++)
+                    for (int k = 0; k < 4; k++) {
+                        const int r = j * lp.num_cols + i;
+                        if (!(g_has_slot(lp, r, k) && g_has_door(lp, g, r, k))) continue;
+                        if (pick-- == 0)
+                            door = k == 0 ? g.m->door_id_right[r] : k == 1 ? g.m->door_id_down[r]
+                                 : k == 2 ? g.m->door_id_right[r - 1] : g.m->door_id_down[r - lp.num_cols];
+                    }
+            g_single_desc(g, lp, o, I_OPEN, door);
+        } else if (lp.instr == I_PUTNEXT) {          // o1, o2 = self._rand_subset(objs, 2)
+            const int i1 = g.rng.randint(0, lp.num_dists);
+            int i2 = g.rng.randint(0, lp.num_dists - 1);
+            if (i2 >= i1) i2++;                      // index into the list with o1 removed
+            g_single_desc(g, lp, o, I_PUTNEXT, first + i1);
+            const int tc2 = g.m->obj.tc[first + i2];
+            g.m->desc_type[1] = tc2 & 7; g.m->desc_color[1] = tc2 >> 3; g.m->desc_loc[1] = LOC_NONE;
+            g.m->desc_mask[1] = g_match(lp, g, o, tc2 & 7, tc2 >> 3, LOC_NONE);
+        } else {
+            int pick = first + g.rng.randint(0, lp.num_dists);
+            g_single_desc(g, lp, o, lp.instr, pick);
+        }
         return GEN_OK;
     }
     // LevelGen.gen_mission, levelgen.py:293-319

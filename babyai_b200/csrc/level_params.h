@@ -19,6 +19,9 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
     lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
     lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
+    lp->all_unique = s->all_unique; lp->require_unreachable = s->require_unreachable;
+    if (s->kind == BB_KIND_OBJ && (s->instr < BB_I_GOTO || s->instr > BB_I_PUTNEXT)) return "bad instruction kind";
+    if (s->kind == BB_KIND_OBJ && s->instr == BB_I_PUTNEXT && s->num_dists < 2) return "PutNext needs two objects";
     lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
     for (int i = 0; i < 4; i++) lp->action_kinds[i] = s->action_kinds[i];
     for (int i = 0; i < 3; i++) lp->instr_kinds[i] = s->instr_kinds[i];
@@ -33,7 +36,7 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     lp->gt_off = (lp->H * lp->rs_g + 15) / 16 * 16;
     lp->cells_pad = lp->gt_off + (lp->W * lp->rs_t + 15) / 16 * 16;
     lp->nav_time_maze = s->room_size * s->room_size * s->num_rows * s->num_cols;   // levelgen.py:42-43
-    int max_objs = s->num_dists + 1;
+    int max_objs = s->num_dists + (s->kind == BB_KIND_OBJ ? 0 : 1);   // + the red ball / the key of the locked room
     if (s->kind == BB_KIND_LEVELGEN) {
         if (s->n_action_kinds < 1 || s->n_action_kinds > 4 || s->n_instr_kinds < 1 || s->n_instr_kinds > 3)
             return "bad LevelGen kinds";
@@ -53,7 +56,7 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
         if (putnext) leaf = 1 + per_desc + 2 + per_desc;
         int side = (has_and || has_seq) ? 2 * leaf + 1 : leaf;
         lp->max_tokens = has_seq ? 2 * side + 2 : side;
-    } else lp->max_tokens = leaf;
+    } else lp->max_tokens = (s->kind == BB_KIND_OBJ && s->instr == BB_I_PUTNEXT) ? 1 + per_desc + 2 + per_desc : leaf;
     lp->max_tokens = (lp->max_tokens + 7) / 8 * 8;          // 16-byte rows
     if (lp->max_tokens > MAXTOK) lp->max_tokens = MAXTOK;
     // wall template of the empty RoomGrid (Grid.wall_rect per room)
@@ -68,7 +71,8 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     const bool lg_ok = s->kind != BB_KIND_LEVELGEN ||
         (s->locked_room_prob <= 0 && s->n_instr_kinds == 1 && s->instr_kinds[0] == BB_K_ACTION && s->n_action_kinds == 1 &&
          (s->action_kinds[0] == BB_I_GOTO || s->action_kinds[0] == BB_I_PICKUP));
-    if (s->num_rows == 1 && s->num_cols == 1 && lp->W <= 8 && lp->H <= 8 && s->num_dists + 1 <= 10 && lg_ok) {
+    const bool obj_ok = s->kind != BB_KIND_OBJ || ((s->instr == BB_I_GOTO || s->instr == BB_I_PICKUP) && !s->all_unique && !s->require_unreachable);
+    if (s->num_rows == 1 && s->num_cols == 1 && lp->W <= 8 && lp->H <= 8 && s->num_dists + 1 <= 10 && lg_ok && obj_ok) {
         lp->small = 1;
         lp->wall64 = 0;
         for (int y = 0; y < 8; y++)

@@ -2,11 +2,12 @@
 level class, as a `bb_level_spec` (include/babyai_b200.h).
 
 Each entry cites the class in /root/reference/babyai/levels/iclr19_levels.py it
-mirrors.  Three generator families cover 39 of the 47 ICLR-19 levels:
+mirrors.  Three generator families cover 45 of the 47 ICLR-19 levels (all but Unlock and GoToImpUnlock):
   REDBALL  : Level_GoToRedBall* (:10-72)
   OBJ      : place_agent, connect_all, add_distractors, check_objs_reachable,
-             pick one, GoTo/Pickup it -- Level_GoToObj* (:75-102),
-             Level_GoToLocal* (:105-184), Level_GoTo* (:224-301), Level_Pickup (:360-371)
+             pick one (or a door, or two), GoTo / Pickup / Open / PutNext it -- Level_GoToObj* (:75-102),
+             Level_GoToLocal* (:105-184), Level_PutNextLocal* (:187-221), Level_GoTo* (:224-301),
+             Level_Pickup (:360-371), Level_UnblockPickup (:374-391), Level_Open (:394-415), Level_PutNext (:477-491)
   LEVELGEN : levelgen.py:256-460 LevelGen -- PickupLoc (:494), GoToSeq (:518), Synth*
              (:554-633), MiniBossLevel (:636), BossLevel (:648), BossLevelNoUnlock (:655)
 """
@@ -26,11 +27,13 @@ class LevelSpec(C.Structure):
         ('locations', C.c_int32), ('unblocking', C.c_int32), ('implicit_unlock', C.c_int32),
         ('n_action_kinds', C.c_int32), ('action_kinds', C.c_int32 * 4),
         ('n_instr_kinds', C.c_int32), ('instr_kinds', C.c_int32 * 3),
+        ('all_unique', C.c_int32), ('require_unreachable', C.c_int32),
     ]
 
 
 def _spec(kind, room_size=8, num_rows=1, num_cols=1, num_dists=0, instr=I_GOTO, doors_open=0, grey_dists=0,
-          locked_room_prob=0.0, locations=0, unblocking=0, implicit_unlock=1, action_kinds=(), instr_kinds=()):
+          locked_room_prob=0.0, locations=0, unblocking=0, implicit_unlock=1, action_kinds=(), instr_kinds=(),
+          all_unique=0, require_unreachable=0):
     s = LevelSpec()
     s.kind, s.room_size, s.num_rows, s.num_cols, s.num_dists = kind, room_size, num_rows, num_cols, num_dists
     s.instr, s.doors_open, s.grey_dists = instr, doors_open, grey_dists
@@ -42,6 +45,7 @@ def _spec(kind, room_size=8, num_rows=1, num_cols=1, num_dists=0, instr=I_GOTO, 
     s.n_instr_kinds = len(instr_kinds)
     for i, a in enumerate(instr_kinds):
         s.instr_kinds[i] = a
+    s.all_unique, s.require_unreachable = all_unique, require_unreachable
     return s
 
 
@@ -49,8 +53,9 @@ def redball(num_dists=7, grey=0):
     return _spec(KIND_REDBALL, 8, 1, 1, num_dists, grey_dists=grey)
 
 
-def obj_level(room_size=8, num_rows=1, num_cols=1, num_dists=8, instr=I_GOTO, doors_open=0):
-    return _spec(KIND_OBJ, room_size, num_rows, num_cols, num_dists, instr=instr, doors_open=doors_open)
+def obj_level(room_size=8, num_rows=1, num_cols=1, num_dists=8, instr=I_GOTO, doors_open=0, all_unique=0, require_unreachable=0):
+    return _spec(KIND_OBJ, room_size, num_rows, num_cols, num_dists, instr=instr, doors_open=doors_open,
+                 all_unique=all_unique, require_unreachable=require_unreachable)
 
 
 ALL_ACTIONS = (I_GOTO, I_PICKUP, I_OPEN, I_PUTNEXT)
@@ -95,6 +100,12 @@ LEVELS = {
     'GoToObjMazeS6': lambda: obj_level(6, 3, 3, 1),
     'GoToObjMazeS7': lambda: obj_level(7, 3, 3, 1),
     'Pickup': lambda: obj_level(8, 3, 3, 18, instr=I_PICKUP),
+    'UnblockPickup': lambda: obj_level(8, 3, 3, 20, instr=I_PICKUP, require_unreachable=1),
+    'Open': lambda: obj_level(8, 3, 3, 18, instr=I_OPEN),
+    'PutNext': lambda: obj_level(8, 3, 3, 18, instr=I_PUTNEXT),
+    'PutNextLocal': lambda: obj_level(8, 1, 1, 8, instr=I_PUTNEXT, all_unique=1),
+    'PutNextLocalS5N3': lambda: obj_level(5, 1, 1, 3, instr=I_PUTNEXT, all_unique=1),
+    'PutNextLocalS6N4': lambda: obj_level(6, 1, 1, 4, instr=I_PUTNEXT, all_unique=1),
     'PickupLoc': lambda: levelgen(num_rows=1, num_cols=1, num_dists=8, locked_room_prob=0, locations=1, unblocking=0,
                                   action_kinds=(I_PICKUP,), instr_kinds=(K_ACTION,)),
     'GoToSeq': lambda: levelgen(action_kinds=(I_GOTO,), locked_room_prob=0, locations=0, unblocking=0),

@@ -31,7 +31,7 @@ extern "C" {
 
 /* level families (which gen_mission the generator kernel runs) */
 #define BB_KIND_REDBALL 0         /* iclr19_levels.py:10-72   GoToRedBall*          */
-#define BB_KIND_OBJ 1             /* iclr19_levels.py:75-301,360-371 GoToObj/GoToLocal/GoTo/Pickup */
+#define BB_KIND_OBJ 1             /* iclr19_levels.py:75-301,360-415,477-491 GoToObj/GoToLocal/PutNextLocal/GoTo/Pickup/UnblockPickup/Open/PutNext */
 #define BB_KIND_LEVELGEN 2        /* levelgen.py:256-460 LevelGen (PickupLoc .. BossLevel) */
 /* instruction / action kinds (verifier.py) */
 #define BB_I_GOTO 0
@@ -49,13 +49,15 @@ extern "C" {
 typedef struct bb_level_spec {
     int32_t kind;
     int32_t room_size, num_rows, num_cols, num_dists;
-    int32_t instr;              /* BB_KIND_OBJ: BB_I_GOTO or BB_I_PICKUP      */
+    int32_t instr;              /* BB_KIND_OBJ: BB_I_GOTO / BB_I_PICKUP / BB_I_OPEN / BB_I_PUTNEXT */
     int32_t doors_open;         /* Level_GoTo(doors_open=...)                 */
     int32_t grey_dists;         /* Level_GoToRedBallGrey                      */
     double  locked_room_prob;   /* LevelGen(...) from here on                 */
     int32_t locations, unblocking, implicit_unlock;
     int32_t n_action_kinds; int32_t action_kinds[4];
     int32_t n_instr_kinds;  int32_t instr_kinds[3];
+    int32_t all_unique;         /* BB_KIND_OBJ: add_distractors(all_unique=...) (Level_PutNextLocal)        */
+    int32_t require_unreachable;/* BB_KIND_OBJ: Level_UnblockPickup rejects levels whose objects are all reachable */
 } bb_level_spec;
 
 typedef struct bb_pool bb_pool;

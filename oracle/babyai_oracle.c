@@ -81,6 +81,8 @@ typedef struct {
     int32_t locations, unblocking, implicit_unlock;
     int32_t n_action_kinds; int32_t action_kinds[4];
     int32_t n_instr_kinds;  int32_t instr_kinds[3];
+    int32_t all_unique;           /* add_distractors(all_unique=...) of the KIND_OBJ levels */
+    int32_t require_unreachable;  /* Level_UnblockPickup: reject when every object IS reachable */
 } LevelSpec;
 
 typedef struct { int type, color, is_open, is_locked, cur_x, cur_y; } Obj;
@@ -771,14 +773,35 @@ static int gen_mission(Env *e)
         return OK;
     }
     if (sp->kind == KIND_OBJ) {
-        /* iclr19_levels.py:88-92 GoToObj, :119-124 GoToLocal, :247-257 GoTo, :365-371 Pickup */
+        /* iclr19_levels.py:88-92 GoToObj, :119-124 GoToLocal, :202-211 PutNextLocal, :247-257 GoTo, :365-371 Pickup,
+         * :380-391 UnblockPickup, :399-415 Open, :482-491 PutNext */
         int objs[MAXOBJ], n;
         TRY(place_agent(e));
         TRY(connect_all(e));
-        TRY(add_distractors(e, sp->num_dists, 0, objs, &n));
-        TRY(check_objs_reachable(e));
-        int obj = objs[rand_int(e, 0, n)];
-        e->root = new_node(e, sp->instr, NONE, NONE, new_desc(e, e->obj[obj].type, e->obj[obj].color, NONE), NONE);
+        TRY(add_distractors(e, sp->num_dists, sp->all_unique, objs, &n));
+        if (sp->require_unreachable) { if (check_objs_reachable(e) == OK) return REJECT; }
+        else TRY(check_objs_reachable(e));
+        if (sp->instr == I_OPEN) {
+            /* every door once per adjacent room: columns outer, rows inner, sides right/down/left/up */
+            int doors[MAXROOM * 4], nd = 0;
+            for (int i = 0; i < sp->num_cols; i++)
+                for (int j = 0; j < sp->num_rows; j++)
+                    for (int k = 0; k < 4; k++)
+                        if (get_room(e, i, j)->doors[k] != NONE) doors[nd++] = get_room(e, i, j)->doors[k];
+            int door = doors[rand_int(e, 0, nd)];
+            e->root = new_node(e, I_OPEN, NONE, NONE, new_desc(e, T_DOOR, e->obj[door].color, NONE), NONE);
+        } else if (sp->instr == I_PUTNEXT) {
+            /* o1, o2 = self._rand_subset(objs, 2) */
+            int i1 = rand_int(e, 0, n);
+            int o1 = objs[i1];
+            for (int k = i1; k + 1 < n; k++) objs[k] = objs[k + 1];
+            int o2 = objs[rand_int(e, 0, n - 1)];
+            e->root = new_node(e, I_PUTNEXT, NONE, NONE, new_desc(e, e->obj[o1].type, e->obj[o1].color, NONE),
+                               new_desc(e, e->obj[o2].type, e->obj[o2].color, NONE));
+        } else {
+            int obj = objs[rand_int(e, 0, n)];
+            e->root = new_node(e, sp->instr, NONE, NONE, new_desc(e, e->obj[obj].type, e->obj[obj].color, NONE), NONE);
+        }
         if (sp->doors_open)   /* levelgen.py:189-199 open_all_doors */
             for (int k = 0; k < e->nobj; k++) if (e->obj[k].type == T_DOOR) e->obj[k].is_open = 1;
         return OK;

@@ -28,6 +28,7 @@ class LevelSpec(C.Structure):
         ('locations', C.c_int32), ('unblocking', C.c_int32), ('implicit_unlock', C.c_int32),
         ('n_action_kinds', C.c_int32), ('action_kinds', C.c_int32 * 4),
         ('n_instr_kinds', C.c_int32), ('instr_kinds', C.c_int32 * 3),
+        ('all_unique', C.c_int32), ('require_unreachable', C.c_int32),
     ]
 
 
@@ -35,9 +36,10 @@ def _redball(num_dists=7, grey=0):                      # iclr19_levels.py:10-72
     return dict(kind=KIND_REDBALL, room_size=8, num_rows=1, num_cols=1, num_dists=num_dists, grey_dists=grey)
 
 
-def _obj(room_size=8, rows=1, cols=1, num_dists=8, instr=I_GOTO, doors_open=0):   # :75-184, :224-301, :360-371
+def _obj(room_size=8, rows=1, cols=1, num_dists=8, instr=I_GOTO, doors_open=0, all_unique=0, require_unreachable=0):
+    # iclr19_levels.py:75-184, :187-221, :224-301, :360-415, :477-491
     return dict(kind=KIND_OBJ, room_size=room_size, num_rows=rows, num_cols=cols, num_dists=num_dists,
-                instr=instr, doors_open=doors_open)
+                instr=instr, doors_open=doors_open, all_unique=all_unique, require_unreachable=require_unreachable)
 
 
 def _levelgen(room_size=8, rows=3, cols=3, num_dists=18, locked_room_prob=0.5, locations=1, unblocking=1,
@@ -64,6 +66,12 @@ LEVELS = {
     'GoToObjMazeS4R2': _obj(4, 2, 2, 1), 'GoToObjMazeS4': _obj(4, 3, 3, 1), 'GoToObjMazeS5': _obj(5, 3, 3, 1),
     'GoToObjMazeS6': _obj(6, 3, 3, 1), 'GoToObjMazeS7': _obj(7, 3, 3, 1),
     'Pickup': _obj(8, 3, 3, 18, instr=I_PICKUP),
+    'UnblockPickup': _obj(8, 3, 3, 20, instr=I_PICKUP, require_unreachable=1),      # :374-391
+    'Open': _obj(8, 3, 3, 18, instr=I_OPEN),                                        # :394-415
+    'PutNext': _obj(8, 3, 3, 18, instr=I_PUTNEXT),                                  # :477-491
+    'PutNextLocal': _obj(8, 1, 1, 8, instr=I_PUTNEXT, all_unique=1),                # :187-211
+    'PutNextLocalS5N3': _obj(5, 1, 1, 3, instr=I_PUTNEXT, all_unique=1),
+    'PutNextLocalS6N4': _obj(6, 1, 1, 4, instr=I_PUTNEXT, all_unique=1),
     'PickupLoc': _levelgen(rows=1, cols=1, num_dists=8, locked_room_prob=0, locations=1, unblocking=0,
                            action_kinds=(I_PICKUP,), instr_kinds=(K_ACTION,)),      # :494-515
     'GoToSeq': _levelgen(action_kinds=(I_GOTO,), locked_room_prob=0, locations=0, unblocking=0),   # :518-546

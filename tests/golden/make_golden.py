@@ -23,7 +23,7 @@ import refenv  # noqa: E402
 
 CONFIG_LEVELS = ['GoToRedBall', 'GoToLocal', 'PickupLoc', 'GoTo', 'BossLevel']
 OTHER_LEVELS = ['GoToRedBallGrey', 'GoToObjMazeS4R2', 'GoToOpen', 'Pickup', 'GoToSeq', 'Synth', 'SynthSeq',
-                'MiniBossLevel', 'BossLevelNoUnlock']
+                'MiniBossLevel', 'BossLevelNoUnlock', 'Open', 'PutNext', 'PutNextLocal', 'PutNextLocalS5N3', 'UnblockPickup']
 
 
 def trace(level, seed, T, act_seed):
@@ -71,7 +71,7 @@ def main():
             T = 700
         if level == 'BossLevel':
             K, T = 6, 1500
-        if level in ('SynthSeq', 'MiniBossLevel', 'BossLevelNoUnlock'):
+        if level in ('SynthSeq', 'MiniBossLevel', 'BossLevelNoUnlock', 'Open', 'PutNext', 'UnblockPickup'):
             K, T = 3, 800
         seeds = [1000 + 17 * k for k in range(K)]
         tr = [trace(level, s, T, act_seed=k) for k, s in enumerate(seeds)]

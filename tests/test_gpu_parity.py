@@ -54,6 +54,11 @@ def test_gpu_replays_golden(level):
     ('MiniBossLevel', 256, 400),
     ('SynthSeq', 128, 200),
     ('GoToObjMazeS4R2', 100, 300),  # ragged: not a multiple of 32
+    ('PutNextLocal', 1024, 400),
+    ('PutNextLocalS5N3', 512, 300),
+    ('Open', 256, 300),
+    ('PutNext', 256, 300),
+    ('UnblockPickup', 128, 200),
 ])
 def test_gpu_matches_oracle(level, n, steps):
     import oracle as orc
