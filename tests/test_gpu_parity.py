@@ -69,7 +69,7 @@ def test_gpu_matches_oracle(level, n, steps):
     # config 1 uses the shared action stream RandomState(0).randint(0, 7, (T, N))
     eps = compare_pools(o, g, n, steps, act_seed=0, state=(n <= 512),
                         mission_a=lambda p, i: p.mission(i), mission_b=lambda p, i: p.mission(i))
-    assert eps > 0
+    assert eps > 0 or level in ('PutNext', 'UnblockPickup', 'Open')      # max_steps 576..1152: no episode may end in 300 steps
     assert g.env.counters()['errors'] == 0
 
 
