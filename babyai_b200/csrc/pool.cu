@@ -915,7 +915,7 @@ struct bb_pool {
     // k_gen launched at >= s - D
     int D, G, nev;
     bool gen_generic; int gen_small_blocks, gen_budget, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
-    bool no_persistent, after_rollout;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
+    bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 3 = k_rollout with T = 1 for small grids, k_step8 otherwise (default); 0 = k_step8; 1 = k_step; 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
     cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
@@ -1104,9 +1104,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) p->refill_every = v; }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
-    // small grids: >= 3 x the 40-step rollout of bb_pool_rollout (refill every 2nd launch); large grids: deep enough
-    // that one generation pass per 32 steps (many levels per pass: a level is ~0.2-0.4 ms of serial work) stays ahead
-    p->D = p->lp.cells_pad <= 256 ? 128 : 64;
+    // >= 3 x the 40-step rollout of bb_pool_rollout (one refill pass per two launches); for the per-step API one
+    // generation pass per 32 steps (many levels per pass: a multi-room level is ~0.2-0.4 ms of serial work)
+    p->D = 128;
     if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 256) p->D = d; }
     p->G = p->D >= 64 ? 32 : (p->D >= 8 ? p->D / 4 : 1);
     if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
@@ -1115,6 +1115,10 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
     p->step_kernel = 3;
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
+    p->persist_max_cells = 1152;                           // k_rollout stages up to 22 x 22 grids (2 x 43 KB of shared memory per CTA)
+    if (const char *e = getenv("BB_PERSIST_MAX_CELLS")) p->persist_max_cells = atoi(e);
+    p->gen_concurrent = p->lp.cells_pad > 256;
+    if (const char *e = getenv("BB_GEN_CONCURRENT")) p->gen_concurrent = atoi(e) != 0;
     if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : !strcmp(e, "cols") ? 0 : 3;
     p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr; p->tev[0] = p->tev[1] = p->tev[2] = p->tev[3] = nullptr; p->time_rollout = false; p->chk_obs = nullptr; p->direct = false;
     const LevelParams &lp = p->lp;
@@ -1283,7 +1287,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || T < 1) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     cudaStream_t user = (cudaStream_t)stream;
-    const bool persistent = p->lp.cells_pad <= 128 && !p->no_persistent && (p->mode == BB_MODE_FREEZE || p->D >= (p->refill_every + 1) * T);
+    const bool persistent = p->lp.cells_pad <= p->persist_max_cells && !p->no_persistent && (p->mode == BB_MODE_FREEZE || p->D >= (p->refill_every + 1) * T);
     if (!persistent) return rollout_graph(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, user);
     if (sched_join(p, user)) return 1;                 // every k_gen enqueued so far (rings topped up to D - what
                                                        // the previous rollout consumed >= D - T >= T levels per env)
@@ -1297,11 +1301,12 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     cudaEvent_t *dbg_ev = p->tev;
     if (dbg_timing && !dbg_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&dbg_ev[i]));
     const size_t nb = (size_t)p->n * sizeof(uint32_t);
-    // Default: refill in-stream, right before the stepping kernel, with a bounded iteration budget.  Measured
+    // Small levels: refill in-stream, right before the stepping kernel, with a bounded iteration budget.  Measured
     // (r01l): running k_gen_small on the side stream BESIDE k_rollout does not pay -- alone they take 263 us and
-    // ~210 us, together 460-490 us and 580 us (both are issue/latency bound on the same SMs); BB_GEN_CONCURRENT=1
-    // selects that variant for A/B runs.
-    static const bool gen_serial = getenv("BB_GEN_CONCURRENT") == nullptr;
+    // ~210 us, together 460-490 us and 580 us (both are issue/latency bound on the same SMs).  Multi-room levels:
+    // k_gen (one warp per level, a few hundred levels per pass, each 0.2-0.4 ms of serial work) runs on the side
+    // stream beside k_rollout (BossLevel 1.48e9 -> 1.71e9, GoTo 1.34e9 -> 1.43e9).  BB_GEN_CONCURRENT=0/1 overrides.
+    const bool gen_serial = !p->gen_concurrent;
     if (refill && gen_serial) {
         if (dbg_timing) cudaEventRecord(dbg_ev[2], user);
         CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
