@@ -129,13 +129,14 @@ def test_reseed_and_reset_like_batch_evaluate():
         assert np.array_equal(oo, go) and np.array_equal(orr, gr) and np.array_equal(od, gd)
 
 
-def test_rollout_graph_equals_stepwise():
+@pytest.mark.parametrize('level,n,T', [('GoToLocal', 4096, 24), ('BossLevel', 512, 16), ('GoToObjMazeS4R2', 300, 40)])
+def test_rollout_graph_equals_stepwise(level, n, T):
+    """bb_pool_rollout (persistent kernel, 8x8 and 22x22 staging, ragged last warp) == T x bb_pool_step."""
     import torch
     from babyai_b200 import BabyAIVecEnv
-    n, T = 4096, 24
     seeds = np.arange(n, dtype=np.uint64) + 77
-    a = BabyAIVecEnv('GoToLocal', n, seeds=seeds)
-    b = BabyAIVecEnv('GoToLocal', n, seeds=seeds)
+    a = BabyAIVecEnv(level, n, seeds=seeds)
+    b = BabyAIVecEnv(level, n, seeds=seeds)
     acts = torch.randint(0, 7, (T, n), device='cuda', dtype=torch.int8)
     a.reset(); b.reset()
     obs = torch.zeros((T, n, 7, 7, 3), dtype=torch.uint8, device='cuda')
