@@ -43,14 +43,14 @@ def replay_golden(level, make_pool, get_mission):
     return int(g['done'].sum())
 
 
-def compare_pools(a, b, n, steps, act_seed=0, mission_a=None, mission_b=None, state=True, check_draws=False):
-    """Drive two pools with the same uniform random actions; everything must be identical."""
+def compare_pools(a, b, n, steps, act_seed=0, mission_a=None, mission_b=None, state=True, check_draws=False, action_p=None):
+    """Drive two pools with the same random actions (uniform, or distribution action_p); everything must be identical."""
     rng = np.random.RandomState(act_seed)
     oa, ob = np.asarray(a.reset()).copy(), np.asarray(b.reset()).copy()
     assert np.array_equal(oa, ob), 'reset obs'
     episodes = 0
     for t in range(steps):
-        act = rng.randint(0, 7, n).astype(np.int8)
+        act = (rng.randint(0, 7, n) if action_p is None else rng.choice(7, size=n, p=action_p)).astype(np.int8)
         oa, ra, da = [np.asarray(x).copy() for x in a.step(act)]
         ob, rb, db = [np.asarray(x).copy() for x in b.step(act)]
         assert np.array_equal(da.astype(bool), db.astype(bool)), (t, 'done')

@@ -73,6 +73,33 @@ def test_gpu_matches_oracle(level, n, steps):
     assert g.env.counters()['errors'] == 0
 
 
+@pytest.mark.parametrize('level,n', [('PickupLoc', 1024), ('PutNextLocal', 1024), ('MiniBossLevel', 256), ('BossLevel', 256)])
+def test_gpu_matches_oracle_interaction_heavy_actions(level, n):
+    """Pickup / drop / toggle heavy action mix (stale and refreshed obj_poss snapshots, opened boxes, toggled doors)."""
+    import oracle as orc
+    seeds = np.arange(n, dtype=np.uint64) * 3 + 77
+    p = [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02]
+    g = GpuPool(level, n, seeds)
+    compare_pools(orc.OraclePool(level, n, seeds), g, n, 400, act_seed=5, action_p=p, state=(n <= 256),
+                  mission_a=lambda q, i: q.mission(i), mission_b=lambda q, i: q.mission(i))
+    assert g.env.counters()['errors'] == 0
+
+
+def test_preprocess_obss_adapter():
+    """Device-resident stand-in for ObssPreprocessor (utils/format.py:100-119): float image + long token tensors."""
+    import torch
+    from babyai_b200 import BabyAIVecEnv, preprocess_obss, VOCAB
+    env = BabyAIVecEnv('PickupLoc', 128, seeds=np.arange(128, dtype=np.uint64))
+    env.reset()
+    fn = preprocess_obss(env)
+    out = fn(None, device='cuda')
+    assert out.image.shape == (128, 7, 7, 3) and out.image.dtype == torch.float32 and out.image.is_cuda
+    assert out.instr.dtype == torch.long and out.instr.shape[0] == 128 and int(out.instr.max()) < len(VOCAB)
+    assert fn.vocab['pick'] == VOCAB.index('pick')
+    from babyai_b200 import detokenize
+    assert [detokenize(row.tolist()) for row in out.instr.cpu()] == env.missions()
+
+
 def test_int64_actions_and_counters():
     import oracle as orc
     n = 96

@@ -31,6 +31,17 @@ def test_emu_matches_oracle_random_actions(level):
                   mission_a=lambda p, i: p.mission(i), mission_b=lambda p, i: detokenize(p.tokens(i)))
 
 
+@pytest.mark.parametrize('level', ['PickupLoc', 'PutNextLocal', 'PutNextLocalS5N3', 'Synth', 'MiniBossLevel', 'Open', 'BossLevel'])
+def test_emu_matches_oracle_interaction_heavy_actions(level):
+    """Actions biased towards forward / pickup / drop / toggle so that objects are carried around, boxes opened,
+    doors toggled and the obj_poss snapshots go stale and get refreshed (verifier.py:195-202, levelgen.py:53-54)."""
+    n = 12
+    seeds = np.arange(n, dtype=np.uint64) * 3 + 77
+    p = [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02]
+    compare_pools(orc.OraclePool(level, n, seeds), _emu(level, n, seeds), n, 400, act_seed=5, action_p=p,
+                  mission_a=lambda q, i: q.mission(i), mission_b=lambda q, i: detokenize(q.tokens(i)))
+
+
 def test_freeze_mode_matches_oracle_without_autoreset():
     """ManyEnvs flavour (evaluate.py:72-78): finished envs stop and replay their last result."""
     level, n = 'GoToLocal', 16
