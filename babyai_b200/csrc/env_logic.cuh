@@ -361,6 +361,24 @@ BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g)
     int i = g.rng.randint(0, lp.num_cols);
     int j = g.rng.randint(0, lp.num_rows);
     int room = j * lp.num_cols + i;
+    {   // KNOWN DIVERGENCE: the reference's loop below never returns when no empty cell of the
+        // room has an empty or wall cell in front of it for any heading (3x3 rooms packed with distractors and
+        // doors: MiniBossLevel seed 698, 57th level).  The reference hangs; here the level is rejected like any
+        // other failed rejection sampling and generation starts over.  Levels the reference CAN generate are unaffected.
+        const int S = lp.room_size;
+        const int tx = (room % lp.num_cols) * (S - 1), ty = (room / lp.num_cols) * (S - 1);
+        const uint32_t rmask = ((1u << (S - 2)) - 1u) << (tx + 1);
+        bool any = false;
+        for (int y = ty + 1; y < ty + S - 1; y++) {
+            const uint32_t empty = ~g.m->occ[y] & rmask;
+            // cells that may be in front of the agent: empty, or wall (a door is neither)
+            const uint32_t f0 = ~g.m->occ[y] | (lp.wall_rows[y] & ~g.m->doorcell[y]);
+            const uint32_t fu = ~g.m->occ[y - 1] | (lp.wall_rows[y - 1] & ~g.m->doorcell[y - 1]);
+            const uint32_t fd = ~g.m->occ[y + 1] | (lp.wall_rows[y + 1] & ~g.m->doorcell[y + 1]);
+            if (empty & ((f0 << 1) | (f0 >> 1) | fu | fd)) any = true;
+        }
+        if (!any) return GEN_RECURSION;
+    }
     for (;;) {
         int x, y;
         g.agent_placed = false;          // MiniGridEnv.place_agent: agent_pos = None while sampling
@@ -1432,9 +1450,65 @@ BB_HD void col_encode(uint32_t lo, uint32_t hi, uint32_t cv, uint32_t out[6])
     encode4(hi, out[3], out[4], out[5]);
 }
 
+// 49 masked cells (R[2 vi] = vj 0..3, R[2 vi + 1] = vj 4..6 and a zero byte) -> 37 observation words:
+// the cell stream (index 7 vi + vj) four cells at a time, 3 output words each
+BB_HD void encode_view(const uint32_t R[14], uint32_t w[OBS_WORDS])
+{
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+        // stream bytes 4k .. 4k+3 live in at most two consecutive registers of R (7-byte records: 4 + 3)
+        uint32_t sel = 0; int ra = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = 4 * k + i;
+            const int vi = q / 7, vj = q % 7;
+            const int r = 2 * vi + (vj >= 4 ? 1 : 0), byte = vj >= 4 ? vj - 4 : vj;
+            if (q >= 49) { sel |= 3u << (4 * i); continue; }          // byte 3 of R[13] is zero
+            if (ra < 0) ra = r;
+            sel |= (uint32_t)(r == ra ? byte : 4 + byte) << (4 * i);
+        }
+        const uint32_t c = byte_perm(R[ra], ra + 1 < 14 ? R[ra + 1] : 0u, sel);
+        uint32_t o0, o1, o2;
+        encode4(c, o0, o1, o2);
+        w[3 * k] = o0;
+        if (k < 12) { w[3 * k + 1] = o1; w[3 * k + 2] = o2; }
+    }
+}
+
+// Single-room levels (num_rows = num_cols = 1): the only opaque cells are the outer walls (no doors; keys, balls
+// and boxes let light through, minigrid.py:146-148), so process_vis lights exactly the view cells that lie inside
+// the grid: the agent's row floods sideways up to and including the side walls, every interior row above it does
+// the same, the far wall row is lit from below (corners through the diagonal rule) and nothing passes it.
+// Visible <=> in bounds: no see-through flags, no transposes, no propagation -- the column windows with
+// out-of-grid cells zeroed.  (test_room_observation_equals_generic compares it with observe_generic for every pose.)
+template <class M>
+BB_HD void observe_room(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+{
+    const ViewGeom v = view_geom(lp, ax, ay, dir);
+    // cells from the agent to the wall it faces (inclusive): view depths vj >= 6 - dist are inside the grid
+    const int dist = dir == 3 ? ay : dir == 1 ? lp.H - 1 - ay : dir == 0 ? lp.W - 1 - ax : ax;
+    const uint32_t dm = dist >= 6 ? 0x7Fu : (0x7Fu << (6 - dist)) & 0x7Fu;
+    const uint32_t mlo = expand4(dm), mhi = expand4(dm >> 4) & 0x00FFFFFFu;
+    uint32_t R[14];
+#pragma unroll
+    for (int vi = 0; vi < 7; vi++) {
+        const int row = v.c_row + v.rstep * (vi - 3);
+        const bool rok = row >= 0 && row < v.nrows;
+        const int off = v.off0 + vi * v.dstep;
+        const uint32_t w0 = (rok && v.ok0) ? mem.word_at(off) : 0u;
+        const uint32_t w1 = (rok && v.ok1) ? mem.word_at(off + 4) : 0u;
+        const uint32_t w2 = (rok && v.ok2) ? mem.word_at(off + 8) : 0u;
+        const uint32_t a = funnel_r(w0, w1, v.sh), b = funnel_r(w1, w2, v.sh);
+        R[2 * vi] = byte_perm(a, b, v.sel_lo) & mlo;
+        R[2 * vi + 1] = byte_perm(a, b, v.sel_hi) & mhi;
+    }
+    R[7] = (R[7] & 0xFF00FFFFu) | ((uint32_t)carry_cell << 16);        // the agent's own cell shows what it carries
+    encode_view(R, w);
+}
+
 // Writes the 147 observation bytes as 37 little-endian words (last byte 0): one lane does all columns.
 template <class M>
-BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+BB_HD void observe_generic(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
 {
     const ViewGeom v = view_geom(lp, ax, ay, dir);
     uint32_t R[14];                              // R[2 vi] = cells vj 0..3, R[2 vi + 1] = cells vj 4..6 (+1 unused byte)
@@ -1464,26 +1538,14 @@ BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir,
         R[2 * vi] &= expand4(cv);
         R[2 * vi + 1] &= expand4(cv >> 4);       // also clears the unused fourth byte
     }
-    // cell stream (49 bytes, index 7 vi + vj) four cells at a time -> 3 output words each
-#pragma unroll
-    for (int k = 0; k < 13; k++) {
-        // stream bytes 4k .. 4k+3 live in at most two consecutive registers of R (7-byte records: 4 + 3)
-        uint32_t sel = 0; int ra = -1;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int q = 4 * k + i;
-            const int vi = q / 7, vj = q % 7;
-            const int r = 2 * vi + (vj >= 4 ? 1 : 0), byte = vj >= 4 ? vj - 4 : vj;
-            if (q >= 49) { sel |= 3u << (4 * i); continue; }          // byte 3 of R[13] is zero
-            if (ra < 0) ra = r;
-            sel |= (uint32_t)(r == ra ? byte : 4 + byte) << (4 * i);
-        }
-        const uint32_t c = byte_perm(R[ra], ra + 1 < 14 ? R[ra + 1] : 0u, sel);
-        uint32_t o0, o1, o2;
-        encode4(c, o0, o1, o2);
-        w[3 * k] = o0;
-        if (k < 12) { w[3 * k + 1] = o1; w[3 * k + 2] = o2; }
-    }
+    encode_view(R, w);
+}
+
+template <class M>
+BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+{
+    if (lp.num_rows == 1 && lp.num_cols == 1) observe_room(lp, mem, ax, ay, dir, carry_cell, w);
+    else observe_generic(lp, mem, ax, ay, dir, carry_cell, w);
 }
 
 // The same observation assembled from per-column pieces exactly as the 8-lanes-per-env kernel does

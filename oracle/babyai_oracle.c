@@ -336,6 +336,23 @@ static int place_agent(Env *e)
     int i = rand_int(e, 0, e->sp.num_cols);
     int j = rand_int(e, 0, e->sp.num_rows);
     Room *r = get_room(e, i, j);
+    {   /* KNOWN DIVERGENCE: the reference's loop below (roomgrid.py place_agent, `while True`) never returns when no
+         * empty cell of the room has an empty or wall cell in front of it for any heading -- it happens with 3x3
+         * rooms packed with distractors and doors (MiniBossLevel, seed 698, 57th level; reproduced with the
+         * reference itself: tests/test_oracle_vs_reference.py::test_reference_place_agent_hang_is_rejected).
+         * The reference hangs there; the oracle (and the kernels) reject the level like any other failed rejection
+         * sampling.  Levels the reference can generate are unaffected. */
+        int any = 0;
+        for (int y = r->top_y + 1; y < r->top_y + r->size - 1 && !any; y++)
+            for (int x = r->top_x + 1; x < r->top_x + r->size - 1 && !any; x++) {
+                if (cell_get(e, x, y) != NONE) continue;
+                for (int d = 0; d < 4; d++) {
+                    int fc = cell_get(e, x + DIR_X[d], y + DIR_Y[d]);
+                    if (fc == NONE || fc == WALL) any = 1;
+                }
+            }
+        if (!any) return RECURSION;
+    }
     for (;;) {
         /* MiniGridEnv.place_agent: agent_pos = None while sampling */
         int x, y;

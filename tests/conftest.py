@@ -16,6 +16,11 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import refenv
+    # a device kernel that never returns cannot be interrupted from Python: bound every GPU test with a watchdog
+    # thread that ends the process (a hung box is a lost GPU visit)
+    for it in items:
+        if 'gpu' in it.keywords and it.get_closest_marker('timeout') is None:
+            it.add_marker(pytest.mark.timeout(240, method='thread'))
     if not refenv.available():
         skip = pytest.mark.skip(reason='/root/reference not present (GPU box)')
         for it in items:

@@ -154,6 +154,28 @@ void he_get_state(HPool *p, int e, uint8_t *grid, int32_t *info)
     info[4] = s.hot.step_count; info[5] = s.hot.max_steps;
     info[6] = (int32_t)(p->rng[e].draws & 0x7FFFFFFF); info[7] = (int32_t)p->attempts[e];
 }
+// single-room levels: observe_room == observe_generic == the literal loops, for every agent pose on env e's live grid
+int he_check_room_obs(HPool *p, int e)
+{
+    Slot &s = p->live[e];
+    const LevelParams &lp = p->lp;
+    if (!(lp.num_rows == 1 && lp.num_cols == 1)) return -1;
+    GlobalMem mem(lp, s.grid.data(), &s.obj, &s.ins);
+    int checked = 0;
+    for (int y = 1; y < lp.H - 1; y++)
+        for (int x = 1; x < lp.W - 1; x++)
+            for (int d = 0; d < 4; d++)
+                for (int carry = 0; carry < 2; carry++) {
+                    const int cc = carry ? (T_KEY | (3 << 3)) : CELL_EMPTY;
+                    uint32_t a[OBS_WORDS], b[OBS_WORDS]; uint8_t lit[OBS_BYTES];
+                    observe_room(lp, mem, x, y, d, cc, a);
+                    observe_generic(lp, mem, x, y, d, cc, b);
+                    observe_simple(lp, s.grid.data(), x, y, d, cc, lit);
+                    if (memcmp(a, b, OBS_BYTES) != 0 || memcmp(a, lit, OBS_BYTES) != 0) return -2 - checked;
+                    checked++;
+                }
+    return checked;
+}
 int he_width(HPool *p) { return p->lp.W; }
 int he_height(HPool *p) { return p->lp.H; }
 

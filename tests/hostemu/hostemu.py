@@ -40,6 +40,7 @@ def lib():
         L.he_step.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.he_tokens.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.he_get_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.he_check_room_obs.argtypes = [C.c_void_p, C.c_int]
         L.he_width.argtypes = [C.c_void_p]
         L.he_height.argtypes = [C.c_void_p]
         L.he_vis_rows.argtypes = [C.c_void_p, C.c_void_p]

@@ -42,6 +42,41 @@ def test_emu_matches_oracle_interaction_heavy_actions(level):
                   mission_a=lambda q, i: q.mission(i), mission_b=lambda q, i: detokenize(q.tokens(i)))
 
 
+@pytest.mark.parametrize('level', ['GoToRedBallGrey', 'GoToLocal', 'GoToObjS4', 'GoToLocalS5N2', 'PickupLoc', 'PutNextLocal'])
+def test_room_observation_equals_generic(level):
+    """Single-room levels use the closed-form visibility (visible <=> inside the grid): it must equal the general
+    process_vis path (minigrid.py:1211-1245 restated in vis_rows) and the literal loops for every pose on real levels."""
+    n = 24
+    e = _emu(level, n, np.arange(n, dtype=np.uint64) + 900)
+    e.reset()
+    for i in range(n):
+        c = e.L.he_check_room_obs(e.h, i)
+        interior = (e.width - 2) * (e.height - 2)
+        assert c == interior * 4 * 2, (level, i, c)
+
+
+@pytest.mark.timeout(120)
+def test_unsatisfiable_agent_room_is_rejected_not_spun_on():
+    """MiniBossLevel seed 698, 57th level: RoomGrid.place_agent's `while True` can never succeed in the room it
+    drew (the reference hangs there, tests/test_oracle_vs_reference.py); generation must reject and move on."""
+    seeds = np.array([698], dtype=np.uint64)
+    e, o = _emu('MiniBossLevel', 1, seeds), orc.OraclePool('MiniBossLevel', 1, seeds)
+    for k in range(80):
+        assert np.array_equal(e.reset(), np.asarray(o.reset())), k
+        assert detokenize(e.tokens(0)) == o.mission(0)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('level', ['MiniBossLevel', 'GoToObjMazeS4', 'SynthS5R2', 'BossLevel', 'GoToLocal', 'PutNextLocal'])
+def test_deep_generation_matches_oracle(level):
+    """Generation far down each env's random stream (the GPU pool pre-generates 128 levels per env)."""
+    n = 48
+    seeds = np.arange(n, dtype=np.uint64) * 7 + 5000
+    e, o = _emu(level, n, seeds), orc.OraclePool(level, n, seeds)
+    for k in range(400):
+        assert np.array_equal(e.reset(), np.asarray(o.reset())), k
+
+
 def test_freeze_mode_matches_oracle_without_autoreset():
     """ManyEnvs flavour (evaluate.py:72-78): finished envs stop and replay their last result."""
     level, n = 'GoToLocal', 16

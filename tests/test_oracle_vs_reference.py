@@ -38,3 +38,54 @@ def test_reference_level_test_on_shim():
 def test_bot_solves_config_levels():
     import selfcheck_bot
     assert selfcheck_bot.run(CONFIG_LEVELS, 3, 'philox')
+
+
+def test_reference_place_agent_hang_is_rejected():
+    """RoomGrid.place_agent loops `while True` until the cell in front of the agent is empty or a wall
+    (gym_minigrid/roomgrid.py place_agent).  MiniBossLevel, seed 698: the 57th level picks a 3x3 room whose two empty
+    cells face objects / doors in all four headings, so the reference never returns.  The oracle (and the kernels)
+    reject that level instead: same levels up to there, then the oracle carries on."""
+    import signal
+    import numpy as np
+    import oracle as orc
+    import refenv
+    env = refenv.make_env('MiniBossLevel', 698)
+    pool = orc.OraclePool('MiniBossLevel', 1, np.array([698], dtype=np.uint64))
+    for k in range(56):
+        ob = env.reset()
+        oo = pool.reset()
+        assert np.array_equal(np.asarray(oo)[0].reshape(7, 7, 3), ob['image']), k
+        assert pool.mission(0) == ob['mission']
+
+    class Hung(Exception):
+        pass
+
+    def on_alarm(*a):
+        raise Hung()
+    old = signal.signal(signal.SIGALRM, on_alarm)
+    signal.alarm(3)
+    try:
+        with pytest.raises(Hung):
+            env.reset()
+    finally:
+        signal.alarm(0)
+        signal.signal(signal.SIGALRM, old)
+    # the room the reference is stuck in: no empty cell with an empty / wall cell in front of it
+    e = env.unwrapped
+    stuck = []
+    for j in range(e.num_rows):
+        for i in range(e.num_cols):
+            room = e.get_room(i, j)
+            ok = False
+            for y in range(room.top[1] + 1, room.top[1] + room.size[1] - 1):
+                for x in range(room.top[0] + 1, room.top[0] + room.size[0] - 1):
+                    if e.grid.get(x, y) is not None:
+                        continue
+                    for dx, dy in ((1, 0), (0, 1), (-1, 0), (0, -1)):
+                        c = e.grid.get(x + dx, y + dy)
+                        ok = ok or c is None or c.type == 'wall'
+            if not ok:
+                stuck.append((i, j))
+    assert stuck, 'expected a room without any admissible agent pose'
+    pool.reset()        # returns: the oracle rejected the unsatisfiable level
+    assert pool.state(0)[1]['attempts'] >= 58
