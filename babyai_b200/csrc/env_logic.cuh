@@ -864,8 +864,6 @@ struct SmallLevel {             // everything emit_small_level() needs
     uint32_t d_mask;
 };
 
-enum : int { PH_START = 0, PH_AGENT, PH_OBJ, PH_CHECK, PH_PICK, PH_DESC, PH_DONE };
-
 BB_HD int sm_obj_x(uint64_t poss, int k) { return (int)((poss >> (6 * k)) & 7u); }
 BB_HD int sm_obj_y(uint64_t poss, int k) { return (int)((poss >> (6 * k + 3)) & 7u); }
 BB_HD int sm_obj_tc(uint64_t tcs, int k) { return (int)((tcs >> (6 * k)) & 63u); }
@@ -890,215 +888,288 @@ BB_HD uint32_t sm_match(const SmallLevel &L, int type, int color, int loc)
     return m;
 }
 
-// Generator state of one lane; small_gen_step() performs ONE iteration of the flat loop.
-struct SmallGen {
-    RngScalar rng;
+// ---- draw source of one lane: a ring of the stream's next 64 draws ---------------------------------------
+// The generator below never asks for randomness through a branchy "refill if needed" path: the draws of the
+// lane's stream sit in a 64-word ring (16 Philox blocks; word d & 63 holds draw d) that is topped up for ALL lanes
+// of a warp together (k_gen_small: converged Philox, the expensive part of generation), and a draw is one indexed
+// read.  Memory with dynamic indexing: shared memory on the device (stride `ws` words between a lane's
+// consecutive entries), a plain array in the host build.
+constexpr int RING_BLOCKS = 16, RING_WORDS = 4 * RING_BLOCKS;
+struct DrawRing {
+    uint32_t *w; int ws;
+    uint32_t k0, k1;
+    uint64_t draws;               // index of the next draw of the stream
+    uint64_t gen;                 // blocks gen-16 .. gen-1 are in the ring
+
+    BB_HD void init(uint32_t *w_, int ws_, uint64_t seed, uint64_t d)
+    {
+        w = w_; ws = ws_; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); draws = d; gen = d >> 2;
+    }
+    BB_HD int avail() const { return (int)((int64_t)(gen * 4ull) - (int64_t)draws); }     // draws ready to be read
+    // the slot of block `gen` holds block gen-16: free once every draw of that block is consumed
+    BB_HD bool room() const { return gen < (draws >> 2) + (uint64_t)RING_BLOCKS; }
+    BB_HD void gen_block()
+    {
+        RngScalar r; r.k0 = k0; r.k1 = k1;
+        r.refill(gen);
+        const int s = (int)(gen & (uint64_t)(RING_BLOCKS - 1)) * 4;
+        w[s * ws] = r.b0; w[(s + 1) * ws] = r.b1; w[(s + 2) * ws] = r.b2; w[(s + 3) * ws] = r.b3;
+        gen++;
+    }
+    BB_HD void fill() { while (room()) gen_block(); }                                      // scalar top-up (host, rare device path)
+    BB_HD uint32_t peek(int j) const { return w[(int)((draws + (uint64_t)j) & (uint64_t)(RING_WORDS - 1)) * ws]; }   // needs avail() > j
+    BB_HD void advance(int n) { draws += (uint64_t)n; }
+};
+constexpr int RING_LOW = 8;       // every generator step below reads at most 5 draws: top up when fewer than 8 are ready
+
+// ---- one ATTEMPT at a small level, in phases that a warp runs in lock-step ---------------------------------
+//   small_attempt_begin     RoomGrid._gen_grid of the one room
+//   small_place_try         one placement try of whatever the lane is placing (agent or next object): the
+//                           bulk of the work, one shared code path
+//   small_flood_sweep/_ok   check_objs_reachable as a bitboard flood fill
+//   small_pick / small_desc_try   the instruction's object descriptor
+// generate_small() below drives them for one lane (host build); k_gen_small drives them for 32 lanes with
+// warp-level loops: every lane of the warp is in the same phase, lanes that are done with a phase wait.
+enum : int { ST_OBJ = 0, ST_AGENT, ST_PLACED, ST_FAIL, ST_IDLE };
+struct SmallAttempt {
     SmallLevel L;
     uint64_t occ, fill;
-    int phase, tries, k, attempts, cur_tc;
+    int stage, k, tries, cur_tc;
     bool agent_placed;
 };
 
-BB_HD void small_gen_begin(const LevelParams &lp, SmallGen &g)
+BB_HD void small_attempt_begin(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
 {
     const bool levelgen = lp.kind == KIND_LEVELGEN;
-    g.occ = 0; g.fill = 0; g.phase = PH_START; g.tries = 0; g.k = 0; g.attempts = 0; g.cur_tc = 0; g.agent_placed = true;
-    g.L.poss = 0; g.L.tcs = 0; g.L.nobj = 0; g.L.ax = g.L.ay = g.L.adir = 0;
-    g.L.leaf_kind = lp.kind == KIND_OBJ ? lp.instr : (levelgen ? lp.action_kinds[0] : I_GOTO);
-    g.L.d_type = ANY_TYPE; g.L.d_color = ANY; g.L.d_loc = LOC_NONE; g.L.d_mask = 0;
+    const int S = lp.room_size;
+    a.occ = lp.wall64; a.fill = 0; a.k = 0; a.tries = 0; a.cur_tc = 0;
+    a.L.poss = 0; a.L.tcs = 0; a.L.nobj = 0;
+    a.L.ax = S / 2; a.L.ay = S / 2; a.L.adir = 0; a.agent_placed = true;        // RoomGrid._gen_grid: agent in the middle, facing right
+    a.L.leaf_kind = lp.kind == KIND_OBJ ? lp.instr : (levelgen ? lp.action_kinds[0] : I_GOTO);
+    a.L.d_type = ANY_TYPE; a.L.d_color = ANY; a.L.d_loc = LOC_NONE; a.L.d_mask = 0;
+    if (levelgen) { ds.advance(1); a.stage = lp.num_dists > 0 ? ST_OBJ : ST_AGENT; }   // `_rand_float(0,1) < 0`: one draw; distractors first
+    else a.stage = ST_AGENT;                                                             // iclr19 levels: agent first
 }
 
-// Draw window of a lane: the eight 32-bit words of Philox blocks blk and blk + 1, kept in memory that can be
-// indexed dynamically (shared memory on the device, stride ws words between consecutive entries).  One iteration
-// of the generator consumes at most four draws, so after win_ensure() every draw it needs is a plain indexed read.
-BB_HD void win_ensure(RngScalar &r, uint32_t *win, int ws)
+// RoomGrid.place_agent -> MiniGridEnv.place_agent tries / add_object, add_distractors: one placement try
+BB_HD void small_place_try(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
 {
-    const uint64_t nb = r.draws >> 2;
-    if (nb == r.blk) return;
-    if (nb == r.blk + 1 && r.blk != ~0ull) {       // slide: block blk + 1 becomes the low half
-#pragma unroll
-        for (int j = 0; j < 4; j++) win[j * ws] = win[(4 + j) * ws];
+    const int S = lp.room_size;
+    const bool levelgen = lp.kind == KIND_LEVELGEN;
+    const int nplace = lp.num_dists + (lp.kind == KIND_REDBALL ? 1 : 0);     // objects placed per attempt
+    SmallLevel &L = a.L;
+    if (a.tries > 1000) { a.stage = ST_FAIL; return; }                       // place_obj: RecursionError
+    const bool isobj = a.stage == ST_OBJ;
+    const bool fixed = lp.kind == KIND_REDBALL && a.k == 0;                  // the red ball: no colour / type draws
+    int used = 0;
+    if (isobj && a.tries == 0) {
+        if (fixed) a.cur_tc = T_BALL | (C_RED << 3);
+        else {
+            const int color = color_by_name_rank((int)mulhi32(ds.peek(0), 6u));
+            const int t = (int)mulhi32(ds.peek(1), 3u);
+            a.cur_tc = (t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX) | (color << 3);
+            used = 2;
+        }
+    }
+    a.tries++;
+    const int x = (int)mulhi32(ds.peek(used), (uint32_t)S), y = (int)mulhi32(ds.peek(used + 1), (uint32_t)S);
+    used += 2;
+    bool ok = !((a.occ >> (8 * y + x)) & 1u);
+    if (isobj) ok = ok && !(a.agent_placed && x == L.ax && y == L.ay) && (iabs(L.ax - x) + iabs(L.ay - y) >= 2);   // reject_next_to
+    if (!ok) { ds.advance(used); return; }
+    a.tries = 0;
+    if (isobj) {
+        a.occ |= 1ull << (8 * y + x);
+        L.poss |= (uint64_t)(x | (y << 3)) << (6 * a.k);
+        L.tcs |= (uint64_t)a.cur_tc << (6 * a.k);
+        a.k++; L.nobj = a.k;
+        if (a.k == nplace) {
+            if (lp.kind == KIND_REDBALL && lp.grey_dists)                  // GoToRedBallGrey: distractors turn grey
+                for (int q = 1; q < a.k; q++) L.tcs = (L.tcs & ~(56ull << (6 * q))) | ((uint64_t)(C_GREY << 3) << (6 * q));
+            if (levelgen) { a.stage = ST_AGENT; a.agent_placed = false; }   // MiniGridEnv.place_agent: agent_pos = None
+            else a.stage = ST_PLACED;
+        }
     } else {
-        r.refill(nb);
-        win[0] = r.b0; win[ws] = r.b1; win[2 * ws] = r.b2; win[3 * ws] = r.b3;
+        L.ax = x; L.ay = y; a.agent_placed = true;
+        L.adir = (int)mulhi32(ds.peek(used), 4u);
+        used++;
+        const int fb = 8 * (y + dir_dy(L.adir)) + x + dir_dx(L.adir);
+        const bool front_ok = !((a.occ >> fb) & 1u) || ((lp.wall64 >> fb) & 1u);
+        if (front_ok) a.stage = (!levelgen && nplace > 0) ? ST_OBJ : ST_PLACED;
     }
-    r.refill(nb + 1);
-    win[4 * ws] = r.b0; win[5 * ws] = r.b1; win[6 * ws] = r.b2; win[7 * ws] = r.b3;
-    r.blk = nb;
+    ds.advance(used);
 }
 
-// One iteration of the flat generator loop.  Agent and object placement share one code path (they are ~95 %
-// of the iterations), draws are indexed reads from the lane's window: lanes of a warp stay converged.
-BB_HD void small_gen_step(const LevelParams &lp, SmallGen &g, uint32_t *win, int ws)
+// check_objs_reachable: the fill starts on the agent; two dilations per call; returns whether anything changed
+BB_HD void small_flood_begin(SmallAttempt &a) { a.fill = 1ull << (8 * a.L.ay + a.L.ax); }
+BB_HD bool small_flood_sweep(SmallAttempt &a)
 {
-    const int S = lp.room_size, n = lp.num_dists;
-    const bool levelgen = lp.kind == KIND_LEVELGEN;
-    const int nplace = n + (lp.kind == KIND_REDBALL ? 1 : 0);   // objects placed per attempt
-    SmallLevel &L = g.L;
-    win_ensure(g.rng, win, ws);
-    const int off = (int)(g.rng.draws & 3u);
-#define BB_PEEK(j) win[(off + (j)) * ws]
-    const int ph = g.phase;
-    if (ph == PH_AGENT || ph == PH_OBJ) {
-        // RoomGrid.place_agent -> MiniGridEnv.place_agent tries / add_object, add_distractors: one placement try
-        if (g.tries > 1000) { g.phase = PH_START; return; }
-        const bool isobj = ph == PH_OBJ;
-        const bool fixed = lp.kind == KIND_REDBALL && g.k == 0;            // the red ball: no colour / type draws
-        int used = 0;
-        if (isobj && g.tries == 0) {
-            if (fixed) g.cur_tc = T_BALL | (C_RED << 3);
-            else {
-                const int color = color_by_name_rank((int)mulhi32(BB_PEEK(0), 6u));
-                const int t = (int)mulhi32(BB_PEEK(1), 3u);
-                g.cur_tc = (t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX) | (color << 3);
-                used = 2;
-            }
-        }
-        g.tries++;
-        const int x = (int)mulhi32(BB_PEEK(used), (uint32_t)S), y = (int)mulhi32(BB_PEEK(used + 1), (uint32_t)S);
-        used += 2;
-        bool ok = !((g.occ >> (8 * y + x)) & 1u);
-        if (isobj) ok = ok && !(g.agent_placed && x == L.ax && y == L.ay) && (iabs(L.ax - x) + iabs(L.ay - y) >= 2);   // reject_next_to
-        if (!ok) { g.rng.draws += (uint64_t)used; return; }
-        g.tries = 0;
-        if (isobj) {
-            g.occ |= 1ull << (8 * y + x);
-            L.poss |= (uint64_t)(x | (y << 3)) << (6 * g.k);
-            L.tcs |= (uint64_t)g.cur_tc << (6 * g.k);
-            g.k++; L.nobj = g.k;
-            if (g.k == nplace) {
-                if (lp.kind == KIND_REDBALL && lp.grey_dists)              // GoToRedBallGrey: distractors turn grey
-                    for (int q = 1; q < g.k; q++) L.tcs = (L.tcs & ~(56ull << (6 * q))) | ((uint64_t)(C_GREY << 3) << (6 * q));
-                if (levelgen) { g.phase = PH_AGENT; g.agent_placed = false; }   // MiniGridEnv.place_agent: agent_pos = None
-                else { g.phase = PH_CHECK; g.fill = 0; }
-            }
-        } else {
-            L.ax = x; L.ay = y; g.agent_placed = true;
-            L.adir = (int)mulhi32(BB_PEEK(used), 4u);
-            used++;
-            const int fb = 8 * (y + dir_dy(L.adir)) + x + dir_dx(L.adir);
-            const bool front_ok = !((g.occ >> fb) & 1u) || ((lp.wall64 >> fb) & 1u);
-            if (front_ok) {
-                if (levelgen) g.phase = lp.unblocking ? PH_DESC : PH_CHECK;
-                else g.phase = nplace > 0 ? PH_OBJ : PH_CHECK;
-                if (g.phase == PH_CHECK) g.fill = 0;
-            }
-        }
-        g.rng.draws += (uint64_t)used;
-    } else if (ph == PH_CHECK) {                     // check_objs_reachable: bitboard flood fill, two sweeps per iteration
-        if (g.fill == 0) g.fill = 1ull << (8 * L.ay + L.ax);
-        const uint64_t pass = ~g.occ;
-        uint64_t f1 = g.fill | ((g.fill << 1 | g.fill >> 1 | g.fill << 8 | g.fill >> 8) & pass);
-        f1 |= (f1 << 1 | f1 >> 1 | f1 << 8 | f1 >> 8) & pass;
-        if (f1 != g.fill) { g.fill = f1; return; }
-        const uint64_t near = g.fill | g.fill << 1 | g.fill >> 1 | g.fill << 8 | g.fill >> 8;
-        const uint64_t things = g.occ & ~lp.wall64;
-        if (things & ~near) { g.phase = PH_START; return; }              // RejectSampling
-        g.phase = levelgen ? PH_DESC : (lp.kind == KIND_OBJ ? PH_PICK : PH_DONE);
-        g.tries = 0;
-        if (g.phase == PH_DONE) {                                        // GoToRedBall: the ball's descriptor
-            const int tc = sm_obj_tc(L.tcs, 0);
-            L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
-            L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
-        }
-    } else if (ph == PH_START) {                     // RoomGrid._gen_grid of one room: no draws
-        g.attempts++;
-        g.occ = lp.wall64; L.poss = 0; L.tcs = 0; L.nobj = 0; g.k = 0; g.tries = 0;
-        L.ax = S / 2; L.ay = S / 2; L.adir = 0; g.agent_placed = true;
-        if (levelgen) { g.rng.draws += 1; g.phase = n > 0 ? PH_OBJ : PH_AGENT; }      // `_rand_float(0,1) < 0`: one draw
-        else g.phase = PH_AGENT;
-    } else if (ph == PH_PICK) {                      // obj = self._rand_elem(objs); one object: no draw
-        int idx = 0;
-        if (n > 1) { idx = (int)mulhi32(BB_PEEK(0), (uint32_t)n); g.rng.draws += 1; }
-        const int tc = sm_obj_tc(L.tcs, idx);
-        L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
-        L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
-        g.phase = PH_DONE;
-    } else if (ph == PH_DESC) {                      // LevelGen.rand_obj, one try
-        if (g.tries > 100) { g.phase = PH_START; return; }
-        g.tries++;
-        const int ci = (int)mulhi32(BB_PEEK(0), 7u);
-        const int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
-        const int ntypes = L.leaf_kind == I_GOTO ? 4 : 3;
-        const int ti = (int)mulhi32(BB_PEEK(1), (uint32_t)ntypes);
-        const int type = ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR;
-        int used = 2, loc = LOC_NONE;
-        if (lp.locations) {
-            const bool with_loc = mulhi32(BB_PEEK(2), 2u) == 0;          // _rand_bool()
-            used = 3;
-            if (with_loc) { loc = (int)mulhi32(BB_PEEK(3), 4u); used = 4; }
-        }
-        g.rng.draws += (uint64_t)used;
-        const uint32_t m = sm_match(L, type, color, loc);
-        if (m == 0) return;
-        L.d_type = type; L.d_color = color; L.d_loc = loc; L.d_mask = m;
-        g.phase = PH_DONE;
-    }
-#undef BB_PEEK
+    const uint64_t pass = ~a.occ;
+    uint64_t f1 = a.fill | ((a.fill << 1 | a.fill >> 1 | a.fill << 8 | a.fill >> 8) & pass);
+    f1 |= (f1 << 1 | f1 >> 1 | f1 << 8 | f1 >> 8) & pass;
+    const bool changed = f1 != a.fill;
+    a.fill = f1;
+    return changed;
+}
+BB_HD bool small_flood_ok(const LevelParams &lp, const SmallAttempt &a)     // every object touches the filled region
+{
+    const uint64_t near = a.fill | a.fill << 1 | a.fill >> 1 | a.fill << 8 | a.fill >> 8;
+    const uint64_t things = a.occ & ~lp.wall64;
+    return (things & ~near) == 0;
+}
+BB_HD bool small_needs_check(const LevelParams &lp) { return !(lp.kind == KIND_LEVELGEN && lp.unblocking); }
+
+// iclr19 levels: GoToRedBall* describe object 0; the others `obj = self._rand_elem(objs)` (one object: no draw)
+BB_HD void small_pick(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
+{
+    SmallLevel &L = a.L;
+    int idx = 0;
+    if (lp.kind == KIND_OBJ && lp.num_dists > 1) { idx = (int)mulhi32(ds.peek(0), (uint32_t)lp.num_dists); ds.advance(1); }
+    const int tc = sm_obj_tc(L.tcs, idx);
+    L.d_type = tc & 7; L.d_color = tc >> 3; L.d_loc = LOC_NONE;
+    L.d_mask = sm_match(L, L.d_type, L.d_color, LOC_NONE);
 }
 
-// Generates one level of a small single-room environment.  Returns the number of attempts.
+// LevelGen.rand_obj, one try; returns true when the lane is finished with this phase (matched, or attempt failed)
+BB_HD bool small_desc_try(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
+{
+    SmallLevel &L = a.L;
+    if (a.tries > 100) { a.stage = ST_FAIL; return true; }                  // rand_obj: RecursionError
+    a.tries++;
+    const int ci = (int)mulhi32(ds.peek(0), 7u);
+    const int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
+    const int ntypes = L.leaf_kind == I_GOTO ? 4 : 3;
+    const int ti = (int)mulhi32(ds.peek(1), (uint32_t)ntypes);
+    const int type = ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR;
+    int used = 2, loc = LOC_NONE;
+    if (lp.locations) {
+        const bool with_loc = mulhi32(ds.peek(2), 2u) == 0;                // _rand_bool()
+        used = 3;
+        if (with_loc) { loc = (int)mulhi32(ds.peek(3), 4u); used = 4; }
+    }
+    ds.advance(used);
+    const uint32_t m = sm_match(L, type, color, loc);
+    if (m == 0) return false;
+    L.d_type = type; L.d_color = color; L.d_loc = loc; L.d_mask = m;
+    return true;
+}
+
+// Generates one level of a small single-room environment on one lane.  Returns the number of attempts.
 BB_HD int generate_small(const LevelParams &lp, RngScalar &rng, SmallLevel &L)
 {
-    SmallGen g;
-    g.rng = rng; g.rng.blk = ~0ull;
-    small_gen_begin(lp, g);
-    uint32_t win[8];
-    while (g.phase != PH_DONE) small_gen_step(lp, g, win, 1);
-    rng = g.rng; L = g.L;
-    return g.attempts;
+    uint32_t words[RING_WORDS];
+    DrawRing ds;
+    ds.init(words, 1, ((uint64_t)rng.k1 << 32) | rng.k0, rng.draws);
+    int attempts = 0;
+    for (;;) {
+        SmallAttempt a;
+        attempts++;
+        small_attempt_begin(lp, a, ds);
+        while (a.stage == ST_OBJ || a.stage == ST_AGENT) {
+            if (ds.avail() < RING_LOW) ds.fill();
+            small_place_try(lp, a, ds);
+        }
+        if (a.stage == ST_FAIL) continue;
+        if (small_needs_check(lp)) {
+            small_flood_begin(a);
+            while (small_flood_sweep(a)) {}
+            if (!small_flood_ok(lp, a)) continue;
+        }
+        a.tries = 0;
+        if (lp.kind == KIND_LEVELGEN) {
+            for (;;) {
+                if (ds.avail() < RING_LOW) ds.fill();
+                if (small_desc_try(lp, a, ds)) break;
+            }
+            if (a.stage == ST_FAIL) continue;
+        } else {
+            if (ds.avail() < RING_LOW) ds.fill();
+            small_pick(lp, a, ds);
+        }
+        L = a.L;
+        break;
+    }
+    rng.draws = ds.draws; rng.blk = ~0ull;
+    return attempts;
 }
 
-// SmallLevel -> the records of a level slot (grid in both orientations, object table, verifier, tokens, hot)
+// SmallLevel -> the records of a level slot (grid in both orientations, object table, verifier, tokens, hot).
+// Written without dynamically indexed local arrays: on the device everything stays in registers.
+BB_HD void store16(void *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d)      // dst is 16-byte aligned
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(a, b, c, d);
+#else
+    const uint32_t v[4] = {a, b, c, d};
+    __builtin_memcpy(dst, v, 16);
+#endif
+}
 BB_HD void emit_small_level(const LevelParams &lp, const SmallLevel &L, const LevelOut &o)
 {
-    uint64_t rows[16];
-    for (int r = 0; r < 16; r++) rows[r] = lp.row_tmpl[r];
-    ObjTab ot;
-    for (int k = 0; k < MAXOBJ; k++) { ot.x[k] = 0; ot.y[k] = 0; ot.tc[k] = 0; }
+    // the empty room in both orientations (row templates), then one byte per object and orientation on top
+    // (same thread, same addresses: the later stores win)
+    if (lp.rs_g == 8) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {                              // 8-byte rows: G rows 0..H-1, then GT rows 0..W-1 (gt_off = 8 H)
+            const uint64_t t0 = lp.row_tmpl[2 * r], t1 = 2 * r + 1 < lp.H ? lp.row_tmpl[2 * r + 1] : 0ull;   // padding stays zero
+            if (2 * r < lp.H) store16(o.grid + 16 * r, (uint32_t)t0, (uint32_t)(t0 >> 32), (uint32_t)t1, (uint32_t)(t1 >> 32));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint64_t t0 = lp.row_tmpl[8 + 2 * r], t1 = 2 * r + 1 < lp.W ? lp.row_tmpl[8 + 2 * r + 1] : 0ull;
+            if (2 * r < lp.W) store16(o.grid + lp.gt_off + 16 * r, (uint32_t)t0, (uint32_t)(t0 >> 32), (uint32_t)t1, (uint32_t)(t1 >> 32));
+        }
+    } else {                                                       // 4-byte rows (rooms up to 4 x 4)
+        store16(o.grid, (uint32_t)lp.row_tmpl[0], (uint32_t)lp.row_tmpl[1], (uint32_t)lp.row_tmpl[2], (uint32_t)lp.row_tmpl[3]);
+        store16(o.grid + lp.gt_off, (uint32_t)lp.row_tmpl[8], (uint32_t)lp.row_tmpl[9], (uint32_t)lp.row_tmpl[10], (uint32_t)lp.row_tmpl[11]);
+    }
     for (int k = 0; k < L.nobj; k++) {
         const int x = sm_obj_x(L.poss, k), y = sm_obj_y(L.poss, k), tc = sm_obj_tc(L.tcs, k);
-        ot.x[k] = (uint8_t)x; ot.y[k] = (uint8_t)y; ot.tc[k] = (uint8_t)tc;
-        rows[y] = (rows[y] & ~(0xFFull << (8 * x))) | ((uint64_t)tc << (8 * x));
-        rows[8 + x] = (rows[8 + x] & ~(0xFFull << (8 * y))) | ((uint64_t)tc << (8 * y));
+        o.grid[y * lp.rs_g + x] = (uint8_t)tc;
+        o.grid[lp.gt_off + x * lp.rs_t + y] = (uint8_t)tc;
     }
-    // rs_g = rs_t = 4 or 8 bytes per stored row
-    if (lp.rs_g == 8) {
-        uint64_t *g = reinterpret_cast<uint64_t *>(o.grid);
-        for (int r = 0; r < lp.H; r++) g[r] = rows[r];
-        uint64_t *gt = reinterpret_cast<uint64_t *>(o.grid + lp.gt_off);
-        for (int r = 0; r < lp.W; r++) gt[r] = rows[8 + r];
-    } else {
-        uint32_t *g = reinterpret_cast<uint32_t *>(o.grid);
-        for (int r = 0; r < lp.H; r++) g[r] = (uint32_t)rows[r];
-        uint32_t *gt = reinterpret_cast<uint32_t *>(o.grid + lp.gt_off);
-        for (int r = 0; r < lp.W; r++) gt[r] = (uint32_t)rows[8 + r];
+    // object table: 6-bit fields -> bytes, objects 0..11 (the rest of the 32 slots is zero)
+    uint32_t X[3], Y[3], TC[3];
+#pragma unroll
+    for (int wd = 0; wd < 3; wd++) {
+        X[wd] = 0; Y[wd] = 0; TC[wd] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = 4 * wd + i;
+            if (k >= 10) continue;                                   // poss / tcs hold at most 10 objects
+            X[wd] |= (uint32_t)sm_obj_x(L.poss, k) << (8 * i);
+            Y[wd] |= (uint32_t)sm_obj_y(L.poss, k) << (8 * i);
+            TC[wd] |= (uint32_t)sm_obj_tc(L.tcs, k) << (8 * i);
+        }
     }
-    *o.obj = ot;
-    InstrRec ins;
-    for (int k = 0; k < 8; k++) ins.desc_mask[k] = 0;
-    ins.desc_mask[0] = L.d_mask;
-    for (int k = 0; k < 4; k++) { ins.leaf_kind[k] = (uint8_t)I_NONE; ins.leaf_pre[k] = NO_OBJ; }
-    ins.leaf_kind[0] = (uint8_t)L.leaf_kind;
-    ins.root_kind = R_SINGLE; ins.side_and = 0; ins.flags = 0; ins.pad0 = 0; ins.pad1 = 0;
-    *o.ins = ins;
-    EnvHot h;
-    h.x = (uint8_t)L.ax; h.y = (uint8_t)L.ay; h.dirflags = (uint8_t)L.adir; h.carry = NO_OBJ;
-    h.step_count = 0; h.max_steps = (uint16_t)lp.nav_time_maze;          // one non-PutNext leaf: one navigation
-    h.cur_mask = (1u << L.nobj) - 1u; h.snap_mask = h.cur_mask;
-    *o.hot = h;
-    // "go to" / "pick up" + ObjDesc.surface
-    int16_t tok[16];
-    int nt = 0;
-    if (L.leaf_kind == I_GOTO) { tok[nt++] = W_GO; tok[nt++] = W_TO; } else { tok[nt++] = W_PICK; tok[nt++] = W_UP; }
-    tok[nt++] = popc32(L.d_mask) > 1 ? W_A : W_THE;
-    if (L.d_color != ANY) tok[nt++] = (int16_t)(W_RED + L.d_color);
-    tok[nt++] = (int16_t)(L.d_type == ANY_TYPE ? W_OBJECT : L.d_type == T_BOX ? W_BOX : L.d_type == T_BALL ? W_BALL : L.d_type == T_KEY ? W_KEY : W_DOOR);
-    if (L.d_loc == LOC_FRONT) { tok[nt++] = W_IN; tok[nt++] = W_FRONT; tok[nt++] = W_OF; tok[nt++] = W_YOU; }
-    else if (L.d_loc == LOC_BEHIND) { tok[nt++] = W_BEHIND; tok[nt++] = W_YOU; }
-    else if (L.d_loc == LOC_LEFT) { tok[nt++] = W_ON; tok[nt++] = W_YOUR; tok[nt++] = W_LEFT; }
-    else if (L.d_loc == LOC_RIGHT) { tok[nt++] = W_ON; tok[nt++] = W_YOUR; tok[nt++] = W_RIGHT; }
-    for (int k = 0; k < lp.max_tokens; k++) o.tok[k] = k < nt ? tok[k] : (int16_t)0;
+    uint8_t *ob = reinterpret_cast<uint8_t *>(o.obj);
+    store16(ob, X[0], X[1], X[2], 0); store16(ob + 16, 0, 0, 0, 0);
+    store16(ob + 32, Y[0], Y[1], Y[2], 0); store16(ob + 48, 0, 0, 0, 0);
+    store16(ob + 64, TC[0], TC[1], TC[2], 0); store16(ob + 80, 0, 0, 0, 0);
+    // verifier record: one leaf, one descriptor
+    uint8_t *ib = reinterpret_cast<uint8_t *>(o.ins);
+    store16(ib, L.d_mask, 0, 0, 0); store16(ib + 16, 0, 0, 0, 0);
+    store16(ib + 32, (uint32_t)L.leaf_kind | ((uint32_t)I_NONE << 8) | ((uint32_t)I_NONE << 16) | ((uint32_t)I_NONE << 24),
+            (uint32_t)NO_OBJ * 0x01010101u, (uint32_t)R_SINGLE, 0);
+    // hot record
+    const uint32_t all = (1u << L.nobj) - 1u;
+    store16(o.hot, (uint32_t)L.ax | ((uint32_t)L.ay << 8) | ((uint32_t)L.adir << 16) | ((uint32_t)NO_OBJ << 24),
+            (uint32_t)(uint16_t)lp.nav_time_maze << 16, all, all);                       // step_count 0, max_steps: one navigation
+    // "go to" / "pick up" + ObjDesc.surface: [v0 v1 article (colour) type loc...], the colour word is optional
+    const uint64_t v0 = L.leaf_kind == I_GOTO ? W_GO : W_PICK, v1 = L.leaf_kind == I_GOTO ? W_TO : W_UP;
+    const uint64_t art = popc32(L.d_mask) > 1 ? W_A : W_THE;
+    const uint64_t ty = L.d_type == ANY_TYPE ? W_OBJECT : L.d_type == T_BOX ? W_BOX : L.d_type == T_BALL ? W_BALL : L.d_type == T_KEY ? W_KEY : W_DOOR;
+    uint64_t loc = 0;                                              // up to four words, 16 bits each
+    if (L.d_loc == LOC_FRONT) loc = (uint64_t)W_IN | ((uint64_t)W_FRONT << 16) | ((uint64_t)W_OF << 32) | ((uint64_t)W_YOU << 48);
+    else if (L.d_loc == LOC_BEHIND) loc = (uint64_t)W_BEHIND | ((uint64_t)W_YOU << 16);
+    else if (L.d_loc == LOC_LEFT) loc = (uint64_t)W_ON | ((uint64_t)W_YOUR << 16) | ((uint64_t)W_LEFT << 32);
+    else if (L.d_loc == LOC_RIGHT) loc = (uint64_t)W_ON | ((uint64_t)W_YOUR << 16) | ((uint64_t)W_RIGHT << 32);
+    uint64_t t0 = v0 | (v1 << 16) | (art << 32), t1, t2;
+    if (L.d_color != ANY) { t0 |= (uint64_t)(W_RED + L.d_color) << 48; t1 = ty | (loc << 16); t2 = loc >> 48; }
+    else { t0 |= ty << 48; t1 = loc; t2 = 0; }
+    store16(o.tok, (uint32_t)t0, (uint32_t)(t0 >> 32), (uint32_t)t1, (uint32_t)(t1 >> 32));
+    if (lp.max_tokens > 8) store16(o.tok + 8, (uint32_t)t2, (uint32_t)(t2 >> 32), 0, 0);
+    for (int k = 16; k < lp.max_tokens; k++) o.tok[k] = 0;
 }
 
 // =============================================================================

@@ -29,7 +29,6 @@
 using namespace bb;
 
 // ---------------------------------------------------------------------------------
-struct GenSave;
 struct PoolPtrs {
     // live state of every environment
     uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
@@ -43,7 +42,7 @@ struct PoolPtrs {
     RngRec *rng; uint8_t *locked_room; uint32_t *attempts;
     float *last_reward;
     uint32_t *gen_ticket;      // work-ticket counter of k_gen / k_gen_small
-    uint32_t *gen_count; int32_t *gen_list; GenSave *gen_save;       // k_gen_scan: envs whose ring is not full
+    uint32_t *gen_count; int32_t *gen_list;                          // k_gen_scan: four lists (by missing levels) of envs whose ring is not full
     unsigned long long *warp_counters;   // [num_warps][4]: steps, episodes, successes, errors
     int32_t depth, n;
 };
@@ -753,85 +752,69 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
     }
 }
 
-// Level generation for small single-room levels: ONE LANE PER ENVIRONMENT running the flat state-machine
-// generator (small_gen_step): lanes differ only in predicates, so the warp stays converged.
-//   k_gen_scan   compacts the environments whose ring is not full into a dense work list (warp ballot);
-//   k_gen_small  every lane runs its own generator; a lane that finished its env immediately takes the next
-//                list entry (warp-aggregated atomic), finished levels wait in a small per-lane shared-memory
-//                buffer and are written out (emit_small_level) for all lanes together when a buffer fills.
+// Level generation for small single-room levels: ONE LANE PER ENVIRONMENT, THE WARP IN LOCK-STEP THROUGH THE PHASES
+// OF ONE ATTEMPT PER ROUND (env_logic.cuh: small_attempt_begin / small_place_try / small_flood_* / small_pick /
+// small_desc_try / emit_small_level).
+//   k_gen_scan   compacts the environments whose ring is not full into four work lists by the number of levels they
+//                miss (>= 4, 3, 2, 1): levels of one env are serial (one random stream), so the longest chains start first;
+//   k_gen_small  a lane takes an env from the lists (warp-aggregated atomic) and produces its missing levels one
+//                attempt per round.  Inside a round every lane of the warp is in the same phase: placement tries
+//                (lanes that are done wait), flood fill, descriptor, and the level is written straight from
+//                registers.  Philox is converged too: a lane's next 64 draws sit in a shared-memory ring that is
+//                topped up for the whole warp whenever one lane runs low (DrawRing).
+// Round 1's version ran a per-lane state machine instead (each lane in its own phase): ncu showed 9.8 active
+// lanes per instruction and IPC 0.7 (profiles/README.md, r01o).  A rejected attempt costs one round of that lane;
+// the env's records (stream position, ring tail) are consistent after every round, so the per-launch round budget
+// of bb_pool_rollout's in-stream refill needs no saved generator state.
 constexpr int GS_THREADS = 128;
-constexpr int GS_BUF = 3;
-
-// A generation interrupted by the per-launch iteration budget (bb_pool_rollout refills concurrently with the
-// stepping kernel and must finish in bounded time; the slowest levels are a geometric tail of rejected
-// attempts) is parked here and resumed by the next launch.
-struct __align__(16) GenSave {
-    uint64_t draws, occ, fill, poss, tcs;
-    uint16_t tries, attempts;
-    uint8_t phase, k, cur_tc, agent_placed, nobj, ax, ay, adir;
-    uint8_t valid, pad[11];
-};
-static_assert(sizeof(GenSave) == 64, "GenSave is one 64-byte record");
-
-__device__ __forceinline__ void gen_save(GenSave *d, const SmallGen &g)
-{
-    GenSave v;
-    v.draws = g.rng.draws; v.occ = g.occ; v.fill = g.fill; v.poss = g.L.poss; v.tcs = g.L.tcs;
-    v.tries = (uint16_t)g.tries; v.attempts = (uint16_t)g.attempts;
-    v.phase = (uint8_t)g.phase; v.k = (uint8_t)g.k; v.cur_tc = (uint8_t)g.cur_tc; v.agent_placed = g.agent_placed ? 1 : 0;
-    v.nobj = (uint8_t)g.L.nobj; v.ax = (uint8_t)g.L.ax; v.ay = (uint8_t)g.L.ay; v.adir = (uint8_t)g.L.adir;
-    v.valid = 1;
-    for (int i = 0; i < 11; i++) v.pad[i] = 0;
-    *d = v;
-}
-__device__ __forceinline__ void gen_restore(const GenSave &v, SmallGen &g)
-{
-    g.rng.draws = v.draws; g.rng.blk = ~0ull;
-    g.occ = v.occ; g.fill = v.fill; g.L.poss = v.poss; g.L.tcs = v.tcs;
-    g.tries = v.tries; g.attempts = v.attempts; g.phase = v.phase; g.k = v.k; g.cur_tc = v.cur_tc;
-    g.agent_placed = v.agent_placed != 0;
-    g.L.nobj = v.nobj; g.L.ax = v.ax; g.L.ay = v.ay; g.L.adir = v.adir;
-}
 
 __global__ void k_gen_scan(const PoolPtrs P, const int n, const int target)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool need = false;
-    if (env < n) need = target - (int)(P.tail[env] - P.head_snap[env]) > 0;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
-    if (m) {
-        int base = 0;
-        if (lane == 0) base = (int)atomicAdd(P.gen_count, (uint32_t)__popc(m));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (need) P.gen_list[base + __popc(m & ((1u << lane) - 1u))] = env;
+    int b = -1;
+    if (env < n) {
+        const int missing = target - (int)(P.tail[env] - P.head_snap[env]);
+        if (missing > 0) b = missing >= 4 ? 3 : missing - 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, b == k);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(P.gen_count + k, (uint32_t)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (b == k) P.gen_list[(size_t)k * n + base + __popc(m & ((1u << lane) - 1u))] = env;
+        }
     }
 }
 
-struct GsBuffered { SmallLevel L; int env, slot; };
-
 __global__ void __launch_bounds__(GS_THREADS)
-k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_iters)
+k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_rounds)
 {
-    __shared__ GsBuffered buf[GS_BUF][GS_THREADS];
-    __shared__ uint32_t s_win[8][GS_THREADS];                 // per-lane draw windows (win_ensure)
-    uint32_t *win = &s_win[0][threadIdx.x];
+    __shared__ uint32_t s_ring[RING_WORDS][GS_THREADS];         // the lanes' draw rings: word j of thread t at [j][t]
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, tid = threadIdx.x;
-    const uint32_t count = *P.gen_count;
+    const uint32_t c3 = P.gen_count[3], c2 = P.gen_count[2], c1 = P.gen_count[1], c0 = P.gen_count[0];
+    const uint32_t count = c0 + c1 + c2 + c3;
     const uint32_t D = (uint32_t)P.depth;
-    SmallGen g;
-    g.rng.init(0, 0);
-    small_gen_begin(lp, g);
-    int env = -1, left = 0, nbuf = 0, iters = 0;
+    DrawRing ds;
+    ds.init(&s_ring[0][tid], GS_THREADS, 0, 0);
+    int env = -1, left = 0, rounds = 0;
     uint32_t tl = 0;
     bool exhausted = false;
+    // converged top-up: when a lane that is about to draw has fewer than RING_LOW draws ready, EVERY working lane
+    // generates the blocks its ring has room for (all lanes end up 61..64 draws ahead)
+#define BB_TOPUP(cond)                                                                                   \
+    if (__any_sync(FULL, (cond) && ds.avail() < RING_LOW)) {                                             \
+        for (;;) {                                                                                       \
+            const bool rm = active && ds.room();                                                         \
+            if (!__any_sync(FULL, rm)) break;                                                            \
+            if (rm) ds.gen_block();                                                                      \
+        }                                                                                                \
+    }
     for (;;) {
-        // ---- idle lanes take the next work item (one atomic per warp) -----------------------------
-        if (max_iters > 0 && iters >= max_iters && !exhausted) {   // budget spent: park the level in progress
-            if (left > 0) gen_save(P.gen_save + env, g);
-            left = 0; exhausted = true;
-        }
+        // ---- idle lanes take the next work item (one atomic per warp), longest chains first -----------
         const bool need = left == 0 && !exhausted;
         const uint32_t mneed = __ballot_sync(FULL, need);
         if (mneed) {
@@ -839,46 +822,65 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int 
             if (lane == 0) base = atomicAdd(P.gen_ticket, (uint32_t)__popc(mneed));
             base = __shfl_sync(FULL, base, 0);
             if (need) {
-                const uint32_t idx = base + (uint32_t)__popc(mneed & ((1u << lane) - 1u));
+                uint32_t idx = base + (uint32_t)__popc(mneed & ((1u << lane) - 1u));
                 if (idx < count) {
-                    env = P.gen_list[idx];
+                    int b = 3;
+                    if (idx >= c3) { idx -= c3; b = 2; if (idx >= c2) { idx -= c2; b = 1; if (idx >= c1) { idx -= c1; b = 0; } } }
+                    env = P.gen_list[(size_t)b * P.n + idx];
                     tl = P.tail[env];
                     left = target - (int)(tl - P.head_snap[env]);
                     const RngRec r = P.rng[env];
-                    g.rng.init(r.seed, r.draws);
-                    small_gen_begin(lp, g);
-                    const GenSave sv = P.gen_save[env];
-                    if (sv.valid) { gen_restore(sv, g); P.gen_save[env].valid = 0; }
+                    ds.init(&s_ring[0][tid], GS_THREADS, r.seed, r.draws);
                 } else exhausted = true;
             }
         }
-        if (!__any_sync(FULL, left > 0)) break;
-        // ---- one generator iteration per lane --------------------------------------------------------
-        if (left > 0) {
-            small_gen_step(lp, g, win, GS_THREADS);
-            iters++;
-            if (g.phase == PH_DONE) {
-                GsBuffered &b = buf[nbuf][tid];
-                b.L = g.L; b.env = env; b.slot = (int)(tl % D);
-                nbuf++; tl++; left--;
-                RngRec r; r.seed = ((uint64_t)g.rng.k1 << 32) | g.rng.k0; r.draws = g.rng.draws;
-                P.rng[env] = r;                                 // the env's records are consistent after every level
-                P.tail[env] = tl;
-                P.attempts[env] += (uint32_t)g.attempts;
-                if (left > 0) small_gen_begin(lp, g);
+        const bool active = left > 0;
+        if (!__any_sync(FULL, active)) break;
+        if (max_rounds > 0 && rounds >= max_rounds) break;          // budget spent: the envs keep their deficit
+        rounds++;
+        // ---- one attempt per working lane ---------------------------------------------------------------
+        SmallAttempt a;
+        a.stage = ST_IDLE; a.occ = 0; a.fill = 0; a.k = 0; a.tries = 0; a.cur_tc = 0; a.agent_placed = false;
+        a.L.poss = 0; a.L.tcs = 0; a.L.nobj = 0; a.L.ax = a.L.ay = a.L.adir = 0;
+        a.L.leaf_kind = 0; a.L.d_type = 0; a.L.d_color = 0; a.L.d_loc = 0; a.L.d_mask = 0;
+        if (active) small_attempt_begin(lp, a, ds);
+        for (;;) {                                                  // placements: agent and objects, one try per trip
+            const bool placing = a.stage == ST_OBJ || a.stage == ST_AGENT;
+            if (!__any_sync(FULL, placing)) break;
+            BB_TOPUP(placing)
+            if (placing) small_place_try(lp, a, ds);
+        }
+        bool ok = a.stage == ST_PLACED;
+        if (small_needs_check(lp)) {                                // check_objs_reachable
+            if (ok) small_flood_begin(a);
+            for (;;) {
+                const bool changed = ok && small_flood_sweep(a);
+                if (!__any_sync(FULL, changed)) break;
             }
+            ok = ok && small_flood_ok(lp, a);
         }
-        // ---- flush: all lanes write their buffered levels together ---------------------------------
-        if (__any_sync(FULL, nbuf == GS_BUF)) {
-#pragma unroll 1
-            for (int j = 0; j < GS_BUF; j++)
-                if (j < nbuf) { const GsBuffered &b = buf[j][tid]; emit_small_level(lp, b.L, ring_slot(lp, P, b.env, b.slot)); }
-            nbuf = 0;
+        a.tries = 0;
+        if (lp.kind == KIND_LEVELGEN) {                             // rand_obj: rejection sampling of a descriptor
+            bool trying = ok;
+            for (;;) {
+                if (!__any_sync(FULL, trying)) break;
+                BB_TOPUP(trying)
+                if (trying && small_desc_try(lp, a, ds)) trying = false;
+            }
+            ok = ok && a.stage != ST_FAIL;
+        } else {
+            BB_TOPUP(ok)
+            if (ok) small_pick(lp, a, ds);
         }
+        // ---- write the level; the env's records are consistent after every round -------------------------
+        if (ok) {
+            emit_small_level(lp, a.L, ring_slot(lp, P, env, (int)(tl % D)));
+            tl++; left--;
+            P.tail[env] = tl;
+        }
+        if (active) { P.rng[env].draws = ds.draws; P.attempts[env] += 1u; }
     }
-#pragma unroll 1
-    for (int j = 0; j < GS_BUF; j++)
-        if (j < nbuf) { const GsBuffered &b = buf[j][tid]; emit_small_level(lp, b.L, ring_slot(lp, P, b.env, b.slot)); }
+#undef BB_TOPUP
 }
 
 __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
@@ -890,7 +892,6 @@ __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
     P.locked_room[env] = 0xFF;
     P.tail[env] = P.head[env];                                 // empty ring: old levels belong to the old stream
     P.tail_pub[env] = P.head[env];
-    reinterpret_cast<uint4 *>(P.gen_save)[4 * (size_t)env + 3] = make_uint4(0, 0, 0, 0);      // GenSave::valid = 0
     P.attempts[env] = 0;
 }
 
@@ -949,28 +950,18 @@ static int dalloc(bb_pool *p, T **out, size_t count)
     return 0;
 }
 
-static int dalloc_bytes(bb_pool *p, void **out, size_t bytes)
-{
-    void *ptr = nullptr;
-    CU(cudaMalloc(&ptr, bytes ? bytes : 16));
-    CU(cudaMemset(ptr, 0, bytes ? bytes : 16));
-    p->allocs.push_back(ptr);
-    *out = ptr;
-    return 0;
-}
-
 static int make_params(const bb_level_spec *s, LevelParams *lp)
 {
     const char *e = make_level_params(s, lp);
     return e ? fail("%s", e) : 0;
 }
 
-static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_iters = 0)
+static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0)
 {
     if (p->lp.small && !p->gen_generic) {
-        cudaMemsetAsync(p->P.gen_count, 0, sizeof(uint32_t), st);
+        cudaMemsetAsync(p->P.gen_count, 0, 4 * sizeof(uint32_t), st);
         k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target);
-        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_iters);
+        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds);
         p->launches++;
     } else k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
@@ -1098,7 +1089,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         p->gen_small_blocks = prop.multiProcessorCount * per_sm;
     }
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
-    p->gen_budget = 128;                                   // generator iterations per lane per refill pass
+    p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
     p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
     if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) p->refill_every = v; }
@@ -1130,7 +1121,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         dalloc(p, &P.robj, D * n) || dalloc(p, &P.rins, D * n) || dalloc(p, &P.rtok, D * n * lp.max_tokens) ||
         dalloc(p, &P.head, n) || dalloc(p, &P.tail, n) || dalloc(p, &P.head_snap, n) || dalloc(p, &P.tail_pub, n) ||
         dalloc(p, &P.rng, n) || dalloc(p, &P.locked_room, n) || dalloc(p, &P.attempts, n) || dalloc(p, &P.last_reward, n) ||
-        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_count, 4) || dalloc(p, &P.gen_list, n) || dalloc_bytes(p, (void **)&P.gen_save, n * 64) ||
+        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_count, 4) || dalloc(p, &P.gen_list, 4 * n) ||
         dalloc(p, &P.warp_counters, (size_t)p->num_warps * 4) ||
         dalloc(p, &p->d_act, n) || dalloc(p, &p->d_obs, n * OBS_BYTES) || dalloc(p, &p->d_rew, n) || dalloc(p, &p->d_done, n) ||
         dalloc(p, &p->d_dir, n) || dalloc(p, &p->d_seeds, n)) {
