@@ -768,13 +768,16 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
 // of bb_pool_rollout's in-stream refill needs no saved generator state.
 constexpr int GS_THREADS = 128;
 
-__global__ void k_gen_scan(const PoolPtrs P, const int n, const int target)
+__global__ void k_gen_scan(const PoolPtrs P, const int n, const int target, const int snap_heads)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int b = -1;
     if (env < n) {
-        const int missing = target - (int)(P.tail[env] - P.head_snap[env]);
+        uint32_t hd;
+        if (snap_heads) { hd = P.head[env]; P.head_snap[env] = hd; }      // in-stream refill: the snapshot is taken here
+        else hd = P.head_snap[env];
+        const int missing = target - (int)(P.tail[env] - hd);
         if (missing > 0) b = missing >= 4 ? 3 : missing - 1;
     }
 #pragma unroll
@@ -790,7 +793,7 @@ __global__ void k_gen_scan(const PoolPtrs P, const int n, const int target)
 }
 
 __global__ void __launch_bounds__(GS_THREADS)
-k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_rounds)
+k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_rounds, const int min_active)
 {
     __shared__ uint32_t s_ring[RING_WORDS][GS_THREADS];         // the lanes' draw rings: word j of thread t at [j][t]
     const unsigned FULL = 0xFFFFFFFFu;
@@ -835,8 +838,13 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int 
             }
         }
         const bool active = left > 0;
-        if (!__any_sync(FULL, active)) break;
+        const uint32_t mact = __ballot_sync(FULL, active);
+        if (!mact) break;
         if (max_rounds > 0 && rounds >= max_rounds) break;          // budget spent: the envs keep their deficit
+        // bounded refill (bb_pool_rollout): a round costs the same whether 32 lanes work or 2 (deficits > 1 and
+        // rejected attempts leave sparse warps behind), so a sparse warp stops after its first round and leaves the
+        // rest to the next pass -- unless a ring is more than half empty
+        if (min_active > 0 && rounds >= 1 && __popc(mact) < min_active && !__any_sync(FULL, active && left > (int)(D / 2))) break;
         rounds++;
         // ---- one attempt per working lane ---------------------------------------------------------------
         SmallAttempt a;
@@ -915,7 +923,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
-    bool gen_generic; int gen_small_blocks, gen_budget, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
+    bool gen_generic; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 3 = k_rollout with T = 1 for small grids, k_step8 otherwise (default); 0 = k_step8; 1 = k_step; 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
@@ -956,12 +964,12 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
     return e ? fail("%s", e) : 0;
 }
 
-static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0)
+static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false)
 {
+    cudaMemsetAsync(p->P.gen_count, 0, 8 * sizeof(uint32_t), st);      // list counters + work ticket
     if (p->lp.small && !p->gen_generic) {
-        cudaMemsetAsync(p->P.gen_count, 0, 4 * sizeof(uint32_t), st);
-        k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target);
-        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds);
+        k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
+        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active);
         p->launches++;
     } else k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
@@ -974,7 +982,6 @@ static void launch_gen(bb_pool *p, cudaStream_t st)
     const int target = p->mode == BB_MODE_AUTORESET ? p->D : 1;
     const size_t nb = (size_t)p->n * sizeof(uint32_t);
     cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, st);
-    cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), st);
     launch_gen_kernel(p, target, st);
     cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, st);
     p->launches++;
@@ -1091,6 +1098,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
+    p->gen_min_active = 16;                                // ... and a warp with fewer working lanes than this stops after its first round
+    if (const char *e = getenv("BB_GEN_MIN_ACTIVE")) p->gen_min_active = atoi(e);
     p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
     if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) p->refill_every = v; }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
@@ -1121,13 +1130,14 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         dalloc(p, &P.robj, D * n) || dalloc(p, &P.rins, D * n) || dalloc(p, &P.rtok, D * n * lp.max_tokens) ||
         dalloc(p, &P.head, n) || dalloc(p, &P.tail, n) || dalloc(p, &P.head_snap, n) || dalloc(p, &P.tail_pub, n) ||
         dalloc(p, &P.rng, n) || dalloc(p, &P.locked_room, n) || dalloc(p, &P.attempts, n) || dalloc(p, &P.last_reward, n) ||
-        dalloc(p, &P.gen_ticket, 4) || dalloc(p, &P.gen_count, 4) || dalloc(p, &P.gen_list, 4 * n) ||
+        dalloc(p, &P.gen_count, 8) || dalloc(p, &P.gen_list, 4 * n) ||
         dalloc(p, &P.warp_counters, (size_t)p->num_warps * 4) ||
         dalloc(p, &p->d_act, n) || dalloc(p, &p->d_obs, n * OBS_BYTES) || dalloc(p, &p->d_rew, n) || dalloc(p, &p->d_done, n) ||
         dalloc(p, &p->d_dir, n) || dalloc(p, &p->d_seeds, n)) {
         bb_pool_destroy(p);
         return 1;
     }
+    P.gen_ticket = P.gen_count + 4;                      // one memset clears the list counters and the work ticket
     CU(cudaMemset(P.locked_room, 0xFF, n));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     {
@@ -1300,9 +1310,9 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     const bool gen_serial = !p->gen_concurrent;
     if (refill && gen_serial) {
         if (dbg_timing) cudaEventRecord(dbg_ev[2], user);
-        CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
-        cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), user);
-        launch_gen_kernel(p, p->D, user, p->gen_budget);
+        const bool fused_snap = p->lp.small && !p->gen_generic;       // k_gen_scan takes the head snapshot itself
+        if (!fused_snap) CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
+        launch_gen_kernel(p, p->D, user, p->gen_budget, p->gen_min_active, fused_snap);
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, user);
         if (dbg_timing) { cudaEventRecord(dbg_ev[3], user); p->tev_refill = true; }
         p->launches++;
@@ -1318,8 +1328,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (refill && !gen_serial) {
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
         if (dbg_timing) cudaEventRecord(dbg_ev[2], p->gen_stream);
-        cudaMemsetAsync(p->P.gen_ticket, 0, sizeof(uint32_t), p->gen_stream);
-        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget);      // bounded: runs beside k_rollout
+        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget, p->gen_min_active);      // bounded: runs beside k_rollout
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
         if (dbg_timing) { cudaEventRecord(dbg_ev[3], p->gen_stream); p->tev_refill = true; }
         p->gen_outstanding = true;
