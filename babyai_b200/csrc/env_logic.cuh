@@ -894,19 +894,20 @@ BB_HD uint32_t sm_match(const SmallLevel &L, int type, int color, int loc)
 // of a warp together (k_gen_small: converged Philox, the expensive part of generation), and a draw is one indexed
 // read.  Memory with dynamic indexing: shared memory on the device (stride `ws` words between a lane's
 // consecutive entries), a plain array in the host build.
-constexpr int RING_BLOCKS = 16, RING_WORDS = 4 * RING_BLOCKS;
-struct DrawRing {
+template <int RING_BLOCKS>
+struct DrawRingT {
+    static constexpr int RING_WORDS = 4 * RING_BLOCKS;
     uint32_t *w; int ws;
     uint32_t k0, k1;
     uint64_t draws;               // index of the next draw of the stream
-    uint64_t gen;                 // blocks gen-16 .. gen-1 are in the ring
+    uint64_t gen;                 // blocks gen - RING_BLOCKS .. gen - 1 are in the ring
 
     BB_HD void init(uint32_t *w_, int ws_, uint64_t seed, uint64_t d)
     {
         w = w_; ws = ws_; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); draws = d; gen = d >> 2;
     }
     BB_HD int avail() const { return (int)((int64_t)(gen * 4ull) - (int64_t)draws); }     // draws ready to be read
-    // the slot of block `gen` holds block gen-16: free once every draw of that block is consumed
+    // the slot of block `gen` holds block gen - RING_BLOCKS: free once every draw of that block is consumed
     BB_HD bool room() const { return gen < (draws >> 2) + (uint64_t)RING_BLOCKS; }
     BB_HD void gen_block()
     {
@@ -920,6 +921,7 @@ struct DrawRing {
     BB_HD uint32_t peek(int j) const { return w[(int)((draws + (uint64_t)j) & (uint64_t)(RING_WORDS - 1)) * ws]; }   // needs avail() > j
     BB_HD void advance(int n) { draws += (uint64_t)n; }
 };
+typedef DrawRingT<16> DrawRing;   // k_gen_small, host build; the generator warp inside k_rollout uses 8 blocks
 constexpr int RING_LOW = 8;       // every generator step below reads at most 5 draws: top up when fewer than 8 are ready
 
 // ---- one ATTEMPT at a small level, in phases that a warp runs in lock-step ---------------------------------
@@ -938,7 +940,8 @@ struct SmallAttempt {
     bool agent_placed;
 };
 
-BB_HD void small_attempt_begin(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
+template <class DS>
+BB_HD void small_attempt_begin(const LevelParams &lp, SmallAttempt &a, DS &ds)
 {
     const bool levelgen = lp.kind == KIND_LEVELGEN;
     const int S = lp.room_size;
@@ -952,7 +955,8 @@ BB_HD void small_attempt_begin(const LevelParams &lp, SmallAttempt &a, DrawRing 
 }
 
 // RoomGrid.place_agent -> MiniGridEnv.place_agent tries / add_object, add_distractors: one placement try
-BB_HD void small_place_try(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
+template <class DS>
+BB_HD void small_place_try(const LevelParams &lp, SmallAttempt &a, DS &ds)
 {
     const int S = lp.room_size;
     const bool levelgen = lp.kind == KIND_LEVELGEN;
@@ -1020,7 +1024,8 @@ BB_HD bool small_flood_ok(const LevelParams &lp, const SmallAttempt &a)     // e
 BB_HD bool small_needs_check(const LevelParams &lp) { return !(lp.kind == KIND_LEVELGEN && lp.unblocking); }
 
 // iclr19 levels: GoToRedBall* describe object 0; the others `obj = self._rand_elem(objs)` (one object: no draw)
-BB_HD void small_pick(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
+template <class DS>
+BB_HD void small_pick(const LevelParams &lp, SmallAttempt &a, DS &ds)
 {
     SmallLevel &L = a.L;
     int idx = 0;
@@ -1031,7 +1036,8 @@ BB_HD void small_pick(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
 }
 
 // LevelGen.rand_obj, one try; returns true when the lane is finished with this phase (matched, or attempt failed)
-BB_HD bool small_desc_try(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
+template <class DS>
+BB_HD bool small_desc_try(const LevelParams &lp, SmallAttempt &a, DS &ds)
 {
     SmallLevel &L = a.L;
     if (a.tries > 100) { a.stage = ST_FAIL; return true; }                  // rand_obj: RecursionError
@@ -1057,7 +1063,7 @@ BB_HD bool small_desc_try(const LevelParams &lp, SmallAttempt &a, DrawRing &ds)
 // Generates one level of a small single-room environment on one lane.  Returns the number of attempts.
 BB_HD int generate_small(const LevelParams &lp, RngScalar &rng, SmallLevel &L)
 {
-    uint32_t words[RING_WORDS];
+    uint32_t words[DrawRing::RING_WORDS];
     DrawRing ds;
     ds.init(words, 1, ((uint64_t)rng.k1 << 32) | rng.k0, rng.draws);
     int attempts = 0;

@@ -525,6 +525,158 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
     }
 }
 
+// Level generation for small single-room levels: ONE LANE PER ENVIRONMENT, THE WARP IN LOCK-STEP THROUGH THE PHASES
+// OF ONE ATTEMPT PER ROUND (env_logic.cuh: small_attempt_begin / small_place_try / small_flood_* / small_pick /
+// small_desc_try / emit_small_level).
+//   k_gen_scan   compacts the environments whose ring is not full into four work lists by the number of levels they
+//                miss (>= 4, 3, 2, 1): levels of one env are serial (one random stream), so the longest chains start first;
+//   k_gen_small  a lane takes an env from the lists (warp-aggregated atomic) and produces its missing levels one
+//                attempt per round.  Inside a round every lane of the warp is in the same phase: placement tries
+//                (lanes that are done wait), flood fill, descriptor, and the level is written straight from
+//                registers.  Philox is converged too: a lane's next 64 draws sit in a shared-memory ring that is
+//                topped up for the whole warp whenever one lane runs low (DrawRing).
+// Round 1's version ran a per-lane state machine instead (each lane in its own phase): ncu showed 9.8 active
+// lanes per instruction and IPC 0.7 (profiles/README.md, r01o).  A rejected attempt costs one round of that lane;
+// the env's records (stream position, ring tail) are consistent after every round, so the per-launch round budget
+// of bb_pool_rollout's in-stream refill needs no saved generator state.
+constexpr int GS_THREADS = 128;
+
+// One round of the small-level generator for the 32 lanes of a warp (see the comment above k_gen_small): every
+// working lane (`active`) makes one attempt at the next level of its env; on success the level is written to ring
+// slot tl % D and tl / left advance.  Called with all 32 lanes.
+template <class DS, bool PUBLISH>
+__device__ __forceinline__ void gen_small_round(const LevelParams &lp, const PoolPtrs &P, DS &ds, const bool active,
+                                                const int env, uint32_t &tl, int &left, const uint32_t D)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    // converged top-up: when a lane that is about to draw has fewer than RING_LOW draws ready, EVERY working lane
+    // generates the blocks its ring has room for
+#define BB_TOPUP(cond)                                                                                   \
+    if (__any_sync(FULL, (cond) && ds.avail() < RING_LOW)) {                                             \
+        for (;;) {                                                                                       \
+            const bool rm = active && ds.room();                                                         \
+            if (!__any_sync(FULL, rm)) break;                                                            \
+            if (rm) ds.gen_block();                                                                      \
+        }                                                                                                \
+    }
+    // ---- one attempt per working lane ---------------------------------------------------------------
+    SmallAttempt a;
+    a.stage = ST_IDLE; a.occ = 0; a.fill = 0; a.k = 0; a.tries = 0; a.cur_tc = 0; a.agent_placed = false;
+    a.L.poss = 0; a.L.tcs = 0; a.L.nobj = 0; a.L.ax = a.L.ay = a.L.adir = 0;
+    a.L.leaf_kind = 0; a.L.d_type = 0; a.L.d_color = 0; a.L.d_loc = 0; a.L.d_mask = 0;
+    if (active) small_attempt_begin(lp, a, ds);
+    for (;;) {                                                  // placements: agent and objects, one try per trip
+        const bool placing = a.stage == ST_OBJ || a.stage == ST_AGENT;
+        if (!__any_sync(FULL, placing)) break;
+        BB_TOPUP(placing)
+        if (placing) small_place_try(lp, a, ds);
+    }
+    bool ok = a.stage == ST_PLACED;
+    if (small_needs_check(lp)) {                                // check_objs_reachable
+        if (ok) small_flood_begin(a);
+        for (;;) {
+            const bool changed = ok && small_flood_sweep(a);
+            if (!__any_sync(FULL, changed)) break;
+        }
+        ok = ok && small_flood_ok(lp, a);
+    }
+    a.tries = 0;
+    if (lp.kind == KIND_LEVELGEN) {                             // rand_obj: rejection sampling of a descriptor
+        bool trying = ok;
+        for (;;) {
+            if (!__any_sync(FULL, trying)) break;
+            BB_TOPUP(trying)
+            if (trying && small_desc_try(lp, a, ds)) trying = false;
+        }
+        ok = ok && a.stage != ST_FAIL;
+    } else {
+        BB_TOPUP(ok)
+        if (ok) small_pick(lp, a, ds);
+    }
+    // ---- write the level; the env's records are consistent after every round -------------------------
+    if (ok) {
+        emit_small_level(lp, a.L, ring_slot(lp, P, env, (int)(tl % D)));
+        tl++; left--;
+        P.tail[env] = tl;
+        if (PUBLISH) P.tail_pub[env] = tl;        // generator warp inside k_rollout: nobody reads tail_pub during the launch
+    }
+    if (active) { P.rng[env].draws = ds.draws; P.attempts[env] += 1u; }
+#undef BB_TOPUP
+}
+
+
+__global__ void k_gen_scan(const PoolPtrs P, const int n, const int target, const int snap_heads)
+{
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int b = -1;
+    if (env < n) {
+        uint32_t hd;
+        if (snap_heads) { hd = P.head[env]; P.head_snap[env] = hd; }      // in-stream refill: the snapshot is taken here
+        else hd = P.head_snap[env];
+        const int missing = target - (int)(P.tail[env] - hd);
+        if (missing > 0) b = missing >= 4 ? 3 : missing - 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, b == k);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(P.gen_count + k, (uint32_t)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (b == k) P.gen_list[(size_t)k * n + base + __popc(m & ((1u << lane) - 1u))] = env;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GS_THREADS)
+k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_rounds, const int min_active)
+{
+    __shared__ uint32_t s_ring[DrawRing::RING_WORDS][GS_THREADS];         // the lanes' draw rings: word j of thread t at [j][t]
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    const uint32_t c3 = P.gen_count[3], c2 = P.gen_count[2], c1 = P.gen_count[1], c0 = P.gen_count[0];
+    const uint32_t count = c0 + c1 + c2 + c3;
+    const uint32_t D = (uint32_t)P.depth;
+    DrawRing ds;
+    ds.init(&s_ring[0][tid], GS_THREADS, 0, 0);
+    int env = -1, left = 0, rounds = 0;
+    uint32_t tl = 0;
+    bool exhausted = false;
+    for (;;) {
+        // ---- idle lanes take the next work item (one atomic per warp), longest chains first -----------
+        const bool need = left == 0 && !exhausted;
+        const uint32_t mneed = __ballot_sync(FULL, need);
+        if (mneed) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.gen_ticket, (uint32_t)__popc(mneed));
+            base = __shfl_sync(FULL, base, 0);
+            if (need) {
+                uint32_t idx = base + (uint32_t)__popc(mneed & ((1u << lane) - 1u));
+                if (idx < count) {
+                    int b = 3;
+                    if (idx >= c3) { idx -= c3; b = 2; if (idx >= c2) { idx -= c2; b = 1; if (idx >= c1) { idx -= c1; b = 0; } } }
+                    env = P.gen_list[(size_t)b * P.n + idx];
+                    tl = P.tail[env];
+                    left = target - (int)(tl - P.head_snap[env]);
+                    const RngRec r = P.rng[env];
+                    ds.init(&s_ring[0][tid], GS_THREADS, r.seed, r.draws);
+                } else exhausted = true;
+            }
+        }
+        const bool active = left > 0;
+        const uint32_t mact = __ballot_sync(FULL, active);
+        if (!mact) break;
+        if (max_rounds > 0 && rounds >= max_rounds) break;          // budget spent: the envs keep their deficit
+        // bounded refill (bb_pool_rollout): a round costs the same whether 32 lanes work or 2 (deficits > 1 and
+        // rejected attempts leave sparse warps behind), so a sparse warp stops after its first round and leaves the
+        // rest to the next pass -- unless a ring is more than half empty
+        if (min_active > 0 && rounds >= 1 && __popc(mact) < min_active && !__any_sync(FULL, active && left > (int)(D / 2))) break;
+        rounds++;
+        gen_small_round<DrawRing, false>(lp, P, ds, active, env, tl, left, D);
+    }
+}
+
 // ---- persistent rollout kernel: T steps per launch, state resident in shared memory --------------
 // bb_pool_rollout's kernel.  Every per-step kernel above reloads ~290 bytes of env state per step through
 // a chain of dependent DRAM round trips and is latency-bound at 11-14 warps per SM.  Here a warp loads the
@@ -533,8 +685,16 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
 // back at the end.  Finished envs take their next level from the ring (the host guarantees >= T levels
 // per env before the launch; k_gen refills concurrently on the side stream from a head snapshot taken
 // before the launch, so it never touches a slot this launch can consume).
-constexpr int R_THREADS = 64;
-constexpr int R_WARPS = R_THREADS / 32;
+constexpr int R_WARPS = 2;                    // stepping warps per CTA
+constexpr int R_THREADS = 32 * R_WARPS;       // ... and the launch adds one generator warp in fused mode (R_THREADS_FUSED)
+constexpr int R_THREADS_FUSED = R_THREADS + 32;
+// Generator warp of a fused launch (single-room levels, ParallelEnv mode): while the two stepping warps of the CTA
+// run their T steps (k_rollout issues ~48 % of the SM's slots: latency-bound), a third warp refills the rings of the
+// CTA's 64 envs with the same round function as k_gen_small -- in issue slots that are idle anyway, with no
+// refill pass between launches.  Its shared-memory area: draw rings of 8 Philox blocks per lane, the work list.
+typedef DrawRingT<8> RolloutRing;
+constexpr int RG_RING_WORDS = 32 * RolloutRing::RING_WORDS;            // 1024 words
+constexpr int RG_AREA_WORDS = RG_RING_WORDS + 64 /*tails*/ + 32 /*deficits, u16*/ + 16 /*list, u8*/ + 4 /*flag*/;
 
 struct SmemOnlyMem {            // lane-private records in shared memory (byte addressable; odd word strides)
     const LevelParams &lp; uint8_t *g, *o, *i;
@@ -570,19 +730,84 @@ __device__ __forceinline__ void warp_copy_records(uint32_t *sm, int stride_words
 }
 
 template <int ACT_BYTES>
-__global__ void __launch_bounds__(R_THREADS)
+__global__ void __launch_bounds__(R_THREADS_FUSED, 7)
 k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions_v, uint8_t *__restrict__ obs,
           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
-          const int mode, const int force_reset)
+          const int mode, const int force_reset, const int gen_rounds, const int gen_min_active)
 {
     const int8_t *actions = reinterpret_cast<const int8_t *>(actions_v);
     extern __shared__ __align__(16) uint32_t smr[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;
+    const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
+    const bool fused = gen_rounds > 0;                  // launched with R_THREADS_FUSED threads and RG_AREA_WORDS more shared memory
+    uint32_t *g_area = smr + R_WARPS * warp_words;
+    volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
+    if (warp == R_WARPS) {
+        // ================= generator warp (fused launches only) =================
+        const unsigned FULL = 0xFFFFFFFFu;
+        const uint32_t D = (uint32_t)P.depth;
+        uint32_t *ring = g_area, *s_tl = g_area + RG_RING_WORDS;
+        uint16_t *s_def = reinterpret_cast<uint16_t *>(s_tl + 64);
+        uint8_t *list = reinterpret_cast<uint8_t *>(s_tl + 64 + 32);
+        const int cta_env0 = blockIdx.x * R_WARPS * 32;
+        int cta_nv = n - cta_env0; cta_nv = cta_nv > 64 ? 64 : (cta_nv < 0 ? 0 : cta_nv);
+        // ring state of the CTA's envs as of the launch start (the stepping warps advance `head` only at their end)
+        int cnt = 0;
+        bool urgent = false;
+        if (lane == 0) *s_done = 0;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int i = 32 * h2 + lane;
+            bool need = false;
+            if (i < cta_nv) {
+                const uint32_t hd = P.head[cta_env0 + i], tl0 = P.tail[cta_env0 + i];
+                const int have = (int)(tl0 - hd);
+                s_tl[i] = tl0; s_def[i] = (uint16_t)((int)D - have);
+                need = have < (int)D;
+                urgent = urgent || have < 2 * T;         // the next launch may consume T levels and this one another T
+            }
+            const uint32_t m = __ballot_sync(FULL, need);
+            if (need) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
+            cnt += __popc(m);
+        }
+        const bool must_complete = __any_sync(FULL, urgent);
+        __syncthreads();                                  // the stepping warps have read head / tail: generation may start
+        RolloutRing ds;
+        ds.init(ring + lane, 32, 0, 0);
+        int env_g = -1, left = 0, next = 0, rounds = 0;
+        uint32_t tl = 0;
+        for (;;) {
+            const bool idle = left == 0;
+            const uint32_t midle = __ballot_sync(FULL, idle);
+            if (midle && next < cnt) {                    // idle lanes take the next envs of the CTA's list
+                const int idx = next + __popc(midle & ((1u << lane) - 1u));
+                if (idle && idx < cnt) {
+                    const int i = list[idx];
+                    env_g = cta_env0 + i; tl = s_tl[i]; left = (int)s_def[i];
+                    const RngRec r = P.rng[env_g];
+                    ds.init(ring + lane, 32, r.seed, r.draws);
+                }
+                next += __popc(midle);
+            }
+            const bool active = left > 0;
+            const uint32_t mact = __ballot_sync(FULL, active);
+            if (!mact) break;
+            if (!must_complete) {                         // otherwise: a ring is low, fill everything up whatever it takes
+                int dn = 0;
+                if (lane == 0) dn = *s_done;
+                dn = __shfl_sync(FULL, dn, 0);
+                if (rounds >= gen_rounds || dn >= R_WARPS) break;           // budget spent / the stepping warps are finished
+                if (rounds >= 1 && __popc(mact) < gen_min_active) break;     // sparse warp: leave the rest to the next launch
+            }
+            rounds++;
+            gen_small_round<RolloutRing, true>(lp, P, ds, active, env_g, tl, left, D);
+        }
+        return;
+    }
     const int env0 = (blockIdx.x * R_WARPS + warp) * 32, env = env0 + lane;
     int nv = n - env0; nv = nv > 32 ? 32 : (nv < 0 ? 0 : nv);
     const bool valid = lane < nv;
-    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;
-    const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
     uint32_t *sg = smr + warp * warp_words, *so = sg + 32 * gs, *si = so + 32 * SM_OBJ_STRIDE;
     uint32_t *tile = si + 32 * SM_INS_STRIDE;       // 16-byte aligned: see launch_rollout
     // ---- load the state of the warp's envs once ---------------------------------------------------
@@ -596,9 +821,11 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
     if (valid) {
         h = P.hot[env];
         head = P.head[env];
-        avail = __ldcg(P.tail_pub + env) - head;
+        // fused launch: the CTA's generator warp is the only producer and has not started yet (barrier below)
+        avail = (fused ? P.tail[env] : __ldcg(P.tail_pub + env)) - head;
         if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env];
     }
+    if (fused) __syncthreads();
     __syncwarp();
     SmemOnlyMem mem(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * SM_OBJ_STRIDE),
                     reinterpret_cast<uint8_t *>(si + lane * SM_INS_STRIDE));
@@ -693,6 +920,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
         n_step += __shfl_down_sync(0xFFFFFFFFu, n_step, off); n_end += __shfl_down_sync(0xFFFFFFFFu, n_end, off);
         n_succ += __shfl_down_sync(0xFFFFFFFFu, n_succ, off); n_err += __shfl_down_sync(0xFFFFFFFFu, n_err, off);
     }
+    if (fused && lane == 0) atomicAdd(const_cast<int *>(s_done), 1);     // tells the generator warp not to start another round
     if (lane == 0) {
         unsigned long long *c = P.warp_counters + 4ull * (blockIdx.x * R_WARPS + warp);
         if (n_step) atomicAdd(c + 0, (unsigned long long)n_step);
@@ -752,145 +980,6 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
     }
 }
 
-// Level generation for small single-room levels: ONE LANE PER ENVIRONMENT, THE WARP IN LOCK-STEP THROUGH THE PHASES
-// OF ONE ATTEMPT PER ROUND (env_logic.cuh: small_attempt_begin / small_place_try / small_flood_* / small_pick /
-// small_desc_try / emit_small_level).
-//   k_gen_scan   compacts the environments whose ring is not full into four work lists by the number of levels they
-//                miss (>= 4, 3, 2, 1): levels of one env are serial (one random stream), so the longest chains start first;
-//   k_gen_small  a lane takes an env from the lists (warp-aggregated atomic) and produces its missing levels one
-//                attempt per round.  Inside a round every lane of the warp is in the same phase: placement tries
-//                (lanes that are done wait), flood fill, descriptor, and the level is written straight from
-//                registers.  Philox is converged too: a lane's next 64 draws sit in a shared-memory ring that is
-//                topped up for the whole warp whenever one lane runs low (DrawRing).
-// Round 1's version ran a per-lane state machine instead (each lane in its own phase): ncu showed 9.8 active
-// lanes per instruction and IPC 0.7 (profiles/README.md, r01o).  A rejected attempt costs one round of that lane;
-// the env's records (stream position, ring tail) are consistent after every round, so the per-launch round budget
-// of bb_pool_rollout's in-stream refill needs no saved generator state.
-constexpr int GS_THREADS = 128;
-
-__global__ void k_gen_scan(const PoolPtrs P, const int n, const int target, const int snap_heads)
-{
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    int b = -1;
-    if (env < n) {
-        uint32_t hd;
-        if (snap_heads) { hd = P.head[env]; P.head_snap[env] = hd; }      // in-stream refill: the snapshot is taken here
-        else hd = P.head_snap[env];
-        const int missing = target - (int)(P.tail[env] - hd);
-        if (missing > 0) b = missing >= 4 ? 3 : missing - 1;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, b == k);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = (int)atomicAdd(P.gen_count + k, (uint32_t)__popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (b == k) P.gen_list[(size_t)k * n + base + __popc(m & ((1u << lane) - 1u))] = env;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(GS_THREADS)
-k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_rounds, const int min_active)
-{
-    __shared__ uint32_t s_ring[RING_WORDS][GS_THREADS];         // the lanes' draw rings: word j of thread t at [j][t]
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, tid = threadIdx.x;
-    const uint32_t c3 = P.gen_count[3], c2 = P.gen_count[2], c1 = P.gen_count[1], c0 = P.gen_count[0];
-    const uint32_t count = c0 + c1 + c2 + c3;
-    const uint32_t D = (uint32_t)P.depth;
-    DrawRing ds;
-    ds.init(&s_ring[0][tid], GS_THREADS, 0, 0);
-    int env = -1, left = 0, rounds = 0;
-    uint32_t tl = 0;
-    bool exhausted = false;
-    // converged top-up: when a lane that is about to draw has fewer than RING_LOW draws ready, EVERY working lane
-    // generates the blocks its ring has room for (all lanes end up 61..64 draws ahead)
-#define BB_TOPUP(cond)                                                                                   \
-    if (__any_sync(FULL, (cond) && ds.avail() < RING_LOW)) {                                             \
-        for (;;) {                                                                                       \
-            const bool rm = active && ds.room();                                                         \
-            if (!__any_sync(FULL, rm)) break;                                                            \
-            if (rm) ds.gen_block();                                                                      \
-        }                                                                                                \
-    }
-    for (;;) {
-        // ---- idle lanes take the next work item (one atomic per warp), longest chains first -----------
-        const bool need = left == 0 && !exhausted;
-        const uint32_t mneed = __ballot_sync(FULL, need);
-        if (mneed) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(P.gen_ticket, (uint32_t)__popc(mneed));
-            base = __shfl_sync(FULL, base, 0);
-            if (need) {
-                uint32_t idx = base + (uint32_t)__popc(mneed & ((1u << lane) - 1u));
-                if (idx < count) {
-                    int b = 3;
-                    if (idx >= c3) { idx -= c3; b = 2; if (idx >= c2) { idx -= c2; b = 1; if (idx >= c1) { idx -= c1; b = 0; } } }
-                    env = P.gen_list[(size_t)b * P.n + idx];
-                    tl = P.tail[env];
-                    left = target - (int)(tl - P.head_snap[env]);
-                    const RngRec r = P.rng[env];
-                    ds.init(&s_ring[0][tid], GS_THREADS, r.seed, r.draws);
-                } else exhausted = true;
-            }
-        }
-        const bool active = left > 0;
-        const uint32_t mact = __ballot_sync(FULL, active);
-        if (!mact) break;
-        if (max_rounds > 0 && rounds >= max_rounds) break;          // budget spent: the envs keep their deficit
-        // bounded refill (bb_pool_rollout): a round costs the same whether 32 lanes work or 2 (deficits > 1 and
-        // rejected attempts leave sparse warps behind), so a sparse warp stops after its first round and leaves the
-        // rest to the next pass -- unless a ring is more than half empty
-        if (min_active > 0 && rounds >= 1 && __popc(mact) < min_active && !__any_sync(FULL, active && left > (int)(D / 2))) break;
-        rounds++;
-        // ---- one attempt per working lane ---------------------------------------------------------------
-        SmallAttempt a;
-        a.stage = ST_IDLE; a.occ = 0; a.fill = 0; a.k = 0; a.tries = 0; a.cur_tc = 0; a.agent_placed = false;
-        a.L.poss = 0; a.L.tcs = 0; a.L.nobj = 0; a.L.ax = a.L.ay = a.L.adir = 0;
-        a.L.leaf_kind = 0; a.L.d_type = 0; a.L.d_color = 0; a.L.d_loc = 0; a.L.d_mask = 0;
-        if (active) small_attempt_begin(lp, a, ds);
-        for (;;) {                                                  // placements: agent and objects, one try per trip
-            const bool placing = a.stage == ST_OBJ || a.stage == ST_AGENT;
-            if (!__any_sync(FULL, placing)) break;
-            BB_TOPUP(placing)
-            if (placing) small_place_try(lp, a, ds);
-        }
-        bool ok = a.stage == ST_PLACED;
-        if (small_needs_check(lp)) {                                // check_objs_reachable
-            if (ok) small_flood_begin(a);
-            for (;;) {
-                const bool changed = ok && small_flood_sweep(a);
-                if (!__any_sync(FULL, changed)) break;
-            }
-            ok = ok && small_flood_ok(lp, a);
-        }
-        a.tries = 0;
-        if (lp.kind == KIND_LEVELGEN) {                             // rand_obj: rejection sampling of a descriptor
-            bool trying = ok;
-            for (;;) {
-                if (!__any_sync(FULL, trying)) break;
-                BB_TOPUP(trying)
-                if (trying && small_desc_try(lp, a, ds)) trying = false;
-            }
-            ok = ok && a.stage != ST_FAIL;
-        } else {
-            BB_TOPUP(ok)
-            if (ok) small_pick(lp, a, ds);
-        }
-        // ---- write the level; the env's records are consistent after every round -------------------------
-        if (ok) {
-            emit_small_level(lp, a.L, ring_slot(lp, P, env, (int)(tl % D)));
-            tl++; left--;
-            P.tail[env] = tl;
-        }
-        if (active) { P.rng[env].draws = ds.draws; P.attempts[env] += 1u; }
-    }
-#undef BB_TOPUP
-}
-
 __global__ void k_seed(const PoolPtrs P, const uint64_t *seeds, const int n)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -923,7 +1012,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
-    bool gen_generic; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
+    bool gen_generic, gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 3 = k_rollout with T = 1 for small grids, k_step8 otherwise (default); 0 = k_step8; 1 = k_step; 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
@@ -997,8 +1086,8 @@ static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8
         const int gs = (p->lp.cells_pad >> 2) | 1;
         const size_t smem = (size_t)R_WARPS * (32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS) * 4;
         const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
-        if (action_bytes == 8) k_rollout<8><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset);
-        else k_rollout<1><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset);
+        if (action_bytes == 8) k_rollout<8><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0);
+        else k_rollout<1><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0);
         p->launches++;
         return;
     }
@@ -1098,6 +1187,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
+    p->gen_fused = true;                                   // bb_pool_rollout on single-room levels: generator warp inside k_rollout (BB_GEN_FUSED=0: refill passes)
+    if (const char *e = getenv("BB_GEN_FUSED")) p->gen_fused = atoi(e) != 0;
     p->gen_min_active = 16;                                // ... and a warp with fewer working lanes than this stops after its first round
     if (const char *e = getenv("BB_GEN_MIN_ACTIVE")) p->gen_min_active = atoi(e);
     p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
@@ -1296,8 +1387,13 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
     const size_t smem = (size_t)R_WARPS * warp_words * 4;
     const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
-    // one refill pass serves `refill_every` launches (more envs per pass = more lanes busy in k_gen_small)
-    const bool refill = p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL") && (p->rollouts++ % p->refill_every) == 0;
+    // Single-room levels: FUSED -- a generator warp inside every CTA of k_rollout refills the rings of the CTA's envs
+    // while the stepping warps run (no refill pass at all).  It guarantees >= 2T levels per ring at the end of a
+    // launch (must_complete rule in the kernel), so the next launch cannot run dry; needs D > 2T.
+    const bool fused = p->gen_fused && p->lp.small && !p->gen_generic && !p->gen_concurrent && p->mode == BB_MODE_AUTORESET &&
+                       p->D >= 2 * T + 8 && !getenv("BB_DEBUG_NO_REFILL");
+    // otherwise one refill pass serves `refill_every` launches (more envs per pass = more lanes busy in k_gen_small)
+    const bool refill = !fused && p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL") && (p->rollouts++ % p->refill_every) == 0;
     const bool dbg_timing = p->time_rollout;
     cudaEvent_t *dbg_ev = p->tev;
     if (dbg_timing && !dbg_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&dbg_ev[i]));
@@ -1322,7 +1418,9 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaEventRecord(p->ev_fork, user));
     }
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
-    k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0);
+    if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
+                                                                                       p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
+    else k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
     if (dbg_timing) { cudaEventRecord(dbg_ev[1], user); p->tev_kernel = true; }
     p->launches++;
     if (refill && !gen_serial) {

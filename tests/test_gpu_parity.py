@@ -177,13 +177,20 @@ def test_rollout_graph_equals_stepwise(level, n, T):
     assert a.counters()['errors'] == 0
 
 
-def test_rollout_with_suspended_generation(monkeypatch):
-    """A per-launch generation budget of ONE round (one attempt per env and refill pass) leaves most rings with a
-    deficit that later launches work off; rollouts must still equal the oracle bit for bit."""
+@pytest.mark.parametrize('knobs', [
+    {'BB_GEN_BUDGET': '1'},                              # fused generator warp, one round per launch: deficits carry over
+    {'BB_GEN_BUDGET': '1', 'BB_RING_DEPTH': '48'},       # ... with a shallow ring: the must-complete rule (< 2T levels left) kicks in
+    {'BB_GEN_FUSED': '0', 'BB_GEN_BUDGET': '1'},         # refill passes (k_gen_scan + k_gen_small) between launches instead
+    {'BB_GEN_FUSED': '0', 'BB_REFILL_EVERY': '1', 'BB_GEN_MIN_ACTIVE': '0'},
+])
+def test_rollout_with_suspended_generation(monkeypatch, knobs):
+    """Bounded generation (a round budget per launch, sparse warps stop early) leaves rings with a deficit that later
+    launches work off; rollouts must still equal the oracle bit for bit, whichever way the levels are supplied."""
     import torch
     import oracle as orc
     from babyai_b200 import BabyAIVecEnv
-    monkeypatch.setenv('BB_GEN_BUDGET', '1')
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
     n, T, R = 512, 16, 12
     seeds = np.arange(n, dtype=np.uint64) + 4242
     env = BabyAIVecEnv('PickupLoc', n, seeds=seeds)
