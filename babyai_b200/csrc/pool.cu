@@ -1012,7 +1012,7 @@ struct bb_pool {
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
-    bool gen_generic, gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
+    bool gen_generic; int gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
     int step_kernel;               // 3 = k_rollout with T = 1 for small grids, k_step8 otherwise (default); 0 = k_step8; 1 = k_step; 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
     long long rel;
@@ -1187,8 +1187,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
-    p->gen_fused = true;                                   // bb_pool_rollout on single-room levels: generator warp inside k_rollout (BB_GEN_FUSED=0: refill passes)
-    if (const char *e = getenv("BB_GEN_FUSED")) p->gen_fused = atoi(e) != 0;
+    p->gen_fused = 1;                                      // bb_pool_rollout on single-room levels: generator warp inside k_rollout (see bb_pool_rollout)
+    if (const char *e = getenv("BB_GEN_FUSED")) p->gen_fused = atoi(e);
     p->gen_min_active = 16;                                // ... and a warp with fewer working lanes than this stops after its first round
     if (const char *e = getenv("BB_GEN_MIN_ACTIVE")) p->gen_min_active = atoi(e);
     p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
@@ -1390,7 +1390,12 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     // Single-room levels: FUSED -- a generator warp inside every CTA of k_rollout refills the rings of the CTA's envs
     // while the stepping warps run (no refill pass at all).  It guarantees >= 2T levels per ring at the end of a
     // launch (must_complete rule in the kernel), so the next launch cannot run dry; needs D > 2T.
-    const bool fused = p->gen_fused && p->lp.small && !p->gen_generic && !p->gen_concurrent && p->mode == BB_MODE_AUTORESET &&
+    // One generator warp per 64 envs keeps up while an env needs at most ~1.5 levels per launch: episodes last up to
+    // max_steps = room_size^2 steps, so fused when 3 max_steps >= 2 T (measured, profiles/r01y_ab_fused.log: S8 / S6
+    // rooms +32 % / +13 % fused; S5 / S4 rooms -7 % / -60 %: there the GPU-wide refill passes win).  BB_GEN_FUSED=0/1/2:
+    // never / by this rule (default) / whenever possible.
+    const bool fused = p->gen_fused != 0 && (p->gen_fused == 2 || 3 * p->lp.nav_time_maze >= 2 * T) &&
+                       p->lp.small && !p->gen_generic && !p->gen_concurrent && p->mode == BB_MODE_AUTORESET &&
                        p->D >= 2 * T + 8 && !getenv("BB_DEBUG_NO_REFILL");
     // otherwise one refill pass serves `refill_every` launches (more envs per pass = more lanes busy in k_gen_small)
     const bool refill = !fused && p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL") && (p->rollouts++ % p->refill_every) == 0;

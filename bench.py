@@ -318,15 +318,16 @@ def main():
                                    'ParallelEnv auto-reset, in-kernel verifier' % (args.level, n),
                        'envs_per_gpu': n, 'rollout_chunk': T,
                        'l2_policy': 'obs written to a [%d, %d, 147] buffer (%.0f MB) larger than L2' % (T, n, T * n * 147 / 1e6),
-                       'execution': 'bb_pool_rollout: persistent kernel k_rollout (%d steps per launch, env state resident in '
-                                    'shared memory) + bounded in-stream level refill (k_gen_scan, k_gen_small)' % T,
+                       'execution': 'bb_pool_rollout: ONE persistent kernel per %d steps (k_rollout: per CTA two stepping warps with '
+                                    'the env state resident in shared memory + one generator warp that refills the level rings of the '
+                                    "CTA's envs; refill_ms_per_launch > 0 only when BB_GEN_FUSED=0 or for rooms smaller than 6x6)" % T,
                        'parallelism': 'replicas x%d, counters all-gather only' % world},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'kernel': 'k_rollout', 'kernel_ms': k_roll_ms, 'steps_per_launch': T,
                          'kernel_us_per_step': 1e3 * k_roll_ms / T, 'refill_ms_per_launch': k_refill_ms,
                          'algorithmic_bytes_per_launch': ALGO_BYTES_PER_STEP * n * T, 'peak_source': peak_src},
             'per_step_api': {'value': world * n / (per_step_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': per_step_ms,
-                             'api': 'bb_pool_step (k_step8 + k_gen on a side stream), device buffers', 'steps': Ks},
+                             'api': 'bb_pool_step (one launch per step: k_rollout with T = 1 on single-room levels, k_step8 otherwise; level generation on a side stream), device buffers', 'steps': Ks},
             'e2e': {'value': world * n * Ke / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n,
                     'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke,
                     'api': 'bb_pool_step_host, page-locked host buffers'},

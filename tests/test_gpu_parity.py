@@ -178,8 +178,8 @@ def test_rollout_graph_equals_stepwise(level, n, T):
 
 
 @pytest.mark.parametrize('knobs', [
-    {'BB_GEN_BUDGET': '1'},                              # fused generator warp, one round per launch: deficits carry over
-    {'BB_GEN_BUDGET': '1', 'BB_RING_DEPTH': '48'},       # ... with a shallow ring: the must-complete rule (< 2T levels left) kicks in
+    {'BB_GEN_FUSED': '2', 'BB_GEN_BUDGET': '1'},         # fused generator warp, one round per launch: deficits carry over
+    {'BB_GEN_FUSED': '2', 'BB_GEN_BUDGET': '1', 'BB_RING_DEPTH': '48'},       # ... with a shallow ring: the must-complete rule (< 2T levels left) kicks in
     {'BB_GEN_FUSED': '0', 'BB_GEN_BUDGET': '1'},         # refill passes (k_gen_scan + k_gen_small) between launches instead
     {'BB_GEN_FUSED': '0', 'BB_REFILL_EVERY': '1', 'BB_GEN_MIN_ACTIVE': '0'},
 ])
