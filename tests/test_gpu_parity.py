@@ -156,9 +156,11 @@ def test_reseed_and_reset_like_batch_evaluate():
         assert np.array_equal(oo, go) and np.array_equal(orr, gr) and np.array_equal(od, gd)
 
 
-@pytest.mark.parametrize('level,n,T', [('GoToLocal', 4096, 24), ('BossLevel', 512, 16), ('GoToObjMazeS4R2', 300, 40)])
+@pytest.mark.parametrize('level,n,T', [('GoToLocal', 4096, 24), ('GoToLocal', 1000, 40), ('PickupLoc', 200, 40), ('GoToObjS4', 256, 40),
+                                        ('BossLevel', 512, 16), ('GoToObjMazeS4R2', 300, 40)])
 def test_rollout_graph_equals_stepwise(level, n, T):
-    """bb_pool_rollout (persistent kernel, 8x8 and 22x22 staging, ragged last warp) == T x bb_pool_step."""
+    """bb_pool_rollout (persistent kernel: fused generator warp with full and ragged CTAs, refill passes for 4x4
+    rooms, 22x22 staging with k_gen beside it) == T x bb_pool_step."""
     import torch
     from babyai_b200 import BabyAIVecEnv
     seeds = np.arange(n, dtype=np.uint64) + 77
@@ -169,7 +171,7 @@ def test_rollout_graph_equals_stepwise(level, n, T):
     obs = torch.zeros((T, n, 7, 7, 3), dtype=torch.uint8, device='cuda')
     rew = torch.zeros((T, n), device='cuda')
     done = torch.zeros((T, n), dtype=torch.uint8, device='cuda')
-    for rep in range(2):            # second call reuses the instantiated graph
+    for rep in range(3):            # later calls consume levels generated during the earlier ones
         a.rollout(acts, obs, rew, done)
         for t in range(T):
             o, r, d = b.step(acts[t])
