@@ -105,8 +105,10 @@ int bb_pool_step_timed(bb_pool *pool, const void *actions_dev, int32_t action_by
  * of BASELINE.json configs, and the shape of BaseAlgo.collect_experiences'
  * [frames_per_proc][procs] buffers, rl/algos/base.py:110-188): actions int8
  * [T][n_envs]; outputs [T][n_envs]...  Results are identical to T calls of
- * bb_pool_step.  Single-room levels: one persistent kernel keeps the env state in
- * shared memory for the T steps; other levels: one CUDA graph of T step launches. */
+ * bb_pool_step.  Grids up to 22 x 22 with a ring of pre-generated levels deep enough
+ * (>= 3 T): ONE persistent kernel keeps the env state in shared memory for the T steps
+ * (single-room levels: level generation runs inside it too); otherwise one CUDA graph
+ * of T step launches. */
 int bb_pool_rollout(bb_pool *pool, const int8_t *actions_dev, int32_t T,
                     uint8_t *obs_dev, float *reward_dev, uint8_t *done_dev, int8_t *dir_dev, void *stream);
 
