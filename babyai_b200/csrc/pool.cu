@@ -1025,6 +1025,7 @@ struct bb_pool {
     std::vector<void *> allocs;
     // host-buffer API staging
     int8_t *h_act; uint8_t *h_obs; float *h_rew; uint8_t *h_done; int8_t *h_dir;      // pinned
+    int zerocopy, zc_level; const void *chk_rew; int8_t *zc_act; float *zc_rew; uint8_t *zc_done; int8_t *zc_dir; uint8_t *zc_obs;   // BB_HOST_ZEROCOPY
     int8_t *d_act; uint8_t *d_obs; float *d_rew; uint8_t *d_done; int8_t *d_dir;
     uint64_t *d_seeds;
     long long launches;
@@ -1187,6 +1188,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
+    p->zerocopy = 0; p->zc_level = 0; p->chk_rew = nullptr;
+    if (const char *e = getenv("BB_HOST_ZEROCOPY")) p->zerocopy = atoi(e);
     p->gen_fused = 1;                                      // bb_pool_rollout on single-room levels: generator warp inside k_rollout (see bb_pool_rollout)
     if (const char *e = getenv("BB_GEN_FUSED")) p->gen_fused = atoi(e);
     p->gen_min_active = 16;                                // ... and a warp with fewer working lanes than this stops after its first round
@@ -1514,19 +1517,38 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
     const size_t n = (size_t)p->n;
     // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are the DMA targets
     // themselves; pageable ones go through the pool's pinned staging buffers + a host memcpy
-    if (obs_host != p->chk_obs) { p->chk_obs = obs_host; p->direct = is_pinned(obs_host) && is_pinned(reward_host) && is_pinned(done_host) && (!dir_host || is_pinned(dir_host)); }
+    if (obs_host != p->chk_obs || reward_host != p->chk_rew) {
+        p->chk_obs = obs_host; p->chk_rew = reward_host;
+        p->direct = is_pinned(obs_host) && is_pinned(reward_host) && is_pinned(done_host) && (!dir_host || is_pinned(dir_host));
+        // BB_HOST_ZEROCOPY (page-locked caller buffers only): 1 = the step kernel reads the actions from the pool's pinned
+        // staging buffer and writes reward / done / direction straight into the caller's buffers over PCIe (mapped host
+        // memory: 1 H2D + 3 small D2H copies less per step); 2 = the observations too (no copy at all)
+        p->zc_level = 0;
+        if (p->direct && p->zerocopy > 0) {
+            void *da = nullptr, *dr = nullptr, *dd = nullptr, *dq = nullptr, *dobs = nullptr;
+            bool ok = cudaHostGetDevicePointer(&da, p->h_act, 0) == cudaSuccess && cudaHostGetDevicePointer(&dr, reward_host, 0) == cudaSuccess &&
+                      cudaHostGetDevicePointer(&dd, done_host, 0) == cudaSuccess && (!dir_host || cudaHostGetDevicePointer(&dq, dir_host, 0) == cudaSuccess);
+            if (ok && p->zerocopy > 1) ok = cudaHostGetDevicePointer(&dobs, obs_host, 0) == cudaSuccess;
+            if (ok) { p->zc_level = p->zerocopy > 1 ? 2 : 1; p->zc_act = (int8_t *)da; p->zc_rew = (float *)dr; p->zc_done = (uint8_t *)dd; p->zc_dir = (int8_t *)dq; p->zc_obs = (uint8_t *)dobs; }
+            else cudaGetLastError();
+        }
+    }
     const bool direct = p->direct;
+    const int zc = p->zc_level;
     memcpy(p->h_act, actions_host, n);
-    CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, p->stream));
+    if (!zc) CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, p->stream));
     if (sched_leave_rollout(p, p->stream)) return 1;
     if (sched_before_step(p, p->rel, p->stream)) return 1;
-    launch_step(p, p->d_act, 1, p->d_obs, p->d_rew, p->d_done, p->d_dir, 0, p->stream);
+    if (zc) launch_step(p, p->zc_act, 1, zc > 1 ? p->zc_obs : p->d_obs, p->zc_rew, p->zc_done, dir_host ? p->zc_dir : p->d_dir, 0, p->stream);
+    else launch_step(p, p->d_act, 1, p->d_obs, p->d_rew, p->d_done, p->d_dir, 0, p->stream);
     if (sched_after_step(p, p->rel, p->stream)) return 1;
     p->rel++;
-    CU(cudaMemcpyAsync(direct ? obs_host : p->h_obs, p->d_obs, n * OBS_BYTES, cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaMemcpyAsync(direct ? (void *)reward_host : (void *)p->h_rew, p->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaMemcpyAsync(direct ? done_host : p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, p->stream));
-    if (!direct || dir_host) CU(cudaMemcpyAsync(direct ? dir_host : p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
+    if (zc < 2) CU(cudaMemcpyAsync(direct ? obs_host : p->h_obs, p->d_obs, n * OBS_BYTES, cudaMemcpyDeviceToHost, p->stream));
+    if (!zc) {
+        CU(cudaMemcpyAsync(direct ? (void *)reward_host : (void *)p->h_rew, p->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaMemcpyAsync(direct ? done_host : p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, p->stream));
+        if (!direct || dir_host) CU(cudaMemcpyAsync(direct ? dir_host : p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
+    }
     CU(cudaStreamSynchronize(p->stream));
     if (!direct) {
         memcpy(obs_host, p->h_obs, n * OBS_BYTES);
