@@ -1188,7 +1188,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
-    p->zerocopy = 0; p->zc_level = 0; p->chk_rew = nullptr;
+    p->zerocopy = 1; p->zc_level = 0; p->chk_rew = nullptr;    // measured (profiles/r01z_zerocopy_ab.log): e2e 2.74e8 copies only, 2.97e8 level 1, 2.91e8 level 2
     if (const char *e = getenv("BB_HOST_ZEROCOPY")) p->zerocopy = atoi(e);
     p->gen_fused = 1;                                      // bb_pool_rollout on single-room levels: generator warp inside k_rollout (see bb_pool_rollout)
     if (const char *e = getenv("BB_GEN_FUSED")) p->gen_fused = atoi(e);
