@@ -1,18 +1,18 @@
 // pool.cu -- kernels and C ABI of the batched BabyAI environment pool (sm_100a).
 //
-//   k_step : one lane per environment.  Applies the action, runs the verifier,
-//            swaps in the pre-generated next level when the episode ended
-//            (ParallelEnv auto-reset, penv.py:7-11), computes the 7x7 egocentric
-//            observation, stages the 32 x 147 observation bytes of a warp in
-//            shared memory as aligned words and streams them out as 16-byte
-//            vectors; finished episodes are compacted with a warp ballot into
-//            the refill list.
-//   k_gen  : second kernel, one lane per list entry: generates the next level
-//            of an environment (RoomGridLevel._gen_grid + gen_mission +
-//            validate_instrs) from its Philox stream into the env's spare slot.
-//            Levels depend only on the env's random stream, never on actions,
-//            so generating episode k+1 while episode k is being played is
-//            equivalent to generating it at reset time.
+//   k_rollout     bb_pool_rollout (and bb_pool_step on single-room levels, T = 1): persistent over T steps, per CTA
+//                 two stepping warps (one lane per environment, state resident in shared memory) and, in fused
+//                 launches, one generator warp that refills the level rings of the CTA's environments.
+//   k_step8       bb_pool_step on multi-room levels: eight lanes per environment (one per view column).
+//   k_step, k_step_staged   lane-per-env A/B variants of the per-step kernel (BB_STEP_KERNEL).
+//   k_gen_scan, k_gen_small  level generation for single-room levels as separate passes (reset, per-step API, rooms
+//                 smaller than 6x6): one lane per environment, the warp in lock-step through one attempt per round.
+//   k_gen         level generation for every other level: one warp per level (generate_level).
+//   k_seed        env.seed().
+// Levels depend only on the env's random stream, never on actions, so generating episodes k+1 .. k+D while episode k
+// is being played is equivalent to generating them at reset time: every env owns a ring of D pre-generated levels.
+// The per-environment logic (step, verifier, observation, generators) is env_logic.cuh; DESIGN.md section 4 has the
+// measurements behind each choice.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -682,9 +682,9 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int 
 // a chain of dependent DRAM round trips and is latency-bound at 11-14 warps per SM.  Here a warp loads the
 // records of its 32 envs ONCE (coalesced), then runs T steps on them out of shared memory -- per step it
 // only reads 32 action bytes and writes the 32 observations / rewards / dones -- and stores the state
-// back at the end.  Finished envs take their next level from the ring (the host guarantees >= T levels
-// per env before the launch; k_gen refills concurrently on the side stream from a head snapshot taken
-// before the launch, so it never touches a slot this launch can consume).
+// back at the end.  Finished envs take their next level from the ring: >= T levels per env are there before
+// the launch, and whoever refills (the CTA's own generator warp, a refill pass between launches, or k_gen on the
+// side stream from a head snapshot taken before the launch) never touches a slot this launch can consume.
 constexpr int R_WARPS = 2;                    // stepping warps per CTA
 constexpr int R_THREADS = 32 * R_WARPS;       // ... and the launch adds one generator warp in fused mode (R_THREADS_FUSED)
 constexpr int R_THREADS_FUSED = R_THREADS + 32;
