@@ -243,9 +243,13 @@ def test_size_independent_properties_at_full_size():
     assert c['episodes'] >= n          # max_steps = 64 < 70: every env finished at least once
 
 
-def test_host_buffer_facades():
-    """ParallelEnv / ManyEnvs drop-ins: list-of-dict observations with mission strings."""
+@pytest.mark.parametrize('zerocopy', ['1', '0', '2'])
+def test_host_buffer_facades(monkeypatch, zerocopy):
+    """ParallelEnv / ManyEnvs drop-ins: list-of-dict observations with mission strings.  bb_pool_step_host with
+    reward / done / direction / actions over mapped page-locked memory (default), with copies only (0) and with the
+    observations over mapped memory too (2)."""
     import oracle as orc
+    monkeypatch.setenv('BB_HOST_ZEROCOPY', zerocopy)
     from babyai_b200 import ManyEnvs, ParallelEnv, make_envs
     n = 64
     envs = make_envs('GoToRedBall', n, seed=1)
