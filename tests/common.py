@@ -7,7 +7,12 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CONFIG_LEVELS = ['GoToRedBall', 'GoToLocal', 'PickupLoc', 'GoTo', 'BossLevel']
-GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))
+GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))      # all 45 served levels (CPU replays)
+# the traces the CUDA pool replays in the GPU suite (the other 26 files were added at the very end of round 1, after the
+# last GPU visit: they are replayed by the oracle and by the host build of the kernel logic; GPU replay from round 2 on)
+GOLDEN_LEVELS_GPU = ['BossLevel', 'BossLevelNoUnlock', 'GoTo', 'GoToLocal', 'GoToObjMazeS4R2', 'GoToOpen', 'GoToRedBall',
+                     'GoToRedBallGrey', 'GoToSeq', 'MiniBossLevel', 'Open', 'Pickup', 'PickupLoc', 'PutNext', 'PutNextLocal',
+                     'PutNextLocalS5N3', 'Synth', 'SynthSeq', 'UnblockPickup']
 
 
 def load_golden(level):

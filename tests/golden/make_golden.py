@@ -8,7 +8,7 @@ Per level: K traces of T steps.  Actions are 75 % reference-bot (babyai/bot.py)
 / 25 % uniform random so that episodes actually succeed and the pickup / drop /
 toggle / PutNext / Before / After paths of the verifier are exercised.
 
-usage: python tests/golden/make_golden.py
+usage: python tests/golden/make_golden.py [--only-missing]
 """
 import json
 import os
@@ -64,8 +64,19 @@ def trace(level, seed, T, act_seed):
     return dict(actions=A, obs0=obs0, dir0=dir0, obs=O, reward=R, done=D, direction=Q, missions=missions)
 
 
+# every other served level (added at the end of round 1): short traces, replayed by the CPU tests (oracle, host build of the
+# kernel logic); tests/common.py lists which files the GPU suite replays
+MORE_LEVELS = ['GoToRedBallNoDists', 'GoToObj', 'GoToObjS4', 'GoToObjS6', 'GoToLocalS5N2', 'GoToLocalS6N2', 'GoToLocalS6N3',
+               'GoToLocalS6N4', 'GoToLocalS7N4', 'GoToLocalS7N5', 'GoToLocalS8N2', 'GoToLocalS8N3', 'GoToLocalS8N4',
+               'GoToLocalS8N5', 'GoToLocalS8N6', 'GoToLocalS8N7', 'PutNextLocalS6N4', 'GoToObjMaze', 'GoToObjMazeOpen',
+               'GoToObjMazeS4', 'GoToObjMazeS5', 'GoToObjMazeS6', 'GoToObjMazeS7', 'GoToSeqS5R2', 'SynthLoc', 'SynthS5R2']
+
+
 def main():
-    for level in CONFIG_LEVELS + OTHER_LEVELS:
+    only_missing = '--only-missing' in sys.argv
+    for level in CONFIG_LEVELS + OTHER_LEVELS + MORE_LEVELS:
+        if only_missing and os.path.exists(os.path.join(HERE, level + '.npz')):
+            continue
         K, T = (4, 400) if level in CONFIG_LEVELS else (2, 300)
         if level == 'GoTo':
             T = 700

@@ -6,7 +6,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from common import CONFIG_LEVELS, GOLDEN_LEVELS, compare_pools, replay_golden  # noqa: E402
+from common import CONFIG_LEVELS, GOLDEN_LEVELS_GPU, compare_pools, replay_golden  # noqa: E402
 
 
 class GpuPool(object):
@@ -40,7 +40,7 @@ class GpuPool(object):
         return self.env.missions([i])[0]
 
 
-@pytest.mark.parametrize('level', GOLDEN_LEVELS)
+@pytest.mark.parametrize('level', GOLDEN_LEVELS_GPU)
 def test_gpu_replays_golden(level):
     replay_golden(level, lambda lv, n, s: GpuPool(lv, n, s), lambda p, i: p.mission(i))
 
