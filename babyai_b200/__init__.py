@@ -3,6 +3,7 @@ mila-iqia/babyai: MiniGridEnv.step/gen_obs, RoomGrid, RoomGridLevel, verifier,
 ParallelEnv) behind the reference's own vectorised-env surface.
 
     from babyai_b200 import BabyAIVecEnv, ParallelEnv, ManyEnvs, make_envs
+    from babyai_b200 import DeviceParallelEnv, ObssPreprocessor        # observations stay in HBM (learner.py)
 
 The compute path is the CUDA library babyai_b200/libbabyai_b200.so (C ABI in
 include/babyai_b200.h); there is no CPU fallback.
@@ -16,4 +17,7 @@ def __getattr__(name):
                 'MODE_AUTORESET', 'MODE_FREEZE'):
         from . import vecenv
         return getattr(vecenv, name)
+    if name in ('DeviceParallelEnv', 'ObssPreprocessor', 'FixedVocabulary', 'DictList', 'ObsBatch'):
+        from . import learner
+        return getattr(learner, name)
     raise AttributeError(name)

@@ -209,16 +209,35 @@ def make_envs(level, num_envs, seed=1, device=0):
     return EnvList(level, [100 * seed + i for i in range(num_envs)], device)
 
 
+def _as_env_list(envs, need_seeds):
+    """An EnvList as is.  A plain list of reference envs -- what `batch_evaluate` builds with gym.make before it
+    wraps them in ManyEnvs (evaluate.py:86-94) -- is accepted where the seeds arrive later through seed(): the level is
+    read from the reference's own class attribute (`level_name`, levelgen.py:492)."""
+    if isinstance(envs, EnvList):
+        return envs
+    if need_seeds:
+        raise TypeError('build the env list with babyai_b200.make_envs(): the seeds of gym envs cannot be read back')
+    first = envs[0]
+    first = getattr(first, 'unwrapped', first)
+    name = getattr(type(first), 'level_name', None)
+    if not isinstance(name, str):
+        raise TypeError('cannot tell the BabyAI level of %r; use babyai_b200.make_envs()' % (first,))
+    return EnvList(name, [0] * len(envs))
+
+
 class _HostVec(object):
-    def __init__(self, envs, mode):
-        assert isinstance(envs, EnvList), 'build the env list with babyai_b200.make_envs()'
+    def __init__(self, envs, mode, pool=None):
+        """`pool` is a test hook (an object with BabyAIVecEnv's host-buffer interface: the GPU-less suite passes the
+        host build of the kernel logic); the product always builds the CUDA pool."""
+        envs = _as_env_list(envs, need_seeds=(mode == MODE_AUTORESET))
         self.envs = envs
         self.observation_space, self.action_space = _spaces()
-        self.pool = BabyAIVecEnv(envs.level, len(envs), seeds=envs.seeds, device=envs.device, mode=mode)
+        self.pool = pool if pool is not None else BabyAIVecEnv(envs.level, len(envs), seeds=envs.seeds, device=envs.device, mode=mode)
         n = len(envs)
         # page-locked host buffers: bb_pool_step_host DMAs straight into them
-        self._pin = [torch.zeros((n, 7, 7, 3), dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
-                     torch.zeros(n, dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.int8).pin_memory()]
+        pin = (lambda t: t.pin_memory()) if pool is None else (lambda t: t)
+        self._pin = [pin(torch.zeros((n, 7, 7, 3), dtype=torch.uint8)), pin(torch.zeros(n, dtype=torch.float32)),
+                     pin(torch.zeros(n, dtype=torch.uint8)), pin(torch.zeros(n, dtype=torch.int8))]
         self._obs, self._rew, self._done, self._dir = [t.numpy() for t in self._pin]
         self._missions = [''] * n
 
@@ -241,8 +260,8 @@ class _HostVec(object):
 class ParallelEnv(_HostVec):
     """babyai.rl.utils.penv.ParallelEnv surface (auto-reset on done)."""
 
-    def __init__(self, envs):
-        super().__init__(envs, MODE_AUTORESET)
+    def __init__(self, envs, pool=None):
+        super().__init__(envs, MODE_AUTORESET, pool)
 
     def reset(self):
         self.pool.reset_host(self._obs, self._dir)
@@ -261,8 +280,8 @@ class ParallelEnv(_HostVec):
 class ManyEnvs(_HostVec):
     """babyai.evaluate.ManyEnvs surface (seed / reset / step; finished envs freeze)."""
 
-    def __init__(self, envs):
-        super().__init__(envs, MODE_FREEZE)
+    def __init__(self, envs, pool=None):
+        super().__init__(envs, MODE_FREEZE, pool)
 
     def seed(self, seeds):
         self.pool.seed(list(seeds))

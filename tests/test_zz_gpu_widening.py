@@ -1,0 +1,57 @@
+"""GPU tests added after the last GPU visit of round 1 (the GPU budget was spent): they sort after
+test_gpu_parity.py so that `-x` reaches them last.  Their logic is exercised in the GPU-less suite through the host
+build of the kernel source (test_hostemu.py, test_learner_adapters.py); here the CUDA pool itself is on the other end."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from common import GOLDEN_LEVELS, GOLDEN_LEVELS_GPU, replay_golden  # noqa: E402
+from test_gpu_parity import GpuPool  # noqa: E402
+
+
+@pytest.mark.parametrize('level', [lv for lv in GOLDEN_LEVELS if lv not in GOLDEN_LEVELS_GPU])
+def test_gpu_replays_remaining_golden(level):
+    """Reference-generated traces (tests/golden/make_golden.py) of the served levels test_gpu_parity.py does not replay."""
+    replay_golden(level, lambda lv, n, s: GpuPool(lv, n, s), lambda p, i: p.mission(i))
+
+
+@pytest.mark.parametrize('level,n', [('PutNextLocal', 96), ('GoToSeqS5R2', 64)])
+def test_device_parallel_env_and_preprocessor(level, n):
+    """babyai_b200.learner: observations stay in HBM between the step kernel and the learner's tensors."""
+    import torch
+    import oracle as orc
+    from babyai_b200 import DeviceParallelEnv, ObssPreprocessor, make_envs
+    from babyai_b200.levels import VOCAB
+    T = 70
+    env = DeviceParallelEnv(make_envs(level, n, seed=1))
+    o = orc.OraclePool(level, n, np.array([100 + i for i in range(n)], dtype=np.uint64))
+    pre = ObssPreprocessor()
+    obs = env.reset()
+    assert obs.image.is_cuda and np.array_equal(obs.image.cpu().numpy(), o.reset())
+    rng = np.random.RandomState(2)
+    history, images, missions = [], [], []
+    for t in range(T):
+        p = pre(obs, device='cuda')
+        assert p.image.is_cuda and p.image.dtype == torch.float32 and p.instr.dtype == torch.long
+        ms = [o.mission(i) for i in range(n)]
+        width = max(len(m.replace(',', '').split()) for m in ms)
+        want = [[VOCAB.index(w) for w in m.replace(',', '').split()] for m in ms]
+        assert p.instr.cpu().tolist() == [w + [0] * (width - len(w)) for w in want]
+        assert obs[n - 1]['mission'] == ms[n - 1] and obs[0]['direction'] == int(o.direction[0])
+        history.append(obs); images.append(p.image.clone()); missions.append(want)
+        act = rng.randint(0, 7, n)
+        obs, rew, done, info = env.step(act if t % 2 else torch.as_tensor(act, device='cuda'))
+        oo, orr, od = o.step(act.astype(np.int8))
+        assert np.array_equal(obs.image.cpu().numpy(), oo)
+        assert np.array_equal(np.asarray(rew, dtype=np.float32).view(np.uint32), orr.view(np.uint32))
+        assert np.array_equal(np.asarray(done), od.astype(bool))
+    flat = [history[i][j] for j in range(n) for i in range(T)]          # rl/algos/base.py:208-210
+    p = pre(flat, device='cuda')
+    assert p.image.shape == (n * T, 7, 7, 3)
+    want_img = torch.stack(images).transpose(0, 1).reshape(n * T, 7, 7, 3)
+    assert torch.equal(p.image, want_img)
+    width = p.instr.shape[1]
+    rows = [missions[i][j] + [0] * (width - len(missions[i][j])) for j in range(n) for i in range(T)]
+    assert p.instr.cpu().tolist() == rows
+    assert env.pool.counters()['errors'] == 0
