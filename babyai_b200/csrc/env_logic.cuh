@@ -40,7 +40,7 @@ namespace bb {
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_DOOR = 4, T_KEY = 5, T_BALL = 6, T_BOX = 7 };
 enum : int { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5 };
 enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
-enum : int { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2 };
+enum : int { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3 };
 enum : int { I_GOTO = 0, I_PICKUP = 1, I_OPEN = 2, I_PUTNEXT = 3, I_NONE = 0xFF };
 enum : int { K_ACTION = 0, K_AND = 1, K_SEQ = 2 };
 enum : int { R_SINGLE = 0, R_BEFORE = 1, R_AFTER = 2 };
@@ -430,7 +430,7 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 
 // RoomGrid.add_distractors(i=None, j=None, num, all_unique): with all_unique a (type, color) pair that was
 // already drawn is drawn again before any room / position draw
-BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o, int num, int &first_id, bool all_unique = false)
+BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o, int num, int &first_id, bool all_unique = false, int room = -1)
 {
     first_id = g.nobj;
     uint32_t seen = 0;                       // bit 6 * type_rank + color
@@ -443,10 +443,14 @@ BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o,
             if (seen & bit) continue;
             seen |= bit;
         }
-        int ri = g.rng.randint(0, lp.num_cols);
-        int rj = g.rng.randint(0, lp.num_rows);
+        int r = room;                        // add_distractors(i, j, ...): no room draws when the room is given
+        if (r < 0) {
+            int ri = g.rng.randint(0, lp.num_cols);
+            int rj = g.rng.randint(0, lp.num_rows);
+            r = rj * lp.num_cols + ri;
+        }
         int id;
-        BB_TRY(g_add_object(lp, g, o, rj * lp.num_cols + ri, type, color, id));
+        BB_TRY(g_add_object(lp, g, o, r, type, color, id));
         n++;
     }
     return GEN_OK;
@@ -668,12 +672,48 @@ BB_HD void g_single_desc(GenCtx &g, const LevelParams &lp, const LevelOut &o, in
     g.m->desc_mask[0] = g_match(lp, g, o, tc & 7, tc >> 3, LOC_NONE);
 }
 
-// gen_mission of the three level families
+// Level_GoToImpUnlock.gen_mission (iclr19_levels.py:311-355)
+BB_HD int g_mission_impunlock(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+{
+    const int id = g.rng.randint(0, lp.num_cols);
+    const int jd = g.rng.randint(0, lp.num_rows);
+    const int locked = jd * lp.num_cols + id;
+    int k;
+    do k = g.rng.randint(0, 4); while (!g_has_slot(lp, locked, k));      // add_door(door_idx=None): no door exists yet
+    const int door = g_add_door(lp, g, o, locked, k, color_by_name_rank(g.rng.randint(0, 6)), true);
+    for (;;) {                                 // the key goes to a different room
+        const int ik = g.rng.randint(0, lp.num_cols);
+        const int jk = g.rng.randint(0, lp.num_rows);
+        if (ik == id && jk == jd) continue;
+        int key;
+        BB_TRY(g_add_object(lp, g, o, jk * lp.num_cols + ik, T_KEY, g.m->obj.tc[door] >> 3, key));
+        break;
+    }
+    BB_TRY(g_connect_all(lp, g, o));
+    int first;
+    for (int i = 0; i < lp.num_cols; i++)      // columns outer, rows inner (:334-342); num_dists per unlocked room
+        for (int j = 0; j < lp.num_rows; j++)
+            if (j * lp.num_cols + i != locked) BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first, false, j * lp.num_cols + i));
+    for (;;) {
+        BB_TRY(g_place_agent(lp, g));
+        if ((g.ay / (lp.room_size - 1)) * lp.num_cols + g.ax / (lp.room_size - 1) == locked) continue;
+        break;
+    }
+    BB_TRY(g_check_reachable(lp, g));
+    BB_TRY(g_add_distractors(lp, g, o, 1, first, false, locked));        // the target, behind the locked door
+    g_single_desc(g, lp, o, I_GOTO, first);
+    return GEN_OK;
+}
+
+// gen_mission of the level families.  IMPUNLOCK selects the instantiation that only serves KIND_IMPUNLOCK, so that the code
+// generated for the other families (register allocation of generate_level inside k_gen) stays the one profiled in round 1.
+template <bool IMPUNLOCK>
 BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 {
     for (int k = 0; k < 4; k++) g.m->leaf_kind[k] = I_NONE;
     for (int k = 0; k < 8; k++) { g.m->desc_mask[k] = 0; g.m->desc_type[k] = ANY_TYPE; g.m->desc_color[k] = ANY; g.m->desc_loc[k] = LOC_NONE; }
     g.side_and = 0; g.root_kind = R_SINGLE;
+    if constexpr (IMPUNLOCK) return g_mission_impunlock(lp, g, o);
     if (lp.kind == KIND_REDBALL) {                 // iclr19_levels.py:26-37, 55-63
         int ball, first;
         BB_TRY(g_place_agent(lp, g));
@@ -773,7 +813,8 @@ BB_HD int tok_side(const GenCtx &g, int side, int16_t *tok, int n)
 // One whole RoomGridLevel.reset() worth of generation (levelgen.py:35-47,77-102):
 // retries until an attempt is accepted, then renders grid + records into `o`.
 // Returns the number of attempts.
-BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist, GenMem *mem)
+template <bool IMPUNLOCK>
+BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist, GenMem *mem)
 {
     GenCtx g;
     g.m = mem;
@@ -783,7 +824,7 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     for (;;) {
         attempts++;
         g_roomgrid(lp, g);
-        if (g_mission(lp, g, o)) continue;
+        if (g_mission<IMPUNLOCK>(lp, g, o)) continue;
         if (g_validate(lp, g, o)) continue;
         break;
     }
@@ -843,6 +884,12 @@ BB_HD_NOINLINE int generate_level(const LevelParams &lp, const LevelOut &o, RngR
     else if (g.root_kind == R_AFTER) { tok[n++] = W_AFTER; tok[n++] = W_YOU; n = tok_side(g, 1, tok, n); }
     for (int k = lane; k < lp.max_tokens; k += nlanes) o.tok[k] = k < n ? tok[k] : (int16_t)0;
     return attempts;
+}
+
+BB_HD int generate_level(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist, GenMem *mem)
+{
+    return lp.kind == KIND_IMPUNLOCK ? generate_level_t<true>(lp, o, rngrec, locked_room_persist, mem)
+                                     : generate_level_t<false>(lp, o, rngrec, locked_room_persist, mem);
 }
 
 // =============================================================================

@@ -13,7 +13,7 @@ namespace bb {
 static inline const char *make_level_params(const bb_level_spec *s, LevelParams *lp)
 {
     memset(lp, 0, sizeof *lp);
-    if (s->kind < 0 || s->kind > 2) return "bad level kind";
+    if (s->kind < 0 || s->kind > 3) return "bad level kind";
     if (s->room_size < 4 || s->room_size > 8) return "room_size must be in 4..8";
     if (s->num_rows < 1 || s->num_cols < 1 || s->num_rows * s->num_cols > MAXROOMS) return "too many rooms";
     lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
@@ -37,6 +37,10 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     lp->cells_pad = lp->gt_off + (lp->W * lp->rs_t + 15) / 16 * 16;
     lp->nav_time_maze = s->room_size * s->room_size * s->num_rows * s->num_cols;   // levelgen.py:42-43
     int max_objs = s->num_dists + (s->kind == BB_KIND_OBJ ? 0 : 1);   // + the red ball / the key of the locked room
+    if (s->kind == BB_KIND_IMPUNLOCK) {      // num_dists per unlocked room + the target in the locked room + the key
+        if (s->num_rows * s->num_cols < 2) return "GoToImpUnlock needs at least two rooms";
+        max_objs = s->num_dists * (s->num_rows * s->num_cols - 1) + 2;
+    }
     if (s->kind == BB_KIND_LEVELGEN) {
         if (s->n_action_kinds < 1 || s->n_action_kinds > 4 || s->n_instr_kinds < 1 || s->n_instr_kinds > 3)
             return "bad LevelGen kinds";

@@ -939,6 +939,9 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
 // the lanes split the grid rendering, and lane 0 commits the scalar records.
 // Work distribution: tickets of GEN_CHUNK consecutive envs from a global counter (the slowest
 // generations are a geometric tail of rejected attempts, so static assignment would wait for them).
+// IMPUNLOCK: the instantiation that serves KIND_IMPUNLOCK only (Level_GoToImpUnlock); every other level family runs
+// k_gen<false>, whose code is the kernel profiled in round 1.
+template <bool IMPUNLOCK>
 __global__ void __launch_bounds__(GEN_THREADS)
 k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
 {
@@ -971,7 +974,7 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
             int att = 0;
             for (int i = 0; i < m; i++) {
                 const LevelOut o = ring_slot(lp, P, env, (int)((t0 + (uint32_t)i) % D));
-                att += generate_level(lp, o, &r, &lr, mem);
+                att += generate_level_t<IMPUNLOCK>(lp, o, &r, &lr, mem);
                 __syncwarp();
                 if (lane == 0) P.tail[env] = t0 + (uint32_t)i + 1u;
             }
@@ -1061,7 +1064,8 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_r
         k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
         k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active);
         p->launches++;
-    } else k_gen<<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    } else if (p->lp.kind == KIND_IMPUNLOCK) k_gen<true><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    else k_gen<false><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
 
 // One generation pass on stream `st`: snapshot the consumption counters, reset the work-ticket counter,
@@ -1247,7 +1251,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_gen_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_gen_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_gen, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_gen<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_gen<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_step8<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_step8<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_step<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -67,7 +67,7 @@ enum { LOC_LEFT = 0, LOC_RIGHT = 1, LOC_FRONT = 2, LOC_BEHIND = 3 };
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
 /* level kinds */
-enum { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2 };
+enum { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3 };
 enum { I_GOTO = 0, I_PICKUP = 1, I_OPEN = 2, I_PUTNEXT = 3, I_BEFORE = 4, I_AFTER = 5, I_AND = 6 };
 enum { K_ACTION = 0, K_AND = 1, K_SEQ = 2 };
 
@@ -398,7 +398,13 @@ static int connect_all(Env *e)
 }
 
 /* RoomGrid.add_distractors(i=None, j=None, num, all_unique); ids appended to out */
+static int add_distractors_at(Env *e, int i, int j, int num, int all_unique, int *out, int *nout);
 static int add_distractors(Env *e, int num, int all_unique, int *out, int *nout)
+{
+    return add_distractors_at(e, NONE, NONE, num, all_unique, out, nout);
+}
+/* i / j == NONE: the room column / row is drawn per object */
+static int add_distractors_at(Env *e, int i, int j, int num, int all_unique, int *out, int *nout)
 {
     int seen_t[MAXOBJ * 2], seen_c[MAXOBJ * 2], nseen = 0;
     for (int r = 0; r < e->nroom; r++)
@@ -415,8 +421,8 @@ static int add_distractors(Env *e, int num, int all_unique, int *out, int *nout)
             for (int k = 0; k < nseen; k++) if (seen_t[k] == type && seen_c[k] == color) dup = 1;
             if (dup) continue;
         }
-        int ri = rand_int(e, 0, e->sp.num_cols);
-        int rj = rand_int(e, 0, e->sp.num_rows);
+        int ri = i != NONE ? i : rand_int(e, 0, e->sp.num_cols);
+        int rj = j != NONE ? j : rand_int(e, 0, e->sp.num_rows);
         int id;
         TRY(add_object(e, ri, rj, type, color, &id));
         seen_t[nseen] = type; seen_c[nseen++] = color;
@@ -821,6 +827,33 @@ static int gen_mission(Env *e)
         }
         if (sp->doors_open)   /* levelgen.py:189-199 open_all_doors */
             for (int k = 0; k < e->nobj; k++) if (e->obj[k].type == T_DOOR) e->obj[k].is_open = 1;
+        return OK;
+    }
+    if (sp->kind == KIND_IMPUNLOCK) {
+        /* iclr19_levels.py:311-355 Level_GoToImpUnlock.gen_mission; num_dists = distractors per unlocked room (2) */
+        const int id = rand_int(e, 0, sp->num_cols);
+        const int jd = rand_int(e, 0, sp->num_rows);
+        const int door = add_door(e, id, jd, NONE, NONE, 1);
+        for (;;) {                                    /* the key goes to a different room */
+            int ik = rand_int(e, 0, sp->num_cols);
+            int jk = rand_int(e, 0, sp->num_rows);
+            if (ik == id && jk == jd) continue;
+            TRY(add_object(e, ik, jk, T_KEY, e->obj[door].color, NULL));
+            break;
+        }
+        TRY(connect_all(e));
+        for (int i = 0; i < sp->num_cols; i++)        /* columns outer, rows inner (:334-342) */
+            for (int j = 0; j < sp->num_rows; j++)
+                if (i != id || j != jd) TRY(add_distractors_at(e, i, j, sp->num_dists, 0, NULL, NULL));
+        for (;;) {
+            TRY(place_agent(e));
+            if (room_index_from_pos(e, e->agent_x, e->agent_y) == jd * sp->num_cols + id) continue;
+            break;
+        }
+        TRY(check_objs_reachable(e));
+        int obj, n;
+        TRY(add_distractors_at(e, id, jd, 1, 0, &obj, &n));
+        e->root = new_node(e, I_GOTO, NONE, NONE, new_desc(e, e->obj[obj].type, e->obj[obj].color, NONE), NONE);
         return OK;
     }
     /* levelgen.py:293-319 LevelGen.gen_mission */

@@ -87,6 +87,8 @@ def soak_resets(nseeds, resets, base):
 
 if __name__ == '__main__':
     mode, nseeds, count, base = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    if len(sys.argv) > 5:                                  # optional: comma-separated subset of the served levels
+        LEVELS = {k: LEVELS[k] for k in sys.argv[5].split(',')}
     signal.signal(signal.SIGALRM, _on_alarm)
     t0 = time.time()
     bad = soak_resets(nseeds, count, base) if mode == 'reset' else soak_steps(mode, nseeds, count, base)

@@ -55,3 +55,35 @@ def test_device_parallel_env_and_preprocessor(level, n):
     rows = [missions[i][j] + [0] * (width - len(missions[i][j])) for j in range(n) for i in range(T)]
     assert p.instr.cpu().tolist() == rows
     assert env.pool.counters()['errors'] == 0
+
+
+@pytest.mark.parametrize('level,n,steps,p', [('GoToImpUnlock', 256, 300, None),
+                                              ('GoToImpUnlock', 128, 400, [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02])])
+def test_gpu_matches_oracle_new_levels(level, n, steps, p):
+    """Levels added after the last GPU visit: k_gen (one warp per level) + k_step8 against the C oracle."""
+    import oracle as orc
+    from common import compare_pools
+    seeds = np.array([100 + i for i in range(n)], dtype=np.uint64)
+    g = GpuPool(level, n, seeds)
+    compare_pools(orc.OraclePool(level, n, seeds), g, n, steps, act_seed=3, action_p=p, state=(n <= 128),
+                  mission_a=lambda q, i: q.mission(i), mission_b=lambda q, i: q.mission(i))
+    assert g.env.counters()['errors'] == 0
+
+
+def test_rollout_equals_stepwise_new_levels():
+    import torch
+    from babyai_b200 import BabyAIVecEnv
+    level, n, T = 'GoToImpUnlock', 300, 16
+    seeds = np.arange(n, dtype=np.uint64) + 77
+    a, b = BabyAIVecEnv(level, n, seeds=seeds), BabyAIVecEnv(level, n, seeds=seeds)
+    acts = torch.randint(0, 7, (T, n), device='cuda', dtype=torch.int8)
+    a.reset(); b.reset()
+    obs = torch.zeros((T, n, 7, 7, 3), dtype=torch.uint8, device='cuda')
+    rew = torch.zeros((T, n), device='cuda')
+    done = torch.zeros((T, n), dtype=torch.uint8, device='cuda')
+    for rep in range(2):
+        a.rollout(acts, obs, rew, done)
+        for t in range(T):
+            o, r, d = b.step(acts[t])
+            assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]) and torch.equal(d, done[t]), (rep, t)
+    assert a.counters()['errors'] == 0
