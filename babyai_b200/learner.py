@@ -139,6 +139,28 @@ class ObsRef(object):
         return key in self.keys()
 
 
+class _Infos(object):
+    """The per-env `info` dicts (always `{}` in BabyAI), made on demand: a tuple of N dicts per step would cost more
+    host time than the step kernel at pool sizes."""
+    __slots__ = ('n',)
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, j):
+        if isinstance(j, slice):
+            return [{} for _ in range(*j.indices(self.n))]
+        if not -self.n <= j < self.n:
+            raise IndexError(j)
+        return {}
+
+    def __iter__(self):
+        return ({} for _ in range(self.n))
+
+
 class DeviceParallelEnv(object):
     """babyai.rl.utils.penv.ParallelEnv surface; observations stay on the device.
 
@@ -180,7 +202,7 @@ class DeviceParallelEnv(object):
         done_h = done.cpu().numpy().astype(bool)
         obs = self._batch(img, bool(done_h.any()))
         # penv.py:51-52 returns zip(*per_env_results): four sequences (obs, reward, done, info)
-        return iter((obs, rew_h, done_h, tuple({} for _ in range(len(done_h)))))
+        return iter((obs, rew_h, done_h, _Infos(len(done_h))))
 
     def render(self):
         raise NotImplementedError                          # penv.py:54-55

@@ -9,7 +9,9 @@ the C ABI (include/babyai_b200.h):
                     seed(seeds), reset(), step() that freezes finished envs
   make_envs         what `[gym.make(id) ...; env.seed(100*seed+i)]` builds in
                     scripts/train_rl.py:53-60, as one list-like handle
-  preprocess_obss   device-resident stand-in for ObssPreprocessor (utils/format.py:100-119)
+  preprocess_obss   the pool's CURRENT observation as model inputs (image float, instr long);
+                    the full learner-facing adapters (per-step batches AND the flattened
+                    rollout BaseAlgo builds) are babyai_b200/learner.py
 
 PyTorch is used for device memory and streams only.
 """
@@ -301,9 +303,10 @@ class ManyEnvs(_HostVec):
 
 
 def preprocess_obss(pool):
-    """Returns a `preprocess_obss(obss, device=None)` callable for BaseAlgo
-    (rl/algos/base.py:13-14,65,134) that ignores the host obs list and hands the
-    model the pool's device tensors: image float[B,7,7,3], instr long[B,L]."""
+    """Returns a `preprocess_obss(obss, device=None)` callable that ignores its argument and hands the model the
+    pool's CURRENT device tensors: image float[B,7,7,3], instr long[B,L] -- the acting half of rl/algos/base.py:134.
+    BaseAlgo also preprocesses the flattened rollout (base.py:208-210,232): use learner.DeviceParallelEnv +
+    learner.ObssPreprocessor for the complete contract."""
     from types import SimpleNamespace
 
     def fn(obss=None, device=None):

@@ -299,6 +299,32 @@ def main():
     # ---- the only collective on this path: all-gather of the counters --------------------
     cnt = gather_counters(env.counters(), device=dev)
 
+    # ---- the learner-facing path with observations resident in HBM (babyai_b200.learner; informational) ----------
+    # per step: actions host->device, the step kernel writing into a fresh observation tensor, ObssPreprocessor handing
+    # the model image float[N,7,7,3] + instr long[N,L] on the device, reward/done device->host.  Measured on this rank.
+    learner = None
+    try:
+        from babyai_b200 import make_envs
+        from babyai_b200.learner import DeviceParallelEnv, ObssPreprocessor
+        denv = DeviceParallelEnv(make_envs(args.level, n), pool=env)
+        pre = ObssPreprocessor(trim=False)
+        ob = denv.reset()
+        Kl = min(K, 300)
+        for k in range(5):
+            pre(ob, device=dev)
+            ob, _r, _d, _i = denv.step(h_act[k])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(Kl):
+            pre(ob, device=dev)
+            ob, _r, _d, _i = denv.step(h_act[k % 64])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        learner = {'value_per_gpu': n * Kl / dt, 'unit': 'env-steps/s', 'steps': Kl, 'h2d_bytes_per_step': n,
+                   'd2h_bytes_per_step': n * 5, 'api': 'DeviceParallelEnv.step + ObssPreprocessor (observations stay in HBM)'}
+    except Exception as ex:          # informational leg: never lose the bench line over it
+        learner = {'error': repr(ex)[:300]}
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         value = world * n * K / (ms * 1e-3)
@@ -331,6 +357,7 @@ def main():
             'e2e': {'value': world * n * Ke / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n,
                     'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke,
                     'api': 'bb_pool_step_host, page-locked host buffers'},
+            'learner_path': learner,
             'gpu_launches': int(launches),
             'clocks': clocks,
             'counters': cnt,
