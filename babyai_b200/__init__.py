@@ -20,4 +20,7 @@ def __getattr__(name):
     if name in ('DeviceParallelEnv', 'ObssPreprocessor', 'FixedVocabulary', 'DictList', 'ObsBatch'):
         from . import learner
         return getattr(learner, name)
+    if name == 'gymapi':
+        import importlib
+        return importlib.import_module('.gymapi', __name__)
     raise AttributeError(name)

@@ -241,3 +241,44 @@ def test_reference_batch_evaluate_consumes_the_pool_unchanged(level):
     # reference env returns the Python double before that rounding
     assert [np.float32(x) for x in a['return_per_episode']] == [np.float32(x) for x in b['return_per_episode']]
     assert max(a['return_per_episode']) > 0 or level != 'GoToLocal'
+
+
+@pytest.mark.parametrize('level', ['GoToRedBall', 'PickupLoc'])
+def test_single_env_gym_surface(level):
+    """babyai_b200.gymapi: gym.make / seed / reset / step / spaces / actions of ONE environment (imitation.py:84,114,
+    scripts/enjoy.py:35-44), registered under the reference's ids with the shim's gym."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(orc.__file__)), 'shim'))
+    import gym
+    from babyai_b200 import gymapi
+    env = gymapi.make('BabyAI-%s-v0' % level, pool=EmuTensorPool(level, [0], mode=1))
+    assert env.action_space.n == 7 and env.observation_space.spaces['image'].shape == (7, 7, 3)
+    assert env.actions.forward == 2 and env.actions.done == 6 and env.level_name == level and env.unwrapped is env
+    o = orc.OraclePool(level, 1, np.array([4242], dtype=np.uint64))
+    assert env.seed(4242) == [4242]
+    rng = np.random.RandomState(5)
+    for episode in range(4):                              # reset() continues the random stream: next level of the seed
+        obs = env.reset()
+        assert np.array_equal(obs['image'], o.reset()[0]) and obs['mission'] == o.mission(0) == env.mission
+        assert obs['direction'] == int(o.direction[0])
+        for t in range(80):
+            a = int(rng.randint(0, 7))
+            obs, reward, done, info = env.step(a)
+            oo, orr, od = o.step(np.array([a], dtype=np.int8), autoreset=False)
+            assert np.array_equal(obs['image'], oo[0]) and np.float32(reward) == orr[0] and done == bool(od[0]) and info == {}
+            if done:
+                again = env.step(2)                       # a finished env repeats its terminal result until reset()
+                assert np.array_equal(again[0]['image'], obs['image']) and again[1] == reward and again[2] is True
+                break
+        assert done                                       # max_steps = 64
+    with pytest.raises(NotImplementedError):
+        env.render()
+    # registration under the reference's ids (levelgen.py:481-486)
+    saved = dict(gym.envs.registration.registry.env_specs)          # other tests make the REFERENCE's envs by these ids
+    try:
+        ids = gymapi.register_levels(gym)
+        assert 'BabyAI-BossLevel-v0' in ids and len(ids) == 46
+        assert gym.spec('BabyAI-%s-v0' % level).entry_point.func is gymapi.SingleEnv
+    finally:
+        gym.envs.registration.registry.env_specs.clear()
+        gym.envs.registration.registry.env_specs.update(saved)
