@@ -40,7 +40,7 @@ namespace bb {
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_DOOR = 4, T_KEY = 5, T_BALL = 6, T_BOX = 7 };
 enum : int { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5 };
 enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
-enum : int { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3 };
+enum : int { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3, KIND_UNLOCK = 4 };
 enum : int { I_GOTO = 0, I_PICKUP = 1, I_OPEN = 2, I_PUTNEXT = 3, I_NONE = 0xFF };
 enum : int { K_ACTION = 0, K_AND = 1, K_SEQ = 2 };
 enum : int { R_SINGLE = 0, R_BEFORE = 1, R_AFTER = 2 };
@@ -50,6 +50,12 @@ enum : int { ANY = 7, ANY_TYPE = 0 };   // "None" for descriptor colour / type (
 constexpr int CELL_EMPTY = T_EMPTY;                       // 0x01
 constexpr int CELL_WALL = T_WALL | (C_GREY << 3);         // 0x2A
 constexpr int NO_OBJ = 0xFF;
+// Level_Unlock places 24 distractors + a key + up to 12 doors: more than the 32-entry object table.  Its instruction
+// (open a door) only ever names doors, so only the doors are TRACKED (table entry, set-mask bit); every other object of
+// that level is UNTRACKED: it exists as its cell byte alone, and while carried as CARRY_UNTRACKED | type | color << 3 in
+// EnvHot.carry.  Only the kernels instantiated with UNTR = true (KIND_UNLOCK pools) know this encoding.
+constexpr int CARRY_UNTRACKED = 0x40;
+constexpr int MAXUNTRACKED = 32;
 constexpr int MAXOBJ = 32;
 constexpr int MAXH = 25;
 constexpr int MAXROOMS = 16;
@@ -88,7 +94,7 @@ struct LevelParams {
 struct BB_ALIGN16 EnvHot {
     uint8_t x, y;
     uint8_t dirflags;             // bits 0-1 agent_dir, bit 2 frozen (ManyEnvs flavour)
-    uint8_t carry;                // object id or NO_OBJ
+    uint8_t carry;                // object id, NO_OBJ, or (KIND_UNLOCK) CARRY_UNTRACKED | type | color << 3
     uint16_t step_count, max_steps;
     uint32_t cur_mask;            // objects currently on the grid
     uint32_t snap_mask;           // objects on the grid at the last obj_poss refresh
@@ -250,9 +256,17 @@ struct GenMem {
     ObjTab obj;                    // object table under construction (copied to the slot at the end)
 };
 
+struct GenMemX : GenMem {          // KIND_UNLOCK only: the untracked objects of the level under construction
+    uint8_t ux[MAXUNTRACKED], uy[MAXUNTRACKED], utc[MAXUNTRACKED];
+};
+
+template <bool X> struct GenMemFor { typedef GenMem type; };
+template <> struct GenMemFor<true> { typedef GenMemX type; };
+
 struct GenCtx {
     Rng rng;
     GenMem *m;
+    int nun;                          // untracked objects placed so far (KIND_UNLOCK)
     uint32_t door_right, door_down;   // bit r: a door exists in room r's right / down slot
     uint32_t room_locked;             // bit r: Room.locked
     int nobj;
@@ -282,7 +296,7 @@ BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
         uint32_t *ow = reinterpret_cast<uint32_t *>(&g.m->obj);
         for (int k = 0; k < (int)(sizeof(ObjTab) / 4); k++) ow[k] = 0;
     }
-    g.nobj = 0;
+    g.nobj = 0; g.nun = 0;
     g.ax = (C / 2) * (S - 1) + S / 2;
     g.ay = (R / 2) * (S - 1) + S / 2;
     g.adir = 0; g.agent_placed = true;
@@ -311,9 +325,19 @@ BB_HD int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_t
 }
 
 // RoomGrid.add_object -> place_in_room
-BB_HD int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id)
+BB_HD int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id, bool untracked = false)
 {
     int x, y;
+    if (untracked) {                    // KIND_UNLOCK: no table entry, the object is its cell byte (rendered by generate_level_t<true>)
+        GenMemX *mx = static_cast<GenMemX *>(g.m);
+        id = NO_OBJ;
+        BB_TRY(g_place(lp, g, room, true, x, y));
+        if (g.nun >= MAXUNTRACKED) return GEN_RECURSION;     // cannot happen: make_level_params bounds the count
+        mx->ux[g.nun] = (uint8_t)x; mx->uy[g.nun] = (uint8_t)y; mx->utc[g.nun] = (uint8_t)(type | (color << 3));
+        g.nun++;
+        g.m->occ[y] |= 1u << x;
+        return GEN_OK;
+    }
     id = g.nobj++;                      // the Python object exists even if placement then fails
     BB_TRY(g_place(lp, g, room, true, x, y));
     g.m->obj.x[id] = (uint8_t)x; g.m->obj.y[id] = (uint8_t)y; g.m->obj.tc[id] = (uint8_t)(type | (color << 3));
@@ -395,7 +419,8 @@ BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g)
 }
 
 // RoomGrid.connect_all(door_colors=COLOR_NAMES, max_itrs=5000)
-BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+// exclude >= 0: door_colors = COLOR_NAMES without that colour (Level_Unlock, iclr19_levels.py:441-446)
+BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o, int exclude = -1)
 {
     const int S = lp.room_size, C = lp.num_cols, NR = lp.num_rows * lp.num_cols;
     const int start = (g.ay / (S - 1)) * C + g.ax / (S - 1);
@@ -422,7 +447,14 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o)
         int room = j * C + i;
         if (!g_has_slot(lp, room, k) || g_has_door(lp, g, room, k)) continue;
         if (((g.room_locked >> room) & 1u) || ((g.room_locked >> g_neighbor(lp, room, k)) & 1u)) continue;
-        int color = color_by_name_rank(g.rng.randint(0, 6));
+        int color;
+        if (exclude < 0) color = color_by_name_rank(g.rng.randint(0, 6));
+        else {                               // _rand_elem over the five remaining names, in name order
+            const int pick = g.rng.randint(0, 5);
+            int rank = 0;
+            for (int c = 0, n = 0; c < 6; c++) if (color_by_name_rank(c) != exclude && n++ == pick) rank = c;
+            color = color_by_name_rank(rank);
+        }
         g_add_door(lp, g, o, room, k, color, false);
     }
     return GEN_OK;
@@ -430,7 +462,7 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 
 // RoomGrid.add_distractors(i=None, j=None, num, all_unique): with all_unique a (type, color) pair that was
 // already drawn is drawn again before any room / position draw
-BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o, int num, int &first_id, bool all_unique = false, int room = -1)
+BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o, int num, int &first_id, bool all_unique = false, int room = -1, bool untracked = false)
 {
     first_id = g.nobj;
     uint32_t seen = 0;                       // bit 6 * type_rank + color
@@ -450,7 +482,7 @@ BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o,
             r = rj * lp.num_cols + ri;
         }
         int id;
-        BB_TRY(g_add_object(lp, g, o, r, type, color, id));
+        BB_TRY(g_add_object(lp, g, o, r, type, color, id, untracked));
         n++;
     }
     return GEN_OK;
@@ -705,6 +737,41 @@ BB_HD int g_mission_impunlock(const LevelParams &lp, GenCtx &g, const LevelOut &
     return GEN_OK;
 }
 
+// Level_Unlock.gen_mission (iclr19_levels.py:418-474); only the doors are tracked objects (see CARRY_UNTRACKED)
+BB_HD int g_mission_unlock(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+{
+    const int id = g.rng.randint(0, lp.num_cols);
+    const int jd = g.rng.randint(0, lp.num_rows);
+    const int locked = jd * lp.num_cols + id;
+    int k;
+    do k = g.rng.randint(0, 4); while (!g_has_slot(lp, locked, k));
+    const int door = g_add_door(lp, g, o, locked, k, color_by_name_rank(g.rng.randint(0, 6)), true);
+    const int door_color = g.m->obj.tc[door] >> 3;
+    for (;;) {
+        const int ik = g.rng.randint(0, lp.num_cols);
+        const int jk = g.rng.randint(0, lp.num_rows);
+        if (ik == id && jk == jd) continue;
+        int key;
+        BB_TRY(g_add_object(lp, g, o, jk * lp.num_cols + ik, T_KEY, door_color, key, true));
+        break;
+    }
+    // with probability 1/2 the locked door is the only door of its colour (_rand_bool: randint(0, 2) == 0)
+    if (g.rng.randint(0, 2) == 0) BB_TRY(g_connect_all(lp, g, o, door_color));
+    else BB_TRY(g_connect_all(lp, g, o));
+    int first;
+    for (int i = 0; i < lp.num_cols; i++)
+        for (int j = 0; j < lp.num_rows; j++)
+            if (j * lp.num_cols + i != locked) BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first, false, j * lp.num_cols + i, true));
+    for (;;) {
+        BB_TRY(g_place_agent(lp, g));
+        if ((g.ay / (lp.room_size - 1)) * lp.num_cols + g.ax / (lp.room_size - 1) == locked) continue;
+        break;
+    }
+    BB_TRY(g_check_reachable(lp, g));
+    g_single_desc(g, lp, o, I_OPEN, door);
+    return GEN_OK;
+}
+
 // gen_mission of the level families.  IMPUNLOCK selects the instantiation that only serves KIND_IMPUNLOCK, so that the code
 // generated for the other families (register allocation of generate_level inside k_gen) stays the one profiled in round 1.
 template <bool IMPUNLOCK>
@@ -713,7 +780,7 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
     for (int k = 0; k < 4; k++) g.m->leaf_kind[k] = I_NONE;
     for (int k = 0; k < 8; k++) { g.m->desc_mask[k] = 0; g.m->desc_type[k] = ANY_TYPE; g.m->desc_color[k] = ANY; g.m->desc_loc[k] = LOC_NONE; }
     g.side_and = 0; g.root_kind = R_SINGLE;
-    if constexpr (IMPUNLOCK) return g_mission_impunlock(lp, g, o);
+    if constexpr (IMPUNLOCK) return lp.kind == KIND_UNLOCK ? g_mission_unlock(lp, g, o) : g_mission_impunlock(lp, g, o);
     if (lp.kind == KIND_REDBALL) {                 // iclr19_levels.py:26-37, 55-63
         int ball, first;
         BB_TRY(g_place_agent(lp, g));
@@ -855,6 +922,10 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
         if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (k == g.locked_door ? 2 : 1);   // open_all_doors levelgen.py:189-199
         set_cell(lp, o.grid, g.m->obj.x[k], g.m->obj.y[k], tc | (st << 6));
     }
+    if constexpr (IMPUNLOCK) {            // KIND_UNLOCK: the untracked objects are their cell bytes
+        const GenMemX *mx = static_cast<const GenMemX *>(g.m);
+        for (int k = 0; k < g.nun; k++) set_cell(lp, o.grid, mx->ux[k], mx->uy[k], mx->utc[k]);
+    }
     // object table: working copy -> slot
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&g.m->obj);
@@ -888,8 +959,8 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
 
 BB_HD int generate_level(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist, GenMem *mem)
 {
-    return lp.kind == KIND_IMPUNLOCK ? generate_level_t<true>(lp, o, rngrec, locked_room_persist, mem)
-                                     : generate_level_t<false>(lp, o, rngrec, locked_room_persist, mem);
+    return (lp.kind == KIND_IMPUNLOCK || lp.kind == KIND_UNLOCK) ? generate_level_t<true>(lp, o, rngrec, locked_room_persist, mem)
+                                                                 : generate_level_t<false>(lp, o, rngrec, locked_room_persist, mem);
 }
 
 // =============================================================================
@@ -1346,7 +1417,8 @@ struct StepResult { bool done; bool success; float reward; };
 
 // Applies one action to the live state of one env.  `h` is the env's hot record
 // held in registers by the caller (written back by the caller).
-template <class M>
+// UNTR: the pool serves KIND_UNLOCK, whose non-door objects are untracked (CARRY_UNTRACKED)
+template <bool UNTR = false, class M>
 BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
 {
     int x = h.x, y = h.y, dir = h.dirflags & 3, carry = h.carry;
@@ -1361,9 +1433,20 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
         if (ftype >= T_KEY && carry == NO_OBJ) {
             int id = find_obj_at(mem, h.cur_mask, fx, fy);
             if (id != NO_OBJ) { carry = id; h.cur_mask &= ~(1u << id); mem.set_cell(fx, fy, CELL_EMPTY); }
+            else if constexpr (UNTR) { carry = CARRY_UNTRACKED | (fc & 0x3F); mem.set_cell(fx, fy, CELL_EMPTY); }
         }
     } else if (action == A_DROP) {
-        if (fc == CELL_EMPTY && carry != NO_OBJ) {
+        if constexpr (UNTR) {
+            if (fc == CELL_EMPTY && carry != NO_OBJ) {
+                if (carry & CARRY_UNTRACKED) mem.set_cell(fx, fy, carry & 0x3F);
+                else {
+                    mem.set_cell(fx, fy, mem.otc(carry));
+                    mem.set_oxy(carry, fx, fy);
+                    h.cur_mask |= 1u << carry;
+                }
+                carry = NO_OBJ;
+            }
+        } else if (fc == CELL_EMPTY && carry != NO_OBJ) {
             mem.set_cell(fx, fy, mem.otc(carry));
             mem.set_oxy(carry, fx, fy);
             h.cur_mask |= 1u << carry;
@@ -1373,7 +1456,12 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
         if (ftype == T_DOOR) {
             int st = fc >> 6, ns = st;
             if (st == 2) {           // locked: needs a carried key of the door's colour; key stays in hand
-                if (carry != NO_OBJ && (mem.otc(carry) & 7) == T_KEY && (mem.otc(carry) >> 3) == ((fc >> 3) & 7)) ns = 0;
+                if constexpr (UNTR) {
+                    if (carry != NO_OBJ) {
+                        const int ctc = (carry & CARRY_UNTRACKED) ? (carry & 0x3F) : mem.otc(carry);
+                        if ((ctc & 7) == T_KEY && (ctc >> 3) == ((fc >> 3) & 7)) ns = 0;
+                    }
+                } else if (carry != NO_OBJ && (mem.otc(carry) & 7) == T_KEY && (mem.otc(carry) >> 3) == ((fc >> 3) & 7)) ns = 0;
             } else ns = st ^ 1;
             if (ns != st) mem.set_cell(fx, fy, (fc & 0x3F) | (ns << 6));
         } else if (ftype == T_BOX) {  // Box.toggle: replaced by its contents (None)
@@ -1721,8 +1809,12 @@ BB_HD void observe_simple(const LevelParams &lp, const uint8_t *grid, int ax, in
         }
 }
 
-template <class M>
-BB_HD int carry_cell_of(const EnvHot &h, const M &mem) { return h.carry == NO_OBJ ? CELL_EMPTY : mem.otc(h.carry); }
+template <bool UNTR = false, class M>
+BB_HD int carry_cell_of(const EnvHot &h, const M &mem)
+{
+    if constexpr (UNTR) { if (h.carry != NO_OBJ && (h.carry & CARRY_UNTRACKED)) return h.carry & 0x3F; }
+    return h.carry == NO_OBJ ? CELL_EMPTY : mem.otc(h.carry);
+}
 
 // ---- staging of 32 observations of a warp as aligned words ----------------------
 // Lane l owns bytes [147 l, 147 l + 147) of the 4704-byte warp tile; 147 is not a

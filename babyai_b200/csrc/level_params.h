@@ -13,7 +13,7 @@ namespace bb {
 static inline const char *make_level_params(const bb_level_spec *s, LevelParams *lp)
 {
     memset(lp, 0, sizeof *lp);
-    if (s->kind < 0 || s->kind > 3) return "bad level kind";
+    if (s->kind < 0 || s->kind > 4) return "bad level kind";
     if (s->room_size < 4 || s->room_size > 8) return "room_size must be in 4..8";
     if (s->num_rows < 1 || s->num_cols < 1 || s->num_rows * s->num_cols > MAXROOMS) return "too many rooms";
     lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
@@ -40,6 +40,11 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     if (s->kind == BB_KIND_IMPUNLOCK) {      // num_dists per unlocked room + the target in the locked room + the key
         if (s->num_rows * s->num_cols < 2) return "GoToImpUnlock needs at least two rooms";
         max_objs = s->num_dists * (s->num_rows * s->num_cols - 1) + 2;
+    }
+    if (s->kind == BB_KIND_UNLOCK) {         // only the doors are table objects; the key and the distractors are untracked
+        if (s->num_rows * s->num_cols < 2) return "Unlock needs at least two rooms";
+        if (s->num_dists * (s->num_rows * s->num_cols - 1) + 1 > MAXUNTRACKED) return "too many untracked objects";
+        max_objs = 0;
     }
     if (s->kind == BB_KIND_LEVELGEN) {
         if (s->n_action_kinds < 1 || s->n_action_kinds > 4 || s->n_instr_kinds < 1 || s->n_instr_kinds > 3)

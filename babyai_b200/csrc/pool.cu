@@ -401,7 +401,9 @@ __device__ __forceinline__ void swap_in8(const LevelParams &lp, const PoolPtrs &
     for (int i = r; i < lp.max_tokens / 8; i += 8) lt[i] = __ldcg(st + i);
 }
 
-template <int ACT_BYTES>
+// UNTR: KIND_UNLOCK pools (objects without a table entry, env_logic.cuh CARRY_UNTRACKED); every other level runs the
+// UNTR = false instantiations, whose code is the one profiled in round 1
+template <int ACT_BYTES, bool UNTR = false>
 __global__ void __launch_bounds__(S8_THREADS)
 k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
         float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
@@ -447,7 +449,7 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
     float rew = 0.0f; bool dn = false;
     if (valid && r == 0 && !force_reset) {                        // the group's leader steps the env
         if (!(h.dirflags & 4)) {
-            const StepResult sr = step_env(h, mem, a);
+            const StepResult sr = step_env<UNTR>(h, mem, a);
             rew = sr.reward; dn = sr.done;
             stepped = true; ended = dn; succeeded = sr.success;
             if (dn) {
@@ -494,7 +496,7 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
     uint32_t cv = 0;
 #pragma unroll
     for (int j = 0; j < 7; j++) cv |= ((vis[j] >> r) & 1u) << j;
-    if (r == 3 && valid) hi = (hi & 0xFF00FFFFu) | ((uint32_t)carry_cell_of(h, mem) << 16);   // own cell: what it carries
+    if (r == 3 && valid) hi = (hi & 0xFF00FFFFu) | ((uint32_t)carry_cell_of<UNTR>(h, mem) << 16);   // own cell: what it carries
     uint32_t o[6];
     col_encode(lo, hi, (valid && r < 7) ? cv : 0u, o);
     // ---- stage 28 records of 21 bytes, then coalesced stores ------------------------------------
@@ -729,7 +731,7 @@ __device__ __forceinline__ void warp_copy_records(uint32_t *sm, int stride_words
     }
 }
 
-template <int ACT_BYTES>
+template <int ACT_BYTES, bool UNTR = false>
 __global__ void __launch_bounds__(R_THREADS_FUSED, 7)
 k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions_v, uint8_t *__restrict__ obs,
           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
@@ -847,7 +849,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
             float rew = 0.0f; bool dn = false, begin = force_reset != 0;
             if (force_reset) {
             } else if (!(h.dirflags & 4)) {
-                const StepResult sr = step_env(h, mem, a);
+                const StepResult sr = step_env<UNTR>(h, mem, a);
                 rew = sr.reward; dn = sr.done;
                 n_step++; n_end += dn; n_succ += sr.success;
                 if (dn) {
@@ -894,7 +896,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(o.hot));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(o.tok));
             }
-            observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of(h, mem), w);
+            observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of<UNTR>(h, mem), w);
             const size_t oi = (size_t)t * n + env;
             if (reward) reward[oi] = rew;
             if (done) done[oi] = dn ? 1 : 0;
@@ -945,7 +947,7 @@ template <bool IMPUNLOCK>
 __global__ void __launch_bounds__(GEN_THREADS)
 k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
 {
-    __shared__ GenMem gen_mem[GEN_THREADS / 32];
+    __shared__ typename GenMemFor<IMPUNLOCK>::type gen_mem[GEN_THREADS / 32];     // GenMemX (untracked objects) for k_gen<true>
     GenMem *mem = &gen_mem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t nchunks = (uint32_t)((n + GEN_CHUNK - 1) / GEN_CHUNK);
@@ -1064,7 +1066,7 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_r
         k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
         k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active);
         p->launches++;
-    } else if (p->lp.kind == KIND_IMPUNLOCK) k_gen<true><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    } else if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK) k_gen<true><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
     else k_gen<false><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
 
@@ -1087,6 +1089,7 @@ static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8
     const int blocks8 = (p->n + 4 * S8_WARPS - 1) / (4 * S8_WARPS);
     int kernel = p->step_kernel;
     if ((kernel == 2 || kernel == 3) && p->lp.cells_pad > 128) kernel = kernel == 3 ? 0 : 1;
+    if (p->lp.kind == KIND_UNLOCK) kernel = 0;          // untracked objects: only k_step8 / k_rollout have UNTR instantiations
     if (kernel == 3) {                   // small grids: the persistent kernel with T = 1 (coalesced state load / store)
         const int gs = (p->lp.cells_pad >> 2) | 1;
         const size_t smem = (size_t)R_WARPS * (32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS) * 4;
@@ -1103,7 +1106,11 @@ static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8
     } while (0)
     if (kernel == 0) {
         const size_t sm8 = (size_t)S8_WARPS * 4 * (p->lp.cells_pad + S8_REC_FIXED) + (size_t)S8_WARPS * (S8_TILE_WORDS + 1) * 4;
-        if (action_bytes == 8) k_step8<8><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+        if (p->lp.kind == KIND_UNLOCK) {
+            if (action_bytes == 8) k_step8<8, true><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+            else k_step8<1, true><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+        }
+        else if (action_bytes == 8) k_step8<8><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
         else k_step8<1><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
     }
     else if (kernel == 2) BB_LAUNCH(k_step_staged, p->step_blocks, STEP_THREADS);
@@ -1245,6 +1252,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     }
     CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
     // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
     CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1255,6 +1263,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CU(cudaFuncSetAttribute(k_gen<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_step8<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_step8<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_step8<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_step8<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_step<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -1433,6 +1444,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
     if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
                                                                                        p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
+    else if (p->lp.kind == KIND_UNLOCK) k_rollout<1, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
     else k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
     if (dbg_timing) { cudaEventRecord(dbg_ev[1], user); p->tev_kernel = true; }
     p->launches++;
@@ -1613,7 +1625,7 @@ int bb_pool_get_state(bb_pool *p, int32_t env, uint8_t *grid_host, int32_t *info
     CU(cudaMemcpy(&r, p->P.rng + env, sizeof r, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&att, p->P.attempts + env, sizeof att, cudaMemcpyDeviceToHost));
     info[0] = h.x; info[1] = h.y; info[2] = h.dirflags & 3;
-    info[3] = h.carry == NO_OBJ ? 0 : ot.tc[h.carry];
+    info[3] = h.carry == NO_OBJ ? 0 : (p->lp.kind == KIND_UNLOCK && (h.carry & CARRY_UNTRACKED)) ? (h.carry & 0x3F) : ot.tc[h.carry];
     info[4] = h.step_count; info[5] = h.max_steps;
     info[6] = (int32_t)(r.draws & 0x7FFFFFFF); info[7] = (int32_t)att;
     return 0;

@@ -2,20 +2,20 @@
 level class, as a `bb_level_spec` (include/babyai_b200.h).
 
 Each entry cites the class in /root/reference/babyai/levels/iclr19_levels.py it
-mirrors.  Four generator families cover 46 of the 47 ICLR-19 levels (all but Unlock, whose 24 distractors + key +
-up to 12 doors exceed the 32-entry object table):
+mirrors.  Five generator families cover all 47 ICLR-19 levels:
   REDBALL  : Level_GoToRedBall* (:10-72)
   OBJ      : place_agent, connect_all, add_distractors, check_objs_reachable,
              pick one (or a door, or two), GoTo / Pickup / Open / PutNext it -- Level_GoToObj* (:75-102),
              Level_GoToLocal* (:105-184), Level_PutNextLocal* (:187-221), Level_GoTo* (:224-301),
              Level_Pickup (:360-371), Level_UnblockPickup (:374-391), Level_Open (:394-415), Level_PutNext (:477-491)
   IMPUNLOCK: Level_GoToImpUnlock (:304-355)
+  UNLOCK   : Level_Unlock (:418-474) -- 37 objects: only the doors are table objects, the rest are untracked cell bytes
   LEVELGEN : levelgen.py:256-460 LevelGen -- PickupLoc (:494), GoToSeq (:518), Synth*
              (:554-633), MiniBossLevel (:636), BossLevel (:648), BossLevelNoUnlock (:655)
 """
 import ctypes as C
 
-KIND_REDBALL, KIND_OBJ, KIND_LEVELGEN, KIND_IMPUNLOCK = 0, 1, 2, 3
+KIND_REDBALL, KIND_OBJ, KIND_LEVELGEN, KIND_IMPUNLOCK, KIND_UNLOCK = 0, 1, 2, 3, 4
 I_GOTO, I_PICKUP, I_OPEN, I_PUTNEXT = 0, 1, 2, 3
 K_ACTION, K_AND, K_SEQ = 0, 1, 2
 
@@ -109,6 +109,7 @@ LEVELS = {
     'PutNextLocalS5N3': lambda: obj_level(5, 1, 1, 3, instr=I_PUTNEXT, all_unique=1),
     'PutNextLocalS6N4': lambda: obj_level(6, 1, 1, 4, instr=I_PUTNEXT, all_unique=1),
     'GoToImpUnlock': lambda: _spec(KIND_IMPUNLOCK, 8, 3, 3, num_dists=2),
+    'Unlock': lambda: _spec(KIND_UNLOCK, 8, 3, 3, num_dists=3),
     'PickupLoc': lambda: levelgen(num_rows=1, num_cols=1, num_dists=8, locked_room_prob=0, locations=1, unblocking=0,
                                   action_kinds=(I_PICKUP,), instr_kinds=(K_ACTION,)),
     'GoToSeq': lambda: levelgen(action_kinds=(I_GOTO,), locked_room_prob=0, locations=0, unblocking=0),

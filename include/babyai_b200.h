@@ -34,6 +34,7 @@ extern "C" {
 #define BB_KIND_OBJ 1             /* iclr19_levels.py:75-301,360-415,477-491 GoToObj/GoToLocal/PutNextLocal/GoTo/Pickup/UnblockPickup/Open/PutNext */
 #define BB_KIND_LEVELGEN 2        /* levelgen.py:256-460 LevelGen (PickupLoc .. BossLevel) */
 #define BB_KIND_IMPUNLOCK 3       /* iclr19_levels.py:304-355 GoToImpUnlock; num_dists = distractors per unlocked room */
+#define BB_KIND_UNLOCK 4          /* iclr19_levels.py:418-474 Unlock;        num_dists = distractors per unlocked room */
 /* instruction / action kinds (verifier.py) */
 #define BB_I_GOTO 0
 #define BB_I_PICKUP 1

@@ -67,7 +67,7 @@ enum { LOC_LEFT = 0, LOC_RIGHT = 1, LOC_FRONT = 2, LOC_BEHIND = 3 };
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
 /* level kinds */
-enum { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3 };
+enum { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3, KIND_UNLOCK = 4 };
 enum { I_GOTO = 0, I_PICKUP = 1, I_OPEN = 2, I_PUTNEXT = 3, I_BEFORE = 4, I_AFTER = 5, I_AND = 6 };
 enum { K_ACTION = 0, K_AND = 1, K_SEQ = 2 };
 
@@ -367,7 +367,10 @@ static int place_agent(Env *e)
 }
 
 /* RoomGrid.connect_all(door_colors=COLOR_NAMES, max_itrs=5000) */
-static int connect_all(Env *e)
+static int connect_all_colors(Env *e, int exclude_color);
+static int connect_all(Env *e) { return connect_all_colors(e, NONE); }
+/* connect_all(door_colors=[c for c in COLOR_NAMES if c is not exclude_color]) (iclr19_levels.py:441-446) */
+static int connect_all_colors(Env *e, int exclude_color)
 {
     int start = room_index_from_pos(e, e->agent_x, e->agent_y);
     int num_itrs = 0;
@@ -391,7 +394,12 @@ static int connect_all(Env *e)
         Room *r = get_room(e, i, j);
         if (!r->has_pos[k] || r->doors[k] != NONE) continue;
         if (r->locked || e->room[r->neighbors[k]].locked) continue;
-        int color = COLOR_NAMES[rand_int(e, 0, 6)];
+        int color;
+        if (exclude_color == NONE) color = COLOR_NAMES[rand_int(e, 0, 6)];
+        else {                                  /* _rand_elem over the five remaining names, same order */
+            int pick = rand_int(e, 0, 5);
+            for (int c = 0, n = 0; ; c++) if (COLOR_NAMES[c] != exclude_color && n++ == pick) { color = COLOR_NAMES[c]; break; }
+        }
         add_door(e, i, j, k, color, 0);
     }
     return OK;
@@ -827,6 +835,33 @@ static int gen_mission(Env *e)
         }
         if (sp->doors_open)   /* levelgen.py:189-199 open_all_doors */
             for (int k = 0; k < e->nobj; k++) if (e->obj[k].type == T_DOOR) e->obj[k].is_open = 1;
+        return OK;
+    }
+    if (sp->kind == KIND_UNLOCK) {
+        /* iclr19_levels.py:418-474 Level_Unlock.gen_mission; num_dists = distractors per unlocked room (3) */
+        const int id = rand_int(e, 0, sp->num_cols);
+        const int jd = rand_int(e, 0, sp->num_rows);
+        const int door = add_door(e, id, jd, NONE, NONE, 1);
+        for (;;) {
+            int ik = rand_int(e, 0, sp->num_cols);
+            int jk = rand_int(e, 0, sp->num_rows);
+            if (ik == id && jk == jd) continue;
+            TRY(add_object(e, ik, jk, T_KEY, e->obj[door].color, NULL));
+            break;
+        }
+        /* with probability 1/2 the locked door is the only door of its colour */
+        if (rand_bool(e)) TRY(connect_all_colors(e, e->obj[door].color));
+        else TRY(connect_all(e));
+        for (int i = 0; i < sp->num_cols; i++)
+            for (int j = 0; j < sp->num_rows; j++)
+                if (i != id || j != jd) TRY(add_distractors_at(e, i, j, sp->num_dists, 0, NULL, NULL));
+        for (;;) {
+            TRY(place_agent(e));
+            if (room_index_from_pos(e, e->agent_x, e->agent_y) == jd * sp->num_cols + id) continue;
+            break;
+        }
+        TRY(check_objs_reachable(e));
+        e->root = new_node(e, I_OPEN, NONE, NONE, new_desc(e, T_DOOR, e->obj[door].color, NONE), NONE);
         return OK;
     }
     if (sp->kind == KIND_IMPUNLOCK) {

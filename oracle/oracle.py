@@ -15,7 +15,7 @@ if HERE not in sys.path:
     sys.path.insert(0, HERE)
 import build as _build  # noqa: E402
 
-KIND_REDBALL, KIND_OBJ, KIND_LEVELGEN, KIND_IMPUNLOCK = 0, 1, 2, 3
+KIND_REDBALL, KIND_OBJ, KIND_LEVELGEN, KIND_IMPUNLOCK, KIND_UNLOCK = 0, 1, 2, 3, 4
 I_GOTO, I_PICKUP, I_OPEN, I_PUTNEXT = 0, 1, 2, 3
 K_ACTION, K_AND, K_SEQ = 0, 1, 2
 
@@ -72,6 +72,7 @@ LEVELS = {
     'PutNextLocal': _obj(8, 1, 1, 8, instr=I_PUTNEXT, all_unique=1),                # :187-211
     'PutNextLocalS5N3': _obj(5, 1, 1, 3, instr=I_PUTNEXT, all_unique=1),
     'PutNextLocalS6N4': _obj(6, 1, 1, 4, instr=I_PUTNEXT, all_unique=1),
+    'Unlock': dict(kind=KIND_UNLOCK, room_size=8, num_rows=3, num_cols=3, num_dists=3),          # :418-474
     'GoToImpUnlock': dict(kind=KIND_IMPUNLOCK, room_size=8, num_rows=3, num_cols=3, num_dists=2),   # :304-355
     'PickupLoc': _levelgen(rows=1, cols=1, num_dists=8, locked_room_prob=0, locations=1, unblocking=0,
                            action_kinds=(I_PICKUP,), instr_kinds=(K_ACTION,)),      # :494-515

@@ -70,7 +70,7 @@ MORE_LEVELS = ['GoToRedBallNoDists', 'GoToObj', 'GoToObjS4', 'GoToObjS6', 'GoToL
                'GoToLocalS6N4', 'GoToLocalS7N4', 'GoToLocalS7N5', 'GoToLocalS8N2', 'GoToLocalS8N3', 'GoToLocalS8N4',
                'GoToLocalS8N5', 'GoToLocalS8N6', 'GoToLocalS8N7', 'PutNextLocalS6N4', 'GoToObjMaze', 'GoToObjMazeOpen',
                'GoToObjMazeS4', 'GoToObjMazeS5', 'GoToObjMazeS6', 'GoToObjMazeS7', 'GoToSeqS5R2', 'SynthLoc', 'SynthS5R2',
-               'GoToImpUnlock']
+               'GoToImpUnlock', 'Unlock']
 
 
 def main():
@@ -83,7 +83,7 @@ def main():
             T = 700
         if level == 'BossLevel':
             K, T = 6, 1500
-        if level in ('SynthSeq', 'MiniBossLevel', 'BossLevelNoUnlock', 'Open', 'PutNext', 'UnblockPickup', 'GoToImpUnlock'):
+        if level in ('SynthSeq', 'MiniBossLevel', 'BossLevelNoUnlock', 'Open', 'PutNext', 'UnblockPickup', 'GoToImpUnlock', 'Unlock'):
             K, T = 3, 800
         seeds = [1000 + 17 * k for k in range(K)]
         tr = [trace(level, s, T, act_seed=k) for k, s in enumerate(seeds)]

@@ -55,7 +55,7 @@ static void gen_spare(HPool *p, int e)
         // cross-check with the nested-loop generator from the same stream position
         Slot ref = s; ref.grid.assign(s.grid.size(), 0);
         LevelOut oref; oref.grid = ref.grid.data(); oref.hot = &ref.hot; oref.obj = &ref.obj; oref.ins = &ref.ins; oref.tok = ref.tok.data();
-        GenMem mem; uint8_t lr = p->locked_room[e]; RngRec r1 = r0;
+        GenMemX mem; uint8_t lr = p->locked_room[e]; RngRec r1 = r0;
         int att2 = generate_level(p->lp, oref, &r1, &lr, &mem);
         if (att != att2 || r1.draws != rng.draws || !records_equal(p->lp, s, ref)) {
             fprintf(stderr, "hostemu: generate_small != generate_level (env %d: attempts %d/%d draws %llu/%llu)\n", e, att, att2,
@@ -65,10 +65,16 @@ static void gen_spare(HPool *p, int e)
         p->rng[e].draws = rng.draws;
         p->attempts[e] += (uint32_t)att;
     } else {
-        GenMem mem;
+        GenMemX mem;
         p->attempts[e] += (uint32_t)generate_level(p->lp, o, &p->rng[e], &p->locked_room[e], &mem);
     }
     p->sready[e] = 1;
+}
+
+// KIND_UNLOCK pools run the UNTR = true instantiations, as pool.cu does
+static int carry_cell(const HPool *p, const EnvHot &h, const GlobalMem &mem)
+{
+    return p->lp.kind == KIND_UNLOCK ? carry_cell_of<true>(h, mem) : carry_cell_of(h, mem);
 }
 
 static void obs_of(HPool *p, int e, uint8_t *out)
@@ -76,7 +82,7 @@ static void obs_of(HPool *p, int e, uint8_t *out)
     Slot &s = p->live[e];
     uint32_t w[OBS_WORDS];
     GlobalMem mem(p->lp, s.grid.data(), &s.obj, &s.ins);
-    observe(p->lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), w);
+    observe(p->lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell(p, s.hot, mem), w);
     memcpy(out, w, OBS_BYTES);
 }
 
@@ -119,7 +125,7 @@ void he_step(HPool *p, const int8_t *actions, uint8_t *obs, float *reward, uint8
         float rew = 0; bool dn = false;
         if (!(s.hot.dirflags & 4)) {
             GlobalMem mem(p->lp, s.grid.data(), &s.obj, &s.ins);
-            StepResult r = step_env(s.hot, mem, actions[e]);
+            StepResult r = p->lp.kind == KIND_UNLOCK ? step_env<true>(s.hot, mem, actions[e]) : step_env(s.hot, mem, actions[e]);
             rew = r.reward; dn = r.done;
             if (dn) {
                 if (p->mode == BB_MODE_AUTORESET) { p->live[e] = p->spare[e]; p->sready[e] = 0; gen_spare(p, e); }
@@ -142,15 +148,15 @@ void he_get_state(HPool *p, int e, uint8_t *grid, int32_t *info)
     {   // and the SWAR observation must equal the cell-by-cell one
         uint32_t w[OBS_WORDS]; uint8_t simple[OBS_BYTES];
         GlobalMem mem(lp, s.grid.data(), &s.obj, &s.ins);
-        observe(lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), w);
-        observe_simple(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), simple);
+        observe(lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell(p, s.hot, mem), w);
+        observe_simple(lp, s.grid.data(), s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell(p, s.hot, mem), simple);
         if (memcmp(w, simple, OBS_BYTES) != 0) { fprintf(stderr, "hostemu: observe != observe_simple\n"); abort(); }
         uint8_t cols[OBS_BYTES];
-        observe_columns(lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell_of(s.hot, mem), cols);
+        observe_columns(lp, mem, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell(p, s.hot, mem), cols);
         if (memcmp(cols, simple, OBS_BYTES) != 0) { fprintf(stderr, "hostemu: observe_columns != observe_simple\n"); abort(); }
     }
     info[0] = s.hot.x; info[1] = s.hot.y; info[2] = s.hot.dirflags & 3;
-    info[3] = s.hot.carry == NO_OBJ ? 0 : s.obj.tc[s.hot.carry];
+    info[3] = s.hot.carry == NO_OBJ ? 0 : (lp.kind == KIND_UNLOCK && (s.hot.carry & CARRY_UNTRACKED)) ? (s.hot.carry & 0x3F) : s.obj.tc[s.hot.carry];
     info[4] = s.hot.step_count; info[5] = s.hot.max_steps;
     info[6] = (int32_t)(p->rng[e].draws & 0x7FFFFFFF); info[7] = (int32_t)p->attempts[e];
 }

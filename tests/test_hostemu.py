@@ -31,7 +31,7 @@ def test_emu_matches_oracle_random_actions(level):
                   mission_a=lambda p, i: p.mission(i), mission_b=lambda p, i: detokenize(p.tokens(i)))
 
 
-@pytest.mark.parametrize('level', ['PickupLoc', 'PutNextLocal', 'PutNextLocalS5N3', 'Synth', 'MiniBossLevel', 'Open', 'BossLevel', 'GoToImpUnlock'])
+@pytest.mark.parametrize('level', ['PickupLoc', 'PutNextLocal', 'PutNextLocalS5N3', 'Synth', 'MiniBossLevel', 'Open', 'BossLevel', 'GoToImpUnlock', 'Unlock'])
 def test_emu_matches_oracle_interaction_heavy_actions(level):
     """Actions biased towards forward / pickup / drop / toggle so that objects are carried around, boxes opened,
     doors toggled and the obj_poss snapshots go stale and get refreshed (verifier.py:195-202, levelgen.py:53-54)."""
@@ -67,7 +67,7 @@ def test_unsatisfiable_agent_room_is_rejected_not_spun_on():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize('level', ['MiniBossLevel', 'GoToObjMazeS4', 'SynthS5R2', 'BossLevel', 'GoToLocal', 'PutNextLocal', 'GoToImpUnlock'])
+@pytest.mark.parametrize('level', ['MiniBossLevel', 'GoToObjMazeS4', 'SynthS5R2', 'BossLevel', 'GoToLocal', 'PutNextLocal', 'GoToImpUnlock', 'Unlock'])
 def test_deep_generation_matches_oracle(level):
     """Generation far down each env's random stream (the GPU pool pre-generates 128 levels per env)."""
     n = 48

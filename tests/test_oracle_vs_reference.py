@@ -17,7 +17,7 @@ def test_random_policy(level):
         compare_ref.compare(level, 4000 + s, 150, 'random', act_seed=s)
 
 
-@pytest.mark.parametrize('level', ['GoToLocal', 'PickupLoc', 'BossLevel', 'SynthSeq', 'GoToImpUnlock'])
+@pytest.mark.parametrize('level', ['GoToLocal', 'PickupLoc', 'BossLevel', 'SynthSeq', 'GoToImpUnlock', 'Unlock'])
 def test_bot_policy(level):
     import compare_ref
     eps = compare_ref.compare(level, 5000, 250, 'bot', act_seed=1)

@@ -58,7 +58,9 @@ def test_device_parallel_env_and_preprocessor(level, n):
 
 
 @pytest.mark.parametrize('level,n,steps,p', [('GoToImpUnlock', 256, 300, None),
-                                              ('GoToImpUnlock', 128, 400, [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02])])
+                                              ('GoToImpUnlock', 128, 400, [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02]),
+                                              ('Unlock', 256, 300, None),
+                                              ('Unlock', 128, 500, [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02])])
 def test_gpu_matches_oracle_new_levels(level, n, steps, p):
     """Levels added after the last GPU visit: k_gen (one warp per level) + k_step8 against the C oracle."""
     import oracle as orc
@@ -70,10 +72,11 @@ def test_gpu_matches_oracle_new_levels(level, n, steps, p):
     assert g.env.counters()['errors'] == 0
 
 
-def test_rollout_equals_stepwise_new_levels():
+@pytest.mark.parametrize('level', ['GoToImpUnlock', 'Unlock'])
+def test_rollout_equals_stepwise_new_levels(level):
     import torch
     from babyai_b200 import BabyAIVecEnv
-    level, n, T = 'GoToImpUnlock', 300, 16
+    n, T = 300, 16
     seeds = np.arange(n, dtype=np.uint64) + 77
     a, b = BabyAIVecEnv(level, n, seeds=seeds), BabyAIVecEnv(level, n, seeds=seeds)
     acts = torch.randint(0, 7, (T, n), device='cuda', dtype=torch.int8)
