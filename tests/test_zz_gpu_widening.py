@@ -90,3 +90,14 @@ def test_rollout_equals_stepwise_new_levels(level):
             o, r, d = b.step(acts[t])
             assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]) and torch.equal(d, done[t]), (rep, t)
     assert a.counters()['errors'] == 0
+
+
+def test_own_arm_json_line():
+    from test_bench_contract import BASE_KEYS, _line
+    d = _line(['--steps', '80', '--warmup', '40', '--envs', '4096', '--no-cpu-baseline'])
+    assert (BASE_KEYS - {'cpu_baseline'}) | {'roofline', 'clocks', 'per_step_api', 'counters', 'learner_path'} <= set(d)
+    r = d['roofline']
+    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['achieved'] > 0 and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert d['e2e']['h2d_bytes_per_step'] == 4096 and d['e2e']['d2h_bytes_per_step'] == 4096 * 153
+    assert d['gpu_launches'] > 0 and d['counters']['errors'] == 0 and d['dtype'] == 'u8'
+    assert 'error' not in (d['learner_path'] or {}), d['learner_path']
