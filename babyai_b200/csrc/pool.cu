@@ -1038,6 +1038,7 @@ struct bb_pool {
     cudaEvent_t ev[3];
     cudaEvent_t tev[4]; bool time_rollout, tev_kernel, tev_refill;
     const void *chk_obs; bool direct;            // bb_pool_step_host: caller buffers are page-locked       // bb_pool_rollout_timed
+    int lz_state; int8_t *lz_act; float *lz_rew; uint8_t *lz_done;   // bb_pool_step_learner: 0 = not probed, 1 = mapped staging, 2 = copies
 };
 
 template <typename T>
@@ -1199,6 +1200,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_generic = getenv("BB_GEN_GENERIC") != nullptr;
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
+    p->lz_state = 0;
     p->zerocopy = 1; p->zc_level = 0; p->chk_rew = nullptr;    // measured (profiles/r01z_zerocopy_ab.log): e2e 2.74e8 copies only, 2.97e8 level 1, 2.91e8 level 2
     if (const char *e = getenv("BB_HOST_ZEROCOPY")) p->zerocopy = atoi(e);
     p->gen_fused = 1;                                      // bb_pool_rollout on single-room levels: generator warp inside k_rollout (see bb_pool_rollout)
@@ -1573,6 +1575,42 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
         memcpy(done_host, p->h_done, n);
         if (dir_host) memcpy(dir_host, p->h_dir, n);
     }
+    return 0;
+}
+
+// The learner's step (babyai_b200/learner.py): actions arrive from the host (base.py:144 hands numpy), the observation
+// stays on the device, reward / done go back to the host (base.py:158-179 reads them there).  The step kernel reads the
+// actions from and writes reward / done to the pool's page-locked staging buffers over PCIe (mapped memory), so the
+// call is: one host memcpy, one kernel, one stream synchronise, two host memcpys -- no copy-engine transfers at all.
+int bb_pool_step_learner(bb_pool *p, const int8_t *actions_host, uint8_t *obs_dev, float *reward_host, uint8_t *done_host,
+                         int8_t *dir_dev, void *stream)
+{
+    if (!p || !actions_host || !obs_dev || !reward_host || !done_host) return fail("bad arguments");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)p->n;
+    if (p->lz_state == 0) {
+        void *da = nullptr, *dr = nullptr, *dd = nullptr;
+        const bool ok = p->zerocopy > 0 && cudaHostGetDevicePointer(&da, p->h_act, 0) == cudaSuccess &&
+                        cudaHostGetDevicePointer(&dr, p->h_rew, 0) == cudaSuccess && cudaHostGetDevicePointer(&dd, p->h_done, 0) == cudaSuccess;
+        if (ok) { p->lz_state = 1; p->lz_act = (int8_t *)da; p->lz_rew = (float *)dr; p->lz_done = (uint8_t *)dd; }
+        else { cudaGetLastError(); p->lz_state = 2; }
+    }
+    const bool zc = p->lz_state == 1;
+    memcpy(p->h_act, actions_host, n);
+    if (!zc) CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, st));
+    if (sched_leave_rollout(p, st)) return 1;
+    if (sched_before_step(p, p->rel, st)) return 1;
+    launch_step(p, zc ? p->lz_act : p->d_act, 1, obs_dev, zc ? p->lz_rew : p->d_rew, zc ? p->lz_done : p->d_done, dir_dev, 0, st);
+    if (sched_after_step(p, p->rel, st)) return 1;
+    p->rel++;
+    if (!zc) {
+        CU(cudaMemcpyAsync(p->h_rew, p->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    memcpy(reward_host, p->h_rew, n * sizeof(float));
+    memcpy(done_host, p->h_done, n);
     return 0;
 }
 

@@ -165,15 +165,23 @@ class DeviceParallelEnv(object):
     """babyai.rl.utils.penv.ParallelEnv surface; observations stay on the device.
 
     `envs` is the list `make_envs()` built (scripts/train_rl.py:53-60 shape).  `pool` is for tests only: an object
-    with BabyAIVecEnv's tensor interface (the GPU-less suite passes the host build of the kernel logic)."""
+    with BabyAIVecEnv's tensor interface (the GPU-less suite passes the host build of the kernel logic).
+    `fused_io=True` (or BB_LEARNER_FUSED_IO=1) steps through bb_pool_step_learner -- actions, reward and done travel over
+    mapped page-locked memory inside the one step call instead of as three separate tensor copies; opt-in until it has
+    been measured on the GPU (written after round 1's GPU budget was spent)."""
 
-    def __init__(self, envs, pool=None):
+    def __init__(self, envs, pool=None, fused_io=None):
         assert isinstance(envs, EnvList), 'build the env list with babyai_b200.make_envs()'
         self.envs = envs
         self.observation_space, self.action_space = _spaces()
         self.pool = pool if pool is not None else BabyAIVecEnv(envs.level, len(envs), seeds=envs.seeds,
                                                                device=envs.device, mode=MODE_AUTORESET)
         self._tokens = None
+        if fused_io is None:
+            fused_io = os.environ.get('BB_LEARNER_FUSED_IO', '0') == '1'
+        self.fused_io = bool(fused_io) and hasattr(self.pool, 'step_learner')
+        n = self.pool.num_envs
+        self._rew_h, self._done_h = np.zeros(n, np.float32), np.zeros(n, np.uint8)
 
     def _batch(self, image, refresh_tokens):
         if refresh_tokens or self._tokens is None:         # missions change only when an episode starts
@@ -192,6 +200,14 @@ class DeviceParallelEnv(object):
     def step(self, actions):
         """actions: N values in 0..6 -- numpy (base.py:144), a sequence, or a torch tensor on any device (evaluate.py:124)."""
         dev = self.pool.device
+        if self.fused_io:
+            a = actions.cpu().numpy() if torch.is_tensor(actions) else np.asarray(actions)
+            img, dire = self._new_image(), torch.empty(self.pool.num_envs, dtype=torch.int8, device=dev)
+            self.pool.step_learner(a.astype(np.int8), img, self._rew_h, self._done_h, dire)
+            rew_h, done_h = self._rew_h.copy(), self._done_h.astype(bool)
+            if done_h.any() or self._tokens is None:
+                self._tokens = self.pool.mission_tokens.clone()
+            return iter((ObsBatch(img, self._tokens, dire), rew_h, done_h, _Infos(len(done_h))))
         if torch.is_tensor(actions):
             a = actions.to(device=dev, dtype=torch.int8).contiguous()
         else:

@@ -141,6 +141,14 @@ class BabyAIVecEnv(object):
                                             reward.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p),
                                             direction.ctypes.data_as(C.c_void_p)))
 
+    def step_learner(self, actions, obs, reward, done, direction=None):
+        """bb_pool_step_learner: actions int8 numpy (host) -> obs (and direction) CUDA tensors, reward float32 / done uint8
+        numpy (host); synchronises the current stream."""
+        a = np.ascontiguousarray(actions, dtype=np.int8)
+        assert a.shape == (self.num_envs,) and reward.dtype == np.float32 and done.dtype == np.uint8
+        _lib.check(self.L.bb_pool_step_learner(self.h, a.ctypes.data_as(C.c_void_p), _ptr(obs), reward.ctypes.data_as(C.c_void_p),
+                                               done.ctypes.data_as(C.c_void_p), _ptr(direction), self._stream()))
+
     def reset_host(self, obs, direction):
         _lib.check(self.L.bb_pool_reset_host(self.h, obs.ctypes.data_as(C.c_void_p),
                                              direction.ctypes.data_as(C.c_void_p)))

@@ -302,28 +302,32 @@ def main():
     # ---- the learner-facing path with observations resident in HBM (babyai_b200.learner; informational) ----------
     # per step: actions host->device, the step kernel writing into a fresh observation tensor, ObssPreprocessor handing
     # the model image float[N,7,7,3] + instr long[N,L] on the device, reward/done device->host.  Measured on this rank.
-    learner = None
-    try:
-        from babyai_b200 import make_envs
-        from babyai_b200.learner import DeviceParallelEnv, ObssPreprocessor
-        denv = DeviceParallelEnv(make_envs(args.level, n), pool=env)
-        pre = ObssPreprocessor(trim=False)
-        ob = denv.reset()
-        Kl = min(K, 300)
-        for k in range(5):
-            pre(ob, device=dev)
-            ob, _r, _d, _i = denv.step(h_act[k])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for k in range(Kl):
-            pre(ob, device=dev)
-            ob, _r, _d, _i = denv.step(h_act[k % 64])
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        learner = {'value_per_gpu': n * Kl / dt, 'unit': 'env-steps/s', 'steps': Kl, 'h2d_bytes_per_step': n,
-                   'd2h_bytes_per_step': n * 5, 'api': 'DeviceParallelEnv.step + ObssPreprocessor (observations stay in HBM)'}
-    except Exception as ex:          # informational leg: never lose the bench line over it
-        learner = {'error': repr(ex)[:300]}
+    learner = {}
+    for key, fused_io in (('tensor_copies', False), ('fused_io', True)):
+        # tensor_copies: bb_pool_step + torch copies of actions / reward / done; fused_io: bb_pool_step_learner (those three
+        # over mapped page-locked memory inside the step call)
+        try:
+            from babyai_b200 import make_envs
+            from babyai_b200.learner import DeviceParallelEnv, ObssPreprocessor
+            denv = DeviceParallelEnv(make_envs(args.level, n), pool=env, fused_io=fused_io)
+            pre = ObssPreprocessor(trim=False)
+            ob = denv.reset()
+            Kl = min(K, 300)
+            for k in range(5):
+                pre(ob, device=dev)
+                ob, _r, _d, _i = denv.step(h_act[k])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for k in range(Kl):
+                pre(ob, device=dev)
+                ob, _r, _d, _i = denv.step(h_act[k % 64])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            learner[key] = {'value_per_gpu': n * Kl / dt, 'unit': 'env-steps/s', 'steps': Kl, 'h2d_bytes_per_step': n,
+                            'd2h_bytes_per_step': n * 5}
+        except Exception as ex:          # informational leg: never lose the bench line over it
+            learner[key] = {'error': repr(ex)[:300]}
+    learner['api'] = 'DeviceParallelEnv.step + ObssPreprocessor (observations stay in HBM)'
 
     if rank == 0:
         peak, peak_src = hbm_peak()

@@ -128,6 +128,12 @@ int bb_pool_step_host(bb_pool *pool, const int8_t *actions_host,
                       uint8_t *obs_host, float *reward_host, uint8_t *done_host, int8_t *dir_host);
 int bb_pool_reset_host(bb_pool *pool, uint8_t *obs_host, int8_t *dir_host);
 
+/* The learner's step (BaseAlgo.collect_experiences, rl/algos/base.py:131-188, with the observations resident on the
+ * device): actions from a HOST buffer (base.py:144 hands numpy), observation (and optionally direction) into DEVICE
+ * buffers on `stream`, reward / done into HOST buffers (base.py:158-179 reads them there); synchronises `stream`. */
+int bb_pool_step_learner(bb_pool *pool, const int8_t *actions_host, uint8_t *obs_dev, float *reward_host,
+                         uint8_t *done_host, int8_t *dir_dev, void *stream);
+
 /* Replaces: obs['mission'] + InstructionsPreprocessor (utils/format.py:59-75).
  * Device pointer to int16 [n_envs][max_len] token ids of the current missions
  * (0 = pad, ids index bb_vocab_word); rewritten whenever an env is reset. */

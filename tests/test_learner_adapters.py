@@ -13,6 +13,17 @@ import torch
 
 import hostemu
 import oracle as orc
+
+
+@pytest.fixture
+def single_torch_thread():
+    """The reference's ParallelEnv forks its workers from this (multi-threaded) process; with OpenMP worker threads alive
+    the parent's next backward pass was seen to stall.  One intra-op thread keeps the comparison deterministic and quick."""
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(n)
+
 from babyai_b200 import ParallelEnv, make_envs
 from babyai_b200.learner import DeviceParallelEnv, DictList, FixedVocabulary, ObsBatch, ObssPreprocessor
 from babyai_b200.levels import VOCAB, detokenize, level_spec
@@ -52,6 +63,17 @@ class EmuTensorPool(object):
         return obs, self.reward, self.done
 
 
+    def step_learner(self, actions, obs, reward, done, direction=None):
+        """bb_pool_step_learner: host actions -> device obs / direction, host reward / done"""
+        assert actions.dtype == np.int8 and reward.dtype == np.float32 and done.dtype == np.uint8
+        o, r, d = self.emu.step(actions)
+        obs.copy_(torch.from_numpy(o))
+        reward[...], done[...] = r, d
+        self.direction.copy_(torch.from_numpy(self.emu.direction))
+        if direction is not None:
+            direction.copy_(self.direction)
+        self._tokens(np.nonzero(d)[0])
+
     # host-buffer interface (bb_pool_seed / reset_host / step_host / missions)
     def seed(self, seeds):
         self.emu.seed(np.asarray(list(seeds), dtype=np.uint64))
@@ -68,9 +90,9 @@ class EmuTensorPool(object):
         return [detokenize(self.emu.tokens(int(i))) for i in (range(self.num_envs) if idx is None else idx)]
 
 
-def _device_env(level, n, seed=1):
+def _device_env(level, n, seed=1, fused_io=False):
     envs = make_envs(level, n, seed=seed)
-    return DeviceParallelEnv(envs, pool=EmuTensorPool(level, envs.seeds))
+    return DeviceParallelEnv(envs, pool=EmuTensorPool(level, envs.seeds), fused_io=fused_io)
 
 
 def _ref_tokens(mission, width):
@@ -80,10 +102,11 @@ def _ref_tokens(mission, width):
     return ids + [0] * (width - len(ids))
 
 
-@pytest.mark.parametrize('level', ['GoToLocal', 'PutNextLocal', 'GoToSeqS5R2'])
-def test_device_env_and_preprocessor_against_oracle(level):
+@pytest.mark.parametrize('level,fused_io', [('GoToLocal', False), ('PutNextLocal', True), ('GoToSeqS5R2', False), ('GoToLocal', True)])
+def test_device_env_and_preprocessor_against_oracle(level, fused_io):
     n, T = 12, 70
-    env = _device_env(level, n)
+    env = _device_env(level, n, fused_io=fused_io)
+    assert env.fused_io == fused_io
     o = orc.OraclePool(level, n, np.array([100 + i for i in range(n)], dtype=np.uint64))
     pre = ObssPreprocessor()
     obs = env.reset()
@@ -143,8 +166,9 @@ def test_fixed_vocabulary(tmp_path):
 
 
 @pytest.mark.reference
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize('level', ['PutNextLocal', 'GoToObjMazeS4R2'])
-def test_reference_ppo_consumes_the_pool_unchanged(level):
+def test_reference_ppo_consumes_the_pool_unchanged(level, single_torch_thread):
     import refenv
     gym = refenv.setup('philox')
     import babyai.rl
@@ -208,8 +232,9 @@ def test_reference_ppo_consumes_the_pool_unchanged(level):
 
 
 @pytest.mark.reference
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize('level', ['GoToLocal', 'PickupLoc'])
-def test_reference_batch_evaluate_consumes_the_pool_unchanged(level):
+def test_reference_batch_evaluate_consumes_the_pool_unchanged(level, single_torch_thread):
     """babyai.evaluate.batch_evaluate (evaluate.py:85-140), unmodified, with `ManyEnvs` rebound."""
     import refenv
     refenv.setup('philox')

@@ -16,15 +16,17 @@ def test_gpu_replays_remaining_golden(level):
     replay_golden(level, lambda lv, n, s: GpuPool(lv, n, s), lambda p, i: p.mission(i))
 
 
-@pytest.mark.parametrize('level,n', [('PutNextLocal', 96), ('GoToSeqS5R2', 64)])
-def test_device_parallel_env_and_preprocessor(level, n):
+@pytest.mark.parametrize('level,n,fused_io', [('PutNextLocal', 96, False), ('GoToSeqS5R2', 64, False), ('PutNextLocal', 96, True),
+                                               ('BossLevel', 40, True)])
+def test_device_parallel_env_and_preprocessor(level, n, fused_io):
     """babyai_b200.learner: observations stay in HBM between the step kernel and the learner's tensors."""
     import torch
     import oracle as orc
     from babyai_b200 import DeviceParallelEnv, ObssPreprocessor, make_envs
     from babyai_b200.levels import VOCAB
     T = 70
-    env = DeviceParallelEnv(make_envs(level, n, seed=1))
+    env = DeviceParallelEnv(make_envs(level, n, seed=1), fused_io=fused_io)       # True: bb_pool_step_learner
+    assert env.fused_io == fused_io
     o = orc.OraclePool(level, n, np.array([100 + i for i in range(n)], dtype=np.uint64))
     pre = ObssPreprocessor()
     obs = env.reset()
@@ -100,4 +102,4 @@ def test_own_arm_json_line():
     assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['achieved'] > 0 and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
     assert d['e2e']['h2d_bytes_per_step'] == 4096 and d['e2e']['d2h_bytes_per_step'] == 4096 * 153
     assert d['gpu_launches'] > 0 and d['counters']['errors'] == 0 and d['dtype'] == 'u8'
-    assert 'error' not in (d['learner_path'] or {}), d['learner_path']
+    assert 'error' not in d['learner_path']['tensor_copies'] and 'error' not in d['learner_path']['fused_io'], d['learner_path']
