@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from .levels import VOCAB, detokenize
-from .vecenv import MODE_AUTORESET, BabyAIVecEnv, EnvList, _spaces
+from .vecenv import MODE_AUTORESET, MODE_FREEZE, BabyAIVecEnv, _as_env_list, _spaces
 
 
 class DictList(dict):
@@ -170,12 +170,14 @@ class DeviceParallelEnv(object):
     mapped page-locked memory inside the one step call instead of as three separate tensor copies; opt-in until it has
     been measured on the GPU (written after round 1's GPU budget was spent)."""
 
+    MODE = MODE_AUTORESET
+
     def __init__(self, envs, pool=None, fused_io=None):
-        assert isinstance(envs, EnvList), 'build the env list with babyai_b200.make_envs()'
+        envs = _as_env_list(envs, need_seeds=(self.MODE == MODE_AUTORESET))
         self.envs = envs
         self.observation_space, self.action_space = _spaces()
         self.pool = pool if pool is not None else BabyAIVecEnv(envs.level, len(envs), seeds=envs.seeds,
-                                                               device=envs.device, mode=MODE_AUTORESET)
+                                                               device=envs.device, mode=self.MODE)
         self._tokens = None
         if fused_io is None:
             fused_io = os.environ.get('BB_LEARNER_FUSED_IO', '0') == '1'
@@ -222,6 +224,23 @@ class DeviceParallelEnv(object):
 
     def render(self):
         raise NotImplementedError                          # penv.py:54-55
+
+
+class DeviceManyEnvs(DeviceParallelEnv):
+    """babyai.evaluate.ManyEnvs surface (evaluate.py:58-81: seed / reset / step; finished envs freeze and repeat their last
+    result) with the observations resident on the device -- `batch_evaluate` + `ModelAgent.act_batch` consume it
+    unchanged when the agent's preprocessor is learner.ObssPreprocessor.  Accepts the plain gym.make list batch_evaluate
+    builds, like vecenv.ManyEnvs."""
+    MODE = MODE_FREEZE
+
+    def seed(self, seeds):
+        self.pool.seed(list(seeds))
+
+    def step(self, actions):
+        obs, rew, done, info = super().step(actions)
+        # evaluate.py:78 zips per-env result tuples; ModelAgent.analyze_feedback (utils/agent.py:76-82) tells a tuple of
+        # Python bools (`if done[i]`) from a tensor (`1 - done`): hand it the tuple
+        return iter((obs, tuple(float(r) for r in rew), tuple(bool(d) for d in done), info))
 
 
 class ObssPreprocessor(object):

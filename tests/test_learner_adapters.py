@@ -25,7 +25,7 @@ def single_torch_thread():
     torch.set_num_threads(n)
 
 from babyai_b200 import ParallelEnv, make_envs
-from babyai_b200.learner import DeviceParallelEnv, DictList, FixedVocabulary, ObsBatch, ObssPreprocessor
+from babyai_b200.learner import DeviceManyEnvs, DeviceParallelEnv, DictList, FixedVocabulary, ObsBatch, ObssPreprocessor
 from babyai_b200.levels import VOCAB, detokenize, level_spec
 
 
@@ -248,18 +248,24 @@ def test_reference_batch_evaluate_consumes_the_pool_unchanged(level, single_torc
     model = ACModel(pre.obs_space, make_envs(level, 1)[0].action_space, 128, 128, 128, True, 'gru', True, 'bow_endpool')
     model.eval()
 
-    def run(many_envs):
+    def run(many_envs, preproc=None):
         stock = evaluate.ManyEnvs
         evaluate.ManyEnvs = many_envs
         try:
             torch.manual_seed(11)
-            agent = utils.ModelAgent(model, pre, argmax=False)
+            agent = utils.ModelAgent(model, preproc or pre, argmax=False)
             return evaluate.batch_evaluate(agent, 'BabyAI-%s-v0' % level, 10 ** 9, 20)    # 2 chunks of 10 envs, val seeds
         finally:
             evaluate.ManyEnvs = stock
 
     a = run(evaluate.ManyEnvs)
     b = run(lambda envs: ManyEnvs(envs, pool=EmuTensorPool(level, [0] * len(envs), mode=1)))
+    # observations resident on the "device": DeviceManyEnvs + learner.ObssPreprocessor as the agent's preprocessor
+    import babyai.rl
+    c = run(lambda envs: DeviceManyEnvs(envs, pool=EmuTensorPool(level, [0] * len(envs), mode=1)),
+            ObssPreprocessor(dictlist=babyai.rl.DictList))
+    assert [int(x) for x in a['num_frames_per_episode']] == [int(x) for x in c['num_frames_per_episode']]
+    assert [np.float32(x) for x in a['return_per_episode']] == [np.float32(x) for x in c['return_per_episode']]
     assert list(a['seed_per_episode']) == list(b['seed_per_episode'])
     assert [int(x) for x in a['num_frames_per_episode']] == [int(x) for x in b['num_frames_per_episode']]
     # the pool hands out the reward as float32 -- the precision the learner consumes it in (base.py:167,175); the
