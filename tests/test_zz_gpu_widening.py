@@ -10,14 +10,17 @@ from common import GOLDEN_LEVELS, GOLDEN_LEVELS_GPU, replay_golden  # noqa: E402
 from test_gpu_parity import GpuPool  # noqa: E402
 
 
-@pytest.mark.parametrize('level', [lv for lv in GOLDEN_LEVELS if lv not in GOLDEN_LEVELS_GPU])
+NEW_LEVELS = ['GoToImpUnlock', 'Unlock']          # generator kernel k_gen<true> / UNTR step kernels: never run on a GPU before
+
+
+@pytest.mark.parametrize('level', [lv for lv in GOLDEN_LEVELS if lv not in GOLDEN_LEVELS_GPU and lv not in NEW_LEVELS])
 def test_gpu_replays_remaining_golden(level):
     """Reference-generated traces (tests/golden/make_golden.py) of the served levels test_gpu_parity.py does not replay."""
     replay_golden(level, lambda lv, n, s: GpuPool(lv, n, s), lambda p, i: p.mission(i))
 
 
-@pytest.mark.parametrize('level,n,fused_io', [('PutNextLocal', 96, False), ('GoToSeqS5R2', 64, False), ('PutNextLocal', 96, True),
-                                               ('BossLevel', 40, True)])
+@pytest.mark.parametrize('level,n,fused_io', [('PutNextLocal', 96, False), ('GoToSeqS5R2', 64, False), ('BossLevel', 40, False),
+                                               ('PutNextLocal', 96, True), ('BossLevel', 40, True)])
 def test_device_parallel_env_and_preprocessor(level, n, fused_io):
     """babyai_b200.learner: observations stay in HBM between the step kernel and the learner's tensors."""
     import torch
@@ -59,6 +62,23 @@ def test_device_parallel_env_and_preprocessor(level, n, fused_io):
     assert env.pool.counters()['errors'] == 0
 
 
+def test_own_arm_json_line():
+    from test_bench_contract import BASE_KEYS, _line
+    d = _line(['--steps', '80', '--warmup', '40', '--envs', '4096', '--no-cpu-baseline'])
+    assert (BASE_KEYS - {'cpu_baseline'}) | {'roofline', 'clocks', 'per_step_api', 'counters', 'learner_path'} <= set(d)
+    r = d['roofline']
+    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['achieved'] > 0 and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert d['e2e']['h2d_bytes_per_step'] == 4096 and d['e2e']['d2h_bytes_per_step'] == 4096 * 153
+    assert d['gpu_launches'] > 0 and d['counters']['errors'] == 0 and d['dtype'] == 'u8'
+    assert 'error' not in d['learner_path']['tensor_copies'] and 'error' not in d['learner_path']['fused_io'], d['learner_path']
+
+
+# ---- from here on: kernels instantiated after the last GPU visit (k_gen<true>, k_step8<*, true>, k_rollout<1, true>) ----
+@pytest.mark.parametrize('level', NEW_LEVELS)
+def test_gpu_replays_new_level_golden(level):
+    replay_golden(level, lambda lv, n, s: GpuPool(lv, n, s), lambda p, i: p.mission(i))
+
+
 @pytest.mark.parametrize('level,n,steps,p', [('GoToImpUnlock', 256, 300, None),
                                               ('GoToImpUnlock', 128, 400, [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02]),
                                               ('Unlock', 256, 300, None),
@@ -92,14 +112,3 @@ def test_rollout_equals_stepwise_new_levels(level):
             o, r, d = b.step(acts[t])
             assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]) and torch.equal(d, done[t]), (rep, t)
     assert a.counters()['errors'] == 0
-
-
-def test_own_arm_json_line():
-    from test_bench_contract import BASE_KEYS, _line
-    d = _line(['--steps', '80', '--warmup', '40', '--envs', '4096', '--no-cpu-baseline'])
-    assert (BASE_KEYS - {'cpu_baseline'}) | {'roofline', 'clocks', 'per_step_api', 'counters', 'learner_path'} <= set(d)
-    r = d['roofline']
-    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['achieved'] > 0 and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
-    assert d['e2e']['h2d_bytes_per_step'] == 4096 and d['e2e']['d2h_bytes_per_step'] == 4096 * 153
-    assert d['gpu_launches'] > 0 and d['counters']['errors'] == 0 and d['dtype'] == 'u8'
-    assert 'error' not in d['learner_path']['tensor_copies'] and 'error' not in d['learner_path']['fused_io'], d['learner_path']
