@@ -932,6 +932,252 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
     }
 }
 
+// =====================================================================================================================
+// k_rollout2 -- EXPERIMENTAL (BB_ROLLOUT_LANES=2; written after round 1's GPU budget was spent, never run on a GPU yet):
+// the persistent rollout kernel with TWO LANES PER ENVIRONMENT.  k_rollout is latency bound with 4.2 warps per scheduler and
+// 8.7 cycles per issued instruction (profiles/r01y_ncu_rollout_details.txt); the number of stepping warps is capped by the
+// problem size (65 536 envs = 2 048 warps), so the remaining parallelism is inside an env.  Here a warp serves 16 envs:
+//   * the even lane of a pair applies the action and runs the verifier (step_env) and broadcasts the hot record;
+//   * a finished env's next level is copied from the ring by the two lanes together (half the dependent loads each);
+//   * the observation is split by view columns (even lane: columns 0..3 = 84 bytes, odd lane: 4..6 = 63 bytes; one
+//     shuffle exchanges the see-through bits on multi-room levels), encoded per column and staged as 21-byte records
+//     (pair_cols_load / pair_cols_encode / pair_stage in env_logic.cuh: checked against observe() in the host build).
+// Twice the stepping warps for an estimated 1.3-1.5 x the instructions.  CTA = 4 stepping warps (64 envs, the same
+// shared-memory footprint per env as k_rollout) + the generator warp of the fused mode; 7 CTAs per SM = 35 warps need
+// <= 58 registers per thread (k_rollout compiles to 56 registers with 80 bytes of spills under that cap).
+constexpr int R2_WARPS = 4, R2_ENVS = 16;
+constexpr int R2_THREADS = 32 * R2_WARPS, R2_THREADS_FUSED = R2_THREADS + 32;
+constexpr int TILE2_WORDS = R2_ENVS * OBS_BYTES / 4;              // 588 words = 2352 B per warp
+
+__device__ __forceinline__ void store_tile2(const uint32_t *tile, uint8_t *dst, int lane, int valid_envs)
+{
+    if (valid_envs == R2_ENVS && (((uintptr_t)dst) & 15) == 0) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(tile);
+        uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+        for (int i = 0; i < (TILE2_WORDS / 4 + 31) / 32; i++) {
+            const int idx = lane + 32 * i;
+            if (idx < TILE2_WORDS / 4) d[idx] = s[idx];
+        }
+    } else {
+        const uint8_t *s = reinterpret_cast<const uint8_t *>(tile);
+        const int nbytes = valid_envs * OBS_BYTES;
+        for (int i = lane; i < nbytes; i += 32) dst[i] = s[i];
+    }
+}
+
+__global__ void __launch_bounds__(R2_THREADS_FUSED, 7)
+k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
+           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
+           const int mode, const int gen_rounds, const int gen_min_active)
+{
+    extern __shared__ __align__(16) uint32_t smr[];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;
+    const int warp_words = R2_ENVS * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE2_WORDS;
+    const bool fused = gen_rounds > 0;
+    uint32_t *g_area = smr + R2_WARPS * warp_words;
+    volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
+    if (warp == R2_WARPS) {
+        // ---- generator warp (fused launches only): the same role as in k_rollout, for the CTA's 64 envs ----
+        const uint32_t D = (uint32_t)P.depth;
+        uint32_t *ring = g_area, *s_tl = g_area + RG_RING_WORDS;
+        uint16_t *s_def = reinterpret_cast<uint16_t *>(s_tl + 64);
+        uint8_t *list = reinterpret_cast<uint8_t *>(s_tl + 64 + 32);
+        const int cta_env0 = blockIdx.x * R2_WARPS * R2_ENVS;
+        int cta_nv = n - cta_env0; cta_nv = cta_nv > 64 ? 64 : (cta_nv < 0 ? 0 : cta_nv);
+        int cnt = 0;
+        bool urgent = false;
+        if (lane == 0) *s_done = 0;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int i = 32 * h2 + lane;
+            bool need = false;
+            if (i < cta_nv) {
+                const uint32_t hd = P.head[cta_env0 + i], tl0 = P.tail[cta_env0 + i];
+                const int have = (int)(tl0 - hd);
+                s_tl[i] = tl0; s_def[i] = (uint16_t)((int)D - have);
+                need = have < (int)D;
+                urgent = urgent || have < 2 * T;
+            }
+            const uint32_t m = __ballot_sync(FULL, need);
+            if (need) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
+            cnt += __popc(m);
+        }
+        const bool must_complete = __any_sync(FULL, urgent);
+        __syncthreads();                                  // the stepping warps have read head / tail: generation may start
+        RolloutRing ds;
+        ds.init(ring + lane, 32, 0, 0);
+        int env_g = -1, left = 0, next = 0, rounds = 0;
+        uint32_t tl = 0;
+        for (;;) {
+            const bool idle = left == 0;
+            const uint32_t midle = __ballot_sync(FULL, idle);
+            if (midle && next < cnt) {
+                const int idx = next + __popc(midle & ((1u << lane) - 1u));
+                if (idle && idx < cnt) {
+                    const int i = list[idx];
+                    env_g = cta_env0 + i; tl = s_tl[i]; left = (int)s_def[i];
+                    const RngRec r = P.rng[env_g];
+                    ds.init(ring + lane, 32, r.seed, r.draws);
+                }
+                next += __popc(midle);
+            }
+            const bool active = left > 0;
+            const uint32_t mact = __ballot_sync(FULL, active);
+            if (!mact) break;
+            if (!must_complete) {
+                int dn = 0;
+                if (lane == 0) dn = *s_done;
+                dn = __shfl_sync(FULL, dn, 0);
+                if (rounds >= gen_rounds || dn >= R2_WARPS) break;
+                if (rounds >= 1 && __popc(mact) < gen_min_active) break;
+            }
+            rounds++;
+            gen_small_round<RolloutRing, true>(lp, P, ds, active, env_g, tl, left, D);
+        }
+        return;
+    }
+    // ---- stepping warps: lane = 2 * (env within the warp) + half ----
+    const int el = lane >> 1, hf = lane & 1, even = lane & ~1;
+    const int env0 = (blockIdx.x * R2_WARPS + warp) * R2_ENVS, env = env0 + el;
+    int nv = n - env0; nv = nv > R2_ENVS ? R2_ENVS : (nv < 0 ? 0 : nv);
+    const bool valid = el < nv;
+    uint32_t *sg = smr + warp * warp_words, *so = sg + R2_ENVS * gs, *si = so + R2_ENVS * SM_OBJ_STRIDE;
+    uint32_t *tile = si + R2_ENVS * SM_INS_STRIDE;          // 16-byte aligned: every term is a multiple of 4 words
+    warp_copy_records<true>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
+    warp_copy_records<true>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
+    warp_copy_records<true>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
+    EnvHot h;
+    { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
+    uint32_t head = 0, avail = 0;
+    float last_rew = 0.0f;
+    if (valid) {
+        h = P.hot[env];
+        head = P.head[env];
+        avail = (fused ? P.tail[env] : __ldcg(P.tail_pub + env)) - head;
+        if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env];
+    }
+    if (fused) __syncthreads();
+    __syncwarp();
+    SmemOnlyMem mem(lp, reinterpret_cast<uint8_t *>(sg + el * gs), reinterpret_cast<uint8_t *>(so + el * SM_OBJ_STRIDE),
+                    reinterpret_cast<uint8_t *>(si + el * SM_INS_STRIDE));
+    const bool single_room = lp.num_rows == 1 && lp.num_cols == 1;
+    uint32_t n_step = 0, n_end = 0, n_succ = 0, n_err = 0, consumed = 0;      // counters: even lanes only
+    int a_next = 0;
+    if (valid) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + env));
+    for (int t = 0; t < T; t++) {
+        const int a = a_next;
+        if (valid && t + 1 < T) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + (size_t)(t + 1) * n + env));
+        float rew = 0.0f; bool dn = false; int begin = 0;
+        if (valid && hf == 0) {                             // the even lane steps the env
+            if (!(h.dirflags & 4)) {
+                const StepResult sr = step_env(h, mem, a);
+                rew = sr.reward; dn = sr.done;
+                n_step++; n_end += dn; n_succ += sr.success;
+                if (dn) {
+                    if (mode == BB_MODE_AUTORESET) begin = 1;
+                    else { h.dirflags |= 4; last_rew = rew; }
+                }
+            } else { rew = last_rew; dn = true; }
+        }
+        __syncwarp();                                       // step_env's shared-memory writes -> the partner lane
+        {   // the pair's hot record and "episode begins" flag from the even lane
+            uint4 hv = *reinterpret_cast<uint4 *>(&h);
+            hv.x = __shfl_sync(FULL, hv.x, even); hv.y = __shfl_sync(FULL, hv.y, even);
+            hv.z = __shfl_sync(FULL, hv.z, even); hv.w = __shfl_sync(FULL, hv.w, even);
+            h = *reinterpret_cast<EnvHot *>(&hv);
+            begin = __shfl_sync(FULL, begin, even);
+        }
+        if (begin && valid) {                               // uniform within the pair: both lanes copy the next level
+            if (consumed < avail && avail <= (uint32_t)P.depth) {
+                const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
+                uint32_t *mg = reinterpret_cast<uint32_t *>(mem.g);
+                for (int k = hf; k < lp.cells_pad / 16; k += 2) {
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.grid) + k);
+                    mg[4 * k] = v.x; mg[4 * k + 1] = v.y; mg[4 * k + 2] = v.z; mg[4 * k + 3] = v.w;
+                }
+                uint32_t *mo = reinterpret_cast<uint32_t *>(mem.o);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int c = 2 * k + hf;
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.obj) + c);
+                    mo[4 * c] = v.x; mo[4 * c + 1] = v.y; mo[4 * c + 2] = v.z; mo[4 * c + 3] = v.w;
+                }
+                uint32_t *mi = reinterpret_cast<uint32_t *>(mem.i);
+                for (int c = hf; c < 3; c += 2) {
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.ins) + c);
+                    mi[4 * c] = v.x; mi[4 * c + 1] = v.y; mi[4 * c + 2] = v.z; mi[4 * c + 3] = v.w;
+                }
+                uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
+                for (int k = hf; k < lp.max_tokens / 8; k += 2) lt[k] = __ldcg(reinterpret_cast<const uint4 *>(o.tok) + k);
+                const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(o.hot));
+                h = *reinterpret_cast<const EnvHot *>(&hv);
+                consumed++;
+            } else if (hf == 0) n_err++;
+        }
+        __syncwarp();                                       // the swapped-in level -> both lanes
+        if (valid && hf == 0 && mode == BB_MODE_AUTORESET && (int)h.step_count + 2 == (int)h.max_steps && consumed < avail) {
+            const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.grid));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.obj));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.obj) + 64));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.ins));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.ins) + 32));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.hot));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.tok));
+        }
+        // ---- observation: this lane's half of the view columns ----
+        uint32_t lo[4], hi[4], oc[4][6];
+        const int dir = h.dirflags & 3;
+        const ViewGeom v = view_geom(lp, h.x, h.y, dir);
+        uint32_t cm = 0;
+        if (valid) cm = pair_cols_load(mem, v, hf, lo, hi);
+        uint32_t other = 0;
+        if (!single_room) other = __shfl_xor_sync(FULL, cm, 1);
+        if (valid) pair_cols_encode(lp, v, h.x, h.y, dir, carry_cell_of(h, mem), hf, lo, hi, hf ? other : cm, hf ? cm : other, oc);
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int j = 0; j < 6; j++) oc[k][j] = 0;
+        }
+        const uint32_t next_first = __shfl_down_sync(FULL, oc[0][0], 1);
+        pair_stage(tile, oc, el, hf, next_first);
+        if (valid && hf == 0) {
+            const size_t oi = (size_t)t * n + env;
+            if (reward) reward[oi] = rew;
+            if (done) done[oi] = dn ? 1 : 0;
+            if (dirs) dirs[oi] = (int8_t)dir;
+        }
+        __syncwarp();
+        if (nv > 0) store_tile2(tile, obs + ((size_t)t * n + env0) * OBS_BYTES, lane, nv);
+        __syncwarp();                                       // the tile is rewritten in the next iteration
+    }
+    __syncwarp();
+    warp_copy_records<false>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
+    warp_copy_records<false>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
+    warp_copy_records<false>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
+    if (valid && hf == 0) {
+        P.hot[env] = h;
+        P.head[env] = head + consumed;
+        if (mode == BB_MODE_FREEZE) P.last_reward[env] = last_rew;
+    }
+    for (int off = 16; off; off >>= 1) {
+        n_step += __shfl_down_sync(FULL, n_step, off); n_end += __shfl_down_sync(FULL, n_end, off);
+        n_succ += __shfl_down_sync(FULL, n_succ, off); n_err += __shfl_down_sync(FULL, n_err, off);
+    }
+    if (fused && lane == 0) atomicAdd(const_cast<int *>(s_done), 1);
+    if (lane == 0) {
+        unsigned long long *c = P.warp_counters + 4ull * (blockIdx.x * R2_WARPS + warp);
+        if (n_step) atomicAdd(c + 0, (unsigned long long)n_step);
+        if (n_end) atomicAdd(c + 1, (unsigned long long)n_end);
+        if (n_succ) atomicAdd(c + 2, (unsigned long long)n_succ);
+        if (n_err) atomicAdd(c + 3, (unsigned long long)n_err);
+    }
+}
+
 // Level generation, decoupled from the step: tops every environment's ring up to `target` levels.
 //
 // ONE WARP PER ENVIRONMENT.  Generation is a long, branchy, data-dependent rejection-sampling program;
@@ -1038,6 +1284,7 @@ struct bb_pool {
     cudaEvent_t ev[3];
     cudaEvent_t tev[4]; bool time_rollout, tev_kernel, tev_refill;
     const void *chk_obs; bool direct;            // bb_pool_step_host: caller buffers are page-locked       // bb_pool_rollout_timed
+    int rollout_lanes;            // BB_ROLLOUT_LANES=2: k_rollout2 (experimental) instead of k_rollout in bb_pool_rollout
     int lz_state; int8_t *lz_act; float *lz_rew; uint8_t *lz_done;   // bb_pool_step_learner: 0 = not probed, 1 = mapped staging, 2 = copies
 };
 
@@ -1201,6 +1448,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
     p->lz_state = 0;
+    p->rollout_lanes = 1;
+    if (const char *e = getenv("BB_ROLLOUT_LANES")) p->rollout_lanes = atoi(e) == 2 ? 2 : 1;
     p->zerocopy = 1; p->zc_level = 0; p->chk_rew = nullptr;    // measured (profiles/r01z_zerocopy_ab.log): e2e 2.74e8 copies only, 2.97e8 level 1, 2.91e8 level 2
     if (const char *e = getenv("BB_HOST_ZEROCOPY")) p->zerocopy = atoi(e);
     p->gen_fused = 1;                                      // bb_pool_rollout on single-room levels: generator warp inside k_rollout (see bb_pool_rollout)
@@ -1255,6 +1504,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_rollout2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_rollout2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
     // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
     CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1444,7 +1695,14 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaEventRecord(p->ev_fork, user));
     }
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
-    if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
+    if (p->rollout_lanes == 2 && p->lp.kind != KIND_UNLOCK) {      // experimental: two lanes per environment
+        const size_t smem2 = (size_t)R2_WARPS * (R2_ENVS * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE2_WORDS) * 4;
+        const int blocks2 = (p->n + R2_WARPS * R2_ENVS - 1) / (R2_WARPS * R2_ENVS);
+        if (fused) k_rollout2<<<blocks2, R2_THREADS_FUSED, smem2 + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode,
+                                                                                            p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
+        else k_rollout2<<<blocks2, R2_THREADS, smem2, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
+    }
+    else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
                                                                                        p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
     else if (p->lp.kind == KIND_UNLOCK) k_rollout<1, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
     else k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);

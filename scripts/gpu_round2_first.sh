@@ -23,6 +23,19 @@ for l in sys.stdin:
     elif 'rror' in l: print(l.strip()[:300])
 " >> $OUT/configs_$TAG.log
 done
+# k_rollout2 (two lanes per environment, BB_ROLLOUT_LANES=2): never run before -- correctness first, then the A/B
+( BB_TEST_ROLLOUT2=1 timeout 900 python -m pytest tests/test_zz_gpu_widening.py -q -k rollout2 ) > $OUT/pytest_rollout2_$TAG.log 2>&1
+echo "pytest exit $?" >> $OUT/pytest_rollout2_$TAG.log
+for lanes in 1 2; do for lv in GoToLocal PickupLoc BossLevel; do
+  echo -n "$lv lanes=$lanes: " >> $OUT/ab_lanes_$TAG.log
+  BB_ROLLOUT_LANES=$lanes timeout 300 python bench.py --no-cpu-baseline --steps 2000 --warmup 200 --level $lv $( [ $lv = BossLevel ] && echo --envs 32768 ) 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('value %.3e rollout kernel %.1f us frac %.3f errors %d' % (d['value'], d['roofline']['kernel_ms']*1e3, d['roofline']['frac'], d['counters']['errors']))
+" >> $OUT/ab_lanes_$TAG.log
+done; done
+cat $OUT/ab_lanes_$TAG.log; tail -n 5 $OUT/pytest_rollout2_$TAG.log
 cat $OUT/configs_$TAG.log
 tail -n 15 $OUT/pytest_gpu_$TAG.log; tail -n 2 $OUT/smoke_$TAG.log
 cat $OUT/bench_$TAG.json; tail -n 5 $OUT/bench_$TAG.err

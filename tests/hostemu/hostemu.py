@@ -46,6 +46,7 @@ def lib():
         L.he_vis_rows.argtypes = [C.c_void_p, C.c_void_p]
         L.he_stage.argtypes = [C.c_void_p, C.c_void_p]
         L.he_stage21.argtypes = [C.c_void_p, C.c_void_p]
+        L.he_pair_obs.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -88,6 +89,12 @@ class HostEmuPool:
         a = np.ascontiguousarray(actions, dtype=np.int8)
         self.L.he_step(self.h, _p(a), _p(self.obs), _p(self.reward), _p(self.done), _p(self.direction))
         return self.obs, self.reward, self.done
+
+    def pair_obs(self, e0):
+        """observations of envs e0 .. e0 + 15 through the two-lanes-per-env path (k_rollout2)"""
+        out = np.zeros((16, 147), np.uint8)
+        self.L.he_pair_obs(self.h, e0, _p(out))
+        return out.reshape(16, 7, 7, 3)
 
     def tokens(self, i):
         t = np.zeros(72, np.int16)

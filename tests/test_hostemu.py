@@ -179,3 +179,20 @@ def test_column_record_staging_packs_21_byte_records():
         tile = np.zeros(588 + 16, np.uint8)
         L.he_stage21(words.ctypes.data_as(C.c_void_p), tile.ctypes.data_as(C.c_void_p))
         assert np.array_equal(tile[:588], by.reshape(-1))
+
+
+@pytest.mark.parametrize('level', ['GoToLocal', 'GoToObjS4', 'PickupLoc', 'PutNextLocal', 'GoTo', 'BossLevel', 'Unlock', 'GoToObjMazeS4R2'])
+def test_pair_observation_path_equals_observe(level):
+    """k_rollout2 (experimental, two lanes per environment): column halves, the see-through exchange, per-column encode and
+    the 21-byte record staging of a 16-env warp tile must reproduce observe() byte for byte, for every pose reached in play
+    (ragged last warp included)."""
+    n = 40                                           # 2 full warps of 16 envs + a ragged one of 8
+    e = _emu(level, n, np.arange(n, dtype=np.uint64) * 5 + 123)
+    obs = e.reset().copy()
+    rng = np.random.RandomState(9)
+    for t in range(150):
+        for e0 in (0, 16, 32):
+            tile = e.pair_obs(e0)
+            k = min(16, n - e0)
+            assert np.array_equal(tile[:k], obs[e0:e0 + k]), (level, t, e0)
+        obs = e.step(rng.choice(7, size=n, p=[0.15, 0.15, 0.4, 0.1, 0.08, 0.1, 0.02]).astype(np.int8))[0].copy()

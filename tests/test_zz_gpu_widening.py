@@ -112,3 +112,30 @@ def test_rollout_equals_stepwise_new_levels(level):
             o, r, d = b.step(acts[t])
             assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]) and torch.equal(d, done[t]), (rep, t)
     assert a.counters()['errors'] == 0
+
+
+@pytest.mark.skipif(__import__('os').environ.get('BB_TEST_ROLLOUT2') != '1',
+                    reason='k_rollout2 (two lanes per env) is experimental and has never run on a GPU: opt in with BB_TEST_ROLLOUT2=1')
+@pytest.mark.parametrize('level,n,T', [('GoToLocal', 4096, 24), ('GoToLocal', 1000, 40), ('PickupLoc', 200, 40), ('GoToObjS4', 256, 40),
+                                        ('PutNextLocal', 333, 32), ('BossLevel', 512, 16), ('GoToObjMazeS4R2', 300, 40)])
+def test_rollout2_equals_stepwise(monkeypatch, level, n, T):
+    """BB_ROLLOUT_LANES=2: bb_pool_rollout through k_rollout2 == T x bb_pool_step (and, transitively, the oracle)."""
+    import torch
+    from babyai_b200 import BabyAIVecEnv
+    seeds = np.arange(n, dtype=np.uint64) + 77
+    monkeypatch.setenv('BB_ROLLOUT_LANES', '2')
+    a = BabyAIVecEnv(level, n, seeds=seeds)
+    monkeypatch.delenv('BB_ROLLOUT_LANES')
+    b = BabyAIVecEnv(level, n, seeds=seeds)
+    acts = torch.randint(0, 7, (T, n), device='cuda', dtype=torch.int8)
+    a.reset(); b.reset()
+    obs = torch.zeros((T, n, 7, 7, 3), dtype=torch.uint8, device='cuda')
+    rew = torch.zeros((T, n), device='cuda')
+    done = torch.zeros((T, n), dtype=torch.uint8, device='cuda')
+    dirs = torch.zeros((T, n), dtype=torch.int8, device='cuda')
+    for rep in range(3):
+        a.rollout(acts, obs, rew, done, dirs)
+        for t in range(T):
+            o, r, d = b.step(acts[t])
+            assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]) and torch.equal(d, done[t]) and torch.equal(b.direction, dirs[t]), (rep, t)
+    assert a.counters() == b.counters() and a.counters()['errors'] == 0
