@@ -25,6 +25,7 @@
 #include "../../include/babyai_b200.h"
 #include "env_logic.cuh"
 #include "level_params.h"
+#include "rollout2.cuh"
 
 using namespace bb;
 
@@ -932,39 +933,9 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
     }
 }
 
-// =====================================================================================================================
-// k_rollout2 -- EXPERIMENTAL (BB_ROLLOUT_LANES=2; written after round 1's GPU budget was spent, never run on a GPU yet):
-// the persistent rollout kernel with TWO LANES PER ENVIRONMENT.  k_rollout is latency bound with 4.2 warps per scheduler and
-// 8.7 cycles per issued instruction (profiles/r01y_ncu_rollout_details.txt); the number of stepping warps is capped by the
-// problem size (65 536 envs = 2 048 warps), so the remaining parallelism is inside an env.  Here a warp serves 16 envs:
-//   * the even lane of a pair applies the action and runs the verifier (step_env) and broadcasts the hot record;
-//   * a finished env's next level is copied from the ring by the two lanes together (half the dependent loads each);
-//   * the observation is split by view columns (even lane: columns 0..3 = 84 bytes, odd lane: 4..6 = 63 bytes; one
-//     shuffle exchanges the see-through bits on multi-room levels), encoded per column and staged as 21-byte records
-//     (pair_cols_load / pair_cols_encode / pair_stage in env_logic.cuh: checked against observe() in the host build).
-// Twice the stepping warps for an estimated 1.3-1.5 x the instructions.  CTA = 4 stepping warps (64 envs, the same
-// shared-memory footprint per env as k_rollout) + the generator warp of the fused mode; 7 CTAs per SM = 35 warps need
-// <= 58 registers per thread (k_rollout compiles to 56 registers with 80 bytes of spills under that cap).
-constexpr int R2_WARPS = 4, R2_ENVS = 16;
-constexpr int R2_THREADS = 32 * R2_WARPS, R2_THREADS_FUSED = R2_THREADS + 32;
-constexpr int TILE2_WORDS = R2_ENVS * OBS_BYTES / 4;              // 588 words = 2352 B per warp
-
-__device__ __forceinline__ void store_tile2(const uint32_t *tile, uint8_t *dst, int lane, int valid_envs)
-{
-    if (valid_envs == R2_ENVS && (((uintptr_t)dst) & 15) == 0) {
-        const uint4 *s = reinterpret_cast<const uint4 *>(tile);
-        uint4 *d = reinterpret_cast<uint4 *>(dst);
-#pragma unroll
-        for (int i = 0; i < (TILE2_WORDS / 4 + 31) / 32; i++) {
-            const int idx = lane + 32 * i;
-            if (idx < TILE2_WORDS / 4) d[idx] = s[idx];
-        }
-    } else {
-        const uint8_t *s = reinterpret_cast<const uint8_t *>(tile);
-        const int nbytes = valid_envs * OBS_BYTES;
-        for (int i = lane; i < nbytes; i += 32) dst[i] = s[i];
-    }
-}
+// k_rollout2 -- EXPERIMENTAL (BB_ROLLOUT_LANES=2): two lanes per environment; see rollout2.cuh.  The generator warp below is
+// the one of k_rollout, for the CTA's 64 envs.
+static_assert(R2_OBJ_STRIDE == SM_OBJ_STRIDE && R2_INS_STRIDE == SM_INS_STRIDE, "rollout2.cuh record strides");
 
 __global__ void __launch_bounds__(R2_THREADS_FUSED, 7)
 k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
@@ -1039,143 +1010,9 @@ k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ ac
         }
         return;
     }
-    // ---- stepping warps: lane = 2 * (env within the warp) + half ----
-    const int el = lane >> 1, hf = lane & 1, even = lane & ~1;
-    const int env0 = (blockIdx.x * R2_WARPS + warp) * R2_ENVS, env = env0 + el;
-    int nv = n - env0; nv = nv > R2_ENVS ? R2_ENVS : (nv < 0 ? 0 : nv);
-    const bool valid = el < nv;
-    uint32_t *sg = smr + warp * warp_words, *so = sg + R2_ENVS * gs, *si = so + R2_ENVS * SM_OBJ_STRIDE;
-    uint32_t *tile = si + R2_ENVS * SM_INS_STRIDE;          // 16-byte aligned: every term is a multiple of 4 words
-    warp_copy_records<true>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
-    warp_copy_records<true>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
-    warp_copy_records<true>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
-    EnvHot h;
-    { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
-    uint32_t head = 0, avail = 0;
-    float last_rew = 0.0f;
-    if (valid) {
-        h = P.hot[env];
-        head = P.head[env];
-        avail = (fused ? P.tail[env] : __ldcg(P.tail_pub + env)) - head;
-        if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env];
-    }
-    if (fused) __syncthreads();
-    __syncwarp();
-    SmemOnlyMem mem(lp, reinterpret_cast<uint8_t *>(sg + el * gs), reinterpret_cast<uint8_t *>(so + el * SM_OBJ_STRIDE),
-                    reinterpret_cast<uint8_t *>(si + el * SM_INS_STRIDE));
-    const bool single_room = lp.num_rows == 1 && lp.num_cols == 1;
-    uint32_t n_step = 0, n_end = 0, n_succ = 0, n_err = 0, consumed = 0;      // counters: even lanes only
-    int a_next = 0;
-    if (valid) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + env));
-    for (int t = 0; t < T; t++) {
-        const int a = a_next;
-        if (valid && t + 1 < T) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + (size_t)(t + 1) * n + env));
-        float rew = 0.0f; bool dn = false; int begin = 0;
-        if (valid && hf == 0) {                             // the even lane steps the env
-            if (!(h.dirflags & 4)) {
-                const StepResult sr = step_env(h, mem, a);
-                rew = sr.reward; dn = sr.done;
-                n_step++; n_end += dn; n_succ += sr.success;
-                if (dn) {
-                    if (mode == BB_MODE_AUTORESET) begin = 1;
-                    else { h.dirflags |= 4; last_rew = rew; }
-                }
-            } else { rew = last_rew; dn = true; }
-        }
-        __syncwarp();                                       // step_env's shared-memory writes -> the partner lane
-        {   // the pair's hot record and "episode begins" flag from the even lane
-            uint4 hv = *reinterpret_cast<uint4 *>(&h);
-            hv.x = __shfl_sync(FULL, hv.x, even); hv.y = __shfl_sync(FULL, hv.y, even);
-            hv.z = __shfl_sync(FULL, hv.z, even); hv.w = __shfl_sync(FULL, hv.w, even);
-            h = *reinterpret_cast<EnvHot *>(&hv);
-            begin = __shfl_sync(FULL, begin, even);
-        }
-        if (begin && valid) {                               // uniform within the pair: both lanes copy the next level
-            if (consumed < avail && avail <= (uint32_t)P.depth) {
-                const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
-                uint32_t *mg = reinterpret_cast<uint32_t *>(mem.g);
-                for (int k = hf; k < lp.cells_pad / 16; k += 2) {
-                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.grid) + k);
-                    mg[4 * k] = v.x; mg[4 * k + 1] = v.y; mg[4 * k + 2] = v.z; mg[4 * k + 3] = v.w;
-                }
-                uint32_t *mo = reinterpret_cast<uint32_t *>(mem.o);
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const int c = 2 * k + hf;
-                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.obj) + c);
-                    mo[4 * c] = v.x; mo[4 * c + 1] = v.y; mo[4 * c + 2] = v.z; mo[4 * c + 3] = v.w;
-                }
-                uint32_t *mi = reinterpret_cast<uint32_t *>(mem.i);
-                for (int c = hf; c < 3; c += 2) {
-                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.ins) + c);
-                    mi[4 * c] = v.x; mi[4 * c + 1] = v.y; mi[4 * c + 2] = v.z; mi[4 * c + 3] = v.w;
-                }
-                uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
-                for (int k = hf; k < lp.max_tokens / 8; k += 2) lt[k] = __ldcg(reinterpret_cast<const uint4 *>(o.tok) + k);
-                const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(o.hot));
-                h = *reinterpret_cast<const EnvHot *>(&hv);
-                consumed++;
-            } else if (hf == 0) n_err++;
-        }
-        __syncwarp();                                       // the swapped-in level -> both lanes
-        if (valid && hf == 0 && mode == BB_MODE_AUTORESET && (int)h.step_count + 2 == (int)h.max_steps && consumed < avail) {
-            const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.grid));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.obj));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.obj) + 64));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.ins));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.ins) + 32));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.hot));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(o.tok));
-        }
-        // ---- observation: this lane's half of the view columns ----
-        uint32_t lo[4], hi[4], oc[4][6];
-        const int dir = h.dirflags & 3;
-        const ViewGeom v = view_geom(lp, h.x, h.y, dir);
-        uint32_t cm = 0;
-        if (valid) cm = pair_cols_load(mem, v, hf, lo, hi);
-        uint32_t other = 0;
-        if (!single_room) other = __shfl_xor_sync(FULL, cm, 1);
-        if (valid) pair_cols_encode(lp, v, h.x, h.y, dir, carry_cell_of(h, mem), hf, lo, hi, hf ? other : cm, hf ? cm : other, oc);
-        else {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-#pragma unroll
-                for (int j = 0; j < 6; j++) oc[k][j] = 0;
-        }
-        const uint32_t next_first = __shfl_down_sync(FULL, oc[0][0], 1);
-        pair_stage(tile, oc, el, hf, next_first);
-        if (valid && hf == 0) {
-            const size_t oi = (size_t)t * n + env;
-            if (reward) reward[oi] = rew;
-            if (done) done[oi] = dn ? 1 : 0;
-            if (dirs) dirs[oi] = (int8_t)dir;
-        }
-        __syncwarp();
-        if (nv > 0) store_tile2(tile, obs + ((size_t)t * n + env0) * OBS_BYTES, lane, nv);
-        __syncwarp();                                       // the tile is rewritten in the next iteration
-    }
-    __syncwarp();
-    warp_copy_records<false>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
-    warp_copy_records<false>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
-    warp_copy_records<false>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
-    if (valid && hf == 0) {
-        P.hot[env] = h;
-        P.head[env] = head + consumed;
-        if (mode == BB_MODE_FREEZE) P.last_reward[env] = last_rew;
-    }
-    for (int off = 16; off; off >>= 1) {
-        n_step += __shfl_down_sync(FULL, n_step, off); n_end += __shfl_down_sync(FULL, n_end, off);
-        n_succ += __shfl_down_sync(FULL, n_succ, off); n_err += __shfl_down_sync(FULL, n_err, off);
-    }
-    if (fused && lane == 0) atomicAdd(const_cast<int *>(s_done), 1);
-    if (lane == 0) {
-        unsigned long long *c = P.warp_counters + 4ull * (blockIdx.x * R2_WARPS + warp);
-        if (n_step) atomicAdd(c + 0, (unsigned long long)n_step);
-        if (n_end) atomicAdd(c + 1, (unsigned long long)n_end);
-        if (n_succ) atomicAdd(c + 2, (unsigned long long)n_succ);
-        if (n_err) atomicAdd(c + 3, (unsigned long long)n_err);
-    }
+    // ---- stepping warps: rollout2.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu) ----
+    rollout2_step_warp<PoolPtrs, SmemOnlyMem>(lp, P, actions, obs, reward, done, dirs, n, T, mode, fused, smr + warp * warp_words,
+                                              lane, blockIdx.x * R2_WARPS + warp, s_done);
 }
 
 // Level generation, decoupled from the step: tops every environment's ring up to `target` levels.

@@ -107,3 +107,55 @@ class HostEmuPool:
         self.L.he_get_state(self.h, i, _p(grid), _p(info))
         return grid, dict(agent_x=int(info[0]), agent_y=int(info[1]), agent_dir=int(info[2]), carrying=int(info[3]),
                           step_count=int(info[4]), max_steps=int(info[5]), draws=int(info[6]), attempts=int(info[7]))
+
+
+# ---- k_rollout2's stepping role on OS threads (simt_rollout2.cpp) -------------------------------------------------
+SRC2 = os.path.join(HERE, 'simt_rollout2.cpp')
+OUT2 = os.path.join(HERE, 'libsimt_rollout2.so')
+DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout2.cuh')] + DEPS[1:]
+_lib2 = None
+
+
+def lib2():
+    global _lib2
+    if _lib2 is None:
+        if not (os.path.exists(OUT2) and all(os.path.getmtime(OUT2) >= os.path.getmtime(d) for d in DEPS2)):
+            subprocess.check_call(['g++', '-O1', '-g', '-std=c++20', '-pthread', '-Wall', '-Wno-unknown-pragmas', '-Wno-unused-function',
+                                   '-fno-strict-aliasing', '-ffp-contract=off', '-shared', '-fPIC', SRC2, '-o', OUT2])
+        L = C.CDLL(OUT2)
+        L.r2_create.restype = C.c_void_p
+        L.r2_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.r2_destroy.argtypes = [C.c_void_p]
+        L.r2_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.r2_tokens.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.r2_max_tokens.argtypes = [C.c_void_p]
+        _lib2 = L
+    return _lib2
+
+
+class Rollout2Pool:
+    """A pool in pool.cu's memory layout (SoA + level rings) stepped by rollout2_step_warp, one OS thread per lane."""
+
+    def __init__(self, spec, n, seeds, depth=24, mode=0):
+        self.L, self.n = lib2(), n
+        s = np.ascontiguousarray(seeds, dtype=np.uint64)
+        self.h = self.L.r2_create(C.byref(spec), n, depth, _p(s), mode)
+
+    def __del__(self):
+        try:
+            self.L.r2_destroy(self.h)
+        except Exception:
+            pass
+
+    def rollout(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int8)
+        T, n = a.shape
+        obs, rew = np.zeros((T, n, 7, 7, 3), np.uint8), np.zeros((T, n), np.float32)
+        done, dirs, cnt = np.zeros((T, n), np.uint8), np.zeros((T, n), np.int8), np.zeros(4, np.int64)
+        self.L.r2_rollout(self.h, _p(a), T, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
+        return obs, rew, done, dirs, cnt
+
+    def tokens(self, i):
+        t = np.zeros(self.L.r2_max_tokens(self.h), np.int16)
+        self.L.r2_tokens(self.h, i, _p(t))
+        return t

@@ -1,0 +1,181 @@
+// simt_rollout2.cpp -- TEST-ONLY: runs the stepping role of k_rollout2 (babyai_b200/csrc/rollout2.cuh, the very
+// function the kernel calls) on the host with ONE OS THREAD PER LANE.  The warp primitives the function uses
+// (__syncwarp, __shfl_sync, __shfl_xor_sync, __shfl_down_sync) are rendezvous on a per-warp barrier; every lane of a warp
+// reaches them in the same order (none sits inside divergent code), which is exactly what the hardware requires too --
+// a lane that skipped one would dead-lock here instead of silently reading garbage.  Global memory is host memory laid
+// out as pool.cu lays it out (struct of arrays + the per-env ring of pre-generated levels); shared memory is a per-warp
+// buffer.  The GPU-less suite steps whole rollouts through this and compares them with the per-step path.
+//
+// The product never loads this file.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+#include <barrier>
+#include <thread>
+#include <vector>
+
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v = { x, y, z, w }; return v; }
+
+// ---- the warp primitives of rollout2.cuh, emulated ---------------------------------------------------------------
+struct WarpCtx {
+    std::barrier<> bar{32};
+    uint32_t xchg[32];
+};
+static thread_local WarpCtx *tl_warp = nullptr;
+static thread_local int tl_lane = 0;
+
+static inline void emu_syncwarp() { tl_warp->bar.arrive_and_wait(); }
+static inline uint32_t emu_exchange(uint32_t v, int src)
+{
+    tl_warp->xchg[tl_lane] = v;
+    tl_warp->bar.arrive_and_wait();
+    const uint32_t r = tl_warp->xchg[src & 31];
+    tl_warp->bar.arrive_and_wait();                      // nobody overwrites xchg before everybody has read it
+    return r;
+}
+template <class T> static inline T emu_shfl(T v, int src) { return (T)emu_exchange((uint32_t)v, src); }
+template <class T> static inline T emu_shfl_down(T v, int d) { return (T)emu_exchange((uint32_t)v, tl_lane + d < 32 ? tl_lane + d : tl_lane); }
+template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exchange((uint32_t)v, tl_lane ^ m); }
+
+#define BB_DEV inline
+#define BB_SYNCWARP() emu_syncwarp()
+#define BB_SYNCTHREADS() abort()                          /* fused launches (generator warp) are not emulated */
+#define BB_SHFL(v, src) emu_shfl((v), (src))
+#define BB_SHFL_XOR(v, m) emu_shfl_xor((v), (m))
+#define BB_SHFL_DOWN(v, d) emu_shfl_down((v), (d))
+#define BB_LDCG(p) (*(p))
+#define BB_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+#define BB_PREFETCH_L2(p) ((void)(p))
+#define BB_LD_S8(p) ((int)*(p))
+
+#include "../../babyai_b200/csrc/rollout2.cuh"
+#include "../../babyai_b200/csrc/level_params.h"
+
+using namespace bb;
+
+// the accessor k_rollout / k_rollout2 use on shared memory (pool.cu SmemOnlyMem), restated for the host
+struct HostSmemMem {
+    static constexpr bool untracked = false;
+    const LevelParams &lp; uint8_t *g, *o, *i;
+    HostSmemMem(const LevelParams &lp_, uint8_t *g_, uint8_t *o_, uint8_t *i_) : lp(lp_), g(g_), o(o_), i(i_) {}
+    int cell(int x, int y) const { return g[y * lp.rs_g + x]; }
+    void set_cell(int x, int y, int v) { bb::set_cell(lp, g, x, y, v); }
+    uint32_t word_at(int off) const { uint32_t v; memcpy(&v, g + off, 4); return v; }
+    int ox(int k) const { return o[k]; }
+    int oy(int k) const { return o[MAXOBJ + k]; }
+    int otc(int k) const { return o[2 * MAXOBJ + k]; }
+    void set_oxy(int k, int x, int y) { o[k] = (uint8_t)x; o[MAXOBJ + k] = (uint8_t)y; }
+    uint32_t desc_mask(int d) const { uint32_t v; memcpy(&v, i + 4 * d, 4); return v; }
+    int leaf_kind(int l) const { return i[32 + l]; }
+    int leaf_pre(int l) const { return i[36 + l]; }
+    void set_leaf_pre(int l, int v) { i[36 + l] = (uint8_t)v; }
+    int root_kind() const { return i[40]; }
+    int side_and() const { return i[41]; }
+    int flags() const { return i[42]; }
+    void set_flags(int v) { i[42] = (uint8_t)v; }
+};
+
+struct HostPoolPtrs {                                     // the members of pool.cu's PoolPtrs the stepping role touches
+    uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
+    uint8_t *rgrid; EnvHot *rhot; ObjTab *robj; InstrRec *rins; int16_t *rtok;
+    uint32_t *head, *tail, *tail_pub;
+    float *last_reward;
+    unsigned long long *warp_counters;
+    int32_t depth, n;
+};
+
+struct RPool {
+    LevelParams lp; int n, D, mode;
+    std::vector<uint8_t> grid, rgrid, locked_room;
+    std::vector<EnvHot> hot, rhot; std::vector<ObjTab> obj, robj; std::vector<InstrRec> ins, rins;
+    std::vector<int16_t> tok, rtok;
+    std::vector<uint32_t> head, tail, tail_pub;
+    std::vector<RngRec> rng; std::vector<float> last_reward;
+    std::vector<unsigned long long> counters;
+    HostPoolPtrs P;
+};
+
+static LevelOut slot_of(RPool *p, int env, int slot) { return r2_ring_slot(p->lp, p->P, env, slot); }
+
+static void refill(RPool *p)                              // k_gen's job: top every ring up to D levels
+{
+    for (int e = 0; e < p->n; e++)
+        while ((int)(p->tail[e] - p->head[e]) < p->D) {
+            GenMemX mem;
+            generate_level(p->lp, slot_of(p, e, (int)(p->tail[e] % (uint32_t)p->D)), &p->rng[e], &p->locked_room[e], &mem);
+            p->tail[e]++;
+        }
+    p->tail_pub = p->tail;
+    p->P.tail_pub = p->tail_pub.data();
+}
+
+extern "C" {
+
+RPool *r2_create(const bb_level_spec *spec, int n, int depth, const uint64_t *seeds, int mode)
+{
+    RPool *p = new RPool();
+    const char *err = make_level_params(spec, &p->lp);
+    if (err) { fprintf(stderr, "simt_rollout2: %s\n", err); abort(); }
+    const LevelParams &lp = p->lp;
+    p->n = n; p->D = depth; p->mode = mode;
+    const size_t N = (size_t)n, DN = (size_t)depth * n;
+    p->grid.assign(N * lp.cells_pad, 0); p->rgrid.assign(DN * lp.cells_pad, 0);
+    p->hot.resize(N); p->rhot.resize(DN); p->obj.resize(N); p->robj.resize(DN); p->ins.resize(N); p->rins.resize(DN);
+    memset(p->hot.data(), 0, N * sizeof(EnvHot)); memset(p->obj.data(), 0, N * sizeof(ObjTab)); memset(p->ins.data(), 0, N * sizeof(InstrRec));
+    p->tok.assign(N * lp.max_tokens, 0); p->rtok.assign(DN * lp.max_tokens, 0);
+    p->head.assign(N, 0); p->tail.assign(N, 0); p->tail_pub.assign(N, 0);
+    p->rng.resize(N); p->last_reward.assign(N, 0.f); p->locked_room.assign(N, 0xFF);
+    p->counters.assign(4 * (N / R2_ENVS + 2), 0);
+    for (int e = 0; e < n; e++) { p->rng[e].seed = seeds[e]; p->rng[e].draws = 0; }
+    HostPoolPtrs &P = p->P;
+    P.grid = p->grid.data(); P.hot = p->hot.data(); P.obj = p->obj.data(); P.ins = p->ins.data(); P.tok = p->tok.data();
+    P.rgrid = p->rgrid.data(); P.rhot = p->rhot.data(); P.robj = p->robj.data(); P.rins = p->rins.data(); P.rtok = p->rtok.data();
+    P.head = p->head.data(); P.tail = p->tail.data(); P.tail_pub = p->tail_pub.data();
+    P.last_reward = p->last_reward.data(); P.warp_counters = p->counters.data();
+    P.depth = depth; P.n = n;
+    // reset: generate, then take the first level of every ring as the live state (what bb_pool_reset does)
+    refill(p);
+    for (int e = 0; e < n; e++) {
+        const LevelOut o = slot_of(p, e, 0);
+        memcpy(P.grid + (size_t)e * lp.cells_pad, o.grid, lp.cells_pad);
+        P.hot[e] = *o.hot; P.obj[e] = *o.obj; P.ins[e] = *o.ins;
+        memcpy(P.tok + (size_t)e * lp.max_tokens, o.tok, lp.max_tokens * sizeof(int16_t));
+        p->head[e] = 1;
+    }
+    refill(p);
+    return p;
+}
+void r2_destroy(RPool *p) { delete p; }
+
+// one bb_pool_rollout worth of k_rollout2 (non-fused launch): every warp of the grid, 32 threads each
+void r2_rollout(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *reward, uint8_t *done, int8_t *dirs, int64_t *counters4)
+{
+    const LevelParams &lp = p->lp;
+    const int gs = (lp.cells_pad >> 2) | 1;
+    const int warp_words = R2_ENVS * (gs + R2_OBJ_STRIDE + R2_INS_STRIDE) + TILE2_WORDS;
+    const int nwarps = (p->n + R2_ENVS - 1) / R2_ENVS;
+    for (int wg = 0; wg < nwarps; wg++) {
+        WarpCtx ctx;
+        std::vector<uint32_t> smem((size_t)warp_words + 8, 0xDEADBEEFu);
+        uint32_t *base = smem.data();
+        while (((uintptr_t)base) & 15) base++;                // the kernel's tile is 16-byte aligned
+        std::vector<std::thread> th;
+        for (int lane = 0; lane < 32; lane++)
+            th.emplace_back([&, lane]() {
+                tl_warp = &ctx; tl_lane = lane;
+                rollout2_step_warp<HostPoolPtrs, HostSmemMem>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, false, base, lane, wg, nullptr);
+            });
+        for (auto &t : th) t.join();
+    }
+    refill(p);                                                // the refill pass between launches
+    for (int k = 0; k < 4; k++) counters4[k] = 0;
+    for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
+}
+
+void r2_tokens(RPool *p, int e, int16_t *out) { memcpy(out, p->tok.data() + (size_t)e * p->lp.max_tokens, p->lp.max_tokens * sizeof(int16_t)); }
+int r2_max_tokens(RPool *p) { return p->lp.max_tokens; }
+
+}  // extern "C"

@@ -196,3 +196,51 @@ def test_pair_observation_path_equals_observe(level):
             k = min(16, n - e0)
             assert np.array_equal(tile[:k], obs[e0:e0 + k]), (level, t, e0)
         obs = e.step(rng.choice(7, size=n, p=[0.15, 0.15, 0.4, 0.1, 0.08, 0.1, 0.02]).astype(np.int8))[0].copy()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('level,n,T', [('GoToLocal', 40, 40), ('PickupLoc', 35, 40), ('GoToObjS4', 16, 40), ('PutNextLocal', 24, 32),
+                                        ('GoToObjMazeS4R2', 21, 40), ('BossLevel', 18, 16)])
+def test_rollout2_stepping_role_on_threads(level, n, T):
+    """k_rollout2's stepping role (babyai_b200/csrc/rollout2.cuh: the very function the kernel calls) executed with one OS
+    thread per lane and the warp shuffles / barriers as rendezvous: whole rollouts -- step on the even lane, broadcast,
+    two-lane level swap-in from the ring, split observation, record staging, tile stores, state write-back, counters --
+    must equal the per-step path (which is checked against the oracle), ragged last warps included."""
+    seeds = np.arange(n, dtype=np.uint64) * 11 + 321
+    ref = _emu(level, n, seeds)
+    r2 = hostemu.Rollout2Pool(level_spec(level), n, seeds, depth=max(24, T + 8))
+    obs0 = ref.reset().copy()
+    rng = np.random.RandomState(17)
+    steps = episodes = 0
+    for rep in range(5 if level == 'PutNextLocal' else 3):             # PutNextLocal: max_steps = 128
+        acts = rng.choice(7, size=(T, n), p=[0.13, 0.13, 0.4, 0.12, 0.08, 0.12, 0.02]).astype(np.int8)
+        obs, rew, done, dirs, cnt = r2.rollout(acts)
+        for t in range(T):
+            o, r, d = ref.step(acts[t])
+            assert np.array_equal(obs[t], o), (level, rep, t, np.nonzero((obs[t] != o).reshape(n, -1).any(1))[0])
+            assert np.array_equal(rew[t].view(np.uint32), r.view(np.uint32)) and np.array_equal(done[t], d), (level, rep, t)
+            assert np.array_equal(dirs[t], ref.direction), (level, rep, t)
+            episodes += int(d.sum())
+        steps += T * n
+        assert cnt[0] == steps and cnt[1] == episodes and cnt[3] == 0, (cnt, steps, episodes)
+        assert all(np.array_equal(r2.tokens(i)[:8], ref.tokens(i)[:8]) for i in range(n))
+    assert episodes > 0 or level == 'BossLevel'
+    del obs0
+
+
+@pytest.mark.timeout(300)
+def test_rollout2_stepping_role_freeze_mode():
+    """ManyEnvs flavour in k_rollout2: finished envs freeze and replay their terminal result (evaluate.py:72-78)."""
+    level, n, T = 'GoToLocal', 20, 40
+    seeds = np.arange(n, dtype=np.uint64) + 10 ** 9
+    ref = _emu(level, n, seeds, mode=1)
+    r2 = hostemu.Rollout2Pool(level_spec(level), n, seeds, mode=1)
+    ref.reset()
+    rng = np.random.RandomState(3)
+    for rep in range(2):                                  # max_steps = 64: everything is frozen during the second rollout
+        acts = rng.randint(0, 7, (T, n)).astype(np.int8)
+        obs, rew, done, dirs, cnt = r2.rollout(acts)
+        for t in range(T):
+            o, r, d = ref.step(acts[t])
+            assert np.array_equal(obs[t], o) and np.array_equal(rew[t].view(np.uint32), r.view(np.uint32)) and np.array_equal(done[t], d), (rep, t)
+    assert done[-1].all()
