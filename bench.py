@@ -169,6 +169,53 @@ def run_reference(args, rank):
     print(json.dumps(out), flush=True)
 
 
+def lanes2_probe(args):
+    """Child process of the default bench run (own CUDA context: whatever happens here cannot touch the parent's numbers).
+    k_rollout2 -- the experimental two-lanes-per-environment rollout kernel (BB_ROLLOUT_LANES=2, csrc/rollout2.cuh), written
+    after round 1's GPU budget was spent -- against k_rollout in the same process: bit equality of three rollouts from the
+    same seeds and actions, then the same timing loop for both.  Prints one JSON dict."""
+    import numpy as np
+    import torch
+    from babyai_b200 import BabyAIVecEnv
+    n, T = args.envs, CHUNK
+    seeds = np.array([100 + i for i in range(n)], dtype=np.uint64)
+    os.environ.pop('BB_ROLLOUT_LANES', None)
+    pools = [BabyAIVecEnv(args.level, n, seeds=seeds)]
+    os.environ['BB_ROLLOUT_LANES'] = '2'                 # read by bb_pool_create
+    pools.append(BabyAIVecEnv(args.level, n, seeds=seeds))
+    os.environ.pop('BB_ROLLOUT_LANES')
+    dev = torch.device('cuda', 0)
+    gen = torch.Generator(device=dev).manual_seed(5)
+    acts = torch.randint(0, 7, (T, n), device=dev, dtype=torch.int8, generator=gen)
+    bufs = [(torch.zeros((T, n, 7, 7, 3), dtype=torch.uint8, device=dev), torch.zeros((T, n), device=dev),
+             torch.zeros((T, n), dtype=torch.uint8, device=dev), torch.zeros((T, n), dtype=torch.int8, device=dev)) for _ in pools]
+    for p in pools:
+        p.reset()
+    equal = True
+    for _ in range(3):
+        for p, b in zip(pools, bufs):
+            p.rollout(acts, *b)
+        torch.cuda.synchronize()
+        equal = equal and all(bool(torch.equal(x, y)) for x, y in zip(*bufs))
+    out = {'bit_equal_to_k_rollout': equal, 'level': args.level, 'envs': n, 'steps_per_launch': T}
+    for name, p, b in (('k_rollout', pools[0], bufs[0]), ('k_rollout2', pools[1], bufs[1])):
+        for _ in range(5):
+            p.rollout(acts, *b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 40
+        for _ in range(reps):
+            p.rollout(acts, *b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        kr = [p.rollout_timed(acts, *b)[0] for _ in range(8)][2:]
+        out[name] = {'us_per_step': 1e3 * ms / T, 'env_steps_per_s': n * T / (ms * 1e-3), 'kernel_ms': sum(kr) / len(kr),
+                     'errors': p.counters()['errors']}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -178,6 +225,8 @@ def main():
     ap.add_argument('--envs', type=int, default=N_ENVS, help='environments per GPU')
     ap.add_argument('--level', default=LEVEL)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--lanes2-probe', action='store_true', help='internal: the k_rollout2 child process')
+    ap.add_argument('--no-probe', action='store_true', help='skip the k_rollout2 child process')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -186,6 +235,9 @@ def main():
 
     if args.impl == 'reference':
         run_reference(args, rank)
+        return
+    if args.lanes2_probe:
+        lanes2_probe(args)
         return
 
     import numpy as np
@@ -329,6 +381,17 @@ def main():
             learner[key] = {'error': repr(ex)[:300]}
     learner['api'] = 'DeviceParallelEnv.step + ObssPreprocessor (observations stay in HBM)'
 
+    # ---- experimental kernel, in a child process with its own CUDA context (single-GPU runs only; informational) ----
+    probe = None
+    if rank == 0 and world == 1 and not args.no_probe:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--lanes2-probe', '--level', args.level, '--envs', str(n)],
+                               capture_output=True, text=True, timeout=300)
+            lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+            probe = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
+        except Exception as ex:
+            probe = {'error': repr(ex)[:300]}
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         value = world * n * K / (ms * 1e-3)
@@ -362,6 +425,7 @@ def main():
                     'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke,
                     'api': 'bb_pool_step_host, page-locked host buffers'},
             'learner_path': learner,
+            'experimental': {'k_rollout2': probe},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'counters': cnt,

@@ -15,7 +15,7 @@ echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
 ( timeout 600 python bench.py --impl reference --steps 200 --warmup 10 ) > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
 for cfg in "GoToImpUnlock 32768" "Unlock 32768" "BossLevel 32768" "GoTo 32768"; do set -- $cfg
   echo -n "$1 envs=$2: " >> $OUT/configs_$TAG.log
-  timeout 600 python bench.py --no-cpu-baseline --level $1 --envs $2 --steps 1600 --warmup 160 2>&1 | python -c "
+  timeout 600 python bench.py --no-cpu-baseline --no-probe --level $1 --envs $2 --steps 1600 --warmup 160 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
@@ -28,7 +28,7 @@ done
 echo "pytest exit $?" >> $OUT/pytest_rollout2_$TAG.log
 for lanes in 1 2; do for lv in GoToLocal PickupLoc BossLevel; do
   echo -n "$lv lanes=$lanes: " >> $OUT/ab_lanes_$TAG.log
-  BB_ROLLOUT_LANES=$lanes timeout 300 python bench.py --no-cpu-baseline --steps 2000 --warmup 200 --level $lv $( [ $lv = BossLevel ] && echo --envs 32768 ) 2>/dev/null | python -c "
+  BB_ROLLOUT_LANES=$lanes timeout 300 python bench.py --no-cpu-baseline --no-probe --steps 2000 --warmup 200 --level $lv $( [ $lv = BossLevel ] && echo --envs 32768 ) 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

@@ -64,7 +64,7 @@ def test_device_parallel_env_and_preprocessor(level, n, fused_io):
 
 def test_own_arm_json_line():
     from test_bench_contract import BASE_KEYS, _line
-    d = _line(['--steps', '80', '--warmup', '40', '--envs', '4096', '--no-cpu-baseline'])
+    d = _line(['--steps', '80', '--warmup', '40', '--envs', '4096', '--no-cpu-baseline', '--no-probe'])
     assert (BASE_KEYS - {'cpu_baseline'}) | {'roofline', 'clocks', 'per_step_api', 'counters', 'learner_path'} <= set(d)
     r = d['roofline']
     assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['achieved'] > 0 and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
