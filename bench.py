@@ -384,13 +384,16 @@ def main():
     # ---- experimental kernel, in a child process with its own CUDA context (single-GPU runs only; informational) ----
     probe = None
     if rank == 0 and world == 1 and not args.no_probe:
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--lanes2-probe', '--level', args.level, '--envs', str(n)],
-                               capture_output=True, text=True, timeout=300)
-            lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
-            probe = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
-        except Exception as ex:
-            probe = {'error': repr(ex)[:300]}
+        probe = {}
+        # the bench workload, and BASELINE config 5's per-GPU share (multi-room: 22x22 staging, k_gen beside the kernel)
+        for lv, ne in ((args.level, n),) + ((('BossLevel', 32768),) if args.level == LEVEL and n == N_ENVS else ()):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--lanes2-probe', '--level', lv, '--envs', str(ne)],
+                                   capture_output=True, text=True, timeout=300)
+                lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+                probe[lv] = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
+            except Exception as ex:
+                probe[lv] = {'error': repr(ex)[:300]}
 
     if rank == 0:
         peak, peak_src = hbm_peak()
