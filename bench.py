@@ -386,14 +386,20 @@ def main():
     if rank == 0 and world == 1 and not args.no_probe:
         probe = {}
         # the bench workload, and BASELINE config 5's per-GPU share (multi-room: 22x22 staging, k_gen beside the kernel)
-        for lv, ne in ((args.level, n),) + ((('BossLevel', 32768),) if args.level == LEVEL and n == N_ENVS else ()):
+        # (key, level, envs, extra environment): the bench workload with the fused generator warp and with refill passes
+        # instead (two separate children: whatever happens to one leaves the other's numbers), and BASELINE config 5's
+        # per-GPU share (multi-room: 22x22 staging, k_gen beside the kernel)
+        jobs = [(args.level, args.level, n, {}), (args.level + ' BB_GEN_FUSED=0', args.level, n, {'BB_GEN_FUSED': '0'})]
+        if args.level == LEVEL and n == N_ENVS:
+            jobs.append(('BossLevel', 'BossLevel', 32768, {}))
+        for key, lv, ne, extra in jobs:
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--lanes2-probe', '--level', lv, '--envs', str(ne)],
-                                   capture_output=True, text=True, timeout=300)
+                                   capture_output=True, text=True, timeout=300, env=dict(os.environ, **extra))
                 lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
-                probe[lv] = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
+                probe[key] = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
             except Exception as ex:
-                probe[lv] = {'error': repr(ex)[:300]}
+                probe[key] = {'error': repr(ex)[:300]}
 
     if rank == 0:
         peak, peak_src = hbm_peak()
