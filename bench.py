@@ -395,9 +395,12 @@ def main():
         for key, lv, ne, extra in jobs:
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--lanes2-probe', '--level', lv, '--envs', str(ne)],
-                                   capture_output=True, text=True, timeout=300, env=dict(os.environ, **extra))
+                                   capture_output=True, text=True, timeout=100, env=dict(os.environ, **extra))
                 lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
                 probe[key] = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
+            except subprocess.TimeoutExpired:
+                probe[key] = {'error': 'timed out after 100 s (child killed); remaining probes skipped'}
+                break                                        # keep the whole bench run within minutes
             except Exception as ex:
                 probe[key] = {'error': repr(ex)[:300]}
 
