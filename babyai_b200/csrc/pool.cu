@@ -26,6 +26,7 @@
 #include "env_logic.cuh"
 #include "level_params.h"
 #include "rollout2.cuh"
+#include "gen_round.cuh"
 
 using namespace bb;
 
@@ -544,69 +545,8 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
 // of bb_pool_rollout's in-stream refill needs no saved generator state.
 constexpr int GS_THREADS = 128;
 
-// One round of the small-level generator for the 32 lanes of a warp (see the comment above k_gen_small): every
-// working lane (`active`) makes one attempt at the next level of its env; on success the level is written to ring
-// slot tl % D and tl / left advance.  Called with all 32 lanes.
-template <class DS, bool PUBLISH>
-__device__ __forceinline__ void gen_small_round(const LevelParams &lp, const PoolPtrs &P, DS &ds, const bool active,
-                                                const int env, uint32_t &tl, int &left, const uint32_t D)
-{
-    const unsigned FULL = 0xFFFFFFFFu;
-    // converged top-up: when a lane that is about to draw has fewer than RING_LOW draws ready, EVERY working lane
-    // generates the blocks its ring has room for
-#define BB_TOPUP(cond)                                                                                   \
-    if (__any_sync(FULL, (cond) && ds.avail() < RING_LOW)) {                                             \
-        for (;;) {                                                                                       \
-            const bool rm = active && ds.room();                                                         \
-            if (!__any_sync(FULL, rm)) break;                                                            \
-            if (rm) ds.gen_block();                                                                      \
-        }                                                                                                \
-    }
-    // ---- one attempt per working lane ---------------------------------------------------------------
-    SmallAttempt a;
-    a.stage = ST_IDLE; a.occ = 0; a.fill = 0; a.k = 0; a.tries = 0; a.cur_tc = 0; a.agent_placed = false;
-    a.L.poss = 0; a.L.tcs = 0; a.L.nobj = 0; a.L.ax = a.L.ay = a.L.adir = 0;
-    a.L.leaf_kind = 0; a.L.d_type = 0; a.L.d_color = 0; a.L.d_loc = 0; a.L.d_mask = 0;
-    if (active) small_attempt_begin(lp, a, ds);
-    for (;;) {                                                  // placements: agent and objects, one try per trip
-        const bool placing = a.stage == ST_OBJ || a.stage == ST_AGENT;
-        if (!__any_sync(FULL, placing)) break;
-        BB_TOPUP(placing)
-        if (placing) small_place_try(lp, a, ds);
-    }
-    bool ok = a.stage == ST_PLACED;
-    if (small_needs_check(lp)) {                                // check_objs_reachable
-        if (ok) small_flood_begin(a);
-        for (;;) {
-            const bool changed = ok && small_flood_sweep(a);
-            if (!__any_sync(FULL, changed)) break;
-        }
-        ok = ok && small_flood_ok(lp, a);
-    }
-    a.tries = 0;
-    if (lp.kind == KIND_LEVELGEN) {                             // rand_obj: rejection sampling of a descriptor
-        bool trying = ok;
-        for (;;) {
-            if (!__any_sync(FULL, trying)) break;
-            BB_TOPUP(trying)
-            if (trying && small_desc_try(lp, a, ds)) trying = false;
-        }
-        ok = ok && a.stage != ST_FAIL;
-    } else {
-        BB_TOPUP(ok)
-        if (ok) small_pick(lp, a, ds);
-    }
-    // ---- write the level; the env's records are consistent after every round -------------------------
-    if (ok) {
-        emit_small_level(lp, a.L, ring_slot(lp, P, env, (int)(tl % D)));
-        tl++; left--;
-        P.tail[env] = tl;
-        if (PUBLISH) P.tail_pub[env] = tl;        // generator warp inside k_rollout: nobody reads tail_pub during the launch
-    }
-    if (active) { P.rng[env].draws = ds.draws; P.attempts[env] += 1u; }
-#undef BB_TOPUP
-}
-
+// gen_small_round: one round of the small-level generator for the 32 lanes of a warp -- gen_round.cuh (also compiled for
+// the host, with the warp vote emulated by threads, in tests/hostemu)
 
 __global__ void k_gen_scan(const PoolPtrs P, const int n, const int target, const int snap_heads)
 {
@@ -695,9 +635,7 @@ constexpr int R_THREADS_FUSED = R_THREADS + 32;
 // run their T steps (k_rollout issues ~48 % of the SM's slots: latency-bound), a third warp refills the rings of the
 // CTA's 64 envs with the same round function as k_gen_small -- in issue slots that are idle anyway, with no
 // refill pass between launches.  Its shared-memory area: draw rings of 8 Philox blocks per lane, the work list.
-typedef DrawRingT<8> RolloutRing;
-constexpr int RG_RING_WORDS = 32 * RolloutRing::RING_WORDS;            // 1024 words
-constexpr int RG_AREA_WORDS = RG_RING_WORDS + 64 /*tails*/ + 32 /*deficits, u16*/ + 16 /*list, u8*/ + 4 /*flag*/;
+// RolloutRing, RG_RING_WORDS, RG_AREA_WORDS: gen_round.cuh
 
 struct SmemOnlyMem {            // lane-private records in shared memory (byte addressable; odd word strides)
     const LevelParams &lp; uint8_t *g, *o, *i;
@@ -943,7 +881,6 @@ k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ ac
            const int mode, const int gen_rounds, const int gen_min_active)
 {
     extern __shared__ __align__(16) uint32_t smr[];
-    const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwords = lp.cells_pad >> 2, gs = gwords | 1;
     const int warp_words = R2_ENVS * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE2_WORDS;
@@ -951,63 +888,7 @@ k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ ac
     uint32_t *g_area = smr + R2_WARPS * warp_words;
     volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
     if (warp == R2_WARPS) {
-        // ---- generator warp (fused launches only): the same role as in k_rollout, for the CTA's 64 envs ----
-        const uint32_t D = (uint32_t)P.depth;
-        uint32_t *ring = g_area, *s_tl = g_area + RG_RING_WORDS;
-        uint16_t *s_def = reinterpret_cast<uint16_t *>(s_tl + 64);
-        uint8_t *list = reinterpret_cast<uint8_t *>(s_tl + 64 + 32);
-        const int cta_env0 = blockIdx.x * R2_WARPS * R2_ENVS;
-        int cta_nv = n - cta_env0; cta_nv = cta_nv > 64 ? 64 : (cta_nv < 0 ? 0 : cta_nv);
-        int cnt = 0;
-        bool urgent = false;
-        if (lane == 0) *s_done = 0;
-#pragma unroll
-        for (int h2 = 0; h2 < 2; h2++) {
-            const int i = 32 * h2 + lane;
-            bool need = false;
-            if (i < cta_nv) {
-                const uint32_t hd = P.head[cta_env0 + i], tl0 = P.tail[cta_env0 + i];
-                const int have = (int)(tl0 - hd);
-                s_tl[i] = tl0; s_def[i] = (uint16_t)((int)D - have);
-                need = have < (int)D;
-                urgent = urgent || have < 2 * T;
-            }
-            const uint32_t m = __ballot_sync(FULL, need);
-            if (need) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
-            cnt += __popc(m);
-        }
-        const bool must_complete = __any_sync(FULL, urgent);
-        __syncthreads();                                  // the stepping warps have read head / tail: generation may start
-        RolloutRing ds;
-        ds.init(ring + lane, 32, 0, 0);
-        int env_g = -1, left = 0, next = 0, rounds = 0;
-        uint32_t tl = 0;
-        for (;;) {
-            const bool idle = left == 0;
-            const uint32_t midle = __ballot_sync(FULL, idle);
-            if (midle && next < cnt) {
-                const int idx = next + __popc(midle & ((1u << lane) - 1u));
-                if (idle && idx < cnt) {
-                    const int i = list[idx];
-                    env_g = cta_env0 + i; tl = s_tl[i]; left = (int)s_def[i];
-                    const RngRec r = P.rng[env_g];
-                    ds.init(ring + lane, 32, r.seed, r.draws);
-                }
-                next += __popc(midle);
-            }
-            const bool active = left > 0;
-            const uint32_t mact = __ballot_sync(FULL, active);
-            if (!mact) break;
-            if (!must_complete) {
-                int dn = 0;
-                if (lane == 0) dn = *s_done;
-                dn = __shfl_sync(FULL, dn, 0);
-                if (rounds >= gen_rounds || dn >= R2_WARPS) break;
-                if (rounds >= 1 && __popc(mact) < gen_min_active) break;
-            }
-            rounds++;
-            gen_small_round<RolloutRing, true>(lp, P, ds, active, env_g, tl, left, D);
-        }
+        rollout2_gen_warp(lp, P, g_area, s_done, n, T, blockIdx.x * R2_WARPS * R2_ENVS, gen_rounds, gen_min_active, lane);
         return;
     }
     // ---- stepping warps: rollout2.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu) ----

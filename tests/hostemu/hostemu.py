@@ -112,7 +112,7 @@ class HostEmuPool:
 # ---- k_rollout2's stepping role on OS threads (simt_rollout2.cpp) -------------------------------------------------
 SRC2 = os.path.join(HERE, 'simt_rollout2.cpp')
 OUT2 = os.path.join(HERE, 'libsimt_rollout2.so')
-DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout2.cuh')] + DEPS[1:]
+DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout2.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'gen_round.cuh')] + DEPS[1:]
 _lib2 = None
 
 
@@ -128,6 +128,8 @@ def lib2():
         L.r2_destroy.argtypes = [C.c_void_p]
         L.r2_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.r2_tokens.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.r2_rollout_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.r2_min_ring_level.argtypes = [C.c_void_p]
         L.r2_max_tokens.argtypes = [C.c_void_p]
         _lib2 = L
     return _lib2
@@ -147,13 +149,20 @@ class Rollout2Pool:
         except Exception:
             pass
 
-    def rollout(self, actions):
+    def rollout(self, actions, fused=False, gen_rounds=1 << 20, gen_min_active=0):
+        """fused=True: the CTA's generator warp refills the rings during the launch (nothing else does)"""
         a = np.ascontiguousarray(actions, dtype=np.int8)
         T, n = a.shape
         obs, rew = np.zeros((T, n, 7, 7, 3), np.uint8), np.zeros((T, n), np.float32)
         done, dirs, cnt = np.zeros((T, n), np.uint8), np.zeros((T, n), np.int8), np.zeros(4, np.int64)
-        self.L.r2_rollout(self.h, _p(a), T, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
+        if fused:
+            self.L.r2_rollout_fused(self.h, _p(a), T, gen_rounds, gen_min_active, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
+        else:
+            self.L.r2_rollout(self.h, _p(a), T, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
         return obs, rew, done, dirs, cnt
+
+    def min_ring_level(self):
+        return self.L.r2_min_ring_level(self.h)
 
     def tokens(self, i):
         t = np.zeros(self.L.r2_max_tokens(self.h), np.int16)

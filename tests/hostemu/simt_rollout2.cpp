@@ -26,6 +26,7 @@ struct WarpCtx {
 };
 static thread_local WarpCtx *tl_warp = nullptr;
 static thread_local int tl_lane = 0;
+static thread_local std::barrier<> *tl_cta = nullptr;       // __syncthreads of a fused launch (4 stepping warps + the generator warp)
 
 static inline void emu_syncwarp() { tl_warp->bar.arrive_and_wait(); }
 static inline uint32_t emu_exchange(uint32_t v, int src)
@@ -36,13 +37,25 @@ static inline uint32_t emu_exchange(uint32_t v, int src)
     tl_warp->bar.arrive_and_wait();                      // nobody overwrites xchg before everybody has read it
     return r;
 }
+static inline uint32_t emu_ballot(bool pred)
+{
+    tl_warp->xchg[tl_lane] = pred ? 1u : 0u;
+    tl_warp->bar.arrive_and_wait();
+    uint32_t m = 0;
+    for (int l = 0; l < 32; l++) m |= tl_warp->xchg[l] << l;
+    tl_warp->bar.arrive_and_wait();
+    return m;
+}
 template <class T> static inline T emu_shfl(T v, int src) { return (T)emu_exchange((uint32_t)v, src); }
 template <class T> static inline T emu_shfl_down(T v, int d) { return (T)emu_exchange((uint32_t)v, tl_lane + d < 32 ? tl_lane + d : tl_lane); }
 template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exchange((uint32_t)v, tl_lane ^ m); }
 
 #define BB_DEV inline
 #define BB_SYNCWARP() emu_syncwarp()
-#define BB_SYNCTHREADS() abort()                          /* fused launches (generator warp) are not emulated */
+#define BB_SYNCTHREADS() tl_cta->arrive_and_wait()
+#define BB_ANY(x) (emu_ballot(x) != 0u)
+#define BB_BALLOT(x) emu_ballot(x)
+#define BB_POPC(x) __builtin_popcount(x)
 #define BB_SHFL(v, src) emu_shfl((v), (src))
 #define BB_SHFL_XOR(v, m) emu_shfl_xor((v), (m))
 #define BB_SHFL_DOWN(v, d) emu_shfl_down((v), (d))
@@ -52,6 +65,7 @@ template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exch
 #define BB_LD_S8(p) ((int)*(p))
 
 #include "../../babyai_b200/csrc/rollout2.cuh"
+#include "../../babyai_b200/csrc/gen_round.cuh"
 #include "../../babyai_b200/csrc/level_params.h"
 
 using namespace bb;
@@ -82,6 +96,7 @@ struct HostPoolPtrs {                                     // the members of pool
     uint8_t *grid; EnvHot *hot; ObjTab *obj; InstrRec *ins; int16_t *tok;
     uint8_t *rgrid; EnvHot *rhot; ObjTab *robj; InstrRec *rins; int16_t *rtok;
     uint32_t *head, *tail, *tail_pub;
+    RngRec *rng; uint32_t *attempts;
     float *last_reward;
     unsigned long long *warp_counters;
     int32_t depth, n;
@@ -92,7 +107,7 @@ struct RPool {
     std::vector<uint8_t> grid, rgrid, locked_room;
     std::vector<EnvHot> hot, rhot; std::vector<ObjTab> obj, robj; std::vector<InstrRec> ins, rins;
     std::vector<int16_t> tok, rtok;
-    std::vector<uint32_t> head, tail, tail_pub;
+    std::vector<uint32_t> head, tail, tail_pub, attempts;
     std::vector<RngRec> rng; std::vector<float> last_reward;
     std::vector<unsigned long long> counters;
     HostPoolPtrs P;
@@ -127,7 +142,7 @@ RPool *r2_create(const bb_level_spec *spec, int n, int depth, const uint64_t *se
     memset(p->hot.data(), 0, N * sizeof(EnvHot)); memset(p->obj.data(), 0, N * sizeof(ObjTab)); memset(p->ins.data(), 0, N * sizeof(InstrRec));
     p->tok.assign(N * lp.max_tokens, 0); p->rtok.assign(DN * lp.max_tokens, 0);
     p->head.assign(N, 0); p->tail.assign(N, 0); p->tail_pub.assign(N, 0);
-    p->rng.resize(N); p->last_reward.assign(N, 0.f); p->locked_room.assign(N, 0xFF);
+    p->rng.resize(N); p->last_reward.assign(N, 0.f); p->locked_room.assign(N, 0xFF); p->attempts.assign(N, 0);
     p->counters.assign(4 * (N / R2_ENVS + 2), 0);
     for (int e = 0; e < n; e++) { p->rng[e].seed = seeds[e]; p->rng[e].draws = 0; }
     HostPoolPtrs &P = p->P;
@@ -135,6 +150,7 @@ RPool *r2_create(const bb_level_spec *spec, int n, int depth, const uint64_t *se
     P.rgrid = p->rgrid.data(); P.rhot = p->rhot.data(); P.robj = p->robj.data(); P.rins = p->rins.data(); P.rtok = p->rtok.data();
     P.head = p->head.data(); P.tail = p->tail.data(); P.tail_pub = p->tail_pub.data();
     P.last_reward = p->last_reward.data(); P.warp_counters = p->counters.data();
+    P.rng = p->rng.data(); P.attempts = p->attempts.data();
     P.depth = depth; P.n = n;
     // reset: generate, then take the first level of every ring as the live state (what bb_pool_reset does)
     refill(p);
@@ -174,6 +190,42 @@ void r2_rollout(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *rew
     for (int k = 0; k < 4; k++) counters4[k] = 0;
     for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
 }
+
+// a FUSED launch of k_rollout2: per CTA four stepping warps + the generator warp (rollout2_gen_warp, gen_small_round), 160
+// threads, one CTA after the other; nothing refills the rings but the generator warps
+void r2_rollout_fused(RPool *p, const int8_t *actions, int T, int gen_rounds, int gen_min_active, uint8_t *obs, float *reward,
+                      uint8_t *done, int8_t *dirs, int64_t *counters4)
+{
+    const LevelParams &lp = p->lp;
+    if (!lp.small) { fprintf(stderr, "simt_rollout2: fused launches are for small single-room levels\n"); abort(); }
+    const int gs = (lp.cells_pad >> 2) | 1;
+    const int warp_words = R2_ENVS * (gs + R2_OBJ_STRIDE + R2_INS_STRIDE) + TILE2_WORDS;
+    const int cta_envs = R2_WARPS * R2_ENVS;
+    const int nctas = (p->n + cta_envs - 1) / cta_envs;
+    for (int cta = 0; cta < nctas; cta++) {
+        std::vector<WarpCtx> ctx(R2_WARPS + 1);
+        std::barrier<> cta_bar(32 * (R2_WARPS + 1));
+        std::vector<uint32_t> smem((size_t)R2_WARPS * warp_words + RG_AREA_WORDS + 8, 0xDEADBEEFu);
+        uint32_t *smr = smem.data();
+        while (((uintptr_t)smr) & 15) smr++;
+        uint32_t *g_area = smr + R2_WARPS * warp_words;
+        volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
+        std::vector<std::thread> th;
+        for (int tid = 0; tid < 32 * (R2_WARPS + 1); tid++)
+            th.emplace_back([&, tid]() {
+                const int lane = tid & 31, warp = tid >> 5;
+                tl_warp = &ctx[warp]; tl_lane = lane; tl_cta = &cta_bar;
+                if (warp == R2_WARPS) rollout2_gen_warp(lp, p->P, g_area, s_done, p->n, T, cta * cta_envs, gen_rounds, gen_min_active, lane);
+                else rollout2_step_warp<HostPoolPtrs, HostSmemMem>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, true,
+                                                                   smr + warp * warp_words, lane, cta * R2_WARPS + warp, s_done);
+            });
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < 4; k++) counters4[k] = 0;
+    for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
+}
+
+int r2_min_ring_level(RPool *p) { int m = 1 << 30; for (int e = 0; e < p->n; e++) { const int have = (int)(p->tail[e] - p->head[e]); if (have < m) m = have; } return m; }
 
 void r2_tokens(RPool *p, int e, int16_t *out) { memcpy(out, p->tok.data() + (size_t)e * p->lp.max_tokens, p->lp.max_tokens * sizeof(int16_t)); }
 int r2_max_tokens(RPool *p) { return p->lp.max_tokens; }

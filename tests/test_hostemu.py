@@ -244,3 +244,30 @@ def test_rollout2_stepping_role_freeze_mode():
             o, r, d = ref.step(acts[t])
             assert np.array_equal(obs[t], o) and np.array_equal(rew[t].view(np.uint32), r.view(np.uint32)) and np.array_equal(done[t], d), (rep, t)
     assert done[-1].all()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('level,n,T,rounds,min_active', [('GoToLocal', 100, 16, 1 << 20, 0), ('PickupLoc', 70, 16, 2, 16), ('GoToObjS4', 64, 16, 1, 0),
+                                                         ('GoToRedBallGrey', 90, 12, 3, 8)])
+def test_rollout2_fused_cta_on_threads(level, n, T, rounds, min_active):
+    """A whole fused CTA of k_rollout2 on threads: four stepping warps + the generator warp (rollout2_gen_warp driving
+    gen_small_round -- the round function of k_gen_small and of k_rollout's generator warp) behind one __syncthreads.  Nothing
+    but the generator warps refills the rings over 14 launches, with small round budgets and the sparse-warp rule switched
+    on in some cases (deficits carry over; the must-complete rule keeps every ring above what the next launch can consume)."""
+    seeds = np.arange(n, dtype=np.uint64) * 5 + 2024
+    ref = _emu(level, n, seeds)
+    r2 = hostemu.Rollout2Pool(level_spec(level), n, seeds, depth=2 * T + 8)       # the smallest ring fused launches accept
+    ref.reset()
+    rng = np.random.RandomState(23)
+    steps = episodes = 0
+    for rep in range(14):
+        acts = rng.choice(7, size=(T, n), p=[0.13, 0.13, 0.4, 0.12, 0.08, 0.12, 0.02]).astype(np.int8)
+        obs, rew, done, dirs, cnt = r2.rollout(acts, fused=True, gen_rounds=rounds, gen_min_active=min_active)
+        for t in range(T):
+            o, r, d = ref.step(acts[t])
+            assert np.array_equal(obs[t], o) and np.array_equal(rew[t].view(np.uint32), r.view(np.uint32)) and np.array_equal(done[t], d), (level, rep, t)
+            episodes += int(d.sum())
+        steps += T * n
+        assert cnt[0] == steps and cnt[1] == episodes and cnt[3] == 0, (rep, cnt, steps, episodes)
+        assert r2.min_ring_level() >= T, (rep, r2.min_ring_level())
+    assert episodes > n
