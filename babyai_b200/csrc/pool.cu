@@ -875,6 +875,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
 // the one of k_rollout, for the CTA's 64 envs.
 static_assert(R2_OBJ_STRIDE == SM_OBJ_STRIDE && R2_INS_STRIDE == SM_INS_STRIDE, "rollout2.cuh record strides");
 
+template <bool UNTR>
 __global__ void __launch_bounds__(R2_THREADS_FUSED, 7)
 k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
            float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
@@ -892,7 +893,7 @@ k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ ac
         return;
     }
     // ---- stepping warps: rollout2.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu) ----
-    rollout2_step_warp<PoolPtrs, SmemOnlyMem>(lp, P, actions, obs, reward, done, dirs, n, T, mode, fused, smr + warp * warp_words,
+    rollout2_step_warp<PoolPtrs, SmemOnlyMem, UNTR>(lp, P, actions, obs, reward, done, dirs, n, T, mode, fused, smr + warp * warp_words,
                                               lane, blockIdx.x * R2_WARPS + warp, s_done);
 }
 
@@ -1222,8 +1223,10 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CU(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_rollout2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_rollout2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rollout2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_rollout2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rollout2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(k_rollout2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
     // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
     CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1413,12 +1416,13 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaEventRecord(p->ev_fork, user));
     }
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
-    if (p->rollout_lanes == 2 && p->lp.kind != KIND_UNLOCK) {      // experimental: two lanes per environment
+    if (p->rollout_lanes == 2) {                                   // experimental: two lanes per environment
         const size_t smem2 = (size_t)R2_WARPS * (R2_ENVS * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE2_WORDS) * 4;
         const int blocks2 = (p->n + R2_WARPS * R2_ENVS - 1) / (R2_WARPS * R2_ENVS);
-        if (fused) k_rollout2<<<blocks2, R2_THREADS_FUSED, smem2 + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode,
+        if (p->lp.kind == KIND_UNLOCK) k_rollout2<true><<<blocks2, R2_THREADS, smem2, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
+        else if (fused) k_rollout2<false><<<blocks2, R2_THREADS_FUSED, smem2 + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode,
                                                                                             p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
-        else k_rollout2<<<blocks2, R2_THREADS, smem2, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
+        else k_rollout2<false><<<blocks2, R2_THREADS, smem2, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
     }
     else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
                                                                                        p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);

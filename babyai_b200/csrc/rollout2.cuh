@@ -83,7 +83,8 @@ BB_DEV void store_tile2(const uint32_t *tile, uint8_t *dst, int lane, int valid_
 
 // One stepping warp: 16 envs, lane = 2 * (env within the warp) + half.  warp_smem: the warp's shared-memory area
 // (R2_ENVS records of grid / object table / verifier record + the observation tile); warp_global: its index in the grid.
-template <class PP, class MemT>
+// UNTR: KIND_UNLOCK pools (untracked objects, env_logic.cuh CARRY_UNTRACKED)
+template <class PP, class MemT, bool UNTR = false>
 BB_DEV void rollout2_step_warp(const LevelParams &lp, const PP &P, const int8_t *actions, uint8_t *obs, float *reward, uint8_t *done,
                                int8_t *dirs, const int n, const int T, const int mode, const bool fused, uint32_t *warp_smem,
                                const int lane, const int warp_global, volatile int *s_done)
@@ -122,7 +123,7 @@ BB_DEV void rollout2_step_warp(const LevelParams &lp, const PP &P, const int8_t 
         float rew = 0.0f; bool dn = false; int begin = 0;
         if (valid && hf == 0) {                             // the even lane steps the env
             if (!(h.dirflags & 4)) {
-                const StepResult sr = step_env(h, mem, a);
+                const StepResult sr = step_env<UNTR>(h, mem, a);
                 rew = sr.reward; dn = sr.done;
                 n_step++; n_end += dn; n_succ += sr.success;
                 if (dn) {
@@ -185,7 +186,7 @@ BB_DEV void rollout2_step_warp(const LevelParams &lp, const PP &P, const int8_t 
         if (valid) cm = pair_cols_load(mem, v, hf, lo, hi);
         uint32_t other = 0;
         if (!single_room) other = BB_SHFL_XOR(cm, 1);
-        if (valid) pair_cols_encode(lp, v, h.x, h.y, dir, carry_cell_of(h, mem), hf, lo, hi, hf ? other : cm, hf ? cm : other, oc);
+        if (valid) pair_cols_encode(lp, v, h.x, h.y, dir, carry_cell_of<UNTR>(h, mem), hf, lo, hi, hf ? other : cm, hf ? cm : other, oc);
         else {
 #pragma unroll
             for (int k = 0; k < 4; k++)

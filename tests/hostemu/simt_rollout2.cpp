@@ -182,7 +182,8 @@ void r2_rollout(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *rew
         for (int lane = 0; lane < 32; lane++)
             th.emplace_back([&, lane]() {
                 tl_warp = &ctx; tl_lane = lane;
-                rollout2_step_warp<HostPoolPtrs, HostSmemMem>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, false, base, lane, wg, nullptr);
+                if (lp.kind == KIND_UNLOCK) rollout2_step_warp<HostPoolPtrs, HostSmemMem, true>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, false, base, lane, wg, nullptr);
+                else rollout2_step_warp<HostPoolPtrs, HostSmemMem>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, false, base, lane, wg, nullptr);
             });
         for (auto &t : th) t.join();
     }

@@ -200,7 +200,7 @@ def test_pair_observation_path_equals_observe(level):
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize('level,n,T', [('GoToLocal', 40, 40), ('PickupLoc', 35, 40), ('GoToObjS4', 16, 40), ('PutNextLocal', 24, 32),
-                                        ('GoToObjMazeS4R2', 21, 40), ('BossLevel', 18, 16)])
+                                        ('GoToObjMazeS4R2', 21, 40), ('BossLevel', 18, 16), ('Unlock', 20, 24)])
 def test_rollout2_stepping_role_on_threads(level, n, T):
     """k_rollout2's stepping role (babyai_b200/csrc/rollout2.cuh: the very function the kernel calls) executed with one OS
     thread per lane and the warp shuffles / barriers as rendezvous: whole rollouts -- step on the even lane, broadcast,
@@ -224,7 +224,7 @@ def test_rollout2_stepping_role_on_threads(level, n, T):
         steps += T * n
         assert cnt[0] == steps and cnt[1] == episodes and cnt[3] == 0, (cnt, steps, episodes)
         assert all(np.array_equal(r2.tokens(i)[:8], ref.tokens(i)[:8]) for i in range(n))
-    assert episodes > 0 or level == 'BossLevel'
+    assert episodes > 0 or level in ('BossLevel', 'Unlock')
     del obs0
 
 

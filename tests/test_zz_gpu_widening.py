@@ -117,7 +117,7 @@ def test_rollout_equals_stepwise_new_levels(level):
 @pytest.mark.skipif(__import__('os').environ.get('BB_TEST_ROLLOUT2') != '1',
                     reason='k_rollout2 (two lanes per env) is experimental and has never run on a GPU: opt in with BB_TEST_ROLLOUT2=1')
 @pytest.mark.parametrize('level,n,T', [('GoToLocal', 4096, 24), ('GoToLocal', 1000, 40), ('PickupLoc', 200, 40), ('GoToObjS4', 256, 40),
-                                        ('PutNextLocal', 333, 32), ('BossLevel', 512, 16), ('GoToObjMazeS4R2', 300, 40)])
+                                        ('PutNextLocal', 333, 32), ('BossLevel', 512, 16), ('GoToObjMazeS4R2', 300, 40), ('Unlock', 200, 16)])
 def test_rollout2_equals_stepwise(monkeypatch, level, n, T):
     """BB_ROLLOUT_LANES=2: bb_pool_rollout through k_rollout2 == T x bb_pool_step (and, transitively, the oracle)."""
     import torch
