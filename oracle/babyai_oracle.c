@@ -73,8 +73,8 @@ enum { K_ACTION = 0, K_AND = 1, K_SEQ = 2 };
 
 typedef struct {
     int32_t kind;
-    int32_t room_size, num_rows, num_cols, num_dists;
-    int32_t instr;            /* KIND_OBJ: I_GOTO or I_PICKUP */
+    int32_t room_size, num_rows, num_cols, num_dists;   /* KIND_IMPUNLOCK / KIND_UNLOCK: num_dists per unlocked room */
+    int32_t instr;            /* KIND_OBJ: I_GOTO / I_PICKUP / I_OPEN / I_PUTNEXT */
     int32_t doors_open;       /* Level_GoTo(doors_open=...) */
     int32_t grey_dists;       /* Level_GoToRedBallGrey */
     double  locked_room_prob; /* LevelGen ... */
