@@ -1760,63 +1760,6 @@ BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir,
     else observe_generic(lp, mem, ax, ay, dir, carry_cell, w);
 }
 
-// ---- two lanes per environment (k_rollout2, experimental): half p of the lane pair owns the view columns
-// [4p, 4p + 4) of [0, 7): p = 0 -> columns 0..3 (84 output bytes), p = 1 -> columns 4..6 (63 bytes).
-// pair_cols_load: the half's column windows + their see-through bits packed 7 bits per column (slot k = column 4p + k).
-template <class M>
-BB_HD uint32_t pair_cols_load(const M &mem, const ViewGeom &v, int p, uint32_t lo[4], uint32_t hi[4])
-{
-    uint32_t cm = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int vi = 4 * p + k;
-        lo[k] = hi[k] = 0;
-        if (vi < 7) { col_load(mem, v, vi, lo[k], hi[k]); cm |= col_see(lo[k], hi[k]) << (7 * k); }
-    }
-    return cm;
-}
-// pair_cols_encode: cm0 / cm1 = the packed see-through bits of half 0 / half 1 (one shuffle brings the partner's);
-// o[k] = the 21 output bytes of column 4p + k (6 words, bytes 21..23 zero)
-BB_HD void pair_cols_encode(const LevelParams &lp, const ViewGeom &v, int ax, int ay, int dir, int carry_cell, int p,
-                            const uint32_t lo[4], const uint32_t hi[4], uint32_t cm0, uint32_t cm1, uint32_t o[4][6])
-{
-    uint32_t cvs[4];
-    if (lp.num_rows == 1 && lp.num_cols == 1) {        // observe_room: visible <=> inside the grid
-        const int dist = dir == 3 ? ay : dir == 1 ? lp.H - 1 - ay : dir == 0 ? lp.W - 1 - ax : ax;
-        const uint32_t dm = dist >= 6 ? 0x7Fu : (0x7Fu << (6 - dist)) & 0x7Fu;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int row = v.c_row + v.rstep * (4 * p + k - 3);
-            cvs[k] = (row >= 0 && row < v.nrows) ? dm : 0u;
-        }
-    } else {                                            // observe_generic: process_vis on the row masks
-        uint32_t see[7], vis[7];
-#pragma unroll
-        for (int vj = 0; vj < 7; vj++) {
-            uint32_t r = 0;
-#pragma unroll
-            for (int vi = 0; vi < 7; vi++) {
-                const uint32_t c = vi < 4 ? (cm0 >> (7 * vi)) : (cm1 >> (7 * (vi - 4)));
-                r |= ((c >> vj) & 1u) << vi;
-            }
-            see[vj] = r;
-        }
-        vis_rows(see, vis);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t cv = 0;
-#pragma unroll
-            for (int vj = 0; vj < 7; vj++) cv |= ((vis[vj] >> ((4 * p + k) & 7)) & 1u) << vj;
-            cvs[k] = cv;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t h = hi[k];
-        if (p == 0 && k == 3) h = (h & 0xFF00FFFFu) | ((uint32_t)carry_cell << 16);   // the agent's own cell: what it carries
-        col_encode(lo[k], h, 4 * p + k < 7 ? cvs[k] : 0u, o[k]);
-    }
-}
 // The same observation assembled from per-column pieces exactly as the 8-lanes-per-env kernel does
 // (lane vi = column vi; the ballots become loops here).  Test cross-check only.
 template <class M>
@@ -1926,19 +1869,6 @@ BB_HD void stage_record_words(uint32_t *tile, const uint32_t w[NW], int q, uint3
         if (k > kl) continue;
         if (k == kl && nvalid < 4) v |= next_w0 << (8 * nvalid);
         tile[wb + k] = v;
-    }
-}
-
-// pair_stage: the half's column records into the warp tile (16 envs x 147 bytes).  next_first = first word of the NEXT
-// lane's first record (lane + 1: the partner half, or half 0 of the next env) -- one __shfl_down_sync in the kernel.
-BB_HD void pair_stage(uint32_t *tile, const uint32_t o[4][6], int e_local, int p, uint32_t next_first)
-{
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int vi = 4 * p + k;
-        if (vi >= 7) continue;
-        const bool last = (p == 0 && k == 3) || (p == 1 && k == 2);
-        stage_record_words<21, 6>(tile, o[k], 7 * e_local + vi, last ? next_first : o[k + 1 < 4 ? k + 1 : 3][0]);
     }
 }
 

@@ -1,14 +1,8 @@
 // gen_round.cuh -- one round of the small-level generator for the 32 lanes of a warp (k_gen_small and the generator warps
-// of k_rollout / k_rollout2 in pool.cu).  The warp vote is a macro so that tests/hostemu can compile this very function
-// for the host with one OS thread per lane (tests/hostemu/simt_rollout2.cpp).
+// of k_rollout in pool.cu).  The warp vote is a macro so that tests/hostemu can compile this very function
+// for the host with one OS thread per lane (tests/hostemu/simt_rollout.cpp).
 #pragma once
-#include "rollout2.cuh"
-
-#if defined(__CUDACC__)
-#define BB_ANY(x) __any_sync(0xFFFFFFFFu, (x))
-#define BB_BALLOT(x) __ballot_sync(0xFFFFFFFFu, (x))
-#define BB_POPC(x) __popc(x)
-#endif
+#include "simt.cuh"
 
 namespace bb {
 
@@ -79,12 +73,12 @@ BB_DEV void gen_small_round(const LevelParams &lp, const PP &P, DS &ds, const bo
 #undef BB_TOPUP
 }
 
-// The generator warp of k_rollout2 (fused launches): the role of k_rollout's generator warp for the CTA's 64 envs
-// [cta_env0, cta_env0 + 64).  g_area: RG_AREA_WORDS of the CTA's shared memory; s_done: its last word (the stepping warps
+// The generator warp of a fused k_rollout launch, for the CTA's envs [cta_env0, cta_env0 + 64) (`step_warps` stepping
+// warps count themselves into *s_done when they are finished).  g_area: RG_AREA_WORDS of the CTA's shared memory; s_done: its last word (the stepping warps
 // count themselves in there when they are finished).
 template <class PP>
-BB_DEV void rollout2_gen_warp(const LevelParams &lp, const PP &P, uint32_t *g_area, volatile int *s_done, const int n, const int T,
-                              const int cta_env0, const int gen_rounds, const int gen_min_active, const int lane)
+BB_DEV void rollout_gen_warp(const LevelParams &lp, const PP &P, uint32_t *g_area, volatile int *s_done, const int n, const int T,
+                             const int cta_env0, const int gen_rounds, const int gen_min_active, const int lane, const int step_warps)
 {
     const uint32_t D = (uint32_t)P.depth;
     uint32_t *ring = g_area, *s_tl = g_area + RG_RING_WORDS;
@@ -135,7 +129,7 @@ BB_DEV void rollout2_gen_warp(const LevelParams &lp, const PP &P, uint32_t *g_ar
             int dn = 0;
             if (lane == 0) dn = *s_done;
             dn = BB_SHFL(dn, 0);
-            if (rounds >= gen_rounds || dn >= R2_WARPS) break;
+            if (rounds >= gen_rounds || dn >= step_warps) break;
             if (rounds >= 1 && BB_POPC(mact) < gen_min_active) break;
         }
         rounds++;

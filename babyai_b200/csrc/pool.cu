@@ -4,7 +4,6 @@
 //                 two stepping warps (one lane per environment, state resident in shared memory) and, in fused
 //                 launches, one generator warp that refills the level rings of the CTA's environments.
 //   k_step8       bb_pool_step on multi-room levels: eight lanes per environment (one per view column).
-//   k_step, k_step_staged   lane-per-env A/B variants of the per-step kernel (BB_STEP_KERNEL).
 //   k_gen_scan, k_gen_small  level generation for single-room levels as separate passes (reset, per-step API, rooms
 //                 smaller than 6x6): one lane per environment, the warp in lock-step through one attempt per round.
 //   k_gen         level generation for every other level: one warp per level (generate_level).
@@ -25,8 +24,9 @@
 #include "../../include/babyai_b200.h"
 #include "env_logic.cuh"
 #include "level_params.h"
-#include "rollout2.cuh"
+#include "simt.cuh"
 #include "gen_round.cuh"
+#include "rollout_lane.cuh"
 
 using namespace bb;
 
@@ -46,39 +46,13 @@ struct PoolPtrs {
     uint32_t *gen_ticket;      // work-ticket counter of k_gen / k_gen_small
     uint32_t *gen_count; int32_t *gen_list;                          // k_gen_scan: four lists (by missing levels) of envs whose ring is not full
     unsigned long long *warp_counters;   // [num_warps][4]: steps, episodes, successes, errors
+    int *err_flag;                       // mapped page-locked word: set by a kernel that found a ring dry; the host fails the next call
     int32_t depth, n;
 };
 
-constexpr int STEP_THREADS = 128;
-constexpr int STEP_WARPS = STEP_THREADS / 32;
-constexpr int TILE_WORDS = 32 * OBS_BYTES / 4;     // 1176 words = 4704 B per warp
 constexpr int GEN_THREADS = 64;                    // 2 warps per block; one warp generates one level at a time
 constexpr int GEN_BLOCKS_PER_SM = 8;
 constexpr int GEN_CHUNK = 8;                       // environments per work ticket
-
-// warp-level staging of 32 observations: see stage_obs_words() in env_logic.cuh
-__device__ __forceinline__ void stage_obs(uint32_t *tile, const uint32_t w[OBS_WORDS], int lane)
-{
-    const uint32_t next_w0 = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
-    stage_obs_words(tile, w, lane, next_w0);
-}
-
-__device__ __forceinline__ void store_tile(const uint32_t *tile, uint8_t *dst, int lane, int valid_envs)
-{
-    if (valid_envs == 32 && (((uintptr_t)dst) & 15) == 0) {
-        const uint4 *s = reinterpret_cast<const uint4 *>(tile);
-        uint4 *d = reinterpret_cast<uint4 *>(dst);
-#pragma unroll
-        for (int i = 0; i < (TILE_WORDS / 4 + 31) / 32; i++) {
-            const int idx = lane + 32 * i;
-            if (idx < TILE_WORDS / 4) d[idx] = s[idx];
-        }
-    } else {                                                  // ragged tail / unaligned destination
-        const uint8_t *s = reinterpret_cast<const uint8_t *>(tile);
-        const int nbytes = valid_envs * OBS_BYTES;
-        for (int i = lane; i < nbytes; i += 32) dst[i] = s[i];
-    }
-}
 
 __device__ __forceinline__ LevelOut ring_slot(const LevelParams &lp, const PoolPtrs &P, int env, int slot)
 {
@@ -87,253 +61,6 @@ __device__ __forceinline__ LevelOut ring_slot(const LevelParams &lp, const PoolP
     o.grid = P.rgrid + idx * lp.cells_pad; o.hot = P.rhot + idx; o.obj = P.robj + idx; o.ins = P.rins + idx;
     o.tok = P.rtok + idx * lp.max_tokens;
     return o;
-}
-
-// ring slot -> live state (the new episode begins).  k_gen may be running concurrently on other slots, so
-// the slot is read through L2 (ld.global.cg), never through a possibly stale L1 line.
-__device__ __forceinline__ void swap_in(const LevelParams &lp, const PoolPtrs &P, int env, int slot, EnvHot &h)
-{
-    const LevelOut o = ring_slot(lp, P, env, slot);
-    const uint4 *sg = reinterpret_cast<const uint4 *>(o.grid);
-    uint4 *lg = reinterpret_cast<uint4 *>(P.grid + (size_t)env * lp.cells_pad);
-    for (int i = 0; i < lp.cells_pad / 16; i++) lg[i] = __ldcg(sg + i);
-    const uint4 *so = reinterpret_cast<const uint4 *>(o.obj);
-    uint4 *lo = reinterpret_cast<uint4 *>(P.obj + env);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(ObjTab) / 16); i++) lo[i] = __ldcg(so + i);
-    const uint4 *si = reinterpret_cast<const uint4 *>(o.ins);
-    uint4 *li = reinterpret_cast<uint4 *>(P.ins + env);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(InstrRec) / 16); i++) li[i] = __ldcg(si + i);
-    const uint4 *st = reinterpret_cast<const uint4 *>(o.tok);
-    uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
-    for (int i = 0; i < lp.max_tokens / 8; i++) lt[i] = __ldcg(st + i);
-    const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(o.hot));
-    h = *reinterpret_cast<const EnvHot *>(&hv);
-}
-
-// ---- one environment step for the lane's env (shared by the two k_step variants) -----------------
-struct LaneOut { bool stepped, ended, succeeded, error; };
-
-template <int ACT_BYTES, class M, class SwapIn>
-__device__ __forceinline__ LaneOut lane_step(const LevelParams &lp, const PoolPtrs &P, int env, EnvHot &h, M &mem,
-                                             const void *actions, float *reward, uint8_t *done, int8_t *dirs,
-                                             int mode, int force_reset, uint32_t w[OBS_WORDS], SwapIn swap)
-{
-    LaneOut lo = { false, false, false, false };
-    const bool frozen = (h.dirflags & 4) != 0;
-    bool begin = force_reset != 0;
-    float rew = 0.0f; bool dn = false;
-    if (!force_reset) {
-        if (!frozen) {
-            int a;
-            if (ACT_BYTES == 1) a = reinterpret_cast<const int8_t *>(actions)[env];
-            else a = (int)reinterpret_cast<const long long *>(actions)[env];
-            StepResult r = step_env(h, mem, a);
-            rew = r.reward; dn = r.done;
-            lo.stepped = true; lo.ended = dn; lo.succeeded = r.success;
-            if (dn) {
-                if (mode == BB_MODE_AUTORESET) begin = true;
-                else { h.dirflags |= 4; P.last_reward[env] = rew; }
-            }
-        } else {                                   // ManyEnvs: replay the last result (evaluate.py:72-78)
-            rew = P.last_reward[env]; dn = true;
-        }
-    }
-    if (begin) {
-        const uint32_t hd = P.head[env];
-        const uint32_t tl = __ldcg(P.tail_pub + env);
-        if (tl - hd >= 1u && tl - hd <= (uint32_t)P.depth) {
-            swap(env, (int)(hd % (uint32_t)P.depth), h);
-            P.head[env] = hd + 1u;
-        } else lo.error = true;                    // cannot happen: the host orders k_gen before this step
-    }
-    P.hot[env] = h;
-    observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of(h, mem), w);
-    if (reward) reward[env] = rew;
-    if (done) done[env] = dn ? 1 : 0;
-    if (dirs) dirs[env] = (int8_t)(h.dirflags & 3);
-    return lo;
-}
-
-__device__ __forceinline__ void warp_counters(const PoolPtrs &P, int warp_global, int lane, const LaneOut &lo)
-{
-    const uint32_t m_step = __ballot_sync(0xFFFFFFFFu, lo.stepped), m_end = __ballot_sync(0xFFFFFFFFu, lo.ended);
-    const uint32_t m_succ = __ballot_sync(0xFFFFFFFFu, lo.succeeded), m_err = __ballot_sync(0xFFFFFFFFu, lo.error);
-    if (lane == 0) {                               // one slot per warp, no atomics
-        unsigned long long *c = P.warp_counters + 4ull * warp_global;
-        if (m_step) atomicAdd(c + 0, (unsigned long long)__popc(m_step));
-        if (m_end) atomicAdd(c + 1, (unsigned long long)__popc(m_end));
-        if (m_succ) atomicAdd(c + 2, (unsigned long long)__popc(m_succ));
-        if (m_err) atomicAdd(c + 3, (unsigned long long)__popc(m_err));
-    }
-}
-
-// ---- generic variant: state read straight from global memory (large grids) ----------------------
-template <int ACT_BYTES>
-__global__ void __launch_bounds__(STEP_THREADS, 4)
-k_step(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
-       float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
-       const int mode, const int force_reset)
-{
-    __shared__ __align__(16) uint32_t tiles[STEP_WARPS][TILE_WORDS];
-    const int env = blockIdx.x * STEP_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t w[OBS_WORDS];
-#pragma unroll
-    for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
-    LaneOut lo = { false, false, false, false };
-    if (env < n) {
-        EnvHot h = P.hot[env];
-        GlobalMem mem(lp, P.grid + (size_t)env * lp.cells_pad, P.obj + env, P.ins + env);
-        lo = lane_step<ACT_BYTES>(lp, P, env, h, mem, actions, reward, done, dirs, mode, force_reset, w,
-                                  [&](int e, int slot, EnvHot &hh) { swap_in(lp, P, e, slot, hh); });
-    }
-    warp_counters(P, blockIdx.x * STEP_WARPS + warp, lane, lo);
-    // ---- observation bytes: stage per warp, then coalesced 16-byte stores ---------
-    uint32_t *tile = tiles[warp];
-    stage_obs(tile, w, lane);
-    __syncwarp();
-    const int env0 = blockIdx.x * STEP_THREADS + warp * 32;
-    int nv = n - env0; nv = nv > 32 ? 32 : nv;
-    if (nv > 0) store_tile(tile, obs + (size_t)env0 * OBS_BYTES, lane, nv);
-}
-
-// ---- staged variant (grids up to 128 bytes per env: every single-room level) ---------------------
-// Round-1 profile of the generic kernel: 58 % of the warp stalls are long-scoreboard -- a chain of dependent
-// DRAM round trips (hot -> front cell -> verifier records -> view window).  All of an env's state addresses
-// depend only on the env index, so the warp first copies the records of its 32 envs into shared memory with
-// coalesced 16-byte loads, all in flight at once (ONE DRAM latency), and the per-lane logic then runs on
-// shared memory.  Record strides are odd numbers of words: the coalesced fill (8 lanes per env, 4 envs per
-// instruction) and the per-lane same-offset accesses are both bank-conflict free.
-constexpr int SM_OBJ_STRIDE = 25, SM_INS_STRIDE = 13, SM_GRID_STRIDE_MAX = 33;
-constexpr int SM_WORDS = 32 * (SM_GRID_STRIDE_MAX + SM_OBJ_STRIDE + SM_INS_STRIDE);     // 2272 words per warp
-
-struct SmemMem {
-    const LevelParams &lp;
-    uint32_t *g, *o, *i;                           // this lane's records in shared memory
-    uint8_t *grid; ObjTab *ot; InstrRec *ins;      // the same records in global memory (write-through)
-    bool ins_dirty;
-    __device__ __forceinline__ SmemMem(const LevelParams &lp_, uint32_t *g_, uint32_t *o_, uint32_t *i_, uint8_t *grid_,
-                                       ObjTab *ot_, InstrRec *ins_)
-        : lp(lp_), g(g_), o(o_), i(i_), grid(grid_), ot(ot_), ins(ins_), ins_dirty(false) {}
-    __device__ __forceinline__ static int byte_of(const uint32_t *base, int k) { return (base[k >> 2] >> (8 * (k & 3))) & 0xFF; }
-    __device__ __forceinline__ static void put_byte(uint32_t *base, int k, int v)
-    {
-        const int sh = 8 * (k & 3);
-        base[k >> 2] = (base[k >> 2] & ~(0xFFu << sh)) | ((uint32_t)(v & 0xFF) << sh);
-    }
-    __device__ __forceinline__ int cell(int x, int y) const { return byte_of(g, y * lp.rs_g + x); }
-    __device__ __forceinline__ void set_cell(int x, int y, int v)
-    {
-        put_byte(g, y * lp.rs_g + x, v);
-        put_byte(g, lp.gt_off + x * lp.rs_t + y, v);
-        bb::set_cell(lp, grid, x, y, v);
-    }
-    __device__ __forceinline__ uint32_t word_at(int off) const { return g[off >> 2]; }
-    __device__ __forceinline__ int ox(int k) const { return byte_of(o, k); }
-    __device__ __forceinline__ int oy(int k) const { return byte_of(o + 8, k); }
-    __device__ __forceinline__ int otc(int k) const { return byte_of(o + 16, k); }
-    __device__ __forceinline__ void set_oxy(int k, int x, int y)
-    {
-        put_byte(o, k, x); put_byte(o + 8, k, y);
-        ot->x[k] = (uint8_t)x; ot->y[k] = (uint8_t)y;
-    }
-    __device__ __forceinline__ uint32_t desc_mask(int d) const { return i[d]; }
-    __device__ __forceinline__ int leaf_kind(int l) const { return byte_of(i + 8, l); }
-    __device__ __forceinline__ int leaf_pre(int l) const { return byte_of(i + 9, l); }
-    __device__ __forceinline__ void set_leaf_pre(int l, int v) { put_byte(i + 9, l, v); ins_dirty = true; }
-    __device__ __forceinline__ int root_kind() const { return i[10] & 0xFF; }
-    __device__ __forceinline__ int side_and() const { return (i[10] >> 8) & 0xFF; }
-    __device__ __forceinline__ int flags() const { return (i[10] >> 16) & 0xFF; }
-    __device__ __forceinline__ void set_flags(int v) { i[10] = (i[10] & 0xFF00FFFFu) | ((uint32_t)(v & 0xFF) << 16); ins_dirty = true; }
-    __device__ __forceinline__ void write_back()
-    {
-        if (ins_dirty) {                           // leaf_pre[4] and root_kind/side_and/flags words
-            uint32_t *gi = reinterpret_cast<uint32_t *>(ins);
-            gi[9] = i[9]; gi[10] = i[10];
-        }
-    }
-};
-
-template <int ACT_BYTES>
-__global__ void __launch_bounds__(STEP_THREADS, 4)
-k_step_staged(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
-              float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n,
-              const int mode, const int force_reset)
-{
-    __shared__ __align__(16) uint32_t sm[STEP_WARPS][SM_WORDS];
-    const int env = blockIdx.x * STEP_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int env0 = blockIdx.x * STEP_THREADS + warp * 32;
-    int nv = n - env0; nv = nv > 32 ? 32 : (nv < 0 ? 0 : nv);
-    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;       // odd stride
-    uint32_t *sg = sm[warp], *so = sg + 32 * gs, *si = so + 32 * SM_OBJ_STRIDE;
-    // ---- coalesced fill: grid, object table, instruction record of the warp's envs ----------------
-    {
-        const int cpe = lp.cells_pad >> 4;                       // 16-byte chunks per env
-        const uint4 *src = reinterpret_cast<const uint4 *>(P.grid + (size_t)env0 * lp.cells_pad);
-        for (int idx = lane; idx < nv * cpe; idx += 32) {
-            const uint4 v = src[idx];
-            const int e = idx / cpe, w0 = (idx - e * cpe) * 4;
-            uint32_t *d = sg + e * gs + w0;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-        const uint4 *osrc = reinterpret_cast<const uint4 *>(P.obj + env0);
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const int idx = lane + 32 * k;
-            if (idx < nv * 6) {
-                const uint4 v = osrc[idx];
-                const int e = idx / 6, w0 = (idx - e * 6) * 4;
-                uint32_t *d = so + e * SM_OBJ_STRIDE + w0;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-            }
-        }
-        const uint4 *isrc = reinterpret_cast<const uint4 *>(P.ins + env0);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int idx = lane + 32 * k;
-            if (idx < nv * 3) {
-                const uint4 v = isrc[idx];
-                const int e = idx / 3, w0 = (idx - e * 3) * 4;
-                uint32_t *d = si + e * SM_INS_STRIDE + w0;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-            }
-        }
-    }
-    uint32_t w[OBS_WORDS];
-#pragma unroll
-    for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
-    LaneOut lo = { false, false, false, false };
-    EnvHot h;
-    if (env < n) h = P.hot[env];
-    __syncwarp();
-    if (env < n) {
-        SmemMem mem(lp, sg + lane * gs, so + lane * SM_OBJ_STRIDE, si + lane * SM_INS_STRIDE,
-                    P.grid + (size_t)env * lp.cells_pad, P.obj + env, P.ins + env);
-        lo = lane_step<ACT_BYTES>(lp, P, env, h, mem, actions, reward, done, dirs, mode, force_reset, w,
-            [&](int e, int slot, EnvHot &hh) {
-                swap_in(lp, P, e, slot, hh);                     // ring slot -> live state in global memory
-                // ... and into this lane's staged copy (same thread wrote the live state just now)
-                const uint32_t *lg = reinterpret_cast<const uint32_t *>(mem.grid);
-                for (int k = 0; k < gwords; k++) mem.g[k] = lg[k];
-                const uint32_t *lob = reinterpret_cast<const uint32_t *>(mem.ot);
-#pragma unroll
-                for (int k = 0; k < 24; k++) mem.o[k] = lob[k];
-                const uint32_t *li = reinterpret_cast<const uint32_t *>(mem.ins);
-#pragma unroll
-                for (int k = 0; k < 12; k++) mem.i[k] = li[k];
-                mem.ins_dirty = false;
-            });
-        mem.write_back();
-    }
-    warp_counters(P, blockIdx.x * STEP_WARPS + warp, lane, lo);
-    __syncwarp();                                                // every lane is done with the staged state:
-    uint32_t *tile = sm[warp];                                   // reuse the region as the observation tile
-    stage_obs(tile, w, lane);
-    __syncwarp();
-    if (nv > 0) store_tile(tile, obs + (size_t)env0 * OBS_BYTES, lane, nv);
 }
 
 // ---- column-parallel variant: EIGHT LANES PER ENVIRONMENT (default) ------------------------------
@@ -478,7 +205,7 @@ k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions
             h = *reinterpret_cast<const EnvHot *>(&hv);
             __syncwarp(gmask);
             if (r == 0) P.head[env] = hd + 1u;
-        } else if (r == 0) error = true;                          // cannot happen: the host orders k_gen first
+        } else if (r == 0) { error = true; *P.err_flag = 1; }     // ring dry (the host orders k_gen first): the next call fails
     }
     if (valid && r == 0) {
         P.hot[env] = h;
@@ -573,7 +300,7 @@ __global__ void k_gen_scan(const PoolPtrs P, const int n, const int target, cons
 }
 
 __global__ void __launch_bounds__(GS_THREADS)
-k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_rounds, const int min_active)
+k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int max_rounds, const int min_active, const int min_keep)
 {
     __shared__ uint32_t s_ring[DrawRing::RING_WORDS][GS_THREADS];         // the lanes' draw rings: word j of thread t at [j][t]
     const unsigned FULL = 0xFFFFFFFFu;
@@ -610,11 +337,14 @@ k_gen_small(const LevelParams lp, const PoolPtrs P, const int target, const int 
         const bool active = left > 0;
         const uint32_t mact = __ballot_sync(FULL, active);
         if (!mact) break;
-        if (max_rounds > 0 && rounds >= max_rounds) break;          // budget spent: the envs keep their deficit
+        // budget spent: the envs keep their deficit -- unless a ring holds fewer than `min_keep` levels (what the launches
+        // up to the next refill pass can consume): then the pass goes on until that ring is safe (must-complete rule)
+        const bool low = __any_sync(FULL, active && target - left < min_keep);
+        if (max_rounds > 0 && rounds >= max_rounds && !low) break;
         // bounded refill (bb_pool_rollout): a round costs the same whether 32 lanes work or 2 (deficits > 1 and
         // rejected attempts leave sparse warps behind), so a sparse warp stops after its first round and leaves the
         // rest to the next pass -- unless a ring is more than half empty
-        if (min_active > 0 && rounds >= 1 && __popc(mact) < min_active && !__any_sync(FULL, active && left > (int)(D / 2))) break;
+        if (min_active > 0 && rounds >= 1 && __popc(mact) < min_active && !low && !__any_sync(FULL, active && left > (int)(D / 2))) break;
         rounds++;
         gen_small_round<DrawRing, false>(lp, P, ds, active, env, tl, left, D);
     }
@@ -657,244 +387,26 @@ struct SmemOnlyMem {            // lane-private records in shared memory (byte a
     __device__ __forceinline__ void set_flags(int v) { i[42] = (uint8_t)v; }
 };
 
-// coalesced copy of `chunks_per_env` 16-byte chunks per env between global memory (contiguous records of
-// the warp's envs) and the lane-strided shared-memory records
-template <bool TO_SMEM>
-__device__ __forceinline__ void warp_copy_records(uint32_t *sm, int stride_words, uint4 *glob, int chunks_per_env, int nv, int lane)
-{
-    for (int idx = lane; idx < nv * chunks_per_env; idx += 32) {
-        const int e = idx / chunks_per_env, w0 = (idx - e * chunks_per_env) * 4;
-        uint32_t *d = sm + e * stride_words + w0;
-        if (TO_SMEM) { const uint4 v = glob[idx]; d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
-        else glob[idx] = make_uint4(d[0], d[1], d[2], d[3]);
-    }
-}
-
 template <int ACT_BYTES, bool UNTR = false>
 __global__ void __launch_bounds__(R_THREADS_FUSED, 7)
 k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions_v, uint8_t *__restrict__ obs,
           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
           const int mode, const int force_reset, const int gen_rounds, const int gen_min_active)
 {
-    const int8_t *actions = reinterpret_cast<const int8_t *>(actions_v);
     extern __shared__ __align__(16) uint32_t smr[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;
-    const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
+    const int warp_words = rl_warp_words(lp);
     const bool fused = gen_rounds > 0;                  // launched with R_THREADS_FUSED threads and RG_AREA_WORDS more shared memory
     uint32_t *g_area = smr + R_WARPS * warp_words;
     volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
     if (warp == R_WARPS) {
-        // ================= generator warp (fused launches only) =================
-        const unsigned FULL = 0xFFFFFFFFu;
-        const uint32_t D = (uint32_t)P.depth;
-        uint32_t *ring = g_area, *s_tl = g_area + RG_RING_WORDS;
-        uint16_t *s_def = reinterpret_cast<uint16_t *>(s_tl + 64);
-        uint8_t *list = reinterpret_cast<uint8_t *>(s_tl + 64 + 32);
-        const int cta_env0 = blockIdx.x * R_WARPS * 32;
-        int cta_nv = n - cta_env0; cta_nv = cta_nv > 64 ? 64 : (cta_nv < 0 ? 0 : cta_nv);
-        // ring state of the CTA's envs as of the launch start (the stepping warps advance `head` only at their end)
-        int cnt = 0;
-        bool urgent = false;
-        if (lane == 0) *s_done = 0;
-#pragma unroll
-        for (int h2 = 0; h2 < 2; h2++) {
-            const int i = 32 * h2 + lane;
-            bool need = false;
-            if (i < cta_nv) {
-                const uint32_t hd = P.head[cta_env0 + i], tl0 = P.tail[cta_env0 + i];
-                const int have = (int)(tl0 - hd);
-                s_tl[i] = tl0; s_def[i] = (uint16_t)((int)D - have);
-                need = have < (int)D;
-                urgent = urgent || have < 2 * T;         // the next launch may consume T levels and this one another T
-            }
-            const uint32_t m = __ballot_sync(FULL, need);
-            if (need) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)i;
-            cnt += __popc(m);
-        }
-        const bool must_complete = __any_sync(FULL, urgent);
-        __syncthreads();                                  // the stepping warps have read head / tail: generation may start
-        RolloutRing ds;
-        ds.init(ring + lane, 32, 0, 0);
-        int env_g = -1, left = 0, next = 0, rounds = 0;
-        uint32_t tl = 0;
-        for (;;) {
-            const bool idle = left == 0;
-            const uint32_t midle = __ballot_sync(FULL, idle);
-            if (midle && next < cnt) {                    // idle lanes take the next envs of the CTA's list
-                const int idx = next + __popc(midle & ((1u << lane) - 1u));
-                if (idle && idx < cnt) {
-                    const int i = list[idx];
-                    env_g = cta_env0 + i; tl = s_tl[i]; left = (int)s_def[i];
-                    const RngRec r = P.rng[env_g];
-                    ds.init(ring + lane, 32, r.seed, r.draws);
-                }
-                next += __popc(midle);
-            }
-            const bool active = left > 0;
-            const uint32_t mact = __ballot_sync(FULL, active);
-            if (!mact) break;
-            if (!must_complete) {                         // otherwise: a ring is low, fill everything up whatever it takes
-                int dn = 0;
-                if (lane == 0) dn = *s_done;
-                dn = __shfl_sync(FULL, dn, 0);
-                if (rounds >= gen_rounds || dn >= R_WARPS) break;           // budget spent / the stepping warps are finished
-                if (rounds >= 1 && __popc(mact) < gen_min_active) break;     // sparse warp: leave the rest to the next launch
-            }
-            rounds++;
-            gen_small_round<RolloutRing, true>(lp, P, ds, active, env_g, tl, left, D);
-        }
+        // generator warp (fused launches only): gen_round.cuh
+        rollout_gen_warp(lp, P, g_area, s_done, n, T, blockIdx.x * R_WARPS * 32, gen_rounds, gen_min_active, lane, R_WARPS);
         return;
     }
-    const int env0 = (blockIdx.x * R_WARPS + warp) * 32, env = env0 + lane;
-    int nv = n - env0; nv = nv > 32 ? 32 : (nv < 0 ? 0 : nv);
-    const bool valid = lane < nv;
-    uint32_t *sg = smr + warp * warp_words, *so = sg + 32 * gs, *si = so + 32 * SM_OBJ_STRIDE;
-    uint32_t *tile = si + 32 * SM_INS_STRIDE;       // 16-byte aligned: see launch_rollout
-    // ---- load the state of the warp's envs once ---------------------------------------------------
-    warp_copy_records<true>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
-    warp_copy_records<true>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
-    warp_copy_records<true>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
-    EnvHot h;
-    { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
-    uint32_t head = 0, avail = 0;
-    float last_rew = 0.0f;
-    if (valid) {
-        h = P.hot[env];
-        head = P.head[env];
-        // fused launch: the CTA's generator warp is the only producer and has not started yet (barrier below)
-        avail = (fused ? P.tail[env] : __ldcg(P.tail_pub + env)) - head;
-        if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env];
-    }
-    if (fused) __syncthreads();
-    __syncwarp();
-    SmemOnlyMem mem(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * SM_OBJ_STRIDE),
-                    reinterpret_cast<uint8_t *>(si + lane * SM_INS_STRIDE));
-    uint32_t n_step = 0, n_end = 0, n_succ = 0, n_err = 0, consumed = 0;
-    // actions are read one step ahead with a sign-extending load (no dependent conversion instruction: the
-    // compiler otherwise converts the byte right after the load and the warp waits for DRAM there)
-    int a_next = 0;
-    if (valid && !force_reset) {
-        if (ACT_BYTES == 1) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + env));
-        else a_next = (int)reinterpret_cast<const long long *>(actions_v)[env];      // int64 actions: single-step calls only
-    }
-    for (int t = 0; t < T; t++) {
-        const int a = a_next;
-        if (ACT_BYTES == 1 && valid && t + 1 < T) asm volatile("ld.global.nc.s8 %0, [%1];" : "=r"(a_next) : "l"(actions + (size_t)(t + 1) * n + env));
-        uint32_t w[OBS_WORDS];
-#pragma unroll
-        for (int k = 0; k < OBS_WORDS; k++) w[k] = 0;
-        if (valid) {
-            float rew = 0.0f; bool dn = false, begin = force_reset != 0;
-            if (force_reset) {
-            } else if (!(h.dirflags & 4)) {
-                const StepResult sr = step_env<UNTR>(h, mem, a);
-                rew = sr.reward; dn = sr.done;
-                n_step++; n_end += dn; n_succ += sr.success;
-                if (dn) {
-                    if (mode == BB_MODE_AUTORESET) begin = true;
-                    else { h.dirflags |= 4; last_rew = rew; }
-                }
-            } else { rew = last_rew; dn = true; }
-            if (begin) {
-                if (consumed < avail && avail <= (uint32_t)P.depth) {
-                    const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
-                    uint32_t *mg = reinterpret_cast<uint32_t *>(mem.g);
-                    for (int k = 0; k < lp.cells_pad / 16; k++) {
-                        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.grid) + k);
-                        mg[4 * k] = v.x; mg[4 * k + 1] = v.y; mg[4 * k + 2] = v.z; mg[4 * k + 3] = v.w;
-                    }
-                    uint32_t *mo = reinterpret_cast<uint32_t *>(mem.o);
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.obj) + k);
-                        mo[4 * k] = v.x; mo[4 * k + 1] = v.y; mo[4 * k + 2] = v.z; mo[4 * k + 3] = v.w;
-                    }
-                    uint32_t *mi = reinterpret_cast<uint32_t *>(mem.i);
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(o.ins) + k);
-                        mi[4 * k] = v.x; mi[4 * k + 1] = v.y; mi[4 * k + 2] = v.z; mi[4 * k + 3] = v.w;
-                    }
-                    uint4 *lt = reinterpret_cast<uint4 *>(P.tok + (size_t)env * lp.max_tokens);
-                    for (int k = 0; k < lp.max_tokens / 8; k++) lt[k] = __ldcg(reinterpret_cast<const uint4 *>(o.tok) + k);
-                    const uint4 hv = __ldcg(reinterpret_cast<const uint4 *>(o.hot));
-                    h = *reinterpret_cast<const EnvHot *>(&hv);
-                    consumed++;
-                } else n_err++;
-            }
-            // an episode about to time out (73 % of the episode ends under random actions) will need its next
-            // level two steps from now: pull that ring slot into L2 ahead of the dependent loads of the swap-in
-            if (mode == BB_MODE_AUTORESET && (int)h.step_count + 2 == (int)h.max_steps && consumed < avail) {
-                const LevelOut o = ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.grid));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.obj));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.obj) + 64));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.ins));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(o.ins) + 32));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.hot));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(o.tok));
-            }
-            observe(lp, mem, h.x, h.y, h.dirflags & 3, carry_cell_of<UNTR>(h, mem), w);
-            const size_t oi = (size_t)t * n + env;
-            if (reward) reward[oi] = rew;
-            if (done) done[oi] = dn ? 1 : 0;
-            if (dirs) dirs[oi] = (int8_t)(h.dirflags & 3);
-        }
-        stage_obs(tile, w, lane);
-        __syncwarp();
-        if (nv > 0) store_tile(tile, obs + ((size_t)t * n + env0) * OBS_BYTES, lane, nv);
-        __syncwarp();                              // the tile is rewritten in the next iteration
-    }
-    // ---- store the state back ---------------------------------------------------------------------
-    __syncwarp();
-    warp_copy_records<false>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
-    warp_copy_records<false>(so, SM_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
-    warp_copy_records<false>(si, SM_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
-    if (valid) {
-        P.hot[env] = h;
-        P.head[env] = head + consumed;
-        if (mode == BB_MODE_FREEZE) P.last_reward[env] = last_rew;
-    }
-    // counters: warp sums, one RED per counter per warp
-    for (int off = 16; off; off >>= 1) {
-        n_step += __shfl_down_sync(0xFFFFFFFFu, n_step, off); n_end += __shfl_down_sync(0xFFFFFFFFu, n_end, off);
-        n_succ += __shfl_down_sync(0xFFFFFFFFu, n_succ, off); n_err += __shfl_down_sync(0xFFFFFFFFu, n_err, off);
-    }
-    if (fused && lane == 0) atomicAdd(const_cast<int *>(s_done), 1);     // tells the generator warp not to start another round
-    if (lane == 0) {
-        unsigned long long *c = P.warp_counters + 4ull * (blockIdx.x * R_WARPS + warp);
-        if (n_step) atomicAdd(c + 0, (unsigned long long)n_step);
-        if (n_end) atomicAdd(c + 1, (unsigned long long)n_end);
-        if (n_succ) atomicAdd(c + 2, (unsigned long long)n_succ);
-        if (n_err) atomicAdd(c + 3, (unsigned long long)n_err);
-    }
-}
-
-// k_rollout2 -- EXPERIMENTAL (BB_ROLLOUT_LANES=2): two lanes per environment; see rollout2.cuh.  The generator warp below is
-// the one of k_rollout, for the CTA's 64 envs.
-static_assert(R2_OBJ_STRIDE == SM_OBJ_STRIDE && R2_INS_STRIDE == SM_INS_STRIDE, "rollout2.cuh record strides");
-
-template <bool UNTR>
-__global__ void __launch_bounds__(R2_THREADS_FUSED, 7)
-k_rollout2(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
-           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
-           const int mode, const int gen_rounds, const int gen_min_active)
-{
-    extern __shared__ __align__(16) uint32_t smr[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gwords = lp.cells_pad >> 2, gs = gwords | 1;
-    const int warp_words = R2_ENVS * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE2_WORDS;
-    const bool fused = gen_rounds > 0;
-    uint32_t *g_area = smr + R2_WARPS * warp_words;
-    volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
-    if (warp == R2_WARPS) {
-        rollout2_gen_warp(lp, P, g_area, s_done, n, T, blockIdx.x * R2_WARPS * R2_ENVS, gen_rounds, gen_min_active, lane);
-        return;
-    }
-    // ---- stepping warps: rollout2.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu) ----
-    rollout2_step_warp<PoolPtrs, SmemOnlyMem, UNTR>(lp, P, actions, obs, reward, done, dirs, n, T, mode, fused, smr + warp * warp_words,
-                                              lane, blockIdx.x * R2_WARPS + warp, s_done);
+    // stepping warps: rollout_lane.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu)
+    rollout_lane_step_warp<PoolPtrs, SmemOnlyMem, ACT_BYTES, UNTR>(lp, P, actions_v, obs, reward, done, dirs, n, T, mode, force_reset, fused,
+                                                                   smr + warp * warp_words, lane, blockIdx.x * R_WARPS + warp, s_done);
 }
 
 // Level generation, decoupled from the step: tops every environment's ring up to `target` levels.
@@ -971,20 +483,24 @@ static int fail(const char *fmt, const char *a = "")
 }
 #define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail("CUDA error: %s", cudaGetErrorString(_e)); } while (0)
 
+struct bb_pool;
+static int ring_dry(const bb_pool *p);
+#define BB_CHECK_RINGS(p) do { if (ring_dry(p)) return fail("a level ring ran dry (level generation fell behind the rollouts: counters()['errors'] > 0); the pool's episodes are no longer valid -- seed() it again, and use a deeper ring (BB_RING_DEPTH) or a shorter rollout"); } while (0)
+
 struct GraphKey { const void *a, *o, *r, *d, *q; int T; int mode; };
 constexpr int MAX_GEN_EVENTS = 40;
 
 struct bb_pool {
     LevelParams lp;
     PoolPtrs P;
-    int n, device, mode, num_warps, step_blocks, gen_blocks;
+    int n, device, mode, num_warps, gen_blocks;
     // level supply schedule: ring depth D; k_gen is enqueued on gen_stream after every G-th step and
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
     int D, G, nev;
     bool gen_generic; int gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
-    int step_kernel;               // 3 = k_rollout with T = 1 for small grids, k_step8 otherwise (default); 0 = k_step8; 1 = k_step; 2 = k_step_staged; BB_STEP_KERNEL=cols|lane|staged
+    bool step_cols;                // BB_STEP_KERNEL=cols: k_step8 for every level (default: k_rollout with T = 1 on single-room grids)
     long long rel;
     cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
     cudaStream_t gen_stream;       // level generation runs here, concurrently with the steps
@@ -995,7 +511,9 @@ struct bb_pool {
     std::vector<void *> allocs;
     // host-buffer API staging
     int8_t *h_act; uint8_t *h_obs; float *h_rew; uint8_t *h_done; int8_t *h_dir;      // pinned
-    int zerocopy, zc_level; const void *chk_rew; int8_t *zc_act; float *zc_rew; uint8_t *zc_done; int8_t *zc_dir; uint8_t *zc_obs;   // BB_HOST_ZEROCOPY
+    int *h_err;                    // mapped: PoolPtrs::err_flag (a kernel found a level ring dry)
+    int fused_T;                   // longest T a fused rollout launch has guaranteed levels for (see bb_pool_rollout)
+    int zerocopy, zc_level; const void *chk_rew, *chk_done, *chk_dir; bool chk_pinned; int8_t *zc_act; float *zc_rew; uint8_t *zc_done; int8_t *zc_dir; uint8_t *zc_obs;   // BB_HOST_ZEROCOPY
     int8_t *d_act; uint8_t *d_obs; float *d_rew; uint8_t *d_done; int8_t *d_dir;
     uint64_t *d_seeds;
     long long launches;
@@ -1003,9 +521,10 @@ struct bb_pool {
     cudaEvent_t ev[3];
     cudaEvent_t tev[4]; bool time_rollout, tev_kernel, tev_refill;
     const void *chk_obs; bool direct;            // bb_pool_step_host: caller buffers are page-locked       // bb_pool_rollout_timed
-    int rollout_lanes;            // BB_ROLLOUT_LANES=2: k_rollout2 (experimental) instead of k_rollout in bb_pool_rollout
     int lz_state; int8_t *lz_act; float *lz_rew; uint8_t *lz_done;   // bb_pool_step_learner: 0 = not probed, 1 = mapped staging, 2 = copies
 };
+
+static int ring_dry(const bb_pool *p) { return p->h_err && *reinterpret_cast<volatile const int *>(p->h_err) != 0; }
 
 template <typename T>
 static int dalloc(bb_pool *p, T **out, size_t count)
@@ -1026,12 +545,12 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
     return e ? fail("%s", e) : 0;
 }
 
-static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false)
+static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false, int min_keep = 0)
 {
     cudaMemsetAsync(p->P.gen_count, 0, 8 * sizeof(uint32_t), st);      // list counters + work ticket
     if (p->lp.small && !p->gen_generic) {
         k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
-        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active);
+        k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active, min_keep);
         p->launches++;
     } else if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK) k_gen<true><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
     else k_gen<false><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
@@ -1053,36 +572,25 @@ static void launch_gen(bb_pool *p, cudaStream_t st)
 static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8_t *obs, float *rew, uint8_t *done,
                         int8_t *dirs, int force_reset, cudaStream_t st)
 {
-    const int blocks8 = (p->n + 4 * S8_WARPS - 1) / (4 * S8_WARPS);
-    int kernel = p->step_kernel;
-    if ((kernel == 2 || kernel == 3) && p->lp.cells_pad > 128) kernel = kernel == 3 ? 0 : 1;
-    if (p->lp.kind == KIND_UNLOCK) kernel = 0;          // untracked objects: only k_step8 / k_rollout have UNTR instantiations
-    if (kernel == 3) {                   // small grids: the persistent kernel with T = 1 (coalesced state load / store)
-        const int gs = (p->lp.cells_pad >> 2) | 1;
-        const size_t smem = (size_t)R_WARPS * (32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS) * 4;
+    // single-room grids (<= 128 bytes of cells): the persistent kernel with T = 1 (coalesced state load / store);
+    // everything else, and KIND_UNLOCK: k_step8, eight lanes per environment.  BB_STEP_KERNEL=cols forces k_step8.
+    const bool cols = p->step_cols || p->lp.cells_pad > 128 || p->lp.kind == KIND_UNLOCK;
+    if (!cols) {
+        const size_t smem = (size_t)R_WARPS * rl_warp_words(p->lp) * 4;
         const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
         if (action_bytes == 8) k_rollout<8><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0);
         else k_rollout<1><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0);
         p->launches++;
         return;
     }
-#define BB_LAUNCH(K, GRID, THREADS)                                                                                      \
-    do {                                                                                                                 \
-        if (action_bytes == 8) K<8><<<GRID, THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset); \
-        else K<1><<<GRID, THREADS, 0, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);     \
-    } while (0)
-    if (kernel == 0) {
-        const size_t sm8 = (size_t)S8_WARPS * 4 * (p->lp.cells_pad + S8_REC_FIXED) + (size_t)S8_WARPS * (S8_TILE_WORDS + 1) * 4;
-        if (p->lp.kind == KIND_UNLOCK) {
-            if (action_bytes == 8) k_step8<8, true><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-            else k_step8<1, true><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-        }
-        else if (action_bytes == 8) k_step8<8><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
-        else k_step8<1><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    const int blocks8 = (p->n + 4 * S8_WARPS - 1) / (4 * S8_WARPS);
+    const size_t sm8 = (size_t)S8_WARPS * 4 * (p->lp.cells_pad + S8_REC_FIXED) + (size_t)S8_WARPS * (S8_TILE_WORDS + 1) * 4;
+    if (p->lp.kind == KIND_UNLOCK) {
+        if (action_bytes == 8) k_step8<8, true><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+        else k_step8<1, true><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
     }
-    else if (kernel == 2) BB_LAUNCH(k_step_staged, p->step_blocks, STEP_THREADS);
-    else BB_LAUNCH(k_step, p->step_blocks, STEP_THREADS);
-#undef BB_LAUNCH
+    else if (action_bytes == 8) k_step8<8><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
+    else k_step8<1><<<blocks8, S8_THREADS, sm8, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, p->mode, force_reset);
     p->launches++;
 }
 
@@ -1129,7 +637,7 @@ static int sched_join(bb_pool *p, cudaStream_t st)
 static int sched_leave_rollout(bb_pool *p, cudaStream_t st)
 {
     if (!p->after_rollout) return 0;
-    p->rollouts = 0;
+    p->rollouts = 0; p->fused_T = 0;
     if (sched_join(p, st)) return 1;
     if (p->mode == BB_MODE_AUTORESET) launch_gen(p, st);
     p->after_rollout = false;
@@ -1140,6 +648,8 @@ extern "C" {
 
 const char *bb_last_error(void) { return g_err; }
 
+// inside bb_pool_create: a failing CUDA call releases everything allocated so far
+#define CUP(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { fail("CUDA error: %s", cudaGetErrorString(_e)); bb_pool_destroy(p); return 1; } } while (0)
 int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb_pool **out)
 {
     if (!spec || !out || n_envs < 1) return fail("bad arguments");
@@ -1151,11 +661,10 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (!p) return fail("out of memory");
     if (make_params(spec, &p->lp)) { delete p; return 1; }
     p->n = n_envs; p->device = device; p->mode = BB_MODE_AUTORESET;
-    p->step_blocks = (n_envs + STEP_THREADS - 1) / STEP_THREADS;
-    p->num_warps = (n_envs + 3) / 4 + STEP_WARPS;          // counter slots: the 8-lanes-per-env kernel has the most warps
+    p->num_warps = (n_envs + 3) / 4 + 4;          // counter slots: the 8-lanes-per-env kernel has the most warps
     {
         cudaDeviceProp prop;
-        CU(cudaGetDeviceProperties(&prop, device));
+        CUP(cudaGetDeviceProperties(&prop, device));
         int want = ((n_envs + GEN_CHUNK - 1) / GEN_CHUNK + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);
         int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
@@ -1167,8 +676,6 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_budget = 8;                                     // k_gen_small rounds (attempts per lane) per refill pass of bb_pool_rollout
     if (const char *e = getenv("BB_GEN_BUDGET")) p->gen_budget = atoi(e);
     p->lz_state = 0;
-    p->rollout_lanes = 1;
-    if (const char *e = getenv("BB_ROLLOUT_LANES")) p->rollout_lanes = atoi(e) == 2 ? 2 : 1;
     p->zerocopy = 1; p->zc_level = 0; p->chk_rew = nullptr;    // measured (profiles/r01z_zerocopy_ab.log): e2e 2.74e8 copies only, 2.97e8 level 1, 2.91e8 level 2
     if (const char *e = getenv("BB_HOST_ZEROCOPY")) p->zerocopy = atoi(e);
     p->gen_fused = 1;                                      // bb_pool_rollout on single-room levels: generator warp inside k_rollout (see bb_pool_rollout)
@@ -1186,15 +693,15 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->G = p->D >= 64 ? 32 : (p->D >= 8 ? p->D / 4 : 1);
     if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
     p->nev = p->D / p->G + 3;
-    if (p->nev > MAX_GEN_EVENTS) { delete p; return fail("ring depth / generation period too large"); }
+    if (p->nev > MAX_GEN_EVENTS) { p->nev = 0; bb_pool_destroy(p); return fail("ring depth / generation period too large"); }
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
-    p->step_kernel = 3;
+    p->step_cols = false;
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
     p->persist_max_cells = 1152;                           // k_rollout stages up to 22 x 22 grids (2 x 43 KB of shared memory per CTA)
     if (const char *e = getenv("BB_PERSIST_MAX_CELLS")) p->persist_max_cells = atoi(e);
     p->gen_concurrent = p->lp.cells_pad > 256;
     if (const char *e = getenv("BB_GEN_CONCURRENT")) p->gen_concurrent = atoi(e) != 0;
-    if (const char *e = getenv("BB_STEP_KERNEL")) p->step_kernel = !strcmp(e, "lane") ? 1 : !strcmp(e, "staged") ? 2 : !strcmp(e, "cols") ? 0 : 3;
+    if (const char *e = getenv("BB_STEP_KERNEL")) p->step_cols = !strcmp(e, "cols");
     p->launches = 0; p->graph = nullptr; p->ev[0] = p->ev[1] = p->ev[2] = nullptr; p->tev[0] = p->tev[1] = p->tev[2] = p->tev[3] = nullptr; p->time_rollout = false; p->chk_obs = nullptr; p->direct = false;
     const LevelParams &lp = p->lp;
     const size_t n = (size_t)n_envs, D = (size_t)p->D;
@@ -1213,49 +720,49 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         return 1;
     }
     P.gen_ticket = P.gen_count + 4;                      // one memset clears the list counters and the work ticket
-    CU(cudaMemset(P.locked_room, 0xFF, n));
-    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CUP(cudaMemset(P.locked_room, 0xFF, n));
+    CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     {
         int lo = 0, hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));                  // lo = lowest priority
-        CU(cudaStreamCreateWithPriority(&p->gen_stream, cudaStreamNonBlocking, lo));
+        CUP(cudaDeviceGetStreamPriorityRange(&lo, &hi));                  // lo = lowest priority
+        CUP(cudaStreamCreateWithPriority(&p->gen_stream, cudaStreamNonBlocking, lo));
     }
-    CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_rollout2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_rollout2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_rollout2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CU(cudaFuncSetAttribute(k_rollout2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUP(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUP(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
     // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
-    CU(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_gen_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_gen_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_gen<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_gen<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_step8<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_step8<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_step8<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_step8<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_step<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_step<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-    for (int i = 0; i < p->nev; i++) CU(cudaEventCreateWithFlags(&p->gen_ev[i], cudaEventDisableTiming));
-    CU(cudaMallocHost((void **)&p->h_act, n));
-    CU(cudaMallocHost((void **)&p->h_obs, n * OBS_BYTES));
-    CU(cudaMallocHost((void **)&p->h_rew, n * sizeof(float)));
-    CU(cudaMallocHost((void **)&p->h_done, n));
-    CU(cudaMallocHost((void **)&p->h_dir, n));
+    CUP(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_gen_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_gen_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_gen<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_gen<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_step8<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_step8<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_step8<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_step8<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CUP(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < p->nev; i++) CUP(cudaEventCreateWithFlags(&p->gen_ev[i], cudaEventDisableTiming));
+    CUP(cudaMallocHost((void **)&p->h_act, n));
+    CUP(cudaMallocHost((void **)&p->h_obs, n * OBS_BYTES));
+    CUP(cudaMallocHost((void **)&p->h_rew, n * sizeof(float)));
+    CUP(cudaMallocHost((void **)&p->h_done, n));
+    CUP(cudaMallocHost((void **)&p->h_dir, n));
+    CUP(cudaHostAlloc((void **)&p->h_err, sizeof(int), cudaHostAllocMapped));
+    *p->h_err = 0;
+    { void *d = nullptr; CUP(cudaHostGetDevicePointer(&d, p->h_err, 0)); P.err_flag = (int *)d; }
     // default seeds 0..n-1 so that an unseeded pool is still deterministic
     std::vector<uint64_t> seeds(n);
     for (size_t i = 0; i < n; i++) seeds[i] = i;
+    if (bb_pool_seed(p, seeds.data())) { bb_pool_destroy(p); return 1; }
     *out = p;
-    return bb_pool_seed(p, seeds.data());
+    return 0;
 }
+
+#undef CUP
 
 int bb_pool_destroy(bb_pool *p)
 {
@@ -1274,6 +781,7 @@ int bb_pool_destroy(bb_pool *p)
     if (p->h_rew) cudaFreeHost(p->h_rew);
     if (p->h_done) cudaFreeHost(p->h_done);
     if (p->h_dir) cudaFreeHost(p->h_dir);
+    if (p->h_err) cudaFreeHost(p->h_err);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->gen_stream) cudaStreamDestroy(p->gen_stream);
     delete p;
@@ -1285,7 +793,8 @@ int bb_pool_seed(bb_pool *p, const uint64_t *seeds_host)
     if (!p || !seeds_host) return fail("bad arguments");
     CU(cudaSetDevice(p->device));
     CU(cudaDeviceSynchronize());
-    p->gen_outstanding = false; p->rel = 0; p->after_rollout = false;
+    p->gen_outstanding = false; p->rel = 0; p->after_rollout = false; p->fused_T = 0;
+    if (p->h_err) *p->h_err = 0;
     // stream-ordered copy: a synchronous cudaMemcpy from pageable memory may return before its last
     // chunk has landed, and p->stream (non-blocking) is not ordered after the legacy stream
     CU(cudaMemcpyAsync(p->d_seeds, seeds_host, (size_t)p->n * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
@@ -1328,6 +837,7 @@ int bb_pool_step(bb_pool *p, const void *actions_dev, int32_t action_bytes, uint
 {
     if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("bad arguments");
     if (action_bytes != 1 && action_bytes != 8) return fail("action_bytes must be 1 or 8");
+    BB_CHECK_RINGS(p);
     CU(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (sched_leave_rollout(p, st)) return 1;
@@ -1370,15 +880,14 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
                     uint8_t *done_dev, int8_t *dir_dev, void *stream)
 {
     if (!p || !actions_dev || !obs_dev || !reward_dev || !done_dev || T < 1) return fail("bad arguments");
+    BB_CHECK_RINGS(p);
     CU(cudaSetDevice(p->device));
     cudaStream_t user = (cudaStream_t)stream;
     const bool persistent = p->lp.cells_pad <= p->persist_max_cells && !p->no_persistent && (p->mode == BB_MODE_FREEZE || p->D >= (p->refill_every + 1) * T);
     if (!persistent) return rollout_graph(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, user);
     if (sched_join(p, user)) return 1;                 // every k_gen enqueued so far (rings topped up to D - what
                                                        // the previous rollout consumed >= D - T >= T levels per env)
-    const int gs = (p->lp.cells_pad >> 2) | 1;
-    const int warp_words = 32 * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE_WORDS;
-    const size_t smem = (size_t)R_WARPS * warp_words * 4;
+    const size_t smem = (size_t)R_WARPS * rl_warp_words(p->lp) * 4;
     const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
     // Single-room levels: FUSED -- a generator warp inside every CTA of k_rollout refills the rings of the CTA's envs
     // while the stepping warps run (no refill pass at all).  It guarantees >= 2T levels per ring at the end of a
@@ -1390,6 +899,10 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     const bool fused = p->gen_fused != 0 && (p->gen_fused == 2 || 3 * p->lp.nav_time_maze >= 2 * T) &&
                        p->lp.small && !p->gen_generic && !p->gen_concurrent && p->mode == BB_MODE_AUTORESET &&
                        p->D >= 2 * T + 8 && !getenv("BB_DEBUG_NO_REFILL");
+    // a fused launch leaves >= T levels in every ring (must-complete rule in the kernel: >= 2T before they are consumed), which
+    // covers the next launch only if it is not longer: a longer one tops every ring up first (blocking pass)
+    if (fused && T > p->fused_T) launch_gen(p, user);
+    p->fused_T = fused ? T : 0;
     // otherwise one refill pass serves `refill_every` launches (more envs per pass = more lanes busy in k_gen_small)
     const bool refill = !fused && p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL") && (p->rollouts++ % p->refill_every) == 0;
     const bool dbg_timing = p->time_rollout;
@@ -1406,7 +919,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         if (dbg_timing) cudaEventRecord(dbg_ev[2], user);
         const bool fused_snap = p->lp.small && !p->gen_generic;       // k_gen_scan takes the head snapshot itself
         if (!fused_snap) CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
-        launch_gen_kernel(p, p->D, user, p->gen_budget, p->gen_min_active, fused_snap);
+        launch_gen_kernel(p, p->D, user, p->gen_budget, p->gen_min_active, fused_snap, p->refill_every * T);
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, user);
         if (dbg_timing) { cudaEventRecord(dbg_ev[3], user); p->tev_refill = true; }
         p->launches++;
@@ -1416,15 +929,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         CU(cudaEventRecord(p->ev_fork, user));
     }
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
-    if (p->rollout_lanes == 2) {                                   // experimental: two lanes per environment
-        const size_t smem2 = (size_t)R2_WARPS * (R2_ENVS * (gs + SM_OBJ_STRIDE + SM_INS_STRIDE) + TILE2_WORDS) * 4;
-        const int blocks2 = (p->n + R2_WARPS * R2_ENVS - 1) / (R2_WARPS * R2_ENVS);
-        if (p->lp.kind == KIND_UNLOCK) k_rollout2<true><<<blocks2, R2_THREADS, smem2, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
-        else if (fused) k_rollout2<false><<<blocks2, R2_THREADS_FUSED, smem2 + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode,
-                                                                                            p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
-        else k_rollout2<false><<<blocks2, R2_THREADS, smem2, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
-    }
-    else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
+    if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
                                                                                        p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
     else if (p->lp.kind == KIND_UNLOCK) k_rollout<1, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
     else k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
@@ -1433,7 +938,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (refill && !gen_serial) {
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
         if (dbg_timing) cudaEventRecord(dbg_ev[2], p->gen_stream);
-        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget, p->gen_min_active);      // bounded: runs beside k_rollout
+        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget, p->gen_min_active, false, (p->refill_every + 1) * T);      // bounded: runs beside k_rollout
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
         if (dbg_timing) { cudaEventRecord(dbg_ev[3], p->gen_stream); p->tev_refill = true; }
         p->gen_outstanding = true;
@@ -1516,9 +1021,12 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
     const size_t n = (size_t)p->n;
     // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are the DMA targets
     // themselves; pageable ones go through the pool's pinned staging buffers + a host memcpy
-    if (obs_host != p->chk_obs || reward_host != p->chk_rew) {
-        p->chk_obs = obs_host; p->chk_rew = reward_host;
-        p->direct = is_pinned(obs_host) && is_pinned(reward_host) && is_pinned(done_host) && (!dir_host || is_pinned(dir_host));
+    // the probe result is cached per (obs, reward, done, dir) pointer set; the observation buffer is re-probed on every call
+    // (a buffer freed and reallocated at the same address as pageable memory must not keep its old mapping)
+    const bool obs_pinned = is_pinned(obs_host);
+    if (obs_host != p->chk_obs || reward_host != p->chk_rew || done_host != p->chk_done || dir_host != p->chk_dir || obs_pinned != p->chk_pinned) {
+        p->chk_obs = obs_host; p->chk_rew = reward_host; p->chk_done = done_host; p->chk_dir = dir_host; p->chk_pinned = obs_pinned;
+        p->direct = obs_pinned && is_pinned(reward_host) && is_pinned(done_host) && (!dir_host || is_pinned(dir_host));
         // BB_HOST_ZEROCOPY (page-locked caller buffers only): 1 = the step kernel reads the actions from the pool's pinned
         // staging buffer and writes reward / done / direction straight into the caller's buffers over PCIe (mapped host
         // memory: 1 H2D + 3 small D2H copies less per step); 2 = the observations too (no copy at all)
@@ -1549,6 +1057,7 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
         if (!direct || dir_host) CU(cudaMemcpyAsync(direct ? dir_host : p->h_dir, p->d_dir, n, cudaMemcpyDeviceToHost, p->stream));
     }
     CU(cudaStreamSynchronize(p->stream));
+    BB_CHECK_RINGS(p);
     if (!direct) {
         memcpy(obs_host, p->h_obs, n * OBS_BYTES);
         memcpy(reward_host, p->h_rew, n * sizeof(float));
@@ -1589,6 +1098,7 @@ int bb_pool_step_learner(bb_pool *p, const int8_t *actions_host, uint8_t *obs_de
         CU(cudaMemcpyAsync(p->h_done, p->d_done, n, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
+    BB_CHECK_RINGS(p);
     memcpy(reward_host, p->h_rew, n * sizeof(float));
     memcpy(done_host, p->h_done, n);
     return 0;

@@ -38,6 +38,18 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _check(t, name, device, dtype, shape):
+    """the kernels write through raw pointers: a wrong-sized, strided or foreign-device buffer would be a silent
+    out-of-bounds device write"""
+    if t is None:
+        return
+    dtypes = dtype if isinstance(dtype, tuple) else (dtype,)
+    if not (torch.is_tensor(t) and t.is_cuda and t.device == device):
+        raise ValueError('%s must be a CUDA tensor on %s' % (name, device))
+    if t.dtype not in dtypes or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+        raise ValueError('%s must be a contiguous %s tensor of shape %s (got %s %s)' % (name, dtypes[0], tuple(shape), t.dtype, tuple(t.shape)))
+
+
 class BabyAIVecEnv(object):
     """N environments of one BabyAI level living in HBM of one GPU."""
 
@@ -96,20 +108,42 @@ class BabyAIVecEnv(object):
     def reset(self, obs=None, direction=None):
         obs = self.obs if obs is None else obs
         direction = self.direction if direction is None else direction
+        n = self.num_envs
+        _check(obs, 'obs', self.device, torch.uint8, (n, 7, 7, 3))
+        _check(direction, 'direction', self.device, torch.int8, (n,))
         _lib.check(self.L.bb_pool_reset(self.h, _ptr(obs), _ptr(direction), self._stream()))
         return obs
 
     def step(self, actions, obs=None, reward=None, done=None, direction=None):
         """actions: CUDA tensor of N int8/uint8 or int64 values."""
-        assert actions.is_cuda and actions.is_contiguous() and actions.numel() == self.num_envs
+        n = self.num_envs
+        if not (torch.is_tensor(actions) and actions.is_cuda and actions.device == self.device and actions.is_contiguous()
+                and actions.numel() == n and actions.dtype in (torch.int8, torch.uint8, torch.int64)):
+            raise ValueError('actions must be a contiguous CUDA tensor of %d int8 / uint8 / int64 values on %s' % (n, self.device))
         nbytes = actions.element_size()
         obs = self.obs if obs is None else obs
         reward = self.reward if reward is None else reward
         done = self.done if done is None else done
         direction = self.direction if direction is None else direction
+        self._check_step_outputs(obs, reward, done, direction, ())
         _lib.check(self.L.bb_pool_step(self.h, _ptr(actions), nbytes, _ptr(obs), _ptr(reward), _ptr(done),
                                        _ptr(direction), self._stream()))
         return obs, reward, done
+
+    def _check_step_outputs(self, obs, reward, done, direction, lead):
+        n = self.num_envs
+        _check(obs, 'obs', self.device, torch.uint8, lead + (n, 7, 7, 3))
+        _check(reward, 'reward', self.device, torch.float32, lead + (n,))
+        _check(done, 'done', self.device, (torch.uint8, torch.bool), lead + (n,))
+        _check(direction, 'direction', self.device, torch.int8, lead + (n,))
+
+    def _check_rollout(self, actions, obs, reward, done, direction):
+        if not (torch.is_tensor(actions) and actions.dim() == 2 and actions.shape[1] == self.num_envs and actions.shape[0] >= 1):
+            raise ValueError('actions must have shape [T, %d]' % self.num_envs)
+        _check(actions, 'actions', self.device, (torch.int8, torch.uint8), tuple(actions.shape))
+        if obs is None or reward is None or done is None:
+            raise ValueError('rollout needs obs, reward and done buffers')
+        self._check_step_outputs(obs, reward, done, direction, (actions.shape[0],))
 
     def step_timed(self, actions):
         """bb_pool_step with CUDA events around each kernel -> (ms k_step, ms k_gen)."""
@@ -121,14 +155,15 @@ class BabyAIVecEnv(object):
 
     def rollout(self, actions, obs, reward, done, direction=None):
         """actions int8 [T, N] (CUDA); outputs [T, N, ...] CUDA tensors written in place."""
+        self._check_rollout(actions, obs, reward, done, direction)
         T = actions.shape[0]
-        assert actions.dtype in (torch.int8, torch.uint8) and actions.is_contiguous()
         _lib.check(self.L.bb_pool_rollout(self.h, _ptr(actions), T, _ptr(obs), _ptr(reward), _ptr(done),
                                           _ptr(direction), self._stream()))
         return obs, reward, done
 
     def rollout_timed(self, actions, obs, reward, done, direction=None):
         """rollout() with CUDA events around the stepping kernel and the level refill -> (ms, ms)."""
+        self._check_rollout(actions, obs, reward, done, direction)
         a, b = C.c_float(), C.c_float()
         _lib.check(self.L.bb_pool_rollout_timed(self.h, _ptr(actions), actions.shape[0], _ptr(obs), _ptr(reward), _ptr(done),
                                                 _ptr(direction), C.byref(a), C.byref(b)))

@@ -1,28 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/sec of the batched BabyAI pool (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--level L] [--envs E]
 
 Workload (config.workload): BASELINE.json configs[1] -- BabyAI-GoToLocal-v0,
 65 536 environments per GPU, uniform random actions, ParallelEnv auto-reset on.
-A "step" is one environment step of all 65 536 environments of a rank.
+A "step" is one environment step of all environments of a rank.
 
 Own arm, printed as ONE JSON line by rank 0:
   value     env-steps/sec, whole job, actions resident in HBM ([T, N] int8),
-            observations written to a [T, N, 147] rollout buffer (385 MB > L2),
-            K steps run as K/T calls of bb_pool_rollout (T = 40): the persistent
-            stepping kernel k_rollout + the bounded level refill (k_gen_scan,
-            k_gen_small); CUDA events, barrier + synchronize on both sides,
-            max over ranks.
-  e2e       the same metric through the reference-facing host-buffer call
-            (bb_pool_step_host = what ParallelEnv.step returns to BaseAlgo):
-            actions host->device and obs/reward/done/direction device->host
-            inside the timed region, every step.
-  roofline  dominant kernel k_rollout: 153 algorithmic bytes per env-step
-            (147 obs + 4 reward + 1 done + 1 action) x N envs x T
-            steps per launch / its CUDA-event duration (bb_pool_rollout_timed),
-            against MEASURED_PEAKS.json hbm_gbs.
+            observations written to a [T, N, 147] rollout buffer (385 MB > L2).
+            The timed region is ALWAYS calls of bb_pool_rollout (the persistent
+            stepping kernel, T = 40 steps per launch): K is rounded up to whole
+            rollouts and to at least MIN_TIMED_STEPS steps (`steps` = what was timed,
+            `steps_requested` = K); CUDA events, barrier + synchronize on both
+            sides, max over ranks.
+  roofline  achieved = 153 algorithmic bytes per env-step (147 obs + 4 reward +
+            1 done + 1 action) x the per-GPU `value` of that SAME
+            timed region, against MEASURED_PEAKS.json hbm_gbs; `kernel_frac` is
+            the same figure for the stepping kernel alone (CUDA events around it,
+            bb_pool_rollout_timed).
+  e2e       the same metric through the reference-facing C-ABI host-buffer call
+            (bb_pool_step_host = what ParallelEnv.step hands BaseAlgo): actions
+            host->device and obs/reward/done/direction device->host inside the
+            timed region, every step, >= 200 steps; per-rank min/median/max.
+  facade_e2e  the reference-SHAPED Python facade (vecenv.ParallelEnv.step: N obs
+            dicts per step) -- host bound by construction, a few steps only.
   cpu_baseline  the oracle's C port of the same path on this box's host cores.
+  reference_parallel_env  the reference's own ParallelEnv (64 procs) when a
+            reference tree is reachable (build container), else available: false.
 
 --impl reference: the CPU arm (oracle C port, all host threads, same workload);
 the reference itself is Python on a third-party package that is absent here
@@ -42,9 +48,16 @@ sys.path.insert(0, ROOT)
 LEVEL = 'GoToLocal'
 N_ENVS = 65536
 CHUNK = int(os.environ.get("BENCH_CHUNK", "40"))   # rollout length per launch (= --frames-per-proc, arguments.py:42)
+MIN_TIMED_STEPS = 1000          # the timed region never covers fewer steps than this (25 launches of 40 steps)
+MIN_HOST_STEPS = 200            # ... and the per-step legs (e2e, per_step_api) never fewer than this
 ALGO_BYTES_PER_STEP = 153       # 147 obs + 4 reward + 1 done + 1 action
 FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
 METRIC = 'env-steps/sec at 65 536 envs (GoToLocal); obs bit-exact vs CPU ref'
+
+
+def workload(level, n):
+    """config.workload -- the SAME string in both arms"""
+    return 'BabyAI-%s-v0, %d envs/GPU, uniform random actions, ParallelEnv auto-reset, in-kernel verifier' % (level, n)
 
 
 def hbm_peak():
@@ -103,12 +116,12 @@ class ClockSampler(object):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def cpu_port(steps_budget_s, n_envs, threads):
-    """Oracle C port (oracle/babyai_oracle.c) on the host cores: GoToLocal, random actions, auto-reset."""
+def cpu_port(level, steps_budget_s, n_envs, threads):
+    """Oracle C port (oracle/babyai_oracle.c) on the host cores: random actions, auto-reset."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import oracle as orc
-    pool = orc.OraclePool(LEVEL, n_envs, np.array([100 + i for i in range(n_envs)], dtype=np.uint64))
+    pool = orc.OraclePool(level, n_envs, np.array([100 + i for i in range(n_envs)], dtype=np.uint64))
     pool.reset()
     rng = np.random.RandomState(0)
     acts = rng.randint(0, 7, (64, n_envs)).astype(np.int8)
@@ -125,6 +138,32 @@ def cpu_port(steps_budget_s, n_envs, threads):
     return n_envs * k / dt, k
 
 
+def reference_parallel_env(level, procs=64, steps=300):
+    """north_star's side-by-side number: the reference's OWN ParallelEnv (penv.py:4-59, one forked process per env) over
+    envs built as scripts/train_rl.py:53-60 does, timed around ParallelEnv.step -- possible only where a reference tree is
+    reachable (BABYAI_REFERENCE or /root/reference: the build container).  The GPU box has none: say so."""
+    ref = os.environ.get('BABYAI_REFERENCE', '/root/reference')
+    if os.environ.get('BENCH_REF_PENV', '1') == '0':
+        return {'available': False, 'why': 'disabled (BENCH_REF_PENV=0)'}
+    if not os.path.isdir(os.path.join(ref, 'babyai', 'levels')):
+        return {'available': False, 'why': 'no reference tree at %s (the GPU box has none); measured in the build container: '
+                                           'see DESIGN.md section 7 / profiles/r02_reference_parallel_env.json' % ref}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'bench_ref_parallel_env.py'), '--level', level,
+                            '--procs', str(procs), '--steps', str(steps), '--warmup', '30'],
+                           capture_output=True, text=True, timeout=600)
+        lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+        if not lines:
+            return {'available': False, 'why': (r.stderr or 'no output')[-300:]}
+        d = json.loads(lines[-1])
+        d['available'] = True
+        d['value'] = d['parallel_env_steps_per_s']
+        d['unit'] = 'env-steps/s'
+        return d
+    except Exception as ex:
+        return {'available': False, 'why': repr(ex)[:300]}
+
+
 def run_reference(args, rank):
     """CPU arm: the oracle port with every host thread, same workload and metric."""
     if rank != 0:
@@ -133,8 +172,8 @@ def run_reference(args, rank):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import oracle as orc
     threads = os.cpu_count() or 1
-    n = N_ENVS
-    pool = orc.OraclePool(LEVEL, n, np.array([100 + i for i in range(n)], dtype=np.uint64))
+    n = args.envs
+    pool = orc.OraclePool(args.level, n, np.array([100 + i for i in range(n)], dtype=np.uint64))
     pool.reset()
     acts = np.random.RandomState(0).randint(0, 7, (64, n)).astype(np.int8)
     t0 = time.perf_counter()
@@ -145,7 +184,7 @@ def run_reference(args, rank):
     m = n
     if total > 120:
         m = max(1024, int(n * 120 / total) // 1024 * 1024)
-        pool = orc.OraclePool(LEVEL, m, np.array([100 + i for i in range(m)], dtype=np.uint64))
+        pool = orc.OraclePool(args.level, m, np.array([100 + i for i in range(m)], dtype=np.uint64))
         pool.reset()
         acts = acts[:, :m].copy()
     for k in range(args.warmup):
@@ -155,64 +194,18 @@ def run_reference(args, rank):
         pool.step(acts[k % 64], nthreads=threads)
     dt = time.perf_counter() - t0
     v = m * args.steps / dt
-    sample = '%d steps x %d envs (of %d) of %s, oracle C port, %d host threads' % (args.steps, m, n, LEVEL, threads)
+    sample = '%d steps x %d envs (of %d) of %s, oracle C port, %d host threads' % (args.steps, m, n, args.level, threads)
     out = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps * (n / m),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': 'BabyAI-%s-v0, %d envs, uniform random actions, auto-reset' % (LEVEL, n),
-                   'envs_per_step_sampled': m},
+        'config': {'workload': workload(args.level, n), 'envs_per_step_sampled': m,
+                   'execution': 'oracle/babyai_oracle.c (C restatement of the reference path), %d host threads' % threads},
         'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'reference_parallel_env': reference_parallel_env(args.level),
     }
-    print(json.dumps(out), flush=True)
-
-
-def lanes2_probe(args):
-    """Child process of the default bench run (own CUDA context: whatever happens here cannot touch the parent's numbers).
-    k_rollout2 -- the experimental two-lanes-per-environment rollout kernel (BB_ROLLOUT_LANES=2, csrc/rollout2.cuh), written
-    after round 1's GPU budget was spent -- against k_rollout in the same process: bit equality of three rollouts from the
-    same seeds and actions, then the same timing loop for both.  Prints one JSON dict."""
-    import numpy as np
-    import torch
-    from babyai_b200 import BabyAIVecEnv
-    n, T = args.envs, CHUNK
-    seeds = np.array([100 + i for i in range(n)], dtype=np.uint64)
-    os.environ.pop('BB_ROLLOUT_LANES', None)
-    pools = [BabyAIVecEnv(args.level, n, seeds=seeds)]
-    os.environ['BB_ROLLOUT_LANES'] = '2'                 # read by bb_pool_create
-    pools.append(BabyAIVecEnv(args.level, n, seeds=seeds))
-    os.environ.pop('BB_ROLLOUT_LANES')
-    dev = torch.device('cuda', 0)
-    gen = torch.Generator(device=dev).manual_seed(5)
-    acts = torch.randint(0, 7, (T, n), device=dev, dtype=torch.int8, generator=gen)
-    bufs = [(torch.zeros((T, n, 7, 7, 3), dtype=torch.uint8, device=dev), torch.zeros((T, n), device=dev),
-             torch.zeros((T, n), dtype=torch.uint8, device=dev), torch.zeros((T, n), dtype=torch.int8, device=dev)) for _ in pools]
-    for p in pools:
-        p.reset()
-    equal = True
-    for _ in range(3):
-        for p, b in zip(pools, bufs):
-            p.rollout(acts, *b)
-        torch.cuda.synchronize()
-        equal = equal and all(bool(torch.equal(x, y)) for x, y in zip(*bufs))
-    out = {'bit_equal_to_k_rollout': equal, 'level': args.level, 'envs': n, 'steps_per_launch': T}
-    for name, p, b in (('k_rollout', pools[0], bufs[0]), ('k_rollout2', pools[1], bufs[1])):
-        for _ in range(5):
-            p.rollout(acts, *b)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        reps = 40
-        for _ in range(reps):
-            p.rollout(acts, *b)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        kr = [p.rollout_timed(acts, *b)[0] for _ in range(8)][2:]
-        out[name] = {'us_per_step': 1e3 * ms / T, 'env_steps_per_s': n * T / (ms * 1e-3), 'kernel_ms': sum(kr) / len(kr),
-                     'errors': p.counters()['errors']}
     print(json.dumps(out), flush=True)
 
 
@@ -225,8 +218,8 @@ def main():
     ap.add_argument('--envs', type=int, default=N_ENVS, help='environments per GPU')
     ap.add_argument('--level', default=LEVEL)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--lanes2-probe', action='store_true', help='internal: the k_rollout2 child process')
-    ap.add_argument('--no-probe', action='store_true', help='skip the k_rollout2 child process')
+    ap.add_argument('--brief', action='store_true', help='device-resident value + kernel timing only (child runs of --other-configs)')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the child runs of BASELINE configs 3-5 (per-GPU share)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -236,9 +229,10 @@ def main():
     if args.impl == 'reference':
         run_reference(args, rank)
         return
-    if args.lanes2_probe:
-        lanes2_probe(args)
-        return
+
+    # one rank per GPU: bind the rank to its GPU's NUMA node before the CUDA context and any page-locked buffer exist
+    from babyai_b200.sharding import gather_counters, pin_to_gpu_numa, shard_seeds
+    numa = pin_to_gpu_numa(local_rank) if os.environ.get('BENCH_NO_NUMA_PIN') is None else None
 
     import numpy as np
     import torch
@@ -257,14 +251,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_f64(x):
+        """per-rank float -> list over ranks (all-gather of one double)"""
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return [float(p.item()) for p in parts]
+
     n, K, W = args.envs, args.steps, args.warmup
+    T = CHUNK
     # rank r owns global env indices [r*n, (r+1)*n); seeds follow the global index (train_rl.py:59, --seed 1)
-    from babyai_b200.sharding import gather_counters, shard_seeds
     seeds = shard_seeds(1, world * n, rank, world)
     env = BabyAIVecEnv(args.level, n, seeds=seeds, device=local_rank)
     env.reset()
 
-    T = CHUNK
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     actions = torch.randint(0, 7, (T, n), device=dev, dtype=torch.int8, generator=gen)
     obs = torch.empty((T, n, 7, 7, 3), dtype=torch.uint8, device=dev)       # 385 MB at n = 65 536: larger than L2
@@ -272,15 +274,15 @@ def main():
     done = torch.empty((T, n), dtype=torch.uint8, device=dev)
     dirs = torch.empty((T, n), dtype=torch.int8, device=dev)
 
-    def run_steps(k):
-        full, rem = divmod(k, T)
-        for _ in range(full):
+    def run_rollouts(r):
+        for _ in range(r):
             env.rollout(actions, obs, rew, done, dirs)
-        for t in range(rem):
-            env.step(actions[t], obs[t], rew[t], done[t], dirs[t])
 
-    # ---- device-resident throughput ------------------------------------------------
-    run_steps(max(W, 3))
+    # ---- device-resident throughput: whole rollouts, whatever K ---------------------------------
+    n_roll = max((K + T - 1) // T, (MIN_TIMED_STEPS + T - 1) // T)
+    K_eff = n_roll * T
+    w_roll = max((max(W, 3) + T - 1) // T, 2)
+    run_rollouts(w_roll)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -289,7 +291,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    run_steps(K)
+    run_rollouts(n_roll)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -299,24 +301,36 @@ def main():
     if rank == 0:
         t_end = time.time() + 0.4
         while time.time() < t_end:
-            run_steps(T)
-        torch.cuda.synchronize()
+            run_rollouts(4)
+            torch.cuda.synchronize()
         clocks = sampler.stop()
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
+    ms_ranks = gather_f64(ms)
+    ms = max(ms_ranks)
 
-    # ---- per-kernel timing (roofline): the stepping kernel of one rollout launch, CUDA events on its stream ----
+    # ---- per-kernel timing: the stepping kernel of one rollout launch, CUDA events on its stream ----
     kr, kf = [], []
-    for t in range(24):
+    for t in range(16):
         a, b = env.rollout_timed(actions, obs, rew, done, dirs)
         if t >= 4 and a > 0:
             kr.append(a); kf.append(b)          # b = 0 for the launches that do not refill
     k_roll_ms = sum(kr) / len(kr) if kr else 0.0
     k_refill_ms = sum(kf) / len(kf) if kf else 0.0      # amortised per launch
-    # the per-step entry point (policy in the loop): bb_pool_step on device buffers, one launch per step
-    Ks = min(K, 600)
+
+    peak, peak_src = hbm_peak()
+    value = world * n * K_eff / (ms * 1e-3)
+    achieved = ALGO_BYTES_PER_STEP * (value / world) / 1e9           # GB/s of algorithmic bytes per GPU, SAME timed region
+    kernel_achieved = ALGO_BYTES_PER_STEP * n * T / (k_roll_ms * 1e-3) / 1e9 if k_roll_ms > 0 else 0.0
+    if args.brief:
+        if rank == 0:
+            print(json.dumps({'level': args.level, 'envs_per_gpu': n, 'value': value, 'us_per_step': 1e3 * ms / K_eff, 'steps': K_eff,
+                              'kernel_us_per_step': 1e3 * k_roll_ms / T, 'refill_ms_per_launch': k_refill_ms,
+                              'roofline_frac': achieved / peak, 'counters': env.counters()}), flush=True)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- the per-step entry point (policy in the loop): bb_pool_step on device buffers, one launch per step ----
+    Ks = max(min(K, 600), MIN_HOST_STEPS)
     for t in range(20):
         env.step(actions[t % T], obs[t % T], rew[t % T], done[t % T], dirs[t % T])
     barrier()
@@ -326,27 +340,26 @@ def main():
         env.step(actions[t % T], obs[t % T], rew[t % T], done[t % T], dirs[t % T])
     s1.record()
     barrier()
-    per_step_ms = s0.elapsed_time(s1) / Ks
+    per_step_ms = max(gather_f64(s0.elapsed_time(s1) / Ks))
 
-    # ---- end to end through the host-buffer call ----------------------------------------
+    # ---- end to end through the host-buffer C-ABI call --------------------------------------------
     h_act = np.random.RandomState(7 + rank).randint(0, 7, (64, n)).astype(np.int8)
     # page-locked host buffers (what babyai_b200.ParallelEnv hands to bb_pool_step_host)
     pins = [torch.zeros((n, 7, 7, 3), dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.float32).pin_memory(),
             torch.zeros(n, dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.int8).pin_memory()]
     h_obs, h_rew, h_done, h_dir = [t.numpy() for t in pins]
-    Ke = min(K, 400)
-    for k in range(5):
+    Ke = max(min(K, 400), MIN_HOST_STEPS)
+    for k in range(10):
         env.step_host(h_act[k], h_obs, h_rew, h_done, h_dir)
     barrier()
     t0 = time.perf_counter()
     for k in range(Ke):
         env.step_host(h_act[k % 64], h_obs, h_rew, h_done, h_dir)
+    own_s = time.perf_counter() - t0             # this rank's own loop (bb_pool_step_host synchronises its stream)
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_ranks = sorted(n * Ke / s for s in gather_f64(own_s))
+    e2e_s = max(gather_f64(e2e_s))
 
     # ---- the only collective on this path: all-gather of the counters --------------------
     cnt = gather_counters(env.counters(), device=dev)
@@ -355,16 +368,16 @@ def main():
     # per step: actions host->device, the step kernel writing into a fresh observation tensor, ObssPreprocessor handing
     # the model image float[N,7,7,3] + instr long[N,L] on the device, reward/done device->host.  Measured on this rank.
     learner = {}
-    for key, fused_io in (('tensor_copies', False), ('fused_io', True)):
-        # tensor_copies: bb_pool_step + torch copies of actions / reward / done; fused_io: bb_pool_step_learner (those three
-        # over mapped page-locked memory inside the step call)
+    for key, fused_io in (('fused_io', True), ('tensor_copies', False)):
+        # fused_io (default): bb_pool_step_learner (actions / reward / done over mapped page-locked memory inside the step call);
+        # tensor_copies: bb_pool_step + torch copies of those three
         try:
             from babyai_b200 import make_envs
             from babyai_b200.learner import DeviceParallelEnv, ObssPreprocessor
             denv = DeviceParallelEnv(make_envs(args.level, n), pool=env, fused_io=fused_io)
             pre = ObssPreprocessor(trim=False)
             ob = denv.reset()
-            Kl = min(K, 300)
+            Kl = max(min(K, 300), MIN_HOST_STEPS)
             for k in range(5):
                 pre(ob, device=dev)
                 ob, _r, _d, _i = denv.step(h_act[k])
@@ -379,35 +392,47 @@ def main():
                             'd2h_bytes_per_step': n * 5}
         except Exception as ex:          # informational leg: never lose the bench line over it
             learner[key] = {'error': repr(ex)[:300]}
-    learner['api'] = 'DeviceParallelEnv.step + ObssPreprocessor (observations stay in HBM)'
+    learner['api'] = 'DeviceParallelEnv.step + ObssPreprocessor (observations stay in HBM); fused_io is the default'
 
-    # ---- experimental kernel, in a child process with its own CUDA context (single-GPU runs only; informational) ----
-    probe = None
-    if rank == 0 and world == 1 and not args.no_probe:
-        probe = {}
-        # the bench workload, and BASELINE config 5's per-GPU share (multi-room: 22x22 staging, k_gen beside the kernel)
-        # (key, level, envs, extra environment): the bench workload with the fused generator warp and with refill passes
-        # instead (two separate children: whatever happens to one leaves the other's numbers), and BASELINE config 5's
-        # per-GPU share (multi-room: 22x22 staging, k_gen beside the kernel)
-        jobs = [(args.level, args.level, n, {}), (args.level + ' BB_GEN_FUSED=0', args.level, n, {'BB_GEN_FUSED': '0'})]
-        if args.level == LEVEL and n == N_ENVS:
-            jobs.append(('BossLevel', 'BossLevel', 32768, {}))
-        for key, lv, ne, extra in jobs:
+    # ---- the reference-SHAPED facade: vecenv.ParallelEnv.step builds N Python obs dicts per step (rank 0, single-GPU runs) ----
+    facade = None
+    if rank == 0 and world == 1:
+        try:
+            from babyai_b200 import ParallelEnv, make_envs
+            nf = min(n, 4096)                     # penv-sized: the dict facade is host bound by orders of magnitude
+            pe = ParallelEnv(make_envs(args.level, nf))
+            pe.reset()
+            fa = np.random.RandomState(3).randint(0, 7, (8, nf))
+            for k in range(2):
+                list(pe.step(fa[k]))
+            t0 = time.perf_counter()
+            for k in range(2, 8):
+                list(pe.step(fa[k]))
+            dt = time.perf_counter() - t0
+            facade = {'value': nf * 6 / dt, 'unit': 'env-steps/s', 'envs': nf, 'steps': 6,
+                      'api': 'babyai_b200.ParallelEnv.step (penv.py surface: tuple of N obs dicts, rewards, dones, infos); '
+                             'host bound: the per-env Python objects dominate'}
+            pe.pool.close()
+        except Exception as ex:
+            facade = {'error': repr(ex)[:300]}
+
+    # ---- BASELINE configs 3-5 at their per-GPU size, each in a child process (single-GPU default runs only) ----
+    others = None
+    if rank == 0 and world == 1 and not args.no_other_configs and args.level == LEVEL and n == N_ENVS:
+        others = {}
+        for key, lv, ne in (('C3 PickupLoc', 'PickupLoc', 65536), ('C4 GoTo', 'GoTo', 32768), ('C5 BossLevel (per-GPU share)', 'BossLevel', 32768)):
             try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--lanes2-probe', '--level', lv, '--envs', str(ne)],
-                                   capture_output=True, text=True, timeout=100, env=dict(os.environ, **extra))
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--brief', '--level', lv, '--envs', str(ne),
+                                    '--steps', '1000', '--warmup', '80'], capture_output=True, text=True, timeout=150)
                 lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
-                probe[key] = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
+                others[key] = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
             except subprocess.TimeoutExpired:
-                probe[key] = {'error': 'timed out after 100 s (child killed); remaining probes skipped'}
-                break                                        # keep the whole bench run within minutes
+                others[key] = {'error': 'timed out after 150 s (child killed); remaining configs skipped'}
+                break
             except Exception as ex:
-                probe[key] = {'error': repr(ex)[:300]}
+                others[key] = {'error': repr(ex)[:300]}
 
     if rank == 0:
-        peak, peak_src = hbm_peak()
-        value = world * n * K / (ms * 1e-3)
-        achieved = ALGO_BYTES_PER_STEP * n * T / (k_roll_ms * 1e-3) / 1e9 if k_roll_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp):
@@ -416,35 +441,43 @@ def main():
             except Exception:
                 traffic = None
         out = {
-            'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K_eff, 'steps_requested': K,
+            'warmup': w_roll * T, 'ms_per_step': ms / K_eff, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': 'BabyAI-%s-v0, %d envs/GPU, uniform random actions (int8, resident in HBM), '
-                                   'ParallelEnv auto-reset, in-kernel verifier' % (args.level, n),
+            'config': {'workload': workload(args.level, n),
                        'envs_per_gpu': n, 'rollout_chunk': T,
                        'l2_policy': 'obs written to a [%d, %d, 147] buffer (%.0f MB) larger than L2' % (T, n, T * n * 147 / 1e6),
-                       'execution': 'bb_pool_rollout: ONE persistent kernel per %d steps (k_rollout: per CTA two stepping warps with '
-                                    'the env state resident in shared memory + one generator warp that refills the level rings of the '
-                                    "CTA's envs; refill_ms_per_launch > 0 only when BB_GEN_FUSED=0 or for rooms smaller than 6x6)" % T,
-                       'parallelism': 'replicas x%d, counters all-gather only' % world},
+                       'execution': 'timed region = %d calls of bb_pool_rollout (%d steps each; K = %d requested, rounded up to whole '
+                                    'rollouts and to >= %d steps): one persistent stepping kernel per call with the env state resident in '
+                                    'shared memory; level generation inside it (single-room levels) or beside it on a side stream' %
+                                    (n_roll, T, K, MIN_TIMED_STEPS),
+                       'actions': 'int8 [T, N], resident in HBM',
+                       'parallelism': 'replicas x%d, counters all-gather only' % world,
+                       'numa': numa},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'kernel': 'k_rollout', 'kernel_ms': k_roll_ms, 'steps_per_launch': T,
+                         'traffic': traffic, 'kernel': 'k_rollout', 'from': 'value / n_gpus x 153 B (the timed region above)',
+                         'kernel_achieved': kernel_achieved, 'kernel_frac': kernel_achieved / peak,
+                         'kernel_ms': k_roll_ms, 'steps_per_launch': T,
                          'kernel_us_per_step': 1e3 * k_roll_ms / T, 'refill_ms_per_launch': k_refill_ms,
                          'algorithmic_bytes_per_launch': ALGO_BYTES_PER_STEP * n * T, 'peak_source': peak_src},
             'per_step_api': {'value': world * n / (per_step_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': per_step_ms,
-                             'api': 'bb_pool_step (one launch per step: k_rollout with T = 1 on single-room levels, k_step8 otherwise; level generation on a side stream), device buffers', 'steps': Ks},
+                             'api': 'bb_pool_step (one launch per step; level generation on a side stream), device buffers', 'steps': Ks},
             'e2e': {'value': world * n * Ke / e2e_s, 'unit': 'env-steps/s', 'h2d_bytes_per_step': n,
                     'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke,
-                    'api': 'bb_pool_step_host, page-locked host buffers'},
+                    'api': 'bb_pool_step_host (the C-ABI call, not the Python dict facade), page-locked host buffers',
+                    'per_rank': {'min': e2e_ranks[0], 'median': e2e_ranks[len(e2e_ranks) // 2], 'max': e2e_ranks[-1]}},
+            'facade_e2e': facade,
             'learner_path': learner,
-            'experimental': {'k_rollout2': probe},
+            'other_configs': others,
+            'reference_parallel_env': reference_parallel_env(args.level),
             'gpu_launches': int(launches),
+            'ms_per_rank': ms_ranks,
             'clocks': clocks,
             'counters': cnt,
         }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, k = cpu_port(12.0, n, threads)
+            v, k = cpu_port(args.level, 12.0, n, threads)
             out['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
                                    'sample': '%d steps x %d envs of %s, oracle C port, %d host threads' % (k, n, args.level, threads)}
         print(json.dumps(out), flush=True)

@@ -21,6 +21,16 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if 'gpu' in it.keywords and it.get_closest_marker('timeout') is None:
             it.add_marker(pytest.mark.timeout(240, method='thread'))
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if not have_gpu:                          # a plain `pytest` on a GPU-less machine skips the GPU tests instead of failing
+        skip_gpu = pytest.mark.skip(reason='no CUDA device (run with -m gpu on the B200 box)')
+        for it in items:
+            if 'gpu' in it.keywords:
+                it.add_marker(skip_gpu)
     if not refenv.available():
         skip = pytest.mark.skip(reason='/root/reference not present (GPU box)')
         for it in items:

@@ -136,42 +136,6 @@ void he_step(HPool *p, const int8_t *actions, uint8_t *obs, float *reward, uint8
         reward[e] = rew; done[e] = dn; if (dir) dir[e] = (int8_t)(p->live[e].hot.dirflags & 3);
     }
 }
-// The observation path of k_rollout2 (two lanes per environment), one warp's worth: envs e0 .. e0 + 15, the 32 lanes
-// emulated in turn (the two shuffles of the kernel become array reads).  out: the 16 x 147-byte warp tile.
-void he_pair_obs(HPool *p, int e0, uint8_t *out)
-{
-    const LevelParams &lp = p->lp;
-    uint32_t lo[32][4], hi[32][4], cm[32], o[32][4][6];
-    uint32_t tile[16 * OBS_BYTES / 4 + 4];
-    memset(tile, 0xEE, sizeof tile);
-    for (int lane = 0; lane < 32; lane++) {
-        const int e = e0 + (lane >> 1), h = lane & 1;
-        cm[lane] = 0;
-        for (int k = 0; k < 4; k++) lo[lane][k] = hi[lane][k] = 0;
-        if (e >= p->n) continue;
-        Slot &s = p->live[e];
-        GlobalMem mem(lp, s.grid.data(), &s.obj, &s.ins);
-        const ViewGeom v = view_geom(lp, s.hot.x, s.hot.y, s.hot.dirflags & 3);
-        cm[lane] = pair_cols_load(mem, v, h, lo[lane], hi[lane]);
-    }
-    for (int lane = 0; lane < 32; lane++) {
-        const int e = e0 + (lane >> 1), h = lane & 1;
-        for (int k = 0; k < 4; k++) for (int j = 0; j < 6; j++) o[lane][k][j] = 0;
-        if (e >= p->n) continue;
-        Slot &s = p->live[e];
-        GlobalMem mem(lp, s.grid.data(), &s.obj, &s.ins);
-        const ViewGeom v = view_geom(lp, s.hot.x, s.hot.y, s.hot.dirflags & 3);
-        const uint32_t other = cm[lane ^ 1];                       // __shfl_xor_sync(.., cm, 1)
-        pair_cols_encode(lp, v, s.hot.x, s.hot.y, s.hot.dirflags & 3, carry_cell(p, s.hot, mem), h, lo[lane], hi[lane],
-                         h == 0 ? cm[lane] : other, h == 0 ? other : cm[lane], o[lane]);
-    }
-    for (int lane = 0; lane < 32; lane++) {
-        const uint32_t next_first = lane < 31 ? o[lane + 1][0][0] : o[lane][0][0];   // __shfl_down_sync(.., o[0][0], 1)
-        pair_stage(tile, o[lane], lane >> 1, lane & 1, next_first);
-    }
-    memcpy(out, tile, 16 * OBS_BYTES);
-}
-
 void he_tokens(HPool *p, int e, int16_t *out) { memcpy(out, p->live[e].tok.data(), MAXTOK * sizeof(int16_t)); }
 void he_get_state(HPool *p, int e, uint8_t *grid, int32_t *info)
 {

@@ -46,7 +46,6 @@ def lib():
         L.he_vis_rows.argtypes = [C.c_void_p, C.c_void_p]
         L.he_stage.argtypes = [C.c_void_p, C.c_void_p]
         L.he_stage21.argtypes = [C.c_void_p, C.c_void_p]
-        L.he_pair_obs.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -90,12 +89,6 @@ class HostEmuPool:
         self.L.he_step(self.h, _p(a), _p(self.obs), _p(self.reward), _p(self.done), _p(self.direction))
         return self.obs, self.reward, self.done
 
-    def pair_obs(self, e0):
-        """observations of envs e0 .. e0 + 15 through the two-lanes-per-env path (k_rollout2)"""
-        out = np.zeros((16, 147), np.uint8)
-        self.L.he_pair_obs(self.h, e0, _p(out))
-        return out.reshape(16, 7, 7, 3)
-
     def tokens(self, i):
         t = np.zeros(72, np.int16)
         self.L.he_tokens(self.h, i, _p(t))
@@ -109,10 +102,10 @@ class HostEmuPool:
                           step_count=int(info[4]), max_steps=int(info[5]), draws=int(info[6]), attempts=int(info[7]))
 
 
-# ---- k_rollout2's stepping role on OS threads (simt_rollout2.cpp) -------------------------------------------------
-SRC2 = os.path.join(HERE, 'simt_rollout2.cpp')
-OUT2 = os.path.join(HERE, 'libsimt_rollout2.so')
-DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout2.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'gen_round.cuh')] + DEPS[1:]
+# ---- the rollout kernels' roles on OS threads (simt_rollout.cpp) -------------------------------------------------
+SRC2 = os.path.join(HERE, 'simt_rollout.cpp')
+OUT2 = os.path.join(HERE, 'libsimt_rollout.so')
+DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'simt.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_lane.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'gen_round.cuh')] + DEPS[1:]
 _lib2 = None
 
 
@@ -131,12 +124,13 @@ def lib2():
         L.r2_rollout_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.r2_min_ring_level.argtypes = [C.c_void_p]
         L.r2_max_tokens.argtypes = [C.c_void_p]
+        L.r2_error_flag.argtypes = [C.c_void_p]
         _lib2 = L
     return _lib2
 
 
-class Rollout2Pool:
-    """A pool in pool.cu's memory layout (SoA + level rings) stepped by rollout2_step_warp, one OS thread per lane."""
+class RolloutPool:
+    """A pool in pool.cu's memory layout (SoA + level rings) stepped by the rollout kernels' role functions, one OS thread per lane."""
 
     def __init__(self, spec, n, seeds, depth=24, mode=0):
         self.L, self.n = lib2(), n

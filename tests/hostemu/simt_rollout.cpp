@@ -1,5 +1,6 @@
-// simt_rollout2.cpp -- TEST-ONLY: runs the stepping role of k_rollout2 (babyai_b200/csrc/rollout2.cuh, the very
-// function the kernel calls) on the host with ONE OS THREAD PER LANE.  The warp primitives the function uses
+// simt_rollout.cpp -- TEST-ONLY: runs the stepping roles of the rollout kernels (babyai_b200/csrc/rollout_lane.cuh and
+// rollout_cta.cuh: the very functions k_rollout / k_rollout_cta call) and the fused generator warp (gen_round.cuh) on the
+// host with ONE OS THREAD PER LANE.  The warp primitives the functions use
 // (__syncwarp, __shfl_sync, __shfl_xor_sync, __shfl_down_sync) are rendezvous on a per-warp barrier; every lane of a warp
 // reaches them in the same order (none sits inside divergent code), which is exactly what the hardware requires too --
 // a lane that skipped one would dead-lock here instead of silently reading garbage.  Global memory is host memory laid
@@ -19,7 +20,7 @@
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v = { x, y, z, w }; return v; }
 
-// ---- the warp primitives of rollout2.cuh, emulated ---------------------------------------------------------------
+// ---- the warp primitives of simt.cuh, emulated ---------------------------------------------------------------
 struct WarpCtx {
     std::barrier<> bar{32};
     uint32_t xchg[32];
@@ -28,7 +29,20 @@ static thread_local WarpCtx *tl_warp = nullptr;
 static thread_local int tl_lane = 0;
 static thread_local std::barrier<> *tl_cta = nullptr;       // __syncthreads of a fused launch (4 stepping warps + the generator warp)
 
+static thread_local int *tl_cta_or = nullptr;               // two alternating accumulators of __syncthreads_or
+static thread_local int tl_cta_phase = 0;
 static inline void emu_syncwarp() { tl_warp->bar.arrive_and_wait(); }
+static inline int emu_syncthreads_or(int pred)
+{
+    int *acc = tl_cta_or + (tl_cta_phase & 1);
+    if (pred) __atomic_store_n(acc, 1, __ATOMIC_RELAXED);
+    tl_cta->arrive_and_wait();
+    const int r = __atomic_load_n(acc, __ATOMIC_RELAXED);
+    tl_cta->arrive_and_wait();                           // everybody has read it ...
+    if (tl_lane == 0) __atomic_store_n(tl_cta_or + ((tl_cta_phase + 1) & 1), 0, __ATOMIC_RELAXED);   // ... the OTHER one is clear for the next use
+    tl_cta_phase++;
+    return r;
+}
 static inline uint32_t emu_exchange(uint32_t v, int src)
 {
     tl_warp->xchg[tl_lane] = v;
@@ -63,14 +77,20 @@ template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exch
 #define BB_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
 #define BB_PREFETCH_L2(p) ((void)(p))
 #define BB_LD_S8(p) ((int)*(p))
+#define BB_SYNCTHREADS_OR(x) emu_syncthreads_or(x)
+// the bulk (async proxy) tile store: a plain copy here; the fence / wait are no-ops
+#define BB_FENCE_ASYNC_SMEM() ((void)0)
+#define BB_BULK_STORE(gdst, ssrc, bytes) memcpy((gdst), (ssrc), (bytes))
+#define BB_BULK_WAIT_READ() ((void)0)
 
-#include "../../babyai_b200/csrc/rollout2.cuh"
+#include "../../babyai_b200/csrc/simt.cuh"
 #include "../../babyai_b200/csrc/gen_round.cuh"
+#include "../../babyai_b200/csrc/rollout_lane.cuh"
 #include "../../babyai_b200/csrc/level_params.h"
 
 using namespace bb;
 
-// the accessor k_rollout / k_rollout2 use on shared memory (pool.cu SmemOnlyMem), restated for the host
+// the accessor k_rollout uses on shared memory (pool.cu SmemOnlyMem), restated for the host
 struct HostSmemMem {
     static constexpr bool untracked = false;
     const LevelParams &lp; uint8_t *g, *o, *i;
@@ -99,6 +119,7 @@ struct HostPoolPtrs {                                     // the members of pool
     RngRec *rng; uint32_t *attempts;
     float *last_reward;
     unsigned long long *warp_counters;
+    int *err_flag;
     int32_t depth, n;
 };
 
@@ -110,6 +131,7 @@ struct RPool {
     std::vector<uint32_t> head, tail, tail_pub, attempts;
     std::vector<RngRec> rng; std::vector<float> last_reward;
     std::vector<unsigned long long> counters;
+    int err;
     HostPoolPtrs P;
 };
 
@@ -133,7 +155,7 @@ RPool *r2_create(const bb_level_spec *spec, int n, int depth, const uint64_t *se
 {
     RPool *p = new RPool();
     const char *err = make_level_params(spec, &p->lp);
-    if (err) { fprintf(stderr, "simt_rollout2: %s\n", err); abort(); }
+    if (err) { fprintf(stderr, "simt_rollout: %s\n", err); abort(); }
     const LevelParams &lp = p->lp;
     p->n = n; p->D = depth; p->mode = mode;
     const size_t N = (size_t)n, DN = (size_t)depth * n;
@@ -143,14 +165,14 @@ RPool *r2_create(const bb_level_spec *spec, int n, int depth, const uint64_t *se
     p->tok.assign(N * lp.max_tokens, 0); p->rtok.assign(DN * lp.max_tokens, 0);
     p->head.assign(N, 0); p->tail.assign(N, 0); p->tail_pub.assign(N, 0);
     p->rng.resize(N); p->last_reward.assign(N, 0.f); p->locked_room.assign(N, 0xFF); p->attempts.assign(N, 0);
-    p->counters.assign(4 * (N / R2_ENVS + 2), 0);
+    p->counters.assign(4 * (N / 8 + 2), 0); p->err = 0;
     for (int e = 0; e < n; e++) { p->rng[e].seed = seeds[e]; p->rng[e].draws = 0; }
     HostPoolPtrs &P = p->P;
     P.grid = p->grid.data(); P.hot = p->hot.data(); P.obj = p->obj.data(); P.ins = p->ins.data(); P.tok = p->tok.data();
     P.rgrid = p->rgrid.data(); P.rhot = p->rhot.data(); P.robj = p->robj.data(); P.rins = p->rins.data(); P.rtok = p->rtok.data();
     P.head = p->head.data(); P.tail = p->tail.data(); P.tail_pub = p->tail_pub.data();
     P.last_reward = p->last_reward.data(); P.warp_counters = p->counters.data();
-    P.rng = p->rng.data(); P.attempts = p->attempts.data();
+    P.rng = p->rng.data(); P.attempts = p->attempts.data(); P.err_flag = &p->err;
     P.depth = depth; P.n = n;
     // reset: generate, then take the first level of every ring as the live state (what bb_pool_reset does)
     refill(p);
@@ -166,13 +188,12 @@ RPool *r2_create(const bb_level_spec *spec, int n, int depth, const uint64_t *se
 }
 void r2_destroy(RPool *p) { delete p; }
 
-// one bb_pool_rollout worth of k_rollout2 (non-fused launch): every warp of the grid, 32 threads each
+// one bb_pool_rollout worth of k_rollout (non-fused launch): every warp of the grid, 32 threads each
 void r2_rollout(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *reward, uint8_t *done, int8_t *dirs, int64_t *counters4)
 {
     const LevelParams &lp = p->lp;
-    const int gs = (lp.cells_pad >> 2) | 1;
-    const int warp_words = R2_ENVS * (gs + R2_OBJ_STRIDE + R2_INS_STRIDE) + TILE2_WORDS;
-    const int nwarps = (p->n + R2_ENVS - 1) / R2_ENVS;
+    const int warp_words = rl_warp_words(lp);
+    const int nwarps = (p->n + 31) / 32;
     for (int wg = 0; wg < nwarps; wg++) {
         WarpCtx ctx;
         std::vector<uint32_t> smem((size_t)warp_words + 8, 0xDEADBEEFu);
@@ -182,8 +203,8 @@ void r2_rollout(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *rew
         for (int lane = 0; lane < 32; lane++)
             th.emplace_back([&, lane]() {
                 tl_warp = &ctx; tl_lane = lane;
-                if (lp.kind == KIND_UNLOCK) rollout2_step_warp<HostPoolPtrs, HostSmemMem, true>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, false, base, lane, wg, nullptr);
-                else rollout2_step_warp<HostPoolPtrs, HostSmemMem>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, false, base, lane, wg, nullptr);
+                if (lp.kind == KIND_UNLOCK) rollout_lane_step_warp<HostPoolPtrs, HostSmemMem, 1, true>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, false, base, lane, wg, nullptr);
+                else rollout_lane_step_warp<HostPoolPtrs, HostSmemMem, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, false, base, lane, wg, nullptr);
             });
         for (auto &t : th) t.join();
     }
@@ -192,33 +213,32 @@ void r2_rollout(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *rew
     for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
 }
 
-// a FUSED launch of k_rollout2: per CTA four stepping warps + the generator warp (rollout2_gen_warp, gen_small_round), 160
+// a FUSED launch of k_rollout: per CTA two stepping warps + the generator warp (rollout_gen_warp, gen_small_round), 96
 // threads, one CTA after the other; nothing refills the rings but the generator warps
 void r2_rollout_fused(RPool *p, const int8_t *actions, int T, int gen_rounds, int gen_min_active, uint8_t *obs, float *reward,
                       uint8_t *done, int8_t *dirs, int64_t *counters4)
 {
     const LevelParams &lp = p->lp;
-    if (!lp.small) { fprintf(stderr, "simt_rollout2: fused launches are for small single-room levels\n"); abort(); }
-    const int gs = (lp.cells_pad >> 2) | 1;
-    const int warp_words = R2_ENVS * (gs + R2_OBJ_STRIDE + R2_INS_STRIDE) + TILE2_WORDS;
-    const int cta_envs = R2_WARPS * R2_ENVS;
+    if (!lp.small) { fprintf(stderr, "simt_rollout: fused launches are for small single-room levels\n"); abort(); }
+    const int warp_words = rl_warp_words(lp);
+    const int SW = 2, cta_envs = SW * 32;
     const int nctas = (p->n + cta_envs - 1) / cta_envs;
     for (int cta = 0; cta < nctas; cta++) {
-        std::vector<WarpCtx> ctx(R2_WARPS + 1);
-        std::barrier<> cta_bar(32 * (R2_WARPS + 1));
-        std::vector<uint32_t> smem((size_t)R2_WARPS * warp_words + RG_AREA_WORDS + 8, 0xDEADBEEFu);
+        std::vector<WarpCtx> ctx(SW + 1);
+        std::barrier<> cta_bar(32 * (SW + 1));
+        std::vector<uint32_t> smem((size_t)SW * warp_words + RG_AREA_WORDS + 8, 0xDEADBEEFu);
         uint32_t *smr = smem.data();
         while (((uintptr_t)smr) & 15) smr++;
-        uint32_t *g_area = smr + R2_WARPS * warp_words;
+        uint32_t *g_area = smr + SW * warp_words;
         volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
         std::vector<std::thread> th;
-        for (int tid = 0; tid < 32 * (R2_WARPS + 1); tid++)
+        for (int tid = 0; tid < 32 * (SW + 1); tid++)
             th.emplace_back([&, tid]() {
                 const int lane = tid & 31, warp = tid >> 5;
                 tl_warp = &ctx[warp]; tl_lane = lane; tl_cta = &cta_bar;
-                if (warp == R2_WARPS) rollout2_gen_warp(lp, p->P, g_area, s_done, p->n, T, cta * cta_envs, gen_rounds, gen_min_active, lane);
-                else rollout2_step_warp<HostPoolPtrs, HostSmemMem>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, true,
-                                                                   smr + warp * warp_words, lane, cta * R2_WARPS + warp, s_done);
+                if (warp == SW) rollout_gen_warp(lp, p->P, g_area, s_done, p->n, T, cta * cta_envs, gen_rounds, gen_min_active, lane, SW);
+                else rollout_lane_step_warp<HostPoolPtrs, HostSmemMem, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, true,
+                                                                                 smr + warp * warp_words, lane, cta * SW + warp, s_done);
             });
         for (auto &t : th) t.join();
     }
@@ -228,6 +248,7 @@ void r2_rollout_fused(RPool *p, const int8_t *actions, int T, int gen_rounds, in
 
 int r2_min_ring_level(RPool *p) { int m = 1 << 30; for (int e = 0; e < p->n; e++) { const int have = (int)(p->tail[e] - p->head[e]); if (have < m) m = have; } return m; }
 
+int r2_error_flag(RPool *p) { return p->err; }
 void r2_tokens(RPool *p, int e, int16_t *out) { memcpy(out, p->tok.data() + (size_t)e * p->lp.max_tokens, p->lp.max_tokens * sizeof(int16_t)); }
 int r2_max_tokens(RPool *p) { return p->lp.max_tokens; }
 

@@ -20,12 +20,13 @@ def _line(args, env=None):
 
 
 def test_reference_arm_json_line():
-    d = _line(['--impl', 'reference', '--gpus', '1', '--steps', '3', '--warmup', '1'])
+    d = _line(['--impl', 'reference', '--gpus', '1', '--steps', '3', '--warmup', '1'], env={'BENCH_REF_PENV': '0'})
     assert BASE_KEYS <= set(d) and d['impl'] == 'reference'
     assert d['metric'] == json.load(open(os.path.join(ROOT, 'BASELINE.json')))['metric']
     assert d['unit'] == 'env-steps/s' and d['higher_is_better'] is True and d['steps'] == 3 and d['warmup'] == 1
     assert d['value'] > 0 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['reference_parallel_env']['available'] is False
     assert 'workload' in d['config'] and 'GoToLocal' in d['config']['workload'] and d['gpu_launches'] == 0
 
 

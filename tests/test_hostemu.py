@@ -181,34 +181,17 @@ def test_column_record_staging_packs_21_byte_records():
         assert np.array_equal(tile[:588], by.reshape(-1))
 
 
-@pytest.mark.parametrize('level', ['GoToLocal', 'GoToObjS4', 'PickupLoc', 'PutNextLocal', 'GoTo', 'BossLevel', 'Unlock', 'GoToObjMazeS4R2'])
-def test_pair_observation_path_equals_observe(level):
-    """k_rollout2 (experimental, two lanes per environment): column halves, the see-through exchange, per-column encode and
-    the 21-byte record staging of a 16-env warp tile must reproduce observe() byte for byte, for every pose reached in play
-    (ragged last warp included)."""
-    n = 40                                           # 2 full warps of 16 envs + a ragged one of 8
-    e = _emu(level, n, np.arange(n, dtype=np.uint64) * 5 + 123)
-    obs = e.reset().copy()
-    rng = np.random.RandomState(9)
-    for t in range(150):
-        for e0 in (0, 16, 32):
-            tile = e.pair_obs(e0)
-            k = min(16, n - e0)
-            assert np.array_equal(tile[:k], obs[e0:e0 + k]), (level, t, e0)
-        obs = e.step(rng.choice(7, size=n, p=[0.15, 0.15, 0.4, 0.1, 0.08, 0.1, 0.02]).astype(np.int8))[0].copy()
-
-
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize('level,n,T', [('GoToLocal', 40, 40), ('PickupLoc', 35, 40), ('GoToObjS4', 16, 40), ('PutNextLocal', 24, 32),
                                         ('GoToObjMazeS4R2', 21, 40), ('BossLevel', 18, 16), ('Unlock', 20, 24)])
-def test_rollout2_stepping_role_on_threads(level, n, T):
-    """k_rollout2's stepping role (babyai_b200/csrc/rollout2.cuh: the very function the kernel calls) executed with one OS
-    thread per lane and the warp shuffles / barriers as rendezvous: whole rollouts -- step on the even lane, broadcast,
-    two-lane level swap-in from the ring, split observation, record staging, tile stores, state write-back, counters --
-    must equal the per-step path (which is checked against the oracle), ragged last warps included."""
+def test_rollout_stepping_role_on_threads(level, n, T):
+    """k_rollout's stepping role (babyai_b200/csrc/rollout_lane.cuh: the very function the kernel calls) executed with one OS
+    thread per lane and the warp shuffles / votes / barriers as rendezvous: whole rollouts -- step, warp-cooperative level
+    swap-in from the ring, observation, tile staging, (bulk) tile stores, state write-back, counters -- must equal the
+    per-step path (which is checked against the oracle), ragged last warps included."""
     seeds = np.arange(n, dtype=np.uint64) * 11 + 321
     ref = _emu(level, n, seeds)
-    r2 = hostemu.Rollout2Pool(level_spec(level), n, seeds, depth=max(24, T + 8))
+    r2 = hostemu.RolloutPool(level_spec(level), n, seeds, depth=max(24, T + 8))
     obs0 = ref.reset().copy()
     rng = np.random.RandomState(17)
     steps = episodes = 0
@@ -229,12 +212,12 @@ def test_rollout2_stepping_role_on_threads(level, n, T):
 
 
 @pytest.mark.timeout(300)
-def test_rollout2_stepping_role_freeze_mode():
-    """ManyEnvs flavour in k_rollout2: finished envs freeze and replay their terminal result (evaluate.py:72-78)."""
+def test_rollout_stepping_role_freeze_mode():
+    """ManyEnvs flavour in k_rollout: finished envs freeze and replay their terminal result (evaluate.py:72-78)."""
     level, n, T = 'GoToLocal', 20, 40
     seeds = np.arange(n, dtype=np.uint64) + 10 ** 9
     ref = _emu(level, n, seeds, mode=1)
-    r2 = hostemu.Rollout2Pool(level_spec(level), n, seeds, mode=1)
+    r2 = hostemu.RolloutPool(level_spec(level), n, seeds, mode=1)
     ref.reset()
     rng = np.random.RandomState(3)
     for rep in range(2):                                  # max_steps = 64: everything is frozen during the second rollout
@@ -249,14 +232,14 @@ def test_rollout2_stepping_role_freeze_mode():
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize('level,n,T,rounds,min_active', [('GoToLocal', 100, 16, 1 << 20, 0), ('PickupLoc', 70, 16, 2, 16), ('GoToObjS4', 64, 16, 1, 0),
                                                          ('GoToRedBallGrey', 90, 12, 3, 8)])
-def test_rollout2_fused_cta_on_threads(level, n, T, rounds, min_active):
-    """A whole fused CTA of k_rollout2 on threads: four stepping warps + the generator warp (rollout2_gen_warp driving
-    gen_small_round -- the round function of k_gen_small and of k_rollout's generator warp) behind one __syncthreads.  Nothing
+def test_rollout_fused_cta_on_threads(level, n, T, rounds, min_active):
+    """A whole fused CTA of k_rollout on threads: two stepping warps + the generator warp (rollout_gen_warp driving
+    gen_small_round -- the round function of k_gen_small too) behind one __syncthreads.  Nothing
     but the generator warps refills the rings over 14 launches, with small round budgets and the sparse-warp rule switched
     on in some cases (deficits carry over; the must-complete rule keeps every ring above what the next launch can consume)."""
     seeds = np.arange(n, dtype=np.uint64) * 5 + 2024
     ref = _emu(level, n, seeds)
-    r2 = hostemu.Rollout2Pool(level_spec(level), n, seeds, depth=2 * T + 8)       # the smallest ring fused launches accept
+    r2 = hostemu.RolloutPool(level_spec(level), n, seeds, depth=2 * T + 8)       # the smallest ring fused launches accept
     ref.reset()
     rng = np.random.RandomState(23)
     steps = episodes = 0

@@ -64,11 +64,17 @@ def test_device_parallel_env_and_preprocessor(level, n, fused_io):
 
 def test_own_arm_json_line():
     from test_bench_contract import BASE_KEYS, _line
-    d = _line(['--steps', '80', '--warmup', '40', '--envs', '4096', '--no-cpu-baseline', '--no-probe'])
+    d = _line(['--steps', '80', '--warmup', '40', '--envs', '4096', '--no-cpu-baseline', '--no-other-configs'])
     assert (BASE_KEYS - {'cpu_baseline'}) | {'roofline', 'clocks', 'per_step_api', 'counters', 'learner_path'} <= set(d)
     r = d['roofline']
     assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['achieved'] > 0 and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
     assert d['e2e']['h2d_bytes_per_step'] == 4096 and d['e2e']['d2h_bytes_per_step'] == 4096 * 153
+    # the roofline comes from the SAME timed region as `value`, which always runs whole rollouts (never fewer than 1000 steps)
+    assert d['steps'] >= 1000 and d['steps'] % 40 == 0 and d['steps_requested'] == 80
+    assert abs(d['value'] / d['n_gpus'] * 153 / 1e9 - r['achieved']) <= 1e-6 * r['achieved'] and r['kernel_frac'] > 0
+    assert abs(d['ms_per_step'] * d['steps'] * 1e-3 * d['value'] - d['steps'] * 4096) <= 1e-3 * d['steps'] * 4096
+    assert d['e2e']['steps'] >= 200 and d['per_step_api']['steps'] >= 200 and d['e2e']['per_rank']['min'] > 0
+    assert d['reference_parallel_env']['available'] is False and d['facade_e2e']['value'] > 0
     assert d['gpu_launches'] > 0 and d['counters']['errors'] == 0 and d['dtype'] == 'u8'
     assert 'error' not in d['learner_path']['tensor_copies'] and 'error' not in d['learner_path']['fused_io'], d['learner_path']
 
@@ -114,18 +120,15 @@ def test_rollout_equals_stepwise_new_levels(level):
     assert a.counters()['errors'] == 0
 
 
-@pytest.mark.skipif(__import__('os').environ.get('BB_TEST_ROLLOUT2') != '1',
-                    reason='k_rollout2 (two lanes per env) is experimental and has never run on a GPU: opt in with BB_TEST_ROLLOUT2=1')
 @pytest.mark.parametrize('level,n,T', [('GoToLocal', 4096, 24), ('GoToLocal', 1000, 40), ('PickupLoc', 200, 40), ('GoToObjS4', 256, 40),
                                         ('PutNextLocal', 333, 32), ('BossLevel', 512, 16), ('GoToObjMazeS4R2', 300, 40), ('Unlock', 200, 16)])
-def test_rollout2_equals_stepwise(monkeypatch, level, n, T):
-    """BB_ROLLOUT_LANES=2: bb_pool_rollout through k_rollout2 == T x bb_pool_step (and, transitively, the oracle)."""
+def test_rollout_equals_stepwise(level, n, T):
+    """bb_pool_rollout (persistent kernels: bulk tile stores, warp-cooperative swap-in, fused generator warp) == T x
+    bb_pool_step (and, transitively, the oracle), directions and counters included; ragged sizes included."""
     import torch
     from babyai_b200 import BabyAIVecEnv
     seeds = np.arange(n, dtype=np.uint64) + 77
-    monkeypatch.setenv('BB_ROLLOUT_LANES', '2')
     a = BabyAIVecEnv(level, n, seeds=seeds)
-    monkeypatch.delenv('BB_ROLLOUT_LANES')
     b = BabyAIVecEnv(level, n, seeds=seeds)
     acts = torch.randint(0, 7, (T, n), device='cuda', dtype=torch.int8)
     a.reset(); b.reset()
