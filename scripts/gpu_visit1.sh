@@ -14,7 +14,7 @@ echo "smoke exit $?" >> $OUT/smoke_$TAG.log
 echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
 ( timeout 600 python bench.py ) > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 # multi-room "before" captures: BossLevel, 32 768 envs (k_rollout on 22x22 staging + k_gen beside it)
-( timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_rollout|k_gen" -s 4 -c 3 \
+( timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_rollout|k_gen" -s 10 -c 3 \
     -o $OUT/prof_boss_$TAG -f python bench.py --brief --level BossLevel --envs 32768 --steps 200 --warmup 40 ) > $OUT/ncu_boss_$TAG.log 2>&1
 # single-room: source-level capture of the fused k_rollout (stall reasons per line)
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_rollout -s 3 -c 1 \
