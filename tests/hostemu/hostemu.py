@@ -105,7 +105,7 @@ class HostEmuPool:
 # ---- the rollout kernels' roles on OS threads (simt_rollout.cpp) -------------------------------------------------
 SRC2 = os.path.join(HERE, 'simt_rollout.cpp')
 OUT2 = os.path.join(HERE, 'libsimt_rollout.so')
-DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'simt.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_lane.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'gen_round.cuh')] + DEPS[1:]
+DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'simt.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_lane.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_cta.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'gen_round.cuh')] + DEPS[1:]
 _lib2 = None
 
 
@@ -125,6 +125,8 @@ def lib2():
         L.r2_min_ring_level.argtypes = [C.c_void_p]
         L.r2_max_tokens.argtypes = [C.c_void_p]
         L.r2_error_flag.argtypes = [C.c_void_p]
+        L.r2_rollout_cta.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.r2_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib2 = L
     return _lib2
 
@@ -143,17 +145,28 @@ class RolloutPool:
         except Exception:
             pass
 
-    def rollout(self, actions, fused=False, gen_rounds=1 << 20, gen_min_active=0):
-        """fused=True: the CTA's generator warp refills the rings during the launch (nothing else does)"""
+    def rollout(self, actions, fused=False, gen_rounds=1 << 20, gen_min_active=0, kernel='lane'):
+        """fused=True: the CTA's generator warp refills the rings during the launch (nothing else does);
+        kernel='cta': k_rollout_cta's role (rollout_cta.cuh) instead of k_rollout's (rollout_lane.cuh)"""
         a = np.ascontiguousarray(actions, dtype=np.int8)
         T, n = a.shape
         obs, rew = np.zeros((T, n, 7, 7, 3), np.uint8), np.zeros((T, n), np.float32)
         done, dirs, cnt = np.zeros((T, n), np.uint8), np.zeros((T, n), np.int8), np.zeros(4, np.int64)
-        if fused:
+        if kernel == 'cta':
+            self.L.r2_rollout_cta(self.h, _p(a), T, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
+        elif fused:
             self.L.r2_rollout_fused(self.h, _p(a), T, gen_rounds, gen_min_active, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
         else:
             self.L.r2_rollout(self.h, _p(a), T, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
         return obs, rew, done, dirs, cnt
+
+    def state(self, i, width, height):
+        grid, info = np.zeros((height, width), np.uint8), np.zeros(8, np.int32)
+        self.L.r2_state(self.h, i, _p(grid), _p(info))
+        return grid, info
+
+    def error_flag(self):
+        return self.L.r2_error_flag(self.h)
 
     def min_ring_level(self):
         return self.L.r2_min_ring_level(self.h)

@@ -86,6 +86,7 @@ template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exch
 #include "../../babyai_b200/csrc/simt.cuh"
 #include "../../babyai_b200/csrc/gen_round.cuh"
 #include "../../babyai_b200/csrc/rollout_lane.cuh"
+#include "../../babyai_b200/csrc/rollout_cta.cuh"
 #include "../../babyai_b200/csrc/level_params.h"
 
 using namespace bb;
@@ -244,6 +245,48 @@ void r2_rollout_fused(RPool *p, const int8_t *actions, int T, int gen_rounds, in
     }
     for (int k = 0; k < 4; k++) counters4[k] = 0;
     for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
+}
+
+// one bb_pool_rollout worth of k_rollout_cta: every CTA of the grid, 128 threads each (4 warps: shuffles within a warp,
+// __syncthreads / __syncthreads_or across the CTA)
+void r2_rollout_cta(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *reward, uint8_t *done, int8_t *dirs, int64_t *counters4)
+{
+    const LevelParams &lp = p->lp;
+    const int words = rc_cta_words(lp);
+    const int nctas = (p->n + RC_ENVS - 1) / RC_ENVS;
+    for (int cta = 0; cta < nctas; cta++) {
+        std::vector<WarpCtx> ctx(RC_THREADS / 32);
+        std::barrier<> cta_bar(RC_THREADS);
+        int cta_or[2] = { 0, 0 };
+        std::vector<uint32_t> smem((size_t)words + 8, 0xDEADBEEFu);
+        uint32_t *base = smem.data();
+        while (((uintptr_t)base) & 15) base++;
+        std::vector<std::thread> th;
+        for (int tid = 0; tid < RC_THREADS; tid++)
+            th.emplace_back([&, tid]() {
+                tl_warp = &ctx[tid >> 5]; tl_lane = tid & 31; tl_cta = &cta_bar; tl_cta_or = cta_or; tl_cta_phase = 0;
+                if (lp.kind == KIND_UNLOCK) rollout_cta_role<HostPoolPtrs, true>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, base, tid, cta);
+                else rollout_cta_role<HostPoolPtrs, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, base, tid, cta);
+            });
+        for (auto &t : th) t.join();
+    }
+    refill(p);                                                // the generation pass between launches
+    for (int k = 0; k < 4; k++) counters4[k] = 0;
+    for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
+}
+
+// the live state of env e (both grid orientations must agree after a launch)
+void r2_state(RPool *p, int e, uint8_t *grid, int32_t *info)
+{
+    const LevelParams &lp = p->lp;
+    const uint8_t *g = p->grid.data() + (size_t)e * lp.cells_pad;
+    for (int y = 0; y < lp.H; y++)
+        for (int x = 0; x < lp.W; x++) {
+            grid[y * lp.W + x] = g[y * lp.rs_g + x];
+            if (g[lp.gt_off + x * lp.rs_t + y] != g[y * lp.rs_g + x]) { fprintf(stderr, "simt_rollout: G/GT mismatch env %d (%d,%d)\n", e, x, y); abort(); }
+        }
+    const EnvHot &h = p->hot[e];
+    info[0] = h.x; info[1] = h.y; info[2] = h.dirflags & 3; info[3] = h.carry; info[4] = h.step_count; info[5] = h.max_steps;
 }
 
 int r2_min_ring_level(RPool *p) { int m = 1 << 30; for (int e = 0; e < p->n; e++) { const int have = (int)(p->tail[e] - p->head[e]); if (have < m) m = have; } return m; }

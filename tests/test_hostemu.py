@@ -211,6 +211,43 @@ def test_rollout_stepping_role_on_threads(level, n, T):
     del obs0
 
 
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('level,n,T,mode', [('BossLevel', 40, 16, 0), ('GoTo', 70, 24, 0), ('GoToObjMazeS4R2', 45, 40, 0), ('Unlock', 33, 24, 0),
+                                             ('GoToLocal', 50, 40, 0), ('PutNextLocal', 20, 32, 0), ('MiniBossLevel', 64, 40, 0), ('GoToObjMazeS4R2', 37, 40, 1)])
+def test_rollout_cta_role_on_threads(level, n, T, mode):
+    """k_rollout_cta's role (babyai_b200/csrc/rollout_cta.cuh: the very function the kernel calls) with one OS thread per
+    lane, 128 threads per CTA: lane-per-env step phase, CTA-wide swap-in, 4-lanes-per-env observation from the row-major
+    grid alone (byte gathers, xor-shuffle exchange of the see-through masks, 21-byte record staging), tile store, and the
+    write-back that regenerates the transposed grid -- must equal the per-step path, ragged last CTA included; afterwards
+    the hidden state (both grid orientations, pose, carried object, step counter) equals it too."""
+    seeds = np.arange(n, dtype=np.uint64) * 13 + 99
+    ref = _emu(level, n, seeds, mode=mode)
+    r2 = hostemu.RolloutPool(level_spec(level), n, seeds, depth=max(24, T + 8), mode=mode)
+    ref.reset()
+    rng = np.random.RandomState(29)
+    steps = episodes = 0
+    for rep in range(4):
+        acts = rng.choice(7, size=(T, n), p=[0.13, 0.13, 0.4, 0.12, 0.08, 0.12, 0.02]).astype(np.int8)
+        obs, rew, done, dirs, cnt = r2.rollout(acts, kernel='cta')
+        for t in range(T):
+            o, r, d = ref.step(acts[t])
+            assert np.array_equal(obs[t], o), (level, rep, t, np.nonzero((obs[t] != o).reshape(n, -1).any(1))[0])
+            assert np.array_equal(rew[t].view(np.uint32), r.view(np.uint32)) and np.array_equal(done[t], d), (level, rep, t)
+            assert np.array_equal(dirs[t], ref.direction), (level, rep, t)
+            if mode == 0:
+                episodes += int(d.sum())
+        if mode == 0:
+            steps += T * n
+            assert cnt[0] == steps and cnt[1] == episodes and cnt[3] == 0, (cnt, steps, episodes)
+        assert r2.error_flag() == 0
+        for i in range(0, n, 3):
+            g, st = ref.state(i)
+            g2, info = r2.state(i, ref.width, ref.height)
+            assert np.array_equal(g, g2), (level, rep, i)
+            assert (st['agent_x'], st['agent_y'], st['agent_dir'], st['step_count']) == (info[0], info[1], info[2], info[4]), (level, rep, i)
+        assert all(np.array_equal(r2.tokens(i)[:8], ref.tokens(i)[:8]) for i in range(n))
+
+
 @pytest.mark.timeout(300)
 def test_rollout_stepping_role_freeze_mode():
     """ManyEnvs flavour in k_rollout: finished envs freeze and replay their terminal result (evaluate.py:72-78)."""
