@@ -7,7 +7,9 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CONFIG_LEVELS = ['GoToRedBall', 'GoToLocal', 'PickupLoc', 'GoTo', 'BossLevel']
-GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))      # all 45 served levels (CPU replays)
+GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('succ_'))      # all 47 served levels (CPU replays)
+# success-heavy reference traces (97 % bot actions, >= 50 successful episodes each; make_golden.py --success): 'succ_<Level>'
+SUCCESS_GOLDENS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and f.startswith('succ_'))
 # the traces the CUDA pool replays in the GPU suite (the other 26 files were added at the very end of round 1, after the
 # last GPU visit: they are replayed by the oracle and by the host build of the kernel logic; GPU replay from round 2 on)
 GOLDEN_LEVELS_GPU = ['BossLevel', 'BossLevelNoUnlock', 'GoTo', 'GoToLocal', 'GoToObjMazeS4R2', 'GoToOpen', 'GoToRedBall',
@@ -26,6 +28,8 @@ def replay_golden(level, make_pool, get_mission):
     """make_pool(level, n, seeds) -> object with reset() -> obs[n,7,7,3], step(a) -> (obs, reward, done),
     .direction; get_mission(pool, i) -> str.  All K traces are run as ONE pool of K envs."""
     g = load_golden(level)
+    if level.startswith('succ_'):
+        level = level[5:]
     K, T = g['actions'].shape
     pool = make_pool(level, K, g['seeds'])
     obs = np.asarray(pool.reset())

@@ -10,7 +10,7 @@ import pytest
 import hostemu
 import oracle as orc
 from babyai_b200.levels import LEVELS, detokenize, level_spec
-from common import GOLDEN_LEVELS, compare_pools, replay_golden
+from common import GOLDEN_LEVELS, SUCCESS_GOLDENS, compare_pools, replay_golden
 
 
 def _emu(level, n, seeds, mode=0):
@@ -20,6 +20,11 @@ def _emu(level, n, seeds, mode=0):
 @pytest.mark.parametrize('level', GOLDEN_LEVELS)
 def test_emu_replays_golden(level):
     replay_golden(level, _emu, lambda p, i: detokenize(p.tokens(i)))
+
+
+@pytest.mark.parametrize('name', SUCCESS_GOLDENS)
+def test_hostemu_replays_success_golden(name):
+    replay_golden(name, _emu, lambda p, i: detokenize(p.tokens(i)))
 
 
 @pytest.mark.parametrize('level', sorted(LEVELS))
