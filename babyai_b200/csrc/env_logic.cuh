@@ -1581,19 +1581,39 @@ BB_HD void transpose8(uint32_t &lo, uint32_t &hi)
 // (run + its two neighbours) is what the next row starts from.  The flood towards
 // higher bits is one addition: carries ripple through the run of ones in `s` and stop
 // on (and set) the first blocked cell; the other direction is the same on reversed bits.
+BB_HD uint32_t both7(uint32_t x)            // the low 7 bits of x, and the same 7 bits reversed at bits 8..14
+{
+#if defined(__CUDA_ARCH__)
+    return (x & 0x7Fu) | (__brev(x & 0x7Fu) >> 17);
+#else
+    return (x & 0x7Fu) | (rev7(x) << 8);
+#endif
+}
+BB_HD uint32_t swap7(uint32_t u)            // exchanges the two 7-bit fields of a both7() word, reversing each
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(u) >> 17;                 // bit i -> 14 - i
+#else
+    return rev7(u >> 8) | (rev7(u) << 8);
+#endif
+}
+// Both flood directions in ONE addition: a row mask is carried together with its bit-reversed copy (both7), so the carry
+// chain that floods towards higher bits in the low field floods towards lower bits of the row in the high field; bit 7
+// between the fields absorbs the low field's carry-out (the exhaustive test covers all 2^14 (visible, see-through) pairs
+// of every row).
 BB_HD void vis_rows(const uint32_t see[7], uint32_t vis[7])
 {
-    uint32_t v = 1u << 3;                       // agent cell (3, 6)
+    uint32_t s2[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) s2[j] = both7(see[j]);
+    uint32_t v2 = both7(1u << 3);               // agent cell (3, 6)
 #pragma unroll
     for (int j = 6; j >= 0; j--) {
-        const uint32_t s = see[j] & 0x7Fu;
-        const uint32_t a = v & s;               // visible cells that let light through
-        const uint32_t up = ((s + a) ^ s) | a;
-        const uint32_t rs = rev7(s), ra = rev7(a);
-        const uint32_t dn = rev7(((rs + ra) ^ rs) | ra);
-        const uint32_t d = (up | dn) & 0x7Fu;
-        vis[j] = v | d;
-        v = d;                                  // what the row above starts from
+        const uint32_t a2 = v2 & s2[j];         // visible cells that let light through (both orientations)
+        const uint32_t u = (((s2[j] + a2) ^ s2[j]) | a2) & 0x7F7Fu;     // low field: flood up; high field: flood down, reversed
+        const uint32_t d2 = (u | swap7(u)) & 0x7F7Fu;                   // the union, again in both orientations
+        vis[j] = (v2 | d2) & 0x7Fu;
+        v2 = d2;                                // what the row above starts from
     }
 }
 

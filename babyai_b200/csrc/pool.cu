@@ -28,6 +28,7 @@
 #include "gen_round.cuh"
 #include "rollout_lane.cuh"
 #include "rollout_cta.cuh"
+#include "rgb_tiles.h"
 
 using namespace bb;
 
@@ -53,7 +54,6 @@ struct PoolPtrs {
 
 constexpr int GEN_THREADS = 64;                    // 2 warps per block; one warp generates one level at a time
 constexpr int GEN_BLOCKS_PER_SM = 8;
-constexpr int GEN_CHUNK = 8;                       // environments per work ticket
 
 __device__ __forceinline__ LevelOut ring_slot(const LevelParams &lp, const PoolPtrs &P, int env, int slot)
 {
@@ -428,8 +428,9 @@ k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__
 // 3.0 active lanes per instruction).  Instead every lane of the warp runs the same env with identical
 // control flow: no divergence, the Philox blocks are computed 32 at a time across the lanes (Rng::u32),
 // the lanes split the grid rendering, and lane 0 commits the scalar records.
-// Work distribution: tickets of GEN_CHUNK consecutive envs from a global counter (the slowest
-// generations are a geometric tail of rejected attempts, so static assignment would wait for them).
+// Work distribution: k_gen_scan lists the envs whose ring is not full, longest chains first; a warp takes ONE env per
+// ticket from a global counter (the slowest generations are a geometric tail of rejected attempts, so static
+// assignment would wait for them).
 // IMPUNLOCK: the instantiation that serves KIND_IMPUNLOCK only (Level_GoToImpUnlock); every other level family runs
 // k_gen<false>, whose code is the kernel profiled in round 1.
 template <bool IMPUNLOCK>
@@ -439,38 +440,92 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
     __shared__ typename GenMemFor<IMPUNLOCK>::type gen_mem[GEN_THREADS / 32];     // GenMemX (untracked objects) for k_gen<true>
     GenMem *mem = &gen_mem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const uint32_t nchunks = (uint32_t)((n + GEN_CHUNK - 1) / GEN_CHUNK);
+    // work items: the envs k_gen_scan listed (ring not full), longest chains first -- the levels of one env are serial (one
+    // random stream), so the pass lasts as long as its longest chain: ONE env per ticket.  (Round 1 handed out tickets of 8
+    // consecutive envs: ncu r02a, BossLevel 32 768 envs: 650 us per pass at 2.5 of 16 warps per SM active -- ~1 900 levels of
+    // ~40 us each, serialised behind whichever warp drew the tickets with the most work.)
+    const uint32_t c3 = P.gen_count[3], c2 = P.gen_count[2], c1 = P.gen_count[1], c0 = P.gen_count[0];
+    const uint32_t count = c0 + c1 + c2 + c3;
     const uint32_t D = (uint32_t)P.depth;
     for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(P.gen_ticket, 1u);
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        if (c >= nchunks) break;
-        const int e_l = (int)c * GEN_CHUNK + (lane & (GEN_CHUNK - 1));
-        uint32_t tl = 0; int missing = 0;
-        if (lane < GEN_CHUNK && e_l < n) {
-            const uint32_t hd = P.head_snap[e_l];             // consumption as of the step this launch was forked from
-            tl = P.tail[e_l];
-            missing = target - (int)(tl - hd);
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(P.gen_ticket, 1u);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        if (idx >= count) break;
+        int b = 3;
+        if (idx >= c3) { idx -= c3; b = 2; if (idx >= c2) { idx -= c2; b = 1; if (idx >= c1) { idx -= c1; b = 0; } } }
+        const int env = P.gen_list[(size_t)b * n + idx];
+        const uint32_t t0 = P.tail[env];
+        const int m = target - (int)(t0 - P.head_snap[env]);      // consumption as of the step this pass was forked from
+        RngRec r = P.rng[env];
+        uint8_t lr = P.locked_room[env];
+        int att = 0;
+        for (int i = 0; i < m; i++) {
+            const LevelOut o = ring_slot(lp, P, env, (int)((t0 + (uint32_t)i) % D));
+            att += generate_level_t<IMPUNLOCK>(lp, o, &r, &lr, mem);
+            __syncwarp();
+            if (lane == 0) P.tail[env] = t0 + (uint32_t)i + 1u;
         }
-        uint32_t need = __ballot_sync(0xFFFFFFFFu, missing > 0);
-        while (need) {                                         // warp-uniform loop
-            const int b = __ffs((int)need) - 1;
-            need &= need - 1;
-            const int env = (int)c * GEN_CHUNK + b;
-            const int m = __shfl_sync(0xFFFFFFFFu, missing, b);
-            const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, tl, b);
-            RngRec r = P.rng[env];
-            uint8_t lr = P.locked_room[env];
-            int att = 0;
-            for (int i = 0; i < m; i++) {
-                const LevelOut o = ring_slot(lp, P, env, (int)((t0 + (uint32_t)i) % D));
-                att += generate_level_t<IMPUNLOCK>(lp, o, &r, &lr, mem);
-                __syncwarp();
-                if (lane == 0) P.tail[env] = t0 + (uint32_t)i + 1u;
+        if (lane == 0) { P.rng[env] = r; P.locked_room[env] = lr; P.attempts[env] += (uint32_t)att; }
+        __syncwarp();
+    }
+}
+
+// k_render_rgb -- RGBImgPartialObsWrapper.observation for a batch: uint8[n][7][7][3] observations -> uint8[n][56][56][3]
+// images (tile size 8).  The image is a pure function of the observation: every view cell selects one of 513 pre-rendered
+// 192-byte tiles (rgb_tiles.h).  This is the one output of the path that is genuinely HBM bound: 9 408 bytes written per
+// 147 bytes read (616 MB per step of 65 536 envs).  One warp per environment at a time: the 49 tile ids go to shared
+// memory, then the warp streams the image out as 588 coalesced 16-byte stores; each store is two 8-byte pieces of tile
+// rows (a pixel row is 7 tiles x 24 bytes, so 8-byte pieces never straddle a tile) fetched from the L1-resident table.
+// Which tile piece a lane needs in iteration k does not depend on the environment: the (cell, offset inside the tile) pairs
+// are computed once per CTA into shared memory.
+constexpr int RGB_THREADS = 256, RGB_IMG_BYTES = 56 * 56 * 3, RGB_VEC = RGB_IMG_BYTES / 16, RGB_ITERS = (RGB_VEC + 31) / 32;   // 9408 B, 588, 19
+
+__global__ void __launch_bounds__(RGB_THREADS, 4)
+k_render_rgb(const uint8_t *__restrict__ obs, uint8_t *__restrict__ rgb, const uint8_t *__restrict__ lut, const int n)
+{
+    __shared__ uint16_t s_ids[RGB_THREADS / 32][64];
+    __shared__ uint32_t s_where[RGB_ITERS][32];  // two (cell index | offset in tile << 8) pairs per 16-byte vector, per lane
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = gridDim.x * (RGB_THREADS / 32);
+    // piece h (8 bytes) of the image: pixel row h / 21, 8-byte column h % 21 -> tile column vi = (h % 21) / 3, part (h % 21) % 3
+    for (int idx = threadIdx.x; idx < RGB_ITERS * 32; idx += RGB_THREADS) {
+        uint32_t w = 0;
+        for (int half = 0; half < 2; half++) {
+            const int h = 2 * ((idx & 31) + 32 * (idx >> 5)) + half;
+            const int row = h / 21, c8 = h - row * 21, vi = c8 / 3, part = c8 - vi * 3;
+            const int vj = (row >> 3) % 7, ty = row & 7;           // (% 7: the padding vectors past 588 stay inside the id table)
+            const uint32_t v = (uint32_t)(vi * 7 + vj) | ((uint32_t)(ty * 24 + part * 8) << 8);
+            w |= v << (16 * half);
+        }
+        s_where[idx >> 5][idx & 31] = w;
+    }
+    __syncthreads();
+    uint16_t *ids = s_ids[warp];
+    for (int env = blockIdx.x * (RGB_THREADS / 32) + warp; env < n; env += nwarps) {
+        const uint8_t *o = obs + (size_t)env * OBS_BYTES;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int cell = lane + 32 * r;
+            if (cell < 49) {
+                const uint32_t t = o[3 * cell], c = o[3 * cell + 1], st = o[3 * cell + 2];
+                const uint32_t b = t | (c << 3) | (st << 6);
+                ids[cell] = (uint16_t)(t == 0 ? bb_rgb::ID_UNSEEN : (cell == 27 ? bb_rgb::ID_AGENT0 + b : b));   // cell 27 = view (3, 6): the agent
             }
-            if (lane == 0) { P.rng[env] = r; P.locked_room[env] = lr; P.attempts[env] += (uint32_t)att; }
         }
+        __syncwarp();
+        uint4 *dst = reinterpret_cast<uint4 *>(rgb + (size_t)env * RGB_IMG_BYTES);
+#pragma unroll 4
+        for (int k = 0; k < RGB_ITERS; k++) {
+            const int i = lane + 32 * k;
+            if (i < RGB_VEC) {
+                const uint32_t w = s_where[k][lane];
+                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)ids[w & 0xFF] * bb_rgb::TILE_BYTES + ((w >> 8) & 0xFF)));
+                const uint2 b = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)ids[(w >> 16) & 0xFF] * bb_rgb::TILE_BYTES + (w >> 24)));
+                __stcs(dst + i, make_uint4(a.x, a.y, b.x, b.y));           // streaming store: the image is not read again here
+            }
+        }
+        __syncwarp();                              // ids are rewritten for the next env
     }
 }
 
@@ -505,7 +560,7 @@ constexpr int MAX_GEN_EVENTS = 40;
 struct bb_pool {
     LevelParams lp;
     PoolPtrs P;
-    int n, device, mode, num_warps, gen_blocks;
+    int n, device, mode, num_warps, gen_blocks, sm_count;
     // level supply schedule: ring depth D; k_gen is enqueued on gen_stream after every G-th step and
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
@@ -524,6 +579,7 @@ struct bb_pool {
     std::vector<void *> allocs;
     // host-buffer API staging
     int8_t *h_act; uint8_t *h_obs; float *h_rew; uint8_t *h_done; int8_t *h_dir;      // pinned
+    uint8_t *d_rgb_lut;            // the 513 RGB tiles (rgb_tiles.h), rendered on first use
     int *h_err;                    // mapped: PoolPtrs::err_flag (a kernel found a level ring dry)
     int fused_T;                   // longest T a fused rollout launch has guaranteed levels for (see bb_pool_rollout)
     int zerocopy, zc_level; const void *chk_rew, *chk_done, *chk_dir; bool chk_pinned; int8_t *zc_act; float *zc_rew; uint8_t *zc_done; int8_t *zc_dir; uint8_t *zc_obs;   // BB_HOST_ZEROCOPY
@@ -561,10 +617,10 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
 static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false, int min_keep = 0)
 {
     cudaMemsetAsync(p->P.gen_count, 0, 8 * sizeof(uint32_t), st);      // list counters + work ticket
+    k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
+    p->launches++;
     if (p->lp.small && !p->gen_generic) {
-        k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
         k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active, min_keep);
-        p->launches++;
     } else if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK) k_gen<true><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
     else k_gen<false><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
 }
@@ -678,7 +734,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     {
         cudaDeviceProp prop;
         CUP(cudaGetDeviceProperties(&prop, device));
-        int want = ((n_envs + GEN_CHUNK - 1) / GEN_CHUNK + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);
+        p->sm_count = prop.multiProcessorCount;
+        int want = (n_envs + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);      // one warp per env at most
         int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
         int per_sm = 4;
@@ -915,7 +972,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     // max_steps = room_size^2 steps, so fused when 3 max_steps >= 2 T (measured, profiles/r01y_ab_fused.log: S8 / S6
     // rooms +32 % / +13 % fused; S5 / S4 rooms -7 % / -60 %: there the GPU-wide refill passes win).  BB_GEN_FUSED=0/1/2:
     // never / by this rule (default) / whenever possible.
-    const bool fused = p->gen_fused != 0 && (p->gen_fused == 2 || 3 * p->lp.nav_time_maze >= 2 * T) &&
+    const bool fused = !p->rollout_cta && p->gen_fused != 0 && (p->gen_fused == 2 || 3 * p->lp.nav_time_maze >= 2 * T) &&
                        p->lp.small && !p->gen_generic && !p->gen_concurrent && p->mode == BB_MODE_AUTORESET &&
                        p->D >= 2 * T + 8 && !getenv("BB_DEBUG_NO_REFILL");
     // a fused launch leaves >= T levels in every ring (must-complete rule in the kernel: >= 2T before they are consumed), which
@@ -1139,6 +1196,33 @@ int bb_pool_reset_host(bb_pool *p, uint8_t *obs_host, int8_t *dir_host)
     CU(cudaStreamSynchronize(p->stream));
     memcpy(obs_host, p->h_obs, n * OBS_BYTES);
     if (dir_host) memcpy(dir_host, p->h_dir, n);
+    return 0;
+}
+
+int bb_rgb_tiles(uint8_t *tiles_host)
+{
+    if (!tiles_host) return fail("bad arguments");
+    bb_rgb::render_all_tiles(tiles_host);
+    return 0;
+}
+
+int bb_pool_render_rgb(bb_pool *p, const uint8_t *obs_dev, uint8_t *rgb_dev, int32_t n_obs, void *stream)
+{
+    if (!p || !obs_dev || !rgb_dev || n_obs < 0) return fail("bad arguments");
+    if ((((uintptr_t)rgb_dev) & 15) != 0) return fail("rgb_dev must be 16-byte aligned");
+    CU(cudaSetDevice(p->device));
+    if (!p->d_rgb_lut) {                                   // rasterise the tile table once (host), keep it on the device
+        std::vector<uint8_t> lut((size_t)bb_rgb::N_TILES * bb_rgb::TILE_BYTES);
+        bb_rgb::render_all_tiles(lut.data());
+        if (dalloc(p, &p->d_rgb_lut, lut.size())) return 1;
+        CU(cudaMemcpy(p->d_rgb_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice));
+    }
+    if (n_obs == 0) return 0;
+    int blocks = (n_obs + RGB_THREADS / 32 - 1) / (RGB_THREADS / 32);
+    if (blocks > p->sm_count * 8) blocks = p->sm_count * 8;          // grid-stride over the envs: a multiple of the SM count
+    k_render_rgb<<<blocks, RGB_THREADS, 0, (cudaStream_t)stream>>>(obs_dev, rgb_dev, p->d_rgb_lut, n_obs);
+    p->launches++;
+    CU(cudaGetLastError());
     return 0;
 }
 

@@ -62,25 +62,37 @@ struct SmemGMem {
     BB_HD void set_flags(int v) { i[42] = (uint8_t)v; }
 };
 
-// view column vi of the agent at (ax, ay, dir), gathered cell by cell from the row-major grid `g`:
-// view cell (vi, vj) is world cell  a + f (6 - vj) + r (vi - 3),  f = DIR_TO_VEC[dir], r = (-f.y, f.x); outside the grid: wall.
-// lo = depths vj 0..3, hi = vj 4..6 (+ a zero byte) -- what col_load() yields from the two stored orientations.
-BB_HD void rc_col_gather(const LevelParams &lp, const uint8_t *g, int ax, int ay, int dir, int vi, uint32_t &lo, uint32_t &hi)
+// The agent's 7 x 7 view on the row-major grid: view cell (vi, vj) is world cell  a + f (6 - vj) + r (vi - 3),
+// f = DIR_TO_VEC[dir], r = (-f.y, f.x); outside the grid: wall.  Per pose: the byte offset of view cell (0, 0), the offset
+// steps per column / per depth, the depths that lie inside the grid (the same for every column) and the lateral range.
+struct RcView { int a00, di, dj, lat0, lstep, nlat; uint32_t dm; };
+BB_HD RcView rc_view(const LevelParams &lp, int ax, int ay, int dir)
 {
-    const int fx = dir_dx(dir), fy = dir_dy(dir);
-    const int rx = -fy, ry = fx;
-    const int x0 = ax + 6 * fx + (vi - 3) * rx, y0 = ay + 6 * fy + (vi - 3) * ry;     // the cell at depth vj = 0
-    const int dj = -(fy * lp.rs_g + fx);
-    const int a0 = y0 * lp.rs_g + x0;
+    const int fx = dir_dx(dir), fy = dir_dy(dir), rx = -fy, ry = fx;
+    RcView v;
+    v.a00 = (ay + 6 * fy - 3 * ry) * lp.rs_g + ax + 6 * fx - 3 * rx;
+    v.di = ry * lp.rs_g + rx;
+    v.dj = -(fy * lp.rs_g + fx);
+    // cells from the agent to the edge of the grid it faces: depths vj >= 6 - dist are inside
+    const int dist = dir == 0 ? lp.W - 1 - ax : dir == 1 ? lp.H - 1 - ay : dir == 2 ? ax : ay;
+    v.dm = dist >= 6 ? 0x7Fu : (0x7Fu << (6 - dist)) & 0x7Fu;
+    const bool horiz = fy == 0;                // facing left / right: columns are spread along y
+    v.lat0 = (horiz ? ay - 3 * ry : ax - 3 * rx);
+    v.lstep = horiz ? ry : rx;
+    v.nlat = horiz ? lp.H : lp.W;
+    return v;
+}
+// view column vi: lo = depths vj 0..3, hi = vj 4..6 (+ a zero byte) -- what col_load() yields from the two stored orientations
+BB_HD void rc_col_gather(const uint8_t *g, const RcView &v, int vi, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t cm = (unsigned)(v.lat0 + vi * v.lstep) < (unsigned)v.nlat ? v.dm : 0u;     // depths of this column inside the grid
+    const int a0 = v.a00 + vi * v.di;
     uint32_t c[7];
 #pragma unroll
-    for (int vj = 0; vj < 7; vj++) {
-        const int x = x0 - vj * fx, y = y0 - vj * fy;
-        const bool in = (unsigned)x < (unsigned)lp.W && (unsigned)y < (unsigned)lp.H;
-        c[vj] = in ? (uint32_t)g[a0 + vj * dj] : (uint32_t)CELL_WALL;
-    }
-    lo = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-    hi = c[4] | (c[5] << 8) | (c[6] << 16);
+    for (int vj = 0; vj < 7; vj++) c[vj] = ((cm >> vj) & 1u) ? (uint32_t)g[a0 + vj * v.dj] : 0u;
+    const uint32_t WALLW = 0x2A2A2A2Au;
+    lo = (c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24)) | (WALLW & ~expand4(cm));
+    hi = (c[4] | (c[5] << 8) | (c[6] << 16)) | (WALLW & ~expand4(cm >> 4) & 0x00FFFFFFu);
 }
 
 // MemT: SmemGMem (device and host build alike)
@@ -208,9 +220,10 @@ BB_DEV void rollout_cta_role(const LevelParams &lp, const PP &P, const int8_t *a
         const int ax = (int)(pose & 0xFF), ay = (int)((pose >> 8) & 0xFF), dir = (int)((pose >> 16) & 3);
         uint32_t loA = 0, hiA = 0, loB = 0, hiB = 0, cmA = 0, cmB = 0;
         if (valid_b) {
-            rc_col_gather(lp, g_b, ax, ay, dir, 2 * q, loA, hiA);
+            const RcView view = rc_view(lp, ax, ay, dir);
+            rc_col_gather(g_b, view, 2 * q, loA, hiA);
             cmA = col_see(loA, hiA);
-            if (q < 3) { rc_col_gather(lp, g_b, ax, ay, dir, 2 * q + 1, loB, hiB); cmB = col_see(loB, hiB); }
+            if (q < 3) { rc_col_gather(g_b, view, 2 * q + 1, loB, hiB); cmB = col_see(loB, hiB); }
         }
         // the 7 column masks (see-through bits, bit vj) of the env to all of its 4 lanes: byte vi of (blo : bhi)
         const uint32_t v16 = cmA | (cmB << 8);

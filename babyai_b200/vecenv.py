@@ -145,6 +145,20 @@ class BabyAIVecEnv(object):
             raise ValueError('rollout needs obs, reward and done buffers')
         self._check_step_outputs(obs, reward, done, direction, (actions.shape[0],))
 
+    def render_rgb(self, obs=None, out=None):
+        """RGBImgPartialObsWrapper.observation for a batch (bb_pool_render_rgb): uint8 observations [..., 7, 7, 3] (default:
+        the pool's current ones) -> uint8 images [..., 56, 56, 3] on the device; `obs` may be a whole [T, N, 7, 7, 3] rollout."""
+        obs = self.obs if obs is None else obs
+        if not (torch.is_tensor(obs) and obs.is_cuda and obs.device == self.device and obs.dtype == torch.uint8
+                and obs.is_contiguous() and obs.dim() >= 3 and tuple(obs.shape[-3:]) == (7, 7, 3)):
+            raise ValueError('obs must be a contiguous CUDA uint8 tensor [..., 7, 7, 3] on %s' % self.device)
+        lead = tuple(obs.shape[:-3])
+        if out is None:
+            out = torch.empty(lead + (56, 56, 3), dtype=torch.uint8, device=self.device)
+        _check(out, 'out', self.device, torch.uint8, lead + (56, 56, 3))
+        _lib.check(self.L.bb_pool_render_rgb(self.h, _ptr(obs), _ptr(out), obs.numel() // 147, self._stream()))
+        return out
+
     def step_timed(self, actions):
         """bb_pool_step with CUDA events around each kernel -> (ms k_step, ms k_gen)."""
         a, b = C.c_float(), C.c_float()
@@ -217,13 +231,13 @@ class _Space(object):
     pass
 
 
-def _spaces():
+def _spaces(pixel=False):
     """observation_space / action_space with the attributes the reference reads
     (utils/format.py:124-126: .spaces['image'].shape/.high; train_rl.py:96: action_space.n)."""
     img = _Space()
-    img.shape = (7, 7, 3)
-    img.low = np.zeros((7, 7, 3), np.uint8)
-    img.high = np.full((7, 7, 3), 255, np.uint8)
+    img.shape = (56, 56, 3) if pixel else (7, 7, 3)
+    img.low = np.zeros(img.shape, np.uint8)
+    img.high = np.full(img.shape, 255, np.uint8)
     img.dtype = np.dtype('uint8')
     obs = _Space()
     obs.spaces = {'image': img}
@@ -238,20 +252,31 @@ class EnvHandle(object):
     def __init__(self, pool_spec, index):
         self.pool_spec = pool_spec
         self.index = index
-        self.observation_space, self.action_space = _spaces()
+        self.observation_space, self.action_space = _spaces(getattr(pool_spec, 'pixel', False))
 
 
 class EnvList(list):
     """What scripts/train_rl.py:53-60 builds: N seeded envs of one level."""
 
-    def __init__(self, level, seeds, device=0):
-        self.level, self.seeds, self.device = level, list(seeds), device
+    def __init__(self, level, seeds, device=0, pixel=False):
+        self.level, self.seeds, self.device, self.pixel = level, list(seeds), device, bool(pixel)
         super().__init__(EnvHandle(self, i) for i in range(len(self.seeds)))
 
 
-def make_envs(level, num_envs, seed=1, device=0):
-    """`env.seed(100 * seed + i)` for env i (scripts/train_rl.py:59)."""
-    return EnvList(level, [100 * seed + i for i in range(num_envs)], device)
+def make_envs(level, num_envs, seed=1, device=0, pixel=False):
+    """`env.seed(100 * seed + i)` for env i (scripts/train_rl.py:59); pixel=True: every env wrapped in
+    RGBImgPartialObsWrapper (train_rl.py:54-58, `'pixel' in args.arch`)."""
+    return EnvList(level, [100 * seed + i for i in range(num_envs)], device, pixel)
+
+
+def RGBImgPartialObsWrapper(envs, tile_size=8):
+    """gym_minigrid.wrappers.RGBImgPartialObsWrapper for a whole env list: the pool's facades then return
+    obs['image'] as uint8[56, 56, 3] pictures of the 7x7 view (tile size 8), rendered on the device by bb_pool_render_rgb."""
+    if tile_size != 8:
+        raise ValueError('the pool renders tile_size 8 (the size the pixel architectures consume, babyai/model.py:96-98)')
+    if not isinstance(envs, EnvList):
+        raise TypeError('wrap the list make_envs() built')
+    return EnvList(envs.level, envs.seeds, envs.device, pixel=True)
 
 
 def _as_env_list(envs, need_seeds):
@@ -276,7 +301,8 @@ class _HostVec(object):
         host build of the kernel logic); the product always builds the CUDA pool."""
         envs = _as_env_list(envs, need_seeds=(mode == MODE_AUTORESET))
         self.envs = envs
-        self.observation_space, self.action_space = _spaces()
+        self.pixel = bool(getattr(envs, 'pixel', False))
+        self.observation_space, self.action_space = _spaces(self.pixel)
         self.pool = pool if pool is not None else BabyAIVecEnv(envs.level, len(envs), seeds=envs.seeds, device=envs.device, mode=mode)
         n = len(envs)
         # page-locked host buffers: bb_pool_step_host DMAs straight into them
@@ -294,6 +320,10 @@ class _HostVec(object):
             if len(idx):
                 for i, m in zip(idx, self.pool.missions(idx)):
                     self._missions[i] = m
+        if self.pixel:               # RGBImgPartialObsWrapper.observation: {'mission', 'image' uint8[56, 56, 3]} (no 'direction')
+            dev = self.pool.device
+            img = self.pool.render_rgb(torch.as_tensor(self._obs).to(dev)).cpu().numpy()
+            return [{'image': img[i], 'mission': self._missions[i]} for i in range(len(self.envs))]
         img = self._obs.copy()
         return [{'image': img[i], 'direction': int(self._dir[i]), 'mission': self._missions[i]}
                 for i in range(len(self.envs))]

@@ -361,6 +361,30 @@ def main():
     e2e_ranks = sorted(n * Ke / s for s in gather_f64(own_s))
     e2e_s = max(gather_f64(e2e_s))
 
+    # ---- RGB partial observations (RGBImgPartialObsWrapper, the 'pixel' architectures' input): the one HBM-bound output ----
+    # obs uint8[N,7,7,3] -> uint8[N,56,56,3]: 9 408 B written per 147 B read; 616 MB per call at N = 65 536 (> L2)
+    rgb = {}
+    try:
+        pics = torch.empty((n, 56, 56, 3), dtype=torch.uint8, device=dev)
+        for k in range(3):
+            env.render_rgb(obs[k % T], pics)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        r0.record()
+        for k in range(reps):
+            env.render_rgb(obs[k % T], pics)
+        r1.record()
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1) / reps
+        rbytes = n * (56 * 56 * 3 + 147)
+        rgb = {'kernel': 'k_render_rgb', 'ms': rms, 'algorithmic_bytes': rbytes, 'achieved': rbytes / (rms * 1e-3) / 1e9, 'unit': 'GB/s',
+               'frac': rbytes / (rms * 1e-3) / 1e9 / peak, 'bound': 'hbm', 'frames_per_s': n / (rms * 1e-3),
+               'api': 'bb_pool_render_rgb: obs uint8[N,7,7,3] -> uint8[N,56,56,3] (tile size 8), device buffers'}
+        del pics
+    except Exception as ex:
+        rgb = {'error': repr(ex)[:300]}
+
     # ---- the only collective on this path: all-gather of the counters --------------------
     cnt = gather_counters(env.counters(), device=dev)
 
@@ -466,6 +490,7 @@ def main():
                     'd2h_bytes_per_step': n * (147 + 4 + 1 + 1), 'steps': Ke,
                     'api': 'bb_pool_step_host (the C-ABI call, not the Python dict facade), page-locked host buffers',
                     'per_rank': {'min': e2e_ranks[0], 'median': e2e_ranks[len(e2e_ranks) // 2], 'max': e2e_ranks[-1]}},
+            'rgb_roofline': rgb,
             'facade_e2e': facade,
             'learner_path': learner,
             'other_configs': others,

@@ -134,6 +134,17 @@ int bb_pool_reset_host(bb_pool *pool, uint8_t *obs_host, int8_t *dir_host);
 int bb_pool_step_learner(bb_pool *pool, const int8_t *actions_host, uint8_t *obs_dev, float *reward_host,
                          uint8_t *done_host, int8_t *dir_dev, void *stream);
 
+/* Replaces: gym_minigrid.wrappers.RGBImgPartialObsWrapper.observation -> MiniGridEnv.get_obs_render (tile_size 8), the
+ * wrapper the reference puts around every env when 'pixel' is in the architecture name (scripts/train_rl.py:54-58,
+ * babyai/evaluate.py:91-92; consumed by the 8x8 / stride-8 first convolution, babyai/model.py:96-98).  The image is a pure
+ * function of the 7x7x3 observation: obs_dev uint8 [n_obs][147] (what bb_pool_step / bb_pool_reset / bb_pool_rollout wrote;
+ * n_obs may be T * n_envs) -> rgb_dev uint8 [n_obs][56][56][3], 16-byte aligned.  One HBM-bound kernel (9 408 B written
+ * per 147 B read); the 513 tiles it copies are rasterised once per pool exactly as the reference package draws them. */
+int bb_pool_render_rgb(bb_pool *pool, const uint8_t *obs_dev, uint8_t *rgb_dev, int32_t n_obs, void *stream);
+/* The tile table itself (host): uint8 [513][8][8][3]; id = cell byte (type | color << 3 | state << 6) for a visible cell,
+ * 256 for an unseen cell, 257 + cell byte for the agent's own cell.  For parity tests. */
+int bb_rgb_tiles(uint8_t *tiles_host);
+
 /* Replaces: obs['mission'] + InstructionsPreprocessor (utils/format.py:59-75).
  * Device pointer to int16 [n_envs][max_len] token ids of the current missions
  * (0 = pad, ids index bb_vocab_word); rewritten whenever an env is reset. */

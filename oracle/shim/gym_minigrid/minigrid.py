@@ -18,6 +18,8 @@ import gym
 from gym import spaces
 from gym.utils import seeding
 
+from .rendering import downsample, fill_coords, highlight_img, point_in_circle, point_in_rect, point_in_triangle, rotate_fn
+
 TILE_PIXELS = 32
 
 # A.1 constants ---------------------------------------------------------------
@@ -77,6 +79,33 @@ class WorldObj:
         return (OBJECT_TO_IDX[self.type], COLOR_TO_IDX[self.color], 0)
 
 
+def _decode_obj(type_idx, color_idx, state):
+    """WorldObj.decode: the object a (type, color, state) triple stands for; empty / unseen -> None"""
+    obj_type = IDX_TO_OBJECT[type_idx]
+    color = IDX_TO_COLOR[color_idx]
+    if obj_type in ('empty', 'unseen'):
+        return None
+    is_open = state == 0
+    is_locked = state == 2
+    if obj_type == 'wall':
+        return Wall(color)
+    if obj_type == 'floor':
+        return Floor(color)
+    if obj_type == 'ball':
+        return Ball(color)
+    if obj_type == 'key':
+        return Key(color)
+    if obj_type == 'box':
+        return Box(color)
+    if obj_type == 'door':
+        return Door(color, is_open, is_locked)
+    if obj_type == 'goal':
+        return Goal()
+    if obj_type == 'lava':
+        return Lava()
+    assert False, "unknown object type in decode '%s'" % obj_type
+
+
 class Goal(WorldObj):
     def __init__(self):
         super().__init__('goal', 'green')
@@ -107,6 +136,9 @@ class Wall(WorldObj):
 
     def see_behind(self):
         return False
+
+    def render(self, img):
+        fill_coords(img, point_in_rect(0, 1, 0, 1), COLORS[self.color])
 
 
 class Door(WorldObj):
@@ -142,6 +174,23 @@ class Door(WorldObj):
             state = 1
         return (OBJECT_TO_IDX[self.type], COLOR_TO_IDX[self.color], state)
 
+    def render(self, img):
+        c = COLORS[self.color]
+        if self.is_open:
+            fill_coords(img, point_in_rect(0.88, 1.00, 0.00, 1.00), c)
+            fill_coords(img, point_in_rect(0.92, 0.96, 0.04, 0.96), (0, 0, 0))
+            return
+        if self.is_locked:
+            fill_coords(img, point_in_rect(0.00, 1.00, 0.00, 1.00), c)
+            fill_coords(img, point_in_rect(0.06, 0.94, 0.06, 0.94), 0.45 * np.array(c))
+            fill_coords(img, point_in_rect(0.52, 0.75, 0.50, 0.56), c)          # key slot
+        else:
+            fill_coords(img, point_in_rect(0.00, 1.00, 0.00, 1.00), c)
+            fill_coords(img, point_in_rect(0.04, 0.96, 0.04, 0.96), (0, 0, 0))
+            fill_coords(img, point_in_rect(0.08, 0.92, 0.08, 0.92), c)
+            fill_coords(img, point_in_rect(0.12, 0.88, 0.12, 0.88), (0, 0, 0))
+            fill_coords(img, point_in_circle(cx=0.75, cy=0.50, r=0.08), c)      # handle
+
 
 class Key(WorldObj):
     def __init__(self, color='blue'):
@@ -150,6 +199,14 @@ class Key(WorldObj):
     def can_pickup(self):
         return True
 
+    def render(self, img):
+        c = COLORS[self.color]
+        fill_coords(img, point_in_rect(0.50, 0.63, 0.31, 0.88), c)             # shaft
+        fill_coords(img, point_in_rect(0.38, 0.50, 0.59, 0.66), c)             # teeth
+        fill_coords(img, point_in_rect(0.38, 0.50, 0.81, 0.88), c)
+        fill_coords(img, point_in_circle(cx=0.56, cy=0.28, r=0.190), c)        # ring
+        fill_coords(img, point_in_circle(cx=0.56, cy=0.28, r=0.064), (0, 0, 0))
+
 
 class Ball(WorldObj):
     def __init__(self, color='blue'):
@@ -157,6 +214,9 @@ class Ball(WorldObj):
 
     def can_pickup(self):
         return True
+
+    def render(self, img):
+        fill_coords(img, point_in_circle(0.5, 0.5, 0.31), COLORS[self.color])
 
 
 class Box(WorldObj):
@@ -171,6 +231,12 @@ class Box(WorldObj):
         # the box is replaced by its contents [C bot.py:941-949]
         env.grid.set(*pos, self.contains)
         return True
+
+    def render(self, img):
+        c = COLORS[self.color]
+        fill_coords(img, point_in_rect(0.12, 0.88, 0.12, 0.88), c)             # outline
+        fill_coords(img, point_in_rect(0.18, 0.82, 0.18, 0.82), (0, 0, 0))
+        fill_coords(img, point_in_rect(0.16, 0.84, 0.47, 0.53), c)             # horizontal slit
 
 
 # Grid -------------------------------------------------------------------------
@@ -254,6 +320,58 @@ class Grid:
                     v = Wall()
                 grid.set(i, j, v)
         return grid
+
+    tile_cache = {}
+
+    @classmethod
+    def render_tile(cls, obj, agent_dir=None, highlight=False, tile_size=TILE_PIXELS, subdivs=3):
+        """one cell at tile_size x tile_size pixels: grid lines, the object, the agent triangle, the highlight, all drawn
+        at 3x resolution and box-filtered down (float64 tile, truncated to uint8 when it is copied into the image)"""
+        key = (agent_dir, highlight, tile_size)
+        key = obj.encode() + key if obj else key
+        if key in cls.tile_cache:
+            return cls.tile_cache[key]
+        img = np.zeros(shape=(tile_size * subdivs, tile_size * subdivs, 3), dtype=np.uint8)
+        fill_coords(img, point_in_rect(0, 0.031, 0, 1), (100, 100, 100))
+        fill_coords(img, point_in_rect(0, 1, 0, 0.031), (100, 100, 100))
+        if obj is not None:
+            obj.render(img)
+        if agent_dir is not None:
+            tri_fn = point_in_triangle((0.12, 0.19), (0.87, 0.50), (0.12, 0.81))
+            tri_fn = rotate_fn(tri_fn, cx=0.5, cy=0.5, theta=0.5 * math.pi * agent_dir)
+            fill_coords(img, tri_fn, (255, 0, 0))
+        if highlight:
+            highlight_img(img)
+        img = downsample(img, subdivs)
+        cls.tile_cache[key] = img
+        return img
+
+    def render(self, tile_size, agent_pos=None, agent_dir=None, highlight_mask=None):
+        if highlight_mask is None:
+            highlight_mask = np.zeros(shape=(self.width, self.height), dtype=bool)
+        img = np.zeros(shape=(self.height * tile_size, self.width * tile_size, 3), dtype=np.uint8)
+        for j in range(0, self.height):
+            for i in range(0, self.width):
+                cell = self.get(i, j)
+                agent_here = np.array_equal(agent_pos, (i, j))
+                tile_img = Grid.render_tile(cell, agent_dir=agent_dir if agent_here else None,
+                                            highlight=highlight_mask[i, j], tile_size=tile_size)
+                img[j * tile_size:(j + 1) * tile_size, i * tile_size:(i + 1) * tile_size, :] = tile_img
+        return img
+
+    @staticmethod
+    def decode(array):
+        """the inverse of encode(): (grid, vis_mask) from a uint8[width, height, 3] observation"""
+        width, height, channels = array.shape
+        assert channels == 3
+        vis_mask = np.ones(shape=(width, height), dtype=bool)
+        grid = Grid(width, height)
+        for i in range(width):
+            for j in range(height):
+                type_idx, color_idx, state = array[i, j]
+                grid.set(i, j, _decode_obj(int(type_idx), int(color_idx), int(state)))
+                vis_mask[i, j] = (type_idx != OBJECT_TO_IDX['unseen'])
+        return grid, vis_mask
 
     def encode(self, vis_mask=None):
         """uint8[width, height, 3], x-major; unseen cells stay (0,0,0)."""
@@ -627,6 +745,12 @@ class MiniGridEnv(gym.Env):
             'mission': self.mission
         }
         return obs
+
+    def get_obs_render(self, obs, tile_size=TILE_PIXELS // 2):
+        """the agent's partial view as pixels: decode the 7x7x3 observation, draw the agent at the bottom centre facing up"""
+        grid, vis_mask = Grid.decode(obs)
+        return grid.render(tile_size, agent_pos=(self.agent_view_size // 2, self.agent_view_size - 1), agent_dir=3,
+                           highlight_mask=vis_mask)
 
     def render(self, mode='human', close=False, highlight=True, tile_size=TILE_PIXELS):
         raise NotImplementedError("rendering is out of scope for the oracle shim")

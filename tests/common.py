@@ -7,7 +7,7 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CONFIG_LEVELS = ['GoToRedBall', 'GoToLocal', 'PickupLoc', 'GoTo', 'BossLevel']
-GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith('succ_'))      # all 47 served levels (CPU replays)
+GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('succ_', 'rgb_')))      # all 47 served levels (CPU replays)
 # success-heavy reference traces (97 % bot actions, >= 50 successful episodes each; make_golden.py --success): 'succ_<Level>'
 SUCCESS_GOLDENS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and f.startswith('succ_'))
 # the traces the CUDA pool replays in the GPU suite (the other 26 files were added at the very end of round 1, after the
