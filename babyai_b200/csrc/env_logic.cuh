@@ -80,6 +80,7 @@ struct LevelParams {
     int32_t n_action_kinds, action_kinds[4];
     int32_t n_instr_kinds, instr_kinds[3];
     int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
+    int32_t obj_words;            // ceil(most object-table entries a level of this family uses / 4): words of the packed x / y arrays in use
     int32_t rs_g, rs_t, gt_off;   // grid bytes of one env: G = H rows x rs_g at 0, GT = W rows x rs_t at gt_off
     uint64_t locked_thr;          // rand_float(0,1) < p  <=>  u32 < ceil(p * 2^32)
     uint32_t wall_rows[MAXH];     // bit x of row y: (x, y) is a wall of the empty RoomGrid
@@ -426,19 +427,27 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o, int
     const int start = (g.ay / (S - 1)) * C + g.ax / (S - 1);
     const uint32_t all = NR >= 32 ? 0xFFFFFFFFu : ((1u << NR) - 1u);
     int itrs = 0;
+    // find_reach only changes when a door is added: the reference recomputes it on every trip of the loop (every random
+    // (i, j, k) draw, most of which hit a wall slot or an existing door); here it is recomputed after a door was added only
+    // (ncu r02a: the fixpoint below was 52 % of k_gen's instructions on BossLevel).  The draws are the same.
+    uint32_t reach = 0;
+    bool stale = true;
     for (;;) {
         if (itrs > 5000) return GEN_RECURSION;
         itrs++;
-        uint32_t reach = 1u << start;
-        for (;;) {                        // find_reach as a fixpoint over room bitmasks
-            uint32_t nr = reach;
-            for (int r = 0; r < NR; r++) {
-                if (!((reach >> r) & 1u)) continue;
-                for (int k = 0; k < 4; k++)
-                    if (g_has_slot(lp, r, k) && g_has_door(lp, g, r, k)) nr |= 1u << g_neighbor(lp, r, k);
+        if (stale) {
+            reach = 1u << start;
+            for (;;) {                    // find_reach as a fixpoint over room bitmasks
+                uint32_t nr = reach;
+                for (int r = 0; r < NR; r++) {
+                    if (!((reach >> r) & 1u)) continue;
+                    for (int k = 0; k < 4; k++)
+                        if (g_has_slot(lp, r, k) && g_has_door(lp, g, r, k)) nr |= 1u << g_neighbor(lp, r, k);
+                }
+                if (nr == reach) break;
+                reach = nr;
             }
-            if (nr == reach) break;
-            reach = nr;
+            stale = false;
         }
         if (reach == all) break;
         int i = g.rng.randint(0, C);
@@ -456,6 +465,7 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o, int
             color = color_by_name_rank(rank);
         }
         g_add_door(lp, g, o, room, k, color, false);
+        stale = true;
     }
     return GEN_OK;
 }
@@ -1305,6 +1315,14 @@ BB_HD void emit_small_level(const LevelParams &lp, const SmallLevel &L, const Le
 //   cell(x,y) set_cell(x,y,v) word_at(byte_offset)       grid (both orientations)
 //   ox(k) oy(k) otc(k) set_oxy(k,x,y)                   object table
 //   desc_mask(d) leaf_kind(l) leaf_pre(l) set_leaf_pre(l,v) root_kind() side_and() flags() set_flags(v)
+BB_HD uint32_t load_u32_any(const uint8_t *p)                   // p is 4-byte aligned
+{
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const uint32_t *>(p);
+#else
+    uint32_t v; __builtin_memcpy(&v, p, 4); return v;
+#endif
+}
 struct GlobalMem {
     const LevelParams &lp; uint8_t *grid; ObjTab *ot; InstrRec *ins;
     BB_HD GlobalMem(const LevelParams &lp_, uint8_t *g, ObjTab *o, InstrRec *i) : lp(lp_), grid(g), ot(o), ins(i) {}
@@ -1323,6 +1341,8 @@ struct GlobalMem {
     BB_HD int ox(int k) const { return ot->x[k]; }
     BB_HD int oy(int k) const { return ot->y[k]; }
     BB_HD int otc(int k) const { return ot->tc[k]; }
+    BB_HD uint32_t oxw(int i) const { return load_u32_any(ot->x + 4 * i); }      // x / y of objects 4i .. 4i+3, one byte each
+    BB_HD uint32_t oyw(int i) const { return load_u32_any(ot->y + 4 * i); }
     BB_HD void set_oxy(int k, int x, int y) { ot->x[k] = (uint8_t)x; ot->y[k] = (uint8_t)y; }
     BB_HD uint32_t desc_mask(int d) const { return ins->desc_mask[d]; }
     BB_HD int leaf_kind(int l) const { return ins->leaf_kind[l]; }
@@ -1334,20 +1354,29 @@ struct GlobalMem {
     BB_HD void set_flags(int v) { ins->flags = (uint8_t)v; }
 };
 
+// The objects whose TABLE position is (x, y), as a set mask: SWAR over the packed x / y byte arrays, four objects per
+// word -- no loop over set bits, no divergence (round 1 walked the masks object by object: with the seven actions and the
+// verifier tree in front of them those loops ran at 1.5-3 active lanes, ncu r02b).  Positions are < 32, so a byte of
+// (x ^ X) | (y ^ Y) is < 0x40 and "+ 0x7F" raises bit 7 exactly when it is non-zero.  Unused table entries sit at (0, 0),
+// an outer-wall corner that is never a front cell, and are excluded by every mask this is intersected with anyway.
 template <class M>
-BB_HD int find_obj_at(const M &mem, uint32_t mask, int x, int y)
+BB_HD uint32_t objs_at(const M &mem, int x, int y)
 {
-    for (uint32_t m = mask; m; m &= m - 1) {
-        int k = ffs32(m);
-        if (mem.ox(k) == x && mem.oy(k) == y) return k;
+    const uint32_t bx = (uint32_t)x * 0x01010101u, by = (uint32_t)y * 0x01010101u;
+    uint32_t at = 0;
+    for (int i = 0; i < mem.lp.obj_words; i++) {
+        const uint32_t d = (mem.oxw(i) ^ bx) | (mem.oyw(i) ^ by);
+        const uint32_t z = ((d + 0x7F7F7F7Fu) & 0x80808080u) ^ 0x80808080u;       // 0x80 in the bytes that match
+        at |= ((((z >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
     }
-    return NO_OBJ;
+    return at;
 }
 
 struct StepCtx {            // what a leaf verifier looks at after the action was applied
     int action, fx, fy;     // front_pos AFTER the move
     int carry;              // env.carrying after the action
     uint32_t cur_mask, snap_mask;
+    uint32_t at;            // objects whose table position is front_pos (objs_at)
 };
 
 // ActionInstr.verify_action: Open :257-274, GoTo :296-303, Pickup :330-350, PutNext :393-417
@@ -1356,19 +1385,12 @@ BB_HD bool verify_leaf(M &mem, int leaf, const StepCtx &s)
 {
     const int kind = mem.leaf_kind(leaf);
     const uint32_t set = mem.desc_mask(2 * leaf);
-    if (kind == I_GOTO) {
-        for (uint32_t m = set & s.snap_mask; m; m &= m - 1) {
-            int k = ffs32(m);
-            if (mem.ox(k) == s.fx && mem.oy(k) == s.fy) return true;
-        }
-        return false;
-    }
+    if (kind == I_GOTO) return (set & s.snap_mask & s.at) != 0;      // some pos in obj_poss is front_pos
     if (kind == I_OPEN) {
         if (s.action != A_TOGGLE) return false;
         int c = mem.cell(s.fx, s.fy);
         if ((c & 7) != T_DOOR || (c >> 6) != 0) return false;            // must be a door and open
-        int id = find_obj_at(mem, s.cur_mask, s.fx, s.fy);
-        return id != NO_OBJ && ((set >> id) & 1u);
+        return (set & s.cur_mask & s.at) != 0;                           // ... the one in front (at most one object is ON a cell)
     }
     const int pre = mem.leaf_pre(leaf);
     mem.set_leaf_pre(leaf, s.carry);
@@ -1425,14 +1447,17 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
     const int fx = x + dir_dx(dir), fy = y + dir_dy(dir);
     const int fc = mem.cell(fx, fy);
     const int ftype = fc & 7;
+    // the three actions that change the pose first: the other four act on the cell in front, which for them is also
+    // front_pos AFTER the action -- the position the verifier looks at.  One objs_at() of that cell serves both.
     if (action == A_LEFT) dir = (dir + 3) & 3;
     else if (action == A_RIGHT) dir = (dir + 1) & 3;
-    else if (action == A_FORWARD) {
-        if (fc == CELL_EMPTY || (ftype == T_DOOR && (fc >> 6) == 0)) { x = fx; y = fy; }
-    } else if (action == A_PICKUP) {
+    else if (action == A_FORWARD && (fc == CELL_EMPTY || (ftype == T_DOOR && (fc >> 6) == 0))) { x = fx; y = fy; }
+    const int nfx = x + dir_dx(dir), nfy = y + dir_dy(dir);
+    uint32_t at = objs_at(mem, nfx, nfy);
+    if (action == A_PICKUP) {
         if (ftype >= T_KEY && carry == NO_OBJ) {
-            int id = find_obj_at(mem, h.cur_mask, fx, fy);
-            if (id != NO_OBJ) { carry = id; h.cur_mask &= ~(1u << id); mem.set_cell(fx, fy, CELL_EMPTY); }
+            const uint32_t m = at & h.cur_mask;
+            if (m) { carry = ffs32(m); h.cur_mask &= ~(1u << carry); mem.set_cell(fx, fy, CELL_EMPTY); }
             else if constexpr (UNTR) { carry = CARRY_UNTRACKED | (fc & 0x3F); mem.set_cell(fx, fy, CELL_EMPTY); }
         }
     } else if (action == A_DROP) {
@@ -1443,6 +1468,7 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
                     mem.set_cell(fx, fy, mem.otc(carry));
                     mem.set_oxy(carry, fx, fy);
                     h.cur_mask |= 1u << carry;
+                    at |= 1u << carry;                  // its table position is the front cell now
                 }
                 carry = NO_OBJ;
             }
@@ -1450,6 +1476,7 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
             mem.set_cell(fx, fy, mem.otc(carry));
             mem.set_oxy(carry, fx, fy);
             h.cur_mask |= 1u << carry;
+            at |= 1u << carry;
             carry = NO_OBJ;
         }
     } else if (action == A_TOGGLE) {
@@ -1465,8 +1492,8 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
             } else ns = st ^ 1;
             if (ns != st) mem.set_cell(fx, fy, (fc & 0x3F) | (ns << 6));
         } else if (ftype == T_BOX) {  // Box.toggle: replaced by its contents (None)
-            int id = find_obj_at(mem, h.cur_mask, fx, fy);
-            if (id != NO_OBJ) h.cur_mask &= ~(1u << id);
+            const uint32_t m = at & h.cur_mask;
+            if (m) h.cur_mask &= ~(1u << ffs32(m));
             mem.set_cell(fx, fy, CELL_EMPTY);
         }
     }
@@ -1477,8 +1504,8 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
     if (action == A_DROP) h.snap_mask = h.cur_mask;
     h.x = (uint8_t)x; h.y = (uint8_t)y; h.dirflags = (uint8_t)((h.dirflags & ~3) | dir); h.carry = (uint8_t)carry;
     StepCtx s;
-    s.action = action; s.fx = x + dir_dx(dir); s.fy = y + dir_dy(dir); s.carry = carry;
-    s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask;
+    s.action = action; s.fx = nfx; s.fy = nfy; s.carry = carry;
+    s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.at = at;
     r.success = verify_root(mem, s);
     r.reward = 0.0f;
     if (r.success) {

@@ -55,6 +55,7 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     // doors: one per internal wall at most
     max_objs += s->num_rows * (s->num_cols - 1) + s->num_cols * (s->num_rows - 1);
     if (max_objs > MAXOBJ) return "too many objects for the 32-entry object table";
+    lp->obj_words = max_objs < 1 ? 1 : (max_objs + 3) / 4;
     // longest mission in tokens
     int per_desc = 3 + (s->kind == BB_KIND_LEVELGEN && s->locations ? 4 : 0);
     int leaf = 2 + per_desc;

@@ -101,6 +101,8 @@ struct StagedMem {
     __device__ __forceinline__ int ox(int k) const { return so->x[k]; }
     __device__ __forceinline__ int oy(int k) const { return so->y[k]; }
     __device__ __forceinline__ int otc(int k) const { return so->tc[k]; }
+    __device__ __forceinline__ uint32_t oxw(int i) const { return reinterpret_cast<const uint32_t *>(so->x)[i]; }
+    __device__ __forceinline__ uint32_t oyw(int i) const { return reinterpret_cast<const uint32_t *>(so->y)[i]; }
     __device__ __forceinline__ void set_oxy(int k, int x, int y)
     {
         so->x[k] = (uint8_t)x; so->y[k] = (uint8_t)y; ot->x[k] = (uint8_t)x; ot->y[k] = (uint8_t)y;
@@ -377,6 +379,8 @@ struct SmemOnlyMem {            // lane-private records in shared memory (byte a
     __device__ __forceinline__ int ox(int k) const { return o[k]; }
     __device__ __forceinline__ int oy(int k) const { return o[MAXOBJ + k]; }
     __device__ __forceinline__ int otc(int k) const { return o[2 * MAXOBJ + k]; }
+    __device__ __forceinline__ uint32_t oxw(int i) const { return reinterpret_cast<const uint32_t *>(o)[i]; }
+    __device__ __forceinline__ uint32_t oyw(int i) const { return reinterpret_cast<const uint32_t *>(o)[MAXOBJ / 4 + i]; }
     __device__ __forceinline__ void set_oxy(int k, int x, int y) { o[k] = (uint8_t)x; o[MAXOBJ + k] = (uint8_t)y; }
     __device__ __forceinline__ uint32_t desc_mask(int d) const { return reinterpret_cast<const uint32_t *>(i)[d]; }
     __device__ __forceinline__ int leaf_kind(int l) const { return i[32 + l]; }
@@ -413,7 +417,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
 // k_rollout_cta -- bb_pool_rollout on MULTI-ROOM levels: 32 envs per CTA, a lane-per-env step phase and a 4-lanes-per-env
 // observation phase per step, row-major grid only in shared memory (rollout_cta.cuh has the design and the numbers).
 template <bool UNTR>
-__global__ void __launch_bounds__(RC_THREADS, 7)
+__global__ void __launch_bounds__(RC_THREADS, 8)
 k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
               float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T, const int mode)
 {
@@ -581,6 +585,7 @@ struct bb_pool {
     int8_t *h_act; uint8_t *h_obs; float *h_rew; uint8_t *h_done; int8_t *h_dir;      // pinned
     uint8_t *d_rgb_lut;            // the 513 RGB tiles (rgb_tiles.h), rendered on first use
     int *h_err;                    // mapped: PoolPtrs::err_flag (a kernel found a level ring dry)
+    int last_T, refill_cap;        // rollout length of the previous bb_pool_rollout call; BB_REFILL_EVERY as a cap for concurrent passes
     int fused_T;                   // longest T a fused rollout launch has guaranteed levels for (see bb_pool_rollout)
     int zerocopy, zc_level; const void *chk_rew, *chk_done, *chk_dir; bool chk_pinned; int8_t *zc_act; float *zc_rew; uint8_t *zc_done; int8_t *zc_dir; uint8_t *zc_obs;   // BB_HOST_ZEROCOPY
     int8_t *d_act; uint8_t *d_obs; float *d_rew; uint8_t *d_done; int8_t *d_dir;
@@ -753,12 +758,15 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->gen_min_active = 16;                                // ... and a warp with fewer working lanes than this stops after its first round
     if (const char *e = getenv("BB_GEN_MIN_ACTIVE")) p->gen_min_active = atoi(e);
     p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
-    if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) p->refill_every = v; }
+    p->refill_cap = 0; p->last_T = 0;
+    if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) { p->refill_every = v; p->refill_cap = v; } }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
     // >= 3 x the 40-step rollout of bb_pool_rollout (one refill pass per two launches); for the per-step API one
     // generation pass per 32 steps (many levels per pass: a multi-room level is ~0.2-0.4 ms of serial work)
-    p->D = 128;
+    // multi-room levels (generation passes run BESIDE the rollouts on a side stream): twice the depth, so that one pass may
+    // overlap several launches (bb_pool_rollout: a pass is joined D / 2T launches after it was forked)
+    p->D = p->lp.cells_pad > 256 ? 256 : 128;
     if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 256) p->D = d; }
     p->G = p->D >= 64 ? 32 : (p->D >= 8 ? p->D / 4 : 1);
     if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
@@ -959,10 +967,21 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     BB_CHECK_RINGS(p);
     CU(cudaSetDevice(p->device));
     cudaStream_t user = (cudaStream_t)stream;
-    const bool persistent = p->lp.cells_pad <= p->persist_max_cells && !p->no_persistent && (p->mode == BB_MODE_FREEZE || p->D >= (p->refill_every + 1) * T);
+    // Level supply of the persistent kernels.  In-stream refill passes (single-room levels without the fused generator warp):
+    // one pass per `refill_every` launches, needs D >= (refill_every + 1) T.  Concurrent passes (multi-room levels: k_gen on
+    // the side stream, beside the rollouts): a pass is forked at every R-th launch from a head snapshot taken before that
+    // launch and joined R launches later, so it overlaps R launches; it tops every ring up to D relative to its snapshot,
+    // the R launches it overlaps and the R launches until the next pass is joined consume at most 2 R T: R = D / 2T.
+    const bool conc = p->gen_concurrent && p->mode == BB_MODE_AUTORESET;
+    int R = p->refill_every;
+    if (conc) { R = p->D / (2 * T); if (R > 8) R = 8; if (p->refill_cap > 0 && R > p->refill_cap) R = p->refill_cap; }
+    const bool persistent = p->lp.cells_pad <= p->persist_max_cells && !p->no_persistent &&
+                            (p->mode == BB_MODE_FREEZE || (conc ? R >= 1 : p->D >= (p->refill_every + 1) * T));
     if (!persistent) return rollout_graph(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, user);
-    if (sched_join(p, user)) return 1;                 // every k_gen enqueued so far (rings topped up to D - what
-                                                       // the previous rollout consumed >= D - T >= T levels per env)
+    if (T != p->last_T) { p->rollouts = 0; p->last_T = T; }       // a different rollout length restarts the refill schedule
+    const bool refill_slot = (p->rollouts % R) == 0;
+    // join what is outstanding: always for in-stream refills / ManyEnvs mode; for concurrent passes only where the next one forks
+    if (!conc || refill_slot) { if (sched_join(p, user)) return 1; }
     const size_t smem = (size_t)R_WARPS * rl_warp_words(p->lp) * 4;
     const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
     // Single-room levels: FUSED -- a generator warp inside every CTA of k_rollout refills the rings of the CTA's envs
@@ -980,7 +999,8 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (fused && T > p->fused_T) launch_gen(p, user);
     p->fused_T = fused ? T : 0;
     // otherwise one refill pass serves `refill_every` launches (more envs per pass = more lanes busy in k_gen_small)
-    const bool refill = !fused && p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL") && (p->rollouts++ % p->refill_every) == 0;
+    const bool refill = !fused && p->mode == BB_MODE_AUTORESET && !getenv("BB_DEBUG_NO_REFILL") && refill_slot;
+    p->rollouts++;
     const bool dbg_timing = p->time_rollout;
     cudaEvent_t *dbg_ev = p->tev;
     if (dbg_timing && !dbg_ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&dbg_ev[i]));

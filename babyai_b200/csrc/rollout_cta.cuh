@@ -51,6 +51,8 @@ struct SmemGMem {
     BB_HD int ox(int k) const { return o[k]; }
     BB_HD int oy(int k) const { return o[MAXOBJ + k]; }
     BB_HD int otc(int k) const { return o[2 * MAXOBJ + k]; }
+    BB_HD uint32_t oxw(int i) const { return load_u32_any(o + 4 * i); }
+    BB_HD uint32_t oyw(int i) const { return load_u32_any(o + MAXOBJ + 4 * i); }
     BB_HD void set_oxy(int k, int x, int y) { o[k] = (uint8_t)x; o[MAXOBJ + k] = (uint8_t)y; }
     BB_HD uint32_t desc_mask(int d) const { return reinterpret_cast<const uint32_t *>(i)[d]; }
     BB_HD int leaf_kind(int l) const { return i[32 + l]; }

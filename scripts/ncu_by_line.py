@@ -66,6 +66,7 @@ def main():
         print('warning: %d SASS instructions in the library vs %d in the report (different build?)' % (len(sass), len(rows)))
     n = min(len(sass), len(rows))
     by_line = collections.defaultdict(lambda: [0, 0, 0])
+    line_stalls = collections.defaultdict(collections.Counter)
     by_file = collections.defaultdict(lambda: [0, 0])
     tot_i = tot_s = 0
     stalls = collections.Counter()
@@ -80,7 +81,9 @@ def main():
         by_file[key[0]][0] += ins; by_file[key[0]][1] += smp
         tot_i += ins; tot_s += smp
         for h in scols:
-            stalls[h] += int(float(r[ci[h]] or 0))
+            v = int(float(r[ci[h]] or 0))
+            stalls[h] += v
+            line_stalls[key][h[6:]] += v
     print('%s\n  %d SASS instructions, %.2f M warp instructions executed, %d stall samples' % (b['name'][:100], n, tot_i / 1e6, tot_s))
     print('  stall samples: ' + ', '.join('%s %.1f%%' % (h[6:], 100.0 * v / max(1, sum(stalls.values()))) for h, v in stalls.most_common(8)))
     print('by file:')
@@ -89,7 +92,15 @@ def main():
     print('hottest lines (by warp instructions executed):')
     for (f, l), (i, s, t) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:a.top]:
         print('  %-20s:%-5d %6.2f%% instr  %6.2f%% samples  %5.1f thr/instr' % (f, l, 100.0 * i / tot_i, 100.0 * s / max(1, tot_s), t / max(1, i)))
+    print('hottest lines (by stall samples) and their main stall reasons:')
+    for (f, l), (i, s, t) in sorted(by_line.items(), key=lambda kv: -kv[1][1])[:a.top // 2]:
+        top = ', '.join('%s %d' % kv for kv in line_stalls[(f, l)].most_common(3))
+        print('  %-20s:%-5d %6.2f%% samples  %6.2f%% instr   %s' % (f, l, 100.0 * s / max(1, tot_s), 100.0 * i / tot_i, top))
 
 
 if __name__ == '__main__':
     main()
+
+
+def _unused():
+    pass

@@ -102,6 +102,8 @@ struct HostSmemMem {
     int ox(int k) const { return o[k]; }
     int oy(int k) const { return o[MAXOBJ + k]; }
     int otc(int k) const { return o[2 * MAXOBJ + k]; }
+    uint32_t oxw(int i) const { uint32_t v; memcpy(&v, o + 4 * i, 4); return v; }
+    uint32_t oyw(int i) const { uint32_t v; memcpy(&v, o + MAXOBJ + 4 * i, 4); return v; }
     void set_oxy(int k, int x, int y) { o[k] = (uint8_t)x; o[MAXOBJ + k] = (uint8_t)y; }
     uint32_t desc_mask(int d) const { uint32_t v; memcpy(&v, i + 4 * d, 4); return v; }
     int leaf_kind(int l) const { return i[32 + l]; }

@@ -142,3 +142,42 @@ def test_rollout_equals_stepwise(level, n, T):
             o, r, d = b.step(acts[t])
             assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]) and torch.equal(d, done[t]) and torch.equal(b.direction, dirs[t]), (rep, t)
     assert a.counters() == b.counters() and a.counters()['errors'] == 0
+
+
+@pytest.mark.timeout(600)
+def test_c5_per_gpu_share_matches_oracle_slice():
+    """BASELINE config 5 at its per-GPU size: BossLevel, 32 768 envs with the seeds rank 3 of 8 owns in the 262 144-env job
+    (sharding.shard_seeds), 25 rollouts of 40 steps through k_rollout_cta with the generation passes running beside them
+    (one pass overlaps several launches).  The first 512 envs are compared step by step with the C oracle on the same
+    seeds and actions; a second pool with the same seeds must reproduce the last launch bit for bit (determinism under the
+    asynchronous level supply); no ring may run dry."""
+    import torch
+    import oracle as orc
+    from babyai_b200 import BabyAIVecEnv
+    from babyai_b200.sharding import shard_seeds
+    n, T, L, m = 32768, 40, 25, 512
+    seeds = shard_seeds(1, 8 * n, 3, 8)
+    assert seeds[0] == 100 + 3 * n
+    pools = [BabyAIVecEnv('BossLevel', n, seeds=seeds) for _ in range(2)]
+    ref = orc.OraclePool('BossLevel', m, seeds[:m])
+    gen = torch.Generator(device='cuda').manual_seed(9)
+    acts = torch.randint(0, 7, (L, T, n), device='cuda', dtype=torch.int8, generator=gen)
+    bufs = [(torch.zeros((T, n, 7, 7, 3), dtype=torch.uint8, device='cuda'), torch.zeros((T, n), device='cuda'),
+             torch.zeros((T, n), dtype=torch.uint8, device='cuda'), torch.zeros((T, n), dtype=torch.int8, device='cuda')) for _ in pools]
+    o0 = pools[0].reset().cpu().numpy()
+    pools[1].reset()
+    assert np.array_equal(o0[:m], ref.reset())
+    for k in range(L):
+        pools[0].rollout(acts[k], *bufs[0])
+        ho, hr, hd = bufs[0][0][:, :m].cpu().numpy(), bufs[0][1][:, :m].cpu().numpy(), bufs[0][2][:, :m].cpu().numpy()
+        a = acts[k][:, :m].cpu().numpy()
+        for t in range(T):
+            oo, rr, dd = ref.step(a[t], nthreads=16)
+            assert np.array_equal(ho[t], oo), (k, t)
+            assert np.array_equal(hr[t].view(np.uint32), rr.view(np.uint32)) and np.array_equal(hd[t], dd), (k, t)
+    for k in range(L):
+        pools[1].rollout(acts[k], *bufs[1])
+    torch.cuda.synchronize()
+    assert all(bool(torch.equal(x, y)) for x, y in zip(bufs[0], bufs[1]))
+    c0, c1 = pools[0].counters(), pools[1].counters()
+    assert c0 == c1 and c0['errors'] == 0 and c0['steps'] == n * T * L and c0['episodes'] > 0
