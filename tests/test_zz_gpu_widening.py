@@ -181,3 +181,36 @@ def test_c5_per_gpu_share_matches_oracle_slice():
     assert all(bool(torch.equal(x, y)) for x, y in zip(bufs[0], bufs[1]))
     c0, c1 = pools[0].counters(), pools[1].counters()
     assert c0 == c1 and c0['errors'] == 0 and c0['steps'] == n * T * L and c0['episodes'] > 0
+
+
+@pytest.mark.parametrize('level', ['GoToObjMazeS4R2', 'MiniBossLevel'])
+def test_many_envs_facades_on_a_multi_room_level(level):
+    """babyai.evaluate.ManyEnvs surface (evaluate.py:58-81) on the GPU for a multi-room level: vecenv.ManyEnvs (host dicts) and
+    learner.DeviceManyEnvs (observations resident on the device) -- seed(seeds), reset(), step() that freezes finished envs
+    and repeats their last result -- against the C oracle stepped without auto-reset, two evaluation chunks in a row."""
+    import oracle as orc
+    from babyai_b200 import DeviceManyEnvs, ManyEnvs, make_envs
+    n = 48
+    host, devm = ManyEnvs(make_envs(level, n)), DeviceManyEnvs(make_envs(level, n))
+    rng = np.random.RandomState(4)
+    for chunk in range(2):
+        seeds = [10 ** 9 + chunk * n + k for k in range(n)]              # evaluate.py:105: seed + i * num_envs + k
+        host.seed(seeds); devm.seed(seeds)
+        ref = orc.OraclePool(level, n, np.array(seeds, dtype=np.uint64))
+        oh, od, oo = host.reset(), devm.reset(), ref.reset()
+        assert all(np.array_equal(oh[i]['image'], oo[i]) and oh[i]['mission'] == ref.mission(i) for i in range(n))
+        assert np.array_equal(od.image.cpu().numpy(), oo)
+        frozen, last = np.zeros(n, bool), [None] * n
+        for t in range(160):
+            act = rng.choice(7, size=n, p=[0.12, 0.12, 0.4, 0.1, 0.1, 0.14, 0.02])
+            oh, rh, dh, _ = host.step(act)
+            od, rd, dd, _ = devm.step(act)
+            oo, ro, do = ref.step(act.astype(np.int8), autoreset=False)
+            img = od.image.cpu().numpy()
+            for i in range(n):
+                want = last[i] if frozen[i] else (oo[i].copy(), float(ro[i]), bool(do[i]))
+                assert np.array_equal(oh[i]['image'], want[0]) and np.array_equal(img[i], want[0]), (level, chunk, t, i)
+                assert rh[i] == rd[i] == np.float32(want[1]) and dh[i] == dd[i] == want[2], (level, chunk, t, i)
+                if not frozen[i] and do[i]:
+                    frozen[i], last[i] = True, want
+        assert host.pool.counters()['errors'] == 0 and devm.pool.counters()['errors'] == 0
