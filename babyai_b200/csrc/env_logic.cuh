@@ -1377,48 +1377,52 @@ struct StepCtx {            // what a leaf verifier looks at after the action wa
     int carry;              // env.carrying after the action
     uint32_t cur_mask, snap_mask;
     uint32_t at;            // objects whose table position is front_pos (objs_at)
+    int fcell;              // the cell at front_pos after the action
 };
 
-// ActionInstr.verify_action: Open :257-274, GoTo :296-303, Pickup :330-350, PutNext :393-417
+// ActionInstr.verify_action: Open :257-274, GoTo :296-303, Pickup :330-350, PutNext :393-417.
+// Written branch-light: the four kinds are evaluated as predicates and selected by kind, so that the lanes of a warp
+// (one env each, all with different instructions) run ONE instruction stream (round 1's if-chain per kind, nested in the
+// side / root recursion, ran at 3.6 active lanes: ncu r02c).  Only PutNext's neighbourhood test is a loop, and it runs only
+// on the step where a matching object was just dropped.
 template <class M>
 BB_HD bool verify_leaf(M &mem, int leaf, const StepCtx &s)
 {
     const int kind = mem.leaf_kind(leaf);
     const uint32_t set = mem.desc_mask(2 * leaf);
-    if (kind == I_GOTO) return (set & s.snap_mask & s.at) != 0;      // some pos in obj_poss is front_pos
-    if (kind == I_OPEN) {
-        if (s.action != A_TOGGLE) return false;
-        int c = mem.cell(s.fx, s.fy);
-        if ((c & 7) != T_DOOR || (c >> 6) != 0) return false;            // must be a door and open
-        return (set & s.cur_mask & s.at) != 0;                           // ... the one in front (at most one object is ON a cell)
-    }
     const int pre = mem.leaf_pre(leaf);
-    mem.set_leaf_pre(leaf, s.carry);
-    if (kind == I_PICKUP) {
-        if (s.action != A_PICKUP) return false;
-        return pre == NO_OBJ && s.carry != NO_OBJ && ((set >> s.carry) & 1u);
+    if (kind == I_PICKUP || kind == I_PUTNEXT) mem.set_leaf_pre(leaf, s.carry);       // preCarrying, refreshed on every evaluation
+    const bool goto_ok = (set & s.snap_mask & s.at) != 0;                             // some pos in obj_poss is front_pos
+    // the toggled cell must be a door of the set, and open: at most one object is ON a cell
+    const bool open_ok = s.action == A_TOGGLE && (s.fcell & 0xC7) == T_DOOR && (set & s.cur_mask & s.at) != 0;
+    const bool pick_ok = s.action == A_PICKUP && pre == NO_OBJ && s.carry < MAXOBJ && ((set >> (s.carry & 31)) & 1u);     // (untracked objects, KIND_UNLOCK, are in no set)
+    bool put_ok = false;
+    if (kind == I_PUTNEXT && s.action == A_DROP && pre < MAXOBJ && ((set >> (pre & 31)) & 1u) && s.carry != pre) {
+        const int ax = mem.ox(pre), ay = mem.oy(pre);      // (a carried object that was not dropped: cur_pos == (-1, -1), excluded above)
+        for (uint32_t m = mem.desc_mask(2 * leaf + 1) & s.snap_mask; m; m &= m - 1) {
+            const int k = ffs32(m);
+            if (iabs(ax - mem.ox(k)) + iabs(ay - mem.oy(k)) == 1) put_ok = true;
+        }
     }
-    // PutNext
-    if (s.action != A_DROP) return false;
-    if (pre == NO_OBJ || !((set >> pre) & 1u)) return false;
-    if (s.carry == pre) return false;                   // still in hand: cur_pos == (-1,-1)
-    int ax = mem.ox(pre), ay = mem.oy(pre);
-    for (uint32_t m = mem.desc_mask(2 * leaf + 1) & s.snap_mask; m; m &= m - 1) {
-        int k = ffs32(m);
-        if (iabs(ax - mem.ox(k)) + iabs(ay - mem.oy(k)) == 1) return true;
-    }
-    return false;
+    return kind == I_GOTO ? goto_ok : kind == I_OPEN ? open_ok : kind == I_PICKUP ? pick_ok : put_ok;
 }
 
-// one side: an ActionInstr, or AndInstr.verify (verifier.py:536-550)
+// one side: an ActionInstr, or AndInstr.verify (verifier.py:536-550): each unfinished half is evaluated every step
 template <class M>
 BB_HD bool verify_side(M &mem, int side, const StepCtx &s)
 {
-    if (!((mem.side_and() >> side) & 1)) return verify_leaf(mem, 2 * side, s);
+    const bool is_and = ((mem.side_and() >> side) & 1) != 0;
     const int ba = 2 + 2 * side, bb_ = 3 + 2 * side;
-    if (!((mem.flags() >> ba) & 1) && verify_leaf(mem, 2 * side, s)) mem.set_flags(mem.flags() | (1 << ba));
-    if (!((mem.flags() >> bb_) & 1) && verify_leaf(mem, 2 * side + 1, s)) mem.set_flags(mem.flags() | (1 << bb_));
-    return ((mem.flags() >> ba) & 1) && ((mem.flags() >> bb_) & 1);
+    int fl = mem.flags();
+    const bool a_latched = is_and && ((fl >> ba) & 1);
+    const bool b_latched = ((fl >> bb_) & 1) != 0;
+    bool r0 = true;
+    if (!a_latched) r0 = verify_leaf(mem, 2 * side, s);
+    if (!is_and) return r0;
+    if (!a_latched && r0) fl |= 1 << ba;
+    if (!b_latched && verify_leaf(mem, 2 * side + 1, s)) fl |= 1 << bb_;
+    if (fl != mem.flags()) mem.set_flags(fl);
+    return ((fl >> ba) & 1) && ((fl >> bb_) & 1);
 }
 
 // BeforeInstr.verify :449-471, AfterInstr.verify :490-512 (hand-over re-verifies the same action)
@@ -1426,12 +1430,12 @@ template <class M>
 BB_HD bool verify_root(M &mem, const StepCtx &s)
 {
     const int rk = mem.root_kind();
-    if (rk == R_SINGLE) return verify_side(mem, 0, s);
-    const int first = rk == R_BEFORE ? 0 : 1, second = 1 - first;
-    if (!((mem.flags() >> first) & 1)) {
-        if (!verify_side(mem, first, s)) return false;
-        mem.set_flags(mem.flags() | (1 << first));
-    }
+    const int first = rk == R_AFTER ? 1 : 0, second = 1 - first;
+    const bool first_done = rk != R_SINGLE && ((mem.flags() >> first) & 1);
+    bool ok = true;
+    if (!first_done) ok = verify_side(mem, first, s);
+    if (rk == R_SINGLE || !ok) return ok;
+    if (!first_done) mem.set_flags(mem.flags() | (1 << first));
     return verify_side(mem, second, s);
 }
 
@@ -1506,6 +1510,7 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
     StepCtx s;
     s.action = action; s.fx = nfx; s.fy = nfy; s.carry = carry;
     s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.at = at;
+    s.fcell = mem.cell(nfx, nfy);
     r.success = verify_root(mem, s);
     r.reward = 0.0f;
     if (r.success) {

@@ -417,7 +417,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
 // k_rollout_cta -- bb_pool_rollout on MULTI-ROOM levels: 32 envs per CTA, a lane-per-env step phase and a 4-lanes-per-env
 // observation phase per step, row-major grid only in shared memory (rollout_cta.cuh has the design and the numbers).
 template <bool UNTR>
-__global__ void __launch_bounds__(RC_THREADS, 8)
+__global__ void __launch_bounds__(RC_THREADS, 7)
 k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
               float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T, const int mode)
 {
@@ -564,7 +564,7 @@ constexpr int MAX_GEN_EVENTS = 40;
 struct bb_pool {
     LevelParams lp;
     PoolPtrs P;
-    int n, device, mode, num_warps, gen_blocks, sm_count;
+    int n, device, mode, num_warps, gen_blocks, gen_blocks_beside, sm_count;
     // level supply schedule: ring depth D; k_gen is enqueued on gen_stream after every G-th step and
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
@@ -619,15 +619,21 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
     return e ? fail("%s", e) : 0;
 }
 
-static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false, int min_keep = 0)
+static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false, int min_keep = 0, bool beside = false)
 {
     cudaMemsetAsync(p->P.gen_count, 0, 8 * sizeof(uint32_t), st);      // list counters + work ticket
     k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
     p->launches++;
     if (p->lp.small && !p->gen_generic) {
         k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active, min_keep);
-    } else if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK) k_gen<true><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
-    else k_gen<false><<<p->gen_blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    } else {
+        // a pass that runs BESIDE the rollout kernel gets two blocks per SM: with more, its resident blocks (not preemptible)
+        // keep the next rollout launch from its 7 CTAs per SM (measured r02c: k_rollout_cta 7.5 -> 10.3 us per step beside an
+        // 8-blocks-per-SM pass); the pass is latency bound on its longest chain, not throughput bound
+        const int blocks = beside && p->gen_blocks_beside < p->gen_blocks ? p->gen_blocks_beside : p->gen_blocks;
+        if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+        else k_gen<false><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+    }
 }
 
 // One generation pass on stream `st`: snapshot the consumption counters, reset the work-ticket counter,
@@ -743,6 +749,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         int want = (n_envs + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);      // one warp per env at most
         int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
+        int beside = 2;
+        if (const char *e = getenv("BB_GEN_BESIDE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) beside = v; }
+        p->gen_blocks_beside = prop.multiProcessorCount * beside;
         int per_sm = 4;
         if (const char *e = getenv("BB_GEN_SMALL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) per_sm = v; }
         p->gen_small_blocks = prop.multiProcessorCount * per_sm;
@@ -1040,7 +1049,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (refill && !gen_serial) {
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
         if (dbg_timing) cudaEventRecord(dbg_ev[2], p->gen_stream);
-        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget, p->gen_min_active, false, (p->refill_every + 1) * T);      // bounded: runs beside k_rollout
+        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget, p->gen_min_active, false, (p->refill_every + 1) * T, true);      // bounded: runs beside k_rollout
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
         if (dbg_timing) { cudaEventRecord(dbg_ev[3], p->gen_stream); p->tev_refill = true; }
         p->gen_outstanding = true;

@@ -29,7 +29,7 @@
 namespace bb {
 
 constexpr int RC_ENVS = 32;                    // envs per CTA
-constexpr int RC_THREADS = 128;                // 4 lanes per env in the observation phase
+constexpr int RC_THREADS = 160;                // warps 0..3: observers, 4 lanes per env; warp 4: the stepper, one lane per env
 constexpr int RC_OBJ_STRIDE = 25, RC_INS_STRIDE = 13;             // odd word strides: lane-per-env accesses are conflict free
 constexpr int RC_TILE_WORDS = RC_ENVS * OBS_BYTES / 4;            // 1176 words = 4704 B
 
@@ -132,8 +132,8 @@ BB_DEV void rollout_cta_role(const LevelParams &lp, const PP &P, const int8_t *a
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     if (tid < RC_ENVS) s_swap[tid] = 0;
-    // ---- phase-A state (warp 0: lane = env within the CTA) --------------------------------------------------------
-    const bool stepper = warp == 0;
+    // ---- the stepper: warp 4, lane = env within the CTA ------------------------------------------------------------
+    const bool stepper = warp == RC_THREADS / 32 - 1;
     const int env_a = env0 + lane;
     const bool valid_a = stepper && lane < nv;
     EnvHot h;
@@ -152,40 +152,83 @@ BB_DEV void rollout_cta_role(const LevelParams &lp, const PP &P, const int8_t *a
     BB_SYNCTHREADS();
     SmemGMem mem_a(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * RC_OBJ_STRIDE),
                    reinterpret_cast<uint8_t *>(si + lane * RC_INS_STRIDE));
-    // ---- phase-B identity: 4 lanes per env -------------------------------------------------------------------------
-    const int el = tid >> 2, q = tid & 3;
-    const bool valid_b = el < nv;
+    // ---- the observers: warps 0..3, 4 lanes per env ------------------------------------------------------------------
+    const int el = (tid >> 2) & (RC_ENVS - 1), q = tid & 3;
+    const bool valid_b = !stepper && el < nv;
     const uint8_t *g_b = reinterpret_cast<const uint8_t *>(sg + el * gs);
+    // what an observer carries from the gather of step t (B1) to the encode of step t (B2), which runs while the stepper
+    // is already at step t + 1: its two view columns, the env's see-through column masks, the carried cell byte
+    uint32_t loA = 0, hiA = 0, loB = 0, hiB = 0, blo = 0, bhi = 0, carry_b = 0;
     bool bulk_pending = false;                                     // thread 0 only
-    for (int t = 0; t < T; t++) {
-        // ================= phase A: one lane per env steps it =================
+    for (int t = 0; t <= T; t++) {
         bool begin = false;
         if (stepper) {
-            const int a = a_next;
-            if (valid_a && t + 1 < T) a_next = BB_LD_S8(actions + (size_t)(t + 1) * n + env_a);
-            if (valid_a) {
-                float rew = 0.0f; bool dn = false;
-                if (!(h.dirflags & 4)) {
-                    const StepResult sr = step_env<UNTR>(h, mem_a, a);
-                    rew = sr.reward; dn = sr.done;
-                    n_step++; n_end += dn; n_succ += sr.success;
-                    if (dn) {
-                        if (mode == BB_MODE_AUTORESET) begin = true;
-                        else { h.dirflags |= 4; last_rew = rew; }
-                    }
-                } else { rew = last_rew; dn = true; }
-                if (begin && !(consumed < avail && avail <= (uint32_t)P.depth)) { begin = false; n_err++; *P.err_flag = 1; }   // ring dry
-                if (begin) s_swap[lane] = (head + consumed) % (uint32_t)P.depth + 1u;
-                else s_pose[lane] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)(h.dirflags & 3) << 16) |
-                                    ((uint32_t)carry_cell_of<UNTR>(h, mem_a) << 24);
-                const size_t oi = (size_t)t * n + env_a;
-                if (reward) reward[oi] = rew;
-                if (done) done[oi] = dn ? 1 : 0;
+            // ================= A(t): one lane per env steps it =================
+            if (t < T) {
+                const int a = a_next;
+                if (valid_a && t + 1 < T) a_next = BB_LD_S8(actions + (size_t)(t + 1) * n + env_a);
+                if (valid_a) {
+                    float rew = 0.0f; bool dn = false;
+                    if (!(h.dirflags & 4)) {
+                        const StepResult sr = step_env<UNTR>(h, mem_a, a);
+                        rew = sr.reward; dn = sr.done;
+                        n_step++; n_end += dn; n_succ += sr.success;
+                        if (dn) {
+                            if (mode == BB_MODE_AUTORESET) begin = true;
+                            else { h.dirflags |= 4; last_rew = rew; }
+                        }
+                    } else { rew = last_rew; dn = true; }
+                    if (begin && !(consumed < avail && avail <= (uint32_t)P.depth)) { begin = false; n_err++; *P.err_flag = 1; }   // ring dry
+                    if (begin) s_swap[lane] = (head + consumed) % (uint32_t)P.depth + 1u;
+                    else s_pose[lane] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)(h.dirflags & 3) << 16) |
+                                        ((uint32_t)carry_cell_of<UNTR>(h, mem_a) << 24);
+                    const size_t oi = (size_t)t * n + env_a;
+                    if (reward) reward[oi] = rew;
+                    if (done) done[oi] = dn ? 1 : 0;
+                }
             }
-            if (tid == 0 && bulk_pending) { BB_BULK_WAIT_READ(); bulk_pending = false; }   // the copy engine has read the previous tile
+        } else if (t > 0) {
+            // ================= B2(t - 1): process_vis, encode, stage -- from registers only =================
+            uint32_t tlo = blo, thi = bhi;
+            transpose8(tlo, thi);                                  // column masks -> per view row (bit vi)
+            uint32_t see[7], vis[7];
+#pragma unroll
+            for (int vj = 0; vj < 7; vj++) see[vj] = ((vj < 4 ? tlo >> (8 * vj) : thi >> (8 * (vj - 4)))) & 0x7Fu;
+            vis_rows(see, vis);
+            uint32_t vlo = 0, vhi = 0;
+#pragma unroll
+            for (int vj = 0; vj < 7; vj++) { if (vj < 4) vlo |= vis[vj] << (8 * vj); else vhi |= vis[vj] << (8 * (vj - 4)); }
+            transpose8(vlo, vhi);                                  // byte vi = visibility of column vi, bit vj
+            const uint32_t vmine = (q & 2) ? vhi : vlo;            // columns 4..7 / 0..3
+            const uint32_t cvA = (vmine >> (16 * (q & 1))) & 0x7Fu, cvB = (vmine >> (16 * (q & 1) + 8)) & 0x7Fu;
+            uint32_t hB = hiB;
+            if (q == 1) hB = (hB & 0xFF00FFFFu) | (carry_b << 16);     // view cell (3, 6): the agent's own cell shows what it carries
+            uint32_t oA[6], oB[6];
+            col_encode(loA, hiA, valid_b ? cvA : 0u, oA);
+            col_encode(loB, hB, (valid_b && q < 3) ? cvB : 0u, oB);
+            // 21-byte records: record 7 el + vi; the word a record shares with its successor is completed with the successor's
+            // first word (the lane's own second column, or the next lane's first column: one shuffle)
+            const uint32_t nextA = BB_SHFL_DOWN(oA[0], 1);
+            if (q < 3) {
+                stage_record_words<21, 6>(tile, oA, 7 * el + 2 * q, oB[0]);
+                stage_record_words<21, 6>(tile, oB, 7 * el + 2 * q + 1, nextA);
+            } else stage_record_words<21, 6>(tile, oA, 7 * el + 6, nextA);
+            BB_FENCE_ASYNC_SMEM();                                 // tile writes -> visible to the copy engine
         }
+        // ---- barrier X: A(t) is done, tile(t - 1) is complete ----
+        const int any_begin = BB_SYNCTHREADS_OR(begin ? 1 : 0);
+        if (t > 0) {                                               // the CTA's 32 observations of step t - 1 leave as one tile
+            uint8_t *dst = obs + ((size_t)(t - 1) * n + env0) * OBS_BYTES;
+            if (nv == RC_ENVS && (((uintptr_t)dst) & 15) == 0) {
+                if (tid == 0) { BB_BULK_STORE(dst, tile, RC_ENVS * OBS_BYTES); bulk_pending = true; }
+            } else if (!stepper) {
+                const uint8_t *sb = reinterpret_cast<const uint8_t *>(tile);
+                for (int i = tid; i < nv * OBS_BYTES; i += RC_THREADS - 32) dst[i] = sb[i];
+            }
+        }
+        if (t == T) break;
         // ================= episode swap-in by the whole CTA (rare) =================
-        if (BB_SYNCTHREADS_OR(begin ? 1 : 0)) {
+        if (any_begin) {
             for (int e = 0; e < RC_ENVS; e++) {
                 const uint32_t sw = s_swap[e];
                 if (!sw) continue;                                 // CTA-uniform: every thread reads the same flag
@@ -217,56 +260,30 @@ BB_DEV void rollout_cta_role(const LevelParams &lp, const PP &P, const int8_t *a
                 s_swap[lane] = 0;
             }
         }
-        // ================= phase B: 4 lanes per env build the observation =================
-        const uint32_t pose = valid_b ? s_pose[el] : 0u;
-        const int ax = (int)(pose & 0xFF), ay = (int)((pose >> 8) & 0xFF), dir = (int)((pose >> 16) & 3);
-        uint32_t loA = 0, hiA = 0, loB = 0, hiB = 0, cmA = 0, cmB = 0;
-        if (valid_b) {
-            const RcView view = rc_view(lp, ax, ay, dir);
-            rc_col_gather(g_b, view, 2 * q, loA, hiA);
-            cmA = col_see(loA, hiA);
-            if (q < 3) { rc_col_gather(g_b, view, 2 * q + 1, loB, hiB); cmB = col_see(loB, hiB); }
+        if (!stepper) {
+            // ================= B1(t): pose, the lane's two view columns, the env's see-through masks -> registers =================
+            const uint32_t pose = valid_b ? s_pose[el] : 0u;
+            const int ax = (int)(pose & 0xFF), ay = (int)((pose >> 8) & 0xFF), dir = (int)((pose >> 16) & 3);
+            carry_b = pose >> 24;
+            uint32_t cmA = 0, cmB = 0;
+            loA = hiA = loB = hiB = 0;
+            if (valid_b) {
+                const RcView view = rc_view(lp, ax, ay, dir);
+                rc_col_gather(g_b, view, 2 * q, loA, hiA);
+                cmA = col_see(loA, hiA);
+                if (q < 3) { rc_col_gather(g_b, view, 2 * q + 1, loB, hiB); cmB = col_see(loB, hiB); }
+            }
+            // the 7 column masks (see-through bits, bit vj) of the env to all of its 4 lanes: byte vi of (blo : bhi)
+            const uint32_t v16 = cmA | (cmB << 8);
+            const uint32_t p1 = BB_SHFL_XOR(v16, 1);
+            const uint32_t mine = (q & 1) ? (p1 | (v16 << 16)) : (v16 | (p1 << 16));
+            const uint32_t other = BB_SHFL_XOR(mine, 2);
+            blo = (q & 2) ? other : mine; bhi = (q & 2) ? mine : other;
+            if (valid_b && q == 0 && dirs) dirs[(size_t)t * n + env0 + el] = (int8_t)dir;
+            if (tid == 0 && bulk_pending) { BB_BULK_WAIT_READ(); bulk_pending = false; }   // before B2(t) rewrites the tile
         }
-        // the 7 column masks (see-through bits, bit vj) of the env to all of its 4 lanes: byte vi of (blo : bhi)
-        const uint32_t v16 = cmA | (cmB << 8);
-        const uint32_t p1 = BB_SHFL_XOR(v16, 1);
-        const uint32_t mine = (q & 1) ? (p1 | (v16 << 16)) : (v16 | (p1 << 16));
-        const uint32_t other = BB_SHFL_XOR(mine, 2);
-        uint32_t blo = (q & 2) ? other : mine, bhi = (q & 2) ? mine : other;
-        transpose8(blo, bhi);                                      // -> per view row (bit vi)
-        uint32_t see[7], vis[7];
-#pragma unroll
-        for (int vj = 0; vj < 7; vj++) see[vj] = ((vj < 4 ? blo >> (8 * vj) : bhi >> (8 * (vj - 4)))) & 0x7Fu;
-        vis_rows(see, vis);
-        uint32_t vlo = 0, vhi = 0;
-#pragma unroll
-        for (int vj = 0; vj < 7; vj++) { if (vj < 4) vlo |= vis[vj] << (8 * vj); else vhi |= vis[vj] << (8 * (vj - 4)); }
-        transpose8(vlo, vhi);                                      // byte vi = visibility of column vi, bit vj
-        const uint32_t vmine = (q & 2) ? vhi : vlo;                // columns 4..7 / 0..3
-        const uint32_t cvA = (vmine >> (16 * (q & 1))) & 0x7Fu, cvB = (vmine >> (16 * (q & 1) + 8)) & 0x7Fu;
-        if (q == 1) hiB = (hiB & 0xFF00FFFFu) | ((pose >> 24) << 16);   // view cell (3, 6): the agent's own cell shows what it carries
-        uint32_t oA[6], oB[6];
-        col_encode(loA, hiA, valid_b ? cvA : 0u, oA);
-        col_encode(loB, hiB, (valid_b && q < 3) ? cvB : 0u, oB);
-        // 21-byte records: record 7 el + vi; the word a record shares with its successor is completed with the successor's
-        // first word (the lane's own second column, or the next lane's first column: one shuffle)
-        const uint32_t nextA = BB_SHFL_DOWN(oA[0], 1);
-        if (q < 3) {
-            stage_record_words<21, 6>(tile, oA, 7 * el + 2 * q, oB[0]);
-            stage_record_words<21, 6>(tile, oB, 7 * el + 2 * q + 1, nextA);
-        } else stage_record_words<21, 6>(tile, oA, 7 * el + 6, nextA);
-        if (valid_b && q == 0 && dirs) dirs[(size_t)t * n + env0 + el] = (int8_t)dir;
-        // ================= the CTA's 32 observations leave as one tile =================
-        uint8_t *dst = obs + ((size_t)t * n + env0) * OBS_BYTES;
-        const bool bulk = nv == RC_ENVS && (((uintptr_t)dst) & 15) == 0;
-        if (bulk) BB_FENCE_ASYNC_SMEM();
+        // ---- barrier Y: the observers hold step t in registers: the stepper may go on ----
         BB_SYNCTHREADS();
-        if (bulk) {
-            if (tid == 0) { BB_BULK_STORE(dst, tile, RC_ENVS * OBS_BYTES); bulk_pending = true; }
-        } else {
-            const uint8_t *sb = reinterpret_cast<const uint8_t *>(tile);
-            for (int i = tid; i < nv * OBS_BYTES; i += RC_THREADS) dst[i] = sb[i];
-        }
     }
     if (tid == 0 && bulk_pending) BB_BULK_WAIT_READ();             // shared memory must outlive the copy engine's reads
     BB_SYNCTHREADS();
