@@ -20,6 +20,9 @@ def __getattr__(name):
     if name in ('DeviceParallelEnv', 'DeviceManyEnvs', 'ObssPreprocessor', 'FixedVocabulary', 'DictList', 'ObsBatch'):
         from . import learner
         return getattr(learner, name)
+    if name in ('DemoRecorder', 'episodes_to_demos'):
+        from . import demos
+        return getattr(demos, name)
     if name == 'gymapi':
         import importlib
         return importlib.import_module('.gymapi', __name__)
