@@ -17,7 +17,7 @@ def __getattr__(name):
                 'MODE_AUTORESET', 'MODE_FREEZE'):
         from . import vecenv
         return getattr(vecenv, name)
-    if name in ('DeviceParallelEnv', 'DeviceManyEnvs', 'ObssPreprocessor', 'FixedVocabulary', 'DictList', 'ObsBatch'):
+    if name in ('DeviceParallelEnv', 'DeviceManyEnvs', 'ObssPreprocessor', 'FixedVocabulary', 'ObsTensors', 'ObsBatch'):
         from . import learner
         return getattr(learner, name)
     if name in ('DemoRecorder', 'episodes_to_demos'):

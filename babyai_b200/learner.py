@@ -19,7 +19,7 @@ device.  Here
                       rollout (base.py:208-210: obss[i][j], env-major) -> one device gather.
   FixedVocabulary     utils/format.py:15-41 surface over the closed 32-word baby language
                       (levels.VOCAB); `save()` writes the `vocab.json` the reference reloads.
-  DictList            rl/utils/dictlist.py surface (attribute access, row indexing), restated.
+  ObsTensors          the (image, instr) pair the preprocessor returns, row-indexable; or the caller's `babyai.rl.DictList`.
 
 Items of an `ObsBatch` are `ObsRef`s: `ref['image']` / `ref['mission']` / `ref['direction']`
 materialise on the host on demand, so code that does look at single observations
@@ -35,20 +35,25 @@ from .levels import VOCAB, detokenize
 from .vecenv import MODE_AUTORESET, MODE_FREEZE, BabyAIVecEnv, _as_env_list, _spaces
 
 
-class DictList(dict):
-    """`d.key` is `d['key']`; `d[rows]` indexes every value (rl/utils/dictlist.py)."""
-    __getattr__ = dict.__getitem__
-    __setattr__ = dict.__setitem__
+class ObsTensors(object):
+    """What `ObssPreprocessor.__call__` returns when no container class is given: the two model inputs, row-indexable
+    together (`obs[rows].image`), which is all `ACModel.forward` (model.py) and `PPOAlgo.update_parameters`
+    (ppo.py: `sb = exps[inds + i]`) ask of `babyai.rl.DictList`.  Pass `dictlist=babyai.rl.DictList` to get the reference's
+    own type (INTEGRATION.md does)."""
+    __slots__ = ('image', 'instr')
+
+    def __init__(self, image=None, instr=None):
+        self.image, self.instr = image, instr
 
     def __len__(self):
-        return len(next(iter(dict.values(self))))
+        return len(self.image)
 
     def __getitem__(self, index):
-        return DictList({k: v[index] for k, v in dict.items(self)})
+        return ObsTensors(self.image[index], self.instr[index])
 
-    def __setitem__(self, index, d):
-        for k, v in d.items():
-            dict.__getitem__(self, k)[index] = v
+    def __setitem__(self, index, other):
+        self.image[index] = other.image
+        self.instr[index] = other.instr
 
 
 class FixedVocabulary(object):
@@ -252,11 +257,11 @@ class DeviceManyEnvs(DeviceParallelEnv):
 class ObssPreprocessor(object):
     """Drop-in for babyai.utils.format.ObssPreprocessor (format.py:100-119) over device-resident observations.
 
-    `dictlist` is the container class to return (pass `babyai.rl.DictList` to hand the reference its own type; the
-    restated one above has the same behaviour).  `trim=True` cuts the token tensor to the longest mission of the batch,
+    `dictlist` is the container class to return (pass `babyai.rl.DictList` to hand the reference its own type; the default
+    is ObsTensors, the image / instr pair with row indexing).  `trim=True` cuts the token tensor to the longest mission of the batch,
     as the reference pads (format.py:66-71); it costs one scalar device->host read."""
 
-    def __init__(self, vocab_path=None, dictlist=DictList, trim=True):
+    def __init__(self, vocab_path=None, dictlist=ObsTensors, trim=True):
         self.vocab = FixedVocabulary(vocab_path)
         self.obs_space = {'image': 147, 'instr': self.vocab.max_size}       # format.py:104-107
         self.dictlist = dictlist
