@@ -1746,14 +1746,13 @@ BB_HD void encode_view(const uint32_t R[14], uint32_t w[OBS_WORDS])
 // Visible <=> in bounds: no see-through flags, no transposes, no propagation -- the column windows with
 // out-of-grid cells zeroed.  (test_room_observation_equals_generic compares it with observe_generic for every pose.)
 template <class M>
-BB_HD void observe_room(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+BB_HD void observe_room_cells(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t R[14])
 {
     const ViewGeom v = view_geom(lp, ax, ay, dir);
     // cells from the agent to the wall it faces (inclusive): view depths vj >= 6 - dist are inside the grid
     const int dist = dir == 3 ? ay : dir == 1 ? lp.H - 1 - ay : dir == 0 ? lp.W - 1 - ax : ax;
     const uint32_t dm = dist >= 6 ? 0x7Fu : (0x7Fu << (6 - dist)) & 0x7Fu;
     const uint32_t mlo = expand4(dm), mhi = expand4(dm >> 4) & 0x00FFFFFFu;
-    uint32_t R[14];
 #pragma unroll
     for (int vi = 0; vi < 7; vi++) {
         const int row = v.c_row + v.rstep * (vi - 3);
@@ -1767,15 +1766,20 @@ BB_HD void observe_room(const LevelParams &lp, const M &mem, int ax, int ay, int
         R[2 * vi + 1] = byte_perm(a, b, v.sel_hi) & mhi;
     }
     R[7] = (R[7] & 0xFF00FFFFu) | ((uint32_t)carry_cell << 16);        // the agent's own cell shows what it carries
+}
+template <class M>
+BB_HD void observe_room(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+{
+    uint32_t R[14];
+    observe_room_cells(lp, mem, ax, ay, dir, carry_cell, R);
     encode_view(R, w);
 }
 
 // Writes the 147 observation bytes as 37 little-endian words (last byte 0): one lane does all columns.
 template <class M>
-BB_HD void observe_generic(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+BB_HD void observe_generic_cells(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t R[14])
 {
-    const ViewGeom v = view_geom(lp, ax, ay, dir);
-    uint32_t R[14];                              // R[2 vi] = cells vj 0..3, R[2 vi + 1] = cells vj 4..6 (+1 unused byte)
+    const ViewGeom v = view_geom(lp, ax, ay, dir);          // R[2 vi] = cells vj 0..3, R[2 vi + 1] = cells vj 4..6 (+1 unused byte)
 #pragma unroll
     for (int vi = 0; vi < 7; vi++) col_load(mem, v, vi, R[2 * vi], R[2 * vi + 1]);
     // see-through bits: per column (bit vj), then transposed to per row (bit vi)
@@ -1802,8 +1806,22 @@ BB_HD void observe_generic(const LevelParams &lp, const M &mem, int ax, int ay, 
         R[2 * vi] &= expand4(cv);
         R[2 * vi + 1] &= expand4(cv >> 4);       // also clears the unused fourth byte
     }
+}
+template <class M>
+BB_HD void observe_generic(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
+{
+    uint32_t R[14];
+    observe_generic_cells(lp, mem, ax, ay, dir, carry_cell, R);
     encode_view(R, w);
 }
+// the 49 masked view cells of an observation (what encode_view / encode_stage_view expand to bytes)
+template <class M>
+BB_HD void observe_cells(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t R[14])
+{
+    if (lp.num_rows == 1 && lp.num_cols == 1) observe_room_cells(lp, mem, ax, ay, dir, carry_cell, R);
+    else observe_generic_cells(lp, mem, ax, ay, dir, carry_cell, R);
+}
+
 
 template <class M>
 BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
@@ -1901,6 +1919,57 @@ BB_HD void stage_obs_words(uint32_t *tile, const uint32_t w[OBS_WORDS], int lane
     }
 }
 
+
+// encode_view + stage_obs_words in one pass, for callers that hold the 49 masked cells R[14] and want the lane's 147 bytes
+// in the warp tile without ever keeping the 37 output words alive (the pipelined rollout kernel's observer warps run at
+// 56 registers): the words are produced four cells at a time and leave through the funnel shift one by one.
+// first_word(R) = word 0 of the lane's observation (the caller shuffles it to the previous lane as that lane's next_w0).
+BB_HD uint32_t encode_first_word(const uint32_t R[14])
+{
+    uint32_t o0, o1, o2;
+    encode4(R[0], o0, o1, o2);
+    return o0;
+}
+BB_HD void encode_stage_view(uint32_t *tile, const uint32_t R[14], int lane, uint32_t next_w0)
+{
+    const int D = OBS_BYTES * lane;
+    const int sh = D & 3, wb = D >> 2;
+    const int kl = (sh + OBS_BYTES - 1) >> 2;                 // word holding this lane's last byte
+    const int nvalid = ((sh + OBS_BYTES - 1) & 3) + 1;        // this lane's bytes in that word
+    const int s8 = 8 * sh;
+    uint32_t prev = 0;
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+        uint32_t sel = 0; int ra = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = 4 * k + i;
+            const int vi = q / 7, vj = q % 7;
+            const int r = 2 * vi + (vj >= 4 ? 1 : 0), byte = vj >= 4 ? vj - 4 : vj;
+            if (q >= 49) { sel |= 3u << (4 * i); continue; }          // byte 3 of R[13] is zero
+            if (ra < 0) ra = r;
+            sel |= (uint32_t)(r == ra ? byte : 4 + byte) << (4 * i);
+        }
+        const uint32_t c = byte_perm(R[ra], ra + 1 < 14 ? R[ra + 1] : 0u, sel);
+        uint32_t o[3];
+        encode4(c, o[0], o[1], o[2]);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int wk = 3 * k + j;                                 // output word index 0..36 (k = 12: word 36 only)
+            if (wk >= OBS_WORDS) continue;
+            uint32_t v = funnel_l(prev, o[j], s8);
+            prev = o[j];
+            if (wk == 0 && sh != 0) continue;                         // first word belongs to the previous lane
+            if (wk == kl && nvalid < 4) v |= next_w0 << (8 * nvalid);
+            tile[wb + wk] = v;                                        // wk <= 36 <= kl always
+        }
+    }
+    if (kl == OBS_WORDS) {                                            // the tail word (lanes whose bytes spill into a 38th word)
+        uint32_t v = funnel_l(prev, 0u, s8);
+        if (nvalid < 4) v |= next_w0 << (8 * nvalid);
+        tile[wb + OBS_WORDS] = v;
+    }
+}
 
 // Same idea for records of LBYTES bytes held in NW words (bytes beyond LBYTES must be zero):
 // record number q of the tile starts at byte LBYTES * q; next_w0 = first word of record q + 1.

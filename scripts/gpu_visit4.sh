@@ -16,12 +16,16 @@ for b in 1 4; do
 done
 echo "== BossLevel BB_GEN_CONCURRENT=0" >> $OUT/multiroom_$TAG.log
 ( BB_GEN_CONCURRENT=0 timeout 200 python bench.py --brief --level BossLevel --envs 32768 --steps 2000 --warmup 200 ) >> $OUT/multiroom_$TAG.log 2>&1
+for pp in 0 1; do for lv in GoToLocal PickupLoc GoToObjS4; do
+  echo "== $lv BB_ROLLOUT_PIPE=$pp" >> $OUT/multiroom_$TAG.log
+  ( BB_ROLLOUT_PIPE=$pp timeout 200 python bench.py --brief --level $lv --steps 2000 --warmup 200 ) >> $OUT/multiroom_$TAG.log 2>&1
+done; done
 echo "== GoToLocal BB_ROLLOUT_KERNEL=cta" >> $OUT/multiroom_$TAG.log
 ( BB_ROLLOUT_KERNEL=cta timeout 200 python bench.py --brief --steps 2000 --warmup 200 ) >> $OUT/multiroom_$TAG.log 2>&1
 ( timeout 600 python bench.py ) > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 ( timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_rollout_cta" -s 8 -c 1 \
     -o $OUT/prof_boss_$TAG -f python bench.py --brief --level BossLevel --envs 32768 --steps 200 --warmup 40 ) > $OUT/ncu_boss_$TAG.log 2>&1
-( timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_rollout -s 3 -c 1 \
+( timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_rollout_pipe -s 3 -c 1 \
     -o $OUT/prof_rollout_$TAG -f python bench.py --brief --steps 200 --warmup 40 ) > $OUT/ncu_rollout_$TAG.log 2>&1
 # launch list of the default bench command (shares only)
 ( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 500 --csv \

@@ -187,9 +187,10 @@ def test_column_record_staging_packs_21_byte_records():
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize('kernel', ['lane', 'pipe'])
 @pytest.mark.parametrize('level,n,T', [('GoToLocal', 40, 40), ('PickupLoc', 35, 40), ('GoToObjS4', 16, 40), ('PutNextLocal', 24, 32),
                                         ('GoToObjMazeS4R2', 21, 40), ('BossLevel', 18, 16), ('Unlock', 20, 24)])
-def test_rollout_stepping_role_on_threads(level, n, T):
+def test_rollout_stepping_role_on_threads(level, n, T, kernel):
     """k_rollout's stepping role (babyai_b200/csrc/rollout_lane.cuh: the very function the kernel calls) executed with one OS
     thread per lane and the warp shuffles / votes / barriers as rendezvous: whole rollouts -- step, warp-cooperative level
     swap-in from the ring, observation, tile staging, (bulk) tile stores, state write-back, counters -- must equal the
@@ -202,7 +203,7 @@ def test_rollout_stepping_role_on_threads(level, n, T):
     steps = episodes = 0
     for rep in range(5 if level == 'PutNextLocal' else 3):             # PutNextLocal: max_steps = 128
         acts = rng.choice(7, size=(T, n), p=[0.13, 0.13, 0.4, 0.12, 0.08, 0.12, 0.02]).astype(np.int8)
-        obs, rew, done, dirs, cnt = r2.rollout(acts)
+        obs, rew, done, dirs, cnt = r2.rollout(acts, kernel=kernel)
         for t in range(T):
             o, r, d = ref.step(acts[t])
             assert np.array_equal(obs[t], o), (level, rep, t, np.nonzero((obs[t] != o).reshape(n, -1).any(1))[0])
@@ -254,8 +255,9 @@ def test_rollout_cta_role_on_threads(level, n, T, mode):
 
 
 @pytest.mark.timeout(300)
-def test_rollout_stepping_role_freeze_mode():
-    """ManyEnvs flavour in k_rollout: finished envs freeze and replay their terminal result (evaluate.py:72-78)."""
+@pytest.mark.parametrize('kernel', ['lane', 'pipe'])
+def test_rollout_stepping_role_freeze_mode(kernel):
+    """ManyEnvs flavour in k_rollout / k_rollout_pipe: finished envs freeze and replay their terminal result (evaluate.py:72-78)."""
     level, n, T = 'GoToLocal', 20, 40
     seeds = np.arange(n, dtype=np.uint64) + 10 ** 9
     ref = _emu(level, n, seeds, mode=1)
@@ -264,7 +266,7 @@ def test_rollout_stepping_role_freeze_mode():
     rng = np.random.RandomState(3)
     for rep in range(2):                                  # max_steps = 64: everything is frozen during the second rollout
         acts = rng.randint(0, 7, (T, n)).astype(np.int8)
-        obs, rew, done, dirs, cnt = r2.rollout(acts)
+        obs, rew, done, dirs, cnt = r2.rollout(acts, kernel=kernel)
         for t in range(T):
             o, r, d = ref.step(acts[t])
             assert np.array_equal(obs[t], o) and np.array_equal(rew[t].view(np.uint32), r.view(np.uint32)) and np.array_equal(done[t], d), (rep, t)
@@ -274,7 +276,8 @@ def test_rollout_stepping_role_freeze_mode():
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize('level,n,T,rounds,min_active', [('GoToLocal', 100, 16, 1 << 20, 0), ('PickupLoc', 70, 16, 2, 16), ('GoToObjS4', 64, 16, 1, 0),
                                                          ('GoToRedBallGrey', 90, 12, 3, 8)])
-def test_rollout_fused_cta_on_threads(level, n, T, rounds, min_active):
+@pytest.mark.parametrize('kernel', ['lane', 'pipe'])
+def test_rollout_fused_cta_on_threads(level, n, T, rounds, min_active, kernel):
     """A whole fused CTA of k_rollout on threads: two stepping warps + the generator warp (rollout_gen_warp driving
     gen_small_round -- the round function of k_gen_small too) behind one __syncthreads.  Nothing
     but the generator warps refills the rings over 14 launches, with small round budgets and the sparse-warp rule switched
@@ -287,7 +290,7 @@ def test_rollout_fused_cta_on_threads(level, n, T, rounds, min_active):
     steps = episodes = 0
     for rep in range(14):
         acts = rng.choice(7, size=(T, n), p=[0.13, 0.13, 0.4, 0.12, 0.08, 0.12, 0.02]).astype(np.int8)
-        obs, rew, done, dirs, cnt = r2.rollout(acts, fused=True, gen_rounds=rounds, gen_min_active=min_active)
+        obs, rew, done, dirs, cnt = r2.rollout(acts, fused=True, gen_rounds=rounds, gen_min_active=min_active, kernel=kernel)
         for t in range(T):
             o, r, d = ref.step(acts[t])
             assert np.array_equal(obs[t], o) and np.array_equal(rew[t].view(np.uint32), r.view(np.uint32)) and np.array_equal(done[t], d), (level, rep, t)
