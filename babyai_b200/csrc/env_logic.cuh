@@ -80,6 +80,7 @@ struct LevelParams {
     int32_t n_action_kinds, action_kinds[4];
     int32_t n_instr_kinds, instr_kinds[3];
     int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
+    int32_t strict_mask, done_actions;   // verifier modes (see verify_action / verify_leaf)
     int32_t obj_words;            // ceil(most object-table entries a level of this family uses / 4): words of the packed x / y arrays in use
     int32_t rs_g, rs_t, gt_off;   // grid bytes of one env: G = H rows x rs_g at 0, GT = W rows x rs_t at gt_off
     uint64_t locked_thr;          // rand_float(0,1) < p  <=>  u32 < ceil(p * 2^32)
@@ -109,7 +110,7 @@ struct BB_ALIGN16 InstrRec {
     uint8_t leaf_kind[4];         // leaves 0,1 = side A; 2,3 = side B
     uint8_t leaf_pre[4];          // preCarrying (verifier.py:325,373)
     uint8_t root_kind;            // R_SINGLE / R_BEFORE / R_AFTER
-    uint8_t side_and;             // bit 0: side A is an AndInstr, bit 1: side B
+    uint8_t side_and;             // bit 0: side A is an AndInstr, bit 1: side B; bits 4-7: lastStepMatch of leaf 0-3 (done-action mode)
     uint8_t flags;                // 'success' latches: 0 root.a 1 root.b 2 A.a 3 A.b 4 B.a 5 B.b
     uint8_t pad0;
     uint32_t pad1;
@@ -1350,6 +1351,7 @@ struct GlobalMem {
     BB_HD void set_leaf_pre(int l, int v) { ins->leaf_pre[l] = (uint8_t)v; }
     BB_HD int root_kind() const { return ins->root_kind; }
     BB_HD int side_and() const { return ins->side_and; }
+    BB_HD void set_side_and(int v) { ins->side_and = (uint8_t)v; }
     BB_HD int flags() const { return ins->flags; }
     BB_HD void set_flags(int v) { ins->flags = (uint8_t)v; }
 };
@@ -1380,22 +1382,31 @@ struct StepCtx {            // what a leaf verifier looks at after the action wa
     int fcell;              // the cell at front_pos after the action
 };
 
+// ---- the verifier.  Results are tri-state like the reference's 'continue' / 'success' / 'failure' strings ----
+enum : int { V_CONT = 0, V_SUCC = 1, V_FAIL = 2 };
+// LevelParams::strict_mask: bit l = leaf l was built with strict=True (OpenInstr / PickupInstr / PutNextInstr of the "Debug"
+// bonus levels), bit 4 = the root Before / After is strict.  LevelParams::done_actions = the reference's BABYAI_DONE_ACTIONS
+// mode (verifier.py:15-17): an ActionInstr only reports through the `done` action (lastStepMatch).
+
 // ActionInstr.verify_action: Open :257-274, GoTo :296-303, Pickup :330-350, PutNext :393-417.
 // Written branch-light: the four kinds are evaluated as predicates and selected by kind, so that the lanes of a warp
 // (one env each, all with different instructions) run ONE instruction stream (round 1's if-chain per kind, nested in the
 // side / root recursion, ran at 3.6 active lanes: ncu r02c).  Only PutNext's neighbourhood test is a loop, and it runs only
 // on the step where a matching object was just dropped.
 template <class M>
-BB_HD bool verify_leaf(M &mem, int leaf, const StepCtx &s)
+BB_HD int verify_action(M &mem, int leaf, const StepCtx &s)
 {
     const int kind = mem.leaf_kind(leaf);
     const uint32_t set = mem.desc_mask(2 * leaf);
     const int pre = mem.leaf_pre(leaf);
+    const bool strict = ((mem.lp.strict_mask >> leaf) & 1) != 0;
     if (kind == I_PICKUP || kind == I_PUTNEXT) mem.set_leaf_pre(leaf, s.carry);       // preCarrying, refreshed on every evaluation
     const bool goto_ok = (set & s.snap_mask & s.at) != 0;                             // some pos in obj_poss is front_pos
     // the toggled cell must be a door of the set, and open: at most one object is ON a cell
-    const bool open_ok = s.action == A_TOGGLE && (s.fcell & 0xC7) == T_DOOR && (set & s.cur_mask & s.at) != 0;
-    const bool pick_ok = s.action == A_PICKUP && pre == NO_OBJ && s.carry < MAXOBJ && ((set >> (s.carry & 31)) & 1u);     // (untracked objects, KIND_UNLOCK, are in no set)
+    const bool toggled_door = s.action == A_TOGGLE && (s.fcell & 7) == T_DOOR;
+    const bool open_ok = toggled_door && (s.fcell >> 6) == 0 && (set & s.cur_mask & s.at) != 0;
+    const bool picked = s.action == A_PICKUP && s.carry != NO_OBJ;                    // (carrying something after a pickup action)
+    const bool pick_ok = picked && pre == NO_OBJ && s.carry < MAXOBJ && ((set >> (s.carry & 31)) & 1u);   // (untracked objects are in no set)
     bool put_ok = false;
     if (kind == I_PUTNEXT && s.action == A_DROP && pre < MAXOBJ && ((set >> (pre & 31)) & 1u) && s.carry != pre) {
         const int ax = mem.ox(pre), ay = mem.oy(pre);      // (a carried object that was not dropped: cur_pos == (-1, -1), excluded above)
@@ -1404,42 +1415,70 @@ BB_HD bool verify_leaf(M &mem, int leaf, const StepCtx &s)
             if (iabs(ax - mem.ox(k)) + iabs(ay - mem.oy(k)) == 1) put_ok = true;
         }
     }
-    return kind == I_GOTO ? goto_ok : kind == I_OPEN ? open_ok : kind == I_PICKUP ? pick_ok : put_ok;
+    const bool ok = kind == I_GOTO ? goto_ok : kind == I_OPEN ? open_ok : kind == I_PICKUP ? pick_ok : put_ok;
+    // strict mode (verifier.py:269-272, 343-346, 398-401): the wrong door toggled / any object picked up is a failure;
+    // PutNext tests it BEFORE it looks at the drop, Open and Pickup after their success test
+    const bool bad = kind == I_OPEN ? toggled_door : kind == I_GOTO ? false : picked;
+    if (strict && kind == I_PUTNEXT && bad) return V_FAIL;
+    if (ok) return V_SUCC;
+    return strict && bad ? V_FAIL : V_CONT;
 }
 
-// one side: an ActionInstr, or AndInstr.verify (verifier.py:536-550): each unfinished half is evaluated every step
+// ActionInstr.verify :211-231: with done actions the instruction only reports when the agent says `done`
 template <class M>
-BB_HD bool verify_side(M &mem, int side, const StepCtx &s)
+BB_HD int verify_leaf(M &mem, int leaf, const StepCtx &s)
+{
+    if (!mem.lp.done_actions) return verify_action(mem, leaf, s);
+    const int bit = 0x10 << leaf;                              // lastStepMatch of leaf l: bit 4 + l of the side_and byte
+    if (s.action == A_DONE) return (mem.side_and() & bit) ? V_SUCC : V_FAIL;
+    const int res = verify_action(mem, leaf, s);
+    const int sa = mem.side_and();
+    const int ns = res == V_SUCC ? (sa | bit) : (sa & ~bit);
+    if (ns != sa) mem.set_side_and(ns);
+    return V_CONT;                                             // (the reference falls off the end: None)
+}
+
+// one side: an ActionInstr, or AndInstr.verify (verifier.py:536-550): each unfinished half is evaluated every step; a
+// half's 'failure' is not passed on (the `action is done` test of :544 never holds for the integer actions a vectorised
+// env is stepped with)
+template <class M>
+BB_HD int verify_side(M &mem, int side, const StepCtx &s)
 {
     const bool is_and = ((mem.side_and() >> side) & 1) != 0;
     const int ba = 2 + 2 * side, bb_ = 3 + 2 * side;
     int fl = mem.flags();
     const bool a_latched = is_and && ((fl >> ba) & 1);
     const bool b_latched = ((fl >> bb_) & 1) != 0;
-    bool r0 = true;
+    int r0 = V_SUCC;
     if (!a_latched) r0 = verify_leaf(mem, 2 * side, s);
     if (!is_and) return r0;
-    if (!a_latched && r0) fl |= 1 << ba;
-    if (!b_latched && verify_leaf(mem, 2 * side + 1, s)) fl |= 1 << bb_;
+    if (!a_latched && r0 == V_SUCC) fl |= 1 << ba;
+    if (!b_latched && verify_leaf(mem, 2 * side + 1, s) == V_SUCC) fl |= 1 << bb_;
     if (fl != mem.flags()) mem.set_flags(fl);
-    return ((fl >> ba) & 1) && ((fl >> bb_) & 1);
+    return (((fl >> ba) & 1) && ((fl >> bb_) & 1)) ? V_SUCC : V_CONT;
 }
 
 // BeforeInstr.verify :449-471, AfterInstr.verify :490-512 (hand-over re-verifies the same action)
 template <class M>
-BB_HD bool verify_root(M &mem, const StepCtx &s)
+BB_HD int verify_root(M &mem, const StepCtx &s)
 {
     const int rk = mem.root_kind();
     const int first = rk == R_AFTER ? 1 : 0, second = 1 - first;
     const bool first_done = rk != R_SINGLE && ((mem.flags() >> first) & 1);
-    bool ok = true;
-    if (!first_done) ok = verify_side(mem, first, s);
-    if (rk == R_SINGLE || !ok) return ok;
+    int r = V_SUCC;
+    if (!first_done) r = verify_side(mem, first, s);
+    if (rk == R_SINGLE) return r;
+    if (r == V_FAIL) return V_FAIL;
+    if (r == V_CONT) {
+        // strict Before / After (:466-469, 507-509): finishing the other instruction first is a failure
+        if ((mem.lp.strict_mask & 0x10) && verify_side(mem, second, s) == V_SUCC) return V_FAIL;
+        return V_CONT;
+    }
     if (!first_done) mem.set_flags(mem.flags() | (1 << first));
     return verify_side(mem, second, s);
 }
 
-struct StepResult { bool done; bool success; float reward; };
+struct StepResult { bool done; bool success; float reward; };      // done: success, failure (strict / done-action modes) or time-out
 
 // Applies one action to the live state of one env.  `h` is the env's hot record
 // held in registers by the caller (written back by the caller).
@@ -1511,8 +1550,10 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
     s.action = action; s.fx = nfx; s.fy = nfy; s.carry = carry;
     s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.at = at;
     s.fcell = mem.cell(nfx, nfy);
-    r.success = verify_root(mem, s);
+    const int status = verify_root(mem, s);
+    r.success = status == V_SUCC;
     r.reward = 0.0f;
+    if (status == V_FAIL) r.done = true;                  // RoomGridLevel.step: 'failure' ends the episode with reward 0
     if (r.success) {
         r.done = true;
         // _reward(): 1 - 0.9 * (step_count / max_steps) in float64, no fused multiply-add

@@ -20,6 +20,7 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
     lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
     lp->all_unique = s->all_unique; lp->require_unreachable = s->require_unreachable;
+    lp->strict_mask = s->strict_mask & 0x1F; lp->done_actions = s->done_actions ? 1 : 0;
     if (s->kind == BB_KIND_OBJ && (s->instr < BB_I_GOTO || s->instr > BB_I_PUTNEXT)) return "bad instruction kind";
     if (s->kind == BB_KIND_OBJ && s->instr == BB_I_PUTNEXT && s->num_dists < 2) return "PutNext needs two objects";
     lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;

@@ -113,6 +113,7 @@ struct StagedMem {
     __device__ __forceinline__ void set_leaf_pre(int l, int v) { si->leaf_pre[l] = (uint8_t)v; ins->leaf_pre[l] = (uint8_t)v; }
     __device__ __forceinline__ int root_kind() const { return si->root_kind; }
     __device__ __forceinline__ int side_and() const { return si->side_and; }
+    __device__ __forceinline__ void set_side_and(int v) { si->side_and = (uint8_t)v; ins->side_and = (uint8_t)v; }
     __device__ __forceinline__ int flags() const { return si->flags; }
     __device__ __forceinline__ void set_flags(int v) { si->flags = (uint8_t)v; ins->flags = (uint8_t)v; }
 };
@@ -388,6 +389,7 @@ struct SmemOnlyMem {            // lane-private records in shared memory (byte a
     __device__ __forceinline__ void set_leaf_pre(int l, int v) { i[36 + l] = (uint8_t)v; }
     __device__ __forceinline__ int root_kind() const { return i[40]; }
     __device__ __forceinline__ int side_and() const { return i[41]; }
+    __device__ __forceinline__ void set_side_and(int v) { i[41] = (uint8_t)v; }
     __device__ __forceinline__ int flags() const { return i[42]; }
     __device__ __forceinline__ void set_flags(int v) { i[42] = (uint8_t)v; }
 };

@@ -60,6 +60,7 @@ struct SmemGMem {
     BB_HD void set_leaf_pre(int l, int v) { i[36 + l] = (uint8_t)v; }
     BB_HD int root_kind() const { return i[40]; }
     BB_HD int side_and() const { return i[41]; }
+    BB_HD void set_side_and(int v) { i[41] = (uint8_t)v; }
     BB_HD int flags() const { return i[42]; }
     BB_HD void set_flags(int v) { i[42] = (uint8_t)v; }
 };

@@ -14,6 +14,7 @@ mirrors.  Five generator families cover all 47 ICLR-19 levels:
              (:554-633), MiniBossLevel (:636), BossLevel (:648), BossLevelNoUnlock (:655)
 """
 import ctypes as C
+import os
 
 KIND_REDBALL, KIND_OBJ, KIND_LEVELGEN, KIND_IMPUNLOCK, KIND_UNLOCK = 0, 1, 2, 3, 4
 I_GOTO, I_PICKUP, I_OPEN, I_PUTNEXT = 0, 1, 2, 3
@@ -30,12 +31,13 @@ class LevelSpec(C.Structure):
         ('n_action_kinds', C.c_int32), ('action_kinds', C.c_int32 * 4),
         ('n_instr_kinds', C.c_int32), ('instr_kinds', C.c_int32 * 3),
         ('all_unique', C.c_int32), ('require_unreachable', C.c_int32),
+        ('strict_mask', C.c_int32), ('done_actions', C.c_int32),
     ]
 
 
 def _spec(kind, room_size=8, num_rows=1, num_cols=1, num_dists=0, instr=I_GOTO, doors_open=0, grey_dists=0,
           locked_room_prob=0.0, locations=0, unblocking=0, implicit_unlock=1, action_kinds=(), instr_kinds=(),
-          all_unique=0, require_unreachable=0):
+          all_unique=0, require_unreachable=0, strict_mask=0):
     s = LevelSpec()
     s.kind, s.room_size, s.num_rows, s.num_cols, s.num_dists = kind, room_size, num_rows, num_cols, num_dists
     s.instr, s.doors_open, s.grey_dists = instr, doors_open, grey_dists
@@ -48,6 +50,9 @@ def _spec(kind, room_size=8, num_rows=1, num_cols=1, num_dists=0, instr=I_GOTO, 
     for i, a in enumerate(instr_kinds):
         s.instr_kinds[i] = a
     s.all_unique, s.require_unreachable = all_unique, require_unreachable
+    s.strict_mask = strict_mask
+    # verifier.use_done_actions is read from the environment when babyai.levels.verifier is imported (verifier.py:15-17)
+    s.done_actions = 1 if os.environ.get('BABYAI_DONE_ACTIONS', False) else 0
     return s
 
 

@@ -60,6 +60,9 @@ typedef struct bb_level_spec {
     int32_t n_instr_kinds;  int32_t instr_kinds[3];
     int32_t all_unique;         /* BB_KIND_OBJ: add_distractors(all_unique=...) (Level_PutNextLocal)        */
     int32_t require_unreachable;/* BB_KIND_OBJ: Level_UnblockPickup rejects levels whose objects are all reachable */
+    /* verifier modes (babyai/levels/verifier.py) */
+    int32_t strict_mask;        /* bit l: leaf instruction l is built with strict=True (:255, :323, :369); bit 4: the Before / After root is (:430) */
+    int32_t done_actions;       /* verifier.use_done_actions (BABYAI_DONE_ACTIONS, :15-17): instructions report through the `done` action */
 } bb_level_spec;
 
 typedef struct bb_pool bb_pool;

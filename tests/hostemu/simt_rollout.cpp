@@ -113,6 +113,7 @@ struct HostSmemMem {
     void set_leaf_pre(int l, int v) { i[36 + l] = (uint8_t)v; }
     int root_kind() const { return i[40]; }
     int side_and() const { return i[41]; }
+    void set_side_and(int v) { i[41] = (uint8_t)v; }
     int flags() const { return i[42]; }
     void set_flags(int v) { i[42] = (uint8_t)v; }
 };

@@ -36,7 +36,7 @@ def test_vocab_matches_library():
 
 
 def test_level_spec_layout_matches_header():
-    assert C.sizeof(LevelSpec) == 96          # 8 int32, double, 3 int32, 1+4 int32, 1+3 int32, 2 int32
+    assert C.sizeof(LevelSpec) == 104         # 8 int32, double, 3 int32, 1+4 int32, 1+3 int32, 2 int32, 2 int32 (verifier modes)
     assert LevelSpec.locked_room_prob.offset == 32
     for name in LEVELS:
         s = level_spec(name)
