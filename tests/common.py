@@ -7,8 +7,10 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CONFIG_LEVELS = ['GoToRedBall', 'GoToLocal', 'PickupLoc', 'GoTo', 'BossLevel']
-GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('succ_', 'rgb_')))      # all 47 served levels (CPU replays)
+GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('succ_', 'rgb_', 'done_')))      # all 47 served levels (CPU replays)
 # success-heavy reference traces (97 % bot actions, >= 50 successful episodes each; make_golden.py --success): 'succ_<Level>'
+# reference traces generated with BABYAI_DONE_ACTIONS=1 (verifier.use_done_actions; make_golden.py --done-actions): 'done_<Level>'
+DONE_GOLDENS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and f.startswith('done_'))
 SUCCESS_GOLDENS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and f.startswith('succ_'))
 # the traces the CUDA pool replays in the GPU suite (the other 26 files were added at the very end of round 1, after the
 # last GPU visit: they are replayed by the oracle and by the host build of the kernel logic; GPU replay from round 2 on)
@@ -28,7 +30,7 @@ def replay_golden(level, make_pool, get_mission):
     """make_pool(level, n, seeds) -> object with reset() -> obs[n,7,7,3], step(a) -> (obs, reward, done),
     .direction; get_mission(pool, i) -> str.  All K traces are run as ONE pool of K envs."""
     g = load_golden(level)
-    if level.startswith('succ_'):
+    if level.startswith(('succ_', 'done_')):
         level = level[5:]
     K, T = g['actions'].shape
     pool = make_pool(level, K, g['seeds'])

@@ -9,6 +9,7 @@ Per level: K traces of T steps.  Actions are 75 % reference-bot (babyai/bot.py)
 toggle / PutNext / Before / After paths of the verifier are exercised.
 
 usage: python tests/golden/make_golden.py [--only-missing] [--success]
+       BABYAI_DONE_ACTIONS=1 python tests/golden/make_golden.py --done-actions
 """
 import json
 import os
@@ -26,7 +27,7 @@ OTHER_LEVELS = ['GoToRedBallGrey', 'GoToObjMazeS4R2', 'GoToOpen', 'Pickup', 'GoT
                 'MiniBossLevel', 'BossLevelNoUnlock', 'Open', 'PutNext', 'PutNextLocal', 'PutNextLocalS5N3', 'UnblockPickup']
 
 
-def trace(level, seed, T, act_seed, p_bot=0.75):
+def trace(level, seed, T, act_seed, p_bot=0.75, p_done=0.0):
     env = refenv.make_env(level, seed, 'philox')
     from babyai.bot import Bot
     rng = np.random.RandomState(act_seed)
@@ -42,7 +43,9 @@ def trace(level, seed, T, act_seed, p_bot=0.75):
     Q = np.zeros(T, np.int8)
     for t in range(T):
         a = None
-        if bot is not None and rng.rand() < p_bot:
+        if p_done and rng.rand() < p_done:
+            a = 6                 # the `done` action: how an instruction reports in BABYAI_DONE_ACTIONS mode
+        if a is None and bot is not None and rng.rand() < p_bot:
             try:
                 a = int(bot.replan(last))
             except Exception:
@@ -105,9 +108,30 @@ def main_success():
               % (level, K, T, eps, succ, os.path.basename(out), os.path.getsize(out) // 1024), flush=True)
 
 
+# verifier.use_done_actions (BABYAI_DONE_ACTIONS=1, read when babyai.levels.verifier is imported): the instructions only
+# report through the `done` action -- 'success' if the previous action completed them, 'failure' otherwise
+DONE_LEVELS = {'GoToLocal': (6, 500), 'PickupLoc': (6, 400), 'PutNextLocal': (6, 600), 'GoToSeqS5R2': (6, 700), 'SynthS5R2': (6, 700),
+               'MiniBossLevel': (6, 800), 'Open': (4, 600)}
+
+
+def main_done():
+    assert os.environ.get('BABYAI_DONE_ACTIONS'), 'run with BABYAI_DONE_ACTIONS=1'
+    for level, (K, T) in DONE_LEVELS.items():
+        out = os.path.join(HERE, 'done_' + level + '.npz')
+        seeds = [9000 + 13 * k for k in range(K)]
+        tr = [trace(level, s, T, act_seed=300 + k, p_bot=0.8, p_done=0.10) for k, s in enumerate(seeds)]
+        save(out, seeds, tr)
+        eps = sum(int(t['done'].sum()) for t in tr)
+        succ = sum(int((t['reward'] > 0).sum()) for t in tr)
+        print('%20s  %d traces x %d steps, %d episodes (%d successes) -> %s (%d KB)'
+              % (level, K, T, eps, succ, os.path.basename(out), os.path.getsize(out) // 1024), flush=True)
+
+
 def main():
     if '--success' in sys.argv:
         return main_success()
+    if '--done-actions' in sys.argv:
+        return main_done()
     only_missing = '--only-missing' in sys.argv
     for level in CONFIG_LEVELS + OTHER_LEVELS + MORE_LEVELS:
         if only_missing and os.path.exists(os.path.join(HERE, level + '.npz')):

@@ -213,3 +213,4 @@ void he_stage21(const uint32_t *w /* [28][6] */, uint8_t *tile)
 }
 
 }  // extern "C"
+extern "C" int he_verifier_modes(HPool *p) { return p->lp.strict_mask | (p->lp.done_actions << 8); }
