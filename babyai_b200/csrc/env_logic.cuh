@@ -40,7 +40,11 @@ namespace bb {
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_DOOR = 4, T_KEY = 5, T_BALL = 6, T_BOX = 7 };
 enum : int { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5 };
 enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
-enum : int { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3, KIND_UNLOCK = 4 };
+enum : int { KIND_REDBALL = 0, KIND_OBJ = 1, KIND_LEVELGEN = 2, KIND_IMPUNLOCK = 3, KIND_UNLOCK = 4, KIND_BONUS = 5 };
+// KIND_BONUS: the gen_mission of babyai/levels/bonus_levels.py, selected by LevelParams::bonus (bonus_a / bonus_b: its arguments)
+enum : int { BN_GOTO_REDBLUE = 1, BN_OPEN_RED_DOOR, BN_OPEN_DOOR, BN_GOTO_DOOR, BN_GOTO_OBJ_DOOR, BN_ACTION_OBJ_DOOR, BN_UNLOCK_LOCAL,
+             BN_KEY_IN_BOX, BN_UNLOCK_PICKUP, BN_BLOCKED_UNLOCK_PICKUP, BN_UNLOCK_TO_UNLOCK, BN_PICKUP_DIST, BN_PICKUP_ABOVE,
+             BN_OPEN_TWO_DOORS, BN_FIND_OBJ, BN_KEY_CORRIDOR, BN_ONE_ROOM, BN_PUTNEXT, BN_MOVE_TWO_ACROSS, BN_OPEN_DOORS_ORDER };
 enum : int { I_GOTO = 0, I_PICKUP = 1, I_OPEN = 2, I_PUTNEXT = 3, I_NONE = 0xFF };
 enum : int { K_ACTION = 0, K_AND = 1, K_SEQ = 2 };
 enum : int { R_SINGLE = 0, R_BEFORE = 1, R_AFTER = 2 };
@@ -81,6 +85,8 @@ struct LevelParams {
     int32_t n_instr_kinds, instr_kinds[3];
     int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
     int32_t strict_mask, done_actions;   // verifier modes (see verify_action / verify_leaf)
+    int32_t bonus, bonus_a, bonus_b;     // KIND_BONUS: which bonus_levels.py family and its constructor arguments
+    int32_t box_contains;                // box object id + 1 whose contents is the NEXT table entry (Level_KeyInBox), else 0
     int32_t obj_words;            // ceil(most object-table entries a level of this family uses / 4): words of the packed x / y arrays in use
     int32_t rs_g, rs_t, gt_off;   // grid bytes of one env: G = H rows x rs_g at 0, GT = W rows x rs_t at gt_off
     uint64_t locked_thr;          // rand_float(0,1) < p  <=>  u32 < ceil(p * 2^32)
@@ -246,6 +252,7 @@ struct LevelOut {           // where one generated level is written (live or spa
 struct GenMem {
     uint32_t occ[MAXH];            // walls + doors + objects, one bit per cell
     uint32_t doorcell[MAXH];       // door cells (subset of occ)
+    uint32_t wallmask[MAXH];       // the walls of THIS level: lp.wall_rows minus what remove_wall() took out (bonus levels)
     uint32_t pass[MAXH], fill[MAXH];  // reachability flood fill
     uint8_t door_y_right[MAXROOMS];   // Room.door_pos[0].y of room r
     uint8_t door_x_down[MAXROOMS];    // Room.door_pos[1].x of room r
@@ -274,6 +281,9 @@ struct GenCtx {
     int nobj;
     int ax, ay, adir; bool agent_placed;
     int locked_door;                  // object id of the locked door or -1
+    uint32_t locked_mask;             // every locked door (bonus levels have up to two)
+    uint32_t hidden_mask;             // objects that are not on the grid at reset (the key inside KeyInBox's box)
+    int start_carry;                  // object the agent picks up before its first step (PutNext*Carrying), or NO_OBJ
     int root_kind, side_and;
     // LevelGen.locked_room (persists across episodes, levelgen.py:284)
     int locked_room; bool locked_room_fresh;
@@ -286,7 +296,7 @@ enum : int { GEN_OK = 0, GEN_REJECT = 1, GEN_RECURSION = 2 };
 BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
 {
     const int S = lp.room_size, R = lp.num_rows, C = lp.num_cols;
-    for (int y = 0; y < lp.H; y++) { g.m->occ[y] = lp.wall_rows[y]; g.m->doorcell[y] = 0; }
+    for (int y = 0; y < lp.H; y++) { g.m->occ[y] = lp.wall_rows[y]; g.m->doorcell[y] = 0; g.m->wallmask[y] = lp.wall_rows[y]; }
     for (int j = 0; j < R; j++)
         for (int i = 0; i < C; i++) {
             int r = j * C + i, tx = i * (S - 1), ty = j * (S - 1);
@@ -302,7 +312,7 @@ BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
     g.ax = (C / 2) * (S - 1) + S / 2;
     g.ay = (R / 2) * (S - 1) + S / 2;
     g.adir = 0; g.agent_placed = true;
-    g.locked_door = -1;
+    g.locked_door = -1; g.locked_mask = 0; g.hidden_mask = 0; g.start_carry = NO_OBJ;
     g.locked_room_fresh = false;
 }
 
@@ -377,16 +387,19 @@ BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ro
     if (k == 0 || k == 2) g.m->door_id_right[owner] = (uint8_t)id; else g.m->door_id_down[owner] = (uint8_t)id;
     g.m->obj.x[id] = (uint8_t)x; g.m->obj.y[id] = (uint8_t)y; g.m->obj.tc[id] = (uint8_t)(T_DOOR | (color << 3));
     g.m->doorcell[y] |= 1u << x;
-    if (locked) g.locked_door = id;
+    if (locked) { g.locked_door = id; g.locked_mask |= 1u << id; }
     return id;
 }
 
 // RoomGrid.place_agent(i=None, j=None, rand_dir=True)
-BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g)
+BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g, int room_given = -1)
 {
-    int i = g.rng.randint(0, lp.num_cols);
-    int j = g.rng.randint(0, lp.num_rows);
-    int room = j * lp.num_cols + i;
+    int room = room_given;
+    if (room < 0) {
+        int i = g.rng.randint(0, lp.num_cols);
+        int j = g.rng.randint(0, lp.num_rows);
+        room = j * lp.num_cols + i;
+    }
     {   // KNOWN DIVERGENCE: the reference's loop below never returns when no empty cell of the
         // room has an empty or wall cell in front of it for any heading (3x3 rooms packed with distractors and
         // doors: MiniBossLevel seed 698, 57th level).  The reference hangs; here the level is rejected like any
@@ -398,9 +411,9 @@ BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g)
         for (int y = ty + 1; y < ty + S - 1; y++) {
             const uint32_t empty = ~g.m->occ[y] & rmask;
             // cells that may be in front of the agent: empty, or wall (a door is neither)
-            const uint32_t f0 = ~g.m->occ[y] | (lp.wall_rows[y] & ~g.m->doorcell[y]);
-            const uint32_t fu = ~g.m->occ[y - 1] | (lp.wall_rows[y - 1] & ~g.m->doorcell[y - 1]);
-            const uint32_t fd = ~g.m->occ[y + 1] | (lp.wall_rows[y + 1] & ~g.m->doorcell[y + 1]);
+            const uint32_t f0 = ~g.m->occ[y] | (g.m->wallmask[y] & ~g.m->doorcell[y]);
+            const uint32_t fu = ~g.m->occ[y - 1] | (g.m->wallmask[y - 1] & ~g.m->doorcell[y - 1]);
+            const uint32_t fd = ~g.m->occ[y + 1] | (g.m->wallmask[y + 1] & ~g.m->doorcell[y + 1]);
             if (empty & ((f0 << 1) | (f0 >> 1) | fu | fd)) any = true;
         }
         if (!any) return GEN_RECURSION;
@@ -414,7 +427,7 @@ BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g)
         int fx = x + dir_dx(g.adir), fy = y + dir_dy(g.adir);
         // front cell must be empty or a wall (a door is neither)
         bool occupied = (g.m->occ[fy] >> fx) & 1u;
-        bool wall = ((lp.wall_rows[fy] >> fx) & 1u) && !((g.m->doorcell[fy] >> fx) & 1u);
+        bool wall = ((g.m->wallmask[fy] >> fx) & 1u) && !((g.m->doorcell[fy] >> fx) & 1u);
         if (!occupied || wall) break;
     }
     return GEN_OK;
@@ -477,6 +490,11 @@ BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o,
 {
     first_id = g.nobj;
     uint32_t seen = 0;                       // bit 6 * type_rank + color
+    if (all_unique)                          // everything already placed through place_in_room counts (roomgrid.add_distractors)
+        for (int k = 0; k < g.nobj; k++) {
+            const int tc = g.m->obj.tc[k], ty = tc & 7;
+            if (ty >= T_KEY && !((g.hidden_mask >> k) & 1u)) seen |= 1u << (6 * (ty == T_KEY ? 0 : ty == T_BALL ? 1 : 2) + (tc >> 3));
+        }
     for (int n = 0; n < num;) {
         int color = color_by_name_rank(g.rng.randint(0, 6));
         int t = g.rng.randint(0, 3);
@@ -513,7 +531,7 @@ BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
     if (lane < lp.H) {
         const uint32_t occ = g.m->occ[lane], door = g.m->doorcell[lane];
         pass = (~occ | door) & full;
-        things = (occ & ~lp.wall_rows[lane]) | door;              // non-wall, non-empty cells
+        things = (occ & ~g.m->wallmask[lane]) | door;              // non-wall, non-empty cells
         if (lane == g.ay) f = 1u << g.ax;
     }
     uint32_t up, dn;
@@ -553,7 +571,7 @@ BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
         uint32_t near = v | (v << 1) | (v >> 1);
         if (y > 0) near |= f[y - 1];
         if (y + 1 < lp.H) near |= f[y + 1];
-        uint32_t things = (g.m->occ[y] & ~lp.wall_rows[y]) | g.m->doorcell[y];   // non-wall, non-empty cells
+        uint32_t things = (g.m->occ[y] & ~g.m->wallmask[y]) | g.m->doorcell[y];   // non-wall, non-empty cells
         if (things & ~near) return GEN_REJECT;
     }
     return GEN_OK;
@@ -785,13 +803,297 @@ BB_HD int g_mission_unlock(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 
 // gen_mission of the level families.  IMPUNLOCK selects the instantiation that only serves KIND_IMPUNLOCK, so that the code
 // generated for the other families (register allocation of generate_level inside k_gen) stays the one profiled in round 1.
+// ---- bonus_levels.py ------------------------------------------------------------------------------------------------
+// RoomGrid.remove_wall(i, j, wall_idx): the wall cells between two rooms (corners stay) become empty; both rooms count as
+// connected through that side (room.doors[idx] = True: connect_all sees a door, add_door sees an occupied slot)
+BB_HD void g_remove_wall(const LevelParams &lp, GenCtx &g, int room, int k)
+{
+    const int S = lp.room_size;
+    const int owner = k == 2 ? room - 1 : k == 3 ? room - lp.num_cols : room;
+    const int tx = (owner % lp.num_cols) * (S - 1), ty = (owner / lp.num_cols) * (S - 1);
+    if (k == 0 || k == 2) {                    // the right wall of `owner`
+        for (int i = 1; i < S - 1; i++) { g.m->wallmask[ty + i] &= ~(1u << (tx + S - 1)); g.m->occ[ty + i] &= ~(1u << (tx + S - 1)); }
+        g.door_right |= 1u << owner;
+    } else {                                   // its bottom wall
+        const uint32_t bits = ((1u << (S - 2)) - 1u) << (tx + 1);
+        g.m->wallmask[ty + S - 1] &= ~bits; g.m->occ[ty + S - 1] &= ~bits;
+        g.door_down |= 1u << owner;
+    }
+}
+// RoomGrid.add_door(i, j, door_idx=None, color=None, locked=None): the draws a missing argument costs, in the reference's order
+BB_HD int g_add_door_rand(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int k, int color, int locked)
+{
+    if (k < 0) for (;;) { k = g.rng.randint(0, 4); if (g_has_slot(lp, room, k) && !g_has_door(lp, g, room, k)) break; }
+    if (color < 0) color = color_by_name_rank(g.rng.randint(0, 6));
+    if (locked < 0) locked = g.rng.randbool() ? 1 : 0;
+    return g_add_door(lp, g, o, room, k, color, locked != 0);
+}
+// RoomGrid.add_object(i, j, kind=None, color=None)
+BB_HD int g_add_object_rand(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id)
+{
+    if (type < 0) { const int t = g.rng.randint(0, 3); type = t == 0 ? T_KEY : t == 1 ? T_BALL : T_BOX; }
+    if (color < 0) color = color_by_name_rank(g.rng.randint(0, 6));
+    return g_add_object(lp, g, o, room, type, color, id);
+}
+// a descriptor by (type, color, loc) into slot d; ObjDesc matching happens at reset_verifier, i.e. with the final agent pose
+BB_HD void g_desc(const LevelParams &lp, GenCtx &g, const LevelOut &o, int d, int type, int color, int loc)
+{
+    g.m->desc_type[d] = type; g.m->desc_color[d] = color; g.m->desc_loc[d] = loc;
+    g.m->desc_mask[d] = g_match(lp, g, o, type, color, loc) & ~g.hidden_mask;
+}
+// MiniGridEnv._rand_subset(COLOR_NAMES, n): colours in draw order
+BB_HD void g_rand_colors(GenCtx &g, int n, int out[6])
+{
+    int left[6], nl = 6;
+    for (int c = 0; c < 6; c++) left[c] = color_by_name_rank(c);
+    for (int k = 0; k < n; k++) {
+        const int i = g.rng.randint(0, nl);
+        out[k] = left[i];
+        for (int c = i; c + 1 < nl; c++) left[c] = left[c + 1];
+        nl--;
+    }
+}
+
+BB_HD int g_mission_bonus(const LevelParams &lp, GenCtx &g, const LevelOut &o)
+{
+    const int C = lp.num_cols, mid = (lp.num_rows > 1 && C > 1) ? 1 * C + 1 : 0;      // room (1, 1) of a 3 x 3 grid
+    int id = 0, first = 0;
+    switch (lp.bonus) {
+    case BN_GOTO_REDBLUE: {                 // Level_GoToRedBlueBall :24-40
+        BB_TRY(g_place_agent(lp, g));
+        BB_TRY(g_add_distractors(lp, g, o, lp.num_dists, first));
+        for (int k = first; k < g.nobj; k++) {
+            const int tc = g.m->obj.tc[k];
+            if ((tc & 7) == T_BALL && ((tc >> 3) == C_BLUE || (tc >> 3) == C_RED)) return GEN_REJECT;
+        }
+        const int color = g.rng.randint(0, 2) == 0 ? C_RED : C_BLUE;
+        BB_TRY(g_add_object(lp, g, o, 0, T_BALL, color, id));
+        BB_TRY(g_check_reachable(lp, g));
+        g.m->leaf_kind[0] = I_GOTO; g_desc(lp, g, o, 0, T_BALL, color, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_OPEN_RED_DOOR: {                // Level_OpenRedDoor :59-62
+        g_add_door(lp, g, o, 0, 0, C_RED, false);
+        BB_TRY(g_place_agent(lp, g, 0));
+        g.m->leaf_kind[0] = I_OPEN; g_desc(lp, g, o, 0, T_DOOR, C_RED, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_OPEN_DOOR: {                    // Level_OpenDoor :82-99; bonus_a: 0 = select_by None, 1 = "color", 2 = "loc"
+        int colors[6];
+        g_rand_colors(g, 4, colors);
+        int door0 = -1;
+        for (int i = 0; i < 4; i++) { const int d = g_add_door(lp, g, o, mid, i, colors[i], false); if (i == 0) door0 = d; }
+        int sel = lp.bonus_a;
+        if (sel == 0) sel = g.rng.randint(0, 2) == 0 ? 1 : 2;
+        int loc = LOC_NONE;
+        if (sel == 2) loc = g.rng.randint(0, 4);
+        BB_TRY(g_place_agent(lp, g, mid));
+        g.m->leaf_kind[0] = I_OPEN;
+        if (sel == 1) g_desc(lp, g, o, 0, T_DOOR, g.m->obj.tc[door0] >> 3, LOC_NONE); else g_desc(lp, g, o, 0, T_DOOR, ANY, loc);
+        return GEN_OK;
+    }
+    case BN_GOTO_DOOR: {                    // Level_GoToDoor :163-171
+        int doors[4];
+        for (int i = 0; i < 4; i++) doors[i] = g_add_door_rand(lp, g, o, mid, -1, -1, -1);
+        BB_TRY(g_place_agent(lp, g, mid));
+        const int pick = doors[g.rng.randint(0, 4)];
+        g.m->leaf_kind[0] = I_GOTO; g_desc(lp, g, o, 0, T_DOOR, g.m->obj.tc[pick] >> 3, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_GOTO_OBJ_DOOR: {                // Level_GoToObjDoor :186-197
+        BB_TRY(g_place_agent(lp, g, mid));
+        BB_TRY(g_add_distractors(lp, g, o, 8, first, false, mid));
+        for (int i = 0; i < 4; i++) g_add_door_rand(lp, g, o, mid, -1, -1, -1);
+        BB_TRY(g_check_reachable(lp, g));
+        const int pick = first + g.rng.randint(0, 12);            // 8 distractors, then the 4 doors, in that order
+        const int tc = g.m->obj.tc[pick];
+        g.m->leaf_kind[0] = I_GOTO; g_desc(lp, g, o, 0, tc & 7, tc >> 3, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_ACTION_OBJ_DOOR: {              // Level_ActionObjDoor :214-234 (add_distractors default: all_unique=True)
+        BB_TRY(g_add_distractors(lp, g, o, 5, first, true, mid));
+        for (int i = 0; i < 4; i++) g_add_door_rand(lp, g, o, mid, -1, -1, 0);
+        BB_TRY(g_place_agent(lp, g, mid));
+        const int pick = first + g.rng.randint(0, 9);
+        const int tc = g.m->obj.tc[pick];
+        const bool goto_it = g.rng.randbool();
+        g.m->leaf_kind[0] = goto_it ? I_GOTO : ((tc & 7) == T_DOOR ? I_OPEN : I_PICKUP);
+        g_desc(lp, g, o, 0, tc & 7, tc >> 3, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_UNLOCK_LOCAL: {                 // Level_UnlockLocal :247-254; bonus_a: distractors
+        const int door = g_add_door_rand(lp, g, o, mid, -1, -1, 1);
+        BB_TRY(g_add_object(lp, g, o, mid, T_KEY, g.m->obj.tc[door] >> 3, id));
+        if (lp.bonus_a) BB_TRY(g_add_distractors(lp, g, o, 3, first, true, mid));
+        BB_TRY(g_place_agent(lp, g, mid));
+        g.m->leaf_kind[0] = I_OPEN; g_desc(lp, g, o, 0, T_DOOR, ANY, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_KEY_IN_BOX: {                   // Level_KeyInBox :277-287: the key is inside the box, not on the grid
+        const int door = g_add_door_rand(lp, g, o, mid, -1, -1, 1);
+        const int bcolor = color_by_name_rank(g.rng.randint(0, 6));
+        BB_TRY(g_add_object(lp, g, o, mid, T_BOX, bcolor, id));   // object `id`; its contents is the next table entry
+        const int key = g.nobj++;
+        g.m->obj.x[key] = 0; g.m->obj.y[key] = 0; g.m->obj.tc[key] = (uint8_t)(T_KEY | ((g.m->obj.tc[door] >> 3) << 3));
+        g.hidden_mask |= 1u << key;
+        BB_TRY(g_place_agent(lp, g, mid));
+        g.m->leaf_kind[0] = I_OPEN; g_desc(lp, g, o, 0, T_DOOR, ANY, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_UNLOCK_PICKUP: {                // Level_UnlockPickup :307-319 (1 x 2 rooms); bonus_a: distractors
+        int obj;
+        BB_TRY(g_add_object_rand(lp, g, o, 1, T_BOX, -1, obj));
+        const int door = g_add_door_rand(lp, g, o, 0, 0, -1, 1);
+        BB_TRY(g_add_object(lp, g, o, 0, T_KEY, g.m->obj.tc[door] >> 3, id));
+        if (lp.bonus_a) BB_TRY(g_add_distractors(lp, g, o, 4, first, true, -1));
+        BB_TRY(g_place_agent(lp, g, 0));
+        g.m->leaf_kind[0] = I_PICKUP; g_desc(lp, g, o, 0, T_BOX, g.m->obj.tc[obj] >> 3, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_BLOCKED_UNLOCK_PICKUP: {        // Level_BlockedUnlockPickup :348-361: a ball set directly in front of the locked door
+        int obj;
+        BB_TRY(g_add_object_rand(lp, g, o, 1, T_BOX, -1, obj));
+        const int door = g_add_door_rand(lp, g, o, 0, 0, -1, 1);
+        const int bcolor = color_by_name_rank(g.rng.randint(0, 6));
+        {   // self.grid.set(pos[0] - 1, pos[1], Ball(color)): no rejection sampling, whatever was there is replaced
+            const int bx = g.m->obj.x[door] - 1, by = g.m->obj.y[door];
+            for (int k = 0; k < g.nobj; k++)
+                if (g.m->obj.x[k] == bx && g.m->obj.y[k] == by && !((g.hidden_mask >> k) & 1u)) g.hidden_mask |= 1u << k;   // (an overwritten object leaves the grid)
+            const int ball = g.nobj++;
+            g.m->obj.x[ball] = (uint8_t)bx; g.m->obj.y[ball] = (uint8_t)by; g.m->obj.tc[ball] = (uint8_t)(T_BALL | (bcolor << 3));
+            g.m->occ[by] |= 1u << bx;
+        }
+        BB_TRY(g_add_object(lp, g, o, 0, T_KEY, g.m->obj.tc[door] >> 3, id));
+        BB_TRY(g_place_agent(lp, g, 0));
+        g.m->leaf_kind[0] = I_PICKUP; g_desc(lp, g, o, 0, T_BOX, ANY, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_UNLOCK_TO_UNLOCK: {             // Level_UnlockToUnlock :379-398 (1 x 3 rooms)
+        int colors[6];
+        g_rand_colors(g, 2, colors);
+        g_add_door(lp, g, o, 0, 0, colors[0], true);
+        BB_TRY(g_add_object(lp, g, o, 2, T_KEY, colors[0], id));
+        g_add_door(lp, g, o, 1, 0, colors[1], true);
+        BB_TRY(g_add_object(lp, g, o, 1, T_KEY, colors[1], id));
+        int obj;
+        BB_TRY(g_add_object_rand(lp, g, o, 0, T_BALL, -1, obj));
+        BB_TRY(g_place_agent(lp, g, 1));
+        g.m->leaf_kind[0] = I_PICKUP; g_desc(lp, g, o, 0, T_BALL, ANY, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_PICKUP_DIST: {                  // Level_PickupDist :418-432
+        BB_TRY(g_add_distractors(lp, g, o, 5, first, true, -1));
+        BB_TRY(g_place_agent(lp, g, 0));
+        const int tc = g.m->obj.tc[first + g.rng.randint(0, 5)];
+        const int sel = g.rng.randint(0, 3);                      // ["type", "color", "both"]
+        g.m->leaf_kind[0] = I_PICKUP;
+        g_desc(lp, g, o, 0, sel == 1 ? ANY_TYPE : (tc & 7), sel == 0 ? ANY : (tc >> 3), LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_PICKUP_ABOVE: {                 // Level_PickupAbove :461-469: the object is in room (1, 0)
+        int obj;
+        BB_TRY(g_add_object_rand(lp, g, o, 1, -1, -1, obj));
+        g_add_door_rand(lp, g, o, mid, 3, -1, 0);
+        BB_TRY(g_place_agent(lp, g, mid));
+        BB_TRY(g_connect_all(lp, g, o));
+        g.m->leaf_kind[0] = I_PICKUP; g_desc(lp, g, o, 0, g.m->obj.tc[obj] & 7, g.m->obj.tc[obj] >> 3, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_OPEN_TWO_DOORS: {               // Level_OpenTwoDoors :497-515; bonus_a / bonus_b: first / second colour + 1, 0 = drawn
+        int colors[6];
+        g_rand_colors(g, 2, colors);
+        const int c1 = lp.bonus_a ? lp.bonus_a - 1 : colors[0], c2 = lp.bonus_b ? lp.bonus_b - 1 : colors[1];
+        g_add_door(lp, g, o, mid, 2, c1, false);
+        g_add_door(lp, g, o, mid, 0, c2, false);
+        BB_TRY(g_place_agent(lp, g, mid));
+        g.root_kind = R_BEFORE;
+        g.m->leaf_kind[0] = I_OPEN; g_desc(lp, g, o, 0, T_DOOR, c1, LOC_NONE);
+        g.m->leaf_kind[2] = I_OPEN; g_desc(lp, g, o, 4, T_DOOR, c2, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_FIND_OBJ: {                     // Level_FindObjS5 :579-587 (i from num_rows, j from num_cols, used as (i, j))
+        const int i = g.rng.randint(0, lp.num_rows);
+        const int j = g.rng.randint(0, lp.num_cols);
+        int obj;
+        BB_TRY(g_add_object_rand(lp, g, o, j * C + i, -1, -1, obj));
+        BB_TRY(g_place_agent(lp, g, mid));
+        BB_TRY(g_connect_all(lp, g, o));
+        g.m->leaf_kind[0] = I_PICKUP; g_desc(lp, g, o, 0, g.m->obj.tc[obj] & 7, ANY, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_KEY_CORRIDOR: {                 // KeyCorridor :636-656 (3 columns, num_rows rows); bonus_a: obj_type
+        for (int j = 1; j < lp.num_rows; j++) g_remove_wall(lp, g, j * C + 1, 3);
+        const int row = g.rng.randint(0, lp.num_rows);
+        const int door = g_add_door_rand(lp, g, o, row * C + 2, 2, -1, 1);
+        int obj;
+        BB_TRY(g_add_object_rand(lp, g, o, row * C + 2, lp.bonus_a, -1, obj));
+        BB_TRY(g_add_object(lp, g, o, g.rng.randint(0, lp.num_rows) * C + 0, T_KEY, g.m->obj.tc[door] >> 3, id));
+        BB_TRY(g_place_agent(lp, g, (lp.num_rows / 2) * C + 1));
+        BB_TRY(g_connect_all(lp, g, o));
+        g.m->leaf_kind[0] = I_PICKUP; g_desc(lp, g, o, 0, g.m->obj.tc[obj] & 7, ANY, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_ONE_ROOM: {                     // Level_1RoomS8 :721-724
+        int obj;
+        BB_TRY(g_add_object_rand(lp, g, o, 0, T_BALL, -1, obj));
+        BB_TRY(g_place_agent(lp, g));
+        g.m->leaf_kind[0] = I_PICKUP; g_desc(lp, g, o, 0, T_BALL, ANY, LOC_NONE);
+        return GEN_OK;
+    }
+    case BN_PUTNEXT: case BN_MOVE_TWO_ACROSS: {   // PutNext :793-819 / MoveTwoAcross :931-953 (1 x 2 rooms); bonus_a: objs_per_room
+        const int n = lp.bonus_a;
+        int fl, fr;
+        BB_TRY(g_place_agent(lp, g, 0));
+        BB_TRY(g_add_distractors(lp, g, o, n, fl, true, 0));
+        BB_TRY(g_add_distractors(lp, g, o, n, fr, true, 1));
+        g_remove_wall(lp, g, 0, 0);
+        if (lp.bonus == BN_PUTNEXT) {
+            int a = fl + g.rng.randint(0, n), b = fr + g.rng.randint(0, n);
+            if (g.rng.randbool()) { const int t = a; a = b; b = t; }
+            g.m->leaf_kind[0] = I_PUTNEXT;
+            g_desc(lp, g, o, 0, g.m->obj.tc[a] & 7, g.m->obj.tc[a] >> 3, LOC_NONE);
+            g_desc(lp, g, o, 1, g.m->obj.tc[b] & 7, g.m->obj.tc[b] >> 3, LOC_NONE);
+            if (lp.bonus_b) g.start_carry = a;                    // start_carrying: obj_a, from the first step on
+        } else {
+            int l0 = g.rng.randint(0, n), l1 = g.rng.randint(0, n - 1); if (l1 >= l0) l1++;      // _rand_subset(objs_l, 2)
+            int r0 = g.rng.randint(0, n), r1 = g.rng.randint(0, n - 1); if (r1 >= r0) r1++;
+            const int a = fl + l0, d = fl + l1, b = fr + r0, c = fr + r1;
+            g.root_kind = R_BEFORE;
+            g.m->leaf_kind[0] = I_PUTNEXT;
+            g_desc(lp, g, o, 0, g.m->obj.tc[a] & 7, g.m->obj.tc[a] >> 3, LOC_NONE);
+            g_desc(lp, g, o, 1, g.m->obj.tc[b] & 7, g.m->obj.tc[b] >> 3, LOC_NONE);
+            g.m->leaf_kind[2] = I_PUTNEXT;
+            g_desc(lp, g, o, 4, g.m->obj.tc[c] & 7, g.m->obj.tc[c] >> 3, LOC_NONE);
+            g_desc(lp, g, o, 5, g.m->obj.tc[d] & 7, g.m->obj.tc[d] >> 3, LOC_NONE);
+        }
+        return GEN_OK;
+    }
+    case BN_OPEN_DOORS_ORDER: {             // OpenDoorsOrder :996-1016; bonus_a: num_doors
+        const int nd = lp.bonus_a;
+        int colors[6], doors[6];
+        g_rand_colors(g, nd, colors);
+        for (int i = 0; i < nd; i++) doors[i] = g_add_door_rand(lp, g, o, mid, -1, colors[i], 0);
+        BB_TRY(g_place_agent(lp, g, mid));
+        int i1 = g.rng.randint(0, nd), i2 = g.rng.randint(0, nd - 1); if (i2 >= i1) i2++;         // _rand_subset(doors, 2)
+        const int mode = g.rng.randint(0, 3);
+        g.m->leaf_kind[0] = I_OPEN; g_desc(lp, g, o, 0, T_DOOR, g.m->obj.tc[doors[i1]] >> 3, LOC_NONE);
+        if (mode != 0) {
+            g.root_kind = mode == 1 ? R_BEFORE : R_AFTER;
+            g.m->leaf_kind[2] = I_OPEN; g_desc(lp, g, o, 4, T_DOOR, g.m->obj.tc[doors[i2]] >> 3, LOC_NONE);
+        }
+        return GEN_OK;
+    }
+    }
+    return GEN_RECURSION;
+}
+
 template <bool IMPUNLOCK>
 BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 {
     for (int k = 0; k < 4; k++) g.m->leaf_kind[k] = I_NONE;
     for (int k = 0; k < 8; k++) { g.m->desc_mask[k] = 0; g.m->desc_type[k] = ANY_TYPE; g.m->desc_color[k] = ANY; g.m->desc_loc[k] = LOC_NONE; }
     g.side_and = 0; g.root_kind = R_SINGLE;
-    if constexpr (IMPUNLOCK) return lp.kind == KIND_UNLOCK ? g_mission_unlock(lp, g, o) : g_mission_impunlock(lp, g, o);
+    if constexpr (IMPUNLOCK) return lp.kind == KIND_UNLOCK ? g_mission_unlock(lp, g, o) : lp.kind == KIND_BONUS ? g_mission_bonus(lp, g, o) : g_mission_impunlock(lp, g, o);
     if (lp.kind == KIND_REDBALL) {                 // iclr19_levels.py:26-37, 55-63
         int ball, first;
         BB_TRY(g_place_agent(lp, g));
@@ -919,18 +1221,19 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
     // G (row-major) and GT (column-major); row padding up to the stride is wall
     for (int c = lane; c < lp.H * lp.rs_g; c += nlanes) {
         const int y = c / lp.rs_g, x = c - y * lp.rs_g;
-        o.grid[c] = (uint8_t)((x >= lp.W || ((lp.wall_rows[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
+        o.grid[c] = (uint8_t)((x >= lp.W || ((g.m->wallmask[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
     }
     for (int c = lane; c < lp.W * lp.rs_t; c += nlanes) {
         const int x = c / lp.rs_t, y = c - x * lp.rs_t;
-        o.grid[lp.gt_off + c] = (uint8_t)((y >= lp.H || ((lp.wall_rows[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
+        o.grid[lp.gt_off + c] = (uint8_t)((y >= lp.H || ((g.m->wallmask[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
     }
 #if defined(__CUDA_ARCH__)
     __syncwarp();
 #endif
     for (int k = 0; k < g.nobj; k++) {
+        if ((g.hidden_mask >> k) & 1u) continue;
         int tc = g.m->obj.tc[k], st = 0;
-        if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (k == g.locked_door ? 2 : 1);   // open_all_doors levelgen.py:189-199
+        if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (((g.locked_mask >> k) & 1u) ? 2 : 1);   // open_all_doors levelgen.py:189-199
         set_cell(lp, o.grid, g.m->obj.x[k], g.m->obj.y[k], tc | (st << 6));
     }
     if constexpr (IMPUNLOCK) {            // KIND_UNLOCK: the untracked objects are their cell bytes
@@ -952,11 +1255,11 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
     }
     for (int k = 0; k < 8; k++) o.ins->desc_mask[k] = g.m->desc_mask[k];
     o.ins->root_kind = (uint8_t)g.root_kind; o.ins->side_and = (uint8_t)g.side_and; o.ins->flags = 0;
-    o.ins->pad0 = 0; o.ins->pad1 = 0;
+    o.ins->pad0 = (uint8_t)(g.start_carry == NO_OBJ ? 0 : g.start_carry + 1); o.ins->pad1 = 0;
     EnvHot h;
     h.x = (uint8_t)g.ax; h.y = (uint8_t)g.ay; h.dirflags = (uint8_t)g.adir; h.carry = NO_OBJ;
     h.step_count = 0; h.max_steps = (uint16_t)(navs * lp.nav_time_maze);
-    h.cur_mask = g.nobj >= 32 ? 0xFFFFFFFFu : ((1u << g.nobj) - 1u);
+    h.cur_mask = (g.nobj >= 32 ? 0xFFFFFFFFu : ((1u << g.nobj) - 1u)) & ~g.hidden_mask;
     h.snap_mask = h.cur_mask;
     *o.hot = h;
     // ---- mission tokens ---------------------------------------------------
@@ -970,7 +1273,7 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
 
 BB_HD int generate_level(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist, GenMem *mem)
 {
-    return (lp.kind == KIND_IMPUNLOCK || lp.kind == KIND_UNLOCK) ? generate_level_t<true>(lp, o, rngrec, locked_room_persist, mem)
+    return (lp.kind == KIND_IMPUNLOCK || lp.kind == KIND_UNLOCK || lp.kind == KIND_BONUS) ? generate_level_t<true>(lp, o, rngrec, locked_room_persist, mem)
                                                                  : generate_level_t<false>(lp, o, rngrec, locked_room_persist, mem);
 }
 
@@ -1354,6 +1657,7 @@ struct GlobalMem {
     BB_HD void set_side_and(int v) { ins->side_and = (uint8_t)v; }
     BB_HD int flags() const { return ins->flags; }
     BB_HD void set_flags(int v) { ins->flags = (uint8_t)v; }
+    BB_HD int start_carry() const { return ins->pad0; }       // object id + 1 the agent holds from its first step on (PutNext*Carrying), 0 = none
 };
 
 // The objects whose TABLE position is (x, y), as a set mask: SWAR over the packed x / y byte arrays, four objects per
@@ -1486,6 +1790,16 @@ struct StepResult { bool done; bool success; float reward; };      // done: succ
 template <bool UNTR = false, class M>
 BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
 {
+    if (h.step_count == 0) {
+        // Level_PutNext*Carrying (bonus_levels.py:821-829): reset() returns the observation of the generated level, THEN takes
+        // obj_a off the grid into the agent's hands -- so the first step acts on the modified state
+        const int sc = mem.start_carry();
+        if (sc) {
+            mem.set_cell(mem.ox(sc - 1), mem.oy(sc - 1), CELL_EMPTY);
+            h.cur_mask &= ~(1u << (sc - 1));
+            h.carry = (uint8_t)(sc - 1);
+        }
+    }
     int x = h.x, y = h.y, dir = h.dirflags & 3, carry = h.carry;
     const int fx = x + dir_dx(dir), fy = y + dir_dy(dir);
     const int fc = mem.cell(fx, fy);
@@ -1534,10 +1848,20 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
                 } else if (carry != NO_OBJ && (mem.otc(carry) & 7) == T_KEY && (mem.otc(carry) >> 3) == ((fc >> 3) & 7)) ns = 0;
             } else ns = st ^ 1;
             if (ns != st) mem.set_cell(fx, fy, (fc & 0x3F) | (ns << 6));
-        } else if (ftype == T_BOX) {  // Box.toggle: replaced by its contents (None)
+        } else if (ftype == T_BOX) {  // Box.toggle: replaced by its contents (None, or Level_KeyInBox's key)
             const uint32_t m = at & h.cur_mask;
-            if (m) h.cur_mask &= ~(1u << ffs32(m));
-            mem.set_cell(fx, fy, CELL_EMPTY);
+            int inside = -1;
+            if (m) {
+                const int id = ffs32(m);
+                h.cur_mask &= ~(1u << id);
+                if (mem.lp.box_contains == id + 1) inside = id + 1;
+            }
+            if (inside >= 0) {
+                mem.set_cell(fx, fy, mem.otc(inside));
+                mem.set_oxy(inside, fx, fy);
+                h.cur_mask |= 1u << inside;
+                at |= 1u << inside;
+            } else mem.set_cell(fx, fy, CELL_EMPTY);
         }
     }
     h.step_count = (uint16_t)(h.step_count + 1);
@@ -1960,57 +2284,6 @@ BB_HD void stage_obs_words(uint32_t *tile, const uint32_t w[OBS_WORDS], int lane
     }
 }
 
-
-// encode_view + stage_obs_words in one pass, for callers that hold the 49 masked cells R[14] and want the lane's 147 bytes
-// in the warp tile without ever keeping the 37 output words alive (the pipelined rollout kernel's observer warps run at
-// 56 registers): the words are produced four cells at a time and leave through the funnel shift one by one.
-// first_word(R) = word 0 of the lane's observation (the caller shuffles it to the previous lane as that lane's next_w0).
-BB_HD uint32_t encode_first_word(const uint32_t R[14])
-{
-    uint32_t o0, o1, o2;
-    encode4(R[0], o0, o1, o2);
-    return o0;
-}
-BB_HD void encode_stage_view(uint32_t *tile, const uint32_t R[14], int lane, uint32_t next_w0)
-{
-    const int D = OBS_BYTES * lane;
-    const int sh = D & 3, wb = D >> 2;
-    const int kl = (sh + OBS_BYTES - 1) >> 2;                 // word holding this lane's last byte
-    const int nvalid = ((sh + OBS_BYTES - 1) & 3) + 1;        // this lane's bytes in that word
-    const int s8 = 8 * sh;
-    uint32_t prev = 0;
-#pragma unroll
-    for (int k = 0; k < 13; k++) {
-        uint32_t sel = 0; int ra = -1;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int q = 4 * k + i;
-            const int vi = q / 7, vj = q % 7;
-            const int r = 2 * vi + (vj >= 4 ? 1 : 0), byte = vj >= 4 ? vj - 4 : vj;
-            if (q >= 49) { sel |= 3u << (4 * i); continue; }          // byte 3 of R[13] is zero
-            if (ra < 0) ra = r;
-            sel |= (uint32_t)(r == ra ? byte : 4 + byte) << (4 * i);
-        }
-        const uint32_t c = byte_perm(R[ra], ra + 1 < 14 ? R[ra + 1] : 0u, sel);
-        uint32_t o[3];
-        encode4(c, o[0], o[1], o[2]);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const int wk = 3 * k + j;                                 // output word index 0..36 (k = 12: word 36 only)
-            if (wk >= OBS_WORDS) continue;
-            uint32_t v = funnel_l(prev, o[j], s8);
-            prev = o[j];
-            if (wk == 0 && sh != 0) continue;                         // first word belongs to the previous lane
-            if (wk == kl && nvalid < 4) v |= next_w0 << (8 * nvalid);
-            tile[wb + wk] = v;                                        // wk <= 36 <= kl always
-        }
-    }
-    if (kl == OBS_WORDS) {                                            // the tail word (lanes whose bytes spill into a 38th word)
-        uint32_t v = funnel_l(prev, 0u, s8);
-        if (nvalid < 4) v |= next_w0 << (8 * nvalid);
-        tile[wb + OBS_WORDS] = v;
-    }
-}
 
 // Same idea for records of LBYTES bytes held in NW words (bytes beyond LBYTES must be zero):
 // record number q of the tile starts at byte LBYTES * q; next_w0 = first word of record q + 1.

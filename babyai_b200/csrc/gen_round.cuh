@@ -104,7 +104,7 @@ BB_DEV void rollout_gen_warp(const LevelParams &lp, const PP &P, uint32_t *g_are
         cnt += BB_POPC(m);
     }
     const bool must_complete = BB_ANY(urgent);
-    BB_SYNCTHREADS();                                  // the stepping warps have read head / tail: generation may start
+    BB_ROLE_SYNC(32 * (step_warps + 1));               // the stepping warps have read head / tail: generation may start
     RolloutRing ds;
     ds.init(ring + lane, 32, 0, 0);
     int env_g = -1, left = 0, next = 0, rounds = 0;

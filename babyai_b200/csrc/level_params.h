@@ -13,14 +13,17 @@ namespace bb {
 static inline const char *make_level_params(const bb_level_spec *s, LevelParams *lp)
 {
     memset(lp, 0, sizeof *lp);
-    if (s->kind < 0 || s->kind > 4) return "bad level kind";
-    if (s->room_size < 4 || s->room_size > 8) return "room_size must be in 4..8";
+    if (s->kind < 0 || s->kind > 5) return "bad level kind";
+    if (s->kind == BB_KIND_BONUS) { if (s->room_size < 3 || s->room_size > 20 || s->bonus < 1 || s->bonus > 20) return "bad bonus level"; }
+    else if (s->room_size < 4 || s->room_size > 8) return "room_size must be in 4..8";
     if (s->num_rows < 1 || s->num_cols < 1 || s->num_rows * s->num_cols > MAXROOMS) return "too many rooms";
     lp->kind = s->kind; lp->room_size = s->room_size; lp->num_rows = s->num_rows; lp->num_cols = s->num_cols;
     lp->num_dists = s->num_dists; lp->instr = s->instr; lp->doors_open = s->doors_open; lp->grey_dists = s->grey_dists;
     lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
     lp->all_unique = s->all_unique; lp->require_unreachable = s->require_unreachable;
     lp->strict_mask = s->strict_mask & 0x1F; lp->done_actions = s->done_actions ? 1 : 0;
+    lp->bonus = s->kind == BB_KIND_BONUS ? s->bonus : 0; lp->bonus_a = s->bonus_a; lp->bonus_b = s->bonus_b;
+    lp->box_contains = lp->bonus == BN_KEY_IN_BOX ? 2 : 0;           // door = object 0, box = object 1, its key = object 2
     if (s->kind == BB_KIND_OBJ && (s->instr < BB_I_GOTO || s->instr > BB_I_PUTNEXT)) return "bad instruction kind";
     if (s->kind == BB_KIND_OBJ && s->instr == BB_I_PUTNEXT && s->num_dists < 2) return "PutNext needs two objects";
     lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
@@ -55,6 +58,7 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     }
     // doors: one per internal wall at most
     max_objs += s->num_rows * (s->num_cols - 1) + s->num_cols * (s->num_rows - 1);
+    if (s->kind == BB_KIND_BONUS) max_objs = MAXOBJ;               // (at most 18 objects + 4 doors, MoveTwoAcrossS8N9)
     if (max_objs > MAXOBJ) return "too many objects for the 32-entry object table";
     lp->obj_words = max_objs < 1 ? 1 : (max_objs + 3) / 4;
     // longest mission in tokens
@@ -68,6 +72,7 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
         int side = (has_and || has_seq) ? 2 * leaf + 1 : leaf;
         lp->max_tokens = has_seq ? 2 * side + 2 : side;
     } else lp->max_tokens = (s->kind == BB_KIND_OBJ && s->instr == BB_I_PUTNEXT) ? 1 + per_desc + 2 + per_desc : leaf;
+    if (s->kind == BB_KIND_BONUS) lp->max_tokens = 24;             // longest: MoveTwoAcross, two PutNext of 8 words + 'then'
     lp->max_tokens = (lp->max_tokens + 7) / 8 * 8;          // 16-byte rows
     if (lp->max_tokens > MAXTOK) lp->max_tokens = MAXTOK;
     // wall template of the empty RoomGrid (Grid.wall_rect per room)

@@ -116,6 +116,7 @@ struct StagedMem {
     __device__ __forceinline__ void set_side_and(int v) { si->side_and = (uint8_t)v; ins->side_and = (uint8_t)v; }
     __device__ __forceinline__ int flags() const { return si->flags; }
     __device__ __forceinline__ void set_flags(int v) { si->flags = (uint8_t)v; ins->flags = (uint8_t)v; }
+    __device__ __forceinline__ int start_carry() const { return si->pad0; }
 };
 
 // ring slot -> live state (global) and -> the staged copy (shared), by the 8 lanes of the group together
@@ -392,6 +393,7 @@ struct SmemOnlyMem {            // lane-private records in shared memory (byte a
     __device__ __forceinline__ void set_side_and(int v) { i[41] = (uint8_t)v; }
     __device__ __forceinline__ int flags() const { return i[42]; }
     __device__ __forceinline__ void set_flags(int v) { i[42] = (uint8_t)v; }
+    __device__ __forceinline__ int start_carry() const { return i[43]; }
 };
 
 template <int ACT_BYTES, bool UNTR = false>
@@ -414,31 +416,6 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
     // stepping warps: rollout_lane.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu)
     rollout_lane_step_warp<PoolPtrs, SmemOnlyMem, ACT_BYTES, UNTR>(lp, P, actions_v, obs, reward, done, dirs, n, T, mode, force_reset, fused,
                                                                    smr + warp * warp_words, lane, blockIdx.x * R_WARPS + warp, s_done);
-}
-
-// k_rollout_pipe -- bb_pool_rollout with T > 1 on single-room levels (default): the pipelined form of k_rollout
-// (rollout_lane.cuh): warps 0, 1 step the CTA's two groups of 32 envs, warps 2, 3 build their observations one step behind,
-// warp 4 (fused launches) generates levels.
-template <bool UNTR>
-__global__ void __launch_bounds__(RP_THREADS_FUSED, 7)
-k_rollout_pipe(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
-               float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
-               const int mode, const int gen_rounds, const int gen_min_active)
-{
-    extern __shared__ __align__(16) uint32_t smp[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pair_words = rl_warp_words(lp);
-    const bool fused = gen_rounds > 0;
-    uint32_t *g_area = smp + RP_PAIRS * pair_words;
-    volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
-    if (warp == 2 * RP_PAIRS) {
-        rollout_gen_warp(lp, P, g_area, s_done, n, T, blockIdx.x * RP_PAIRS * 32, gen_rounds, gen_min_active, lane, RP_PAIRS);
-        return;
-    }
-    const int pair = warp & (RP_PAIRS - 1);
-    if (warp < RP_PAIRS) rollout_pipe_stepper<PoolPtrs, SmemOnlyMem, UNTR>(lp, P, actions, reward, done, dirs, n, T, mode, fused, smp + pair * pair_words,
-                                                                       lane, blockIdx.x * RP_PAIRS + pair, 1 + pair, s_done);
-    else rollout_pipe_observer<PoolPtrs, SmemOnlyMem>(lp, P, obs, n, T, fused, smp + pair * pair_words, lane, blockIdx.x * RP_PAIRS + pair, 1 + pair);
 }
 
 // k_rollout_cta -- bb_pool_rollout on MULTI-ROOM levels: 32 envs per CTA, a lane-per-env step phase and a 4-lanes-per-env
@@ -598,7 +575,6 @@ struct bb_pool {
     int D, G, nev;
     bool gen_generic; int gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
-    bool rollout_pipe;             // bb_pool_rollout (T > 1) through k_rollout_pipe instead of k_rollout (default; BB_ROLLOUT_PIPE=0 switches it off)
     bool rollout_cta;              // bb_pool_rollout through k_rollout_cta (default on multi-room levels; BB_ROLLOUT_KERNEL=lane|cta)
     bool step_cols;                // BB_STEP_KERNEL=cols: k_step8 for every level (default: k_rollout with T = 1 on single-room grids)
     long long rel;
@@ -659,7 +635,7 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_r
         // keep the next rollout launch from its 7 CTAs per SM (measured r02c: k_rollout_cta 7.5 -> 10.3 us per step beside an
         // 8-blocks-per-SM pass); the pass is latency bound on its longest chain, not throughput bound
         const int blocks = beside && p->gen_blocks_beside < p->gen_blocks ? p->gen_blocks_beside : p->gen_blocks;
-        if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+        if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK || p->lp.kind == KIND_BONUS) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
         else k_gen<false><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
     }
 }
@@ -811,8 +787,6 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (p->nev > MAX_GEN_EVENTS) { p->nev = 0; bb_pool_destroy(p); return fail("ring depth / generation period too large"); }
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
     p->step_cols = false;
-    p->rollout_pipe = true;
-    if (const char *e = getenv("BB_ROLLOUT_PIPE")) p->rollout_pipe = atoi(e) != 0;
     p->rollout_cta = p->lp.num_rows * p->lp.num_cols > 1;
     if (const char *e = getenv("BB_ROLLOUT_KERNEL")) p->rollout_cta = !strcmp(e, "cta");
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
@@ -849,10 +823,6 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CUP(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUP(cudaFuncSetAttribute(k_rollout_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUP(cudaFuncSetAttribute(k_rollout_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUP(cudaFuncSetAttribute(k_rollout_pipe<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUP(cudaFuncSetAttribute(k_rollout_pipe<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUP(cudaFuncSetAttribute(k_rollout_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout_cta<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1073,12 +1043,6 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         const int blocks_c = (p->n + RC_ENVS - 1) / RC_ENVS;
         if (p->lp.kind == KIND_UNLOCK) k_rollout_cta<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
         else k_rollout_cta<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-    }
-    else if (p->rollout_pipe && T > 1) {  // pipelined: stepper + observer warp per 32 envs (rollout_lane.cuh)
-        const int gr = fused ? (p->gen_budget > 0 ? p->gen_budget : 1 << 20) : 0;
-        if (p->lp.kind == KIND_UNLOCK) k_rollout_pipe<true><<<blocks, RP_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
-        else if (fused) k_rollout_pipe<false><<<blocks, RP_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, gr, p->gen_min_active);
-        else k_rollout_pipe<false><<<blocks, RP_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0);
     }
     else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
                                                                                        p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);

@@ -63,6 +63,7 @@ struct SmemGMem {
     BB_HD void set_side_and(int v) { i[41] = (uint8_t)v; }
     BB_HD int flags() const { return i[42]; }
     BB_HD void set_flags(int v) { i[42] = (uint8_t)v; }
+    BB_HD int start_carry() const { return i[43]; }
 };
 
 // The agent's 7 x 7 view on the row-major grid: view cell (vi, vj) is world cell  a + f (6 - vj) + r (vi - 3),

@@ -23,6 +23,7 @@ namespace bb {
 
 constexpr int RL_OBJ_STRIDE = 25, RL_INS_STRIDE = 13;             // odd word strides of the lane records (= pool.cu SM_*_STRIDE)
 constexpr int RL_TILE_WORDS = 32 * OBS_BYTES / 4;                 // 1176 words = 4704 B per warp
+constexpr int R_STEP_WARPS = 2;                                   // stepping warps per CTA of k_rollout (pool.cu R_WARPS)
 
 BB_HD int rl_warp_words(const LevelParams &lp) { return 32 * (((lp.cells_pad >> 2) | 1) + RL_OBJ_STRIDE + RL_INS_STRIDE) + RL_TILE_WORDS; }
 
@@ -75,7 +76,7 @@ BB_DEV void rollout_lane_step_warp(const LevelParams &lp, const PP &P, const voi
         avail = (fused ? P.tail[env] : BB_LDCG(P.tail_pub + env)) - head;
         if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env];
     }
-    if (fused) BB_SYNCTHREADS();
+    if (fused) BB_ROLE_SYNC(32 * (R_STEP_WARPS + 1));       // heads / tails are read: the CTA's generator warp may start
     BB_SYNCWARP();
     MemT mem(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * RL_OBJ_STRIDE),
              reinterpret_cast<uint8_t *>(si + lane * RL_INS_STRIDE));
@@ -205,197 +206,6 @@ BB_DEV void rollout_lane_step_warp(const LevelParams &lp, const PP &P, const voi
         if (n_succ) BB_ATOMIC_ADD(c + 2, (unsigned long long)n_succ);
         if (n_err) BB_ATOMIC_ADD(c + 3, (unsigned long long)n_err);
     }
-}
-
-// =====================================================================================================================
-// The PIPELINED form of the same kernel (bb_pool_rollout with T > 1; default): per 32 envs TWO warps --
-//   stepper   one lane per env: action, step_env + verifier, episode swap-in, reward / done / direction; leaves the pose
-//             word (x | y << 8 | dir << 16 | carried cell << 24) in the env's verifier record (its unused last word);
-//   observer  one lane per env: B1 = the 21 window loads of the observation -> the 49 masked cells in registers,
-//             B2 = encode + stage + bulk store, from registers only.
-// B2 of step t runs while the stepper is already at step t + 1: the warp-step of the round-1 kernel was ONE dependent
-// program of ~880 instructions (ncu r01y / r02a: 8.7 cycles per issued instruction, half the issue slots idle); here the
-// critical path per step is max(step, encode + stage) + the window loads.  Two named barriers per pair and step:
-//   X  the stepper has finished step t (state + pose word are in shared memory)        -> the observer may load
-//   Y  the observer holds step t in registers                                          -> the stepper may mutate the state
-// CTA = 2 pairs (64 envs, the same shared-memory records and tiles as before) + the generator warp of fused launches.
-constexpr int RP_PAIRS = 2;
-constexpr int RP_THREADS = 32 * 2 * RP_PAIRS, RP_THREADS_FUSED = RP_THREADS + 32;       // warps: S0 S1 O0 O1 (G)
-constexpr int RP_POSE_WORD = 11;                                  // InstrRec::pad1: free in the shared-memory copy
-
-template <class PP, class MemT, bool UNTR>
-BB_DEV void rollout_pipe_stepper(const LevelParams &lp, const PP &P, const int8_t *actions, float *reward, uint8_t *done, int8_t *dirs,
-                                 const int n, const int T, const int mode, const bool fused, uint32_t *pair_smem, const int lane,
-                                 const int pair_global, const int bar_id, volatile int *s_done)
-{
-    const int gs = (lp.cells_pad >> 2) | 1;
-    const int env0 = pair_global * 32, env = env0 + lane;
-    int nv = n - env0; nv = nv > 32 ? 32 : (nv < 0 ? 0 : nv);
-    const bool valid = lane < nv;
-    uint32_t *sg = pair_smem, *so = sg + 32 * gs, *si = so + 32 * RL_OBJ_STRIDE;
-    rl_copy_records<true>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
-    rl_copy_records<true>(so, RL_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
-    rl_copy_records<true>(si, RL_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
-    EnvHot h;
-    { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
-    uint32_t head = 0, avail = 0;
-    float last_rew = 0.0f;
-    if (valid) {
-        h = P.hot[env];
-        head = P.head[env];
-        avail = (fused ? P.tail[env] : BB_LDCG(P.tail_pub + env)) - head;
-        if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env];
-    }
-    if (fused) BB_SYNCTHREADS();                        // heads / tails are read: the generator warp may start
-    BB_SYNCWARP();
-    MemT mem(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * RL_OBJ_STRIDE),
-             reinterpret_cast<uint8_t *>(si + lane * RL_INS_STRIDE));
-    uint32_t n_step = 0, n_end = 0, n_succ = 0, n_err = 0, consumed = 0;
-    const int gchunks = lp.cells_pad >> 4, tchunks = lp.max_tokens >> 3;
-    const int rec_chunks = gchunks + 6 + 3;
-    int a_next = 0;
-    if (valid) a_next = BB_LD_S8(actions + env);
-    for (int t = 0; t < T; t++) {
-        const int a = a_next;
-        if (valid && t + 1 < T) a_next = BB_LD_S8(actions + (size_t)(t + 1) * n + env);
-        float rew = 0.0f; bool dn = false, begin = false;
-        if (valid) {
-            if (!(h.dirflags & 4)) {
-                const StepResult sr = step_env<UNTR>(h, mem, a);
-                rew = sr.reward; dn = sr.done;
-                n_step++; n_end += dn; n_succ += sr.success;
-                if (dn) {
-                    if (mode == BB_MODE_AUTORESET) begin = true;
-                    else { h.dirflags |= 4; last_rew = rew; }
-                }
-            } else { rew = last_rew; dn = true; }
-            if (begin && !(consumed < avail && avail <= (uint32_t)P.depth)) { begin = false; n_err++; *P.err_flag = 1; }   // ring dry
-        }
-        // ---- episode swap-in by the whole warp: ring slot -> the finished lane's records ----------------
-        uint32_t mbeg = BB_BALLOT(begin);
-        if (mbeg) {
-            const uint32_t my_slot = (head + consumed) % (uint32_t)P.depth;
-            BB_SYNCWARP();
-            while (mbeg) {
-                const int src = ffs32(mbeg);
-                mbeg &= mbeg - 1;
-                const int slot = (int)BB_SHFL(my_slot, src);
-                const int e = env0 + src;
-                const LevelOut o = r2_ring_slot(lp, P, e, slot);
-                for (int c = lane; c < rec_chunks + tchunks; c += 32) {
-                    if (c < rec_chunks) {
-                        const uint4 *sp; uint32_t *dp; int k = c;
-                        if (k < gchunks) { sp = reinterpret_cast<const uint4 *>(o.grid) + k; dp = sg + src * gs + 4 * k; }
-                        else if ((k -= gchunks) < 6) { sp = reinterpret_cast<const uint4 *>(o.obj) + k; dp = so + src * RL_OBJ_STRIDE + 4 * k; }
-                        else { k -= 6; sp = reinterpret_cast<const uint4 *>(o.ins) + k; dp = si + src * RL_INS_STRIDE + 4 * k; }
-                        const uint4 v = BB_LDCG(sp);
-                        dp[0] = v.x; dp[1] = v.y; dp[2] = v.z; dp[3] = v.w;
-                    } else {
-                        const int k = c - rec_chunks;
-                        reinterpret_cast<uint4 *>(P.tok + (size_t)e * lp.max_tokens)[k] = BB_LDCG(reinterpret_cast<const uint4 *>(o.tok) + k);
-                    }
-                }
-                if (lane == src) {
-                    const uint4 hv = BB_LDCG(reinterpret_cast<const uint4 *>(o.hot));
-                    h = *reinterpret_cast<const EnvHot *>(&hv);
-                    consumed++;
-                }
-            }
-            BB_SYNCWARP();
-        }
-        if (valid) {
-            if (mode == BB_MODE_AUTORESET && (int)h.step_count + 2 == (int)h.max_steps && consumed < avail) {
-                const LevelOut o = r2_ring_slot(lp, P, env, (int)((head + consumed) % (uint32_t)P.depth));
-                BB_PREFETCH_L2(o.grid);
-                BB_PREFETCH_L2(o.obj);
-                BB_PREFETCH_L2(reinterpret_cast<const uint8_t *>(o.obj) + 64);
-                BB_PREFETCH_L2(o.ins);
-                BB_PREFETCH_L2(reinterpret_cast<const uint8_t *>(o.ins) + 32);
-                BB_PREFETCH_L2(o.hot);
-                BB_PREFETCH_L2(o.tok);
-            }
-            si[lane * RL_INS_STRIDE + RP_POSE_WORD] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)(h.dirflags & 3) << 16) |
-                                                      ((uint32_t)carry_cell_of<UNTR>(h, mem) << 24);
-            const size_t oi = (size_t)t * n + env;
-            if (reward) reward[oi] = rew;
-            if (done) done[oi] = dn ? 1 : 0;
-            if (dirs) dirs[oi] = (int8_t)(h.dirflags & 3);
-        }
-        BB_PAIR_SYNC(bar_id);                           // X: step t is in shared memory
-        BB_PAIR_SYNC(bar_id);                           // Y: the observer holds it in registers
-    }
-    // ---- store the state back ---------------------------------------------------------------------
-    if (valid) si[lane * RL_INS_STRIDE + RP_POSE_WORD] = 0;       // InstrRec::pad1 stays zero in the global state
-    BB_SYNCWARP();
-    rl_copy_records<false>(sg, gs, reinterpret_cast<uint4 *>(P.grid + (size_t)env0 * lp.cells_pad), lp.cells_pad >> 4, nv, lane);
-    rl_copy_records<false>(so, RL_OBJ_STRIDE, reinterpret_cast<uint4 *>(P.obj + env0), 6, nv, lane);
-    rl_copy_records<false>(si, RL_INS_STRIDE, reinterpret_cast<uint4 *>(P.ins + env0), 3, nv, lane);
-    if (valid) {
-        P.hot[env] = h;
-        P.head[env] = head + consumed;
-        if (mode == BB_MODE_FREEZE) P.last_reward[env] = last_rew;
-    }
-    for (int off = 16; off; off >>= 1) {
-        n_step += BB_SHFL_DOWN(n_step, off); n_end += BB_SHFL_DOWN(n_end, off);
-        n_succ += BB_SHFL_DOWN(n_succ, off); n_err += BB_SHFL_DOWN(n_err, off);
-    }
-    if (fused && lane == 0) BB_ATOMIC_ADD(const_cast<int *>(s_done), 1);
-    if (lane == 0) {
-        unsigned long long *c = P.warp_counters + 4ull * pair_global;
-        if (n_step) BB_ATOMIC_ADD(c + 0, (unsigned long long)n_step);
-        if (n_end) BB_ATOMIC_ADD(c + 1, (unsigned long long)n_end);
-        if (n_succ) BB_ATOMIC_ADD(c + 2, (unsigned long long)n_succ);
-        if (n_err) BB_ATOMIC_ADD(c + 3, (unsigned long long)n_err);
-    }
-}
-
-template <class PP, class MemT>
-BB_DEV void rollout_pipe_observer(const LevelParams &lp, const PP &P, uint8_t *obs, const int n, const int T, const bool fused,
-                                  uint32_t *pair_smem, const int lane, const int pair_global, const int bar_id)
-{
-    const int gs = (lp.cells_pad >> 2) | 1;
-    const int env0 = pair_global * 32;
-    int nv = n - env0; nv = nv > 32 ? 32 : (nv < 0 ? 0 : nv);
-    const bool valid = lane < nv;
-    uint32_t *sg = pair_smem, *so = sg + 32 * gs, *si = so + 32 * RL_OBJ_STRIDE;
-    uint32_t *tile = si + 32 * RL_INS_STRIDE;
-    if (fused) BB_SYNCTHREADS();                        // the CTA-wide rendezvous of a fused launch (see the stepper)
-    MemT mem(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * RL_OBJ_STRIDE),
-             reinterpret_cast<uint8_t *>(si + lane * RL_INS_STRIDE));
-    uint32_t R[14];
-#pragma unroll
-    for (int k = 0; k < 14; k++) R[k] = 0;
-    bool bulk_pending = false;                          // lane 0
-    for (int t = 0; t <= T; t++) {
-        if (t > 0) {
-            // ---- B2(t - 1): encode, stage, hand the tile to the copy engine -- registers only ----
-            if (lane == 0 && bulk_pending) { BB_BULK_WAIT_READ(); bulk_pending = false; }
-            BB_SYNCWARP();
-            const uint32_t next_w0 = BB_SHFL_DOWN(encode_first_word(R), 1);
-            encode_stage_view(tile, R, lane, next_w0);
-            uint8_t *dst = obs + ((size_t)(t - 1) * n + env0) * OBS_BYTES;
-            const bool bulk = nv == 32 && (((uintptr_t)dst) & 15) == 0;
-            if (bulk) BB_FENCE_ASYNC_SMEM();
-            BB_SYNCWARP();
-            if (bulk) {
-                if (lane == 0) { BB_BULK_STORE(dst, tile, 32 * OBS_BYTES); bulk_pending = true; }
-            } else if (nv > 0) {
-                rl_store_tile_plain(tile, dst, lane, nv);
-                BB_SYNCWARP();
-            }
-        }
-        if (t == T) break;
-        BB_PAIR_SYNC(bar_id);                           // X: step t is in shared memory
-        // ---- B1(t): the window loads -> the 49 masked cells of the observation ----
-#pragma unroll
-        for (int k = 0; k < 14; k++) R[k] = 0;
-        if (valid) {
-            const uint32_t pose = si[lane * RL_INS_STRIDE + RP_POSE_WORD];
-            observe_cells(lp, mem, (int)(pose & 0xFF), (int)((pose >> 8) & 0xFF), (int)((pose >> 16) & 3), (int)(pose >> 24), R);
-        }
-        BB_PAIR_SYNC(bar_id);                           // Y: the stepper may go on
-    }
-    if (lane == 0 && bulk_pending) BB_BULK_WAIT_READ();
 }
 
 }  // namespace bb

@@ -23,14 +23,9 @@ static __device__ __forceinline__ int bb_ld_s8(const int8_t *p) { int v; asm vol
 #define BB_BALLOT(x) __ballot_sync(0xFFFFFFFFu, (x))
 #define BB_POPC(x) __popc(x)
 #define BB_SYNCTHREADS_OR(x) __syncthreads_or(x)
-// named barrier of one stepper / observer warp pair (64 threads); ids 1.. (0 is __syncthreads)
-// (immediate barrier numbers: with a register operand ptxas reserves all 16 barriers of the CTA)
-static __device__ __forceinline__ void bb_pair_sync(int id)
-{
-    if (id == 1) asm volatile("bar.sync 1, 64;" ::: "memory");
-    else asm volatile("bar.sync 2, 64;" ::: "memory");
-}
-#define BB_PAIR_SYNC(id) bb_pair_sync(id)
+// the rendezvous of a kernel's warp ROLES (stepping warps / generator warp call it from different places): a named
+// barrier with an explicit thread count -- __syncthreads() is only defined when every thread reaches the same call
+#define BB_ROLE_SYNC(nthreads) asm volatile("barrier.sync 1, %0;" ::"r"(nthreads) : "memory")
 // shared -> global bulk copy on the async proxy (SASS UBLKCP): the writers of the shared-memory tile fence the proxy, one
 // elected thread issues the copy and commits it as a bulk group; wait_group.read returns once the source may be rewritten
 #define BB_FENCE_ASYNC_SMEM() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")

@@ -16,7 +16,7 @@ mirrors.  Five generator families cover all 47 ICLR-19 levels:
 import ctypes as C
 import os
 
-KIND_REDBALL, KIND_OBJ, KIND_LEVELGEN, KIND_IMPUNLOCK, KIND_UNLOCK = 0, 1, 2, 3, 4
+KIND_REDBALL, KIND_OBJ, KIND_LEVELGEN, KIND_IMPUNLOCK, KIND_UNLOCK, KIND_BONUS = 0, 1, 2, 3, 4, 5
 I_GOTO, I_PICKUP, I_OPEN, I_PUTNEXT = 0, 1, 2, 3
 K_ACTION, K_AND, K_SEQ = 0, 1, 2
 
@@ -32,12 +32,13 @@ class LevelSpec(C.Structure):
         ('n_instr_kinds', C.c_int32), ('instr_kinds', C.c_int32 * 3),
         ('all_unique', C.c_int32), ('require_unreachable', C.c_int32),
         ('strict_mask', C.c_int32), ('done_actions', C.c_int32),
+        ('bonus', C.c_int32), ('bonus_a', C.c_int32), ('bonus_b', C.c_int32),
     ]
 
 
 def _spec(kind, room_size=8, num_rows=1, num_cols=1, num_dists=0, instr=I_GOTO, doors_open=0, grey_dists=0,
           locked_room_prob=0.0, locations=0, unblocking=0, implicit_unlock=1, action_kinds=(), instr_kinds=(),
-          all_unique=0, require_unreachable=0, strict_mask=0):
+          all_unique=0, require_unreachable=0, strict_mask=0, bonus=0, bonus_a=0, bonus_b=0):
     s = LevelSpec()
     s.kind, s.room_size, s.num_rows, s.num_cols, s.num_dists = kind, room_size, num_rows, num_cols, num_dists
     s.instr, s.doors_open, s.grey_dists = instr, doors_open, grey_dists
@@ -51,6 +52,7 @@ def _spec(kind, room_size=8, num_rows=1, num_cols=1, num_dists=0, instr=I_GOTO, 
         s.instr_kinds[i] = a
     s.all_unique, s.require_unreachable = all_unique, require_unreachable
     s.strict_mask = strict_mask
+    s.bonus, s.bonus_a, s.bonus_b = bonus, bonus_a, bonus_b
     # verifier.use_done_actions is read from the environment when babyai.levels.verifier is imported (verifier.py:15-17)
     s.done_actions = 1 if os.environ.get('BABYAI_DONE_ACTIONS', False) else 0
     return s
@@ -75,6 +77,15 @@ def levelgen(room_size=8, num_rows=3, num_cols=3, num_dists=18, locked_room_prob
     return _spec(KIND_LEVELGEN, room_size, num_rows, num_cols, num_dists, locked_room_prob=locked_room_prob,
                  locations=locations, unblocking=unblocking, implicit_unlock=implicit_unlock,
                  action_kinds=action_kinds, instr_kinds=instr_kinds)
+
+
+T_KEY, T_BALL, T_BOX = 5, 6, 7
+COLOR_IDX = {'red': 0, 'green': 1, 'blue': 2, 'purple': 3, 'yellow': 4, 'grey': 5}
+
+
+def bonus(family, room_size=8, num_rows=3, num_cols=3, a=0, b=0, num_dists=0, strict_mask=0):
+    """babyai/levels/bonus_levels.py: `family` numbers the gen_mission (include/babyai_b200.h, BB_KIND_BONUS)"""
+    return _spec(KIND_BONUS, room_size, num_rows, num_cols, num_dists, strict_mask=strict_mask, bonus=family, bonus_a=a, bonus_b=b)
 
 
 LEVELS = {
@@ -126,7 +137,60 @@ LEVELS = {
     'MiniBossLevel': lambda: levelgen(5, 2, 2, 7, locked_room_prob=0.25),
     'BossLevel': lambda: levelgen(),
     'BossLevelNoUnlock': lambda: levelgen(locked_room_prob=0, implicit_unlock=0),
+    # ---- bonus_levels.py (class Level_<name>) ----
+    'GoToRedBlueBall': lambda: bonus(1, 8, 1, 1, num_dists=7),
+    'OpenRedDoor': lambda: bonus(2, 5, 1, 2),
+    'OpenDoor': lambda: bonus(3),
+    'OpenDoorDebug': lambda: bonus(3, strict_mask=1),
+    'OpenDoorColor': lambda: bonus(3, a=1),
+    'OpenDoorLoc': lambda: bonus(3, a=2),
+    'GoToDoor': lambda: bonus(4, 7),
+    'GoToObjDoor': lambda: bonus(5, 8),
+    'ActionObjDoor': lambda: bonus(6, 7),
+    'UnlockLocal': lambda: bonus(7),
+    'UnlockLocalDist': lambda: bonus(7, a=1),
+    'KeyInBox': lambda: bonus(8),
+    'UnlockPickup': lambda: bonus(9, 6, 1, 2),
+    'UnlockPickupDist': lambda: bonus(9, 6, 1, 2, a=1),
+    'BlockedUnlockPickup': lambda: bonus(10, 6, 1, 2),
+    'UnlockToUnlock': lambda: bonus(11, 6, 1, 3),
+    'PickupDist': lambda: bonus(12, 7, 1, 1),
+    'PickupDistDebug': lambda: bonus(12, 7, 1, 1, strict_mask=1),
+    'PickupAbove': lambda: bonus(13, 6),
+    'OpenTwoDoors': lambda: bonus(14, 6),
+    'OpenTwoDoorsDebug': lambda: bonus(14, 6, strict_mask=1),
+    'OpenRedBlueDoors': lambda: bonus(14, 6, a=1 + COLOR_IDX['red'], b=1 + COLOR_IDX['blue']),
+    'OpenRedBlueDoorsDebug': lambda: bonus(14, 6, a=1 + COLOR_IDX['red'], b=1 + COLOR_IDX['blue'], strict_mask=1),
+    'FindObjS5': lambda: bonus(15, 5),
+    'FindObjS6': lambda: bonus(15, 6),
+    'FindObjS7': lambda: bonus(15, 7),
+    'KeyCorridorS3R1': lambda: bonus(16, 3, 1, 3, a=T_BALL),
+    'KeyCorridorS3R2': lambda: bonus(16, 3, 2, 3, a=T_BALL),
+    'KeyCorridorS3R3': lambda: bonus(16, 3, 3, 3, a=T_BALL),
+    'KeyCorridorS4R3': lambda: bonus(16, 4, 3, 3, a=T_BALL),
+    'KeyCorridorS5R3': lambda: bonus(16, 5, 3, 3, a=T_BALL),
+    'KeyCorridorS6R3': lambda: bonus(16, 6, 3, 3, a=T_BALL),
+    '1RoomS8': lambda: bonus(17, 8, 1, 1),
+    '1RoomS12': lambda: bonus(17, 12, 1, 1),
+    '1RoomS16': lambda: bonus(17, 16, 1, 1),
+    '1RoomS20': lambda: bonus(17, 20, 1, 1),
+    'PutNextS4N1': lambda: bonus(18, 4, 1, 2, a=1),
+    'PutNextS5N1': lambda: bonus(18, 5, 1, 2, a=1),
+    'PutNextS5N2': lambda: bonus(18, 5, 1, 2, a=2),
+    'PutNextS6N3': lambda: bonus(18, 6, 1, 2, a=3),
+    'PutNextS7N4': lambda: bonus(18, 7, 1, 2, a=4),
+    'PutNextS5N2Carrying': lambda: bonus(18, 5, 1, 2, a=2, b=1),
+    'PutNextS6N3Carrying': lambda: bonus(18, 6, 1, 2, a=3, b=1),
+    'PutNextS7N4Carrying': lambda: bonus(18, 7, 1, 2, a=4, b=1),
+    'MoveTwoAcrossS5N2': lambda: bonus(19, 5, 1, 2, a=2),
+    'MoveTwoAcrossS8N9': lambda: bonus(19, 8, 1, 2, a=9),
+    'OpenDoorsOrderN2': lambda: bonus(20, 6, a=2),
+    'OpenDoorsOrderN4': lambda: bonus(20, 6, a=4),
+    'OpenDoorsOrderN2Debug': lambda: bonus(20, 6, a=2, strict_mask=5),
+    'OpenDoorsOrderN4Debug': lambda: bonus(20, 6, a=4, strict_mask=5),
 }
+ICLR19_LEVELS = [k for k in LEVELS if LEVELS[k]().kind != KIND_BONUS]
+BONUS_LEVELS = [k for k in LEVELS if LEVELS[k]().kind == KIND_BONUS]
 
 
 def level_spec(name):

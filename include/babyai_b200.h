@@ -35,6 +35,7 @@ extern "C" {
 #define BB_KIND_LEVELGEN 2        /* levelgen.py:256-460 LevelGen (PickupLoc .. BossLevel) */
 #define BB_KIND_IMPUNLOCK 3       /* iclr19_levels.py:304-355 GoToImpUnlock; num_dists = distractors per unlocked room */
 #define BB_KIND_UNLOCK 4          /* iclr19_levels.py:418-474 Unlock;        num_dists = distractors per unlocked room */
+#define BB_KIND_BONUS 5           /* bonus_levels.py: the family is bb_level_spec::bonus (BB_BN_*), its constructor arguments bonus_a / bonus_b */
 /* instruction / action kinds (verifier.py) */
 #define BB_I_GOTO 0
 #define BB_I_PICKUP 1
@@ -63,6 +64,13 @@ typedef struct bb_level_spec {
     /* verifier modes (babyai/levels/verifier.py) */
     int32_t strict_mask;        /* bit l: leaf instruction l is built with strict=True (:255, :323, :369); bit 4: the Before / After root is (:430) */
     int32_t done_actions;       /* verifier.use_done_actions (BABYAI_DONE_ACTIONS, :15-17): instructions report through the `done` action */
+    /* BB_KIND_BONUS (babyai/levels/bonus_levels.py): 1 GoToRedBlueBall :7, 2 OpenRedDoor :43, 3 OpenDoor :65 (a: 0 / 1 color / 2 loc),
+     * 4 GoToDoor :150, 5 GoToObjDoor :174, 6 ActionObjDoor :200, 7 UnlockLocal :237 (a: distractors), 8 KeyInBox :267,
+     * 9 UnlockPickup :290 (a: distractors), 10 BlockedUnlockPickup :332, 11 UnlockToUnlock :364, 12 PickupDist :401, 13 PickupAbove :447,
+     * 14 OpenTwoDoors :472 (a, b: first / second colour + 1, 0 = random), 15 FindObj :565, 16 KeyCorridor :614 (a: object type),
+     * 17 1Room :707, 18 PutNext :766 (a: objs_per_room, b: start_carrying), 19 MoveTwoAcross :907 (a: objs_per_room),
+     * 20 OpenDoorsOrder :974 (a: num_doors) */
+    int32_t bonus, bonus_a, bonus_b;
 } bb_level_spec;
 
 typedef struct bb_pool bb_pool;

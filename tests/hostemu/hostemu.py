@@ -127,7 +127,6 @@ def lib2():
         L.r2_error_flag.argtypes = [C.c_void_p]
         L.r2_rollout_cta.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.r2_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        L.r2_rollout_pipe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         _lib2 = L
     return _lib2
 
@@ -148,15 +147,12 @@ class RolloutPool:
 
     def rollout(self, actions, fused=False, gen_rounds=1 << 20, gen_min_active=0, kernel='lane'):
         """fused=True: the CTA's generator warp refills the rings during the launch (nothing else does);
-        kernel='cta': k_rollout_cta's role (rollout_cta.cuh); kernel='pipe': k_rollout_pipe's stepper / observer roles
-        (rollout_lane.cuh), fused or not; default: k_rollout's (rollout_lane.cuh)"""
+        kernel='cta': k_rollout_cta's role (rollout_cta.cuh) instead of k_rollout's (rollout_lane.cuh)"""
         a = np.ascontiguousarray(actions, dtype=np.int8)
         T, n = a.shape
         obs, rew = np.zeros((T, n, 7, 7, 3), np.uint8), np.zeros((T, n), np.float32)
         done, dirs, cnt = np.zeros((T, n), np.uint8), np.zeros((T, n), np.int8), np.zeros(4, np.int64)
-        if kernel == 'pipe':
-            self.L.r2_rollout_pipe(self.h, _p(a), T, int(fused), gen_rounds, gen_min_active, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
-        elif kernel == 'cta':
+        if kernel == 'cta':
             self.L.r2_rollout_cta(self.h, _p(a), T, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
         elif fused:
             self.L.r2_rollout_fused(self.h, _p(a), T, gen_rounds, gen_min_active, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))

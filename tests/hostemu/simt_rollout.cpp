@@ -29,7 +29,6 @@ static thread_local WarpCtx *tl_warp = nullptr;
 static thread_local int tl_lane = 0;
 static thread_local std::barrier<> *tl_cta = nullptr;       // __syncthreads of a fused launch (4 stepping warps + the generator warp)
 
-static thread_local std::barrier<> *tl_pair = nullptr;      // bar.sync 1 / 2, 64 of k_rollout_pipe
 static thread_local int *tl_cta_or = nullptr;               // two alternating accumulators of __syncthreads_or
 static thread_local int tl_cta_phase = 0;
 static inline void emu_syncwarp() { tl_warp->bar.arrive_and_wait(); }
@@ -79,7 +78,7 @@ template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exch
 #define BB_PREFETCH_L2(p) ((void)(p))
 #define BB_LD_S8(p) ((int)*(p))
 #define BB_SYNCTHREADS_OR(x) emu_syncthreads_or(x)
-#define BB_PAIR_SYNC(id) tl_pair->arrive_and_wait()          /* the stepper / observer pair's named barrier (64 threads) */
+#define BB_ROLE_SYNC(n) tl_cta->arrive_and_wait()             /* the named barrier of the kernel's warp roles */
 // the bulk (async proxy) tile store: a plain copy here; the fence / wait are no-ops
 #define BB_FENCE_ASYNC_SMEM() ((void)0)
 #define BB_BULK_STORE(gdst, ssrc, bytes) memcpy((gdst), (ssrc), (bytes))
@@ -116,6 +115,7 @@ struct HostSmemMem {
     void set_side_and(int v) { i[41] = (uint8_t)v; }
     int flags() const { return i[42]; }
     void set_flags(int v) { i[42] = (uint8_t)v; }
+    int start_carry() const { return i[43]; }
 };
 
 struct HostPoolPtrs {                                     // the members of pool.cu's PoolPtrs the stepping role touches
@@ -248,48 +248,6 @@ void r2_rollout_fused(RPool *p, const int8_t *actions, int T, int gen_rounds, in
             });
         for (auto &t : th) t.join();
     }
-    for (int k = 0; k < 4; k++) counters4[k] = 0;
-    for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
-}
-
-// one bb_pool_rollout worth of k_rollout_pipe: per CTA two stepper warps, two observer warps (a named barrier per pair) and,
-// in fused launches, the generator warp behind one __syncthreads
-void r2_rollout_pipe(RPool *p, const int8_t *actions, int T, int fused, int gen_rounds, int gen_min_active, uint8_t *obs, float *reward,
-                     uint8_t *done, int8_t *dirs, int64_t *counters4)
-{
-    const LevelParams &lp = p->lp;
-    if (fused && !lp.small) { fprintf(stderr, "simt_rollout: fused launches are for small single-room levels\n"); abort(); }
-    const int pair_words = rl_warp_words(lp);
-    const int cta_envs = RP_PAIRS * 32, nwarps = 2 * RP_PAIRS + (fused ? 1 : 0);
-    const int nctas = (p->n + cta_envs - 1) / cta_envs;
-    for (int cta = 0; cta < nctas; cta++) {
-        std::vector<WarpCtx> ctx(nwarps);
-        std::barrier<> cta_bar(32 * nwarps);
-        std::barrier<> pair_bar0(64), pair_bar1(64);
-        std::vector<uint32_t> smem((size_t)RP_PAIRS * pair_words + RG_AREA_WORDS + 8, 0xDEADBEEFu);
-        uint32_t *smp = smem.data();
-        while (((uintptr_t)smp) & 15) smp++;
-        uint32_t *g_area = smp + RP_PAIRS * pair_words;
-        volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
-        *s_done = 0;
-        std::vector<std::thread> th;
-        for (int tid = 0; tid < 32 * nwarps; tid++)
-            th.emplace_back([&, tid]() {
-                const int lane = tid & 31, warp = tid >> 5;
-                tl_warp = &ctx[warp]; tl_lane = lane; tl_cta = &cta_bar;
-                if (warp == 2 * RP_PAIRS) { rollout_gen_warp(lp, p->P, g_area, s_done, p->n, T, cta * cta_envs, gen_rounds, gen_min_active, lane, RP_PAIRS); return; }
-                const int pair = warp & (RP_PAIRS - 1);
-                tl_pair = pair ? &pair_bar1 : &pair_bar0;
-                uint32_t *ps = smp + pair * pair_words;
-                const int pg = cta * RP_PAIRS + pair;
-                if (warp < RP_PAIRS) {
-                    if (lp.kind == KIND_UNLOCK) rollout_pipe_stepper<HostPoolPtrs, HostSmemMem, true>(lp, p->P, actions, reward, done, dirs, p->n, T, p->mode, fused != 0, ps, lane, pg, 1 + pair, s_done);
-                    else rollout_pipe_stepper<HostPoolPtrs, HostSmemMem, false>(lp, p->P, actions, reward, done, dirs, p->n, T, p->mode, fused != 0, ps, lane, pg, 1 + pair, s_done);
-                } else rollout_pipe_observer<HostPoolPtrs, HostSmemMem>(lp, p->P, obs, p->n, T, fused != 0, ps, lane, pg, 1 + pair);
-            });
-        for (auto &t : th) t.join();
-    }
-    if (!fused) refill(p);
     for (int k = 0; k < 4; k++) counters4[k] = 0;
     for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
 }
