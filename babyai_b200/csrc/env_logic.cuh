@@ -1161,7 +1161,10 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 // ---- mission tokens (Instr.surface / ObjDesc.surface, verifier.py:64-94 ...) --
 BB_HD int tok_desc(const GenCtx &g, int d, int16_t *tok, int n)
 {
-    tok[n++] = popc32(g.m->desc_mask[d]) > 1 ? W_A : W_THE;
+    // ('a' when several objects match.  find_matching_objs scans every grid cell, walls included: a description by colour
+    // alone -- ObjDesc(None, 'grey'), Level_PickupDist -- also matches the grey walls, so it is always 'a grey object')
+    const bool many = popc32(g.m->desc_mask[d]) > 1 || (g.m->desc_type[d] == ANY_TYPE && g.m->desc_color[d] == C_GREY);
+    tok[n++] = many ? W_A : W_THE;
     if (g.m->desc_color[d] != ANY) tok[n++] = (int16_t)(W_RED + g.m->desc_color[d]);
     int t = g.m->desc_type[d];
     tok[n++] = (int16_t)(t == ANY_TYPE ? W_OBJECT : t == T_BOX ? W_BOX : t == T_BALL ? W_BALL : t == T_KEY ? W_KEY : W_DOOR);

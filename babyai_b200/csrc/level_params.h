@@ -88,7 +88,7 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
         (s->locked_room_prob <= 0 && s->n_instr_kinds == 1 && s->instr_kinds[0] == BB_K_ACTION && s->n_action_kinds == 1 &&
          (s->action_kinds[0] == BB_I_GOTO || s->action_kinds[0] == BB_I_PICKUP));
     const bool obj_ok = s->kind != BB_KIND_OBJ || ((s->instr == BB_I_GOTO || s->instr == BB_I_PICKUP) && !s->all_unique && !s->require_unreachable);
-    if (s->num_rows == 1 && s->num_cols == 1 && lp->W <= 8 && lp->H <= 8 && s->num_dists + 1 <= 10 && lg_ok && obj_ok) {
+    if (s->kind <= BB_KIND_LEVELGEN && s->num_rows == 1 && s->num_cols == 1 && lp->W <= 8 && lp->H <= 8 && s->num_dists + 1 <= 10 && lg_ok && obj_ok) {
         lp->small = 1;
         lp->wall64 = 0;
         for (int y = 0; y < 8; y++)

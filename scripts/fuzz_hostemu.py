@@ -16,7 +16,7 @@ for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests'), os.pa
     sys.path.insert(0, p)
 import hostemu  # noqa: E402
 import oracle as orc  # noqa: E402
-from babyai_b200.levels import LEVELS, detokenize, level_spec  # noqa: E402
+from babyai_b200.levels import ICLR19_LEVELS as LEVELS, detokenize, level_spec  # noqa: E402  (the levels the C oracle covers)
 from common import compare_pools  # noqa: E402
 
 MIXES = [None, [0.12, 0.12, 0.30, 0.17, 0.14, 0.13, 0.02], [0.05, 0.05, 0.45, 0.15, 0.15, 0.15, 0.0]]

@@ -7,10 +7,12 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CONFIG_LEVELS = ['GoToRedBall', 'GoToLocal', 'PickupLoc', 'GoTo', 'BossLevel']
-GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('succ_', 'rgb_', 'done_')))      # all 47 served levels (CPU replays)
+GOLDEN_LEVELS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and not f.startswith(('succ_', 'rgb_', 'done_', 'bonus_')))      # all 47 served levels (CPU replays)
 # success-heavy reference traces (97 % bot actions, >= 50 successful episodes each; make_golden.py --success): 'succ_<Level>'
 # reference traces generated with BABYAI_DONE_ACTIONS=1 (verifier.use_done_actions; make_golden.py --done-actions): 'done_<Level>'
 DONE_GOLDENS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and f.startswith('done_'))
+# reference traces of the 50 bonus levels (babyai/levels/bonus_levels.py; make_golden.py --bonus): 'bonus_<Level>'
+BONUS_GOLDENS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and f.startswith('bonus_'))
 SUCCESS_GOLDENS = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz') and f.startswith('succ_'))
 # the traces the CUDA pool replays in the GPU suite (the other 26 files were added at the very end of round 1, after the
 # last GPU visit: they are replayed by the oracle and by the host build of the kernel logic; GPU replay from round 2 on)
@@ -32,6 +34,8 @@ def replay_golden(level, make_pool, get_mission):
     g = load_golden(level)
     if level.startswith(('succ_', 'done_')):
         level = level[5:]
+    elif level.startswith('bonus_'):
+        level = level[6:]
     K, T = g['actions'].shape
     pool = make_pool(level, K, g['seeds'])
     obs = np.asarray(pool.reset())

@@ -10,6 +10,7 @@ toggle / PutNext / Before / After paths of the verifier are exercised.
 
 usage: python tests/golden/make_golden.py [--only-missing] [--success]
        BABYAI_DONE_ACTIONS=1 python tests/golden/make_golden.py --done-actions
+       python tests/golden/make_golden.py --bonus [--only-missing]
 """
 import json
 import os
@@ -127,7 +128,30 @@ def main_done():
               % (level, K, T, eps, succ, os.path.basename(out), os.path.getsize(out) // 1024), flush=True)
 
 
+def main_bonus():
+    """the 50 levels of babyai/levels/bonus_levels.py: 3 traces x 300 steps each, 60 % bot / 40 % random actions (random only
+    where the reference's bot does not return)"""
+    sys.path.insert(0, ROOT)
+    from babyai_b200.levels import BONUS_LEVELS
+    only_missing = '--only-missing' in sys.argv
+    for level in BONUS_LEVELS:
+        out = os.path.join(HERE, 'bonus_' + level + '.npz')
+        if only_missing and os.path.exists(out):
+            continue
+        K, T = 3, 300
+        seeds = [2000 + 11 * k for k in range(K)]
+        p_bot = 0.0 if level in ('UnlockToUnlock', 'KeyInBox') else 0.6
+        tr = [trace(level, s, T, act_seed=500 + k, p_bot=p_bot) for k, s in enumerate(seeds)]
+        save(out, seeds, tr)
+        eps = sum(int(t['done'].sum()) for t in tr)
+        succ = sum(int((t['reward'] > 0).sum()) for t in tr)
+        print('%24s  %d traces x %d steps, %d episodes (%d successes) -> %s (%d KB)'
+              % (level, K, T, eps, succ, os.path.basename(out), os.path.getsize(out) // 1024), flush=True)
+
+
 def main():
+    if '--bonus' in sys.argv:
+        return main_bonus()
     if '--success' in sys.argv:
         return main_success()
     if '--done-actions' in sys.argv:

@@ -307,7 +307,7 @@ def test_single_env_gym_surface(level):
     saved = dict(gym.envs.registration.registry.env_specs)          # other tests make the REFERENCE's envs by these ids
     try:
         ids = gymapi.register_levels(gym)
-        assert 'BabyAI-BossLevel-v0' in ids and 'BabyAI-Unlock-v0' in ids and len(ids) == 47      # every ICLR-19 level
+        assert 'BabyAI-BossLevel-v0' in ids and 'BabyAI-Unlock-v0' in ids and 'BabyAI-KeyCorridorS3R3-v0' in ids and len(ids) == 97      # the 47 ICLR-19 levels + the 50 bonus levels
         assert gym.spec('BabyAI-%s-v0' % level).entry_point.func is gymapi.SingleEnv
     finally:
         gym.envs.registration.registry.env_specs.clear()
