@@ -34,6 +34,20 @@
 #define BB_HD_NOINLINE
 #endif
 
+// Level generation for everything but the small single-room levels (generate_level) runs ONE LANE PER LEVEL on the device, the
+// same scalar code as the host build.  (Round 1 ran one WARP per level -- the 32 lanes executing the same level redundantly,
+// Philox blocks and grid rows split across them; compile with -DBB_GEN_COOP=1 for that form.  It needs ~8 300 warp
+// instructions per BossLevel level whatever the width, so 2 400 warps deliver ~50 levels per microsecond at best while a
+// 32 768-env GoTo pool consumes 20 per microsecond: generation, not stepping, bounded the multi-room configs, ncu r02c.)
+#ifndef BB_GEN_COOP
+#define BB_GEN_COOP 0
+#endif
+#if defined(__CUDA_ARCH__) && BB_GEN_COOP
+#define BB_GEN_WARP 1
+#else
+#define BB_GEN_WARP 0
+#endif
+
 namespace bb {
 
 // ---- constants (gym_minigrid OBJECT_TO_IDX / COLOR_TO_IDX / STATE_TO_IDX) ----
@@ -180,7 +194,7 @@ struct RngScalar {
 // control flow, the 32 lanes compute 32 consecutive Philox blocks (128 draws) at once and a draw is a shuffle
 // from the lane that holds its block.  In the host build it is the scalar generator.
 struct Rng : RngScalar {
-#if defined(__CUDA_ARCH__)
+#if BB_GEN_WARP
     __device__ __forceinline__ uint32_t u32()
     {
         const uint64_t i = draws++;
@@ -523,8 +537,8 @@ BB_HD int g_add_distractors(const LevelParams &lp, GenCtx &g, const LevelOut &o,
 BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
 {
     const uint32_t full = (lp.W >= 32) ? 0xFFFFFFFFu : ((1u << lp.W) - 1u);
-#if defined(__CUDA_ARCH__)
-    // device (generate_level runs with the whole warp on one level): lane y owns grid row y, the rows above and
+#if BB_GEN_WARP
+    // warp-per-level form (generate_level runs with the whole warp on one level): lane y owns grid row y, the rows above and
     // below come by shuffle, one iteration spreads the fill by one row and up to four columns in every row at once
     const int lane = threadIdx.x & 31;
     uint32_t pass = 0, things = 0, f = 0;
@@ -1215,8 +1229,8 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
     *locked_room_persist = g.locked_room < 0 ? 0xFF : (uint8_t)g.locked_room;
 
     // ---- render the byte grid: walls, then doors/objects -----------------
-    // (device: the warp's lanes split the cells; every lane holds the same level)
-#if defined(__CUDA_ARCH__)
+    // (warp-per-level form: the warp's lanes split the cells; every lane holds the same level)
+#if BB_GEN_WARP
     const int lane = threadIdx.x & 31, nlanes = 32;
 #else
     const int lane = 0, nlanes = 1;
@@ -1230,7 +1244,7 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
         const int x = c / lp.rs_t, y = c - x * lp.rs_t;
         o.grid[lp.gt_off + c] = (uint8_t)((y >= lp.H || ((g.m->wallmask[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
     }
-#if defined(__CUDA_ARCH__)
+#if BB_GEN_WARP
     __syncwarp();
 #endif
     for (int k = 0; k < g.nobj; k++) {

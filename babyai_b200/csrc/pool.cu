@@ -421,7 +421,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
 // k_rollout_cta -- bb_pool_rollout on MULTI-ROOM levels: 32 envs per CTA, a lane-per-env step phase and a 4-lanes-per-env
 // observation phase per step, row-major grid only in shared memory (rollout_cta.cuh has the design and the numbers).
 template <bool UNTR>
-__global__ void __launch_bounds__(RC_THREADS, 7)
+__global__ void __launch_bounds__(RC_THREADS, 8)
 k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
               float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T, const int mode)
 {
@@ -441,17 +441,14 @@ k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__
 // assignment would wait for them).
 // IMPUNLOCK: the instantiation that serves KIND_IMPUNLOCK only (Level_GoToImpUnlock); every other level family runs
 // k_gen<false>, whose code is the kernel profiled in round 1.
+#if BB_GEN_COOP
 template <bool IMPUNLOCK>
 __global__ void __launch_bounds__(GEN_THREADS)
-k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
+k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, const int lanes_per_warp)
 {
     __shared__ typename GenMemFor<IMPUNLOCK>::type gen_mem[GEN_THREADS / 32];     // GenMemX (untracked objects) for k_gen<true>
     GenMem *mem = &gen_mem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    // work items: the envs k_gen_scan listed (ring not full), longest chains first -- the levels of one env are serial (one
-    // random stream), so the pass lasts as long as its longest chain: ONE env per ticket.  (Round 1 handed out tickets of 8
-    // consecutive envs: ncu r02a, BossLevel 32 768 envs: 650 us per pass at 2.5 of 16 warps per SM active -- ~1 900 levels of
-    // ~40 us each, serialised behind whichever warp drew the tickets with the most work.)
     const uint32_t c3 = P.gen_count[3], c2 = P.gen_count[2], c1 = P.gen_count[1], c0 = P.gen_count[0];
     const uint32_t count = c0 + c1 + c2 + c3;
     const uint32_t D = (uint32_t)P.depth;
@@ -478,6 +475,41 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target)
         __syncwarp();
     }
 }
+#else
+// ONE LANE PER LEVEL: a lane takes an env from k_gen_scan's lists (one env per ticket, longest chains first) and generates
+// its missing levels with the scalar generator -- the very code of the host build -- its working arrays (GenMem, ~1.3 KB)
+// in local memory.  `lanes_per_warp` of the 32 lanes work (the others exit): the lanes of a warp run different levels, so
+// the warp executes the union of their control flow; fewer working lanes per warp = shorter latency per level, more =
+// more levels per issued instruction (BB_GEN_LANES).
+template <bool IMPUNLOCK>
+__global__ void __launch_bounds__(GEN_THREADS)
+k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, const int lanes_per_warp)
+{
+    if ((int)(threadIdx.x & 31) >= lanes_per_warp) return;
+    typename GenMemFor<IMPUNLOCK>::type mem;
+    const uint32_t c3 = P.gen_count[3], c2 = P.gen_count[2], c1 = P.gen_count[1], c0 = P.gen_count[0];
+    const uint32_t count = c0 + c1 + c2 + c3;
+    const uint32_t D = (uint32_t)P.depth;
+    for (;;) {
+        uint32_t idx = atomicAdd(P.gen_ticket, 1u);
+        if (idx >= count) break;
+        int b = 3;
+        if (idx >= c3) { idx -= c3; b = 2; if (idx >= c2) { idx -= c2; b = 1; if (idx >= c1) { idx -= c1; b = 0; } } }
+        const int env = P.gen_list[(size_t)b * n + idx];
+        const uint32_t t0 = P.tail[env];
+        const int m = target - (int)(t0 - P.head_snap[env]);      // consumption as of the step this pass was forked from
+        RngRec r = P.rng[env];
+        uint8_t lr = P.locked_room[env];
+        int att = 0;
+        for (int i = 0; i < m; i++) {
+            const LevelOut o = ring_slot(lp, P, env, (int)((t0 + (uint32_t)i) % D));
+            att += generate_level_t<IMPUNLOCK>(lp, o, &r, &lr, &mem);
+            P.tail[env] = t0 + (uint32_t)i + 1u;
+        }
+        P.rng[env] = r; P.locked_room[env] = lr; P.attempts[env] += (uint32_t)att;
+    }
+}
+#endif
 
 // k_render_rgb -- RGBImgPartialObsWrapper.observation for a batch: uint8[n][7][7][3] observations -> uint8[n][56][56][3]
 // images (tile size 8).  The image is a pure function of the observation: every view cell selects one of 513 pre-rendered
@@ -568,7 +600,7 @@ constexpr int MAX_GEN_EVENTS = 40;
 struct bb_pool {
     LevelParams lp;
     PoolPtrs P;
-    int n, device, mode, num_warps, gen_blocks, gen_blocks_beside, sm_count;
+    int n, device, mode, num_warps, gen_blocks, gen_blocks_beside, gen_lanes, sm_count;
     // level supply schedule: ring depth D; k_gen is enqueued on gen_stream after every G-th step and
     // step s (counted from the last point at which a finished k_gen launched >= -G existed) waits for the
     // k_gen launched at >= s - D
@@ -635,8 +667,8 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_r
         // keep the next rollout launch from its 7 CTAs per SM (measured r02c: k_rollout_cta 7.5 -> 10.3 us per step beside an
         // 8-blocks-per-SM pass); the pass is latency bound on its longest chain, not throughput bound
         const int blocks = beside && p->gen_blocks_beside < p->gen_blocks ? p->gen_blocks_beside : p->gen_blocks;
-        if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK || p->lp.kind == KIND_BONUS) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
-        else k_gen<false><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target);
+        if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK || p->lp.kind == KIND_BONUS) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes);
+        else k_gen<false><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes);
     }
 }
 
@@ -753,6 +785,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         int want = (n_envs + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);      // one warp per env at most
         int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
+        p->gen_lanes = 8;                                   // working lanes per warp of the lane-per-level k_gen
+        if (const char *e = getenv("BB_GEN_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) p->gen_lanes = v; }
         int beside = 2;
         if (const char *e = getenv("BB_GEN_BESIDE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) beside = v; }
         p->gen_blocks_beside = prop.multiProcessorCount * beside;
@@ -779,8 +813,18 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     // generation pass per 32 steps (many levels per pass: a multi-room level is ~0.2-0.4 ms of serial work)
     // multi-room levels (generation passes run BESIDE the rollouts on a side stream): twice the depth, so that one pass may
     // overlap several launches (bb_pool_rollout: a pass is joined D / 2T launches after it was forked)
-    p->D = p->lp.cells_pad > 256 ? 256 : 128;
-    if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 256) p->D = d; }
+    p->D = 128;
+    if (p->lp.cells_pad > 256) {
+        // 512 levels deep where the rings fit in a fifth of the free device memory (23 GB for 32 768 BossLevel envs), else 256 / 128:
+        // a pass then has six (three, one) 40-step launches to finish in, and an env that ends ten episodes during a pass
+        // (missions that are solved at reset) does not hold the next launch up
+        size_t free_b = 0, total_b = 0;
+        const size_t per_level = (size_t)p->lp.cells_pad + sizeof(EnvHot) + sizeof(ObjTab) + sizeof(InstrRec) + 2 * (size_t)p->lp.max_tokens;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        const size_t ring512 = (size_t)n_envs * 512 * per_level;
+        p->D = ring512 <= free_b / 5 ? 512 : (ring512 / 2 <= free_b / 3 ? 256 : 128);
+    }
+    if (const char *e = getenv("BB_RING_DEPTH")) { int d = atoi(e); if (d >= 1 && d <= 1024) p->D = d; }
     p->G = p->D >= 64 ? 32 : (p->D >= 8 ? p->D / 4 : 1);
     if (const char *e = getenv("BB_GEN_PERIOD")) { int g = atoi(e); if (g >= 1 && g <= p->D) p->G = g; }
     p->nev = p->D / p->G + 3;
