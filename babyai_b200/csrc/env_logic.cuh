@@ -99,6 +99,7 @@ struct LevelParams {
     int32_t n_instr_kinds, instr_kinds[3];
     int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
     int32_t strict_mask, done_actions;   // verifier modes (see verify_action / verify_leaf)
+    int32_t kinds_mask, single_instr;    // bit k: the family can produce an instruction leaf of kind k; 1: it only produces a single ActionInstr
     int32_t bonus, bonus_a, bonus_b;     // KIND_BONUS: which bonus_levels.py family and its constructor arguments
     int32_t box_contains;                // box object id + 1 whose contents is the NEXT table entry (Level_KeyInBox), else 0
     int32_t obj_words;            // ceil(most object-table entries a level of this family uses / 4): words of the packed x / y arrays in use
@@ -1719,17 +1720,25 @@ BB_HD int verify_action(M &mem, int leaf, const StepCtx &s)
 {
     const int kind = mem.leaf_kind(leaf);
     const uint32_t set = mem.desc_mask(2 * leaf);
-    const int pre = mem.leaf_pre(leaf);
-    const bool strict = ((mem.lp.strict_mask >> leaf) & 1) != 0;
-    if (kind == I_PICKUP || kind == I_PUTNEXT) mem.set_leaf_pre(leaf, s.carry);       // preCarrying, refreshed on every evaluation
+    const int km = mem.lp.kinds_mask;              // (kernel argument: the branches on it are uniform)
     const bool goto_ok = (set & s.snap_mask & s.at) != 0;                             // some pos in obj_poss is front_pos
+    if (km == (1 << I_GOTO)) return goto_ok ? V_SUCC : V_CONT;                        // GoTo-only families (GoToLocal, GoToRedBall, GoTo, ...)
+    const bool strict = ((mem.lp.strict_mask >> leaf) & 1) != 0;
+    int pre = NO_OBJ;
+    if (km & ((1 << I_PICKUP) | (1 << I_PUTNEXT))) {
+        pre = mem.leaf_pre(leaf);
+        if (kind == I_PICKUP || kind == I_PUTNEXT) mem.set_leaf_pre(leaf, s.carry);   // preCarrying, refreshed on every evaluation
+    }
     // the toggled cell must be a door of the set, and open: at most one object is ON a cell
-    const bool toggled_door = s.action == A_TOGGLE && (s.fcell & 7) == T_DOOR;
-    const bool open_ok = toggled_door && (s.fcell >> 6) == 0 && (set & s.cur_mask & s.at) != 0;
+    bool toggled_door = false, open_ok = false;
+    if (km & (1 << I_OPEN)) {
+        toggled_door = s.action == A_TOGGLE && (s.fcell & 7) == T_DOOR;
+        open_ok = toggled_door && (s.fcell >> 6) == 0 && (set & s.cur_mask & s.at) != 0;
+    }
     const bool picked = s.action == A_PICKUP && s.carry != NO_OBJ;                    // (carrying something after a pickup action)
     const bool pick_ok = picked && pre == NO_OBJ && s.carry < MAXOBJ && ((set >> (s.carry & 31)) & 1u);   // (untracked objects are in no set)
     bool put_ok = false;
-    if (kind == I_PUTNEXT && s.action == A_DROP && pre < MAXOBJ && ((set >> (pre & 31)) & 1u) && s.carry != pre) {
+    if ((km & (1 << I_PUTNEXT)) && kind == I_PUTNEXT && s.action == A_DROP && pre < MAXOBJ && ((set >> (pre & 31)) & 1u) && s.carry != pre) {
         const int ax = mem.ox(pre), ay = mem.oy(pre);      // (a carried object that was not dropped: cur_pos == (-1, -1), excluded above)
         for (uint32_t m = mem.desc_mask(2 * leaf + 1) & s.snap_mask; m; m &= m - 1) {
             const int k = ffs32(m);
@@ -1783,6 +1792,7 @@ BB_HD int verify_side(M &mem, int side, const StepCtx &s)
 template <class M>
 BB_HD int verify_root(M &mem, const StepCtx &s)
 {
+    if (mem.lp.single_instr) return verify_leaf(mem, 0, s);      // families that only build one ActionInstr (uniform branch)
     const int rk = mem.root_kind();
     const int first = rk == R_AFTER ? 1 : 0, second = 1 - first;
     const bool first_done = rk != R_SINGLE && ((mem.flags() >> first) & 1);
@@ -1807,7 +1817,7 @@ struct StepResult { bool done; bool success; float reward; };      // done: succ
 template <bool UNTR = false, class M>
 BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
 {
-    if (h.step_count == 0) {
+    if (h.step_count == 0 && mem.lp.bonus == BN_PUTNEXT) {
         // Level_PutNext*Carrying (bonus_levels.py:821-829): reset() returns the observation of the generated level, THEN takes
         // obj_a off the grid into the agent's hands -- so the first step acts on the modified state
         const int sc = mem.start_carry();
@@ -1890,7 +1900,7 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
     StepCtx s;
     s.action = action; s.fx = nfx; s.fy = nfy; s.carry = carry;
     s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.at = at;
-    s.fcell = mem.cell(nfx, nfy);
+    s.fcell = (mem.lp.kinds_mask & (1 << I_OPEN)) ? mem.cell(nfx, nfy) : 0;
     const int status = verify_root(mem, s);
     r.success = status == V_SUCC;
     r.reward = 0.0f;

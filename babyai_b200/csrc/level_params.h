@@ -22,6 +22,16 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     lp->locations = s->locations; lp->unblocking = s->unblocking; lp->implicit_unlock = s->implicit_unlock;
     lp->all_unique = s->all_unique; lp->require_unreachable = s->require_unreachable;
     lp->strict_mask = s->strict_mask & 0x1F; lp->done_actions = s->done_actions ? 1 : 0;
+    // the instruction leaves a family can produce, and whether it only ever builds ONE ActionInstr (the verifier's fast paths)
+    lp->kinds_mask = 0xF; lp->single_instr = 1;
+    if (s->kind == BB_KIND_REDBALL || s->kind == BB_KIND_IMPUNLOCK) lp->kinds_mask = 1 << BB_I_GOTO;
+    else if (s->kind == BB_KIND_OBJ) lp->kinds_mask = 1 << s->instr;
+    else if (s->kind == BB_KIND_UNLOCK) lp->kinds_mask = 1 << BB_I_OPEN;
+    else if (s->kind == BB_KIND_LEVELGEN) {
+        lp->kinds_mask = 0;
+        for (int i = 0; i < s->n_action_kinds && i < 4; i++) lp->kinds_mask |= 1 << s->action_kinds[i];
+        lp->single_instr = s->n_instr_kinds == 1 && s->instr_kinds[0] == BB_K_ACTION;
+    } else if (s->kind == BB_KIND_BONUS) lp->single_instr = !(s->bonus == 14 || s->bonus == 19 || s->bonus == 20);   // OpenTwoDoors, MoveTwoAcross, OpenDoorsOrder
     lp->bonus = s->kind == BB_KIND_BONUS ? s->bonus : 0; lp->bonus_a = s->bonus_a; lp->bonus_b = s->bonus_b;
     lp->box_contains = lp->bonus == BN_KEY_IN_BOX ? 2 : 0;           // door = object 0, box = object 1, its key = object 2
     if (s->kind == BB_KIND_OBJ && (s->instr < BB_I_GOTO || s->instr > BB_I_PUTNEXT)) return "bad instruction kind";
