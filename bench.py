@@ -219,6 +219,7 @@ def main():
     ap.add_argument('--level', default=LEVEL)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--brief', action='store_true', help='device-resident value + kernel timing only (child runs of --other-configs)')
+    ap.add_argument('--lean', action='store_true', help='value, roofline and e2e only (multi-GPU scaling runs of the other configs)')
     ap.add_argument('--no-other-configs', action='store_true', help='skip the child runs of BASELINE configs 3-5 (per-GPU share)')
     args = ap.parse_args()
 
@@ -330,7 +331,7 @@ def main():
         return
 
     # ---- the per-step entry point (policy in the loop): bb_pool_step on device buffers, one launch per step ----
-    Ks = max(min(K, 600), MIN_HOST_STEPS)
+    Ks = max(min(K, 600), MIN_HOST_STEPS) if not args.lean else 40
     for t in range(20):
         env.step(actions[t % T], obs[t % T], rew[t % T], done[t % T], dirs[t % T])
     barrier()
@@ -365,6 +366,8 @@ def main():
     # obs uint8[N,7,7,3] -> uint8[N,56,56,3]: 9 408 B written per 147 B read; 616 MB per call at N = 65 536 (> L2)
     rgb = {}
     try:
+        if args.lean:
+            raise RuntimeError('skipped (--lean)')
         pics = torch.empty((n, 56, 56, 3), dtype=torch.uint8, device=dev)
         for k in range(3):
             env.render_rgb(obs[k % T], pics)
@@ -392,7 +395,7 @@ def main():
     # per step: actions host->device, the step kernel writing into a fresh observation tensor, ObssPreprocessor handing
     # the model image float[N,7,7,3] + instr long[N,L] on the device, reward/done device->host.  Measured on this rank.
     learner = {}
-    for key, fused_io in (('fused_io', True), ('tensor_copies', False)):
+    for key, fused_io in ((('fused_io', True), ('tensor_copies', False)) if not args.lean else ()):
         # fused_io (default): bb_pool_step_learner (actions / reward / done over mapped page-locked memory inside the step call);
         # tensor_copies: bb_pool_step + torch copies of those three
         try:
@@ -420,7 +423,7 @@ def main():
 
     # ---- the reference-SHAPED facade: vecenv.ParallelEnv.step builds N Python obs dicts per step (rank 0, single-GPU runs) ----
     facade = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.lean:
         try:
             from babyai_b200 import ParallelEnv, make_envs
             nf = min(n, 4096)                     # penv-sized: the dict facade is host bound by orders of magnitude
