@@ -34,13 +34,13 @@
 #define BB_HD_NOINLINE
 #endif
 
-// Level generation for everything but the small single-room levels (generate_level) runs ONE LANE PER LEVEL on the device, the
-// same scalar code as the host build.  (Round 1 ran one WARP per level -- the 32 lanes executing the same level redundantly,
-// Philox blocks and grid rows split across them; compile with -DBB_GEN_COOP=1 for that form.  It needs ~8 300 warp
-// instructions per BossLevel level whatever the width, so 2 400 warps deliver ~50 levels per microsecond at best while a
-// 32 768-env GoTo pool consumes 20 per microsecond: generation, not stepping, bounded the multi-room configs, ncu r02c.)
+// Level generation for everything but the small single-room levels (generate_level) runs ONE WARP PER LEVEL on the device: the
+// 32 lanes execute the same level with identical control flow, Philox blocks and grid rows split across them.  Compile
+// with -DBB_GEN_COOP=0 for one LANE per level (the scalar code of the host build, working arrays in local memory): measured
+// 3x SLOWER (r02f: GoTo 32 768 envs 8.5e8 vs 2.8e9 env-steps/s; 4 working lanes per warp beat 8, 16 and 32 -- the lanes of
+// a warp sit in different rejection loops, and the scalar working set lives in local memory).
 #ifndef BB_GEN_COOP
-#define BB_GEN_COOP 0
+#define BB_GEN_COOP 1
 #endif
 #if defined(__CUDA_ARCH__) && BB_GEN_COOP
 #define BB_GEN_WARP 1

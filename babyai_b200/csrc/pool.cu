@@ -444,7 +444,7 @@ k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__
 #if BB_GEN_COOP
 template <bool IMPUNLOCK>
 __global__ void __launch_bounds__(GEN_THREADS)
-k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, const int lanes_per_warp)
+k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, const int lanes_per_warp, const int chain_cap)
 {
     __shared__ typename GenMemFor<IMPUNLOCK>::type gen_mem[GEN_THREADS / 32];     // GenMemX (untracked objects) for k_gen<true>
     GenMem *mem = &gen_mem[threadIdx.x >> 5];
@@ -461,7 +461,13 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, con
         if (idx >= c3) { idx -= c3; b = 2; if (idx >= c2) { idx -= c2; b = 1; if (idx >= c1) { idx -= c1; b = 0; } } }
         const int env = P.gen_list[(size_t)b * n + idx];
         const uint32_t t0 = P.tail[env];
-        const int m = target - (int)(t0 - P.head_snap[env]);      // consumption as of the step this pass was forked from
+        const int have = (int)(t0 - P.head_snap[env]);            // consumption as of the step this pass was forked from
+        int m = target - have;
+        // chain cap (concurrent / periodic passes of bb_pool_rollout): a ring that is still at least half full gets at most
+        // `chain_cap` levels per pass -- the levels of one env are serial, and an env that ended ten episodes since the last
+        // pass (missions solved at reset) would otherwise set the duration of the whole pass (ncu r02c: 480 us for ~2 900
+        // levels of 48 us); its deficit is worked off over the next passes, a ring below half is always filled up
+        if (chain_cap > 0 && m > chain_cap && have >= (int)(D / 2)) m = chain_cap;
         RngRec r = P.rng[env];
         uint8_t lr = P.locked_room[env];
         int att = 0;
@@ -483,7 +489,7 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, con
 // more levels per issued instruction (BB_GEN_LANES).
 template <bool IMPUNLOCK>
 __global__ void __launch_bounds__(GEN_THREADS)
-k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, const int lanes_per_warp)
+k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, const int lanes_per_warp, const int chain_cap)
 {
     if ((int)(threadIdx.x & 31) >= lanes_per_warp) return;
     typename GenMemFor<IMPUNLOCK>::type mem;
@@ -497,7 +503,9 @@ k_gen(const LevelParams lp, const PoolPtrs P, const int n, const int target, con
         if (idx >= c3) { idx -= c3; b = 2; if (idx >= c2) { idx -= c2; b = 1; if (idx >= c1) { idx -= c1; b = 0; } } }
         const int env = P.gen_list[(size_t)b * n + idx];
         const uint32_t t0 = P.tail[env];
-        const int m = target - (int)(t0 - P.head_snap[env]);      // consumption as of the step this pass was forked from
+        const int have = (int)(t0 - P.head_snap[env]);
+        int m = target - have;
+        if (chain_cap > 0 && m > chain_cap && have >= (int)(D / 2)) m = chain_cap;
         RngRec r = P.rng[env];
         uint8_t lr = P.locked_room[env];
         int att = 0;
@@ -621,6 +629,7 @@ struct bb_pool {
     int8_t *h_act; uint8_t *h_obs; float *h_rew; uint8_t *h_done; int8_t *h_dir;      // pinned
     uint8_t *d_rgb_lut;            // the 513 RGB tiles (rgb_tiles.h), rendered on first use
     int *h_err;                    // mapped: PoolPtrs::err_flag (a kernel found a level ring dry)
+    int chain_cap;                 // BB_GEN_CHAIN_CAP: levels per env and pass of k_gen while the ring is at least half full (0 = no cap)
     int last_T, refill_cap;        // rollout length of the previous bb_pool_rollout call; BB_REFILL_EVERY as a cap for concurrent passes
     int fused_T;                   // longest T a fused rollout launch has guaranteed levels for (see bb_pool_rollout)
     int zerocopy, zc_level; const void *chk_rew, *chk_done, *chk_dir; bool chk_pinned; int8_t *zc_act; float *zc_rew; uint8_t *zc_done; int8_t *zc_dir; uint8_t *zc_obs;   // BB_HOST_ZEROCOPY
@@ -655,7 +664,7 @@ static int make_params(const bb_level_spec *s, LevelParams *lp)
     return e ? fail("%s", e) : 0;
 }
 
-static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false, int min_keep = 0, bool beside = false)
+static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_rounds = 0, int min_active = 0, bool snap_heads = false, int min_keep = 0, bool beside = false, int chain_cap = 0)
 {
     cudaMemsetAsync(p->P.gen_count, 0, 8 * sizeof(uint32_t), st);      // list counters + work ticket
     k_gen_scan<<<(p->n + 255) / 256, 256, 0, st>>>(p->P, p->n, target, snap_heads ? 1 : 0);
@@ -667,8 +676,8 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_r
         // keep the next rollout launch from its 7 CTAs per SM (measured r02c: k_rollout_cta 7.5 -> 10.3 us per step beside an
         // 8-blocks-per-SM pass); the pass is latency bound on its longest chain, not throughput bound
         const int blocks = beside && p->gen_blocks_beside < p->gen_blocks ? p->gen_blocks_beside : p->gen_blocks;
-        if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK || p->lp.kind == KIND_BONUS) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes);
-        else k_gen<false><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes);
+        if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK || p->lp.kind == KIND_BONUS) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes, chain_cap);
+        else k_gen<false><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes, chain_cap);
     }
 }
 
@@ -806,6 +815,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (const char *e = getenv("BB_GEN_MIN_ACTIVE")) p->gen_min_active = atoi(e);
     p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
     p->refill_cap = 0; p->last_T = 0;
+    p->chain_cap = 2;
+    if (const char *e = getenv("BB_GEN_CHAIN_CAP")) { int v = atoi(e); if (v >= 0 && v <= 1024) p->chain_cap = v; }
     if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) { p->refill_every = v; p->refill_cap = v; } }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
@@ -1029,11 +1040,18 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     // the side stream, beside the rollouts): a pass is forked at every R-th launch from a head snapshot taken before that
     // launch and joined R launches later, so it overlaps R launches; it tops every ring up to D relative to its snapshot,
     // the R launches it overlaps and the R launches until the next pass is joined consume at most 2 R T: R = D / 2T.
+    // Chain cap (k_gen levels): a pass gives a ring that is at least half full at most `chain_cap` levels, a ring below half
+    // is filled up.  Then every ring holds >= D/2 - RT levels at a fork (induction over the passes), its additions may be
+    // published as late as the join, R launches later: D/2 - 2RT >= 0, R = D / 4T.
     const bool conc = p->gen_concurrent && p->mode == BB_MODE_AUTORESET;
+    const bool kgen_levels = !(p->lp.small && !p->gen_generic);
+    const int cap = kgen_levels && p->chain_cap > 0 && p->D >= 4 * T ? p->chain_cap : 0;
     int R = p->refill_every;
-    if (conc) { R = p->D / (2 * T); if (R > 8) R = 8; if (p->refill_cap > 0 && R > p->refill_cap) R = p->refill_cap; }
+    if (conc) R = p->D / (2 * T);
+    if (cap) R = p->D / (4 * T);
+    if (conc || cap) { if (R > 8) R = 8; if (p->refill_cap > 0 && R > p->refill_cap) R = p->refill_cap; }
     const bool persistent = p->lp.cells_pad <= p->persist_max_cells && !p->no_persistent &&
-                            (p->mode == BB_MODE_FREEZE || (conc ? R >= 1 : p->D >= (p->refill_every + 1) * T));
+                            (p->mode == BB_MODE_FREEZE || (conc || cap ? R >= 1 : p->D >= (p->refill_every + 1) * T));
     if (!persistent) return rollout_graph(p, actions_dev, T, obs_dev, reward_dev, done_dev, dir_dev, user);
     if (T != p->last_T) { p->rollouts = 0; p->last_T = T; }       // a different rollout length restarts the refill schedule
     const bool refill_slot = (p->rollouts % R) == 0;
@@ -1072,7 +1090,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         if (dbg_timing) cudaEventRecord(dbg_ev[2], user);
         const bool fused_snap = p->lp.small && !p->gen_generic;       // k_gen_scan takes the head snapshot itself
         if (!fused_snap) CU(cudaMemcpyAsync(p->P.head_snap, p->P.head, nb, cudaMemcpyDeviceToDevice, user));
-        launch_gen_kernel(p, p->D, user, p->gen_budget, p->gen_min_active, fused_snap, p->refill_every * T);
+        launch_gen_kernel(p, p->D, user, p->gen_budget, p->gen_min_active, fused_snap, p->refill_every * T, false, cap);
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, user);
         if (dbg_timing) { cudaEventRecord(dbg_ev[3], user); p->tev_refill = true; }
         p->launches++;
@@ -1097,7 +1115,7 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (refill && !gen_serial) {
         CU(cudaStreamWaitEvent(p->gen_stream, p->ev_fork, 0));
         if (dbg_timing) cudaEventRecord(dbg_ev[2], p->gen_stream);
-        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget, p->gen_min_active, false, (p->refill_every + 1) * T, true);      // bounded: runs beside k_rollout
+        launch_gen_kernel(p, p->D, p->gen_stream, p->gen_budget, p->gen_min_active, false, (p->refill_every + 1) * T, true, cap);      // bounded: runs beside k_rollout
         cudaMemcpyAsync(p->P.tail_pub, p->P.tail, nb, cudaMemcpyDeviceToDevice, p->gen_stream);
         if (dbg_timing) { cudaEventRecord(dbg_ev[3], p->gen_stream); p->tev_refill = true; }
         p->gen_outstanding = true;
