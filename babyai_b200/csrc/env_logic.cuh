@@ -47,6 +47,17 @@
 #else
 #define BB_GEN_WARP 0
 #endif
+// The cooperative generator is bound by INSTRUCTION FETCH (k_gen: 41 700 instructions = 667 KB against a 32 KB L1.5
+// instruction cache; `no_instruction` the top stall, ncu r02c): the helpers that the grammar inlines at dozens of call sites
+// are real functions there (BB_GEN_OUTLINE=0: everything inlined, as in round 1).
+#ifndef BB_GEN_OUTLINE
+#define BB_GEN_OUTLINE 1
+#endif
+#if defined(__CUDACC__) && BB_GEN_COOP && BB_GEN_OUTLINE
+#define BB_GEN_FN __host__ __device__ __noinline__
+#else
+#define BB_GEN_FN BB_HD
+#endif
 
 namespace bb {
 
@@ -194,6 +205,24 @@ struct RngScalar {
 // Warp-cooperative form (generate_level on the device): the WHOLE WARP runs one environment with identical
 // control flow, the 32 lanes compute 32 consecutive Philox blocks (128 draws) at once and a draw is a shuffle
 // from the lane that holds its block.  In the host build it is the scalar generator.
+#if BB_GEN_WARP
+// One Philox block, OUT OF LINE: the cooperative generator draws at ~600 call sites and needs a new block at one draw in
+// 128; inlined, the ten rounds were 45 % of k_gen's 41 700 instructions (667 KB of code against a 32 KB L1.5 instruction
+// cache: `no_instruction` was the top stall of the kernel, ncu r02c).
+static __device__ __noinline__ uint4 philox_block_ool(uint32_t k0, uint32_t k1, uint64_t n)
+{
+    uint32_t c0 = (uint32_t)n, c1 = (uint32_t)(n >> 32), c2 = 0, c3 = 0, x0 = k0, x1 = k1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ x0, n2 = hi0 ^ c3 ^ x1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+#endif
 struct Rng : RngScalar {
 #if BB_GEN_WARP
     __device__ __forceinline__ uint32_t u32()
@@ -203,12 +232,17 @@ struct Rng : RngScalar {
         const uint32_t w = (uint32_t)i & 3u;
         if (blk == ~0ull || nb - blk >= 32ull) {          // warp-uniform condition
             blk = nb;
-            refill(nb + (threadIdx.x & 31));
+            const uint4 b = philox_block_ool(k0, k1, nb + (threadIdx.x & 31));
+            b0 = b.x; b1 = b.y; b2 = b.z; b3 = b.w;
         }
         const uint32_t mine = w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
         return __shfl_sync(0xFFFFFFFFu, mine, (int)(nb - blk));
     }
+#if BB_GEN_OUTLINE
+    __device__ __noinline__ int randint(int lo, int hi)        // one copy: see BB_GEN_OUTLINE
+#else
     __device__ __forceinline__ int randint(int lo, int hi)
+#endif
     {
         uint32_t n = (uint32_t)(hi - lo);
         if (n == 1) return lo;
@@ -332,7 +366,7 @@ BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
 }
 
 // MiniGridEnv.place_obj over one room rectangle (walls included), App. A.3
-BB_HD int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_to, int &ox, int &oy)
+BB_GEN_FN int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_to, int &ox, int &oy)
 {
     const int S = lp.room_size;
     const int tx = (room % lp.num_cols) * (S - 1), ty = (room / lp.num_cols) * (S - 1);
@@ -352,7 +386,7 @@ BB_HD int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_t
 }
 
 // RoomGrid.add_object -> place_in_room
-BB_HD int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id, bool untracked = false)
+BB_GEN_FN int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id, bool untracked = false)
 {
     int x, y;
     if (untracked) {                    // KIND_UNLOCK: no table entry, the object is its cell byte (rendered by generate_level_t<true>)
@@ -390,7 +424,7 @@ BB_HD bool g_has_door(const LevelParams &lp, const GenCtx &g, int room, int k)
 }
 
 // RoomGrid.add_door(i, j, door_idx, color, locked) with everything decided
-BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int k, int color, bool locked)
+BB_GEN_FN int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int k, int color, bool locked)
 {
     const int S = lp.room_size;
     int owner = k == 2 ? room - 1 : k == 3 ? room - lp.num_cols : room;
@@ -407,7 +441,7 @@ BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ro
 }
 
 // RoomGrid.place_agent(i=None, j=None, rand_dir=True)
-BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g, int room_given = -1)
+BB_GEN_FN int g_place_agent(const LevelParams &lp, GenCtx &g, int room_given = -1)
 {
     int room = room_given;
     if (room < 0) {
@@ -595,7 +629,7 @@ BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
 
 // ObjDesc.find_matching_objs(env, use_location=True) over the object table
 // (verifier.py:96-161): every object is on the grid at generation time.
-BB_HD uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &o, int type, int color, int loc)
+BB_GEN_FN uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &o, int type, int color, int loc)
 {
     const int S = lp.room_size;
     const int rtx = (g.ax / (S - 1)) * (S - 1), rty = (g.ay / (S - 1)) * (S - 1);   // agent room top
@@ -619,7 +653,7 @@ BB_HD uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &o
 }
 
 // LevelGen.rand_obj (levelgen.py:354-395); types: 4 = OBJ_TYPES, 3 = NOT_DOOR, 1 = ['door']
-BB_HD int g_rand_obj(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ntypes, int d)
+BB_GEN_FN int g_rand_obj(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ntypes, int d)
 {
     const int S = lp.room_size;
     int tries = 0;
@@ -1174,7 +1208,7 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 }
 
 // ---- mission tokens (Instr.surface / ObjDesc.surface, verifier.py:64-94 ...) --
-BB_HD int tok_desc(const GenCtx &g, int d, int16_t *tok, int n)
+BB_GEN_FN int tok_desc(const GenCtx &g, int d, int16_t *tok, int n)
 {
     // ('a' when several objects match.  find_matching_objs scans every grid cell, walls included: a description by colour
     // alone -- ObjDesc(None, 'grey'), Level_PickupDist -- also matches the grey walls, so it is always 'a grey object')

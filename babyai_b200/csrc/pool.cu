@@ -792,7 +792,9 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         CUP(cudaGetDeviceProperties(&prop, device));
         p->sm_count = prop.multiProcessorCount;
         int want = (n_envs + GEN_THREADS / 32 - 1) / (GEN_THREADS / 32);      // one warp per env at most
-        int cap = prop.multiProcessorCount * GEN_BLOCKS_PER_SM;      // a multiple of the SM count
+        int gen_per_sm = GEN_BLOCKS_PER_SM;
+        if (const char *e = getenv("BB_GEN_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) gen_per_sm = v; }
+        int cap = prop.multiProcessorCount * gen_per_sm;             // a multiple of the SM count
         p->gen_blocks = want < cap ? want : cap;
         p->gen_lanes = 8;                                   // working lanes per warp of the lane-per-level k_gen
         if (const char *e = getenv("BB_GEN_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) p->gen_lanes = v; }
