@@ -223,34 +223,48 @@ static __device__ __noinline__ uint4 philox_block_ool(uint32_t k0, uint32_t k1, 
     return make_uint4(c0, c1, c2, c3);
 }
 #endif
-struct Rng : RngScalar {
 #if BB_GEN_WARP
+// The warp's random stream: 128 consecutive draws (32 Philox blocks, one per lane) sit in the warp's shared GenMem; a draw is
+// one broadcast shared-memory load.  (Round 1 kept the four words of a lane's block in registers and shuffled: a 64-bit
+// counter, three selects and a shuffle per draw, ~25 instructions at each of ~600 call sites.)
+struct Rng {
+    uint32_t k0, k1;
+    uint64_t base;                // draw index of buf[0], a multiple of 4
+    uint32_t pos;                 // draws consumed from buf; 128 = used up
+    uint32_t *buf;                // GenMem::draw_buf
+    __device__ __forceinline__ void fill()
+    {
+        __syncwarp();
+        const uint4 b = philox_block_ool(k0, k1, (base >> 2) + (threadIdx.x & 31));
+        reinterpret_cast<uint4 *>(buf)[threadIdx.x & 31] = b;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t d, uint32_t *b)
+    {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); buf = b;
+        base = d & ~3ull; pos = (uint32_t)d & 3u;
+        fill();
+    }
+    __device__ __forceinline__ uint64_t count() const { return base + pos; }
     __device__ __forceinline__ uint32_t u32()
     {
-        const uint64_t i = draws++;
-        const uint64_t nb = i >> 2;
-        const uint32_t w = (uint32_t)i & 3u;
-        if (blk == ~0ull || nb - blk >= 32ull) {          // warp-uniform condition
-            blk = nb;
-            const uint4 b = philox_block_ool(k0, k1, nb + (threadIdx.x & 31));
-            b0 = b.x; b1 = b.y; b2 = b.z; b3 = b.w;
-        }
-        const uint32_t mine = w == 0 ? b0 : w == 1 ? b1 : w == 2 ? b2 : b3;
-        return __shfl_sync(0xFFFFFFFFu, mine, (int)(nb - blk));
+        if (pos >= 128u) { base += 128ull; pos = 0; fill(); }      // warp-uniform
+        return buf[pos++];
     }
-#if BB_GEN_OUTLINE
-    __device__ __noinline__ int randint(int lo, int hi)        // one copy: see BB_GEN_OUTLINE
-#else
     __device__ __forceinline__ int randint(int lo, int hi)
-#endif
     {
         uint32_t n = (uint32_t)(hi - lo);
         if (n == 1) return lo;
-        return lo + (int)mulhi32(u32(), n);
+        return lo + (int)__umulhi(u32(), n);
     }
     __device__ __forceinline__ bool randbool() { return randint(0, 2) == 0; }
-#endif
 };
+#else
+struct Rng : RngScalar {
+    BB_HD void init(uint64_t seed, uint64_t d, uint32_t *) { RngScalar::init(seed, d); }
+    BB_HD uint64_t count() const { return draws; }
+};
+#endif
 
 BB_HD int popc32(uint32_t v)
 {
@@ -312,6 +326,9 @@ struct GenMem {
     uint32_t desc_mask[8];
     int16_t tok[MAXTOK];
     ObjTab obj;                    // object table under construction (copied to the slot at the end)
+#if defined(__CUDACC__) && BB_GEN_COOP
+    BB_ALIGN16 uint32_t draw_buf[128];   // the warp's next 128 draws (struct Rng)
+#endif
 };
 
 struct GenMemX : GenMem {          // KIND_UNLOCK only: the untracked objects of the level under construction
@@ -366,7 +383,7 @@ BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
 }
 
 // MiniGridEnv.place_obj over one room rectangle (walls included), App. A.3
-BB_GEN_FN int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_to, int &ox, int &oy)
+BB_HD int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_to, int &ox, int &oy)
 {
     const int S = lp.room_size;
     const int tx = (room % lp.num_cols) * (S - 1), ty = (room / lp.num_cols) * (S - 1);
@@ -386,7 +403,7 @@ BB_GEN_FN int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_ne
 }
 
 // RoomGrid.add_object -> place_in_room
-BB_GEN_FN int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id, bool untracked = false)
+BB_HD int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int type, int color, int &id, bool untracked = false)
 {
     int x, y;
     if (untracked) {                    // KIND_UNLOCK: no table entry, the object is its cell byte (rendered by generate_level_t<true>)
@@ -424,7 +441,7 @@ BB_HD bool g_has_door(const LevelParams &lp, const GenCtx &g, int room, int k)
 }
 
 // RoomGrid.add_door(i, j, door_idx, color, locked) with everything decided
-BB_GEN_FN int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int k, int color, bool locked)
+BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int room, int k, int color, bool locked)
 {
     const int S = lp.room_size;
     int owner = k == 2 ? room - 1 : k == 3 ? room - lp.num_cols : room;
@@ -441,7 +458,7 @@ BB_GEN_FN int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, in
 }
 
 // RoomGrid.place_agent(i=None, j=None, rand_dir=True)
-BB_GEN_FN int g_place_agent(const LevelParams &lp, GenCtx &g, int room_given = -1)
+BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g, int room_given = -1)
 {
     int room = room_given;
     if (room < 0) {
@@ -499,14 +516,12 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o, int
         if (itrs > 5000) return GEN_RECURSION;
         itrs++;
         if (stale) {
+            // find_reach as a flood over room bitmasks: door_right bit r joins rooms r and r + 1 (set only where the slot
+            // exists), door_down bit r joins r and r + C
             reach = 1u << start;
-            for (;;) {                    // find_reach as a fixpoint over room bitmasks
-                uint32_t nr = reach;
-                for (int r = 0; r < NR; r++) {
-                    if (!((reach >> r) & 1u)) continue;
-                    for (int k = 0; k < 4; k++)
-                        if (g_has_slot(lp, r, k) && g_has_door(lp, g, r, k)) nr |= 1u << g_neighbor(lp, r, k);
-                }
+            for (;;) {
+                const uint32_t nr = reach | ((reach & g.door_right) << 1) | ((reach >> 1) & g.door_right) |
+                                    ((reach & g.door_down) << C) | ((reach >> C) & g.door_down);
                 if (nr == reach) break;
                 reach = nr;
             }
@@ -635,7 +650,12 @@ BB_GEN_FN uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOu
     const int rtx = (g.ax / (S - 1)) * (S - 1), rty = (g.ay / (S - 1)) * (S - 1);   // agent room top
     const int d1x = dir_dx(g.adir), d1y = dir_dy(g.adir), d2x = -d1y, d2y = d1x;
     uint32_t m = 0;
-    for (int k = 0; k < g.nobj; k++) {
+#if BB_GEN_WARP
+    const int k0 = threadIdx.x & 31, kstep = 32;       // lane k tests object k, the mask is a ballot
+#else
+    const int k0 = 0, kstep = 1;
+#endif
+    for (int k = k0; k < g.nobj; k += kstep) {
         int tc = g.m->obj.tc[k];
         if (type != ANY_TYPE && (tc & 7) != type) continue;
         if (color != ANY && (tc >> 3) != color) continue;
@@ -649,6 +669,9 @@ BB_GEN_FN uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOu
         }
         m |= 1u << k;
     }
+#if BB_GEN_WARP
+    m = __reduce_or_sync(0xFFFFFFFFu, m);
+#endif
     return m;
 }
 
@@ -1242,6 +1265,13 @@ BB_HD int tok_side(const GenCtx &g, int side, int16_t *tok, int n)
     return n;
 }
 
+// four cells from four wall bits: wall (0x2A) where the bit is set, empty (0x01) elsewhere
+BB_HD uint32_t g_cells4(uint32_t bits)
+{
+    const uint32_t e = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+    return ((uint32_t)CELL_WALL * 0x01010101u & e) | ((uint32_t)CELL_EMPTY * 0x01010101u & ~e);
+}
+
 // One whole RoomGridLevel.reset() worth of generation (levelgen.py:35-47,77-102):
 // retries until an attempt is accepted, then renders grid + records into `o`.
 // Returns the number of attempts.
@@ -1250,7 +1280,11 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
 {
     GenCtx g;
     g.m = mem;
-    g.rng.init(rngrec->seed, rngrec->draws);
+#if defined(__CUDACC__) && BB_GEN_COOP
+    g.rng.init(rngrec->seed, rngrec->draws, mem->draw_buf);
+#else
+    g.rng.init(rngrec->seed, rngrec->draws, nullptr);
+#endif
     g.locked_room = *locked_room_persist == 0xFF ? -1 : (int)*locked_room_persist;
     int attempts = 0;
     for (;;) {
@@ -1260,7 +1294,7 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
         if (g_validate(lp, g, o)) continue;
         break;
     }
-    rngrec->draws = g.rng.draws;
+    rngrec->draws = g.rng.count();
     *locked_room_persist = g.locked_room < 0 ? 0xFF : (uint8_t)g.locked_room;
 
     // ---- render the byte grid: walls, then doors/objects -----------------
@@ -1270,19 +1304,28 @@ BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, Rn
 #else
     const int lane = 0, nlanes = 1;
 #endif
-    // G (row-major) and GT (column-major); row padding up to the stride is wall
-    for (int c = lane; c < lp.H * lp.rs_g; c += nlanes) {
-        const int y = c / lp.rs_g, x = c - y * lp.rs_g;
-        o.grid[c] = (uint8_t)((x >= lp.W || ((g.m->wallmask[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
-    }
-    for (int c = lane; c < lp.W * lp.rs_t; c += nlanes) {
-        const int x = c / lp.rs_t, y = c - x * lp.rs_t;
-        o.grid[lp.gt_off + c] = (uint8_t)((y >= lp.H || ((g.m->wallmask[y] >> x) & 1u)) ? CELL_WALL : CELL_EMPTY);
+    // G (row-major) and GT (column-major), four cells per 32-bit store; row padding up to the stride is wall
+    {
+        uint32_t *gw = reinterpret_cast<uint32_t *>(o.grid);
+        const int gwpr = lp.rs_g >> 2, twpr = lp.rs_t >> 2;
+        for (int c = lane; c < lp.H * gwpr; c += nlanes) {
+            const int y = c / gwpr, x0 = (c - y * gwpr) * 4;
+            uint32_t bits = (g.m->wallmask[y] >> x0) & 0xFu;
+            for (int b = 0; b < 4; b++) if (x0 + b >= lp.W) bits |= 1u << b;
+            gw[c] = g_cells4(bits);
+        }
+        uint32_t *tw = reinterpret_cast<uint32_t *>(o.grid + lp.gt_off);
+        for (int c = lane; c < lp.W * twpr; c += nlanes) {
+            const int x = c / twpr, y0 = (c - x * twpr) * 4;
+            uint32_t bits = 0;
+            for (int b = 0; b < 4; b++) bits |= (y0 + b >= lp.H ? 1u : ((g.m->wallmask[y0 + b < lp.H ? y0 + b : 0] >> x) & 1u)) << b;
+            tw[c] = g_cells4(bits);
+        }
     }
 #if BB_GEN_WARP
     __syncwarp();
 #endif
-    for (int k = 0; k < g.nobj; k++) {
+    for (int k = lane; k < g.nobj; k += nlanes) {          // objects never share a cell (a hidden one is not on the grid)
         if ((g.hidden_mask >> k) & 1u) continue;
         int tc = g.m->obj.tc[k], st = 0;
         if ((tc & 7) == T_DOOR) st = lp.doors_open ? 0 : (((g.locked_mask >> k) & 1u) ? 2 : 1);   // open_all_doors levelgen.py:189-199
