@@ -227,18 +227,20 @@ static __device__ __noinline__ uint4 philox_block_ool(uint32_t k0, uint32_t k1, 
 // The warp's random stream: 128 consecutive draws (32 Philox blocks, one per lane) sit in the warp's shared GenMem; a draw is
 // one broadcast shared-memory load.  (Round 1 kept the four words of a lane's block in registers and shuffled: a 64-bit
 // counter, three selects and a shuffle per draw, ~25 instructions at each of ~600 call sites.)
+// the cold path of a draw, one copy, arguments by value (the Rng itself stays in registers)
+static __device__ __noinline__ void rng_fill_ool(uint32_t k0, uint32_t k1, uint64_t base, uint32_t *buf)
+{
+    __syncwarp();
+    const uint4 b = philox_block_ool(k0, k1, (base >> 2) + (threadIdx.x & 31));
+    reinterpret_cast<uint4 *>(buf)[threadIdx.x & 31] = b;
+    __syncwarp();
+}
 struct Rng {
     uint32_t k0, k1;
     uint64_t base;                // draw index of buf[0], a multiple of 4
     uint32_t pos;                 // draws consumed from buf; 128 = used up
     uint32_t *buf;                // GenMem::draw_buf
-    __device__ __forceinline__ void fill()
-    {
-        __syncwarp();
-        const uint4 b = philox_block_ool(k0, k1, (base >> 2) + (threadIdx.x & 31));
-        reinterpret_cast<uint4 *>(buf)[threadIdx.x & 31] = b;
-        __syncwarp();
-    }
+    __device__ __forceinline__ void fill() { rng_fill_ool(k0, k1, base, buf); }
     __device__ __forceinline__ void init(uint64_t seed, uint64_t d, uint32_t *b)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); buf = b;
@@ -644,25 +646,27 @@ BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
 
 // ObjDesc.find_matching_objs(env, use_location=True) over the object table
 // (verifier.py:96-161): every object is on the grid at generation time.
-BB_GEN_FN uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &o, int type, int color, int loc)
+// (out of line in the cooperative device build: everything it needs comes by value, so the caller's GenCtx stays in registers)
+struct MatchPose { int nobj, ax, ay, adir; };
+BB_GEN_FN uint32_t g_match_pose(const LevelParams &lp, const GenMem *gm, const MatchPose mp, int type, int color, int loc)
 {
     const int S = lp.room_size;
-    const int rtx = (g.ax / (S - 1)) * (S - 1), rty = (g.ay / (S - 1)) * (S - 1);   // agent room top
-    const int d1x = dir_dx(g.adir), d1y = dir_dy(g.adir), d2x = -d1y, d2y = d1x;
+    const int rtx = (mp.ax / (S - 1)) * (S - 1), rty = (mp.ay / (S - 1)) * (S - 1);   // agent room top
+    const int d1x = dir_dx(mp.adir), d1y = dir_dy(mp.adir), d2x = -d1y, d2y = d1x;
     uint32_t m = 0;
 #if BB_GEN_WARP
     const int k0 = threadIdx.x & 31, kstep = 32;       // lane k tests object k, the mask is a ballot
 #else
     const int k0 = 0, kstep = 1;
 #endif
-    for (int k = k0; k < g.nobj; k += kstep) {
-        int tc = g.m->obj.tc[k];
+    for (int k = k0; k < mp.nobj; k += kstep) {
+        int tc = gm->obj.tc[k];
         if (type != ANY_TYPE && (tc & 7) != type) continue;
         if (color != ANY && (tc >> 3) != color) continue;
         if (loc != LOC_NONE) {
-            int x = g.m->obj.x[k], y = g.m->obj.y[k];
+            int x = gm->obj.x[k], y = gm->obj.y[k];
             if (x < rtx || y < rty || x >= rtx + S || y >= rty + S) continue;   // Room.pos_inside
-            int vx = x - g.ax, vy = y - g.ay;
+            int vx = x - mp.ax, vy = y - mp.ay;
             int dot1 = vx * d1x + vy * d1y, dot2 = vx * d2x + vy * d2y;
             bool ok = loc == LOC_LEFT ? dot2 < 0 : loc == LOC_RIGHT ? dot2 > 0 : loc == LOC_FRONT ? dot1 > 0 : dot1 < 0;
             if (!ok) continue;
@@ -674,37 +678,54 @@ BB_GEN_FN uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOu
 #endif
     return m;
 }
+BB_HD uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &, int type, int color, int loc)
+{
+    const MatchPose mp = { g.nobj, g.ax, g.ay, g.adir };
+    return g_match_pose(lp, g.m, mp, type, color, loc);
+}
 
 // LevelGen.rand_obj (levelgen.py:354-395); types: 4 = OBJ_TYPES, 3 = NOT_DOOR, 1 = ['door']
-BB_GEN_FN int g_rand_obj(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ntypes, int d)
+// Out of line in the cooperative device build, with its own copy of the random stream: takes and returns it BY VALUE, so that
+// the caller's GenCtx never has its address taken and stays in registers.
+struct RandObjRes { Rng rng; int status; };
+BB_GEN_FN RandObjRes g_rand_obj_v(const LevelParams &lp, GenMem *gm, Rng rng, const MatchPose mp, int locked_room, int ntypes, int d)
 {
     const int S = lp.room_size;
+    RandObjRes res;
     int tries = 0;
     for (;;) {
-        if (tries > 100) return GEN_RECURSION;
+        if (tries > 100) { res.rng = rng; res.status = GEN_RECURSION; return res; }
         tries++;
-        int ci = g.rng.randint(0, 7);                                  // [None, *COLOR_NAMES]
+        int ci = rng.randint(0, 7);                                  // [None, *COLOR_NAMES]
         int color = ci == 0 ? ANY : color_by_name_rank(ci - 1);
-        int ti = g.rng.randint(0, ntypes);
+        int ti = rng.randint(0, ntypes);
         int type = ntypes == 1 ? T_DOOR : (ti == 0 ? T_BOX : ti == 1 ? T_BALL : ti == 2 ? T_KEY : T_DOOR);
         int loc = LOC_NONE;
-        if (lp.locations && g.rng.randbool()) loc = g.rng.randint(0, 4);   // LOC_NAMES order
-        uint32_t m = g_match(lp, g, o, type, color, loc);
+        if (lp.locations && rng.randbool()) loc = rng.randint(0, 4);   // LOC_NAMES order
+        uint32_t m = g_match_pose(lp, gm, mp, type, color, loc);
         if (m == 0) continue;
-        if (!lp.implicit_unlock && g.locked_room >= 0) {
+        if (!lp.implicit_unlock && locked_room >= 0) {
             // at least one match outside the (possibly stale) locked room's rectangle
-            int ltx = (g.locked_room % lp.num_cols) * (S - 1), lty = (g.locked_room / lp.num_cols) * (S - 1);
+            int ltx = (locked_room % lp.num_cols) * (S - 1), lty = (locked_room / lp.num_cols) * (S - 1);
             bool outside = false;
             for (uint32_t mm = m; mm; mm &= mm - 1) {
                 int k = ffs32(mm);
-                int x = g.m->obj.x[k], y = g.m->obj.y[k];
+                int x = gm->obj.x[k], y = gm->obj.y[k];
                 if (x < ltx || y < lty || x >= ltx + S || y >= lty + S) outside = true;
             }
             if (!outside) continue;
         }
-        g.m->desc_type[d] = type; g.m->desc_color[d] = color; g.m->desc_loc[d] = loc; g.m->desc_mask[d] = m;
-        return GEN_OK;
+        gm->desc_type[d] = type; gm->desc_color[d] = color; gm->desc_loc[d] = loc; gm->desc_mask[d] = m;
+        res.rng = rng; res.status = GEN_OK;
+        return res;
     }
+}
+BB_HD int g_rand_obj(const LevelParams &lp, GenCtx &g, const LevelOut &, int ntypes, int d)
+{
+    const MatchPose mp = { g.nobj, g.ax, g.ay, g.adir };
+    const RandObjRes r = g_rand_obj_v(lp, g.m, g.rng, mp, g.locked_room, ntypes, d);
+    g.rng = r.rng;
+    return r.status;
 }
 
 // one ActionInstr of rand_instr (levelgen.py:409-424) into leaf slot `leaf`
@@ -1231,16 +1252,16 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 }
 
 // ---- mission tokens (Instr.surface / ObjDesc.surface, verifier.py:64-94 ...) --
-BB_GEN_FN int tok_desc(const GenCtx &g, int d, int16_t *tok, int n)
+BB_GEN_FN int tok_desc(const GenMem *gm, int d, int16_t *tok, int n)
 {
     // ('a' when several objects match.  find_matching_objs scans every grid cell, walls included: a description by colour
     // alone -- ObjDesc(None, 'grey'), Level_PickupDist -- also matches the grey walls, so it is always 'a grey object')
-    const bool many = popc32(g.m->desc_mask[d]) > 1 || (g.m->desc_type[d] == ANY_TYPE && g.m->desc_color[d] == C_GREY);
+    const bool many = popc32(gm->desc_mask[d]) > 1 || (gm->desc_type[d] == ANY_TYPE && gm->desc_color[d] == C_GREY);
     tok[n++] = many ? W_A : W_THE;
-    if (g.m->desc_color[d] != ANY) tok[n++] = (int16_t)(W_RED + g.m->desc_color[d]);
-    int t = g.m->desc_type[d];
+    if (gm->desc_color[d] != ANY) tok[n++] = (int16_t)(W_RED + gm->desc_color[d]);
+    int t = gm->desc_type[d];
     tok[n++] = (int16_t)(t == ANY_TYPE ? W_OBJECT : t == T_BOX ? W_BOX : t == T_BALL ? W_BALL : t == T_KEY ? W_KEY : W_DOOR);
-    int loc = g.m->desc_loc[d];
+    int loc = gm->desc_loc[d];
     if (loc == LOC_FRONT) { tok[n++] = W_IN; tok[n++] = W_FRONT; tok[n++] = W_OF; tok[n++] = W_YOU; }
     else if (loc == LOC_BEHIND) { tok[n++] = W_BEHIND; tok[n++] = W_YOU; }
     else if (loc == LOC_LEFT) { tok[n++] = W_ON; tok[n++] = W_YOUR; tok[n++] = W_LEFT; }
@@ -1254,8 +1275,8 @@ BB_HD int tok_leaf(const GenCtx &g, int leaf, int16_t *tok, int n)
     else if (k == I_PICKUP) { tok[n++] = W_PICK; tok[n++] = W_UP; }
     else if (k == I_OPEN) { tok[n++] = W_OPEN; }
     else { tok[n++] = W_PUT; }
-    n = tok_desc(g, 2 * leaf, tok, n);
-    if (k == I_PUTNEXT) { tok[n++] = W_NEXT; tok[n++] = W_TO; n = tok_desc(g, 2 * leaf + 1, tok, n); }
+    n = tok_desc(g.m, 2 * leaf, tok, n);
+    if (k == I_PUTNEXT) { tok[n++] = W_NEXT; tok[n++] = W_TO; n = tok_desc(g.m, 2 * leaf + 1, tok, n); }
     return n;
 }
 BB_HD int tok_side(const GenCtx &g, int side, int16_t *tok, int n)

@@ -421,12 +421,21 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
 // k_rollout_cta -- bb_pool_rollout on MULTI-ROOM levels: 32 envs per CTA, a lane-per-env step phase and a 4-lanes-per-env
 // observation phase per step, row-major grid only in shared memory (rollout_cta.cuh has the design and the numbers).
 template <bool UNTR>
-__global__ void __launch_bounds__(RC_THREADS, 8)
+__global__ void __launch_bounds__(RC_THREADS, 7)
 k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
               float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T, const int mode)
 {
     extern __shared__ __align__(16) uint32_t smc[];
     rollout_cta_role<PoolPtrs, UNTR>(lp, P, actions, obs, reward, done, dirs, n, T, mode, smc, threadIdx.x, blockIdx.x);
+}
+// version 1 (stepper and observers in lock-step, two CTA barriers per step): BB_ROLLOUT_KERNEL=cta1, kept for the A/B
+template <bool UNTR>
+__global__ void __launch_bounds__(RC_THREADS, 8)
+k_rollout_cta_v1(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
+                 float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T, const int mode)
+{
+    extern __shared__ __align__(16) uint32_t smc[];
+    rollout_cta_role_v1<PoolPtrs, UNTR>(lp, P, actions, obs, reward, done, dirs, n, T, mode, smc, threadIdx.x, blockIdx.x);
 }
 
 // Level generation, decoupled from the step: tops every environment's ring up to `target` levels.
@@ -615,6 +624,7 @@ struct bb_pool {
     int D, G, nev;
     bool gen_generic; int gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
+    bool rollout_cta_v1;
     bool rollout_cta;              // bb_pool_rollout through k_rollout_cta (default on multi-room levels; BB_ROLLOUT_KERNEL=lane|cta)
     bool step_cols;                // BB_STEP_KERNEL=cols: k_step8 for every level (default: k_rollout with T = 1 on single-room grids)
     long long rel;
@@ -845,7 +855,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
     p->step_cols = false;
     p->rollout_cta = p->lp.num_rows * p->lp.num_cols > 1;
-    if (const char *e = getenv("BB_ROLLOUT_KERNEL")) p->rollout_cta = !strcmp(e, "cta");
+    p->rollout_cta_v1 = false;
+    if (const char *e = getenv("BB_ROLLOUT_KERNEL")) { p->rollout_cta = !strcmp(e, "cta") || !strcmp(e, "cta1"); p->rollout_cta_v1 = !strcmp(e, "cta1"); }
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
     p->persist_max_cells = 1152;                           // k_rollout stages up to 22 x 22 grids (2 x 43 KB of shared memory per CTA)
     if (const char *e = getenv("BB_PERSIST_MAX_CELLS")) p->persist_max_cells = atoi(e);
@@ -884,6 +895,10 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CUP(cudaFuncSetAttribute(k_rollout_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout_cta<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUP(cudaFuncSetAttribute(k_rollout_cta<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
     // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
     CUP(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1103,10 +1118,16 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     }
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
     if (p->rollout_cta) {                  // multi-room levels: 32 envs per CTA, step phase + 4-lanes-per-env observation phase
-        const size_t smc = (size_t)rc_cta_words(p->lp) * 4;
         const int blocks_c = (p->n + RC_ENVS - 1) / RC_ENVS;
-        if (p->lp.kind == KIND_UNLOCK) k_rollout_cta<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-        else k_rollout_cta<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+        if (p->rollout_cta_v1) {
+            const size_t smc = (size_t)rc_cta_words(p->lp) * 4;
+            if (p->lp.kind == KIND_UNLOCK) k_rollout_cta_v1<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+            else k_rollout_cta_v1<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+        } else {
+            const size_t smc = (size_t)rc2_cta_words(p->lp) * 4;
+            if (p->lp.kind == KIND_UNLOCK) k_rollout_cta<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+            else k_rollout_cta<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+        }
     }
     else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
                                                                                        p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);

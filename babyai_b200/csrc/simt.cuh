@@ -36,6 +36,11 @@ static __device__ __forceinline__ void bb_bulk_store(void *gdst, const void *ssr
 }
 #define BB_BULK_STORE(gdst, ssrc, bytes) bb_bulk_store((gdst), (ssrc), (bytes))
 #define BB_BULK_WAIT_READ() asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory")
+#define BB_BULK_WAIT_READ_N(n) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(n) : "memory")
+// producer / consumer named barriers (ids are immediates: a register id makes ptxas reserve all 16 barriers): every thread
+// of the `nthreads` that take part either arrives (does not wait) or syncs (waits for all of them)
+#define BB_BAR_SYNC(id, nthreads) asm volatile("barrier.sync %0, %1;" ::"n"(id), "r"(nthreads) : "memory")
+#define BB_BAR_ARRIVE(id, nthreads) asm volatile("barrier.arrive %0, %1;" ::"n"(id), "r"(nthreads) : "memory")
 #endif
 
 namespace bb {

@@ -14,6 +14,8 @@
 #include <stdio.h>
 #include <math.h>
 #include <barrier>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -28,6 +30,25 @@ struct WarpCtx {
 static thread_local WarpCtx *tl_warp = nullptr;
 static thread_local int tl_lane = 0;
 static thread_local std::barrier<> *tl_cta = nullptr;       // __syncthreads of a fused launch (4 stepping warps + the generator warp)
+
+// named barriers of a CTA (barrier.arrive / barrier.sync with a thread count): a phase completes when `n` threads have
+// arrived or synced; arrive returns at once, sync waits for the phase to complete
+struct NamedBar { std::mutex m; std::condition_variable cv; int count = 0; unsigned gen = 0; };
+static thread_local NamedBar *tl_named = nullptr;           // 8 per CTA
+static inline void emu_bar_arrive(int id, int n)
+{
+    NamedBar &b = tl_named[id];
+    std::unique_lock<std::mutex> lk(b.m);
+    if (++b.count == n) { b.count = 0; b.gen++; b.cv.notify_all(); }
+}
+static inline void emu_bar_sync(int id, int n)
+{
+    NamedBar &b = tl_named[id];
+    std::unique_lock<std::mutex> lk(b.m);
+    const unsigned g = b.gen;
+    if (++b.count == n) { b.count = 0; b.gen++; b.cv.notify_all(); }
+    else b.cv.wait(lk, [&] { return b.gen != g; });
+}
 
 static thread_local int *tl_cta_or = nullptr;               // two alternating accumulators of __syncthreads_or
 static thread_local int tl_cta_phase = 0;
@@ -83,6 +104,9 @@ template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exch
 #define BB_FENCE_ASYNC_SMEM() ((void)0)
 #define BB_BULK_STORE(gdst, ssrc, bytes) memcpy((gdst), (ssrc), (bytes))
 #define BB_BULK_WAIT_READ() ((void)0)
+#define BB_BULK_WAIT_READ_N(n) ((void)0)
+#define BB_BAR_SYNC(id, n) emu_bar_sync((id), (n))
+#define BB_BAR_ARRIVE(id, n) emu_bar_arrive((id), (n))
 
 #include "../../babyai_b200/csrc/simt.cuh"
 #include "../../babyai_b200/csrc/gen_round.cuh"
@@ -257,19 +281,20 @@ void r2_rollout_fused(RPool *p, const int8_t *actions, int T, int gen_rounds, in
 void r2_rollout_cta(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *reward, uint8_t *done, int8_t *dirs, int64_t *counters4)
 {
     const LevelParams &lp = p->lp;
-    const int words = rc_cta_words(lp);
+    const int words = rc2_cta_words(lp);
     const int nctas = (p->n + RC_ENVS - 1) / RC_ENVS;
     for (int cta = 0; cta < nctas; cta++) {
         std::vector<WarpCtx> ctx(RC_THREADS / 32);
         std::barrier<> cta_bar(RC_THREADS);
         int cta_or[2] = { 0, 0 };
+        std::vector<NamedBar> named(8);
         std::vector<uint32_t> smem((size_t)words + 8, 0xDEADBEEFu);
         uint32_t *base = smem.data();
         while (((uintptr_t)base) & 15) base++;
         std::vector<std::thread> th;
         for (int tid = 0; tid < RC_THREADS; tid++)
             th.emplace_back([&, tid]() {
-                tl_warp = &ctx[tid >> 5]; tl_lane = tid & 31; tl_cta = &cta_bar; tl_cta_or = cta_or; tl_cta_phase = 0;
+                tl_warp = &ctx[tid >> 5]; tl_lane = tid & 31; tl_cta = &cta_bar; tl_cta_or = cta_or; tl_cta_phase = 0; tl_named = named.data();
                 if (lp.kind == KIND_UNLOCK) rollout_cta_role<HostPoolPtrs, true>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, base, tid, cta);
                 else rollout_cta_role<HostPoolPtrs, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, base, tid, cta);
             });
