@@ -364,7 +364,14 @@ enum : int { GEN_OK = 0, GEN_REJECT = 1, GEN_RECURSION = 2 };
 BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
 {
     const int S = lp.room_size, R = lp.num_rows, C = lp.num_cols;
-    for (int y = 0; y < lp.H; y++) { g.m->occ[y] = lp.wall_rows[y]; g.m->doorcell[y] = 0; g.m->wallmask[y] = lp.wall_rows[y]; }
+#if BB_GEN_WARP
+    // the lanes split the rows and the object-table words (everything else in the generator is the same store from every lane)
+    const int l0 = threadIdx.x & 31, lstep = 32;
+    __syncwarp();
+#else
+    const int l0 = 0, lstep = 1;
+#endif
+    for (int y = l0; y < lp.H; y += lstep) { g.m->occ[y] = lp.wall_rows[y]; g.m->doorcell[y] = 0; g.m->wallmask[y] = lp.wall_rows[y]; }
     for (int j = 0; j < R; j++)
         for (int i = 0; i < C; i++) {
             int r = j * C + i, tx = i * (S - 1), ty = j * (S - 1);
@@ -374,8 +381,11 @@ BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
     g.door_right = g.door_down = g.room_locked = 0;
     {   // unused object-table entries are zero (deterministic state bytes)
         uint32_t *ow = reinterpret_cast<uint32_t *>(&g.m->obj);
-        for (int k = 0; k < (int)(sizeof(ObjTab) / 4); k++) ow[k] = 0;
+        for (int k = l0; k < (int)(sizeof(ObjTab) / 4); k += lstep) ow[k] = 0;
     }
+#if BB_GEN_WARP
+    __syncwarp();
+#endif
     g.nobj = 0; g.nun = 0;
     g.ax = (C / 2) * (S - 1) + S / 2;
     g.ay = (R / 2) * (S - 1) + S / 2;
@@ -534,7 +544,9 @@ BB_HD int g_connect_all(const LevelParams &lp, GenCtx &g, const LevelOut &o, int
         int j = g.rng.randint(0, lp.num_rows);
         int k = g.rng.randint(0, 4);
         int room = j * C + i;
-        if (!g_has_slot(lp, room, k) || g_has_door(lp, g, room, k)) continue;
+        // (the slot test on the drawn (i, j): g_has_slot(room) would divide to get them back)
+        const bool slot = k == 0 ? i < C - 1 : k == 1 ? j < lp.num_rows - 1 : k == 2 ? i > 0 : j > 0;
+        if (!slot || g_has_door(lp, g, room, k)) continue;
         if (((g.room_locked >> room) & 1u) || ((g.room_locked >> g_neighbor(lp, room, k)) & 1u)) continue;
         int color;
         if (exclude < 0) color = color_by_name_rank(g.rng.randint(0, 6));

@@ -428,16 +428,6 @@ k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__
     extern __shared__ __align__(16) uint32_t smc[];
     rollout_cta_role<PoolPtrs, UNTR>(lp, P, actions, obs, reward, done, dirs, n, T, mode, smc, threadIdx.x, blockIdx.x);
 }
-// version 1 (stepper and observers in lock-step, two CTA barriers per step): BB_ROLLOUT_KERNEL=cta1, kept for the A/B
-template <bool UNTR>
-__global__ void __launch_bounds__(RC_THREADS, 8)
-k_rollout_cta_v1(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__ actions, uint8_t *__restrict__ obs,
-                 float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T, const int mode)
-{
-    extern __shared__ __align__(16) uint32_t smc[];
-    rollout_cta_role_v1<PoolPtrs, UNTR>(lp, P, actions, obs, reward, done, dirs, n, T, mode, smc, threadIdx.x, blockIdx.x);
-}
-
 // Level generation, decoupled from the step: tops every environment's ring up to `target` levels.
 //
 // ONE WARP PER ENVIRONMENT.  Generation is a long, branchy, data-dependent rejection-sampling program;
@@ -624,7 +614,6 @@ struct bb_pool {
     int D, G, nev;
     bool gen_generic; int gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
-    bool rollout_cta_v1;
     bool rollout_cta;              // bb_pool_rollout through k_rollout_cta (default on multi-room levels; BB_ROLLOUT_KERNEL=lane|cta)
     bool step_cols;                // BB_STEP_KERNEL=cols: k_step8 for every level (default: k_rollout with T = 1 on single-room grids)
     long long rel;
@@ -682,9 +671,10 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_r
     if (p->lp.small && !p->gen_generic) {
         k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active, min_keep);
     } else {
-        // a pass that runs BESIDE the rollout kernel gets two blocks per SM: with more, its resident blocks (not preemptible)
-        // keep the next rollout launch from its 7 CTAs per SM (measured r02c: k_rollout_cta 7.5 -> 10.3 us per step beside an
-        // 8-blocks-per-SM pass); the pass is latency bound on its longest chain, not throughput bound
+        // blocks of a pass that runs BESIDE the rollout kernel (BB_GEN_BESIDE_BLOCKS_PER_SM, default 8 = the full width): its
+        // resident blocks delay the next rollout launch's CTAs (k_rollout_cta 6.1 -> 7.8 us per step on BossLevel), but a
+        // narrower pass takes longer than the launches it overlaps and the join waits for it (r02j: 2 / 4 / 8 blocks per SM:
+        // GoTo 2.9e9 / 3.8e9 / 4.1e9, BossLevel 4.19e9 / 4.37e9 / 4.52e9 env-steps/s)
         const int blocks = beside && p->gen_blocks_beside < p->gen_blocks ? p->gen_blocks_beside : p->gen_blocks;
         if (p->lp.kind == KIND_IMPUNLOCK || p->lp.kind == KIND_UNLOCK || p->lp.kind == KIND_BONUS) k_gen<true><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes, chain_cap);
         else k_gen<false><<<blocks, GEN_THREADS, 0, st>>>(p->lp, p->P, p->n, target, p->gen_lanes, chain_cap);
@@ -808,7 +798,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         p->gen_blocks = want < cap ? want : cap;
         p->gen_lanes = 8;                                   // working lanes per warp of the lane-per-level k_gen
         if (const char *e = getenv("BB_GEN_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) p->gen_lanes = v; }
-        int beside = 2;
+        int beside = 8;                                      // measured r02j (32 768 envs): GoTo 2.9e9 / 3.8e9 / 4.1e9, BossLevel 4.19e9 / 4.37e9 / 4.52e9 with 2 / 4 / 8
         if (const char *e = getenv("BB_GEN_BESIDE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) beside = v; }
         p->gen_blocks_beside = prop.multiProcessorCount * beside;
         int per_sm = 4;
@@ -827,7 +817,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     if (const char *e = getenv("BB_GEN_MIN_ACTIVE")) p->gen_min_active = atoi(e);
     p->refill_every = 2; p->rollouts = 0;                  // a refill pass every 2nd rollout launch: more envs per pass, more lanes busy
     p->refill_cap = 0; p->last_T = 0;
-    p->chain_cap = 2;
+    p->chain_cap = 0;                                      // measured r02j: GoTo 4.09e9 with a cap of 2, 4.42e9 without; BossLevel equal
     if (const char *e = getenv("BB_GEN_CHAIN_CAP")) { int v = atoi(e); if (v >= 0 && v <= 1024) p->chain_cap = v; }
     if (const char *e = getenv("BB_REFILL_EVERY")) { int v = atoi(e); if (v >= 1 && v <= 8) { p->refill_every = v; p->refill_cap = v; } }
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
@@ -855,8 +845,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
     p->step_cols = false;
     p->rollout_cta = p->lp.num_rows * p->lp.num_cols > 1;
-    p->rollout_cta_v1 = false;
-    if (const char *e = getenv("BB_ROLLOUT_KERNEL")) { p->rollout_cta = !strcmp(e, "cta") || !strcmp(e, "cta1"); p->rollout_cta_v1 = !strcmp(e, "cta1"); }
+    if (const char *e = getenv("BB_ROLLOUT_KERNEL")) p->rollout_cta = !strcmp(e, "cta");
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
     p->persist_max_cells = 1152;                           // k_rollout stages up to 22 x 22 grids (2 x 43 KB of shared memory per CTA)
     if (const char *e = getenv("BB_PERSIST_MAX_CELLS")) p->persist_max_cells = atoi(e);
@@ -895,10 +884,6 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CUP(cudaFuncSetAttribute(k_rollout_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout_cta<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUP(cudaFuncSetAttribute(k_rollout_cta<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUP(cudaFuncSetAttribute(k_rollout_cta_v1<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // kernels that run concurrently must ask for the SAME L1/shared-memory split: an SM drains before it changes
     // its carve-out, which serialised k_rollout and k_gen_small (measured: 263 us + 212 us alone, 490/590 us together)
     CUP(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1119,15 +1104,9 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     if (dbg_timing) cudaEventRecord(dbg_ev[0], user);
     if (p->rollout_cta) {                  // multi-room levels: 32 envs per CTA, step phase + 4-lanes-per-env observation phase
         const int blocks_c = (p->n + RC_ENVS - 1) / RC_ENVS;
-        if (p->rollout_cta_v1) {
-            const size_t smc = (size_t)rc_cta_words(p->lp) * 4;
-            if (p->lp.kind == KIND_UNLOCK) k_rollout_cta_v1<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-            else k_rollout_cta_v1<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-        } else {
-            const size_t smc = (size_t)rc2_cta_words(p->lp) * 4;
-            if (p->lp.kind == KIND_UNLOCK) k_rollout_cta<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-            else k_rollout_cta<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
-        }
+        const size_t smc = (size_t)rc2_cta_words(p->lp) * 4;
+        if (p->lp.kind == KIND_UNLOCK) k_rollout_cta<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
+        else k_rollout_cta<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
     }
     else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
                                                                                        p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);

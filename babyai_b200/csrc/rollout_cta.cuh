@@ -5,21 +5,21 @@
 // in shared memory: 2 x 43 KB per CTA on 22 x 22 levels, 4 resident warps per SM, one dependent ~1 000-instruction program
 // per warp and step -- 32 768 envs are only 1 024 such warps, 1.7 per scheduler (round 1: 19 us per step of 32 768 BossLevel
 // envs = 3.3 % of the HBM roofline; profiles/r02a_ncu_boss_before.txt).  The parallelism that is left is INSIDE an env, and it
-// is all in the observation (7 view columns), not in the step (one action, one verifier).  So a CTA of 128 threads serves 32
-// envs in two phases per step:
-//   phase A  warp 0, one lane per env: action, step_env, verifier, reward / done -- the efficient SIMT shape for that code;
-//            writes each env's pose word to shared memory.  A finished env only raises a flag;
-//   (swap)   rare on multi-room levels (episodes last hundreds of steps): the whole CTA copies the finished env's next
-//            level from its ring, 128 threads x one 16-byte chunk;
-//   phase B  all 4 warps, FOUR LANES PER ENV: lane q gathers view columns 2q, 2q+1 (7 cells each) from the row-major grid,
-//            computes their see-through bits, two xor-shuffles give every lane of the env all 7 column masks, process_vis
-//            (vis_rows) runs on them, the lane encodes its two columns (42 output bytes) and stages them as 21-byte records
-//            into the CTA's 4 704-byte tile;
-//   store    one elected thread hands the tile to the copy engine (cp.async.bulk shared -> global, SASS UBLKCP).
-// Shared memory per env: the ROW-MAJOR grid only (528 B for 22 x 22; phase B gathers the columns of vertical views byte by
-// byte, so the transposed copy is not needed), object table, verifier record: 684 B instead of 1 204 B -> 7 CTAs = 224 envs
-// = 28 warps per SM, the whole 32 768-env pool in one wave.  The transposed grid copy that the per-step kernels use is
-// regenerated from the row-major one when the state is written back at the end of the launch.
+// is all in the observation (7 view columns), not in the step (one action, one verifier).  So a CTA of 160 threads serves 32
+// envs with two ROLES that run concurrently (the protocol is described above rollout_cta_role below):
+//   the stepper   warp 4, one lane per env: action, step_env, verifier, reward / done -- the efficient SIMT shape for that
+//                 code; publishes each env's pose word in shared memory.  A finished env only raises a flag;
+//   the observers warps 0..3, FOUR LANES PER ENV: lane q gathers view columns 2q, 2q+1 (7 cells each) from the row-major grid,
+//                 computes their see-through bits, two xor-shuffles give every lane of the env all 7 column masks,
+//                 process_vis (vis_rows) runs on them, the lane encodes its two columns (42 output bytes) and stages them as
+//                 21-byte records into one of the CTA's two 4 704-byte tiles;
+//   (swap)        rare on multi-room levels (episodes last hundreds of steps): the observers copy the finished env's next
+//                 level from its ring, 128 threads x one 16-byte chunk, while the stepper waits;
+//   store         one elected thread hands the tile to the copy engine (cp.async.bulk shared -> global, SASS UBLKCP).
+// Shared memory per env: the ROW-MAJOR grid only (528 B for 22 x 22; the observers gather the columns of vertical views byte
+// by byte, so the transposed copy is not needed), object table, verifier record: 684 B instead of 1 204 B; with the two tiles
+// 31.3 KB per CTA -> 7 CTAs = 224 envs = 35 warps per SM, the whole 32 768-env pool in one wave.  The transposed grid copy
+// that the per-step kernels use is regenerated from the row-major one when the state is written back at the end of the launch.
 //
 // Results are identical to rollout_lane.cuh / the per-step kernels (tests: the GPU-less suite runs this very function with
 // one OS thread per lane, tests/hostemu/simt_rollout.cpp; test_rollout_equals_stepwise on the GPU).
@@ -99,252 +99,11 @@ BB_HD void rc_col_gather(const uint8_t *g, const RcView &v, int vi, uint32_t &lo
     hi = (c[4] | (c[5] << 8) | (c[6] << 16)) | (WALLW & ~expand4(cm >> 4) & 0x00FFFFFFu);
 }
 
-// MemT: SmemGMem (device and host build alike)
-template <class PP, bool UNTR>
-BB_DEV void rollout_cta_role_v1(const LevelParams &lp, const PP &P, const int8_t *actions, uint8_t *obs, float *reward, uint8_t *done,
-                             int8_t *dirs, const int n, const int T, const int mode, uint32_t *smem, const int tid, const int cta)
-{
-    const int lane = tid & 31, warp = tid >> 5;
-    const int gs = rc_grid_stride(lp);
-    const int env0 = cta * RC_ENVS;
-    int nv = n - env0; nv = nv > RC_ENVS ? RC_ENVS : (nv < 0 ? 0 : nv);
-    uint32_t *sg = smem, *so = sg + RC_ENVS * gs, *si = so + RC_ENVS * RC_OBJ_STRIDE;
-    uint32_t *s_pose = si + RC_ENVS * RC_INS_STRIDE;               // x | y << 8 | dir << 16 | carried cell byte << 24
-    uint32_t *s_swap = s_pose + RC_ENVS;                           // ring slot + 1 of an env whose episode begins, else 0
-    uint32_t *s_hot = s_swap + RC_ENVS;                            // hot record of a swapped-in level (4 words per env)
-    uint32_t *tile = smem + (rc_cta_words(lp) - RC_TILE_WORDS);    // 16-byte aligned
-    const int gchunks = lp.gt_off >> 4, tchunks = lp.max_tokens >> 3;
-    // ---- load the state of the CTA's envs once: row-major grid part, object table, verifier record -------------
-    for (int idx = tid; idx < nv * gchunks; idx += RC_THREADS) {
-        const int e = idx / gchunks, k = idx - e * gchunks;
-        const uint4 v = reinterpret_cast<const uint4 *>(P.grid + (size_t)(env0 + e) * lp.cells_pad)[k];
-        uint32_t *d = sg + e * gs + 4 * k;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    for (int idx = tid; idx < nv * 6; idx += RC_THREADS) {
-        const int e = idx / 6, k = idx - e * 6;
-        const uint4 v = reinterpret_cast<const uint4 *>(P.obj + env0)[idx];
-        uint32_t *d = so + e * RC_OBJ_STRIDE + 4 * k;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    for (int idx = tid; idx < nv * 3; idx += RC_THREADS) {
-        const int e = idx / 3, k = idx - e * 3;
-        const uint4 v = reinterpret_cast<const uint4 *>(P.ins + env0)[idx];
-        uint32_t *d = si + e * RC_INS_STRIDE + 4 * k;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    if (tid < RC_ENVS) s_swap[tid] = 0;
-    // ---- the stepper: warp 4, lane = env within the CTA ------------------------------------------------------------
-    const bool stepper = warp == RC_THREADS / 32 - 1;
-    const int env_a = env0 + lane;
-    const bool valid_a = stepper && lane < nv;
-    EnvHot h;
-    { uint4 z = make_uint4(0, 0, 0, 0); h = *reinterpret_cast<EnvHot *>(&z); }
-    uint32_t head = 0, avail = 0, consumed = 0;
-    float last_rew = 0.0f;
-    uint32_t n_step = 0, n_end = 0, n_succ = 0, n_err = 0;
-    int a_next = 0;
-    if (valid_a) {
-        h = P.hot[env_a];
-        head = P.head[env_a];
-        avail = BB_LDCG(P.tail_pub + env_a) - head;
-        if (mode == BB_MODE_FREEZE) last_rew = P.last_reward[env_a];
-        a_next = BB_LD_S8(actions + env_a);
-    }
-    BB_SYNCTHREADS();
-    SmemGMem mem_a(lp, reinterpret_cast<uint8_t *>(sg + lane * gs), reinterpret_cast<uint8_t *>(so + lane * RC_OBJ_STRIDE),
-                   reinterpret_cast<uint8_t *>(si + lane * RC_INS_STRIDE));
-    // ---- the observers: warps 0..3, 4 lanes per env ------------------------------------------------------------------
-    const int el = (tid >> 2) & (RC_ENVS - 1), q = tid & 3;
-    const bool valid_b = !stepper && el < nv;
-    const uint8_t *g_b = reinterpret_cast<const uint8_t *>(sg + el * gs);
-    // what an observer carries from the gather of step t (B1) to the encode of step t (B2), which runs while the stepper
-    // is already at step t + 1: its two view columns, the env's see-through column masks, the carried cell byte
-    uint32_t loA = 0, hiA = 0, loB = 0, hiB = 0, blo = 0, bhi = 0, carry_b = 0;
-    bool bulk_pending = false;                                     // thread 0 only
-    for (int t = 0; t <= T; t++) {
-        bool begin = false;
-        if (stepper) {
-            // ================= A(t): one lane per env steps it =================
-            if (t < T) {
-                const int a = a_next;
-                if (valid_a && t + 1 < T) a_next = BB_LD_S8(actions + (size_t)(t + 1) * n + env_a);
-                if (valid_a) {
-                    float rew = 0.0f; bool dn = false;
-                    if (!(h.dirflags & 4)) {
-                        const StepResult sr = step_env<UNTR>(h, mem_a, a);
-                        rew = sr.reward; dn = sr.done;
-                        n_step++; n_end += dn; n_succ += sr.success;
-                        if (dn) {
-                            if (mode == BB_MODE_AUTORESET) begin = true;
-                            else { h.dirflags |= 4; last_rew = rew; }
-                        }
-                    } else { rew = last_rew; dn = true; }
-                    if (begin && !(consumed < avail && avail <= (uint32_t)P.depth)) { begin = false; n_err++; *P.err_flag = 1; }   // ring dry
-                    if (begin) s_swap[lane] = (head + consumed) % (uint32_t)P.depth + 1u;
-                    else s_pose[lane] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)(h.dirflags & 3) << 16) |
-                                        ((uint32_t)carry_cell_of<UNTR>(h, mem_a) << 24);
-                    const size_t oi = (size_t)t * n + env_a;
-                    if (reward) reward[oi] = rew;
-                    if (done) done[oi] = dn ? 1 : 0;
-                }
-            }
-        } else if (t > 0) {
-            // ================= B2(t - 1): process_vis, encode, stage -- from registers only =================
-            uint32_t tlo = blo, thi = bhi;
-            transpose8(tlo, thi);                                  // column masks -> per view row (bit vi)
-            uint32_t see[7], vis[7];
-#pragma unroll
-            for (int vj = 0; vj < 7; vj++) see[vj] = ((vj < 4 ? tlo >> (8 * vj) : thi >> (8 * (vj - 4)))) & 0x7Fu;
-            vis_rows(see, vis);
-            uint32_t vlo = 0, vhi = 0;
-#pragma unroll
-            for (int vj = 0; vj < 7; vj++) { if (vj < 4) vlo |= vis[vj] << (8 * vj); else vhi |= vis[vj] << (8 * (vj - 4)); }
-            transpose8(vlo, vhi);                                  // byte vi = visibility of column vi, bit vj
-            const uint32_t vmine = (q & 2) ? vhi : vlo;            // columns 4..7 / 0..3
-            const uint32_t cvA = (vmine >> (16 * (q & 1))) & 0x7Fu, cvB = (vmine >> (16 * (q & 1) + 8)) & 0x7Fu;
-            uint32_t hB = hiB;
-            if (q == 1) hB = (hB & 0xFF00FFFFu) | (carry_b << 16);     // view cell (3, 6): the agent's own cell shows what it carries
-            uint32_t oA[6], oB[6];
-            col_encode(loA, hiA, valid_b ? cvA : 0u, oA);
-            col_encode(loB, hB, (valid_b && q < 3) ? cvB : 0u, oB);
-            // 21-byte records: record 7 el + vi; the word a record shares with its successor is completed with the successor's
-            // first word (the lane's own second column, or the next lane's first column: one shuffle)
-            const uint32_t nextA = BB_SHFL_DOWN(oA[0], 1);
-            if (q < 3) {
-                stage_record_words<21, 6>(tile, oA, 7 * el + 2 * q, oB[0]);
-                stage_record_words<21, 6>(tile, oB, 7 * el + 2 * q + 1, nextA);
-            } else stage_record_words<21, 6>(tile, oA, 7 * el + 6, nextA);
-            BB_FENCE_ASYNC_SMEM();                                 // tile writes -> visible to the copy engine
-        }
-        // ---- barrier X: A(t) is done, tile(t - 1) is complete ----
-        const int any_begin = BB_SYNCTHREADS_OR(begin ? 1 : 0);
-        if (t > 0) {                                               // the CTA's 32 observations of step t - 1 leave as one tile
-            uint8_t *dst = obs + ((size_t)(t - 1) * n + env0) * OBS_BYTES;
-            if (nv == RC_ENVS && (((uintptr_t)dst) & 15) == 0) {
-                if (tid == 0) { BB_BULK_STORE(dst, tile, RC_ENVS * OBS_BYTES); bulk_pending = true; }
-            } else if (!stepper) {
-                const uint8_t *sb = reinterpret_cast<const uint8_t *>(tile);
-                for (int i = tid; i < nv * OBS_BYTES; i += RC_THREADS - 32) dst[i] = sb[i];
-            }
-        }
-        if (t == T) break;
-        // ================= episode swap-in by the whole CTA (rare) =================
-        if (any_begin) {
-            for (int e = 0; e < RC_ENVS; e++) {
-                const uint32_t sw = s_swap[e];
-                if (!sw) continue;                                 // CTA-uniform: every thread reads the same flag
-                const LevelOut o = r2_ring_slot(lp, P, env0 + e, (int)sw - 1);
-                for (int c = tid; c < gchunks + 9 + tchunks + 1; c += RC_THREADS) {
-                    int k = c;
-                    if (k < gchunks + 9) {
-                        const uint4 *sp; uint32_t *dp;
-                        if (k < gchunks) { sp = reinterpret_cast<const uint4 *>(o.grid) + k; dp = sg + e * gs + 4 * k; }
-                        else if ((k -= gchunks) < 6) { sp = reinterpret_cast<const uint4 *>(o.obj) + k; dp = so + e * RC_OBJ_STRIDE + 4 * k; }
-                        else { k -= 6; sp = reinterpret_cast<const uint4 *>(o.ins) + k; dp = si + e * RC_INS_STRIDE + 4 * k; }
-                        const uint4 v = BB_LDCG(sp);
-                        dp[0] = v.x; dp[1] = v.y; dp[2] = v.z; dp[3] = v.w;
-                    } else if ((k -= gchunks + 9) < tchunks) {
-                        reinterpret_cast<uint4 *>(P.tok + (size_t)(env0 + e) * lp.max_tokens)[k] = BB_LDCG(reinterpret_cast<const uint4 *>(o.tok) + k);
-                    } else {                                       // the hot record: to the stepping lane, and the pose word of the new episode
-                        const uint4 hv = BB_LDCG(reinterpret_cast<const uint4 *>(o.hot));
-                        s_hot[4 * e] = hv.x; s_hot[4 * e + 1] = hv.y; s_hot[4 * e + 2] = hv.z; s_hot[4 * e + 3] = hv.w;
-                        const EnvHot nh = *reinterpret_cast<const EnvHot *>(&hv);
-                        s_pose[e] = (uint32_t)nh.x | ((uint32_t)nh.y << 8) | ((uint32_t)(nh.dirflags & 3) << 16) | ((uint32_t)CELL_EMPTY << 24);
-                    }
-                }
-            }
-            BB_SYNCTHREADS();
-            if (begin) {                                           // the stepping lane takes over the new episode
-                const uint4 hv = make_uint4(s_hot[4 * lane], s_hot[4 * lane + 1], s_hot[4 * lane + 2], s_hot[4 * lane + 3]);
-                h = *reinterpret_cast<const EnvHot *>(&hv);
-                consumed++;
-                s_swap[lane] = 0;
-            }
-        }
-        if (!stepper) {
-            // ================= B1(t): pose, the lane's two view columns, the env's see-through masks -> registers =================
-            const uint32_t pose = valid_b ? s_pose[el] : 0u;
-            const int ax = (int)(pose & 0xFF), ay = (int)((pose >> 8) & 0xFF), dir = (int)((pose >> 16) & 3);
-            carry_b = pose >> 24;
-            uint32_t cmA = 0, cmB = 0;
-            loA = hiA = loB = hiB = 0;
-            if (valid_b) {
-                const RcView view = rc_view(lp, ax, ay, dir);
-                rc_col_gather(g_b, view, 2 * q, loA, hiA);
-                cmA = col_see(loA, hiA);
-                if (q < 3) { rc_col_gather(g_b, view, 2 * q + 1, loB, hiB); cmB = col_see(loB, hiB); }
-            }
-            // the 7 column masks (see-through bits, bit vj) of the env to all of its 4 lanes: byte vi of (blo : bhi)
-            const uint32_t v16 = cmA | (cmB << 8);
-            const uint32_t p1 = BB_SHFL_XOR(v16, 1);
-            const uint32_t mine = (q & 1) ? (p1 | (v16 << 16)) : (v16 | (p1 << 16));
-            const uint32_t other = BB_SHFL_XOR(mine, 2);
-            blo = (q & 2) ? other : mine; bhi = (q & 2) ? mine : other;
-            if (valid_b && q == 0 && dirs) dirs[(size_t)t * n + env0 + el] = (int8_t)dir;
-            if (tid == 0 && bulk_pending) { BB_BULK_WAIT_READ(); bulk_pending = false; }   // before B2(t) rewrites the tile
-        }
-        // ---- barrier Y: the observers hold step t in registers: the stepper may go on ----
-        BB_SYNCTHREADS();
-    }
-    if (tid == 0 && bulk_pending) BB_BULK_WAIT_READ();             // shared memory must outlive the copy engine's reads
-    BB_SYNCTHREADS();
-    // ---- store the state back: row-major part as is, the transposed part regenerated from it ---------------------------
-    for (int idx = tid; idx < nv * gchunks; idx += RC_THREADS) {
-        const int e = idx / gchunks, k = idx - e * gchunks;
-        const uint32_t *d = sg + e * gs + 4 * k;
-        reinterpret_cast<uint4 *>(P.grid + (size_t)(env0 + e) * lp.cells_pad)[k] = make_uint4(d[0], d[1], d[2], d[3]);
-    }
-    {
-        const int twords = lp.rs_t >> 2, per_env = lp.W * twords;
-        for (int idx = tid; idx < nv * per_env; idx += RC_THREADS) {
-            const int e = idx / per_env, r = idx - e * per_env;
-            const int x = r / twords, y0 = (r - x * twords) * 4;
-            const uint8_t *ge = reinterpret_cast<const uint8_t *>(sg + e * gs);
-            uint32_t wv = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int y = y0 + b;
-                const uint32_t c = y < lp.H ? (uint32_t)ge[y * lp.rs_g + x] : (uint32_t)CELL_WALL;      // row padding is wall
-                wv |= c << (8 * b);
-            }
-            reinterpret_cast<uint32_t *>(P.grid + (size_t)(env0 + e) * lp.cells_pad + lp.gt_off)[r] = wv;
-        }
-    }
-    for (int idx = tid; idx < nv * 6; idx += RC_THREADS) {
-        const int e = idx / 6, k = idx - e * 6;
-        const uint32_t *d = so + e * RC_OBJ_STRIDE + 4 * k;
-        reinterpret_cast<uint4 *>(P.obj + env0)[idx] = make_uint4(d[0], d[1], d[2], d[3]);
-    }
-    for (int idx = tid; idx < nv * 3; idx += RC_THREADS) {
-        const int e = idx / 3, k = idx - e * 3;
-        const uint32_t *d = si + e * RC_INS_STRIDE + 4 * k;
-        reinterpret_cast<uint4 *>(P.ins + env0)[idx] = make_uint4(d[0], d[1], d[2], d[3]);
-    }
-    if (stepper) {
-        if (valid_a) {
-            P.hot[env_a] = h;
-            P.head[env_a] = head + consumed;
-            if (mode == BB_MODE_FREEZE) P.last_reward[env_a] = last_rew;
-        }
-        for (int off = 16; off; off >>= 1) {
-            n_step += BB_SHFL_DOWN(n_step, off); n_end += BB_SHFL_DOWN(n_end, off);
-            n_succ += BB_SHFL_DOWN(n_succ, off); n_err += BB_SHFL_DOWN(n_err, off);
-        }
-        if (lane == 0) {
-            unsigned long long *c = P.warp_counters + 4ull * cta;
-            if (n_step) BB_ATOMIC_ADD(c + 0, (unsigned long long)n_step);
-            if (n_end) BB_ATOMIC_ADD(c + 1, (unsigned long long)n_end);
-            if (n_succ) BB_ATOMIC_ADD(c + 2, (unsigned long long)n_succ);
-            if (n_err) BB_ATOMIC_ADD(c + 3, (unsigned long long)n_err);
-        }
-    }
-}
-
 // =====================================================================================================================
-// Version 2: the stepper runs AHEAD of the observers.
+// The stepper runs AHEAD of the observers.
 //
-// ncu r02f (BossLevel, 32 768 envs): 52 % of the stall samples of version 1 sit at barrier X -- the four observer warps wait
+// Version 1 of this kernel (until r02i; git history) ran the two roles in lock-step with two CTA barriers per step.  ncu r02f
+// (BossLevel, 32 768 envs): 52 % of its stall samples sat at the first barrier -- the four observer warps wait
 // for the stepper (A takes ~0.78 of a step, B2 ~0.18), and then the stepper waits at barrier Y while the observers gather
 // (B1, ~0.22): a step lasts A + B1.  The only thing of the stepper's that the observers read is the row-major grid and the
 // pose word, and step_env writes at most two grid cells per step.  So the stepper computes step t + 1 WHILE the observers
