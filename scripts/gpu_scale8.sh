@@ -16,6 +16,7 @@ done
 for N in 8 4; do
   ( run $N --steps 2000 --warmup 200 --lean --no-cpu-baseline --no-other-configs ) > $OUT/scale_gotolocal_${N}_$TAG.json 2> $OUT/scale_gotolocal_${N}_$TAG.err
 done
+( BENCH_NO_NUMA_PIN=1 run 8 --steps 2000 --warmup 200 --lean --no-cpu-baseline --no-other-configs ) > $OUT/scale_gotolocal_8nopin_$TAG.json 2> $OUT/scale_gotolocal_8nopin_$TAG.err
 python - <<PY
 import json, glob
 for f in sorted(glob.glob('$OUT/scale_*_$TAG.json')):
