@@ -1919,6 +1919,20 @@ BB_HD int verify_root(M &mem, const StepCtx &s)
     return verify_side(mem, second, s);
 }
 
+// Compile-time specialisation of the stepping code by level family, carried by the accessor type: an accessor that declares
+// `static constexpr bool spec_goto_room = true` promises  num_rows == num_cols == 1, kinds_mask == GoTo only, single_instr,
+// no done-actions, no bonus family, no untracked objects  (GoToRedBall*, GoToObj*, GoToLocal*: BASELINE configs 1 and 2).
+// The generic code is the same with those tests as uniform run-time branches; the specialised instantiation is there for the
+// INSTRUCTION FOOTPRINT of the persistent kernel's loop (k_rollout: 7 616 instructions against a 32 KB = 2 048-instruction
+// L1.5 instruction cache; `no_instruction` was 17 % of its issue-stall cycles, ncu r02c).
+template <class M, class = void> struct mem_spec { static constexpr bool goto_room = false; };
+template <class M> struct mem_spec<M, decltype((void)M::spec_goto_room)> { static constexpr bool goto_room = M::spec_goto_room; };
+BB_HD bool level_is_goto_room(const LevelParams &lp)
+{
+    return lp.num_rows == 1 && lp.num_cols == 1 && lp.kinds_mask == (1 << I_GOTO) && lp.single_instr && !lp.done_actions &&
+           lp.bonus == 0 && lp.kind != KIND_UNLOCK && lp.kind != KIND_BONUS;
+}
+
 struct StepResult { bool done; bool success; float reward; };      // done: success, failure (strict / done-action modes) or time-out
 
 // Applies one action to the live state of one env.  `h` is the env's hot record
@@ -1927,7 +1941,7 @@ struct StepResult { bool done; bool success; float reward; };      // done: succ
 template <bool UNTR = false, class M>
 BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
 {
-    if (h.step_count == 0 && mem.lp.bonus == BN_PUTNEXT) {
+    if (!mem_spec<M>::goto_room && h.step_count == 0 && mem.lp.bonus == BN_PUTNEXT) {
         // Level_PutNext*Carrying (bonus_levels.py:821-829): reset() returns the observation of the generated level, THEN takes
         // obj_a off the grid into the agent's hands -- so the first step acts on the modified state
         const int sc = mem.start_carry();
@@ -2010,8 +2024,14 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
     StepCtx s;
     s.action = action; s.fx = nfx; s.fy = nfy; s.carry = carry;
     s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.at = at;
-    s.fcell = (mem.lp.kinds_mask & (1 << I_OPEN)) ? mem.cell(nfx, nfy) : 0;
-    const int status = verify_root(mem, s);
+    int status;
+    if constexpr (mem_spec<M>::goto_room) {
+        s.fcell = 0;
+        status = (mem.desc_mask(0) & s.snap_mask & s.at) != 0 ? V_SUCC : V_CONT;          // GoToInstr.verify_action of the one leaf
+    } else {
+        s.fcell = (mem.lp.kinds_mask & (1 << I_OPEN)) ? mem.cell(nfx, nfy) : 0;
+        status = verify_root(mem, s);
+    }
     r.success = status == V_SUCC;
     r.reward = 0.0f;
     if (status == V_FAIL) r.done = true;                  // RoomGridLevel.step: 'failure' ends the episode with reward 0
@@ -2328,6 +2348,7 @@ BB_HD void observe_cells(const LevelParams &lp, const M &mem, int ax, int ay, in
 template <class M>
 BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
 {
+    if constexpr (mem_spec<M>::goto_room) { observe_room(lp, mem, ax, ay, dir, carry_cell, w); return; }
     if (lp.num_rows == 1 && lp.num_cols == 1) observe_room(lp, mem, ax, ay, dir, carry_cell, w);
     else observe_generic(lp, mem, ax, ay, dir, carry_cell, w);
 }
