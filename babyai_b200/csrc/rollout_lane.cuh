@@ -91,34 +91,9 @@ BB_DEV void rollout_lane_step_warp(const LevelParams &lp, const PP &P, const voi
         if (ACT_BYTES == 1) a_next = BB_LD_S8(actions + env);
         else a_next = (int)reinterpret_cast<const long long *>(actions_v)[env];      // int64 actions: single-step calls only
     }
-    const bool can_preload = mode == BB_MODE_AUTORESET && !force_reset && rec_chunks + tchunks <= 32;
     for (int t = 0; t < T; t++) {
         const int a = a_next;
         if (ACT_BYTES == 1 && valid && t + 1 < T) a_next = BB_LD_S8(actions + (size_t)(t + 1) * n + env);
-        // ---- preload: an env in the LAST step of its episode ends it whatever the action is (time-out, or success first), so
-        // the warp starts fetching its next level from the ring BEFORE step_env and stores it afterwards -- the L2 / DRAM
-        // latency of the swap-in (ncu r02k: 16 % of the kernel's stall samples, one dependent round trip per finished env)
-        // passes under the ~250 instructions of step_env.  Time-outs are 73 % of the episode ends under random actions; one
-        // env per warp and step is preloaded (the first), everything else takes the loop below.
-        int pre_src = -1;
-        uint4 pre_v = make_uint4(0, 0, 0, 0), pre_h = make_uint4(0, 0, 0, 0);
-        if (can_preload) {
-            const bool last = valid && !(h.dirflags & 4) && (int)h.step_count + 1 >= (int)h.max_steps && consumed < avail && avail <= (uint32_t)P.depth;
-            const uint32_t mlast = BB_BALLOT(last);
-            if (mlast) {
-                pre_src = ffs32(mlast);
-                const int slot = (int)BB_SHFL((head + consumed) % (uint32_t)P.depth, pre_src);
-                const LevelOut o = r2_ring_slot(lp, P, env0 + pre_src, slot);
-                int k = lane;
-                const uint4 *sp = nullptr;
-                if (k < gchunks) sp = reinterpret_cast<const uint4 *>(o.grid) + k;
-                else if ((k -= gchunks) < 6) sp = reinterpret_cast<const uint4 *>(o.obj) + k;
-                else if ((k -= 6) < 3) sp = reinterpret_cast<const uint4 *>(o.ins) + k;
-                else if ((k -= 3) < tchunks) sp = reinterpret_cast<const uint4 *>(o.tok) + k;
-                if (sp) pre_v = BB_LDCG(sp);
-                if (lane == pre_src) pre_h = BB_LDCG(reinterpret_cast<const uint4 *>(o.hot));
-            }
-        }
         float rew = 0.0f; bool dn = false, begin = false;
         if (valid) {
             begin = force_reset != 0;
@@ -144,15 +119,6 @@ BB_DEV void rollout_lane_step_warp(const LevelParams &lp, const PP &P, const voi
                 mbeg &= mbeg - 1;
                 const int slot = (int)BB_SHFL(my_slot, src);
                 const int e = env0 + src;
-                if (src == pre_src) {                              // preloaded before step_env: registers -> the lane's records
-                    int k = lane;
-                    if (k < gchunks) { uint32_t *dp = sg + src * gs + 4 * k; dp[0] = pre_v.x; dp[1] = pre_v.y; dp[2] = pre_v.z; dp[3] = pre_v.w; }
-                    else if ((k -= gchunks) < 6) { uint32_t *dp = so + src * RL_OBJ_STRIDE + 4 * k; dp[0] = pre_v.x; dp[1] = pre_v.y; dp[2] = pre_v.z; dp[3] = pre_v.w; }
-                    else if ((k -= 6) < 3) { uint32_t *dp = si + src * RL_INS_STRIDE + 4 * k; dp[0] = pre_v.x; dp[1] = pre_v.y; dp[2] = pre_v.z; dp[3] = pre_v.w; }
-                    else if ((k -= 3) < tchunks) reinterpret_cast<uint4 *>(P.tok + (size_t)e * lp.max_tokens)[k] = pre_v;
-                    if (lane == src) { h = *reinterpret_cast<const EnvHot *>(&pre_h); consumed++; }
-                    continue;
-                }
                 const LevelOut o = r2_ring_slot(lp, P, e, slot);
                 for (int c = lane; c < rec_chunks + tchunks; c += 32) {
                     if (c < rec_chunks) {
