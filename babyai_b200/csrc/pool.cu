@@ -54,7 +54,7 @@ struct PoolPtrs {
 };
 
 constexpr int GEN_THREADS = 64;                    // 2 warps per block; one warp generates one level at a time
-constexpr int GEN_BLOCKS_PER_SM = 8;
+constexpr int GEN_BLOCKS_PER_SM = 14;            // k_gen: 64 threads x 72 registers per block: 14 blocks fill an SM's register file (r02n: 8 / 12 / 14 blocks: GoTo 4.43e9 / 4.64e9 / 4.79e9)
 
 __device__ __forceinline__ LevelOut ring_slot(const LevelParams &lp, const PoolPtrs &P, int env, int slot)
 {
@@ -678,7 +678,7 @@ static void launch_gen_kernel(bb_pool *p, int target, cudaStream_t st, int max_r
     if (p->lp.small && !p->gen_generic) {
         k_gen_small<<<p->gen_small_blocks, GS_THREADS, 0, st>>>(p->lp, p->P, target, max_rounds, min_active, min_keep);
     } else {
-        // blocks of a pass that runs BESIDE the rollout kernel (BB_GEN_BESIDE_BLOCKS_PER_SM, default 8 = the full width): its
+        // blocks of a pass that runs BESIDE the rollout kernel (BB_GEN_BESIDE_BLOCKS_PER_SM, default = the full width): its
         // resident blocks delay the next rollout launch's CTAs (k_rollout_cta 6.1 -> 7.8 us per step on BossLevel), but a
         // narrower pass takes longer than the launches it overlaps and the join waits for it (r02j: 2 / 4 / 8 blocks per SM:
         // GoTo 2.9e9 / 3.8e9 / 4.1e9, BossLevel 4.19e9 / 4.37e9 / 4.52e9 env-steps/s)
@@ -805,7 +805,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
         p->gen_blocks = want < cap ? want : cap;
         p->gen_lanes = 8;                                   // working lanes per warp of the lane-per-level k_gen
         if (const char *e = getenv("BB_GEN_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) p->gen_lanes = v; }
-        int beside = 8;                                      // measured r02j (32 768 envs): GoTo 2.9e9 / 3.8e9 / 4.1e9, BossLevel 4.19e9 / 4.37e9 / 4.52e9 with 2 / 4 / 8
+        int beside = GEN_BLOCKS_PER_SM;                                      // measured r02j (32 768 envs): GoTo 2.9e9 / 3.8e9 / 4.1e9, BossLevel 4.19e9 / 4.37e9 / 4.52e9 with 2 / 4 / 8
         if (const char *e = getenv("BB_GEN_BESIDE_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) beside = v; }
         p->gen_blocks_beside = prop.multiProcessorCount * beside;
         int per_sm = 4;
