@@ -406,10 +406,9 @@ template <int ACT_BYTES, bool UNTR = false, bool GOTO_ROOM = false>
 __global__ void __launch_bounds__(R_THREADS_FUSED, 7)
 k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions_v, uint8_t *__restrict__ obs,
           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
-          const int mode, const int force_reset, const int gen_rounds, const int gen_min_active, const int cta_base)
+          const int mode, const int force_reset, const int gen_rounds, const int gen_min_active)
 {
     extern __shared__ __align__(16) uint32_t smr[];
-    const int cta = (int)blockIdx.x + cta_base;         // bb_pool_step_host launches the grid in slices (cta_base > 0)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_words = rl_warp_words(lp);
     const bool fused = gen_rounds > 0;                  // launched with R_THREADS_FUSED threads and RG_AREA_WORDS more shared memory
@@ -417,12 +416,12 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
     volatile int *s_done = reinterpret_cast<volatile int *>(g_area + RG_AREA_WORDS - 4);
     if (warp == R_WARPS) {
         // generator warp (fused launches only): gen_round.cuh
-        rollout_gen_warp(lp, P, g_area, s_done, n, T, cta * R_WARPS * 32, gen_rounds, gen_min_active, lane, R_WARPS);
+        rollout_gen_warp(lp, P, g_area, s_done, n, T, blockIdx.x * R_WARPS * 32, gen_rounds, gen_min_active, lane, R_WARPS);
         return;
     }
     // stepping warps: rollout_lane.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu)
     rollout_lane_step_warp<PoolPtrs, typename std::conditional<GOTO_ROOM, SmemGotoRoomMem, SmemOnlyMem>::type, ACT_BYTES, UNTR>(lp, P, actions_v, obs, reward, done, dirs, n, T, mode, force_reset, fused,
-                                                                   smr + warp * warp_words, lane, cta * R_WARPS + warp, s_done);
+                                                                   smr + warp * warp_words, lane, blockIdx.x * R_WARPS + warp, s_done);
 }
 
 // k_rollout_cta -- bb_pool_rollout on MULTI-ROOM levels: 32 envs per CTA, a lane-per-env step phase and a 4-lanes-per-env
@@ -627,8 +626,6 @@ struct bb_pool {
     long long rel;
     cudaStream_t stream;           // internal stream: host-buffer API, seeding, graph capture origin
     cudaStream_t gen_stream;       // level generation runs here, concurrently with the steps
-    cudaStream_t copy_stream;      // bb_pool_step_host: the observation slices leave here while the next slice is stepped
-    cudaEvent_t ev_chunk[8]; int host_chunks;
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t gen_ev[MAX_GEN_EVENTS];
     long long gens_enqueued;       // k index of the next k_gen in the current epoch
@@ -705,16 +702,16 @@ static void launch_gen(bb_pool *p, cudaStream_t st)
 }
 
 static void launch_step(bb_pool *p, const void *actions, int action_bytes, uint8_t *obs, float *rew, uint8_t *done,
-                        int8_t *dirs, int force_reset, cudaStream_t st, int cta_base = 0, int cta_count = -1)
+                        int8_t *dirs, int force_reset, cudaStream_t st)
 {
     // single-room grids (<= 128 bytes of cells): the persistent kernel with T = 1 (coalesced state load / store);
     // everything else, and KIND_UNLOCK: k_step8, eight lanes per environment.  BB_STEP_KERNEL=cols forces k_step8.
     const bool cols = p->step_cols || p->lp.cells_pad > 128 || p->lp.kind == KIND_UNLOCK;
     if (!cols) {
         const size_t smem = (size_t)R_WARPS * rl_warp_words(p->lp) * 4;
-        const int blocks = cta_count >= 0 ? cta_count : (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);      // a slice of the grid: bb_pool_step_host
-        if (action_bytes == 8) k_rollout<8><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0, cta_base);
-        else k_rollout<1><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0, cta_base);
+        const int blocks = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
+        if (action_bytes == 8) k_rollout<8><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0);
+        else k_rollout<1><<<blocks, R_THREADS, smem, st>>>(p->lp, p->P, actions, obs, rew, done, dirs, p->n, 1, p->mode, force_reset, 0, 0);
         p->launches++;
         return;
     }
@@ -884,10 +881,6 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     P.gen_ticket = P.gen_count + 4;                      // one memset clears the list counters and the work ticket
     CUP(cudaMemset(P.locked_room, 0xFF, n));
     CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    CUP(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; i++) CUP(cudaEventCreateWithFlags(&p->ev_chunk[i], cudaEventDisableTiming));
-    p->host_chunks = 4;
-    if (const char *e = getenv("BB_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 8) p->host_chunks = v; }
     {
         int lo = 0, hi = 0;
         CUP(cudaDeviceGetStreamPriorityRange(&lo, &hi));                  // lo = lowest priority
@@ -956,8 +949,6 @@ int bb_pool_destroy(bb_pool *p)
     if (p->h_err) cudaFreeHost(p->h_err);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->gen_stream) cudaStreamDestroy(p->gen_stream);
-    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
-    for (int i = 0; i < 8; i++) if (p->ev_chunk[i]) cudaEventDestroy(p->ev_chunk[i]);
     delete p;
     return 0;
 }
@@ -1129,12 +1120,12 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         else k_rollout_cta<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
     }
     else if (fused && p->goto_room) k_rollout<1, false, true><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
-                                                                                       p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active, 0);
+                                                                                       p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
     else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
-                                                                                       p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active, 0);
-    else if (p->lp.kind == KIND_UNLOCK) k_rollout<1, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0, 0);
-    else if (p->goto_room) k_rollout<1, false, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0, 0);
-    else k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0, 0);
+                                                                                       p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
+    else if (p->lp.kind == KIND_UNLOCK) k_rollout<1, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
+    else if (p->goto_room) k_rollout<1, false, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
+    else k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
     if (dbg_timing) { cudaEventRecord(dbg_ev[1], user); p->tev_kernel = true; }
     p->launches++;
     if (refill && !gen_serial) {
@@ -1248,29 +1239,6 @@ int bb_pool_step_host(bb_pool *p, const int8_t *actions_host, uint8_t *obs_host,
     if (!zc) CU(cudaMemcpyAsync(p->d_act, p->h_act, n, cudaMemcpyHostToDevice, p->stream));
     if (sched_leave_rollout(p, p->stream)) return 1;
     if (sched_before_step(p, p->rel, p->stream)) return 1;
-    // Sliced step (single-room levels, page-locked caller buffers): the grid is launched in `host_chunks` slices and the
-    // observations of slice c leave on the copy stream while slice c + 1 is stepped -- the copy engine starts ~3/4 of a kernel
-    // earlier and never waits for the whole step (the raw D2H copy of 9.6 MB is 172 us of the ~220 us call).  BB_HOST_CHUNKS.
-    const bool single_room_kernel = !(p->step_cols || p->lp.cells_pad > 128 || p->lp.kind == KIND_UNLOCK);
-    const int blocks_total = (p->n + 32 * R_WARPS - 1) / (32 * R_WARPS);
-    const bool sliced = zc == 1 && direct && single_room_kernel && p->host_chunks > 1 && blocks_total >= 16 * p->host_chunks;
-    if (sliced) {
-        const int per = (blocks_total + p->host_chunks - 1) / p->host_chunks;
-        for (int c = 0; c * per < blocks_total; c++) {
-            const int b0 = c * per, bc = blocks_total - b0 < per ? blocks_total - b0 : per;
-            launch_step(p, p->zc_act, 1, p->d_obs, p->zc_rew, p->zc_done, dir_host ? p->zc_dir : p->d_dir, 0, p->stream, b0, bc);
-            CU(cudaEventRecord(p->ev_chunk[c], p->stream));
-            CU(cudaStreamWaitEvent(p->copy_stream, p->ev_chunk[c], 0));
-            const size_t e0 = (size_t)b0 * 32 * R_WARPS, e1 = (size_t)(b0 + bc) * 32 * R_WARPS < n ? (size_t)(b0 + bc) * 32 * R_WARPS : n;
-            CU(cudaMemcpyAsync(obs_host + e0 * OBS_BYTES, p->d_obs + e0 * OBS_BYTES, (e1 - e0) * OBS_BYTES, cudaMemcpyDeviceToHost, p->copy_stream));
-        }
-        if (sched_after_step(p, p->rel, p->stream)) return 1;
-        p->rel++;
-        CU(cudaStreamSynchronize(p->copy_stream));
-        CU(cudaStreamSynchronize(p->stream));
-        BB_CHECK_RINGS(p);
-        return 0;
-    }
     if (zc) launch_step(p, p->zc_act, 1, zc > 1 ? p->zc_obs : p->d_obs, p->zc_rew, p->zc_done, dir_host ? p->zc_dir : p->d_dir, 0, p->stream);
     else launch_step(p, p->d_act, 1, p->d_obs, p->d_rew, p->d_done, p->d_dir, 0, p->stream);
     if (sched_after_step(p, p->rel, p->stream)) return 1;

@@ -214,34 +214,3 @@ def test_many_envs_facades_on_a_multi_room_level(level):
                 if not frozen[i] and do[i]:
                     frozen[i], last[i] = True, want
         assert host.pool.counters()['errors'] == 0 and devm.pool.counters()['errors'] == 0
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize('level,chunks', [('GoToLocal', '4'), ('GoToLocal', '3'), ('PickupLoc', '4'), ('GoToLocal', '1')])
-def test_sliced_host_step_equals_device_step(monkeypatch, level, chunks):
-    """bb_pool_step_host with page-locked buffers launches the step in slices of the grid and copies the observations of a
-    slice while the next one is stepped (BB_HOST_CHUNKS): same results as bb_pool_step on a twin pool, ragged last CTA,
-    episodes ending and new levels swapped in on the way."""
-    import torch
-    monkeypatch.setenv('BB_HOST_CHUNKS', chunks)
-    from babyai_b200 import BabyAIVecEnv
-    n = 64 * 70 + 37
-    seeds = np.arange(n, dtype=np.uint64) + 4242
-    dev, host = BabyAIVecEnv(level, n, seeds=seeds), BabyAIVecEnv(level, n, seeds=seeds)
-    obs_h = torch.empty((n, 7, 7, 3), dtype=torch.uint8).pin_memory().numpy()
-    rew_h = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
-    done_h = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
-    dir_h = torch.empty(n, dtype=torch.int8).pin_memory().numpy()
-    o0 = dev.reset().cpu().numpy()
-    host.reset_host(obs_h, dir_h)
-    assert np.array_equal(o0, obs_h)
-    rng = np.random.RandomState(5)
-    for t in range(90):
-        a = rng.randint(0, 7, n).astype(np.int8)
-        o, r, d = dev.step(torch.as_tensor(a, device='cuda'))
-        host.step_host(a, obs_h, rew_h, done_h, dir_h)
-        assert np.array_equal(o.cpu().numpy(), obs_h), 'obs differ at step %d' % t
-        assert np.array_equal(r.cpu().numpy().view(np.uint32), rew_h.view(np.uint32)) and np.array_equal(d.cpu().numpy(), done_h)
-        assert np.array_equal(dev.direction.cpu().numpy(), dir_h)
-    assert dev.counters() == host.counters() and host.counters()['errors'] == 0 and host.counters()['episodes'] > n
-    dev.close(); host.close()
