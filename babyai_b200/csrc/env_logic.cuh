@@ -1825,12 +1825,12 @@ enum : int { V_CONT = 0, V_SUCC = 1, V_FAIL = 2 };
 // (one env each, all with different instructions) run ONE instruction stream (round 1's if-chain per kind, nested in the
 // side / root recursion, ran at 3.6 active lanes: ncu r02c).  Only PutNext's neighbourhood test is a loop, and it runs only
 // on the step where a matching object was just dropped.
-template <class M>
+template <int KM = 0, class M>                    // KM != 0: the family's kinds_mask as a compile-time constant (mem_spec)
 BB_HD int verify_action(M &mem, int leaf, const StepCtx &s)
 {
     const int kind = mem.leaf_kind(leaf);
     const uint32_t set = mem.desc_mask(2 * leaf);
-    const int km = mem.lp.kinds_mask;              // (kernel argument: the branches on it are uniform)
+    const int km = KM ? KM : mem.lp.kinds_mask;    // (kernel argument: the branches on it are uniform)
     const bool goto_ok = (set & s.snap_mask & s.at) != 0;                             // some pos in obj_poss is front_pos
     if (km == (1 << I_GOTO)) return goto_ok ? V_SUCC : V_CONT;                        // GoTo-only families (GoToLocal, GoToRedBall, GoTo, ...)
     const bool strict = ((mem.lp.strict_mask >> leaf) & 1) != 0;
@@ -1920,17 +1920,20 @@ BB_HD int verify_root(M &mem, const StepCtx &s)
 }
 
 // Compile-time specialisation of the stepping code by level family, carried by the accessor type: an accessor that declares
-// `static constexpr bool spec_goto_room = true` promises  num_rows == num_cols == 1, kinds_mask == GoTo only, single_instr,
-// no done-actions, no bonus family, no untracked objects  (GoToRedBall*, GoToObj*, GoToLocal*: BASELINE configs 1 and 2).
-// The generic code is the same with those tests as uniform run-time branches; the specialised instantiation is there for the
+// `static constexpr int spec_room_kinds = K` (K != 0) promises  num_rows == num_cols == 1, kinds_mask == K (one instruction
+// kind: GoTo or Pickup), single_instr, no strict / done-action mode, no bonus family, no untracked objects  -- GoToRedBall*,
+// GoToObj*, GoToLocal* (K = GoTo: BASELINE configs 1 and 2) and PickupLoc (K = Pickup: config 3).
+// The generic code is the same with those tests as uniform run-time branches; the specialised instantiations are there for the
 // INSTRUCTION FOOTPRINT of the persistent kernel's loop (k_rollout: 7 616 instructions against a 32 KB = 2 048-instruction
-// L1.5 instruction cache; `no_instruction` was 17 % of its issue-stall cycles, ncu r02c).
-template <class M, class = void> struct mem_spec { static constexpr bool goto_room = false; };
-template <class M> struct mem_spec<M, decltype((void)M::spec_goto_room)> { static constexpr bool goto_room = M::spec_goto_room; };
-BB_HD bool level_is_goto_room(const LevelParams &lp)
+// L1.5 instruction cache; `no_instruction` was 17 % of its issue-stall cycles, ncu r02c; 0.30 of 7.2 cycles after, r02k).
+template <class M, class = void> struct mem_spec { static constexpr int room_kinds = 0; };
+template <class M> struct mem_spec<M, decltype((void)M::spec_room_kinds)> { static constexpr int room_kinds = M::spec_room_kinds; };
+BB_HD int level_spec_room_kinds(const LevelParams &lp)          // the K of the instantiation a level qualifies for, or 0
 {
-    return lp.num_rows == 1 && lp.num_cols == 1 && lp.kinds_mask == (1 << I_GOTO) && lp.single_instr && !lp.done_actions &&
-           lp.bonus == 0 && lp.kind != KIND_UNLOCK && lp.kind != KIND_BONUS;
+    const bool plain = lp.num_rows == 1 && lp.num_cols == 1 && lp.single_instr && !lp.done_actions && lp.strict_mask == 0 &&
+                       lp.bonus == 0 && lp.kind != KIND_UNLOCK && lp.kind != KIND_BONUS;
+    if (!plain) return 0;
+    return lp.kinds_mask == (1 << I_GOTO) || lp.kinds_mask == (1 << I_PICKUP) ? lp.kinds_mask : 0;
 }
 
 struct StepResult { bool done; bool success; float reward; };      // done: success, failure (strict / done-action modes) or time-out
@@ -1941,7 +1944,7 @@ struct StepResult { bool done; bool success; float reward; };      // done: succ
 template <bool UNTR = false, class M>
 BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
 {
-    if (!mem_spec<M>::goto_room && h.step_count == 0 && mem.lp.bonus == BN_PUTNEXT) {
+    if (mem_spec<M>::room_kinds == 0 && h.step_count == 0 && mem.lp.bonus == BN_PUTNEXT) {
         // Level_PutNext*Carrying (bonus_levels.py:821-829): reset() returns the observation of the generated level, THEN takes
         // obj_a off the grid into the agent's hands -- so the first step acts on the modified state
         const int sc = mem.start_carry();
@@ -2025,9 +2028,9 @@ BB_HD StepResult step_env(EnvHot &h, M &mem, int action)
     s.action = action; s.fx = nfx; s.fy = nfy; s.carry = carry;
     s.cur_mask = h.cur_mask; s.snap_mask = h.snap_mask; s.at = at;
     int status;
-    if constexpr (mem_spec<M>::goto_room) {
+    if constexpr (mem_spec<M>::room_kinds != 0) {
         s.fcell = 0;
-        status = (mem.desc_mask(0) & s.snap_mask & s.at) != 0 ? V_SUCC : V_CONT;          // GoToInstr.verify_action of the one leaf
+        status = verify_action<mem_spec<M>::room_kinds>(mem, 0, s);        // the one leaf, its kind known at compile time
     } else {
         s.fcell = (mem.lp.kinds_mask & (1 << I_OPEN)) ? mem.cell(nfx, nfy) : 0;
         status = verify_root(mem, s);
@@ -2348,7 +2351,7 @@ BB_HD void observe_cells(const LevelParams &lp, const M &mem, int ax, int ay, in
 template <class M>
 BB_HD void observe(const LevelParams &lp, const M &mem, int ax, int ay, int dir, int carry_cell, uint32_t w[OBS_WORDS])
 {
-    if constexpr (mem_spec<M>::goto_room) { observe_room(lp, mem, ax, ay, dir, carry_cell, w); return; }
+    if constexpr (mem_spec<M>::room_kinds != 0) { observe_room(lp, mem, ax, ay, dir, carry_cell, w); return; }
     if (lp.num_rows == 1 && lp.num_cols == 1) observe_room(lp, mem, ax, ay, dir, carry_cell, w);
     else observe_generic(lp, mem, ax, ay, dir, carry_cell, w);
 }

@@ -397,12 +397,13 @@ struct SmemOnlyMem {            // lane-private records in shared memory (byte a
     __device__ __forceinline__ int start_carry() const { return i[43]; }
 };
 
-struct SmemGotoRoomMem : SmemOnlyMem {           // env_logic.cuh mem_spec: the GoTo-only single-room instantiation
-    static constexpr bool spec_goto_room = true;
-    __device__ __forceinline__ SmemGotoRoomMem(const LevelParams &lp_, uint8_t *g_, uint8_t *o_, uint8_t *i_) : SmemOnlyMem(lp_, g_, o_, i_) {}
+template <int K>
+struct SmemRoomKindMem : SmemOnlyMem {           // env_logic.cuh mem_spec: single-room levels with one instruction kind K
+    static constexpr int spec_room_kinds = K;
+    __device__ __forceinline__ SmemRoomKindMem(const LevelParams &lp_, uint8_t *g_, uint8_t *o_, uint8_t *i_) : SmemOnlyMem(lp_, g_, o_, i_) {}
 };
 
-template <int ACT_BYTES, bool UNTR = false, bool GOTO_ROOM = false>
+template <int ACT_BYTES, bool UNTR = false, int ROOM_KINDS = 0>
 __global__ void __launch_bounds__(R_THREADS_FUSED, 7)
 k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions_v, uint8_t *__restrict__ obs,
           float *__restrict__ reward, uint8_t *__restrict__ done, int8_t *__restrict__ dirs, const int n, const int T,
@@ -420,7 +421,7 @@ k_rollout(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actio
         return;
     }
     // stepping warps: rollout_lane.cuh (also compiled, with the warp primitives emulated by threads, in tests/hostemu)
-    rollout_lane_step_warp<PoolPtrs, typename std::conditional<GOTO_ROOM, SmemGotoRoomMem, SmemOnlyMem>::type, ACT_BYTES, UNTR>(lp, P, actions_v, obs, reward, done, dirs, n, T, mode, force_reset, fused,
+    rollout_lane_step_warp<PoolPtrs, typename std::conditional<ROOM_KINDS != 0, SmemRoomKindMem<ROOM_KINDS>, SmemOnlyMem>::type, ACT_BYTES, UNTR>(lp, P, actions_v, obs, reward, done, dirs, n, T, mode, force_reset, fused,
                                                                    smr + warp * warp_words, lane, blockIdx.x * R_WARPS + warp, s_done);
 }
 
@@ -620,7 +621,7 @@ struct bb_pool {
     int D, G, nev;
     bool gen_generic; int gen_fused; int gen_small_blocks, gen_budget, gen_min_active, refill_every; long long rollouts;   // BB_GEN_GENERIC=1: warp-per-level k_gen even for small levels
     bool no_persistent, after_rollout, gen_concurrent; int persist_max_cells;   // BB_NO_PERSISTENT=1: bb_pool_rollout always uses the per-step graph
-    bool goto_room;                // level_is_goto_room(lp): bb_pool_rollout uses the specialised k_rollout instantiation (BB_ROLLOUT_SPEC=0: never)
+    int room_kinds;                // level_spec_room_kinds(lp): bb_pool_rollout uses the specialised k_rollout instantiation (BB_ROLLOUT_SPEC=0: never)
     bool rollout_cta;              // bb_pool_rollout through k_rollout_cta (default on multi-room levels; BB_ROLLOUT_KERNEL=lane|cta)
     bool step_cols;                // BB_STEP_KERNEL=cols: k_step8 for every level (default: k_rollout with T = 1 on single-room grids)
     long long rel;
@@ -852,8 +853,8 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     p->rel = 0; p->gens_enqueued = 0; p->gen_outstanding = false;
     p->step_cols = false;
     p->rollout_cta = p->lp.num_rows * p->lp.num_cols > 1;
-    p->goto_room = level_is_goto_room(p->lp);
-    if (const char *e = getenv("BB_ROLLOUT_SPEC")) if (atoi(e) == 0) p->goto_room = false;
+    p->room_kinds = level_spec_room_kinds(p->lp);
+    if (const char *e = getenv("BB_ROLLOUT_SPEC")) if (atoi(e) == 0) p->room_kinds = 0;
     if (const char *e = getenv("BB_ROLLOUT_KERNEL")) p->rollout_cta = !strcmp(e, "cta");
     p->no_persistent = getenv("BB_NO_PERSISTENT") != nullptr; p->after_rollout = false;
     p->persist_max_cells = 1152;                           // k_rollout stages up to 22 x 22 grids (2 x 43 KB of shared memory per CTA)
@@ -889,8 +890,10 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     CUP(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUP(cudaFuncSetAttribute(k_rollout<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUP(cudaFuncSetAttribute(k_rollout<1, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_rollout<1, false, 1 << I_GOTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUP(cudaFuncSetAttribute(k_rollout<1, false, 1 << I_GOTO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUP(cudaFuncSetAttribute(k_rollout<1, false, 1 << I_PICKUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUP(cudaFuncSetAttribute(k_rollout<1, false, 1 << I_PICKUP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUP(cudaFuncSetAttribute(k_rollout_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUP(cudaFuncSetAttribute(k_rollout_cta<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1119,13 +1122,17 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
         if (p->lp.kind == KIND_UNLOCK) k_rollout_cta<true><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
         else k_rollout_cta<false><<<blocks_c, RC_THREADS, smc, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode);
     }
-    else if (fused && p->goto_room) k_rollout<1, false, true><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
-                                                                                       p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
-    else if (fused) k_rollout<1><<<blocks, R_THREADS_FUSED, smem + RG_AREA_WORDS * 4, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0,
-                                                                                       p->gen_budget > 0 ? p->gen_budget : 1 << 20, p->gen_min_active);
-    else if (p->lp.kind == KIND_UNLOCK) k_rollout<1, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
-    else if (p->goto_room) k_rollout<1, false, true><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
-    else k_rollout<1><<<blocks, R_THREADS, smem, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, 0, 0);
+    else {
+        const int gr = fused ? (p->gen_budget > 0 ? p->gen_budget : 1 << 20) : 0, gm = fused ? p->gen_min_active : 0;
+        const int threads = fused ? R_THREADS_FUSED : R_THREADS;
+        const size_t sm = fused ? smem + RG_AREA_WORDS * 4 : smem;
+#define BB_LAUNCH_ROLLOUT(...) k_rollout<__VA_ARGS__><<<blocks, threads, sm, user>>>(p->lp, p->P, actions_dev, obs_dev, reward_dev, done_dev, dir_dev, p->n, T, p->mode, 0, gr, gm)
+        if (p->lp.kind == KIND_UNLOCK) BB_LAUNCH_ROLLOUT(1, true);                         // (never fused: not a small level)
+        else if (p->room_kinds == (1 << I_GOTO)) BB_LAUNCH_ROLLOUT(1, false, 1 << I_GOTO);
+        else if (p->room_kinds == (1 << I_PICKUP)) BB_LAUNCH_ROLLOUT(1, false, 1 << I_PICKUP);
+        else BB_LAUNCH_ROLLOUT(1);
+#undef BB_LAUNCH_ROLLOUT
+    }
     if (dbg_timing) { cudaEventRecord(dbg_ev[1], user); p->tev_kernel = true; }
     p->launches++;
     if (refill && !gen_serial) {

@@ -142,9 +142,10 @@ struct HostSmemMem {
     int start_carry() const { return i[43]; }
 };
 
-struct HostSmemGotoRoomMem : HostSmemMem {                // the GoTo-only single-room instantiation (env_logic.cuh mem_spec), as pool.cu picks it
-    static constexpr bool spec_goto_room = true;
-    HostSmemGotoRoomMem(const LevelParams &lp_, uint8_t *g_, uint8_t *o_, uint8_t *i_) : HostSmemMem(lp_, g_, o_, i_) {}
+template <int K>
+struct HostSmemRoomKindMem : HostSmemMem {                // the single-instruction-kind single-room instantiations (env_logic.cuh mem_spec), as pool.cu picks them
+    static constexpr int spec_room_kinds = K;
+    HostSmemRoomKindMem(const LevelParams &lp_, uint8_t *g_, uint8_t *o_, uint8_t *i_) : HostSmemMem(lp_, g_, o_, i_) {}
 };
 
 struct HostPoolPtrs {                                     // the members of pool.cu's PoolPtrs the stepping role touches
@@ -239,7 +240,8 @@ void r2_rollout(RPool *p, const int8_t *actions, int T, uint8_t *obs, float *rew
             th.emplace_back([&, lane]() {
                 tl_warp = &ctx; tl_lane = lane;
                 if (lp.kind == KIND_UNLOCK) rollout_lane_step_warp<HostPoolPtrs, HostSmemMem, 1, true>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, false, base, lane, wg, nullptr);
-                else if (level_is_goto_room(lp)) rollout_lane_step_warp<HostPoolPtrs, HostSmemGotoRoomMem, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, false, base, lane, wg, nullptr);
+                else if (level_spec_room_kinds(lp) == (1 << I_GOTO)) rollout_lane_step_warp<HostPoolPtrs, HostSmemRoomKindMem<1 << I_GOTO>, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, false, base, lane, wg, nullptr);
+                else if (level_spec_room_kinds(lp) == (1 << I_PICKUP)) rollout_lane_step_warp<HostPoolPtrs, HostSmemRoomKindMem<1 << I_PICKUP>, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, false, base, lane, wg, nullptr);
                 else rollout_lane_step_warp<HostPoolPtrs, HostSmemMem, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, false, base, lane, wg, nullptr);
             });
         for (auto &t : th) t.join();
@@ -273,7 +275,9 @@ void r2_rollout_fused(RPool *p, const int8_t *actions, int T, int gen_rounds, in
                 const int lane = tid & 31, warp = tid >> 5;
                 tl_warp = &ctx[warp]; tl_lane = lane; tl_cta = &cta_bar;
                 if (warp == SW) rollout_gen_warp(lp, p->P, g_area, s_done, p->n, T, cta * cta_envs, gen_rounds, gen_min_active, lane, SW);
-                else if (level_is_goto_room(lp)) rollout_lane_step_warp<HostPoolPtrs, HostSmemGotoRoomMem, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, true,
+                else if (level_spec_room_kinds(lp) == (1 << I_GOTO)) rollout_lane_step_warp<HostPoolPtrs, HostSmemRoomKindMem<1 << I_GOTO>, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, true,
+                                                                                 smr + warp * warp_words, lane, cta * SW + warp, s_done);
+                else if (level_spec_room_kinds(lp) == (1 << I_PICKUP)) rollout_lane_step_warp<HostPoolPtrs, HostSmemRoomKindMem<1 << I_PICKUP>, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, true,
                                                                                  smr + warp * warp_words, lane, cta * SW + warp, s_done);
                 else rollout_lane_step_warp<HostPoolPtrs, HostSmemMem, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, T, p->mode, 0, true,
                                                                                  smr + warp * warp_words, lane, cta * SW + warp, s_done);
