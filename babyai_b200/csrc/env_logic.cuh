@@ -53,6 +53,14 @@
 #ifndef BB_GEN_OUTLINE
 #define BB_GEN_OUTLINE 1
 #endif
+// the generator's working memory is the warp's slice of the kernel's __shared__ array, but it reaches the out-of-line functions
+// as a generic pointer: without the hint every access is a generic LD.E / ST.E with 64-bit address arithmetic (three more
+// instructions than an LDS / STS, and a longer latency)
+#if defined(__CUDA_ARCH__) && BB_GEN_COOP
+#define BB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define BB_ASSUME_SHARED(p) ((void)0)
+#endif
 #if defined(__CUDACC__) && BB_GEN_COOP && BB_GEN_OUTLINE
 #define BB_GEN_FN __host__ __device__ __noinline__
 #else
@@ -662,6 +670,7 @@ BB_HD int g_check_reachable(const LevelParams &lp, GenCtx &g)
 struct MatchPose { int nobj, ax, ay, adir; };
 BB_GEN_FN uint32_t g_match_pose(const LevelParams &lp, const GenMem *gm, const MatchPose mp, int type, int color, int loc)
 {
+    BB_ASSUME_SHARED(gm);
     const int S = lp.room_size;
     const int rtx = (mp.ax / (S - 1)) * (S - 1), rty = (mp.ay / (S - 1)) * (S - 1);   // agent room top
     const int d1x = dir_dx(mp.adir), d1y = dir_dy(mp.adir), d2x = -d1y, d2y = d1x;
@@ -702,6 +711,10 @@ BB_HD uint32_t g_match(const LevelParams &lp, const GenCtx &g, const LevelOut &,
 struct RandObjRes { Rng rng; int status; };
 BB_GEN_FN RandObjRes g_rand_obj_v(const LevelParams &lp, GenMem *gm, Rng rng, const MatchPose mp, int locked_room, int ntypes, int d)
 {
+    BB_ASSUME_SHARED(gm);
+#if BB_GEN_WARP
+    BB_ASSUME_SHARED(rng.buf);
+#endif
     const int S = lp.room_size;
     RandObjRes res;
     int tries = 0;
@@ -1266,6 +1279,7 @@ BB_HD int g_mission(const LevelParams &lp, GenCtx &g, const LevelOut &o)
 // ---- mission tokens (Instr.surface / ObjDesc.surface, verifier.py:64-94 ...) --
 BB_GEN_FN int tok_desc(const GenMem *gm, int d, int16_t *tok, int n)
 {
+    BB_ASSUME_SHARED(gm); BB_ASSUME_SHARED(tok);
     // ('a' when several objects match.  find_matching_objs scans every grid cell, walls included: a description by colour
     // alone -- ObjDesc(None, 'grey'), Level_PickupDist -- also matches the grey walls, so it is always 'a grey object')
     const bool many = popc32(gm->desc_mask[d]) > 1 || (gm->desc_type[d] == ANY_TYPE && gm->desc_color[d] == C_GREY);
@@ -1311,6 +1325,7 @@ BB_HD uint32_t g_cells4(uint32_t bits)
 template <bool IMPUNLOCK>
 BB_HD_NOINLINE int generate_level_t(const LevelParams &lp, const LevelOut &o, RngRec *rngrec, uint8_t *locked_room_persist, GenMem *mem)
 {
+    BB_ASSUME_SHARED(mem);
     GenCtx g;
     g.m = mem;
 #if defined(__CUDACC__) && BB_GEN_COOP
