@@ -447,10 +447,15 @@ def main():
     others = None
     if rank == 0 and world == 1 and not args.no_other_configs and args.level == LEVEL and n == N_ENVS:
         others = {}
-        for key, lv, ne in (('C3 PickupLoc', 'PickupLoc', 65536), ('C4 GoTo', 'GoTo', 32768), ('C5 BossLevel (per-GPU share)', 'BossLevel', 32768)):
+        # steady state: a fresh pool starts all its episodes at once, so on the multi-room levels (episodes of 576 .. 4 608
+        # steps) hardly any level is consumed -- and generated -- during the first thousand steps: a 1 000-step run read 5.2e9 /
+        # 4.9e9 on GoTo / BossLevel where 200 000 steps give 4.5e9 / 4.4e9 (r02m vs r02r).  The warm-up runs past the longest
+        # time-out and the timed region covers several thousand episodes per env slot.
+        for key, lv, ne, ks, kw in (('C3 PickupLoc', 'PickupLoc', 65536, 4000, 400), ('C4 GoTo', 'GoTo', 32768, 40000, 6000),
+                                    ('C5 BossLevel (per-GPU share)', 'BossLevel', 32768, 40000, 6000)):
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--brief', '--level', lv, '--envs', str(ne),
-                                    '--steps', '1000', '--warmup', '80'], capture_output=True, text=True, timeout=150)
+                                    '--steps', str(ks), '--warmup', str(kw)], capture_output=True, text=True, timeout=150)
                 lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
                 others[key] = json.loads(lines[-1]) if lines else {'error': (r.stderr or 'no output')[-400:], 'returncode': r.returncode}
             except subprocess.TimeoutExpired:
