@@ -118,6 +118,7 @@ struct LevelParams {
     int32_t n_instr_kinds, instr_kinds[3];
     int32_t W, H, cells, cells_pad, max_tokens, nav_time_maze;
     int32_t strict_mask, done_actions;   // verifier modes (see verify_action / verify_leaf)
+    int32_t col_mul;                     // room / num_cols == (room * col_mul) >> 6 for every room of the level (make_level_params checks it)
     int32_t kinds_mask, single_instr;    // bit k: the family can produce an instruction leaf of kind k; 1: it only produces a single ActionInstr
     int32_t bonus, bonus_a, bonus_b;     // KIND_BONUS: which bonus_levels.py family and its constructor arguments
     int32_t box_contains;                // box object id + 1 whose contents is the NEXT table entry (Level_KeyInBox), else 0
@@ -258,7 +259,7 @@ struct Rng {
     __device__ __forceinline__ uint64_t count() const { return base + pos; }
     __device__ __forceinline__ uint32_t u32()
     {
-        if (pos >= 128u) { base += 128ull; pos = 0; fill(); }      // warp-uniform
+        if (__builtin_expect(pos >= 128u, 0)) { base += 128ull; pos = 0; fill(); }      // warp-uniform, one draw in 128
         return buf[pos++];
     }
     __device__ __forceinline__ int randint(int lo, int hi)
@@ -301,7 +302,9 @@ BB_HD int dir_dy(int d) { return d == 1 ? 1 : d == 3 ? -1 : 0; }
 // COLOR_NAMES = sorted(['red','green','blue','purple','yellow','grey'])
 BB_HD int color_by_name_rank(int k)   // blue green grey purple red yellow
 {
-    return k == 0 ? C_BLUE : k == 1 ? C_GREEN : k == 2 ? C_GREY : k == 3 ? C_PURPLE : k == 4 ? C_RED : C_YELLOW;
+    // one nibble per rank: C_BLUE, C_GREEN, C_GREY, C_PURPLE, C_RED, C_YELLOW
+    return (int)((((uint32_t)C_BLUE) | ((uint32_t)C_GREEN << 4) | ((uint32_t)C_GREY << 8) | ((uint32_t)C_PURPLE << 12) |
+                  ((uint32_t)C_RED << 16) | ((uint32_t)C_YELLOW << 20)) >> (4 * k)) & 7;
 }
 
 // =============================================================================
@@ -368,6 +371,11 @@ struct GenCtx {
 enum : int { GEN_OK = 0, GEN_REJECT = 1, GEN_RECURSION = 2 };
 #define BB_TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
+// room index -> (column, row) without an integer division (a dozen instructions each on the device; g_place alone was 6.6 % of
+// k_gen's instructions, ncu r02u)
+BB_HD int room_row(const LevelParams &lp, int room) { return (room * lp.col_mul) >> 6; }
+BB_HD int room_col(const LevelParams &lp, int room) { return room - room_row(lp, room) * lp.num_cols; }
+
 // RoomGrid._gen_grid (gym_minigrid.roomgrid; SURVEY App. A.6 / App. B "G0")
 BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
 {
@@ -406,7 +414,7 @@ BB_HD void g_roomgrid(const LevelParams &lp, GenCtx &g)
 BB_HD int g_place(const LevelParams &lp, GenCtx &g, int room, bool reject_next_to, int &ox, int &oy)
 {
     const int S = lp.room_size;
-    const int tx = (room % lp.num_cols) * (S - 1), ty = (room / lp.num_cols) * (S - 1);
+    const int tx = room_col(lp, room) * (S - 1), ty = room_row(lp, room) * (S - 1);
     const int hx = tx + S < lp.W ? tx + S : lp.W, hy = ty + S < lp.H ? ty + S : lp.H;
     int tries = 0;
     for (;;) {
@@ -445,7 +453,7 @@ BB_HD int g_add_object(const LevelParams &lp, GenCtx &g, const LevelOut &o, int 
 
 BB_HD bool g_has_slot(const LevelParams &lp, int room, int k)
 {
-    int i = room % lp.num_cols, j = room / lp.num_cols;
+    int i = room_col(lp, room), j = room_row(lp, room);
     return k == 0 ? i < lp.num_cols - 1 : k == 1 ? j < lp.num_rows - 1 : k == 2 ? i > 0 : j > 0;
 }
 BB_HD int g_neighbor(const LevelParams &lp, int room, int k)
@@ -466,8 +474,8 @@ BB_HD int g_add_door(const LevelParams &lp, GenCtx &g, const LevelOut &o, int ro
     const int S = lp.room_size;
     int owner = k == 2 ? room - 1 : k == 3 ? room - lp.num_cols : room;
     int x, y;
-    if (k == 0 || k == 2) { x = (owner % lp.num_cols) * (S - 1) + S - 1; y = g.m->door_y_right[owner]; g.door_right |= 1u << owner; }
-    else { x = g.m->door_x_down[owner]; y = (owner / lp.num_cols) * (S - 1) + S - 1; g.door_down |= 1u << owner; }
+    if (k == 0 || k == 2) { x = room_col(lp, owner) * (S - 1) + S - 1; y = g.m->door_y_right[owner]; g.door_right |= 1u << owner; }
+    else { x = g.m->door_x_down[owner]; y = room_row(lp, owner) * (S - 1) + S - 1; g.door_down |= 1u << owner; }
     if (locked) g.room_locked |= 1u << room; else g.room_locked &= ~(1u << room);   // room.locked = locked
     int id = g.nobj++;
     if (k == 0 || k == 2) g.m->door_id_right[owner] = (uint8_t)id; else g.m->door_id_down[owner] = (uint8_t)id;
@@ -491,7 +499,7 @@ BB_HD int g_place_agent(const LevelParams &lp, GenCtx &g, int room_given = -1)
         // doors: MiniBossLevel seed 698, 57th level).  The reference hangs; here the level is rejected like any
         // other failed rejection sampling and generation starts over.  Levels the reference CAN generate are unaffected.
         const int S = lp.room_size;
-        const int tx = (room % lp.num_cols) * (S - 1), ty = (room / lp.num_cols) * (S - 1);
+        const int tx = room_col(lp, room) * (S - 1), ty = room_row(lp, room) * (S - 1);
         const uint32_t rmask = ((1u << (S - 2)) - 1u) << (tx + 1);
         bool any = false;
         for (int y = ty + 1; y < ty + S - 1; y++) {

@@ -39,6 +39,9 @@ static inline const char *make_level_params(const bb_level_spec *s, LevelParams 
     lp->n_action_kinds = s->n_action_kinds; lp->n_instr_kinds = s->n_instr_kinds;
     for (int i = 0; i < 4; i++) lp->action_kinds[i] = s->action_kinds[i];
     for (int i = 0; i < 3; i++) lp->instr_kinds[i] = s->instr_kinds[i];
+    lp->col_mul = s->num_cols > 0 ? (64 + s->num_cols - 1) / s->num_cols : 64;
+    for (int r = 0; r < s->num_rows * s->num_cols; r++)
+        if (s->num_cols <= 0 || ((r * lp->col_mul) >> 6) != r / s->num_cols) return "unsupported room grid (room / num_cols by multiplication)";
     lp->W = (s->room_size - 1) * s->num_cols + 1;
     lp->H = (s->room_size - 1) * s->num_rows + 1;
     if (lp->W > MAXH || lp->H > MAXH) return "grid too large";
