@@ -237,22 +237,24 @@ static __device__ __noinline__ uint4 philox_block_ool(uint32_t k0, uint32_t k1, 
 // one broadcast shared-memory load.  (Round 1 kept the four words of a lane's block in registers and shuffled: a 64-bit
 // counter, three selects and a shuffle per draw, ~25 instructions at each of ~600 call sites.)
 // the cold path of a draw, one copy, arguments by value (the Rng itself stays in registers)
-static __device__ __noinline__ void rng_fill_ool(uint32_t k0, uint32_t k1, uint64_t base, uint32_t *buf)
+static __device__ __noinline__ void rng_fill_ool(uint32_t k0, uint32_t k1, uint64_t base, uint32_t sbuf)
 {
     __syncwarp();
     const uint4 b = philox_block_ool(k0, k1, (base >> 2) + (threadIdx.x & 31));
-    reinterpret_cast<uint4 *>(buf)[threadIdx.x & 31] = b;
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + 16u * (threadIdx.x & 31)), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
     __syncwarp();
 }
 struct Rng {
     uint32_t k0, k1;
     uint64_t base;                // draw index of buf[0], a multiple of 4
     uint32_t pos;                 // draws consumed from buf; 128 = used up
-    uint32_t *buf;                // GenMem::draw_buf
-    __device__ __forceinline__ void fill() { rng_fill_ool(k0, k1, base, buf); }
+    uint32_t sbuf;                // GenMem::draw_buf as a SHARED-space address: the draw is an explicit ld.shared (a generic
+                                  // pointer that has passed through an out-of-line call loses its address space: LD.E + 64-bit
+                                  // address arithmetic at the hottest 13 M loads of a pass, ncu r02w)
+    __device__ __forceinline__ void fill() { rng_fill_ool(k0, k1, base, sbuf); }
     __device__ __forceinline__ void init(uint64_t seed, uint64_t d, uint32_t *b)
     {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); buf = b;
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); sbuf = (uint32_t)__cvta_generic_to_shared(b);
         base = d & ~3ull; pos = (uint32_t)d & 3u;
         fill();
     }
@@ -260,7 +262,10 @@ struct Rng {
     __device__ __forceinline__ uint32_t u32()
     {
         if (__builtin_expect(pos >= 128u, 0)) { base += 128ull; pos = 0; fill(); }      // warp-uniform, one draw in 128
-        return buf[pos++];
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbuf + 4u * pos));
+        pos++;
+        return v;
     }
     __device__ __forceinline__ int randint(int lo, int hi)
     {
@@ -720,9 +725,6 @@ struct RandObjRes { Rng rng; int status; };
 BB_GEN_FN RandObjRes g_rand_obj_v(const LevelParams &lp, GenMem *gm, Rng rng, const MatchPose mp, int locked_room, int ntypes, int d)
 {
     BB_ASSUME_SHARED(gm);
-#if BB_GEN_WARP
-    BB_ASSUME_SHARED(rng.buf);
-#endif
     const int S = lp.room_size;
     RandObjRes res;
     int tries = 0;
