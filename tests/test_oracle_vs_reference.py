@@ -17,6 +17,27 @@ def test_random_policy(level):
         compare_ref.compare(level, 4000 + s, 150, 'random', act_seed=s)
 
 
+def _iclr_levels():
+    from babyai_b200.levels import ICLR19_LEVELS
+    return sorted(ICLR19_LEVELS)
+
+
+@pytest.mark.parametrize('level', _iclr_levels())
+def test_random_policy_every_iclr_level(level):
+    """every served ICLR-19 level, 3 seeds x 300 random steps (several episodes on the single-room levels, resets included):
+    the CI-length slice of oracle/soak_ref.py (profiles/r02_soak_ref.log has the long run)"""
+    import compare_ref
+    for s in range(3):
+        compare_ref.compare(level, 7100 + 17 * s, 300, 'random', act_seed=10 + s)
+
+
+@pytest.mark.parametrize('level', _iclr_levels())
+def test_bot_policy_every_iclr_level(level):
+    """... and the reference bot driving both sides (the success / reward path of every instruction kind)"""
+    import compare_ref
+    compare_ref.compare(level, 7300, 200, 'bot', act_seed=3)
+
+
 @pytest.mark.parametrize('level', ['GoToLocal', 'PickupLoc', 'BossLevel', 'SynthSeq', 'GoToImpUnlock', 'Unlock'])
 def test_bot_policy(level):
     import compare_ref
