@@ -137,7 +137,7 @@ __device__ __forceinline__ void swap_in8(const LevelParams &lp, const PoolPtrs &
 }
 
 // UNTR: KIND_UNLOCK pools (objects without a table entry, env_logic.cuh CARRY_UNTRACKED); every other level runs the
-// UNTR = false instantiations, whose code is the one profiled in round 1
+// UNTR = false instantiations
 template <int ACT_BYTES, bool UNTR = false>
 __global__ void __launch_bounds__(S8_THREADS)
 k_step8(const LevelParams lp, const PoolPtrs P, const void *__restrict__ actions, uint8_t *__restrict__ obs,
@@ -440,13 +440,14 @@ k_rollout_cta(const LevelParams lp, const PoolPtrs P, const int8_t *__restrict__
 // ONE WARP PER ENVIRONMENT.  Generation is a long, branchy, data-dependent rejection-sampling program;
 // with one lane per env the 32 lanes of a warp run 32 different paths serially (measured in round 1:
 // 3.0 active lanes per instruction).  Instead every lane of the warp runs the same env with identical
-// control flow: no divergence, the Philox blocks are computed 32 at a time across the lanes (Rng::u32),
-// the lanes split the grid rendering, and lane 0 commits the scalar records.
+// control flow: no divergence, the Philox blocks are computed 32 at a time across the lanes into a shared-memory buffer of 128
+// draws (struct Rng), the lanes split the grid rendering, object matching and row initialisation, and lane 0 commits the
+// scalar records.  DESIGN.md 4.4 has the list of what round 2 did to this kernel and the measurements.
 // Work distribution: k_gen_scan lists the envs whose ring is not full, longest chains first; a warp takes ONE env per
 // ticket from a global counter (the slowest generations are a geometric tail of rejected attempts, so static
 // assignment would wait for them).
-// IMPUNLOCK: the instantiation that serves KIND_IMPUNLOCK only (Level_GoToImpUnlock); every other level family runs
-// k_gen<false>, whose code is the kernel profiled in round 1.
+// IMPUNLOCK: the instantiation that serves GoToImpUnlock, Unlock and the bonus families (implicit-unlock placement, untracked
+// objects, the bonus_levels.py generators); every other level runs k_gen<false>.
 #if BB_GEN_COOP
 template <bool IMPUNLOCK>
 __global__ void __launch_bounds__(GEN_THREADS)
@@ -831,7 +832,7 @@ int bb_pool_create(const bb_level_spec *spec, int32_t n_envs, int32_t device, bb
     // ring depth: short single-room episodes (max_steps 64..128) end often and level generation has a long
     // rejection tail, so they get a deep ring; multi-room episodes last hundreds of steps
     // >= 3 x the 40-step rollout of bb_pool_rollout (one refill pass per two launches); for the per-step API one
-    // generation pass per 32 steps (many levels per pass: a multi-room level is ~0.2-0.4 ms of serial work)
+    // generation pass per 32 steps (many levels per pass: a multi-room level is ~20-40 us of serial work for one warp)
     // multi-room levels (generation passes run BESIDE the rollouts on a side stream): twice the depth, so that one pass may
     // overlap several launches (bb_pool_rollout: a pass is joined D / 2T launches after it was forked)
     p->D = 128;
@@ -1099,8 +1100,9 @@ int bb_pool_rollout(bb_pool *p, const int8_t *actions_dev, int32_t T, uint8_t *o
     // Small levels: refill in-stream, right before the stepping kernel, with a bounded iteration budget.  Measured
     // (r01l): running k_gen_small on the side stream BESIDE k_rollout does not pay -- alone they take 263 us and
     // ~210 us, together 460-490 us and 580 us (both are issue/latency bound on the same SMs).  Multi-room levels:
-    // k_gen (one warp per level, a few hundred levels per pass, each 0.2-0.4 ms of serial work) runs on the side
-    // stream beside k_rollout (BossLevel 1.48e9 -> 1.71e9, GoTo 1.34e9 -> 1.43e9).  BB_GEN_CONCURRENT=0/1 overrides.
+    // k_gen (one warp per level, thousands of levels per pass) runs on the side stream beside k_rollout_cta, forked every R-th
+    // launch and joined R launches later (see the top of this function; r02j: BossLevel 4.1e9 in-stream, 4.5e9 beside).
+    // BB_GEN_CONCURRENT=0/1 overrides.
     const bool gen_serial = !p->gen_concurrent;
     if (refill && gen_serial) {
         if (dbg_timing) cudaEventRecord(dbg_ev[2], user);
