@@ -10,6 +10,16 @@
 #define BB_DEV __device__ __forceinline__
 #define BB_SYNCWARP() __syncwarp()
 #define BB_SYNCTHREADS() __syncthreads()
+#define BB_SYNCWARP_MASK(m) __syncwarp(m)
+// asynchronous 16-byte copy global -> shared (cp.async.cg: L2 only), and "all my copies have landed"
+static __device__ __forceinline__ void bb_cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+static __device__ __forceinline__ void bb_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+#define BB_CP_ASYNC16(dst, src) bb_cp_async16((dst), (src))
+#define BB_CP_ASYNC_WAIT_ALL() bb_cp_async_wait_all()
 #define BB_SHFL(v, src) __shfl_sync(0xFFFFFFFFu, (v), (src))
 #define BB_SHFL_XOR(v, m) __shfl_xor_sync(0xFFFFFFFFu, (v), (m))
 #define BB_SHFL_DOWN(v, d) __shfl_down_sync(0xFFFFFFFFu, (v), (d))

@@ -105,7 +105,7 @@ class HostEmuPool:
 # ---- the rollout kernels' roles on OS threads (simt_rollout.cpp) -------------------------------------------------
 SRC2 = os.path.join(HERE, 'simt_rollout.cpp')
 OUT2 = os.path.join(HERE, 'libsimt_rollout.so')
-DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'simt.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_lane.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_cta.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'gen_round.cuh')] + DEPS[1:]
+DEPS2 = [SRC2, os.path.join(ROOT, 'babyai_b200', 'csrc', 'simt.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_lane.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'rollout_cta.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'step8.cuh'), os.path.join(ROOT, 'babyai_b200', 'csrc', 'gen_round.cuh')] + DEPS[1:]
 _lib2 = None
 
 
@@ -126,6 +126,7 @@ def lib2():
         L.r2_max_tokens.argtypes = [C.c_void_p]
         L.r2_error_flag.argtypes = [C.c_void_p]
         L.r2_rollout_cta.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.r2_step8.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
         L.r2_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib2 = L
     return _lib2
@@ -158,6 +159,15 @@ class RolloutPool:
             self.L.r2_rollout_fused(self.h, _p(a), T, gen_rounds, gen_min_active, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
         else:
             self.L.r2_rollout(self.h, _p(a), T, _p(obs), _p(rew), _p(done), _p(dirs), _p(cnt))
+        return obs, rew, done, dirs, cnt
+
+    def step8(self, actions, force_reset=0):
+        """one bb_pool_step through k_step8's role function (step8.cuh), 128 OS threads per CTA"""
+        a = np.ascontiguousarray(actions, dtype=np.int8)
+        n = a.shape[0]
+        obs, rew = np.zeros((n, 7, 7, 3), np.uint8), np.zeros(n, np.float32)
+        done, dirs, cnt = np.zeros(n, np.uint8), np.zeros(n, np.int8), np.zeros(4, np.int64)
+        self.L.r2_step8(self.h, _p(a), _p(obs), _p(rew), _p(done), _p(dirs), force_reset, _p(cnt))
         return obs, rew, done, dirs, cnt
 
     def state(self, i, width, height):

@@ -25,6 +25,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 // ---- the warp primitives of simt.cuh, emulated ---------------------------------------------------------------
 struct WarpCtx {
     std::barrier<> bar{32};
+    std::barrier<> grp0{8}, grp1{8}, grp2{8}, grp3{8};       // __syncwarp(mask) of k_step8's 8-lane groups
     uint32_t xchg[32];
 };
 static thread_local WarpCtx *tl_warp = nullptr;
@@ -53,6 +54,11 @@ static inline void emu_bar_sync(int id, int n)
 static thread_local int *tl_cta_or = nullptr;               // two alternating accumulators of __syncthreads_or
 static thread_local int tl_cta_phase = 0;
 static inline void emu_syncwarp() { tl_warp->bar.arrive_and_wait(); }
+static inline void emu_syncwarp_mask(unsigned mask)         // the 8 lanes of one group (mask = 0xFF << 8 g)
+{
+    const int g = __builtin_ctz(mask) >> 3;
+    (g == 0 ? tl_warp->grp0 : g == 1 ? tl_warp->grp1 : g == 2 ? tl_warp->grp2 : tl_warp->grp3).arrive_and_wait();
+}
 static inline int emu_syncthreads_or(int pred)
 {
     int *acc = tl_cta_or + (tl_cta_phase & 1);
@@ -88,6 +94,9 @@ template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exch
 #define BB_DEV inline
 #define BB_SYNCWARP() emu_syncwarp()
 #define BB_SYNCTHREADS() tl_cta->arrive_and_wait()
+#define BB_SYNCWARP_MASK(m) emu_syncwarp_mask(m)
+#define BB_CP_ASYNC16(dst, src) memcpy((dst), (src), 16)      /* cp.async: a plain copy here; the wait is a no-op */
+#define BB_CP_ASYNC_WAIT_ALL() ((void)0)
 #define BB_ANY(x) (emu_ballot(x) != 0u)
 #define BB_BALLOT(x) emu_ballot(x)
 #define BB_POPC(x) __builtin_popcount(x)
@@ -112,6 +121,7 @@ template <class T> static inline T emu_shfl_xor(T v, int m) { return (T)emu_exch
 #include "../../babyai_b200/csrc/gen_round.cuh"
 #include "../../babyai_b200/csrc/rollout_lane.cuh"
 #include "../../babyai_b200/csrc/rollout_cta.cuh"
+#include "../../babyai_b200/csrc/step8.cuh"
 #include "../../babyai_b200/csrc/level_params.h"
 
 using namespace bb;
@@ -201,7 +211,7 @@ RPool *r2_create(const bb_level_spec *spec, int n, int depth, const uint64_t *se
     p->tok.assign(N * lp.max_tokens, 0); p->rtok.assign(DN * lp.max_tokens, 0);
     p->head.assign(N, 0); p->tail.assign(N, 0); p->tail_pub.assign(N, 0);
     p->rng.resize(N); p->last_reward.assign(N, 0.f); p->locked_room.assign(N, 0xFF); p->attempts.assign(N, 0);
-    p->counters.assign(4 * (N / 8 + 2), 0); p->err = 0;
+    p->counters.assign(4 * (N / 4 + 8), 0); p->err = 0;
     for (int e = 0; e < n; e++) { p->rng[e].seed = seeds[e]; p->rng[e].draws = 0; }
     HostPoolPtrs &P = p->P;
     P.grid = p->grid.data(); P.hot = p->hot.data(); P.obj = p->obj.data(); P.ins = p->ins.data(); P.tok = p->tok.data();
@@ -313,6 +323,32 @@ void r2_rollout_cta(RPool *p, const int8_t *actions, int T, uint8_t *obs, float 
         for (auto &t : th) t.join();
     }
     refill(p);                                                // the generation pass between launches
+    for (int k = 0; k < 4; k++) counters4[k] = 0;
+    for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
+}
+
+// one bb_pool_step worth of k_step8: every CTA of the grid, 128 threads each (4 warps of four 8-lane groups; shuffles, ballots and
+// the sub-warp __syncwarp(mask) as rendezvous), then the generation pass the pool's scheduler would have run by now
+void r2_step8(RPool *p, const int8_t *actions, uint8_t *obs, float *reward, uint8_t *done, int8_t *dirs, int force_reset, int64_t *counters4)
+{
+    const LevelParams &lp = p->lp;
+    const size_t sm8 = (size_t)S8_WARPS * 4 * (lp.cells_pad + S8_REC_FIXED) + (size_t)S8_WARPS * (S8_TILE_WORDS + 1) * 4;
+    const int nctas = (p->n + 4 * S8_WARPS - 1) / (4 * S8_WARPS);
+    for (int cta = 0; cta < nctas; cta++) {
+        std::vector<WarpCtx> ctx(S8_WARPS);
+        std::vector<uint8_t> smem(sm8 + 32, 0xEE);
+        uint8_t *base = smem.data();
+        while (((uintptr_t)base) & 15) base++;
+        std::vector<std::thread> th;
+        for (int tid = 0; tid < S8_THREADS; tid++)
+            th.emplace_back([&, tid]() {
+                tl_warp = &ctx[tid >> 5]; tl_lane = tid & 31;
+                if (lp.kind == KIND_UNLOCK) step8_role<HostPoolPtrs, 1, true>(lp, p->P, actions, obs, reward, done, dirs, p->n, p->mode, force_reset, base, tid & 31, tid >> 5, (unsigned)cta);
+                else step8_role<HostPoolPtrs, 1, false>(lp, p->P, actions, obs, reward, done, dirs, p->n, p->mode, force_reset, base, tid & 31, tid >> 5, (unsigned)cta);
+            });
+        for (auto &t : th) t.join();
+    }
+    refill(p);
     for (int k = 0; k < 4; k++) counters4[k] = 0;
     for (size_t w = 0; w < p->counters.size() / 4; w++) for (int k = 0; k < 4; k++) counters4[k] += (int64_t)p->counters[4 * w + k];
 }
