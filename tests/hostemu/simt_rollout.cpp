@@ -364,7 +364,8 @@ void r2_state(RPool *p, int e, uint8_t *grid, int32_t *info)
             if (g[lp.gt_off + x * lp.rs_t + y] != g[y * lp.rs_g + x]) { fprintf(stderr, "simt_rollout: G/GT mismatch env %d (%d,%d)\n", e, x, y); abort(); }
         }
     const EnvHot &h = p->hot[e];
-    info[0] = h.x; info[1] = h.y; info[2] = h.dirflags & 3; info[3] = h.carry; info[4] = h.step_count; info[5] = h.max_steps;
+    info[0] = h.x; info[1] = h.y; info[2] = h.dirflags & 3; info[3] = h.carry == NO_OBJ ? 0 : (lp.kind == KIND_UNLOCK && (h.carry & CARRY_UNTRACKED)) ? (h.carry & 0x3F) : p->obj[e].tc[h.carry];   // the carried object's cell byte, as hostemu.cpp reports it
+    info[4] = h.step_count; info[5] = h.max_steps;
 }
 
 int r2_min_ring_level(RPool *p) { int m = 1 << 30; for (int e = 0; e < p->n; e++) { const int have = (int)(p->tail[e] - p->head[e]); if (have < m) m = have; } return m; }
